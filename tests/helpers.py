@@ -1,0 +1,86 @@
+"""Shared test helpers: golden-case loading and output comparison."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+from gci_b200.records import AlnTable, PafTable
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+_ALN_COLS = ("ref_id", "ref_start", "mapq", "flag", "nm", "qlen", "read_id", "cigar_off", "cigar")
+_PAF_COLS = ("read_id", "qlen", "qstart", "qend", "ref_id", "tstart", "tend", "nmatch", "alnlen", "mapq")
+
+_cache = {}
+
+
+def golden_store():
+    if "store" not in _cache:
+        _cache["store"] = np.load(os.path.join(GOLDEN, "filter_cases.npz"))
+        with open(os.path.join(GOLDEN, "filter_cases.json")) as f:
+            _cache["meta"] = json.load(f)
+    return _cache["store"], _cache["meta"]
+
+
+def case_names():
+    _, meta = golden_store()
+    return [c["name"] for c in meta["cases"]]
+
+
+def load_case(name):
+    """-> (case meta, kwargs for run_gci-style drivers, expected outputs)."""
+    store, meta = golden_store()
+    case = next(c for c in meta["cases"] if c["name"] == name)
+    kw = dict(names=case["names"], lengths=case["lengths"], n_runs=[[tuple(iv) for iv in r] for r in case["n_runs"]],
+              chrs=case["chrs"], regions=[tuple(r) for r in case["regions"]] if case["regions"] else None,
+              prefix="T")
+    kw.update(case["args"])
+    for rtype in ("hifi", "nano"):
+        tabs = None
+        if rtype in case["files"]:
+            tabs = []
+            for f in case["files"][rtype]:
+                if f["kind"] == "bam":
+                    tabs.append(AlnTable(*[store[f"{f['key']}.{c}"] for c in _ALN_COLS]))
+                else:
+                    tabs.append(PafTable(*[store[f"{f['key']}.{c}"] for c in _PAF_COLS]))
+        kw[rtype] = tabs
+    expected = {}
+    for fn, o in case["outputs"].items():
+        if "text" in o:
+            expected[fn] = o["text"]
+        else:
+            expected[fn] = {cn: store[f"{name}.out.{fn}.{cn}"] for cn in o["contigs"]}
+    return case, kw, expected
+
+
+def assert_outputs_equal(got: dict, expected: dict):
+    assert sorted(got) == sorted(expected), (sorted(got), sorted(expected))
+    for fn, exp in expected.items():
+        g = got[fn]
+        if isinstance(exp, dict):
+            assert list(g.keys()) == list(exp.keys()), fn
+            for cn in exp:
+                a, b = np.asarray(g[cn]).astype(np.int64), np.asarray(exp[cn]).astype(np.int64)
+                assert a.shape == b.shape, (fn, cn, a.shape, b.shape)
+                if not np.array_equal(a, b):
+                    bad = np.flatnonzero(a != b)
+                    raise AssertionError(f"{fn}:{cn} depth differs at {len(bad)} positions, first {bad[:5]} "
+                                         f"got {a[bad[:5]]} want {b[bad[:5]]}")
+        else:
+            assert g == exp, f"{fn} differs:\n--- got\n{g[:2000]}\n--- want\n{exp[:2000]}"
+
+
+def mh63_depths():
+    z = np.load(os.path.join(GOLDEN, "mh63_depth_rle.npz"))
+    names = [str(n) for n in z["names"]]
+    counts = z["run_counts"]
+    off = np.concatenate([[0], np.cumsum(counts)])
+    depths = []
+    for i in range(len(names)):
+        v = z["values"][off[i]:off[i + 1]]
+        r = z["run_lengths"][off[i]:off[i + 1]]
+        depths.append(np.repeat(v, r).astype(np.int32))
+    return names, [int(x) for x in z["lengths"]], depths
