@@ -1,0 +1,208 @@
+// Shared host-side state and small device helpers of libgci_cuda.so (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gci_cuda.h"
+
+// ---- geometry --------------------------------------------------------------------------------
+// The reference axis is cut into tiles of GCI_TILE positions; a tile never straddles two contigs
+// and every contig owns floor(L / TILE) + 1 tiles, so at least one padded position follows the
+// last base (the "-1" event of a read ending at L and the end of a run touching L - fl land there).
+constexpr int GCI_TILE = 8192;            // positions per depth tile (32 KB of int32)
+constexpr int GCI_TILE_THREADS = 256;
+constexpr int GCI_RUN_CHUNK_WORDS = 2048; // flag words (of 32 positions) per run-extraction chunk
+
+#define GCI_CUDA_TRY(ctx, expr)                                                              \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      (ctx)->fail(GCI_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),       \
+                  __FILE__, __LINE__);                                                       \
+      return GCI_E_CUDA;                                                                     \
+    }                                                                                        \
+  } while (0)
+
+#define GCI_TRY(expr)            \
+  do {                           \
+    int r__ = (expr);            \
+    if (r__ != GCI_OK) return r__; \
+  } while (0)
+
+struct gci_ctx;
+
+// growth-only device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct BamFile {
+  int64_t n = 0, n_ops = 0;
+  DevBuf ref_id, ref_start, mapq, flag, nm, qlen, read_id, cigar_off, cigar;
+  DevBuf stats;    // uint32[n][8]: Mx(M+=+X), I, D, N, S, pad..   (K1 output)
+  DevBuf ref_end;  // int32[n]                                      (K2 output)
+};
+
+// PAF lines stay on the host: the per-read primary-target election (GCI.py:241-254) is a
+// host stage in this round (SURVEY.md §8a-3 "host C++ first"); its result is uploaded as a table.
+struct PafFile {
+  int64_t n = 0;
+  std::vector<uint32_t> read_id;
+  std::vector<int32_t> qlen, qstart, qend, ref_id, tstart, tend, nmatch, alnlen, mapq;
+};
+
+// one file after its per-file leg: at most one entry per read
+struct FileTable {
+  int kind = 0;            // 0 = BAM (entries are records of bam[src]), 1 = table (own columns)
+  int src = -1;
+  int64_t n = 0;
+  DevBuf ref_id, start, end, qlen;   // for kind==1; for BAM these alias the BamFile columns
+  DevBuf win;              // int64[n_reads]: winning entry key per read (-1 = absent)
+};
+
+struct Track {
+  bool allocated = false;
+  DevBuf depth;            // int32[total_padded]
+  DevBuf flags;            // uint32[total_padded / 32]   bit = (lo < depth <= hi)
+  bool flags_valid = false;
+  int32_t flags_lo = 0, flags_hi = 0;
+  DevBuf sums;             // int64[n_contigs]  sum of depth per contig
+  // last scan
+  int64_t n_intervals = 0, n_owners = 0;
+  bool owners_are_windows = false;
+  DevBuf iv_start, iv_end; // int32[n_intervals]
+  DevBuf owner_off;        // int64[n_owners + 1]
+  DevBuf win_contig, win_lo, win_hi;   // int32 / int64 / int64 [n_owners]: scan windows
+  std::vector<int64_t> raw_lo, raw_hi; // windows as given by the caller (before slice normalisation)
+};
+
+struct StageTimer {
+  std::vector<cudaEvent_t> pool;
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  size_t next = 0;
+};
+
+struct gci_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int64_t dev_bytes = 0;
+  int sm_count = 148;
+
+  // contigs
+  int32_t n_contigs = 0;
+  std::vector<int64_t> len;         // host copies
+  std::vector<uint8_t> selected;
+  std::vector<int64_t> tile_off;    // [n+1] first tile of each contig
+  std::vector<int64_t> pos_off;     // [n+1] = tile_off * TILE
+  int64_t n_tiles = 0, total_padded = 0;
+  DevBuf d_len, d_selected, d_tile_off;
+
+  // N runs (sorted by (contig,start) on upload)
+  int64_t n_nruns = 0;
+  DevBuf d_nr_contig, d_nr_start, d_nr_end;   // int32, int64, int64
+
+  // read set
+  uint32_t n_reads = 0;
+  std::vector<BamFile> bam;
+  std::vector<PafFile> paf;
+  std::vector<FileTable> files;     // join order
+  DevBuf highq;                     // uint8[n_reads]
+  DevBuf surv_contig, surv_start, surv_end;   // int32[n_reads]; contig < 0 = not a survivor
+  bool filtered = false;
+  int64_t n_survivors = 0;
+  std::vector<int32_t> name_rank;   // host copy for the PAF election tie-break
+
+  // depth scratch
+  DevBuf tile_cnt, tile_net, tile_evoff, tile_base, events, scan_tmp, scan_tmp2, misc, d_err;
+  DevBuf chunk_cnt, chunk_off;
+  DevBuf scan_lvl[8];               // block sums / offsets of the recursive scan, two per level
+  DevBuf tmp[10];                   // small per-call scratch (score terms, fetches)
+  Track track[GCI_MAX_TRACKS];
+
+  StageTimer timer;
+  void* pinned_scratch = nullptr;
+  size_t pinned_cap = 0;
+
+  int fail(int code, const char* fmt, ...);
+  int ensure(DevBuf& b, size_t bytes);            // grow-only
+  void release(DevBuf& b);
+  void* pinned(size_t bytes);
+  void stage_begin(int stage);
+  void stage_end();
+};
+
+// ---- host helpers implemented in api.cu ---------------------------------------------------------
+int gci_h2d(gci_ctx* ctx, DevBuf& dst, const void* src, size_t bytes);
+int gci_d2h(gci_ctx* ctx, void* dst, const void* src, size_t bytes);
+
+// device-wide exclusive scans (scan.cu)
+int gci_exclusive_scan_i64_from_i32(gci_ctx* ctx, const int32_t* in, int64_t* out, int64_t n, int64_t* total_dev);
+int gci_exclusive_scan_i32(gci_ctx* ctx, const int32_t* in, int32_t* out, int64_t n);
+
+// stage entry points
+int gci_run_bam_leg(gci_ctx* ctx, int file_idx, int bam_idx, int32_t mq, int32_t mq_cutoff, double ip, double cp);
+int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip);
+int gci_run_join(gci_ctx* ctx, double op);
+int gci_alloc_track(gci_ctx* ctx, int track);
+int gci_compute_flags(gci_ctx* ctx, int track, int32_t lo, int32_t hi);
+
+#define GCI_LAUNCH_CHECK(ctx)                      \
+  do {                                             \
+    (ctx)->launches++;                             \
+    GCI_CUDA_TRY(ctx, cudaGetLastError());         \
+  } while (0)
+
+// ---- device helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += t;
+  }
+  return v;
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// last index i in [0, n) with a[i] <= key  (a ascending, a[0] <= key assumed)
+template <typename T>
+__device__ __forceinline__ int64_t upper_bound_minus1(const T* __restrict__ a, int64_t n, T key) {
+  int64_t lo = 0, hi = n;   // invariant: a[lo] <= key, a[hi] > key (virtual)
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (a[mid] <= key) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// Python slice index normalisation (PySlice_AdjustIndices, step 1)
+__device__ __forceinline__ long long py_slice_index(long long i, long long len) {
+  if (i < 0) {
+    i += len;
+    if (i < 0) i = 0;
+  } else if (i >= len) {
+    i = len;
+  }
+  return i;
+}

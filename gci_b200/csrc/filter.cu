@@ -1,0 +1,775 @@
+// Filter stage: CIGAR statistics, per-record gates, last-record-wins dedup, PAF election,
+// cross-file same-read join.  Reference: GCI.py:146-169 (read_sam), :211-254 (PAF leg),
+// :257-301 (fan-out merge + join).
+#include <algorithm>
+#include <map>
+
+#include "common.cuh"
+
+#ifndef GCI_USE_TMA
+#define GCI_USE_TMA 1
+#endif
+
+// ================================================================================================
+// K1  cigar_stats: segmented sum of CIGAR op lengths per record, tiled over the op stream
+// ================================================================================================
+// The packed op stream (uint32 `len << 4 | op`, BAM native) is cut into tiles of CIG_TILE ops.  One
+// CTA stages its tile in shared memory with a single TMA bulk copy (cp.async.bulk, 8 KB), each
+// thread walks 8 consecutive ops and accumulates five class sums
+//     Mx = M + '=' + X,  I,  D,  N,  S
+// (the reference only ever uses M+eq+X as one quantity: GCI.py:164-165; N is needed for
+// reference_end).  Records that lie completely inside the tile are written with plain stores, records
+// cut by a tile border are combined with global atomics.  Work per CTA is constant whatever the
+// ops-per-record distribution (HiFi ~30, ONT 10^3..10^5).
+constexpr int CIG_THREADS = 256;
+constexpr int CIG_OPT = 8;                       // ops per thread
+constexpr int CIG_TILE = CIG_THREADS * CIG_OPT;  // 2048 ops = 8 KB
+constexpr int CIG_CAP = 1024;                    // records per tile handled through shared memory
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+  } while (!done);
+}
+
+// 1-D TMA bulk copy global -> shared (SASS: UBLKCP); dst/src 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// first and last record of every op tile: record r (ops [a,b)) is the first record of the tiles whose
+// first op lies in [a,b) and the last record of the tiles whose last op lies in [a,b)
+__global__ void cigar_tile_index_kernel(const uint64_t* __restrict__ off, int64_t n, int2* __restrict__ tile_rec,
+                                        int64_t n_tiles, int64_t n_ops) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint64_t a = off[r], b = off[r + 1];
+  if (b <= a) return;
+  const int64_t k0 = (int64_t)((a + CIG_TILE - 1) / CIG_TILE);
+  const int64_t k1 = (int64_t)((b - 1) / CIG_TILE);
+  for (int64_t k = k0; k <= k1 && k < n_tiles; k++) tile_rec[k].x = (int32_t)r;
+  const int64_t l0 = (int64_t)(a / CIG_TILE);
+  const int64_t l1 = (int64_t)(b / CIG_TILE) - 1;
+  for (int64_t k = l0; k <= l1 && k < n_tiles; k++) tile_rec[k].y = (int32_t)r;
+  if ((int64_t)b == n_ops) tile_rec[n_tiles - 1].y = (int32_t)r;
+}
+
+struct CigAcc {
+  uint32_t mx, i, d, n, s;
+  __device__ __forceinline__ void clear() { mx = i = d = n = s = 0; }
+  __device__ __forceinline__ void add(uint32_t op) {
+    uint32_t c = op & 15u, l = op >> 4;
+    // class table packed in a 64-bit constant: M,=,X -> 0; I -> 1; D -> 2; N -> 3; S -> 4; H,P,B -> 7
+    const unsigned long long LUT = 0x7777777007743210ull;   // nibble k = class of op code k
+    uint32_t k = (uint32_t)(LUT >> (c * 4)) & 15u;
+    mx += (k == 0) ? l : 0u;
+    i += (k == 1) ? l : 0u;
+    d += (k == 2) ? l : 0u;
+    n += (k == 3) ? l : 0u;
+    s += (k == 4) ? l : 0u;
+  }
+  __device__ __forceinline__ bool any() const { return (mx | i | d | n | s) != 0; }
+};
+
+__global__ void __launch_bounds__(CIG_THREADS)
+cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restrict__ off, int64_t n_rec,
+                   int64_t n_ops, const int2* __restrict__ tile_rec, int64_t n_tiles,
+                   uint32_t* __restrict__ stats /* [n_rec][8] */) {
+  __shared__ __align__(128) uint32_t s_ops[CIG_TILE];
+  __shared__ int32_t s_off[CIG_CAP + 2];          // record starts relative to the tile, clamped
+  __shared__ uint32_t s_acc[CIG_CAP][5];
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t tile = blockIdx.x;
+  const int64_t o0 = tile * CIG_TILE;
+  const int tile_n = (int)min((int64_t)CIG_TILE, n_ops - o0);
+  const int2 tr = tile_rec[tile];
+  const int64_t r_lo = tr.x, r_hi = tr.y;   // first / last record with an op in this tile
+  const int64_t n_loc = r_hi - r_lo + 1;
+  const bool use_smem = n_loc <= CIG_CAP;
+
+#if GCI_USE_TMA
+  if (tid == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t bytes = (uint32_t)((tile_n * 4 + 15) & ~15);
+    mbar_expect_tx(&s_bar, bytes);
+    tma_load_1d(s_ops, cigar + o0, bytes, &s_bar);
+  }
+#else
+  for (int v = tid; v * 4 < tile_n; v += CIG_THREADS)
+    reinterpret_cast<uint4*>(s_ops)[v] = reinterpret_cast<const uint4*>(cigar + o0)[v];
+#endif
+  if (use_smem) {
+    for (int i = tid; i <= n_loc; i += CIG_THREADS) {
+      long long rel = (long long)off[r_lo + i] - (long long)o0;
+      s_off[i] = (int32_t)max(-1ll, min(rel, (long long)CIG_TILE + 1));
+    }
+    for (int i = tid; i < n_loc * 5; i += CIG_THREADS) (&s_acc[0][0])[i] = 0u;
+  }
+#if GCI_USE_TMA
+  mbar_wait(&s_bar, 0);
+#endif
+  __syncthreads();
+
+  const int first = tid * CIG_OPT;
+  const bool active = first < tile_n;
+  const int last = min(first + CIG_OPT, tile_n);
+  int64_t rl = 0;
+  long long next = 0;
+  uint32_t ops[CIG_OPT];
+  if (active) {
+    // local record of my first op
+    if (use_smem) {
+      int lo = 0, hi = (int)n_loc;   // s_off[lo] <= first < s_off[hi] (virtual)
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= first) lo = mid; else hi = mid;
+      }
+      rl = lo;
+    } else {
+      rl = upper_bound_minus1<uint64_t>(off + r_lo, n_loc, (uint64_t)(o0 + first));
+    }
+    next = use_smem ? (long long)s_off[rl + 1] : (long long)off[r_lo + rl + 1] - (long long)o0;
+    const uint4 a = reinterpret_cast<const uint4*>(s_ops)[tid * 2];
+    const uint4 b = reinterpret_cast<const uint4*>(s_ops)[tid * 2 + 1];
+    ops[0] = a.x; ops[1] = a.y; ops[2] = a.z; ops[3] = a.w;
+    ops[4] = b.x; ops[5] = b.y; ops[6] = b.z; ops[7] = b.w;
+  }
+  CigAcc acc;
+  acc.clear();
+  // fast path: the whole warp sits inside one record -> shuffle-reduce, one flush per warp
+  const bool one_rec = active && (next >= (long long)(first + CIG_OPT)) && (first + CIG_OPT <= tile_n);
+  const int64_t rl0 = __shfl_sync(0xffffffffu, rl, 0);
+  const bool warp_one = __all_sync(0xffffffffu, one_rec && rl == rl0);
+  if (warp_one) {
+#pragma unroll
+    for (int k = 0; k < CIG_OPT; k++) acc.add(ops[k]);
+    acc.mx = warp_sum(acc.mx); acc.i = warp_sum(acc.i); acc.d = warp_sum(acc.d);
+    acc.n = warp_sum(acc.n); acc.s = warp_sum(acc.s);
+    if (lane == 0) {
+      uint32_t* p = use_smem ? s_acc[rl] : stats + (r_lo + rl) * 8;
+      if (acc.mx) atomicAdd(p + 0, acc.mx);
+      if (acc.i) atomicAdd(p + 1, acc.i);
+      if (acc.d) atomicAdd(p + 2, acc.d);
+      if (acc.n) atomicAdd(p + 3, acc.n);
+      if (acc.s) atomicAdd(p + 4, acc.s);
+    }
+  } else if (active) {
+#pragma unroll
+    for (int k = 0; k < CIG_OPT; k++) {
+      const int o = first + k;
+      if (o < last) {
+        if ((long long)o >= next) {
+          // crossed into the next record (skip zero-op records)
+          if (acc.any()) {
+            uint32_t* p = use_smem ? s_acc[rl] : stats + (r_lo + rl) * 8;
+            if (acc.mx) atomicAdd(p + 0, acc.mx);
+            if (acc.i) atomicAdd(p + 1, acc.i);
+            if (acc.d) atomicAdd(p + 2, acc.d);
+            if (acc.n) atomicAdd(p + 3, acc.n);
+            if (acc.s) atomicAdd(p + 4, acc.s);
+            acc.clear();
+          }
+          do {
+            rl++;
+            next = use_smem ? (long long)s_off[rl + 1] : (long long)off[r_lo + rl + 1] - (long long)o0;
+          } while ((long long)o >= next);
+        }
+        acc.add(ops[k]);
+      }
+    }
+    if (acc.any()) {
+      uint32_t* p = use_smem ? s_acc[rl] : stats + (r_lo + rl) * 8;
+      if (acc.mx) atomicAdd(p + 0, acc.mx);
+      if (acc.i) atomicAdd(p + 1, acc.i);
+      if (acc.d) atomicAdd(p + 2, acc.d);
+      if (acc.n) atomicAdd(p + 3, acc.n);
+      if (acc.s) atomicAdd(p + 4, acc.s);
+    }
+  }
+  if (!use_smem) return;
+  __syncthreads();
+  for (int i = tid; i < n_loc; i += CIG_THREADS) {
+    const bool complete = s_off[i] >= 0 && s_off[i + 1] <= tile_n;
+    uint32_t* g = stats + (r_lo + i) * 8;
+    const uint32_t* p = s_acc[i];
+    if (complete) {
+      *reinterpret_cast<uint4*>(g) = make_uint4(p[0], p[1], p[2], p[3]);
+      g[4] = p[4];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 5; k++)
+        if (p[k]) atomicAdd(g + k, p[k]);
+    }
+  }
+}
+
+// ================================================================================================
+// K2  gate + dedup  (GCI.py:153-168)
+// ================================================================================================
+// d_err layout: [0] bit mask (1 = NM missing, 2 = zero clip denominator, 4 = zero identity denominator,
+//               8 = zero query length in the join, 16 = zero PAF aln length), [1] first offending index
+__global__ void gate_kernel(int64_t n, const int32_t* __restrict__ ref_id, const int32_t* __restrict__ ref_start,
+                            const uint8_t* __restrict__ mapq, const uint16_t* __restrict__ flag,
+                            const int32_t* __restrict__ nm, const uint32_t* __restrict__ read_id,
+                            const uint32_t* __restrict__ stats, const uint8_t* __restrict__ selected,
+                            int32_t n_contigs, uint32_t n_reads, int32_t map_qual, int32_t mq_cutoff, double ip,
+                            double cp, int32_t* __restrict__ ref_end, long long* __restrict__ win,
+                            uint8_t* __restrict__ highq, unsigned long long* __restrict__ err) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint4 st = *reinterpret_cast<const uint4*>(stats + r * 8);
+  const uint32_t S = stats[r * 8 + 4];
+  const long long Mx = st.x, I = st.y, D = st.z, N = st.w;
+  long long rlen = Mx + D + N;                       // htslib bam_cigar2rlen
+  if (rlen == 0) rlen = 1;                           // htslib bam_endpos
+  const int32_t start = ref_start[r];
+  ref_end[r] = (int32_t)(start + rlen);
+  const int32_t c = ref_id[r];
+  if (c < 0 || c >= n_contigs || !selected[c]) return;          // never fetched (GCI.py:151, :202-207)
+  const uint32_t f = flag[r];
+  if (f & (0x4u | 0x100u | 0x800u)) return;                      // :153-156
+  const int32_t mq = mapq[r];
+  if (mq < map_qual) return;                                     // :156
+  const int32_t nmv = nm[r];
+  if (nmv == INT32_MIN) {                                        // KeyError at :163
+    atomicOr(err, 1ull);
+    atomicMin(err + 1, (unsigned long long)r);
+    return;
+  }
+  const long long mm = (long long)nmv - (I + D);                 // :164
+  const long long d1 = Mx + I + (long long)S;
+  if (d1 == 0) {
+    atomicOr(err, 2ull);
+    atomicMin(err + 1, (unsigned long long)r);
+    return;
+  }
+  if (!((double)S / (double)d1 <= cp)) return;                   // :165, fp64 div.rn like Python int/int
+  const long long d2 = Mx + I + D;
+  if (d2 == 0) {
+    atomicOr(err, 4ull);
+    atomicMin(err + 1, (unsigned long long)r);
+    return;
+  }
+  if (!((double)(Mx - mm) / (double)d2 >= ip)) return;
+  const uint32_t q = read_id[r];
+  if (q >= n_reads) return;
+  // fetch order = contigs in header order, file order inside: the later record wins (:166, :269)
+  atomicMax(win + q, ((long long)c << 32) | (long long)r);
+  if (mq >= mq_cutoff) highq[q] = 1;                             // :167-168
+}
+
+__global__ void table_win_kernel(int64_t n, const uint32_t* __restrict__ read_id, uint32_t n_reads,
+                                 const uint8_t* __restrict__ hq_in, long long* __restrict__ win,
+                                 uint8_t* __restrict__ highq) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t q = read_id[i];
+  if (q >= n_reads) return;
+  atomicMax(win + q, (long long)i);
+  if (hq_in && hq_in[i]) highq[q] = 1;
+}
+
+// ================================================================================================
+// K4  cross-file join (GCI.py:272-301): one thread per read, files in join order
+// ================================================================================================
+struct JoinFile {
+  const long long* win;
+  const int32_t* ref_id;
+  const int32_t* start;
+  const int32_t* end;
+  const int32_t* qlen;
+};
+struct JoinArgs {
+  JoinFile f[GCI_MAX_FILES];
+  int n_files;
+};
+
+__global__ void join_kernel(JoinArgs a, uint32_t n_reads, const uint8_t* __restrict__ highq, double op,
+                            int32_t* __restrict__ s_contig, int32_t* __restrict__ s_start, int32_t* __restrict__ s_end,
+                            unsigned long long* __restrict__ count, unsigned long long* __restrict__ err) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  bool have = false;
+  int32_t c = -1, s = 0, e = 0;
+  if (r < n_reads) {
+    const long long k0 = a.f[0].win[r];
+    if (a.n_files == 1) {                                         // :300-301
+      if (k0 >= 0) {
+        const uint32_t i = (uint32_t)(k0 & 0xffffffffll);
+        have = true;
+        c = a.f[0].ref_id[i]; s = a.f[0].start[i]; e = a.f[0].end[i];
+      }
+    } else {
+      bool comm = true;
+      for (int f = 0; f < a.n_files; f++) comm = comm && (a.f[f].win[r] >= 0);          // :274-277
+      const bool hq = highq[r] != 0;
+      if (k0 >= 0 && (hq || comm)) {                                                     // :279-280
+        const uint32_t i = (uint32_t)(k0 & 0xffffffffll);
+        have = true;
+        c = a.f[0].ref_id[i]; s = a.f[0].start[i]; e = a.f[0].end[i];
+      }
+      for (int f = 1; f < a.n_files; f++) {                                               // :281-299
+        const long long k = a.f[f].win[r];
+        if (k < 0) continue;
+        const uint32_t i = (uint32_t)(k & 0xffffffffll);
+        const int32_t cf = a.f[f].ref_id[i], sf = a.f[f].start[i], ef = a.f[f].end[i];
+        if (have) {
+          if (cf == c) {
+            const long long ov = (long long)min(ef, e) - (long long)max(sf, s);
+            const int32_t ql = a.f[f].qlen[i];
+            if (ql == 0) {                                                                // ZeroDivisionError :292
+              atomicOr(err, 8ull);
+              atomicMin(err + 1, (unsigned long long)r);
+              have = false;
+            } else if ((double)ov / (double)ql < op) {
+              have = false;
+            } else {
+              s = max(sf, s);
+              e = min(ef, e);
+            }
+          } else {
+            have = false;
+          }
+        } else if (hq) {
+          have = true;
+          c = cf; s = sf; e = ef;
+        }
+      }
+    }
+    s_contig[r] = have ? c : -1;
+    s_start[r] = s;
+    s_end[r] = e;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, have);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+}
+
+// ================================================================================================
+// host drivers
+// ================================================================================================
+static int check_err(gci_ctx* ctx, const char* where) {
+  unsigned long long h[2];
+  GCI_CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_err.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h[0] == 0) return GCI_OK;
+  const char* what = (h[0] & 1)   ? "record without NM tag (KeyError at GCI.py:163)"
+                     : (h[0] & 2) ? "ZeroDivisionError at GCI.py:165 (clip ratio: no M/=/X/I/S bases)"
+                     : (h[0] & 4) ? "ZeroDivisionError at GCI.py:165 (identity: no M/=/X/I/D bases)"
+                     : (h[0] & 8) ? "ZeroDivisionError at GCI.py:292 (query_length 0 in the join)"
+                                  : "ZeroDivisionError at GCI.py:231 (PAF alignment length 0)";
+  return ctx->fail(GCI_E_REFERENCE_RAISES, "%s: the reference raises here: %s [first index %llu]", where, what, h[1]);
+}
+
+static int reset_err(gci_ctx* ctx) {
+  GCI_TRY(ctx->ensure(ctx->d_err, 4 * sizeof(unsigned long long)));
+  unsigned long long init[4] = {0ull, ~0ull, 0ull, 0ull};
+  GCI_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_err.p, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+  return GCI_OK;
+}
+
+int gci_run_bam_leg(gci_ctx* ctx, int file_idx, int bam_idx, int32_t mq, int32_t mq_cutoff, double ip, double cp) {
+  BamFile& b = ctx->bam[bam_idx];
+  FileTable& ft = ctx->files[file_idx];
+  const int64_t n = b.n;
+  GCI_TRY(ctx->ensure(ft.win, sizeof(long long) * (size_t)std::max<uint32_t>(1, ctx->n_reads)));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(ft.win.p, 0xff, sizeof(long long) * (size_t)ctx->n_reads, ctx->stream));
+  GCI_TRY(ctx->ensure(b.stats, 32 * (size_t)std::max<int64_t>(1, n)));
+  GCI_TRY(ctx->ensure(b.ref_end, 4 * (size_t)std::max<int64_t>(1, n)));
+  if (n == 0) return GCI_OK;
+  ctx->stage_begin(GCI_ST_CIGAR);
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(b.stats.p, 0, 32 * (size_t)n, ctx->stream));
+  if (b.n_ops > 0) {
+    const int64_t n_tiles = (b.n_ops + CIG_TILE - 1) / CIG_TILE;
+    GCI_TRY(ctx->ensure(ctx->misc, sizeof(int2) * (size_t)(n_tiles + 1)));
+    cigar_tile_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+        b.cigar_off.as<uint64_t>(), n, ctx->misc.as<int2>(), n_tiles, b.n_ops);
+    GCI_LAUNCH_CHECK(ctx);
+    cigar_stats_kernel<<<(unsigned)n_tiles, CIG_THREADS, 0, ctx->stream>>>(
+        b.cigar.as<uint32_t>(), b.cigar_off.as<uint64_t>(), n, b.n_ops, ctx->misc.as<int2>(), n_tiles,
+        b.stats.as<uint32_t>());
+    GCI_LAUNCH_CHECK(ctx);
+  }
+  ctx->stage_end();
+  ctx->stage_begin(GCI_ST_GATE);
+  gate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+      n, b.ref_id.as<int32_t>(), b.ref_start.as<int32_t>(), b.mapq.as<uint8_t>(), b.flag.as<uint16_t>(),
+      b.nm.as<int32_t>(), b.read_id.as<uint32_t>(), b.stats.as<uint32_t>(), ctx->d_selected.as<uint8_t>(),
+      ctx->n_contigs, ctx->n_reads, mq, mq_cutoff, ip, cp, b.ref_end.as<int32_t>(), ft.win.as<long long>(),
+      ctx->highq.as<uint8_t>(), ctx->d_err.as<unsigned long long>());
+  GCI_LAUNCH_CHECK(ctx);
+  ctx->stage_end();
+  return GCI_OK;
+}
+
+static int install_table(gci_ctx* ctx, FileTable& f, int64_t n, const uint32_t* read_id, const int32_t* ref_id,
+                         const int32_t* start, const int32_t* end, const int32_t* qlen, const uint8_t* highq) {
+  f.kind = 1;
+  f.n = n;
+  DevBuf d_read, d_hq;
+  ctx->stage_begin(GCI_ST_H2D);
+  GCI_TRY(gci_h2d(ctx, d_read, read_id, 4 * n));
+  GCI_TRY(gci_h2d(ctx, f.ref_id, ref_id, 4 * n));
+  GCI_TRY(gci_h2d(ctx, f.start, start, 4 * n));
+  GCI_TRY(gci_h2d(ctx, f.end, end, 4 * n));
+  GCI_TRY(gci_h2d(ctx, f.qlen, qlen, 4 * n));
+  if (highq) GCI_TRY(gci_h2d(ctx, d_hq, highq, n));
+  ctx->stage_end();
+  GCI_TRY(ctx->ensure(f.win, sizeof(long long) * (size_t)std::max<uint32_t>(1, ctx->n_reads)));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(f.win.p, 0xff, sizeof(long long) * (size_t)ctx->n_reads, ctx->stream));
+  if (n) {
+    table_win_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+        n, d_read.as<uint32_t>(), ctx->n_reads, highq ? d_hq.as<uint8_t>() : nullptr, f.win.as<long long>(),
+        ctx->highq.as<uint8_t>());
+    GCI_LAUNCH_CHECK(ctx);
+  }
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->release(d_read);
+  ctx->release(d_hq);
+  return GCI_OK;
+}
+
+// ---- PAF leg (host stage, GCI.py:211-254) -----------------------------------------------------------
+namespace {
+struct PafKept {
+  uint32_t read;
+  int32_t ref, qlen, q0, q1, t0, t1;
+  double ident;
+  uint64_t ord;
+};
+
+// GCI.py:64-96 on (lo,hi) pairs: total merged length and the longest merged block (first on ties)
+void merge_blocks(std::vector<std::pair<int32_t, int32_t>>& v, int64_t& total, int32_t& best_lo, int32_t& best_hi) {
+  std::sort(v.begin(), v.end());
+  total = 0;
+  int64_t best_len = -1;
+  int32_t lo = v[0].first, hi = v[0].second;
+  auto close_block = [&]() {
+    int64_t len = (int64_t)hi - lo;
+    total += len;
+    if (len > best_len) { best_len = len; best_lo = lo; best_hi = hi; }
+  };
+  for (auto& p : v) {
+    if (hi >= p.first) {
+      if (hi < p.second) hi = p.second;
+    } else {
+      close_block();
+      lo = p.first;
+      hi = p.second;
+    }
+  }
+  close_block();
+}
+}  // namespace
+
+int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
+  std::vector<PafKept> kept;   // the reference's `synteny`, alive across PAF files (GCI.py:214)
+  uint64_t ord = 0;
+  for (size_t fi = 0; fi < ctx->files.size(); fi++) {
+    FileTable& ft = ctx->files[fi];
+    if (ft.kind != 2) continue;
+    if ((int32_t)ctx->name_rank.size() != ctx->n_contigs)
+      return ctx->fail(GCI_E_ARG, "gci_set_name_rank must be called before filtering PAF files");
+    const PafFile& p = ctx->paf[ft.src];
+    std::vector<uint32_t> hq_reads;
+    for (int64_t i = 0; i < p.n; i++, ord++) {
+      const int32_t t = p.ref_id[i];
+      if (t < 0 || t >= ctx->n_contigs || !ctx->selected[t]) continue;        // :220
+      if (p.alnlen[i] == 0)
+        return ctx->fail(GCI_E_REFERENCE_RAISES,
+                         "PAF line %lld: the reference raises here: ZeroDivisionError at GCI.py:231", (long long)i);
+      const double ident = (double)p.nmatch[i] / (double)p.alnlen[i];          // :231
+      if (p.mapq[i] >= mq && ident >= ip) {                                     // :232
+        kept.push_back({p.read_id[i], t, p.qlen[i], p.qstart[i], p.qend[i], p.tstart[i], p.tend[i], ident, ord});
+        if (p.mapq[i] >= mq_cutoff) hq_reads.push_back(p.read_id[i]);           // :238
+      }
+    }
+    std::sort(kept.begin(), kept.end(), [](const PafKept& a, const PafKept& b) {
+      if (a.read != b.read) return a.read < b.read;
+      if (a.ref != b.ref) return a.ref < b.ref;
+      return a.ord < b.ord;
+    });
+    std::vector<uint32_t> o_read;
+    std::vector<int32_t> o_ref, o_s, o_e, o_q;
+    std::vector<std::pair<int32_t, int32_t>> qv, tv;
+    size_t i = 0;
+    while (i < kept.size()) {
+      const uint32_t read = kept[i].read;
+      bool have = false;
+      double best_score = 0;
+      int32_t best_rank = 0, b_ref = 0, b_s = 0, b_e = 0, b_q = 0;
+      while (i < kept.size() && kept[i].read == read) {
+        const int32_t ref = kept[i].ref;
+        size_t j = i;
+        double sum = 0;   // Python sum() starts from int 0; 0 + x is exact
+        qv.clear();
+        tv.clear();
+        for (; j < kept.size() && kept[j].read == read && kept[j].ref == ref; j++) {
+          sum = sum + kept[j].ident;
+          qv.emplace_back(kept[j].q0, kept[j].q1);
+          tv.emplace_back(kept[j].t0, kept[j].t1);
+        }
+        const int32_t qlen = kept[i].qlen;                                      // alns[0][0], :246
+        if (qlen == 0)
+          return ctx->fail(GCI_E_REFERENCE_RAISES, "the reference raises here: ZeroDivisionError at GCI.py:247");
+        int64_t mapped, dummy;
+        int32_t lo, hi, tlo, thi;
+        merge_blocks(qv, mapped, lo, hi);
+        merge_blocks(tv, dummy, tlo, thi);
+        const double rate = (double)mapped / (double)qlen;                     // :247
+        const double score = (sum / (double)(j - i)) * rate;                   // :248-249
+        const int32_t rank = ctx->name_rank[ref];
+        if (!have || score > best_score || (score == best_score && rank > best_rank)) {   // :252
+          have = true;
+          best_score = score; best_rank = rank;
+          b_ref = ref; b_s = tlo; b_e = thi; b_q = qlen;
+        }
+        i = j;
+      }
+      o_read.push_back(read); o_ref.push_back(b_ref); o_s.push_back(b_s); o_e.push_back(b_e); o_q.push_back(b_q);
+    }
+    // high-quality marks ride along as a second tiny table
+    GCI_TRY(install_table(ctx, ft, (int64_t)o_read.size(), o_read.data(), o_ref.data(), o_s.data(), o_e.data(),
+                          o_q.data(), nullptr));
+    if (!hq_reads.empty()) {
+      std::vector<uint8_t> one(hq_reads.size(), 1);
+      DevBuf d_r, d_h, d_w;
+      GCI_TRY(gci_h2d(ctx, d_r, hq_reads.data(), 4 * hq_reads.size()));
+      GCI_TRY(gci_h2d(ctx, d_h, one.data(), one.size()));
+      GCI_TRY(ctx->ensure(d_w, sizeof(long long) * (size_t)std::max<uint32_t>(1, ctx->n_reads)));
+      table_win_kernel<<<(unsigned)((hq_reads.size() + 255) / 256), 256, 0, ctx->stream>>>(
+          (int64_t)hq_reads.size(), d_r.as<uint32_t>(), ctx->n_reads, d_h.as<uint8_t>(), d_w.as<long long>(),
+          ctx->highq.as<uint8_t>());
+      GCI_LAUNCH_CHECK(ctx);
+      GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      ctx->release(d_r); ctx->release(d_h); ctx->release(d_w);
+    }
+  }
+  return GCI_OK;
+}
+
+int gci_run_join(gci_ctx* ctx, double op) {
+  JoinArgs a;
+  memset(&a, 0, sizeof a);
+  a.n_files = (int)ctx->files.size();
+  for (int i = 0; i < a.n_files; i++) {
+    FileTable& f = ctx->files[i];
+    a.f[i].win = f.win.as<long long>();
+    if (f.kind == 0) {
+      BamFile& b = ctx->bam[f.src];
+      a.f[i].ref_id = b.ref_id.as<int32_t>();
+      a.f[i].start = b.ref_start.as<int32_t>();
+      a.f[i].end = b.ref_end.as<int32_t>();
+      a.f[i].qlen = b.qlen.as<int32_t>();
+    } else {
+      a.f[i].ref_id = f.ref_id.as<int32_t>();
+      a.f[i].start = f.start.as<int32_t>();
+      a.f[i].end = f.end.as<int32_t>();
+      a.f[i].qlen = f.qlen.as<int32_t>();
+    }
+  }
+  const size_t nr = std::max<uint32_t>(1, ctx->n_reads);
+  GCI_TRY(ctx->ensure(ctx->surv_contig, 4 * nr));
+  GCI_TRY(ctx->ensure(ctx->surv_start, 4 * nr));
+  GCI_TRY(ctx->ensure(ctx->surv_end, 4 * nr));
+  unsigned long long* cnt = ctx->d_err.as<unsigned long long>() + 2;
+  ctx->stage_begin(GCI_ST_JOIN);
+  if (ctx->n_reads) {
+    join_kernel<<<(ctx->n_reads + 255) / 256, 256, 0, ctx->stream>>>(
+        a, ctx->n_reads, ctx->highq.as<uint8_t>(), op, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(),
+        ctx->surv_end.as<int32_t>(), cnt, ctx->d_err.as<unsigned long long>());
+    GCI_LAUNCH_CHECK(ctx);
+  }
+  ctx->stage_end();
+  return GCI_OK;
+}
+
+// ordered compaction helpers (fetch paths; not on the timed path)
+__global__ void mark_survivors_kernel(uint32_t n, const int32_t* __restrict__ contig, int32_t* __restrict__ mark) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) mark[r] = contig[r] >= 0 ? 1 : 0;
+}
+
+__global__ void mark_present_kernel(uint32_t n, const long long* __restrict__ win, int32_t* __restrict__ mark) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) mark[r] = win[r] >= 0 ? 1 : 0;
+}
+
+__global__ void gather_survivors_kernel(uint32_t n, const int32_t* __restrict__ mark, const int32_t* __restrict__ pos,
+                                        const int32_t* __restrict__ c, const int32_t* __restrict__ s,
+                                        const int32_t* __restrict__ e, uint32_t* __restrict__ o_read,
+                                        int32_t* __restrict__ o_c, int32_t* __restrict__ o_s, int32_t* __restrict__ o_e) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n || !mark[r]) return;
+  const int32_t p = pos[r];
+  o_read[p] = r; o_c[p] = c[r]; o_s[p] = s[r]; o_e[p] = e[r];
+}
+
+__global__ void gather_table_kernel(uint32_t n, const int32_t* __restrict__ mark, const int32_t* __restrict__ pos,
+                                    JoinFile f, const uint8_t* __restrict__ highq, uint32_t* __restrict__ o_read,
+                                    int32_t* __restrict__ o_c, int32_t* __restrict__ o_s, int32_t* __restrict__ o_e,
+                                    int32_t* __restrict__ o_q, uint8_t* __restrict__ o_h) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n || !mark[r]) return;
+  const int32_t p = pos[r];
+  const uint32_t i = (uint32_t)(f.win[r] & 0xffffffffll);
+  o_read[p] = r; o_c[p] = f.ref_id[i]; o_s[p] = f.start[i]; o_e[p] = f.end[i]; o_q[p] = f.qlen[i];
+  o_h[p] = highq[r];
+}
+
+extern "C" {
+
+int gci_upload_table(gci_ctx* ctx, int64_t n, const uint32_t* read_id, const int32_t* ref_id, const int32_t* start,
+                     const int32_t* end, const int32_t* qlen, const uint8_t* highq) {
+  if (!ctx || n < 0) return GCI_E_ARG;
+  if (n && (!read_id || !ref_id || !start || !end || !qlen)) return GCI_E_ARG;
+  if ((int)ctx->files.size() >= GCI_MAX_FILES) return ctx->fail(GCI_E_ARG, "too many files");
+  cudaSetDevice(ctx->device);
+  ctx->files.emplace_back();
+  ctx->filtered = false;
+  return install_table(ctx, ctx->files.back(), n, read_id, ref_id, start, end, qlen, highq);
+}
+
+int gci_filter(gci_ctx* ctx, int32_t map_qual, int32_t mq_cutoff, double iden_percent, double clip_percent,
+               double ovlp_percent, int64_t* n_survivors) {
+  if (!ctx) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->files.empty()) return ctx->fail(GCI_E_ARG, "gci_filter: no files uploaded");
+  GCI_TRY(reset_err(ctx));
+  // PAF election first (host stage); tables uploaded by the caller are already final
+  ctx->stage_begin(GCI_ST_PAF);
+  ctx->stage_end();
+  GCI_TRY(gci_run_paf_legs(ctx, map_qual, mq_cutoff, iden_percent));
+  for (size_t i = 0; i < ctx->files.size(); i++)
+    if (ctx->files[i].kind == 0)
+      GCI_TRY(gci_run_bam_leg(ctx, (int)i, ctx->files[i].src, map_qual, mq_cutoff, iden_percent, clip_percent));
+  GCI_TRY(gci_run_join(ctx, ovlp_percent));
+  unsigned long long cnt = 0;
+  GCI_CUDA_TRY(ctx, cudaMemcpyAsync(&cnt, ctx->d_err.as<unsigned long long>() + 2, sizeof cnt,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+  GCI_TRY(check_err(ctx, "gci_filter"));
+  ctx->n_survivors = (int64_t)cnt;
+  ctx->filtered = true;
+  if (n_survivors) *n_survivors = ctx->n_survivors;
+  return GCI_OK;
+}
+
+int gci_fetch_survivors(gci_ctx* ctx, int64_t cap, uint32_t* read_id, int32_t* contig, int32_t* start, int32_t* end,
+                        int64_t* n) {
+  if (!ctx) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (!ctx->filtered) return ctx->fail(GCI_E_ARG, "gci_fetch_survivors before gci_filter");
+  if (n) *n = ctx->n_survivors;
+  if (!read_id && !contig && !start && !end) return GCI_OK;
+  if (cap < ctx->n_survivors) return ctx->fail(GCI_E_ARG, "survivor buffer too small");
+  const uint32_t nr = ctx->n_reads;
+  const int64_t ns = ctx->n_survivors;
+  if (ns == 0) return GCI_OK;
+  DevBuf mark, pos, o_r, o_c, o_s, o_e;
+  GCI_TRY(ctx->ensure(mark, 4 * (size_t)nr));
+  GCI_TRY(ctx->ensure(pos, 4 * (size_t)nr));
+  for (DevBuf* d : {&o_r, &o_c, &o_s, &o_e}) GCI_TRY(ctx->ensure(*d, 4 * (size_t)ns));
+  mark_survivors_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(nr, ctx->surv_contig.as<int32_t>(), mark.as<int32_t>());
+  GCI_LAUNCH_CHECK(ctx);
+  GCI_TRY(gci_exclusive_scan_i32(ctx, mark.as<int32_t>(), pos.as<int32_t>(), nr));
+  gather_survivors_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(
+      nr, mark.as<int32_t>(), pos.as<int32_t>(), ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(),
+      ctx->surv_end.as<int32_t>(), o_r.as<uint32_t>(), o_c.as<int32_t>(), o_s.as<int32_t>(), o_e.as<int32_t>());
+  GCI_LAUNCH_CHECK(ctx);
+  if (read_id) GCI_TRY(gci_d2h(ctx, read_id, o_r.p, 4 * ns));
+  if (contig) GCI_TRY(gci_d2h(ctx, contig, o_c.p, 4 * ns));
+  if (start) GCI_TRY(gci_d2h(ctx, start, o_s.p, 4 * ns));
+  if (end) GCI_TRY(gci_d2h(ctx, end, o_e.p, 4 * ns));
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (DevBuf* d : {&mark, &pos, &o_r, &o_c, &o_s, &o_e}) ctx->release(*d);
+  return GCI_OK;
+}
+
+int gci_fetch_file_table(gci_ctx* ctx, int32_t file, int64_t cap, uint32_t* read_id, int32_t* contig, int32_t* start,
+                         int32_t* end, int32_t* qlen, uint8_t* highq, int64_t* n) {
+  if (!ctx) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (!ctx->filtered) return ctx->fail(GCI_E_ARG, "gci_fetch_file_table before gci_filter");
+  if (file < 0 || file >= (int)ctx->files.size()) return ctx->fail(GCI_E_ARG, "bad file index %d", file);
+  FileTable& f = ctx->files[file];
+  const uint32_t nr = ctx->n_reads;
+  DevBuf mark, pos;
+  GCI_TRY(ctx->ensure(mark, 4 * (size_t)(nr + 1)));
+  GCI_TRY(ctx->ensure(pos, 4 * (size_t)(nr + 1)));
+  int64_t cnt = 0;
+  if (nr) {
+    mark_present_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(nr, f.win.as<long long>(), mark.as<int32_t>());
+    GCI_LAUNCH_CHECK(ctx);
+    GCI_CUDA_TRY(ctx, cudaMemsetAsync(mark.as<int32_t>() + nr, 0, 4, ctx->stream));
+    GCI_TRY(gci_exclusive_scan_i32(ctx, mark.as<int32_t>(), pos.as<int32_t>(), (int64_t)nr + 1));
+    int32_t c32 = 0;
+    GCI_TRY(gci_d2h(ctx, &c32, pos.as<int32_t>() + nr, 4));
+    GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cnt = c32;
+  }
+  if (n) *n = cnt;
+  int rc = GCI_OK;
+  if (read_id || contig || start || end || qlen || highq) {
+    if (cap < cnt) {
+      rc = ctx->fail(GCI_E_ARG, "table buffer too small");
+    } else if (cnt) {
+      JoinFile jf;
+      jf.win = f.win.as<long long>();
+      if (f.kind == 0) {
+        BamFile& b = ctx->bam[f.src];
+        jf.ref_id = b.ref_id.as<int32_t>(); jf.start = b.ref_start.as<int32_t>();
+        jf.end = b.ref_end.as<int32_t>(); jf.qlen = b.qlen.as<int32_t>();
+      } else {
+        jf.ref_id = f.ref_id.as<int32_t>(); jf.start = f.start.as<int32_t>();
+        jf.end = f.end.as<int32_t>(); jf.qlen = f.qlen.as<int32_t>();
+      }
+      DevBuf o_r, o_c, o_s, o_e, o_q, o_h;
+      for (DevBuf* d : {&o_r, &o_c, &o_s, &o_e, &o_q}) GCI_TRY(ctx->ensure(*d, 4 * (size_t)cnt));
+      GCI_TRY(ctx->ensure(o_h, (size_t)cnt));
+      gather_table_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(
+          nr, mark.as<int32_t>(), pos.as<int32_t>(), jf, ctx->highq.as<uint8_t>(), o_r.as<uint32_t>(),
+          o_c.as<int32_t>(), o_s.as<int32_t>(), o_e.as<int32_t>(), o_q.as<int32_t>(), o_h.as<uint8_t>());
+      GCI_LAUNCH_CHECK(ctx);
+      if (read_id) GCI_TRY(gci_d2h(ctx, read_id, o_r.p, 4 * cnt));
+      if (contig) GCI_TRY(gci_d2h(ctx, contig, o_c.p, 4 * cnt));
+      if (start) GCI_TRY(gci_d2h(ctx, start, o_s.p, 4 * cnt));
+      if (end) GCI_TRY(gci_d2h(ctx, end, o_e.p, 4 * cnt));
+      if (qlen) GCI_TRY(gci_d2h(ctx, qlen, o_q.p, 4 * cnt));
+      if (highq) GCI_TRY(gci_d2h(ctx, highq, o_h.p, cnt));
+      GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      for (DevBuf* d : {&o_r, &o_c, &o_s, &o_e, &o_q, &o_h}) ctx->release(*d);
+    }
+  }
+  ctx->release(mark);
+  ctx->release(pos);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,613 @@
+// Device-wide scans, issue-run extraction from the flag bitmask (GCI.py:356-390) and score terms
+// (GCI.py:422-519).
+#include <algorithm>
+
+#include "common.cuh"
+
+// ================================================================================================
+// generic exclusive scan: per-block reduce -> (recursive) scan of block sums -> per-block scan
+// ================================================================================================
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;   // 2048 items per block
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_reduce_kernel(const TI* __restrict__ in, int64_t n, TO* __restrict__ block_sums) {
+  __shared__ TO s_w[SCAN_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK;
+  TO v = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    const int64_t i = base + k * SCAN_THREADS + threadIdx.x;
+    if (i < n) v += (TO)in[i];
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    TO t = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; w++) t += s_w[w];
+    block_sums[blockIdx.x] = t;
+  }
+}
+
+// exclusive scan of one block's items (thread-blocked order), adding block_off[blockIdx]
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_apply_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n, const TO* __restrict__ block_off,
+                  TO* __restrict__ total /* nullable: written by the last block */) {
+  __shared__ TO s_w[SCAN_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_ITEMS;
+  TO item[SCAN_ITEMS];
+  TO sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    const int64_t i = base + k;
+    item[k] = i < n ? (TO)in[i] : (TO)0;
+    sum += item[k];
+  }
+  // warp inclusive scan of thread sums
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  TO incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    TO t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) s_w[w] = incl;
+  __syncthreads();
+  TO woff = 0;
+  for (int j = 0; j < w; j++) woff += s_w[j];
+  TO run = (block_off ? block_off[blockIdx.x] : (TO)0) + woff + incl - sum;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    const int64_t i = base + k;
+    if (i < n) out[i] = run;
+    run += item[k];
+  }
+  if (total && blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) *total = run;
+}
+
+template <typename TI, typename TO>
+static int exclusive_scan(gci_ctx* ctx, const TI* in, TO* out, int64_t n, TO* total_dev, int depth = 0) {
+  if (n <= 0) {
+    if (total_dev) GCI_CUDA_TRY(ctx, cudaMemsetAsync(total_dev, 0, sizeof(TO), ctx->stream));
+    return GCI_OK;
+  }
+  const int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  if (nb == 1) {
+    scan_apply_kernel<TI, TO><<<1, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, nullptr, total_dev);
+    GCI_LAUNCH_CHECK(ctx);
+    return GCI_OK;
+  }
+  // block sums / offsets live in per-level context scratch (no allocation in steady state)
+  if (depth >= 4) return ctx->fail(GCI_E_ARG, "scan recursion too deep");
+  DevBuf& sums = ctx->scan_lvl[2 * depth];
+  DevBuf& offs = ctx->scan_lvl[2 * depth + 1];
+  GCI_TRY(ctx->ensure(sums, sizeof(TO) * (size_t)nb));
+  GCI_TRY(ctx->ensure(offs, sizeof(TO) * (size_t)nb));
+  scan_reduce_kernel<TI, TO><<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, n, sums.as<TO>());
+  GCI_LAUNCH_CHECK(ctx);
+  GCI_TRY((exclusive_scan<TO, TO>(ctx, sums.as<TO>(), offs.as<TO>(), nb, nullptr, depth + 1)));
+  scan_apply_kernel<TI, TO><<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, offs.as<TO>(), total_dev);
+  GCI_LAUNCH_CHECK(ctx);
+  return GCI_OK;
+}
+
+int gci_exclusive_scan_i64_from_i32(gci_ctx* ctx, const int32_t* in, int64_t* out, int64_t n, int64_t* total_dev) {
+  return exclusive_scan<int32_t, long long>(ctx, in, reinterpret_cast<long long*>(out), n,
+                                            reinterpret_cast<long long*>(total_dev));
+}
+
+int gci_exclusive_scan_i32(gci_ctx* ctx, const int32_t* in, int32_t* out, int64_t n) {
+  return exclusive_scan<int32_t, int32_t>(ctx, in, out, n, nullptr);
+}
+
+int gci_exclusive_scan_u64(gci_ctx* ctx, const unsigned long long* in, unsigned long long* out, int64_t n,
+                           unsigned long long* total_dev) {
+  return exclusive_scan<unsigned long long, unsigned long long>(ctx, in, out, n, total_dev);
+}
+
+// ================================================================================================
+// K7  run extraction from the flag bitmask
+// ================================================================================================
+// A scan "owner" is a window [lo, hi) of one contig (whole-genome scan: one window per selected
+// contig, lo from the drop rule below, hi = L - fl; regions scan: the regions themselves).  Bits
+// outside the window read as 0, so every run start has a matching end at or before position hi.
+
+__device__ __forceinline__ bool flag_bit(const uint32_t* __restrict__ flags, int64_t gpos) {
+  return (flags[gpos >> 5] >> (gpos & 31)) & 1u;
+}
+
+// Whole-genome windows with the reference's drop rule (GCI.py:385 `if i > flank_len`): a run whose
+// end is <= 2*fl is dropped unless it touches the view end L - fl (GCI.py:380-382).  All dropped runs
+// sit in [fl, 2*fl), so the rule is equivalent to moving the window start to
+//   h = start of the run covering 2*fl-1   if that run continues past 2*fl,   else 2*fl
+// (for contigs with L - fl <= 2*fl: the start of the run touching L - fl, else the empty window).
+__global__ void genome_windows_kernel(int32_t n_contigs, const int64_t* __restrict__ len,
+                                      const uint8_t* __restrict__ selected, const int64_t* __restrict__ tile_off,
+                                      const uint32_t* __restrict__ flags, int32_t fl, int32_t* __restrict__ w_contig,
+                                      int64_t* __restrict__ w_lo, int64_t* __restrict__ w_hi,
+                                      const int32_t* __restrict__ owner_of_contig) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_contigs || !selected[c]) return;
+  const int o = owner_of_contig[c];
+  const int64_t L = len[c];
+  const int64_t g0 = tile_off[c] * GCI_TILE;
+  int64_t lo = 0, hi = 0;
+  if (fl >= 0 && L - 2 * (int64_t)fl > 0) {
+    hi = L - fl;
+    if (fl == 0) {
+      lo = 0;
+    } else {
+      const int64_t two = 2 * (int64_t)fl;
+      int64_t probe;      // last position whose run may survive
+      bool keep;
+      if (hi <= two) {
+        probe = hi - 1;
+        keep = flag_bit(flags, g0 + probe);
+        lo = hi;
+      } else {
+        probe = two - 1;
+        keep = flag_bit(flags, g0 + probe) && flag_bit(flags, g0 + two);
+        lo = two;
+      }
+      if (keep) {
+        int64_t p = probe;
+        while (p > fl && flag_bit(flags, g0 + p - 1)) p--;
+        lo = p;
+      }
+    }
+  }
+  w_contig[o] = c;
+  w_lo[o] = lo;
+  w_hi[o] = hi;
+}
+
+struct RunWin {
+  int64_t g0;       // global padded position of the contig start
+  int64_t lo, hi;   // window in contig coordinates
+  int64_t w0;       // first word (contig-relative) = lo >> 5
+  int64_t n_words;  // words covering [lo, hi] inclusive
+};
+
+__device__ __forceinline__ RunWin load_win(int64_t o, const int32_t* w_contig, const int64_t* w_lo, const int64_t* w_hi,
+                                           const int64_t* tile_off) {
+  RunWin w;
+  w.g0 = tile_off[w_contig[o]] * GCI_TILE;
+  w.lo = w_lo[o];
+  w.hi = w_hi[o];
+  w.w0 = w.lo >> 5;
+  w.n_words = w.hi > w.lo ? (w.hi >> 5) - w.w0 + 1 : 0;
+  return w;
+}
+
+// flag word `j` (window-relative) restricted to the window
+__device__ __forceinline__ uint32_t win_word(const uint32_t* __restrict__ flags, const RunWin& w, int64_t j) {
+  if (j < 0 || j >= w.n_words) return 0u;
+  const int64_t cw = w.w0 + j;                  // contig-relative word
+  uint32_t m = flags[(w.g0 >> 5) + cw];
+  const int64_t p0 = cw << 5;
+  if (p0 < w.lo) m &= 0xffffffffu << (w.lo - p0);
+  if (p0 + 32 > w.hi) {
+    const int64_t keep = w.hi - p0;             // bits [0, keep) stay
+    m = keep <= 0 ? 0u : (keep >= 32 ? m : (m & ((1u << keep) - 1u)));
+  }
+  return m;
+}
+
+constexpr int RUN_THREADS = 256;
+constexpr int RUN_WPT = GCI_RUN_CHUNK_WORDS / RUN_THREADS;   // words per thread (8)
+
+// chunk -> owner by binary search on chunk_off[n_owners+1]
+template <bool WRITE>
+__global__ void __launch_bounds__(RUN_THREADS)
+runs_kernel(const uint32_t* __restrict__ flags, int64_t n_owners, const int64_t* __restrict__ chunk_off,
+            const int32_t* __restrict__ w_contig, const int64_t* __restrict__ w_lo, const int64_t* __restrict__ w_hi,
+            const int64_t* __restrict__ tile_off, int32_t* __restrict__ cnt_s, int32_t* __restrict__ cnt_e,
+            const int64_t* __restrict__ off_s, const int64_t* __restrict__ off_e, int32_t* __restrict__ iv_start,
+            int32_t* __restrict__ iv_end) {
+  __shared__ int s_ws[RUN_THREADS / 32], s_we[RUN_THREADS / 32];
+  const int64_t chunk = blockIdx.x;
+  const int64_t o = upper_bound_minus1<int64_t>(chunk_off, n_owners + 1, chunk);
+  const RunWin w = load_win(o, w_contig, w_lo, w_hi, tile_off);
+  const int64_t j0 = (chunk - chunk_off[o]) * GCI_RUN_CHUNK_WORDS + (int64_t)threadIdx.x * RUN_WPT;
+  uint32_t st[RUN_WPT], en[RUN_WPT];
+  int ns = 0, ne = 0;
+  uint32_t prev = win_word(flags, w, j0 - 1);
+#pragma unroll
+  for (int k = 0; k < RUN_WPT; k++) {
+    const uint32_t m = win_word(flags, w, j0 + k);
+    const uint32_t sh = (m << 1) | (prev >> 31);
+    st[k] = m & ~sh;
+    en[k] = ~m & sh;
+    // an end can only be reported on a word that exists in the window (positions <= hi)
+    if (j0 + k >= w.n_words) en[k] = 0u;
+    ns += __popc(st[k]);
+    ne += __popc(en[k]);
+    prev = m;
+  }
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int is = warp_incl_scan(ns, lane), ie = warp_incl_scan(ne, lane);
+  if (lane == 31) { s_ws[wp] = is; s_we[wp] = ie; }
+  __syncthreads();
+  int bs = 0, be = 0, ts = 0, te = 0;
+  for (int j = 0; j < RUN_THREADS / 32; j++) {
+    if (j < wp) { bs += s_ws[j]; be += s_we[j]; }
+    ts += s_ws[j]; te += s_we[j];
+  }
+  if (!WRITE) {
+    if (threadIdx.x == 0) { cnt_s[chunk] = ts; cnt_e[chunk] = te; }
+    return;
+  }
+  int64_t ps = off_s[chunk] + bs + is - ns;
+  int64_t pe = off_e[chunk] + be + ie - ne;
+#pragma unroll
+  for (int k = 0; k < RUN_WPT; k++) {
+    const int64_t p0 = (w.w0 + j0 + k) << 5;
+    uint32_t m = st[k];
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      iv_start[ps++] = (int32_t)(p0 + b);
+    }
+    m = en[k];
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      iv_end[pe++] = (int32_t)(p0 + b);
+    }
+  }
+}
+
+__global__ void owner_offsets_kernel(int64_t n_owners, const int64_t* __restrict__ chunk_off,
+                                     const int64_t* __restrict__ off_s, const int64_t* __restrict__ total_s,
+                                     int64_t n_chunks, int64_t* __restrict__ owner_off) {
+  const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (o > n_owners) return;
+  const int64_t ch = chunk_off[o];
+  owner_off[o] = (o == n_owners || ch >= n_chunks) ? *total_s : off_s[ch];
+}
+
+// shared tail of gci_scan / gci_scan_windows: windows are on the device in t.win_*
+static int extract_runs(gci_ctx* ctx, Track& t, const std::vector<int64_t>& h_lo, const std::vector<int64_t>& h_hi,
+                        int64_t* n_intervals) {
+  const int64_t n_owners = t.n_owners;
+  std::vector<int64_t> chunk_off(n_owners + 1, 0);
+  for (int64_t o = 0; o < n_owners; o++) {
+    const int64_t nw = h_hi[o] > h_lo[o] ? (h_hi[o] >> 5) - (h_lo[o] >> 5) + 1 : 0;
+    chunk_off[o + 1] = chunk_off[o] + (nw + GCI_RUN_CHUNK_WORDS - 1) / GCI_RUN_CHUNK_WORDS;
+  }
+  const int64_t n_chunks = chunk_off[n_owners];
+  GCI_TRY(gci_h2d(ctx, ctx->chunk_off, chunk_off.data(), sizeof(int64_t) * (n_owners + 1)));
+  GCI_TRY(ctx->ensure(t.owner_off, sizeof(int64_t) * (size_t)(n_owners + 1)));
+  t.n_intervals = 0;
+  if (n_chunks == 0) {
+    GCI_CUDA_TRY(ctx, cudaMemsetAsync(t.owner_off.p, 0, sizeof(int64_t) * (n_owners + 1), ctx->stream));
+    GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_intervals) *n_intervals = 0;
+    return GCI_OK;
+  }
+  // chunk_cnt: [cnt_s | cnt_e] int32, scan_tmp: [off_s | off_e | total_s | total_e] int64
+  GCI_TRY(ctx->ensure(ctx->chunk_cnt, sizeof(int32_t) * 2 * (size_t)n_chunks));
+  GCI_TRY(ctx->ensure(ctx->scan_tmp, sizeof(int64_t) * (2 * (size_t)n_chunks + 2)));
+  int32_t* cnt_s = ctx->chunk_cnt.as<int32_t>();
+  int32_t* cnt_e = cnt_s + n_chunks;
+  int64_t* off_s = ctx->scan_tmp.as<int64_t>();
+  int64_t* off_e = off_s + n_chunks;
+  int64_t* tot = off_e + n_chunks;
+  runs_kernel<false><<<(unsigned)n_chunks, RUN_THREADS, 0, ctx->stream>>>(
+      t.flags.as<uint32_t>(), n_owners, ctx->chunk_off.as<int64_t>(), t.win_contig.as<int32_t>(),
+      t.win_lo.as<int64_t>(), t.win_hi.as<int64_t>(), ctx->d_tile_off.as<int64_t>(), cnt_s, cnt_e, nullptr, nullptr,
+      nullptr, nullptr);
+  GCI_LAUNCH_CHECK(ctx);
+  GCI_TRY(gci_exclusive_scan_i64_from_i32(ctx, cnt_s, off_s, n_chunks, tot));
+  GCI_TRY(gci_exclusive_scan_i64_from_i32(ctx, cnt_e, off_e, n_chunks, tot + 1));
+  int64_t h_tot[2];
+  GCI_TRY(gci_d2h(ctx, h_tot, tot, sizeof h_tot));
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h_tot[0] != h_tot[1])
+    return ctx->fail(GCI_E_CUDA, "internal: run starts (%lld) != run ends (%lld)", (long long)h_tot[0],
+                     (long long)h_tot[1]);
+  t.n_intervals = h_tot[0];
+  GCI_TRY(ctx->ensure(t.iv_start, sizeof(int32_t) * (size_t)std::max<int64_t>(1, t.n_intervals)));
+  GCI_TRY(ctx->ensure(t.iv_end, sizeof(int32_t) * (size_t)std::max<int64_t>(1, t.n_intervals)));
+  if (t.n_intervals) {
+    runs_kernel<true><<<(unsigned)n_chunks, RUN_THREADS, 0, ctx->stream>>>(
+        t.flags.as<uint32_t>(), n_owners, ctx->chunk_off.as<int64_t>(), t.win_contig.as<int32_t>(),
+        t.win_lo.as<int64_t>(), t.win_hi.as<int64_t>(), ctx->d_tile_off.as<int64_t>(), nullptr, nullptr, off_s, off_e,
+        t.iv_start.as<int32_t>(), t.iv_end.as<int32_t>());
+    GCI_LAUNCH_CHECK(ctx);
+  }
+  owner_offsets_kernel<<<(unsigned)((n_owners + 1 + 255) / 256), 256, 0, ctx->stream>>>(
+      n_owners, ctx->chunk_off.as<int64_t>(), off_s, tot, n_chunks, t.owner_off.as<int64_t>());
+  GCI_LAUNCH_CHECK(ctx);
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_intervals) *n_intervals = t.n_intervals;
+  return GCI_OK;
+}
+
+// ================================================================================================
+// K8  score terms: complement lengths, -dp merge count, N50 by bitwise weighted-median selection
+// ================================================================================================
+// For owner o with window [S, E) and sorted disjoint intervals (s_i, e_i):
+//   gaps g_0 = s_0 - S, g_i = s_i - e_{i-1}, tail = E - e_last            (GCI.py:446-458)
+//   complement lengths = {g_i > 0} + {tail > 0}            or  [E - S] if there is no interval (:460)
+//   -dp merge (GCI.py:509-518) joins neighbours across every gap <= dist, starting from the sentinel
+//   (S,S) and ending at E, so the merged complement keeps exactly the gaps that are > dist (and > 0).
+//   N50 (GCI.py:473-479) = largest length v with  2 * sum{len >= v} >= total  -> found bit by bit.
+__global__ void complement_kernel(int64_t n_owners, const int64_t* __restrict__ owner_off,
+                                  const int32_t* __restrict__ iv_start, const int32_t* __restrict__ iv_end,
+                                  const int64_t* __restrict__ S, const int64_t* __restrict__ E,
+                                  const double* __restrict__ dist, int64_t* __restrict__ gaps /* [n_iv + n_owners] */,
+                                  int64_t* __restrict__ n_len, int64_t* __restrict__ n_ctg) {
+  // one block per owner; slot layout in `gaps`: owner o uses [owner_off[o] + o, owner_off[o+1] + o + 1)
+  const int64_t o = blockIdx.x;
+  const int64_t a = owner_off[o], b = owner_off[o + 1];
+  int64_t* g = gaps + a + o;
+  const int64_t n = b - a;
+  long long my_len = 0, my_ctg = 0;
+  const double d = dist[o];
+  if (n == 0) {
+    if (threadIdx.x == 0) {
+      g[0] = E[o] - S[o];                                   // appended unconditionally (:460)
+      my_len = 1;
+      // merged = [(S,S)] then tail rule: (E - S) <= dist -> one segment (S,E) -> empty complement
+      my_ctg = ((double)(E[o] - S[o]) <= d) ? 0 : (E[o] > S[o] ? 1 : 0);
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i <= n; i += blockDim.x) {
+      long long v;
+      if (i < n) {
+        const long long prev = i == 0 ? S[o] : (long long)iv_end[a + i - 1];
+        v = (long long)iv_start[a + i] - prev;
+      } else {
+        v = E[o] - (long long)iv_end[b - 1];
+      }
+      const bool emit = v > 0;
+      g[i] = emit ? v : 0;
+      my_len += emit;
+      my_ctg += (emit && (double)v > d);
+    }
+  }
+  my_len = warp_sum_ll(my_len);
+  my_ctg = warp_sum_ll(my_ctg);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd((unsigned long long*)&n_len[o], (unsigned long long)my_len);
+    atomicAdd((unsigned long long*)&n_ctg[o], (unsigned long long)my_ctg);
+  }
+}
+
+// N50 of the positive entries of vals[lo, hi): one block per segment
+__global__ void n50_kernel(const int64_t* __restrict__ vals, const int64_t* __restrict__ seg_lo,
+                           const int64_t* __restrict__ seg_hi, int64_t* __restrict__ out) {
+  __shared__ long long s_red[32];
+  __shared__ long long s_bcast;
+  const int64_t lo = seg_lo[blockIdx.x], hi = seg_hi[blockIdx.x];
+  auto block_sum = [&](long long v) -> long long {
+    v = warp_sum_ll(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long t = 0;
+      for (int j = 0; j < (int)(blockDim.x >> 5); j++) t += s_red[j];
+      s_bcast = t;
+    }
+    __syncthreads();
+    return s_bcast;
+  };
+  long long part = 0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) part += vals[i] > 0 ? vals[i] : 0;
+  const long long total = block_sum(part);
+  long long best = 0;
+  if (total > 0) {
+    for (int bit = 40; bit >= 0; bit--) {
+      const long long cand = best | (1ll << bit);
+      part = 0;
+      for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) part += vals[i] >= cand ? vals[i] : 0;
+      const long long s = block_sum(part);
+      if (2 * s >= total) best = cand;
+    }
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = best;
+}
+
+extern "C" {
+
+int gci_scan(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int32_t flank_len, int64_t* n_intervals) {
+  if (!ctx || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  Track& t = ctx->track[track];
+  if (!t.allocated) return ctx->fail(GCI_E_ARG, "gci_scan: track %d holds no depth", track);
+  if (!t.flags_valid || t.flags_lo != lo || t.flags_hi != hi) GCI_TRY(gci_compute_flags(ctx, track, lo, hi));
+  ctx->stage_begin(GCI_ST_RUNS);
+  // owners = selected contigs in header order
+  std::vector<int32_t> owner_of(ctx->n_contigs, -1);
+  int64_t n_owners = 0;
+  for (int c = 0; c < ctx->n_contigs; c++)
+    if (ctx->selected[c]) owner_of[c] = (int32_t)n_owners++;
+  t.n_owners = n_owners;
+  t.owners_are_windows = false;
+  GCI_TRY(ctx->ensure(t.win_contig, sizeof(int32_t) * (size_t)std::max<int64_t>(1, n_owners)));
+  GCI_TRY(ctx->ensure(t.win_lo, sizeof(int64_t) * (size_t)std::max<int64_t>(1, n_owners)));
+  GCI_TRY(ctx->ensure(t.win_hi, sizeof(int64_t) * (size_t)std::max<int64_t>(1, n_owners)));
+  GCI_TRY(gci_h2d(ctx, ctx->misc, owner_of.data(), sizeof(int32_t) * ctx->n_contigs));
+  std::vector<int64_t> h_lo(n_owners), h_hi(n_owners);
+  if (n_owners) {
+    genome_windows_kernel<<<(ctx->n_contigs + 127) / 128, 128, 0, ctx->stream>>>(
+        ctx->n_contigs, ctx->d_len.as<int64_t>(), ctx->d_selected.as<uint8_t>(), ctx->d_tile_off.as<int64_t>(),
+        t.flags.as<uint32_t>(), flank_len, t.win_contig.as<int32_t>(), t.win_lo.as<int64_t>(), t.win_hi.as<int64_t>(),
+        ctx->misc.as<int32_t>());
+    GCI_LAUNCH_CHECK(ctx);
+    GCI_TRY(gci_d2h(ctx, h_lo.data(), t.win_lo.p, sizeof(int64_t) * n_owners));
+    GCI_TRY(gci_d2h(ctx, h_hi.data(), t.win_hi.p, sizeof(int64_t) * n_owners));
+    GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  int rc = extract_runs(ctx, t, h_lo, h_hi, n_intervals);
+  ctx->stage_end();
+  return rc;
+}
+
+int gci_scan_windows(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int64_t n_windows, const int32_t* contig,
+                     const int64_t* start, const int64_t* end, int64_t* n_intervals) {
+  if (!ctx || track < 0 || track >= GCI_MAX_TRACKS || n_windows < 0) return GCI_E_ARG;
+  if (n_windows && (!contig || !start || !end)) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  Track& t = ctx->track[track];
+  if (!t.allocated) return ctx->fail(GCI_E_ARG, "gci_scan_windows: track %d holds no depth", track);
+  if (!t.flags_valid || t.flags_lo != lo || t.flags_hi != hi) GCI_TRY(gci_compute_flags(ctx, track, lo, hi));
+  // depth[start:end] is a Python slice (GCI.py:627): normalise against the contig length
+  std::vector<int32_t> c2(n_windows);
+  std::vector<int64_t> lo2(n_windows), hi2(n_windows);
+  for (int64_t i = 0; i < n_windows; i++) {
+    const int32_t c = contig[i];
+    if (c < 0 || c >= ctx->n_contigs || !ctx->selected[c])
+      return ctx->fail(GCI_E_ARG, "window %lld: contig %d is not selected", (long long)i, c);
+    const int64_t L = ctx->len[c];
+    auto norm = [L](int64_t v) {
+      if (v < 0) { v += L; if (v < 0) v = 0; } else if (v >= L) v = L;
+      return v;
+    };
+    c2[i] = c;
+    lo2[i] = norm(start[i]);
+    hi2[i] = std::max(lo2[i], norm(end[i]));
+  }
+  t.raw_lo.assign(start, start + n_windows);
+  t.raw_hi.assign(end, end + n_windows);
+  ctx->stage_begin(GCI_ST_RUNS);
+  t.n_owners = n_windows;
+  t.owners_are_windows = true;
+  GCI_TRY(gci_h2d(ctx, t.win_contig, c2.data(), sizeof(int32_t) * n_windows));
+  GCI_TRY(gci_h2d(ctx, t.win_lo, lo2.data(), sizeof(int64_t) * n_windows));
+  GCI_TRY(gci_h2d(ctx, t.win_hi, hi2.data(), sizeof(int64_t) * n_windows));
+  int rc = extract_runs(ctx, t, lo2, hi2, n_intervals);
+  ctx->stage_end();
+  return rc;
+}
+
+int gci_load_intervals(gci_ctx* ctx, int32_t track, int64_t n_owners, const int32_t* contig, const int64_t* owner_off,
+                       const int32_t* start, const int32_t* end) {
+  if (!ctx || track < 0 || track >= GCI_MAX_TRACKS || n_owners < 0 || !owner_off) return GCI_E_ARG;
+  if (n_owners && !contig) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  Track& t = ctx->track[track];
+  const int64_t n = owner_off[n_owners];
+  if (n && (!start || !end)) return GCI_E_ARG;
+  for (int64_t o = 0; o < n_owners; o++)
+    if (contig[o] < 0 || contig[o] >= ctx->n_contigs) return ctx->fail(GCI_E_ARG, "bad contig in gci_load_intervals");
+  t.n_owners = n_owners;
+  t.n_intervals = n;
+  t.owners_are_windows = false;
+  std::vector<int64_t> zero(std::max<int64_t>(1, n_owners), 0);
+  GCI_TRY(gci_h2d(ctx, t.win_contig, contig, sizeof(int32_t) * n_owners));
+  GCI_TRY(gci_h2d(ctx, t.win_lo, zero.data(), sizeof(int64_t) * n_owners));
+  GCI_TRY(gci_h2d(ctx, t.win_hi, zero.data(), sizeof(int64_t) * n_owners));
+  GCI_TRY(gci_h2d(ctx, t.owner_off, owner_off, sizeof(int64_t) * (n_owners + 1)));
+  GCI_TRY(gci_h2d(ctx, t.iv_start, start, sizeof(int32_t) * n));
+  GCI_TRY(gci_h2d(ctx, t.iv_end, end, sizeof(int32_t) * n));
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return GCI_OK;
+}
+
+int gci_score_terms(gci_ctx* ctx, int32_t track, double dist_percent, int32_t flank_len, int64_t* n50,
+                    int64_t* n_ctg, int64_t cap_lengths, int64_t* lengths, int64_t* lengths_off) {
+  if (!ctx || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  Track& t = ctx->track[track];
+  const int64_t no = t.n_owners;
+  if (no <= 0) return ctx->fail(GCI_E_ARG, "gci_score_terms: no scan on track %d", track);
+  // per-owner [S, E) and dist (GCI.py:505-508, :629-634)
+  std::vector<int32_t> wc(no);
+  std::vector<int64_t> wl(no), wh(no), S(no), E(no);
+  std::vector<double> dist(no);
+  GCI_TRY(gci_d2h(ctx, wc.data(), t.win_contig.p, sizeof(int32_t) * no));
+  GCI_TRY(gci_d2h(ctx, wl.data(), t.win_lo.p, sizeof(int64_t) * no));
+  GCI_TRY(gci_d2h(ctx, wh.data(), t.win_hi.p, sizeof(int64_t) * no));
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int64_t o = 0; o < no; o++) {
+    if (t.owners_are_windows) {
+      // complement / merge use the region bounds as given (GCI.py:629-634), only the depth slice is
+      // normalised (:627)
+      S[o] = t.raw_lo[o];
+      E[o] = t.raw_hi[o];
+      dist[o] = (double)(E[o] - S[o]) * dist_percent;       // targets_length = {target: exp_n50}
+    } else {
+      const int64_t L = ctx->len[wc[o]];
+      S[o] = flank_len;
+      E[o] = L - flank_len;
+      dist[o] = (double)L * dist_percent;
+    }
+  }
+  ctx->stage_begin(GCI_ST_SCORE);
+  const int64_t n_slots = t.n_intervals + no;
+  DevBuf &dS = ctx->tmp[0], &dE = ctx->tmp[1], &dD = ctx->tmp[2], &gaps = ctx->tmp[3], &nlen = ctx->tmp[4],
+         &nctg = ctx->tmp[5], &seg = ctx->tmp[6], &n50d = ctx->tmp[7];
+  GCI_TRY(gci_h2d(ctx, dS, S.data(), 8 * no));
+  GCI_TRY(gci_h2d(ctx, dE, E.data(), 8 * no));
+  GCI_TRY(gci_h2d(ctx, dD, dist.data(), 8 * no));
+  GCI_TRY(ctx->ensure(gaps, 8 * (size_t)n_slots));
+  GCI_TRY(ctx->ensure(nlen, 8 * (size_t)no));
+  GCI_TRY(ctx->ensure(nctg, 8 * (size_t)no));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(nlen.p, 0, 8 * no, ctx->stream));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(nctg.p, 0, 8 * no, ctx->stream));
+  complement_kernel<<<(unsigned)no, 256, 0, ctx->stream>>>(no, t.owner_off.as<int64_t>(), t.iv_start.as<int32_t>(),
+                                                           t.iv_end.as<int32_t>(), dS.as<int64_t>(), dE.as<int64_t>(),
+                                                           dD.as<double>(), gaps.as<int64_t>(), nlen.as<int64_t>(),
+                                                           nctg.as<int64_t>());
+  GCI_LAUNCH_CHECK(ctx);
+  // segments for the N50 kernel: one per owner plus one over everything (the Genome row)
+  std::vector<int64_t> h_off(no + 1);
+  GCI_TRY(gci_d2h(ctx, h_off.data(), t.owner_off.p, 8 * (no + 1)));
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<int64_t> seg_h(2 * (no + 1));
+  for (int64_t o = 0; o < no; o++) {
+    seg_h[o] = h_off[o] + o;
+    seg_h[no + 1 + o] = h_off[o + 1] + o + 1;
+  }
+  seg_h[no] = 0;
+  seg_h[2 * no + 1] = n_slots;
+  GCI_TRY(gci_h2d(ctx, seg, seg_h.data(), 8 * seg_h.size()));
+  GCI_TRY(ctx->ensure(n50d, 8 * (size_t)(no + 1)));
+  n50_kernel<<<(unsigned)(no + 1), 256, 0, ctx->stream>>>(gaps.as<int64_t>(), seg.as<int64_t>(),
+                                                          seg.as<int64_t>() + no + 1, n50d.as<int64_t>());
+  GCI_LAUNCH_CHECK(ctx);
+  ctx->stage_end();
+  std::vector<int64_t> h_nctg(no), h_gaps(n_slots);
+  if (n50) GCI_TRY(gci_d2h(ctx, n50, n50d.p, 8 * (no + 1)));
+  GCI_TRY(gci_d2h(ctx, h_nctg.data(), nctg.p, 8 * no));
+  GCI_TRY(gci_d2h(ctx, h_gaps.data(), gaps.p, 8 * n_slots));
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_ctg) {
+    int64_t all = 0;
+    for (int64_t o = 0; o < no; o++) { n_ctg[o] = h_nctg[o]; all += h_nctg[o]; }
+    n_ctg[no] = all;
+  }
+  // compact the emitted lengths per owner, in position order (zero slots were not emitted, except the
+  // unconditional [E - S] entry of an owner without intervals)
+  int rc = GCI_OK;
+  if (lengths_off || lengths) {
+    int64_t k = 0;
+    for (int64_t o = 0; o < no; o++) {
+      if (lengths_off) lengths_off[o] = k;
+      const int64_t a = h_off[o] + o, b = h_off[o + 1] + o + 1;
+      const bool empty = (h_off[o + 1] == h_off[o]);
+      for (int64_t i = a; i < b; i++) {
+        if (h_gaps[i] > 0 || empty) {
+          if (lengths) {
+            if (k >= cap_lengths) { rc = ctx->fail(GCI_E_ARG, "lengths buffer too small"); break; }
+            lengths[k] = h_gaps[i];
+          }
+          k++;
+        }
+      }
+      if (rc != GCI_OK) break;
+    }
+    if (lengths_off) lengths_off[no] = k;
+  }
+  return rc;
+}
+
+}  // extern "C"

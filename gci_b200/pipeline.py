@@ -1,0 +1,567 @@
+"""Host-side mirror of the reference's hot-path interface (GCI.py) on top of libgci_cuda.so.
+
+Same function names, argument meaning, printed progress lines, output files and `sys.exit`
+texts as the reference, so a `GCI.py` user can switch over:
+
+    filter()                 GCI.py:172-312      -> gci_filter + gci_depth
+    write_depth()            GCI.py:99-143       -> gci_depth_text + gzip members
+    merge_gaps_depths()      GCI.py:315-329      -> gci_mask_gaps
+    merge_two_type_depth()   GCI.py:332-353      -> gci_merge_max
+    collapse_depth_range()   GCI.py:356-390      -> gci_scan / gci_scan_windows
+    merge_depth()            GCI.py:393-419
+    compute_index()          GCI.py:522-657      -> gci_score_terms (+ log2/round on the host)
+    GCI()                    GCI.py:897-1028
+
+Depth dictionaries are `DeviceDepths` mappings whose arrays live on the GPU and are fetched on
+access.  File arguments may be paths (decoded by gci_b200.io) or already-decoded
+`AlnTable` / `PafTable` objects.  Nothing here computes on the CPU what the library computes on
+the GPU, and nothing imports `oracle/`.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from collections.abc import Mapping
+from math import log2
+
+import numpy as np
+
+from . import io as gio
+from ._lib import Context, NO_FLAGS, TRACK_HIFI, TRACK_NANO, TRACK_MERGED
+from .records import AlnTable, PafTable
+
+TEXT_CHUNK = 1 << 24      # positions per gci_depth_text call
+
+
+# ------------------------------------------------------------------------------------------------
+# session
+# ------------------------------------------------------------------------------------------------
+class Session:
+    """One GPU context plus the contig table it was configured with."""
+
+    def __init__(self, device: int = 0):
+        self.ctx = Context(device)
+        self.names = None
+        self.lengths = None
+        self.selected = None
+        self.scan_hint = None          # (lo, hi): thresholds the driver will scan with -> fused flags
+        self._n_runs_key = None
+
+    def close(self):
+        self.ctx.close()
+
+    def configure(self, names, lengths, chrs_list):
+        names = list(names)
+        lengths = [int(x) for x in lengths]
+        selected = [(n in chrs_list) if len(chrs_list) > 0 else True for n in names]
+        if self.names == names and self.lengths == lengths and self.selected == selected:
+            return
+        self.ctx.set_contigs(lengths, selected)
+        order = sorted(range(len(names)), key=lambda i: names[i])
+        rank = np.empty(len(names), np.int32)
+        rank[order] = np.arange(len(names), dtype=np.int32)
+        self.ctx.set_name_rank(rank)
+        self.names, self.lengths, self.selected = names, lengths, selected
+        self._n_runs_key = None
+
+    @property
+    def index(self):
+        return {n: i for i, n in enumerate(self.names)}
+
+    def selected_names(self):
+        return [n for n, s in zip(self.names, self.selected) if s]
+
+    def set_n_runs(self, Ns_bed):
+        key = repr(sorted((k, tuple(v)) for k, v in Ns_bed.items()))
+        if key == self._n_runs_key:
+            return
+        idx = self.index
+        c, s, e = [], [], []
+        for target, segments in Ns_bed.items():
+            if target in idx:
+                for seg in segments:
+                    c.append(idx[target]); s.append(seg[0]); e.append(seg[1])
+        self.ctx.set_n_runs(c, s, e)
+        self._n_runs_key = key
+
+
+_default_session = None
+
+
+def default_session() -> Session:
+    global _default_session
+    if _default_session is None:
+        _default_session = Session(int(os.environ.get("GCI_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
+    return _default_session
+
+
+def set_default_session(s):
+    global _default_session
+    _default_session = s
+
+
+class DeviceDepths(Mapping):
+    """dict[contig -> np.ndarray(int64)] whose values live in a GPU depth track."""
+
+    def __init__(self, session: Session, track: int):
+        self.session, self.track = session, track
+        self._names = session.selected_names()
+
+    def __getitem__(self, name):
+        if name not in self._names:
+            raise KeyError(name)
+        return self.session.ctx.fetch_depth(self.track, self.session.index[name]).astype(np.int64)
+
+    def fetch_i32(self, name):
+        return self.session.ctx.fetch_depth(self.track, self.session.index[name])
+
+    def __iter__(self):
+        return iter(self._names)
+
+    def __len__(self):
+        return len(self._names)
+
+    def mean_depth(self):
+        """np.mean over all contigs (GCI.py:862-868) from the per-contig sums kept on the GPU."""
+        sums = self.session.ctx.depth_sums(self.track)
+        tot_len = sum(l for l, s in zip(self.session.lengths, self.session.selected) if s)
+        return float(sums.sum()) / tot_len if tot_len else float("nan")
+
+
+class DeviceBed(dict):
+    """dict[contig -> [(start, end), ...]] that remembers which GPU track holds the same intervals."""
+
+    session = None
+    track = None
+    scan_id = None
+
+
+def _adopt(depths, session=None, track=TRACK_HIFI) -> DeviceDepths:
+    """Host dict of depth arrays (e.g. parsed from a .depth.gz) -> GPU track."""
+    if isinstance(depths, DeviceDepths):
+        return depths
+    session = session or default_session()
+    names = list(depths.keys())
+    lengths = [len(depths[n]) for n in names]
+    session.configure(names, lengths, [])
+    for i, n in enumerate(names):
+        session.ctx.load_depth(track, i, np.ascontiguousarray(depths[n], dtype=np.int32))
+    return DeviceDepths(session, track)
+
+
+# ------------------------------------------------------------------------------------------------
+# L3: depth file
+# ------------------------------------------------------------------------------------------------
+def write_depth(directory='.', prefix='GCI', depths={}, threads=1):
+    """GCI.py:99-143: `>name` then one decimal per line, gzip (multi-member)."""
+    depths = _adopt(depths)
+    ctx = depths.session.ctx
+    idx = depths.session.index
+
+    def pieces():
+        for target in depths.keys():
+            c = idx[target]
+            n = int(depths.session.lengths[c])
+            head = f'>{target}\n'.encode('utf-8')
+            if n == 0:
+                yield head
+            for first in range(0, n, TEXT_CHUNK):
+                txt = ctx.depth_text(depths.track, c, first, min(TEXT_CHUNK, n - first)).tobytes()
+                yield (head + txt) if first == 0 else txt
+
+    gio.write_depth_gz(f'{directory}/{prefix}.depth.gz', pieces(), threads)
+
+
+# ------------------------------------------------------------------------------------------------
+# L2 + L3: filter
+# ------------------------------------------------------------------------------------------------
+def _load_inputs(paf_files, bam_files):
+    """Decode / collect the files of one read type.  Returns (names, lengths, paf tables, bam tables, n_reads)."""
+    intern = {}
+    bams, pafs = [], []
+    names = lengths = None
+    for f in bam_files:
+        if isinstance(f, AlnTable):
+            t = f
+            n, l = getattr(f, "contig_names", None), getattr(f, "contig_lengths", None)
+            if n is None:
+                raise ValueError("in-memory AlnTable needs .contig_names / .contig_lengths")
+        else:
+            n, l, t = gio.read_bam(f, intern)
+        if names is None:
+            names, lengths = list(n), [int(x) for x in l]     # header of the first BAM (GCI.py:201)
+        bams.append(t)
+    index = {n: i for i, n in enumerate(names)}
+    for f in paf_files:
+        pafs.append(f if isinstance(f, PafTable) else gio.read_paf(f, index, intern))
+    n_reads = len(intern)
+    for t in bams + pafs:
+        if t.n_records:
+            n_reads = max(n_reads, int(t.read_id.max()) + 1)
+    return names, lengths, pafs, bams, n_reads
+
+
+def filter(paf_files=[], bam_files=[], prefix='GCI', map_qual=30, mq_cutoff=50, iden_percent=0.9, clip_percent=0.1,
+           ovlp_percent=0.9, flank_len=15, directory='.', force=False, log_reads_type='', chrs_list=[], threads=1,
+           session=None, write=True):
+    """GCI.py:172-312.  Returns (depths, targets_length)."""
+    if os.path.exists(f'{directory}/{prefix}.depth.gz') and force == False:
+        sys.exit(f'ERROR!!! The file "{directory}/{prefix}.depth.gz" exists\nPlease use "-f" or "--force" to rewrite')
+    print(f'Filtering {log_reads_type} alignment files ...')
+    session = session or default_session()
+    ctx = session.ctx
+    names, lengths, pafs, bams, n_reads = _load_inputs(paf_files, bam_files)
+    session.configure(names, lengths, chrs_list)
+    targets_length = {n: l for n, l, s in zip(names, lengths, session.selected) if s}
+    track = TRACK_NANO if log_reads_type == 'ONT' else TRACK_HIFI
+
+    ctx.reads_begin(n_reads)
+    for t in pafs:                       # files = paf_lines + samfile_dicts (GCI.py:272)
+        ctx.upload_paf(t)
+    for t in bams:
+        ctx.upload_bam(t)
+    ctx.filter(map_qual, mq_cutoff, iden_percent, clip_percent, ovlp_percent)
+    lo, hi = session.scan_hint if session.scan_hint is not None else (NO_FLAGS, NO_FLAGS)
+    ctx.depth(track, flank_len, lo, hi)
+    depths = DeviceDepths(session, track)
+
+    print(f'Filtering {log_reads_type} alignment files done!!!')
+    print(f'Writing depths into "{directory}/{prefix}.depth.gz" ...')
+    if write:
+        write_depth(directory, prefix, depths, threads)
+    print(f'Writing depths done!!!\n\n')
+    return depths, targets_length
+
+
+def merge_gaps_depths(depths={}, Ns_bed=None):
+    """GCI.py:315-329."""
+    if Ns_bed != None:
+        depths = _adopt(depths)
+        depths.session.set_n_runs(Ns_bed)
+        depths.session.ctx.mask_gaps(depths.track)
+    return depths
+
+
+def merge_two_type_depth(hifi_depths={}, nano_depths={}, prefix='GCI_two_type', directory='.', force=False, threads=1,
+                         write=True):
+    """GCI.py:332-353."""
+    print('Merging HiFi and ONT depth file ...')
+    if os.path.exists(f'{directory}/{prefix}.depth.gz') and force == False:
+        sys.exit(f'ERROR!!! The file "{directory}/{prefix}.depth.gz" exists\nPlease use "-f" or "--force" to rewrite')
+    if not (isinstance(hifi_depths, DeviceDepths) and isinstance(nano_depths, DeviceDepths)
+            and hifi_depths.session is nano_depths.session):
+        raise TypeError("merge_two_type_depth expects the depth mappings returned by filter() of one session")
+    session = hifi_depths.session
+    lo, hi = session.scan_hint if session.scan_hint is not None else (NO_FLAGS, NO_FLAGS)
+    session.ctx.merge_max(hifi_depths.track, nano_depths.track, TRACK_MERGED, lo, hi)
+    merged = DeviceDepths(session, TRACK_MERGED)
+    if write:
+        write_depth(directory, prefix, merged, threads)
+    print('Merging HiFi and ONT depth file done!!!\n\n')
+    return merged
+
+
+# ------------------------------------------------------------------------------------------------
+# L4: gap scan
+# ------------------------------------------------------------------------------------------------
+_scan_counter = [0]
+
+
+def collapse_depth_range(depths={}, leftmost=-1, rightmost=0, flank_len=15, start_pos=0):
+    """GCI.py:356-390 over every contig of `depths` (start_pos must be 0 here; the regions variant
+    goes through `_collapse_regions`)."""
+    if start_pos != 0:
+        raise ValueError("use regions scoring for start_pos != 0")
+    depths = _adopt(depths)
+    session, ctx = depths.session, depths.session.ctx
+    ctx.scan(depths.track, leftmost, rightmost, flank_len)
+    owners = session.selected_names()
+    s, e, off = ctx.fetch_intervals(depths.track, len(owners))
+    bed = DeviceBed()
+    sl, el = s.tolist(), e.tolist()
+    for o, name in enumerate(owners):
+        a, b = int(off[o]), int(off[o + 1])
+        bed[name] = list(zip(sl[a:b], el[a:b]))
+    _scan_counter[0] += 1
+    bed.session, bed.track, bed.scan_id = session, depths.track, _scan_counter[0]
+    session.__dict__.setdefault("_last_scan", {})[depths.track] = (bed.scan_id, len(s))
+    return bed
+
+
+def merge_depth(depths={}, prefix='GCI', threshold=0, flank_len=15, directory='.', force=False, log_reads_type=''):
+    """GCI.py:393-419."""
+    print(f'Getting {log_reads_type} issues bed file detected by GCI ...')
+    if os.path.exists(f'{directory}/{prefix}.{threshold}.depth.bed') and force == False:
+        sys.exit(f'ERROR!!! The file "{directory}/{prefix}.{threshold}.depth.bed" exists\nPlease use "-f" or "--force" to rewrite')
+    merged_depths_bed = collapse_depth_range(depths, -1, threshold, flank_len, 0)
+    with open(f'{directory}/{prefix}.{threshold}.depth.bed', 'w') as f:
+        for target, segments in merged_depths_bed.items():
+            f.write(''.join(f'{target}\t{s}\t{e}\n' for s, e in segments))
+    print(f'Getting {log_reads_type} issues bed file done!!!\n\n')
+    return merged_depths_bed
+
+
+# ------------------------------------------------------------------------------------------------
+# L5: score
+# ------------------------------------------------------------------------------------------------
+def compute_n50(lengths=[]):
+    """GCI.py:465-480 for the tiny host-side lists (contig lengths, region lengths)."""
+    n50 = 0
+    lengths = sorted((int(x) for x in lengths), reverse=True)
+    total = sum(lengths)
+    cum = 0
+    for x in lengths:
+        cum += x
+        if cum >= total / 2:
+            n50 = x
+            break
+    return n50
+
+
+def _gci(obs_n50, exp_n50, obs_num_ctg, exp_num_ctg):
+    if obs_num_ctg == 0:                                          # GCI.py:601-604
+        return 0
+    return round(100 * log2(obs_n50 / exp_n50 + 1) / log2(obs_num_ctg / exp_num_ctg + 1), 4)
+
+
+def _terms_for_bed(bed, targets_length, dist_percent, flank_len, session):
+    """(n50[], n_ctg[]) per contig of targets_length + the all-contigs entry, from the GPU."""
+    session = getattr(bed, "session", None) or session or default_session()
+    ctx = session.ctx
+    owners = list(targets_length.keys())
+    last = session.__dict__.get("_last_scan", {})
+    if isinstance(bed, DeviceBed) and bed.track is not None and last.get(bed.track, (None,))[0] == bed.scan_id \
+            and owners == session.selected_names():
+        track, n_iv = bed.track, last[bed.track][1]
+    else:
+        # intervals from elsewhere (a BED file): load them next to track 0's depth
+        if session.names is None or any(t not in session.index for t in owners):
+            session.configure(owners, [targets_length[t] for t in owners], [])
+        idx = session.index
+        off = np.concatenate([[0], np.cumsum([len(bed[t]) for t in owners])])
+        flat = [seg for t in owners for seg in bed[t]]
+        track, n_iv = TRACK_HIFI, len(flat)
+        ctx.load_intervals(track, [idx[t] for t in owners], off, [s for s, _ in flat], [e for _, e in flat])
+        session.__dict__.setdefault("_last_scan", {})[track] = (None, n_iv)
+    n50, nctg, _, _ = ctx.score_terms(track, len(owners), n_iv, dist_percent, flank_len)
+    return n50, nctg
+
+
+def compute_index(targets_length={}, prefix='GCI', directory='.', force=False, merged_depths_bed_list=[], type_list=[],
+                  flank_len=15, dist_percent=0.005, regions_bed={}, depths_list=[], threshold=0, chrs_list=[],
+                  session=None):
+    """GCI.py:522-657."""
+    if os.path.exists(f'{directory}/{prefix}.gci') and force == False:
+        sys.exit(f'ERROR!!! The file "{directory}/{prefix}.gci" exists\nPlease use "-f" or "--force" to rewrite')
+    with open(f'{directory}/{prefix}.gci', 'w') as f:
+        pass
+    if len(regions_bed) > 0:
+        if os.path.exists(f'{directory}/{prefix}.regions.gci') and force == False:
+            sys.exit(f'ERROR!!! The file "{directory}/{prefix}.regions.gci" exists\nPlease use "-f" or "--force" to rewrite')
+        with open(f'{directory}/{prefix}.regions.gci', 'w') as f:
+            f.write('Chromosome\tStart\tEnd\t' + '\t'.join(type_list) + '\n')
+
+    print('Computing Theoretical minimum N50 and contigs number ...')
+    all_label = 'Genome' if len(chrs_list) == 0 else 'All_chromosomes'
+    exp_lengths = [length for length in targets_length.values()]
+    exp_n50_all = compute_n50(exp_lengths)
+    print('Computing Theoretical minimum N50 and contigs number done!!!')
+
+    for i, merged_depths_bed in enumerate(merged_depths_bed_list):
+        print(f'Computing Curated N50 and contigs number for {type_list[i]} ...')
+        n50, nctg = _terms_for_bed(merged_depths_bed, targets_length, dist_percent, flank_len, session)
+        print(f'Computing Curated N50 and contigs number for {type_list[i]} done!!!')
+
+        print(f'Writing results to {directory}/{prefix}.gci ...')
+        with open(f'{directory}/{prefix}.gci', 'a') as f:
+            f.write(f'{type_list[i]}:\n')
+            f.write('Chromosome\tTheoretical maximum N50\tCurated N50\tTheoretical minimum contigs number\tCurated contigs number\tGCI score\n')
+            for o, (target, length) in enumerate(targets_length.items()):
+                obs_n50, obs_num_ctg = int(n50[o]), int(nctg[o])
+                f.write(f'{target}\t{length}\t{obs_n50}\t1\t{obs_num_ctg}\t{_gci(obs_n50, length, obs_num_ctg, 1)}\n')
+            obs_n50, obs_num_ctg = int(n50[-1]), int(nctg[-1])
+            gci = _gci(obs_n50, exp_n50_all, obs_num_ctg, len(exp_lengths))
+            f.write(f'{all_label}\t{exp_n50_all}\t{obs_n50}\t{len(exp_lengths)}\t{obs_num_ctg}\t{gci}\n')
+            f.write('-' * 136 + '\n\n\n')
+        print(f'Writing results to {directory}/{prefix}.gci done!!!\n\n')
+
+    if len(regions_bed) > 0:
+        print('Computing GCI scores for regions ...')
+        windows = [(target, seg[0], seg[1]) for target, segments in regions_bed.items() for seg in segments]
+        region_all_lengths = []
+        for target, start, end in windows:
+            if end - start > 0:
+                region_all_lengths.append(end - start)
+            else:
+                print(f'Warning!!! The region "{target}:{start}-{end}" is not available', file=sys.stderr)
+        per_type = []
+        for depths in depths_list:
+            depths = _adopt(depths, session)
+            ses, ctx = depths.session, depths.session.ctx
+            idx = ses.index
+            n_iv = ctx.scan_windows(depths.track, [idx[t] for t, _, _ in windows], [s for _, s, _ in windows],
+                                    [e for _, _, e in windows], -1, threshold)
+            ses.__dict__.setdefault("_last_scan", {})[depths.track] = (None, n_iv)
+            per_type.append(ctx.score_terms(depths.track, len(windows), n_iv, dist_percent, 0)[:2])
+        with open(f'{directory}/{prefix}.regions.gci', 'a') as f:
+            for w, (target, start, end) in enumerate(windows):
+                gci = [_gci(int(n50[w]), end - start, int(nctg[w]), 1) for n50, nctg in per_type]
+                f.write(f'{target}\t{start}\t{end}\t' + '\t'.join(map(str, gci)) + '\n')
+            region_all_exp_n50 = compute_n50(region_all_lengths)
+            region_all_gci = [_gci(int(n50[-1]), region_all_exp_n50, int(nctg[-1]), len(region_all_lengths))
+                              for n50, nctg in per_type]
+            f.write('-' * 136 + '\n\n\n')
+            f.write(f'All_regions\t*\t*\t' + '\t'.join(map(str, region_all_gci)) + '\n')
+        print('Computing GCI scores for regions done!!!\n\n')
+
+
+# ------------------------------------------------------------------------------------------------
+# L1: driver
+# ------------------------------------------------------------------------------------------------
+def get_Ns_ref(reference=None, prefix='GCI', directory='.', force=False, _parsed=None):
+    """GCI.py:18-46."""
+    ids, Ns_bed = _parsed if _parsed is not None else _read_reference(reference)
+    if len(Ns_bed) > 0:
+        if os.path.exists(f'{directory}/{prefix}.gaps.bed') and force == False:
+            sys.exit(f'ERROR!!! The file "{directory}/{prefix}.gaps.bed" exists\nPlease use "-f" or "--force" to rewrite')
+        with open(f'{directory}/{prefix}.gaps.bed', 'w') as f:
+            for target, segments in Ns_bed.items():
+                for segment in segments:
+                    f.write(f'{target}\t{segment[0]}\t{segment[1]}\n')
+        return Ns_bed, f'{directory}/{prefix}.gaps.bed'
+    return None, None
+
+
+def _read_reference(reference):
+    if isinstance(reference, dict):          # in-memory: {"ids": [...], "gaps": {name: [(s,e)...]}}
+        return list(reference["ids"]), {k: list(v) for k, v in reference["gaps"].items() if len(v)}
+    return gio.read_fasta_gaps(reference)
+
+
+def _is_bam(f):
+    return isinstance(f, AlnTable) or (isinstance(f, str) and f.endswith('.bam'))
+
+
+def _header(f):
+    if isinstance(f, AlnTable):
+        return dict(zip(f.contig_names, (int(x) for x in f.contig_lengths)))
+    n, l = gio.read_bam_header(f)
+    return dict(zip(n, l))
+
+
+def GCI(hifi=[], nano=[], directory='.', prefix='GCI', map_qual=30, mq_cutoff=50, iden_percent=0.9, ovlp_percent=0.9,
+        clip_percent=0.1, flank_len=15, threshold=0, plot=False, depth_min=0.1, depth_max=4.0, window_size=50000,
+        image_type='png', force=False, dist_percent=0.005, reference=None, regions=None, chrs=None, threads=1,
+        session=None):
+    """GCI.py:897-1028 (plotting, `-p`, is outside the hot path and not provided)."""
+    chrs_list = []
+    if chrs != None:
+        chrs_list = chrs.strip().split(',')
+
+    regions_bed = {}
+    if regions != None:
+        if isinstance(regions, dict):
+            regions_bed = regions
+        elif os.path.exists(regions) and os.access(regions, os.R_OK):
+            regions_bed = gio.read_regions_bed(regions)
+        else:
+            sys.exit(f'ERROR!!! "{regions}" is not an available file')
+
+    if directory.endswith('/'):
+        directory = '/'.join(directory.split('/')[:-1])
+    if os.path.exists(directory):
+        if not os.access(directory, os.R_OK):
+            sys.exit(f'ERROR!!! The path "{directory}" is unable to read')
+        if not os.access(directory, os.W_OK):
+            sys.exit(f'ERROR!!! The path "{directory}" is unable to write')
+    else:
+        os.makedirs(directory)
+
+    if prefix.endswith('/'):
+        sys.exit(f'ERROR!!! The prefix "{prefix}" is not allowed')
+    if plot == True:
+        sys.exit('ERROR!!! Plotting (-p) is not part of the GPU hot path; run the reference\'s utility/plot_depth.py on the .depth.gz outputs')
+
+    parsed_ref = _read_reference(reference)
+    ref_refs = parsed_ref[0]
+    if len(chrs_list) > 0:
+        for i in chrs_list:
+            if i not in ref_refs:
+                sys.exit(f'ERROR!!! Chromosome "{i}" provided by `--chrs` is not in the reference')
+    if len(regions_bed) > 0:
+        for i in regions_bed.keys():
+            if i not in ref_refs:
+                sys.exit(f'ERROR!!! Chromosome "{i}" provided by `--regions` is not in the reference')
+    if len(chrs_list) > 0 and len(regions_bed) > 0:
+        if not all(i in chrs_list for i in regions_bed.keys()):
+            sys.exit(f'ERROR!!! Chromosomes in the regions bed file are inconsistent with the provided list of chromosomes\nPlease read the help message use "-h" or "--help"')
+    hifi_bam, hifi_paf, nano_bam, nano_paf = [], [], [], []
+    hifi_refs_lengths, nano_refs_lengths = {}, {}
+    if hifi != None:
+        for file in hifi:
+            if _is_bam(file):
+                hifi_bam.append(file)
+                hifi_refs_lengths = _header(file)
+            else:
+                hifi_paf.append(file)
+        if set(hifi_refs_lengths.keys()) != set(ref_refs):
+            sys.exit('ERROR!!! The targets in hifi alignment files are inconsistent with the reference file\nPlease check both hifi alignment files and the reference')
+    if nano != None:
+        for file in nano:
+            if _is_bam(file):
+                nano_bam.append(file)
+                nano_refs_lengths = _header(file)
+            else:
+                nano_paf.append(file)
+        if set(nano_refs_lengths.keys()) != set(ref_refs):
+            sys.exit('ERROR!!! The targets in ont alignment files are inconsistent with the reference file\nPlease check both ont alignment files and the reference')
+
+    print('Finding gaps ...')
+    Ns_bed, Ns_bed_file = get_Ns_ref(reference, prefix, directory, force, _parsed=parsed_ref)
+    if Ns_bed_file != None:
+        print(f'Finding gaps done!!! The gaps are in {Ns_bed_file}\n\n')
+    else:
+        print('Finding gaps done!!! Awesome! No gaps were found!\n\n')
+
+    session = session or default_session()
+    session.scan_hint = (-1, threshold)      # the depth kernels emit the issue flags in the same pass
+    common = dict(map_qual=map_qual, mq_cutoff=mq_cutoff, iden_percent=iden_percent, clip_percent=clip_percent,
+                  ovlp_percent=ovlp_percent, flank_len=flank_len, directory=directory, force=force,
+                  chrs_list=chrs_list, threads=threads, session=session)
+    try:
+        if nano == None:
+            depths, targets_length = filter(hifi_paf, hifi_bam, prefix, log_reads_type='HiFi', **common)
+            depths = merge_gaps_depths(depths, Ns_bed)
+            merged_depth_bed = merge_depth(depths, prefix, threshold, flank_len, directory, force, 'HiFi')
+            compute_index(targets_length, prefix, directory, force, [merged_depth_bed], ['HiFi'], flank_len, dist_percent,
+                          regions_bed, [depths], threshold, chrs_list, session=session)
+        elif hifi == None:
+            depths, targets_length = filter(nano_paf, nano_bam, prefix, log_reads_type='ONT', **common)
+            depths = merge_gaps_depths(depths, Ns_bed)
+            merged_depth_bed = merge_depth(depths, prefix, threshold, flank_len, directory, force, 'ONT')
+            compute_index(targets_length, prefix, directory, force, [merged_depth_bed], ['Nano'], flank_len, dist_percent,
+                          regions_bed, [depths], threshold, chrs_list, session=session)
+        else:
+            if set(hifi_refs_lengths.keys()) != set(nano_refs_lengths.keys()):
+                sys.exit(f'ERROR!!! The targets in hifi and nano alignment files are inconsistent\nPlease check the reference used in mapping both hifi and ont reads')
+            for target, length in hifi_refs_lengths.items():
+                if length != nano_refs_lengths[target]:
+                    sys.exit(f'ERROR!!! The element "{target}:{length}" in hifi alignment files are inconsistent with that in ont alignment files which is "{target}:{nano_refs_lengths[target]}"\nPlease check the reference used in mapping both hifi and ont reads')
+
+            hifi_depths, targets_length = filter(hifi_paf, hifi_bam, prefix + '_hifi', log_reads_type='HiFi', **common)
+            hifi_depths = merge_gaps_depths(hifi_depths, Ns_bed)
+            nano_depths, targets_length = filter(nano_paf, nano_bam, prefix + '_nano', log_reads_type='ONT', **common)
+            nano_depths = merge_gaps_depths(nano_depths, Ns_bed)
+            merged_two_type_depths = merge_two_type_depth(hifi_depths, nano_depths, prefix + '_two_type', directory, force, threads)
+            merged_two_type_depths = merge_gaps_depths(merged_two_type_depths, Ns_bed)
+
+            hifi_merged_depth_bed = merge_depth(hifi_depths, prefix + '_hifi', threshold, flank_len, directory, force, 'HiFi')
+            nano_merged_depth_bed = merge_depth(nano_depths, prefix + '_nano', threshold, flank_len, directory, force, 'ONT')
+            two_type_merged_depth_bed = merge_depth(merged_two_type_depths, prefix + '_two_type', threshold, flank_len, directory, force, 'two_types')
+            compute_index(targets_length, prefix, directory, force,
+                          [hifi_merged_depth_bed, nano_merged_depth_bed, two_type_merged_depth_bed],
+                          ['HiFi', 'Nano', 'HiFi + Nano'], flank_len, dist_percent, regions_bed,
+                          [hifi_depths, nano_depths, merged_two_type_depths], threshold, chrs_list, session=session)
+    finally:
+        session.scan_hint = None
+    print('GCI finished!!!\nBye!!!')

@@ -1,0 +1,158 @@
+/*
+ * libgci_cuda.so — C ABI of the B200-native GCI hot path
+ * (alignment filter -> per-base depth -> gap scan -> score terms).
+ *
+ * The reference (yeeus/GCI @ 455e19c7) is a single Python script with no FFI; the
+ * boundary this library sits behind is the set of Python functions of GCI.py that
+ * make up the hot path.  Each entry point below names the reference lines it
+ * replaces.  The Python host layer (gci_b200/pipeline.py) mirrors the reference's
+ * function signatures and calls these through ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (GCI_E_*); the message is
+ *     available from gci_last_error(ctx);
+ *   - the caller owns every host buffer, the library owns every device buffer
+ *     until gci_destroy; one host thread per context; all work is queued on one
+ *     CUDA stream per context and host-visible results are synchronised before
+ *     the call returns unless the name says `_async`;
+ *   - coordinates are 0-based; intervals half-open; per-contig coordinates are
+ *     int32 (contigs < 2^31), genome-wide offsets int64;
+ *   - there is NO CPU fallback: without a CUDA device gci_create fails.
+ */
+#ifndef GCI_CUDA_H
+#define GCI_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gci_ctx gci_ctx;
+
+enum {
+  GCI_OK = 0,
+  GCI_E_CUDA = -1,        /* a CUDA runtime call failed */
+  GCI_E_ARG = -2,         /* bad argument / call order */
+  GCI_E_NOMEM = -3,
+  GCI_E_REFERENCE_RAISES = -4 /* the reference would raise here (ZeroDivisionError / KeyError:
+                                 GCI.py:163, :165, :292) — details in gci_last_error */
+};
+
+#define GCI_MAX_TRACKS 3   /* depth tracks: 0 = HiFi, 1 = Nano, 2 = max(HiFi, Nano) */
+#define GCI_MAX_FILES 16
+#define GCI_NM_MISSING INT32_MIN
+
+/* stage ids for gci_stage_ms */
+enum {
+  GCI_ST_H2D = 0, GCI_ST_CIGAR = 1, GCI_ST_GATE = 2, GCI_ST_JOIN = 3, GCI_ST_BUCKET = 4,
+  GCI_ST_DEPTH = 5, GCI_ST_FLAGS = 6, GCI_ST_RUNS = 7, GCI_ST_MAX = 8, GCI_ST_MASK = 9,
+  GCI_ST_D2H = 10, GCI_ST_PAF = 11, GCI_ST_TEXT = 12, GCI_ST_SCORE = 13, GCI_ST_COUNT = 14
+};
+
+/* ---- context ------------------------------------------------------------------------ */
+int gci_version(void);
+int gci_create(int device, gci_ctx** out);
+void gci_destroy(gci_ctx* ctx);
+const char* gci_last_error(gci_ctx* ctx);
+/* run on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = the context's own */
+int gci_set_stream(gci_ctx* ctx, void* cuda_stream);
+int gci_sync(gci_ctx* ctx);
+/* pinned host memory so H2D/D2H copies run at PCIe speed */
+void* gci_host_alloc(uint64_t bytes);
+void gci_host_free(void* p);
+/* CUDA-event time of one stage accumulated since the last gci_stage_reset (synchronises) */
+int gci_stage_reset(gci_ctx* ctx);
+int gci_stage_ms(gci_ctx* ctx, int stage, double* ms, int64_t* launches);
+int64_t gci_kernel_launches(gci_ctx* ctx);       /* kernels launched by this context so far */
+int64_t gci_device_bytes(gci_ctx* ctx);          /* device memory currently owned */
+
+/* ---- contig table: GCI.py:201-207 (targets_length / depths keys, --chrs selection) -------- */
+/* lengths[n]; selected[n] (NULL = all): contigs named by --chrs; unselected contigs get no
+   depth storage and records on them are ignored like the reference's fetch() never sees them */
+int gci_set_contigs(gci_ctx* ctx, int32_t n, const int64_t* lengths, const uint8_t* selected);
+/* N-runs of the assembly: GCI.py:18-46 output, consumed by gci_mask_gaps */
+int gci_set_n_runs(gci_ctx* ctx, int64_t n, const int32_t* contig, const int64_t* start, const int64_t* end);
+
+/* ---- filter stage: one read type at a time ------------------------------------------------ */
+/* start a read set of `n_reads` interned read names; drops the previous set's records */
+int gci_reads_begin(gci_ctx* ctx, uint32_t n_reads);
+/* one BAM file decoded to columns (GCI.py:150-166 touches exactly these).  Files are joined in
+   upload order; the host layer uploads PAF tables first (GCI.py:272). */
+int gci_upload_bam(gci_ctx* ctx, int64_t n_records, const int32_t* ref_id, const int32_t* ref_start,
+                   const uint8_t* mapq, const uint16_t* flag, const int32_t* nm, const int32_t* qlen,
+                   const uint32_t* read_id, const uint64_t* cigar_off, const uint32_t* cigar,
+                   int64_t n_ops);
+/* one PAF file as columns (GCI.py:218-229); name_rank[n_contigs] = rank of each contig name under
+   Python str ordering (tie-break of GCI.py:252), set once per context */
+int gci_set_name_rank(gci_ctx* ctx, const int32_t* name_rank);
+int gci_upload_paf(gci_ctx* ctx, int64_t n_lines, const uint32_t* read_id, const int32_t* qlen,
+                   const int32_t* qstart, const int32_t* qend, const int32_t* ref_id,
+                   const int32_t* tstart, const int32_t* tend, const int32_t* nmatch,
+                   const int32_t* alnlen, const int32_t* mapq);
+/* a file already reduced to one (contig,start,end,qlen) per read on the host (e.g. a PAF leg run
+   elsewhere, or survivors exchanged between GPUs); highq marks reads for the high-quality set */
+int gci_upload_table(gci_ctx* ctx, int64_t n, const uint32_t* read_id, const int32_t* ref_id,
+                     const int32_t* start, const int32_t* end, const int32_t* qlen,
+                     const uint8_t* highq);
+/* read_sam gates (GCI.py:146-169), PAF election (:211-254), last-record-wins dedup (:166, :269)
+   and the cross-file join (:272-301).  n_survivors = len(file1). */
+int gci_filter(gci_ctx* ctx, int32_t map_qual, int32_t mq_cutoff, double iden_percent,
+               double clip_percent, double ovlp_percent, int64_t* n_survivors);
+/* survivors as (read_id, contig, start, end) in read_id order; pass NULL pointers to get the count */
+int gci_fetch_survivors(gci_ctx* ctx, int64_t cap, uint32_t* read_id, int32_t* contig, int32_t* start,
+                        int32_t* end, int64_t* n);
+/* per-file winner tables after gci_filter (for multi-GPU exchange and tests): for file f, entries
+   (read_id, contig, start, end, qlen, highq) of reads present in that file */
+int gci_fetch_file_table(gci_ctx* ctx, int32_t file, int64_t cap, uint32_t* read_id, int32_t* contig,
+                         int32_t* start, int32_t* end, int32_t* qlen, uint8_t* highq, int64_t* n);
+
+/* ---- depth stage -------------------------------------------------------------------------- */
+/* depths[target][start+fl : end-fl+1] += 1 for every survivor (GCI.py:302-306, Python slice
+   semantics) into depth track `track`; also produces the issue flags for (lo < depth <= hi) so a
+   following gci_scan with the same thresholds does not re-read the depth array.  Pass
+   lo = hi = INT32_MIN to skip the fused flags. */
+int gci_depth(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo, int32_t hi);
+/* depths[target][s:e] = 0 over the N-runs (GCI.py:315-329), in place */
+int gci_mask_gaps(gci_ctx* ctx, int32_t track);
+/* element-wise max of two tracks (GCI.py:350) */
+int gci_merge_max(gci_ctx* ctx, int32_t track_a, int32_t track_b, int32_t track_out, int32_t lo, int32_t hi);
+/* resume path (utility/GCI_score.py:11-39): load one contig's depth from the host */
+int gci_load_depth(gci_ctx* ctx, int32_t track, int32_t contig, const int32_t* depth, int64_t n);
+int gci_fetch_depth(gci_ctx* ctx, int32_t track, int32_t contig, int32_t* out, int64_t n);
+/* sum of depth per contig (mean depth of GCI.py:862-868 = sum / length) */
+int gci_depth_sums(gci_ctx* ctx, int32_t track, int64_t* sums /* [n_contigs] */);
+/* decimal text of one contig's depth, one value per line (GCI.py:115-117), produced on the GPU;
+   call with out = NULL to get the byte count first */
+int gci_depth_text(gci_ctx* ctx, int32_t track, int32_t contig, int64_t first, int64_t count,
+                   char* out, int64_t cap, int64_t* n_bytes);
+
+/* ---- gap scan ----------------------------------------------------------------------------- */
+/* collapse_depth_range(depths, lo, hi, flank_len, 0) over every selected contig (GCI.py:356-390) */
+int gci_scan(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int32_t flank_len, int64_t* n_intervals);
+/* regions variant (GCI.py:627-628): windows [start,end) on contigs, flank 0, nothing dropped */
+int gci_scan_windows(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int64_t n_windows,
+                     const int32_t* contig, const int64_t* start, const int64_t* end, int64_t* n_intervals);
+/* intervals of the last scan on `track`, in contig (or window) order then position order;
+   owner_off[n_owners+1] gives each contig's / window's slice */
+int gci_fetch_intervals(gci_ctx* ctx, int32_t track, int64_t cap, int32_t* start, int32_t* end,
+                        int64_t* owner_off, int64_t* n);
+
+/* intervals that did not come from a scan on this context (a BED read from disk — the `--bed` entry of
+   utility/GCI_score.py:586): owner o is whole contig contig[o], its intervals are
+   [owner_off[o], owner_off[o+1]) of start/end, sorted and disjoint */
+int gci_load_intervals(gci_ctx* ctx, int32_t track, int64_t n_owners, const int32_t* contig,
+                       const int64_t* owner_off, const int32_t* start, const int32_t* end);
+
+/* ---- score terms (GCI.py:422-519) --------------------------------------------------------- */
+/* per owner (contig or window) of the last scan: curated N50 of the un-merged complement, number of
+   curated contigs after the -dp merge, and the complement lengths themselves (for the genome row).
+   Windows use flank = window start like GCI.py:629-634. */
+int gci_score_terms(gci_ctx* ctx, int32_t track, double dist_percent, int32_t flank_len,
+                    int64_t* n50 /* [owners] */, int64_t* n_ctg /* [owners] */,
+                    int64_t cap_lengths, int64_t* lengths, int64_t* lengths_off /* [owners+1] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCI_CUDA_H */

@@ -84,3 +84,45 @@ def mh63_depths():
         r = z["run_lengths"][off[i]:off[i + 1]]
         depths.append(np.repeat(v, r).astype(np.int32))
     return names, [int(x) for x in z["lengths"]], depths
+
+
+# ---- running the product (GPU) on a case ---------------------------------------------------------
+def attach_contigs(tabs, names, lengths):
+    for t in tabs or ():
+        if isinstance(t, AlnTable):
+            t.contig_names, t.contig_lengths = list(names), [int(x) for x in lengths]
+    return tabs
+
+
+def run_product(kw, workdir, session=None, threads=2):
+    """Drive gci_b200.pipeline.GCI() with the in-memory tables of a case; returns the output files in the
+    same shape as oracle.run_gci / the golden fixtures."""
+    import contextlib
+    import io as _io
+    from gci_b200 import pipeline as P
+    from gci_b200 import io as gio
+
+    kw = dict(kw)
+    names, lengths = kw.pop("names"), kw.pop("lengths")
+    n_runs = kw.pop("n_runs", None)
+    hifi, nano = kw.pop("hifi", None), kw.pop("nano", None)
+    attach_contigs(hifi, names, lengths)
+    attach_contigs(nano, names, lengths)
+    regions = kw.pop("regions", None)
+    regions_bed = None
+    if regions:
+        regions_bed = {}
+        for c, s, e in regions:
+            regions_bed.setdefault(c, []).append((s, e))
+    gaps = {n: list(r) for n, r in zip(names, n_runs or []) if r}
+    prefix = kw.pop("prefix", "T")
+    out_dir = os.path.join(workdir, "out")
+    buf = _io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        P.GCI(hifi=hifi, nano=nano, directory=out_dir, prefix=prefix, reference={"ids": names, "gaps": gaps},
+              regions=regions_bed, chrs=kw.pop("chrs", None), threads=threads, force=True, session=session, **kw)
+    outs = {}
+    for fn in sorted(os.listdir(out_dir)):
+        p = os.path.join(out_dir, fn)
+        outs[fn] = gio.read_depth_gz(p) if fn.endswith(".depth.gz") else open(p).read()
+    return outs, buf.getvalue()

@@ -1,0 +1,255 @@
+"""Seeded random inputs: CUDA path vs the CPU oracle, stage by stage through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import gci_oracle as O
+from gci_b200 import synth
+from gci_b200.records import AlnTable, PafTable, pack_cigar, NM_MISSING
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from gci_b200._lib import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _name_rank(names):
+    order = sorted(range(len(names)), key=lambda i: names[i])
+    rank = np.empty(len(names), np.int32)
+    rank[order] = np.arange(len(names))
+    return rank
+
+
+def _run_gpu(ctx, names, lengths, pafs, bams, n_reads, selected=None, fl=15, ts=0, params=None, n_runs=None):
+    p = dict(map_qual=30, mq_cutoff=50, iden_percent=0.9, clip_percent=0.1, ovlp_percent=0.9)
+    p.update(params or {})
+    ctx.set_contigs(lengths, selected)
+    ctx.set_name_rank(_name_rank(names))
+    if n_runs:
+        c = [i for i, r in enumerate(n_runs) for _ in r]
+        s = [iv[0] for r in n_runs for iv in r]
+        e = [iv[1] for r in n_runs for iv in r]
+        ctx.set_n_runs(c, s, e)
+    ctx.reads_begin(n_reads)
+    for t in pafs:
+        ctx.upload_paf(t)
+    for t in bams:
+        ctx.upload_bam(t)
+    n_surv = ctx.filter(**p)
+    ctx.depth(0, fl, -1, ts)
+    if n_runs:
+        ctx.mask_gaps(0)
+    return n_surv
+
+
+def _check(ctx, names, lengths, pafs, bams, n_reads, selected=None, fl=15, ts=0, params=None, n_runs=None, dp=0.005):
+    p = dict(map_qual=30, mq_cutoff=50, iden_percent=0.9, clip_percent=0.1, ovlp_percent=0.9)
+    p.update(params or {})
+    sel = np.ones(len(lengths), bool) if selected is None else np.asarray(selected, bool)
+    n_surv = _run_gpu(ctx, names, lengths, pafs, bams, n_reads, selected, fl, ts, params, n_runs)
+    want_d, want_s = O.filter_depth(pafs, bams, names, lengths, sel, flank_len=fl, **p)
+    want_d = O.mask_gaps(want_d, n_runs)
+    assert n_surv == len(want_s)
+    r, c, s, e = ctx.fetch_survivors()
+    got_s = {int(a): (int(b), int(x), int(y)) for a, b, x, y in zip(r, c, s, e)}
+    assert got_s == {k: tuple(v[:3]) for k, v in want_s.items()}
+    sums = ctx.depth_sums(0)
+    owners = [i for i in range(len(lengths)) if sel[i]]
+    for i in owners:
+        got = ctx.fetch_depth(0, i)
+        assert np.array_equal(got.astype(np.int64), want_d[i]), f"depth differs on contig {i}"
+        assert int(sums[i]) == int(want_d[i].sum())
+    n_iv = ctx.scan(0, -1, ts, fl)
+    gs, ge, off = ctx.fetch_intervals(0, len(owners))
+    beds = []
+    for o, i in enumerate(owners):
+        want = O.collapse_depth_range(want_d[i], -1, ts, fl, 0)
+        got = list(zip(gs[off[o]:off[o + 1]].tolist(), ge[off[o]:off[o + 1]].tolist()))
+        assert got == want, f"bed differs on contig {i}"
+        beds.append(want)
+    n50, nctg, lens, loff = ctx.score_terms(0, len(owners), n_iv, dp, fl)
+    all_obs, all_ctg = [], 0
+    for o, i in enumerate(owners):
+        obs = O.complement_lengths(beds[o], int(lengths[i]), fl)
+        new = O.complement_lengths(O.merge_close(beds[o], int(lengths[i]), dp, fl), int(lengths[i]), fl)
+        assert lens[loff[o]:loff[o + 1]].tolist() == obs
+        assert int(n50[o]) == O.n50(obs) and int(nctg[o]) == len(new)
+        all_obs += obs
+        all_ctg += len(new)
+    assert int(n50[-1]) == O.n50(all_obs) and int(nctg[-1]) == all_ctg
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_hifi_single_bam(ctx, seed):
+    rng = np.random.default_rng(seed)
+    lengths = [int(x) for x in rng.integers(20_000, 400_000, int(rng.integers(1, 5)))]
+    d = synth.make_reads(synth.SynthSpec(lengths, coverage=float(rng.uniform(5, 40)), seed=100 + seed,
+                                         read_mean=8000, read_min=1000, read_max=20000, hole_fraction=0.02))
+    _check(ctx, d.contigs.names, lengths, [], [d.bam], d.n_reads, n_runs=d.n_runs,
+           fl=int(rng.integers(0, 40)), ts=int(rng.integers(0, 4)))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_ont_long_cigars(ctx, seed):
+    """records of thousands of ops: every record spans several op tiles"""
+    lengths = [300_000, 150_000]
+    d = synth.make_reads(synth.SynthSpec(lengths, coverage=20, seed=200 + seed, read_mean=30000, read_sigma=0.6,
+                                         read_min=2000, read_max=120000, events_per_base=0.05))
+    assert d.bam.n_ops / max(1, d.bam.n_records) > 1000
+    _check(ctx, d.contigs.names, lengths, [], [d.bam], d.n_reads)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_multi_file_join(ctx, seed):
+    lengths = [200_000, 120_000, 60_000]
+    d = synth.make_reads(synth.SynthSpec(lengths, coverage=25, seed=300 + seed, read_mean=7000, read_min=1000,
+                                         read_max=20000))
+    b1 = synth.drop_reads(d.bam, 0.03, seed)
+    b2 = synth.second_aligner(d, seed=seed + 50)
+    b3 = synth.second_aligner(d, seed=seed + 60)
+    p1 = synth.aln_to_paf(synth.second_aligner(d, seed=seed + 70))
+    p2 = synth.aln_to_paf(synth.second_aligner(d, seed=seed + 80))
+    combos = [([], [b1, b2]), ([p1], [b1]), ([p1, p2], [b1, b2, b3]), ([p1], [b2, b3])]
+    pafs, bams = combos[seed % len(combos)]
+    _check(ctx, d.contigs.names, lengths, pafs, bams, d.n_reads,
+           params=dict(ovlp_percent=[0.9, 0.5, 0.95, 0.0][seed % 4], mq_cutoff=[50, 40, 60, 30][seed % 4]))
+
+
+def test_chrs_selection(ctx):
+    lengths = [100_000, 80_000, 50_000]
+    d = synth.make_reads(synth.SynthSpec(lengths, coverage=15, seed=77, read_mean=6000, read_min=1000, read_max=15000))
+    b2 = synth.second_aligner(d, seed=5)
+    _check(ctx, d.contigs.names, lengths, [synth.aln_to_paf(b2)], [d.bam], d.n_reads, selected=[True, False, True])
+
+
+def _bam(rows, n_contigs=1):
+    out = []
+    for i, r in enumerate(rows):
+        d = dict(ref_id=0, mapq=60, flag=0, nm=0, read_id=i)
+        d.update(r)
+        ops = pack_cigar(d["cigar"])
+        d.setdefault("qlen", int(sum((int(o) >> 4) for o in ops if (int(o) & 15) in (0, 1, 4, 7, 8))))
+        out.append(d)
+    return AlnTable.from_rows(out)
+
+
+def test_edge_records(ctx):
+    """zero-op records, 1-op records, slice wrap quirk, duplicate names, unsorted contig order"""
+    rows = [dict(ref_start=0, cigar="10M"),                       # stop = -4 -> wraps
+            dict(ref_start=100, cigar="200M", read_id=7), dict(ref_start=400, cigar="200M", read_id=7),
+            dict(ref_start=500, cigar="*", flag=4), dict(ref_start=500, cigar="20M"),
+            dict(ref_start=600, cigar="12S100M"), dict(ref_start=610, cigar="500H100M"),
+            dict(ref_start=620, cigar="50M5I50M5D", nm=10), dict(ref_start=630, cigar="100M", nm=11),
+            dict(ref_start=700, cigar="90=10X", nm=10), dict(ref_start=710, cigar="100M", mapq=29),
+            dict(ref_start=720, cigar="100M", flag=0x100), dict(ref_start=730, cigar="100M", flag=0x800),
+            dict(ref_start=900, cigar="100M"), dict(ref_start=980, cigar="20M")]
+    t = _bam(rows)
+    _check(ctx, ["c"], [1000], [], [t], 32)
+    # contig order differs from file order: contig 1 records first
+    rows = [dict(ref_id=1, ref_start=100, cigar="300M", read_id=3), dict(ref_id=0, ref_start=50, cigar="300M", read_id=3)]
+    _check(ctx, ["a", "b"], [1000, 1000], [], [_bam(rows)], 8)
+    # no records at all
+    _check(ctx, ["a", "b"], [1000, 10], [], [_bam([])], 4)
+    # a contig shorter than 2*fl and one exactly a tile long
+    rows = [dict(ref_id=1, ref_start=0, cigar="8192M"), dict(ref_id=2, ref_start=8000, cigar="8384M")]
+    _check(ctx, ["tiny", "tile", "tile2"], [20, 8192, 16384], [], [_bam(rows)], 4)
+
+
+def test_reference_would_raise(ctx):
+    from gci_b200._lib import ReferenceWouldRaise
+    t = _bam([dict(ref_start=10, cigar="100M", nm=None)])
+    with pytest.raises(ReferenceWouldRaise):
+        _run_gpu(ctx, ["c"], [1000], [], [t], 4)
+    t = _bam([dict(ref_start=10, cigar="100H")])
+    with pytest.raises(ReferenceWouldRaise):
+        _run_gpu(ctx, ["c"], [1000], [], [t], 4)
+    with pytest.raises(O.ReferenceWouldRaise):
+        O.filter_depth([], [t], ["c"], [1000])
+
+
+def test_many_tiny_records_per_tile(ctx):
+    """> 1024 records inside one 2048-op tile takes the global-atomics path"""
+    n = 5000
+    rows = [dict(ref_start=int(i * 3), cigar="40M", read_id=i) for i in range(n)]
+    _check(ctx, ["c"], [30_000], [], [_bam(rows)], n)
+
+
+def test_two_type_max_and_text(ctx):
+    lengths = [90_000, 40_000]
+    a = synth.make_reads(synth.SynthSpec(lengths, coverage=12, seed=1, read_mean=5000, read_min=500, read_max=12000))
+    b = synth.make_reads(synth.SynthSpec(lengths, coverage=9, seed=2, read_mean=9000, read_min=500, read_max=30000))
+    _run_gpu(ctx, a.contigs.names, lengths, [], [a.bam], a.n_reads)
+    ctx.reads_begin(b.n_reads)
+    ctx.upload_bam(b.bam)
+    ctx.filter()
+    ctx.depth(1, 15)
+    ctx.merge_max(0, 1, 2, -1, 0)
+    da, _ = O.filter_depth([], [a.bam], a.contigs.names, lengths)
+    db, _ = O.filter_depth([], [b.bam], a.contigs.names, lengths)
+    want = O.merge_two_types(da, db)
+    for i in range(2):
+        assert np.array_equal(ctx.fetch_depth(2, i).astype(np.int64), want[i])
+        assert ctx.depth_text(2, i).tobytes().decode() == "".join(f"{int(v)}\n" for v in want[i])
+    assert ctx.depth_sums(2).tolist() == [int(w.sum()) for w in want]
+    ctx.scan(2, -1, 0, 15)
+    gs, ge, off = ctx.fetch_intervals(2, 2)
+    for i in range(2):
+        assert list(zip(gs[off[i]:off[i + 1]].tolist(), ge[off[i]:off[i + 1]].tolist())) == \
+            O.collapse_depth_range(want[i], -1, 0, 15, 0)
+
+
+def test_regions_windows(ctx):
+    rng = np.random.default_rng(3)
+    lengths = [50_000, 20_000]
+    depth = [(rng.random(l) < 0.97).astype(np.int32) * rng.integers(1, 5, l).astype(np.int32) for l in lengths]
+    for d in depth:
+        for _ in range(6):
+            s = int(rng.integers(0, len(d) - 500))
+            d[s:s + int(rng.integers(1, 400))] = 0
+    ctx.set_contigs(lengths)
+    for i, d in enumerate(depth):
+        ctx.load_depth(0, i, d)
+    wins = [(0, 0, 50_000), (0, 100, 5000), (1, 19_000, 20_000), (1, 5, 5), (0, 31, 64), (0, 49_990, 60_000)]
+    for ts in (0, 2):
+        n_iv = ctx.scan_windows(0, [w[0] for w in wins], [w[1] for w in wins], [w[2] for w in wins], -1, ts)
+        gs, ge, off = ctx.fetch_intervals(0, len(wins))
+        n50, nctg, lens, loff = ctx.score_terms(0, len(wins), n_iv, 0.005, 0)
+        for k, (c, s, e) in enumerate(wins):
+            sub = depth[c][s:e].astype(np.int64)
+            want = O.collapse_depth_range(sub, -1, ts, 0, s)
+            assert list(zip(gs[off[k]:off[k + 1]].tolist(), ge[off[k]:off[k + 1]].tolist())) == want
+            obs = O.complement_lengths(want, e - s, s, s, e)
+            merged = O.merge_close(want, e - s, 0.005, s, s, e)
+            assert int(n50[k]) == O.n50(obs)
+            assert int(nctg[k]) == len(O.complement_lengths(merged, e - s, s, s, e))
+
+
+def test_full_size_chr19_properties(ctx):
+    """BASELINE config 2 size (58 Mbp, 30x): size-independent properties instead of the slow oracle"""
+    L = 58_000_000
+    d = synth.make_reads(synth.SynthSpec([L], coverage=30, seed=20240634, contig_names=["chr19"]))
+    n_surv = _run_gpu(ctx, ["chr19"], [L], [], [d.bam], d.n_reads)
+    r, c, s, e = ctx.fetch_survivors()
+    assert len(r) == n_surv and n_surv > 0.6 * d.n_reads
+    # (1) sum of depth == sum of survivor slice lengths
+    a = np.clip(s.astype(np.int64) + 15, 0, L)
+    b = np.clip(e.astype(np.int64) - 15 + 1, 0, L)
+    assert int(ctx.depth_sums(0)[0]) == int(np.maximum(0, b - a).sum())
+    # (2) the depth array equals the numpy delta/cumsum construction from the survivors
+    delta = np.zeros(L + 1, np.int64)
+    np.add.at(delta, a[b > a], 1)
+    np.add.at(delta, b[b > a], -1)
+    want = np.cumsum(delta[:-1])
+    got = ctx.fetch_depth(0, 0)
+    assert np.array_equal(got, want.astype(np.int32))
+    # (3) intervals == runs of zeros, and every synthetic hole is inside an issue interval
+    ctx.scan(0, -1, 0, 15)
+    gs, ge, off = ctx.fetch_intervals(0, 1)
+    assert list(zip(gs.tolist(), ge.tolist())) == O.collapse_depth_range(want, -1, 0, 15, 0)
+    for hs, he in d.holes[0]:
+        k = np.searchsorted(gs, hs, side="right") - 1
+        assert k >= 0 and gs[k] <= hs and ge[k] >= he
