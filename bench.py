@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — aligned Gbases/s filtered + depth-scanned (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3              # our arm
+    python bench.py --impl reference --steps 3 --warmup 1        # CPU baseline arm (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W   # N > 1
+
+Workload (config.workload): BASELINE.json configs[1] — CHM13 chr19-sized contig (58 Mbp), 30x synthetic
+HiFi, one BAM, seeded generator gci_b200.synth (seed 20240634 + rank).  At N > 1 every rank owns one
+such contig (contig sharding, weak scaling) and the ranks exchange only the genome-row terms.
+
+A step = one pass of the hot path over the batch:
+    gci_filter (CIGAR stats, gates, dedup, join) -> gci_depth (buckets, depth tiles + fused flags)
+    -> gci_scan (issue intervals) -> gci_score_terms (+ the genome-row all-reduce at N > 1)
+`value`  : records already resident in HBM, CUDA events per step, L2 flushed between steps.
+`e2e`    : the same through the C ABI with HOST (pinned) buffers: H2D of the record columns, the
+           step, D2H of the depth array, the intervals and the score terms inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "aligned Gbases/s filtered+depth-scanned at 1/2/4/8 B200 vs CPU ref -t N"
+UNIT = "Gbases/s"
+CHR19 = 58_000_000
+SEED = 20240634
+PARAMS = dict(map_qual=30, mq_cutoff=50, iden_percent=0.9, clip_percent=0.1, ovlp_percent=0.9)
+FLANK, THRESHOLD, DIST = 15, 0, 0.005
+# algorithmic bytes of the dominant kernel (depth_tile_kernel<flags>), per genome base: 4 B int32 depth
+# written once + 1 bit of issue flag; per event 2 B read; per tile 16 B of tile tables
+BYTES_PER_BASE = 4.0 + 1.0 / 8.0
+
+
+def make_workload(rank, length=CHR19, coverage=30.0):
+    from gci_b200 import synth
+    name = "chr19" if rank == 0 else f"chr19_{rank}"
+    return synth.make_reads(synth.SynthSpec([length], coverage=coverage, seed=SEED + rank, contig_names=[name]))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power))}
+
+
+def cpu_port_pass(data, threads):
+    """One pass of the oracle's C port over the workload (test infrastructure used as the timed baseline)."""
+    from oracle import c_oracle as CO
+    from oracle import gci_oracle as O
+    L = [int(x) for x in data.contigs.lengths]
+    depths, beds, n_surv = CO.hot_path([data.bam], L, data.n_reads, flank_len=FLANK, threshold=THRESHOLD,
+                                       threads=threads, **PARAMS)
+    rows = O.score_rows(data.contigs.names, L, beds, FLANK, DIST)
+    return n_surv, sum(len(b) for b in beds), rows
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU arm.  The reference is a pure-Python script whose dependencies (pysam,
+    Biopython) are absent from the image and it cannot travel to the GPU box, so the timed code is the
+    oracle's C port (kind = "port") with every host thread, on the same workload."""
+    if rank != 0:
+        return
+    from oracle import c_oracle as CO
+    data = make_workload(0)
+    threads = CO.max_threads()
+    for _ in range(args.warmup):
+        cpu_port_pass(data, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_pass(data, threads)
+    dt = time.perf_counter() - t0
+    val = data.aligned_bases * args.steps / dt / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "chr19_58Mbp_30x_hifi_1bam", "genome_bases": CHR19, "coverage": 30,
+                       "records": data.bam.n_records, "cigar_ops": data.bam.n_ops, "aligned_bases": data.aligned_bases},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "full workload per step (oracle/gci_oracle.c: gates, dedup, join, int64 depth "
+                                       "+=, per-base collapse loop, score rows)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--length", type=int, default=CHR19, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    from gci_b200 import dist as D
+    from gci_b200._lib import Context, PinnedPool
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        D.init("nccl")
+    import torch.distributed as tdist
+
+    data = make_workload(rank, args.length)
+    L = [int(x) for x in data.contigs.lengths]
+    tab = data.bam
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = Context(local)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_contigs(L)
+    pool = PinnedPool()
+    from gci_b200.records import AlnTable
+    pinned = AlnTable(*[pool.copy(getattr(tab, c)) for c in
+                        ("ref_id", "ref_start", "mapq", "flag", "nm", "qlen", "read_id", "cigar_off", "cigar")])
+    depth_out = pool.empty(L[0], np.int32)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+    h2d_bytes = tab.nbytes()
+    result = {}
+
+    def core_step():
+        n_surv = ctx.filter(**PARAMS)
+        ctx.depth(0, FLANK, -1, THRESHOLD)
+        n_iv = ctx.scan(0, -1, THRESHOLD, FLANK)
+        n50, nctg, lens, _ = ctx.score_terms(0, 1, n_iv, DIST, FLANK)
+        if world > 1:
+            sums = ctx.depth_sums(0)
+            mean, all_ctg, all_len = D.genome_row(int(sums.sum()), sum(L), int(nctg[-1]), lens)
+            result["mean_depth"] = mean
+        result.update(n_surv=n_surv, n_iv=n_iv, n50=int(n50[0]), nctg=int(nctg[0]))
+        return n_iv
+
+    def resident_step():
+        core_step()
+
+    def e2e_step():
+        ctx.reads_begin(data.n_reads)
+        ctx.upload_bam(pinned)
+        n_iv = core_step()
+        ctx.fetch_depth(0, 0, depth_out)
+        ctx.fetch_intervals(0, 1)
+        return n_iv
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            flush.fill_(1)
+            step_fn()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for a, b in evs:
+            flush.fill_(1)            # L2 flush between timed iterations (not inside the event pair)
+            a.record(stream)
+            step_fn()
+            b.record(stream)
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # records resident in HBM for the `value` region
+    ctx.reads_begin(data.n_reads)
+    ctx.upload_bam(pinned)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        resident_step()
+    ctx.stage_reset()
+    launches0 = ctx.kernel_launches
+    ms_res = timed(resident_step, args.steps, 0)
+    launches = ctx.kernel_launches - launches0
+    stage = ctx.stage_report()
+    ms_e2e = timed(e2e_step, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    aligned = np.array([data.aligned_bases], dtype=np.int64)
+    total_aligned = int(D.allreduce(aligned)[0]) if world > 1 else int(aligned[0])
+    value = total_aligned * args.steps / (ms_res * 1e-3) / 1e9
+    e2e = total_aligned * args.steps / (ms_e2e * 1e-3) / 1e9
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (depth tiles) ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    d_ms, d_k = stage["depth"]
+    n_tiles = sum(l // 8192 + 1 for l in L)
+    n_events = 2 * result["n_surv"]
+    alg_bytes = BYTES_PER_BASE * n_tiles * 8192 + 2.0 * n_events + 16.0 * n_tiles
+    achieved = alg_bytes / (d_ms / max(1, d_k) * 1e-3) / 1e9 if d_ms > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "depth_tile_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    step_ms = ms_res / args.steps
+    roofline = {"bound": "hbm", "kernel": "depth_tile_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": d_ms / max(1, d_k),
+                "kernel_share_of_step": (d_ms / max(1, d_k)) / step_ms,
+                "stage_ms_per_step": {k: v[0] / args.steps for k, v in stage.items() if v[1]}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic",
+            "config": {"workload": "chr19_58Mbp_30x_hifi_1bam" + ("" if world == 1 else f"_x{world}_contig_sharded"),
+                       "genome_bases_per_gpu": L[0], "coverage": 30, "records_per_gpu": tab.n_records,
+                       "cigar_ops_per_gpu": tab.n_ops, "aligned_bases_total": total_aligned,
+                       "survivors": result["n_surv"], "issue_intervals": result["n_iv"],
+                       "l2": "512 MiB buffer written between timed steps (L2 flush); depth output 232 MB > L2",
+                       "timing": "CUDA events per step on the library's stream, max over ranks",
+                       "parallelism": "contig sharding, 1 process per GPU" if world > 1 else "single GPU"},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(depth_out.nbytes + 8 * result["n_iv"] + 64),
+                    "ms_per_step": ms_e2e / args.steps,
+                    "note": "host->device copy of all record columns + CIGAR from pinned memory, full hot path, "
+                            "device->host copy of the int32 depth array, intervals and score terms"},
+            "gpu_launches": int(launches),
+            "roofline": roofline}
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import c_oracle as CO
+        threads = CO.max_threads()
+        cpu_port_pass(data, threads)
+        reps = 0
+        t0 = time.perf_counter()
+        while True:
+            out = cpu_port_pass(data, threads)
+            reps += 1
+            if time.perf_counter() - t0 > 10.0 or reps >= 8:
+                break
+        dt = time.perf_counter() - t0
+        assert out[0] == result["n_surv"] and out[1] == result["n_iv"], "GPU and CPU port disagree"
+        line["cpu_baseline"] = {"value": data.aligned_bases * reps / dt / 1e9, "unit": UNIT, "cores": threads,
+                                "kind": "port",
+                                "sample": f"{reps} passes over the full workload (oracle/gci_oracle.c, pthreads)"}
+    print(json.dumps(line), flush=True)
+    pool.close()
+
+
+if __name__ == "__main__":
+    main()

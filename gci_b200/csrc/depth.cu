@@ -29,8 +29,9 @@ __device__ __forceinline__ Slice survivor_slice(int32_t c, int32_t s, int32_t e,
   r.a = py_slice_index((long long)s + fl, L);
   r.b = py_slice_index((long long)e - fl + 1, L);
   if (r.a >= r.b) return r;
-  r.ok = true;
   const int64_t t0 = tile_off[c];
+  if (tile_off[c + 1] == t0) return r;   // contig without depth storage (not selected / not owned)
+  r.ok = true;
   r.tile_a = t0 + r.a / GCI_TILE;
   r.tile_b = t0 + r.b / GCI_TILE;
   return r;

@@ -1,0 +1,123 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink/NVSwitch; gloo on CPU
+for tests).  Contigs shard across ranks; the only exchanges of the path are
+
+  * exchange_file_tables(): all-gather of the compact per-file winner tables before the cross-file
+    join, because the join is keyed by read, not by contig (multi-file read sets only);
+  * genome_row(): all-reduce of (sum depth, sum length, curated-contig count) and all-gather of the
+    curated lengths for the genome-level N50 / GCI row (GCI.py:572-587, :862-868).
+
+Message sizes are KB..MB: latency-bound, no custom kernel is warranted.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def is_dist():
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized()
+
+
+def init(backend=None):
+    """Initialise from torchrun's env (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*).  Returns (rank, world, local)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, world, local
+
+
+def _device():
+    import torch
+    import torch.distributed as dist
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def allreduce(values, op="sum"):
+    """numpy int64/float64 vector -> reduced over ranks (identity without a process group)."""
+    values = np.asarray(values)
+    if not is_dist():
+        return values.copy()
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(values)).to(_device())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX)
+    return t.cpu().numpy()
+
+
+def allgather_varlen(arr):
+    """Each rank contributes a 1-D array of its own length; returns the list of all ranks' arrays."""
+    arr = np.ascontiguousarray(arr)
+    if not is_dist():
+        return [arr.copy()]
+    orig = arr.dtype
+    if orig.kind == "u" or orig == np.bool_:      # unsigned types do not travel through every backend
+        arr = arr.astype(np.int64)
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    dev = _device()
+    n = torch.tensor([arr.size], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(1, max(sizes))
+    buf = torch.zeros(cap, dtype=torch.from_numpy(arr[:0]).dtype, device=dev)
+    if arr.size:
+        buf[:arr.size] = torch.from_numpy(arr).to(dev)
+    outs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf)
+    return [o[:s].cpu().numpy().astype(orig) for o, s in zip(outs, sizes)]
+
+
+def assign_contigs(lengths, weights, world):
+    """LPT bin packing of contigs onto ranks by (aligned bases, length).  Returns owner[contig]."""
+    order = sorted(range(len(lengths)), key=lambda i: (-(weights[i] if weights is not None else 0), -lengths[i], i))
+    load = [0.0] * world
+    owner = [0] * len(lengths)
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        owner[i] = r
+        load[r] += (weights[i] if weights is not None else 0) + lengths[i]
+    return owner
+
+
+def exchange_file_tables(tables):
+    """tables: per file, the tuple (read_id, contig, start, end, qlen, highq) of THIS rank's winners
+    (Context.fetch_file_table).  Returns the same per file with every rank's rows concatenated; a read
+    that won on two ranks (duplicate primary names on different contigs) keeps the row of the
+    higher contig index, which is the reference's fetch order (GCI.py:260-269)."""
+    out = []
+    for cols in tables:
+        gathered = [np.concatenate(allgather_varlen(np.ascontiguousarray(c))) for c in cols]
+        r, c = gathered[0], gathered[1]
+        if len(r):
+            order = np.lexsort((c, r))              # by read, then contig: the last of each read wins
+            last = np.ones(len(r), bool)
+            rs = r[order]
+            last[:-1] = rs[1:] != rs[:-1]
+            keep = order[last]
+            gathered = [g[keep] for g in gathered]
+        out.append(tuple(gathered))
+    return out
+
+
+def genome_row(sum_depth, sum_len, n_ctg, lengths):
+    """Whole-genome terms from per-rank partials: (mean depth, total curated contigs, all curated lengths)."""
+    tot = allreduce(np.array([int(sum_depth), int(sum_len), int(n_ctg)], dtype=np.int64))
+    all_len = np.concatenate(allgather_varlen(np.asarray(lengths, dtype=np.int64)))
+    mean = float(tot[0]) / float(tot[1]) if tot[1] else float("nan")
+    return mean, int(tot[2]), all_len

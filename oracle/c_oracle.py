@@ -1,0 +1,129 @@
+"""ctypes wrapper of oracle/gci_oracle.c — TEST INFRASTRUCTURE ONLY (see oracle/gci_oracle.py header).
+
+`hot_path()` runs BAM gates -> dedup -> join -> depth -> collapse on the CPU with pthreads; it is the
+timed "port" baseline of bench.py and a second checker in tests."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+_p = C.c_void_p
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", _HERE], check=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_collapse.restype = C.c_int64
+        _lib.orc_max_threads.restype = C.c_int
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_p)
+
+
+def max_threads():
+    return int(lib().orc_max_threads())
+
+
+class RaisesLikeReference(Exception):
+    pass
+
+
+def bam_leg(tab, selected, n_reads, map_qual=30, mq_cutoff=50, iden_percent=0.9, clip_percent=0.1, threads=1):
+    """-> per-read table (contig or -1, start, end, qlen) + highq marks, like gci_oracle.bam_leg"""
+    L = lib()
+    n = tab.n_records
+    passed = np.zeros(max(1, n), np.int8)
+    ref_end = np.zeros(max(1, n), np.int32)
+    sel = np.ascontiguousarray(selected, dtype=np.uint8)
+    bad = L.orc_gate(C.c_int64(n), _ptr(tab.ref_id), _ptr(tab.ref_start), _ptr(tab.mapq), _ptr(tab.flag),
+                     _ptr(tab.nm), _ptr(tab.cigar_off), _ptr(tab.cigar), _ptr(sel), C.c_int32(len(sel)),
+                     C.c_int32(map_qual), C.c_double(iden_percent), C.c_double(clip_percent), _ptr(passed),
+                     _ptr(ref_end), C.c_int(threads))
+    if bad:
+        raise RaisesLikeReference(f"the reference raises on this input (mask {bad})")
+    win = np.empty(max(1, n_reads), np.int64)
+    highq = np.zeros(max(1, n_reads), np.uint8)
+    L.orc_dedup(C.c_int64(n), _ptr(tab.ref_id), _ptr(tab.mapq), _ptr(tab.read_id), _ptr(passed),
+                C.c_uint32(n_reads), C.c_int32(mq_cutoff), _ptr(win), _ptr(highq))
+    win = win[:n_reads]
+    idx = (win & 0xffffffff).astype(np.int64)
+    present = win >= 0
+    idx[~present] = 0
+    if n == 0:
+        z = np.zeros(n_reads, np.int32)
+        return np.full(n_reads, -1, np.int32), z, z.copy(), z.copy(), highq[:n_reads]
+    c = np.where(present, tab.ref_id[idx], -1).astype(np.int32)
+    return c, tab.ref_start[idx].astype(np.int32), ref_end[idx].astype(np.int32), tab.qlen[idx].astype(np.int32), \
+        highq[:n_reads]
+
+
+def join(tables, highq, ovlp_percent=0.9, threads=1):
+    L = lib()
+    f = len(tables)
+    n_reads = len(highq)
+    arr = lambda k: (C.c_void_p * f)(*[_ptr(np.ascontiguousarray(t[k], np.int32)) for t in tables])
+    keep = [[np.ascontiguousarray(t[k], np.int32) for t in tables] for k in range(4)]
+    ptrs = [(C.c_void_p * f)(*[_ptr(a) for a in keep[k]]) for k in range(4)]
+    oc, os_, oe = (np.empty(max(1, n_reads), np.int32) for _ in range(3))
+    hq = np.ascontiguousarray(highq, np.uint8)
+    bad = L.orc_join(C.c_int32(f), C.c_uint32(n_reads), ptrs[0], ptrs[1], ptrs[2], ptrs[3], _ptr(hq),
+                     C.c_double(ovlp_percent), _ptr(oc), _ptr(os_), _ptr(oe), C.c_int(threads))
+    if bad:
+        raise RaisesLikeReference("ZeroDivisionError at GCI.py:292")
+    return oc[:n_reads], os_[:n_reads], oe[:n_reads]
+
+
+def depth(sc, ss, se, lengths, flank_len=15, threads=1):
+    L = lib()
+    lengths = np.ascontiguousarray(lengths, np.int64)
+    off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    d = np.zeros(int(off[-1]), np.int64)
+    L.orc_depth(C.c_uint32(len(sc)), _ptr(np.ascontiguousarray(sc, np.int32)), _ptr(np.ascontiguousarray(ss, np.int32)),
+                _ptr(np.ascontiguousarray(se, np.int32)), C.c_int32(flank_len), C.c_int32(len(lengths)),
+                _ptr(lengths), _ptr(off), _ptr(d), C.c_int(threads))
+    return [d[off[i]:off[i + 1]] for i in range(len(lengths))]
+
+
+def collapse(depth_arr, leftmost=-1, rightmost=0, flank_len=15, start_pos=0):
+    L = lib()
+    d = np.ascontiguousarray(depth_arr, np.int64)
+    cap = 1024
+    while True:
+        s, e = np.empty(cap, np.int64), np.empty(cap, np.int64)
+        n = L.orc_collapse(_ptr(d), C.c_int64(len(d)), C.c_int64(leftmost), C.c_int64(rightmost),
+                           C.c_int64(flank_len), C.c_int64(start_pos), _ptr(s), _ptr(e), C.c_int64(cap))
+        if n <= cap:
+            return list(zip(s[:n].tolist(), e[:n].tolist()))
+        cap = int(n)
+
+
+def hot_path(bams, lengths, n_reads, selected=None, map_qual=30, mq_cutoff=50, iden_percent=0.9, clip_percent=0.1,
+             ovlp_percent=0.9, flank_len=15, threshold=0, threads=1):
+    """BAM-only hot path: gates -> dedup -> join -> depth -> collapse.  Returns (depths, beds, n_survivors)."""
+    if selected is None:
+        selected = np.ones(len(lengths), bool)
+    tables, hq = [], np.zeros(n_reads, np.uint8)
+    for t in bams:
+        c, s, e, q, h = bam_leg(t, selected, n_reads, map_qual, mq_cutoff, iden_percent, clip_percent, threads)
+        tables.append((c, s, e, q))
+        hq |= h
+    sc, ss, se = join(tables, hq, ovlp_percent, threads)
+    lens = [int(l) if selected[i] else 0 for i, l in enumerate(lengths)]
+    depths = depth(sc, ss, se, lens, flank_len, threads)
+    beds = [collapse(d, -1, threshold, flank_len, 0) for d in depths]
+    return depths, beds, int((sc >= 0).sum())
