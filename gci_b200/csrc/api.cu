@@ -94,7 +94,7 @@ int gci_d2h(gci_ctx* ctx, void* dst, const void* src, size_t bytes) {
 
 static void free_bam(gci_ctx* ctx, BamFile& b) {
   for (DevBuf* d : {&b.ref_id, &b.ref_start, &b.mapq, &b.flag, &b.nm, &b.qlen, &b.read_id, &b.cigar_off,
-                    &b.cigar, &b.stats, &b.ref_end})
+                    &b.cigar, &b.stats, &b.ref_end, &b.tile_rec})
     ctx->release(*d);
 }
 
@@ -112,6 +112,9 @@ static void free_track(gci_ctx* ctx, Track& t) {
   t.owners_are_windows = false;
   t.raw_lo.clear();
   t.raw_hi.clear();
+  t.h_owner_off.clear();
+  t.owner_contig.clear();
+  t.iv_cap = 0;
 }
 
 int gci_alloc_track(gci_ctx* ctx, int track) {
@@ -163,7 +166,7 @@ void gci_destroy(gci_ctx* ctx) {
   for (auto& b : ctx->bam) free_bam(ctx, b);
   for (auto& f : ctx->files) free_table(ctx, f);
   for (auto& t : ctx->track) free_track(ctx, t);
-  for (DevBuf* d : {&ctx->d_len, &ctx->d_selected, &ctx->d_tile_off, &ctx->d_nr_contig, &ctx->d_nr_start,
+  for (DevBuf* d : {&ctx->d_len, &ctx->d_selected, &ctx->d_tile_off, &ctx->d_owner_of, &ctx->d_nr_contig, &ctx->d_nr_start,
                     &ctx->d_nr_end, &ctx->highq, &ctx->surv_contig, &ctx->surv_start, &ctx->surv_end,
                     &ctx->tile_cnt, &ctx->tile_net, &ctx->tile_evoff, &ctx->tile_base, &ctx->events,
                     &ctx->scan_tmp, &ctx->scan_tmp2, &ctx->misc, &ctx->d_err, &ctx->chunk_cnt, &ctx->chunk_off})
@@ -261,6 +264,7 @@ int gci_set_contigs(gci_ctx* ctx, int32_t n, const int64_t* lengths, const uint8
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->n_nruns = 0;
   ctx->name_rank.clear();
+  ctx->owner_of_stale = true;
   return GCI_OK;
 }
 
@@ -350,6 +354,7 @@ int gci_upload_bam(gci_ctx* ctx, int64_t n, const int32_t* ref_id, const int32_t
   GCI_TRY(gci_h2d(ctx, b.cigar_off, cigar_off, 8 * (n + 1)));
   GCI_TRY(gci_h2d(ctx, b.cigar, cigar, 4 * n_ops));
   ctx->stage_end();
+  GCI_TRY(gci_index_bam(ctx, b));   // op-tile -> record index: a property of the file, built once
   FileTable f;
   f.kind = 0;
   f.src = (int)ctx->bam.size() - 1;
@@ -436,7 +441,8 @@ int gci_fetch_intervals(gci_ctx* ctx, int32_t track, int64_t cap, int32_t* start
   ctx->stage_begin(GCI_ST_D2H);
   if (start) GCI_TRY(gci_d2h(ctx, start, t.iv_start.p, sizeof(int32_t) * t.n_intervals));
   if (end) GCI_TRY(gci_d2h(ctx, end, t.iv_end.p, sizeof(int32_t) * t.n_intervals));
-  if (owner_off) GCI_TRY(gci_d2h(ctx, owner_off, t.owner_off.p, sizeof(int64_t) * (t.n_owners + 1)));
+  if (owner_off && (int64_t)t.h_owner_off.size() == t.n_owners + 1)
+    memcpy(owner_off, t.h_owner_off.data(), sizeof(int64_t) * (size_t)(t.n_owners + 1));
   ctx->stage_end();
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return GCI_OK;

@@ -49,6 +49,7 @@ struct BamFile {
   DevBuf ref_id, ref_start, mapq, flag, nm, qlen, read_id, cigar_off, cigar;
   DevBuf stats;    // uint32[n][8]: Mx(M+=+X), I, D, N, S, pad..   (K1 output)
   DevBuf ref_end;  // int32[n]                                      (K2 output)
+  DevBuf tile_rec; // int2[n_op_tiles]: first / last record of every CIGAR op tile (built at upload)
 };
 
 // PAF lines stay on the host: the per-read primary-target election (GCI.py:241-254) is a
@@ -82,6 +83,10 @@ struct Track {
   DevBuf owner_off;        // int64[n_owners + 1]
   DevBuf win_contig, win_lo, win_hi;   // int32 / int64 / int64 [n_owners]: scan windows
   std::vector<int64_t> raw_lo, raw_hi; // windows as given by the caller (before slice normalisation)
+  std::vector<int64_t> h_owner_off;    // host copy of owner_off after the last scan / load
+  std::vector<int32_t> owner_contig;   // contig of every owner
+  int64_t iv_cap = 0;                  // capacity of iv_start / iv_end
+  int32_t scan_flank = 0;
 };
 
 struct StageTimer {
@@ -106,7 +111,8 @@ struct gci_ctx {
   std::vector<int64_t> tile_off;    // [n+1] first tile of each contig
   std::vector<int64_t> pos_off;     // [n+1] = tile_off * TILE
   int64_t n_tiles = 0, total_padded = 0;
-  DevBuf d_len, d_selected, d_tile_off;
+  DevBuf d_len, d_selected, d_tile_off, d_owner_of;
+  bool owner_of_stale = true;
 
   // N runs (sorted by (contig,start) on upload)
   int64_t n_nruns = 0;
@@ -151,6 +157,7 @@ int gci_exclusive_scan_i64_from_i32(gci_ctx* ctx, const int32_t* in, int64_t* ou
 int gci_exclusive_scan_i32(gci_ctx* ctx, const int32_t* in, int32_t* out, int64_t n);
 
 // stage entry points
+int gci_index_bam(gci_ctx* ctx, BamFile& b);
 int gci_run_bam_leg(gci_ctx* ctx, int file_idx, int bam_idx, int32_t mq, int32_t mq_cutoff, double ip, double cp);
 int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip);
 int gci_run_join(gci_ctx* ctx, double op);

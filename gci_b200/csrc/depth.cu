@@ -112,21 +112,44 @@ __device__ __forceinline__ uint32_t pack_nibbles(uint32_t nib, int lane) {
   return w;
 }
 
+// shared-memory layout of the delta tile: 4 pad words after every 32 positions, so that a lane's 8
+// consecutive positions (two LDS.128) never collide with the other lanes of its quarter-warp
+__device__ __forceinline__ int pad_idx(int p) { return p + ((p >> 5) << 2); }
+constexpr int GCI_TILE_WORDS = GCI_TILE + GCI_TILE / 8;      // 9216 words = 36 KB
+
+// 8 flag bits of one lane (positions idx..idx+7) -> 32-bit words held by lanes 0, 4, 8, ...
+__device__ __forceinline__ uint32_t pack_bytes(uint32_t byte, int lane) {
+  uint32_t w = byte << ((lane & 3) * 8);
+  w |= __shfl_xor_sync(0xffffffffu, w, 1);
+  w |= __shfl_xor_sync(0xffffffffu, w, 2);
+  return w;
+}
+
+__device__ __forceinline__ uint32_t flag8(const int (&o)[8], int lo1, uint32_t span) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) m |= ((uint32_t)(o[k] - lo1) < span ? 1u : 0u) << k;
+  return m;
+}
+
+// FLAGS: also emit the issue bit (lo < depth <= hi) of every position.
+// lo1 = lo + 1, span = number of admissible depth values (0 = none).
 template <bool FLAGS>
 __global__ void __launch_bounds__(GCI_TILE_THREADS)
 depth_tile_kernel(const unsigned long long* __restrict__ tile_pack, const unsigned long long* __restrict__ tile_scan,
                   const uint16_t* __restrict__ events, const int64_t* __restrict__ tile_off,
                   const int64_t* __restrict__ len, int32_t n_contigs, int32_t* __restrict__ depth,
-                  uint32_t* __restrict__ flags, int32_t lo, int32_t hi) {
-  __shared__ __align__(16) int s_delta[GCI_TILE];
+                  uint32_t* __restrict__ flags, int32_t lo1, uint32_t span) {
+  __shared__ __align__(16) int s_delta[GCI_TILE_WORDS];
   __shared__ int s_part[GCI_TILE_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tile = blockIdx.x;
   constexpr int PER_WARP = GCI_TILE / (GCI_TILE_THREADS / 32);   // 1024
-  constexpr int ITERS = PER_WARP / 128;                          // 8
+  constexpr int ITERS = PER_WARP / 256;                          // 4
 
 #pragma unroll
-  for (int v = tid; v < GCI_TILE / 4; v += GCI_TILE_THREADS) reinterpret_cast<int4*>(s_delta)[v] = make_int4(0, 0, 0, 0);
+  for (int v = tid; v < GCI_TILE_WORDS / 4; v += GCI_TILE_THREADS)
+    reinterpret_cast<int4*>(s_delta)[v] = make_int4(0, 0, 0, 0);
   if (tid < GCI_TILE_THREADS / 32) s_part[tid] = 0;
   __syncthreads();
   const unsigned long long pk = tile_pack[tile], sc = tile_scan[tile];
@@ -136,45 +159,45 @@ depth_tile_kernel(const unsigned long long* __restrict__ tile_pack, const unsign
   for (uint32_t i = tid; i < n_ev; i += GCI_TILE_THREADS) {
     const uint32_t e = events[ev0 + i];
     const int d = (e & 1u) ? -1 : 1;
-    const uint32_t p = e >> 1;
-    atomicAdd(&s_delta[p], d);
+    const int p = (int)(e >> 1);
+    atomicAdd(&s_delta[pad_idx(p)], d);
     atomicAdd(&s_part[p / PER_WARP], d);
   }
   __syncthreads();
 
-  // contig of this tile and position of its first base inside the contig
+  // contig of this tile; `valid` = positions of the tile that are real bases (the rest is padding)
   const int64_t c = upper_bound_minus1<int64_t>(tile_off, (int64_t)n_contigs + 1, tile);
-  const int64_t cpos0 = (tile - tile_off[c]) * GCI_TILE;
-  const int64_t L = len[c];
+  const int64_t left = len[c] - (tile - tile_off[c]) * GCI_TILE;
+  const int valid = left >= GCI_TILE ? GCI_TILE : (int)left;
   int carry = base;
   for (int j = 0; j < warp; j++) carry += s_part[j];
-  const int64_t gbase = tile * GCI_TILE;
+  int32_t* __restrict__ out = depth + tile * GCI_TILE;
+  uint32_t* __restrict__ fout = flags + tile * (GCI_TILE / 32);
 #pragma unroll
   for (int it = 0; it < ITERS; it++) {
-    const int idx = warp * PER_WARP + it * 128 + lane * 4;
-    const int4 v = *reinterpret_cast<const int4*>(&s_delta[idx]);
-    const int a = v.x, b = a + v.y, cc = b + v.z, d = cc + v.w;
-    const int incl = warp_incl_scan(d, lane);
-    const int run = carry + incl - d;
-    int4 o = make_int4(run + a, run + b, run + cc, run + d);
+    const int idx = warp * PER_WARP + it * 256 + lane * 8;
+    const int w = pad_idx(idx);
+    const int4 v0 = *reinterpret_cast<const int4*>(&s_delta[w]);
+    const int4 v1 = *reinterpret_cast<const int4*>(&s_delta[w + 4]);
+    int o[8];
+    o[0] = v0.x; o[1] = o[0] + v0.y; o[2] = o[1] + v0.z; o[3] = o[2] + v0.w;
+    o[4] = o[3] + v1.x; o[5] = o[4] + v1.y; o[6] = o[5] + v1.z; o[7] = o[6] + v1.w;
+    const int incl = warp_incl_scan(o[7], lane);
+    const int run = carry + incl - o[7];
     carry += __shfl_sync(0xffffffffu, incl, 31);
-    const int64_t cp = cpos0 + idx;
-    if (cp + 3 >= L) {   // padding behind the last base stays 0
-      if (cp >= L) o.x = 0;
-      if (cp + 1 >= L) o.y = 0;
-      if (cp + 2 >= L) o.z = 0;
-      if (cp + 3 >= L) o.w = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) o[k] += run;
+    if (idx + 8 > valid) {   // only the last tile of a contig: padding behind the last base stays 0
+#pragma unroll
+      for (int k = 0; k < 8; k++) if (idx + k >= valid) o[k] = 0;
     }
-    *reinterpret_cast<int4*>(&depth[gbase + idx]) = o;
+    *reinterpret_cast<int4*>(out + idx) = make_int4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<int4*>(out + idx + 4) = make_int4(o[4], o[5], o[6], o[7]);
     if (FLAGS) {
-      const int4 m = o;
-      uint32_t nib = 0;
-      nib |= (m.x > lo && m.x <= hi && cp < L) ? 1u : 0u;
-      nib |= (m.y > lo && m.y <= hi && cp + 1 < L) ? 2u : 0u;
-      nib |= (m.z > lo && m.z <= hi && cp + 2 < L) ? 4u : 0u;
-      nib |= (m.w > lo && m.w <= hi && cp + 3 < L) ? 8u : 0u;
-      const uint32_t w = pack_nibbles(nib, lane);
-      if ((lane & 7) == 0) flags[(gbase + idx) >> 5] = w;
+      uint32_t m = flag8(o, lo1, span);
+      if (idx + 8 > valid) m &= idx >= valid ? 0u : (0xffu >> (idx + 8 - valid));
+      const uint32_t word = pack_bytes(m, lane);
+      if ((lane & 3) == 0) fout[idx >> 5] = word;
     }
   }
 }
@@ -392,15 +415,15 @@ int gci_depth(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo, int32_
   const uint32_t nr = ctx->n_reads;
   if (nt == 0) return GCI_OK;
   if (nt >= (int64_t(1) << 31)) return ctx->fail(GCI_E_ARG, "too many tiles");
-  GCI_TRY(ctx->ensure(ctx->tile_cnt, 8 * (size_t)nt));     // packed (count, net)
+  // one scratch block: [packed (count, net) u64 x nt | fill cursors u32 x nt] zeroed with one memset
+  GCI_TRY(ctx->ensure(ctx->tile_cnt, 12 * (size_t)nt));
   GCI_TRY(ctx->ensure(ctx->tile_evoff, 8 * (size_t)nt));   // exclusive scan of the packed values
-  GCI_TRY(ctx->ensure(ctx->tile_net, 4 * (size_t)nt));     // fill cursors
   GCI_TRY(ctx->ensure(ctx->events, 2 * 2 * (size_t)std::max<uint32_t>(1, nr)));
   unsigned long long* pack = ctx->tile_cnt.as<unsigned long long>();
+  uint32_t* cursor = reinterpret_cast<uint32_t*>(pack + nt);
   unsigned long long* scan = ctx->tile_evoff.as<unsigned long long>();
   ctx->stage_begin(GCI_ST_BUCKET);
-  GCI_CUDA_TRY(ctx, cudaMemsetAsync(pack, 0, 8 * (size_t)nt, ctx->stream));
-  GCI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->tile_net.p, 0, 4 * (size_t)nt, ctx->stream));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(pack, 0, 12 * (size_t)nt, ctx->stream));
   GCI_CUDA_TRY(ctx, cudaMemsetAsync(t.sums.p, 0, sizeof(int64_t) * (size_t)ctx->n_contigs, ctx->stream));
   if (nr) {
     bucket_count_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(
@@ -412,21 +435,22 @@ int gci_depth(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo, int32_
   if (nr) {
     bucket_fill_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(
         nr, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(), flank_len,
-        ctx->d_len.as<int64_t>(), ctx->d_tile_off.as<int64_t>(), scan, ctx->tile_net.as<uint32_t>(),
-        ctx->events.as<uint16_t>());
+        ctx->d_len.as<int64_t>(), ctx->d_tile_off.as<int64_t>(), scan, cursor, ctx->events.as<uint16_t>());
     GCI_LAUNCH_CHECK(ctx);
   }
   ctx->stage_end();
   const bool fuse = !(lo == INT32_MIN && hi == INT32_MIN);
+  const int32_t lo1 = fuse ? (int32_t)((int64_t)lo + 1 > INT32_MAX ? INT32_MAX : lo + 1) : 0;
+  const uint32_t span = (fuse && hi > lo) ? (uint32_t)((int64_t)hi - (int64_t)lo) : 0u;
   ctx->stage_begin(GCI_ST_DEPTH);
   if (fuse) {
     depth_tile_kernel<true><<<(unsigned)nt, GCI_TILE_THREADS, 0, ctx->stream>>>(
         pack, scan, ctx->events.as<uint16_t>(), ctx->d_tile_off.as<int64_t>(), ctx->d_len.as<int64_t>(),
-        ctx->n_contigs, t.depth.as<int32_t>(), t.flags.as<uint32_t>(), lo, hi);
+        ctx->n_contigs, t.depth.as<int32_t>(), t.flags.as<uint32_t>(), lo1, span);
   } else {
     depth_tile_kernel<false><<<(unsigned)nt, GCI_TILE_THREADS, 0, ctx->stream>>>(
         pack, scan, ctx->events.as<uint16_t>(), ctx->d_tile_off.as<int64_t>(), ctx->d_len.as<int64_t>(),
-        ctx->n_contigs, t.depth.as<int32_t>(), t.flags.as<uint32_t>(), lo, hi);
+        ctx->n_contigs, t.depth.as<int32_t>(), t.flags.as<uint32_t>(), lo1, span);
   }
   GCI_LAUNCH_CHECK(ctx);
   ctx->stage_end();

@@ -81,20 +81,29 @@ __global__ void cigar_tile_index_kernel(const uint64_t* __restrict__ off, int64_
 }
 
 struct CigAcc {
-  uint32_t mx, i, d, n, s;
-  __device__ __forceinline__ void clear() { mx = i = d = n = s = 0; }
+  uint32_t tot, i, d, n, s;   // tot = M + '=' + X + I + D
+  __device__ __forceinline__ void clear() { tot = i = d = n = s = 0; }
   __device__ __forceinline__ void add(uint32_t op) {
-    uint32_t c = op & 15u, l = op >> 4;
-    // class table packed in a 64-bit constant: M,=,X -> 0; I -> 1; D -> 2; N -> 3; S -> 4; H,P,B -> 7
-    const unsigned long long LUT = 0x7777777007743210ull;   // nibble k = class of op code k
-    uint32_t k = (uint32_t)(LUT >> (c * 4)) & 15u;
-    mx += (k == 0) ? l : 0u;
-    i += (k == 1) ? l : 0u;
-    d += (k == 2) ? l : 0u;
-    n += (k == 3) ? l : 0u;
-    s += (k == 4) ? l : 0u;
+    const uint32_t c = op & 15u, l = op >> 4;
+    if ((0xFE78u >> c) & 1u) {          // N, S, H, P, B (and invalid codes): rare, at read ends
+      n += (c == 3u) ? l : 0u;
+      s += (c == 4u) ? l : 0u;
+    } else {                            // M, I, D, '=', X
+      tot += l;
+      i += (c == 1u) ? l : 0u;
+      d += (c == 2u) ? l : 0u;
+    }
   }
-  __device__ __forceinline__ bool any() const { return (mx | i | d | n | s) != 0; }
+  __device__ __forceinline__ bool any() const { return (tot | n | s) != 0; }
+  // stats layout: [Mx, I, D, N, S]
+  __device__ __forceinline__ void flush(uint32_t* p) const {
+    const uint32_t mx = tot - i - d;
+    if (mx) atomicAdd(p + 0, mx);
+    if (i) atomicAdd(p + 1, i);
+    if (d) atomicAdd(p + 2, d);
+    if (n) atomicAdd(p + 3, n);
+    if (s) atomicAdd(p + 4, s);
+  }
 };
 
 __global__ void __launch_bounds__(CIG_THREADS)
@@ -103,7 +112,7 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
                    uint32_t* __restrict__ stats /* [n_rec][8] */) {
   __shared__ __align__(128) uint32_t s_ops[CIG_TILE];
   __shared__ int32_t s_off[CIG_CAP + 2];          // record starts relative to the tile, clamped
-  __shared__ uint32_t s_acc[CIG_CAP][5];
+  __shared__ uint32_t s_acc[CIG_CAP * 5];
   __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -111,15 +120,39 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
   const int64_t o0 = tile * CIG_TILE;
   const int tile_n = (int)min((int64_t)CIG_TILE, n_ops - o0);
   const int2 tr = tile_rec[tile];
-  const int64_t r_lo = tr.x, r_hi = tr.y;   // first / last record with an op in this tile
-  const int64_t n_loc = r_hi - r_lo + 1;
-  const bool use_smem = n_loc <= CIG_CAP;
+  const int64_t r_lo = tr.x;                      // first / last record with an op in this tile
+  const int n_loc = tr.y - tr.x + 1;
+  const int first = tid * CIG_OPT;
+  const int nb = min(CIG_OPT, tile_n - first);    // my ops (<= 0: none)
+
+  if (n_loc > CIG_CAP) {
+    // pathological tile (more than 1024 records in 2048 ops): global atomics, no staging
+    if (nb > 0) {
+      int64_t rl = upper_bound_minus1<uint64_t>(off + r_lo, n_loc, (uint64_t)(o0 + first));
+      CigAcc acc;
+      acc.clear();
+      for (int k = 0; k < nb; k++) {
+        const uint64_t o = (uint64_t)(o0 + first + k);
+        if (o >= off[r_lo + rl + 1]) {
+          if (acc.any()) acc.flush(stats + (r_lo + rl) * 8);
+          acc.clear();
+          do { rl++; } while (o >= off[r_lo + rl + 1]);
+        }
+        acc.add(cigar[o]);
+      }
+      if (acc.any()) acc.flush(stats + (r_lo + rl) * 8);
+    }
+    return;
+  }
 
 #if GCI_USE_TMA
   if (tid == 0) mbar_init(&s_bar, 1);
+#endif
+  for (int i = tid; i < n_loc * 5; i += CIG_THREADS) s_acc[i] = 0u;
   __syncthreads();
+#if GCI_USE_TMA
   if (tid == 0) {
-    uint32_t bytes = (uint32_t)((tile_n * 4 + 15) & ~15);
+    const uint32_t bytes = (uint32_t)((tile_n * 4 + 15) & ~15);
     mbar_expect_tx(&s_bar, bytes);
     tma_load_1d(s_ops, cigar + o0, bytes, &s_bar);
   }
@@ -127,37 +160,26 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
   for (int v = tid; v * 4 < tile_n; v += CIG_THREADS)
     reinterpret_cast<uint4*>(s_ops)[v] = reinterpret_cast<const uint4*>(cigar + o0)[v];
 #endif
-  if (use_smem) {
-    for (int i = tid; i <= n_loc; i += CIG_THREADS) {
-      long long rel = (long long)off[r_lo + i] - (long long)o0;
-      s_off[i] = (int32_t)max(-1ll, min(rel, (long long)CIG_TILE + 1));
-    }
-    for (int i = tid; i < n_loc * 5; i += CIG_THREADS) (&s_acc[0][0])[i] = 0u;
+  for (int i = tid; i <= n_loc; i += CIG_THREADS) {
+    const long long rel = (long long)off[r_lo + i] - (long long)o0;
+    s_off[i] = (int32_t)max(-1ll, min(rel, (long long)CIG_TILE + 1));
   }
 #if GCI_USE_TMA
   mbar_wait(&s_bar, 0);
 #endif
   __syncthreads();
 
-  const int first = tid * CIG_OPT;
-  const bool active = first < tile_n;
-  const int last = min(first + CIG_OPT, tile_n);
-  int64_t rl = 0;
-  long long next = 0;
+  const bool active = nb > 0;
+  int rl = 0, next = 0;
   uint32_t ops[CIG_OPT];
   if (active) {
-    // local record of my first op
-    if (use_smem) {
-      int lo = 0, hi = (int)n_loc;   // s_off[lo] <= first < s_off[hi] (virtual)
-      while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (s_off[mid] <= first) lo = mid; else hi = mid;
-      }
-      rl = lo;
-    } else {
-      rl = upper_bound_minus1<uint64_t>(off + r_lo, n_loc, (uint64_t)(o0 + first));
+    int lo = 0, hi = n_loc;                       // s_off[lo] <= first < s_off[hi] (virtual)
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_off[mid] <= first) lo = mid; else hi = mid;
     }
-    next = use_smem ? (long long)s_off[rl + 1] : (long long)off[r_lo + rl + 1] - (long long)o0;
+    rl = lo;
+    next = s_off[rl + 1];
     const uint4 a = reinterpret_cast<const uint4*>(s_ops)[tid * 2];
     const uint4 b = reinterpret_cast<const uint4*>(s_ops)[tid * 2 + 1];
     ops[0] = a.x; ops[1] = a.y; ops[2] = a.z; ops[3] = a.w;
@@ -165,62 +187,40 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
   }
   CigAcc acc;
   acc.clear();
-  // fast path: the whole warp sits inside one record -> shuffle-reduce, one flush per warp
-  const bool one_rec = active && (next >= (long long)(first + CIG_OPT)) && (first + CIG_OPT <= tile_n);
-  const int64_t rl0 = __shfl_sync(0xffffffffu, rl, 0);
-  const bool warp_one = __all_sync(0xffffffffu, one_rec && rl == rl0);
-  if (warp_one) {
+  const bool simple = active && next >= first + nb;                 // all my ops belong to record rl
+  const int rl0 = __shfl_sync(0xffffffffu, rl, 0);
+  const bool warp_one = __all_sync(0xffffffffu, simple && nb == CIG_OPT && rl == rl0);
+  if (simple) {
 #pragma unroll
-    for (int k = 0; k < CIG_OPT; k++) acc.add(ops[k]);
-    acc.mx = warp_sum(acc.mx); acc.i = warp_sum(acc.i); acc.d = warp_sum(acc.d);
+    for (int k = 0; k < CIG_OPT; k++)
+      if (k < nb) acc.add(ops[k]);
+  }
+  if (warp_one) {
+    // the whole warp sits inside one record (ONT): shuffle-reduce, one flush per warp
+    acc.tot = warp_sum(acc.tot); acc.i = warp_sum(acc.i); acc.d = warp_sum(acc.d);
     acc.n = warp_sum(acc.n); acc.s = warp_sum(acc.s);
-    if (lane == 0) {
-      uint32_t* p = use_smem ? s_acc[rl] : stats + (r_lo + rl) * 8;
-      if (acc.mx) atomicAdd(p + 0, acc.mx);
-      if (acc.i) atomicAdd(p + 1, acc.i);
-      if (acc.d) atomicAdd(p + 2, acc.d);
-      if (acc.n) atomicAdd(p + 3, acc.n);
-      if (acc.s) atomicAdd(p + 4, acc.s);
-    }
+    if (lane == 0) acc.flush(&s_acc[rl * 5]);
+  } else if (simple) {
+    acc.flush(&s_acc[rl * 5]);
   } else if (active) {
 #pragma unroll
     for (int k = 0; k < CIG_OPT; k++) {
-      const int o = first + k;
-      if (o < last) {
-        if ((long long)o >= next) {
-          // crossed into the next record (skip zero-op records)
-          if (acc.any()) {
-            uint32_t* p = use_smem ? s_acc[rl] : stats + (r_lo + rl) * 8;
-            if (acc.mx) atomicAdd(p + 0, acc.mx);
-            if (acc.i) atomicAdd(p + 1, acc.i);
-            if (acc.d) atomicAdd(p + 2, acc.d);
-            if (acc.n) atomicAdd(p + 3, acc.n);
-            if (acc.s) atomicAdd(p + 4, acc.s);
-            acc.clear();
-          }
-          do {
-            rl++;
-            next = use_smem ? (long long)s_off[rl + 1] : (long long)off[r_lo + rl + 1] - (long long)o0;
-          } while ((long long)o >= next);
+      if (k < nb) {
+        if (first + k >= next) {                  // crossed into the next record (skip zero-op records)
+          if (acc.any()) acc.flush(&s_acc[rl * 5]);
+          acc.clear();
+          do { rl++; next = s_off[rl + 1]; } while (first + k >= next);
         }
         acc.add(ops[k]);
       }
     }
-    if (acc.any()) {
-      uint32_t* p = use_smem ? s_acc[rl] : stats + (r_lo + rl) * 8;
-      if (acc.mx) atomicAdd(p + 0, acc.mx);
-      if (acc.i) atomicAdd(p + 1, acc.i);
-      if (acc.d) atomicAdd(p + 2, acc.d);
-      if (acc.n) atomicAdd(p + 3, acc.n);
-      if (acc.s) atomicAdd(p + 4, acc.s);
-    }
+    if (acc.any()) acc.flush(&s_acc[rl * 5]);
   }
-  if (!use_smem) return;
   __syncthreads();
   for (int i = tid; i < n_loc; i += CIG_THREADS) {
     const bool complete = s_off[i] >= 0 && s_off[i + 1] <= tile_n;
     uint32_t* g = stats + (r_lo + i) * 8;
-    const uint32_t* p = s_acc[i];
+    const uint32_t* p = &s_acc[i * 5];
     if (complete) {
       *reinterpret_cast<uint4*>(g) = make_uint4(p[0], p[1], p[2], p[3]);
       g[4] = p[4];
@@ -375,10 +375,14 @@ __global__ void join_kernel(JoinArgs a, uint32_t n_reads, const uint8_t* __restr
 // ================================================================================================
 // host drivers
 // ================================================================================================
-static int check_err(gci_ctx* ctx, const char* where) {
-  unsigned long long h[2];
-  GCI_CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_err.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+// one D2H of [error mask, first index, survivor count] through pinned memory, one sync
+static int check_err(gci_ctx* ctx, const char* where, unsigned long long* count) {
+  unsigned long long* h = (unsigned long long*)ctx->pinned(4 * sizeof(unsigned long long));
+  if (!h) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
+  GCI_CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_err.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                    ctx->stream));
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (count) *count = h[2];
   if (h[0] == 0) return GCI_OK;
   const char* what = (h[0] & 1)   ? "record without NM tag (KeyError at GCI.py:163)"
                      : (h[0] & 2) ? "ZeroDivisionError at GCI.py:165 (clip ratio: no M/=/X/I/S bases)"
@@ -390,8 +394,20 @@ static int check_err(gci_ctx* ctx, const char* where) {
 
 static int reset_err(gci_ctx* ctx) {
   GCI_TRY(ctx->ensure(ctx->d_err, 4 * sizeof(unsigned long long)));
-  unsigned long long init[4] = {0ull, ~0ull, 0ull, 0ull};
-  GCI_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_err.p, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+  // [0] error mask = 0, [1] first offending index = ~0, [2] survivor count = 0
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_err.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_err.as<unsigned long long>() + 1, 0xff, sizeof(unsigned long long),
+                                    ctx->stream));
+  return GCI_OK;
+}
+
+int gci_index_bam(gci_ctx* ctx, BamFile& b) {
+  if (b.n == 0 || b.n_ops == 0) return GCI_OK;
+  const int64_t n_tiles = (b.n_ops + CIG_TILE - 1) / CIG_TILE;
+  GCI_TRY(ctx->ensure(b.tile_rec, sizeof(int2) * (size_t)(n_tiles + 1)));
+  cigar_tile_index_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, ctx->stream>>>(
+      b.cigar_off.as<uint64_t>(), b.n, b.tile_rec.as<int2>(), n_tiles, b.n_ops);
+  GCI_LAUNCH_CHECK(ctx);
   return GCI_OK;
 }
 
@@ -408,12 +424,8 @@ int gci_run_bam_leg(gci_ctx* ctx, int file_idx, int bam_idx, int32_t mq, int32_t
   GCI_CUDA_TRY(ctx, cudaMemsetAsync(b.stats.p, 0, 32 * (size_t)n, ctx->stream));
   if (b.n_ops > 0) {
     const int64_t n_tiles = (b.n_ops + CIG_TILE - 1) / CIG_TILE;
-    GCI_TRY(ctx->ensure(ctx->misc, sizeof(int2) * (size_t)(n_tiles + 1)));
-    cigar_tile_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
-        b.cigar_off.as<uint64_t>(), n, ctx->misc.as<int2>(), n_tiles, b.n_ops);
-    GCI_LAUNCH_CHECK(ctx);
     cigar_stats_kernel<<<(unsigned)n_tiles, CIG_THREADS, 0, ctx->stream>>>(
-        b.cigar.as<uint32_t>(), b.cigar_off.as<uint64_t>(), n, b.n_ops, ctx->misc.as<int2>(), n_tiles,
+        b.cigar.as<uint32_t>(), b.cigar_off.as<uint64_t>(), n, b.n_ops, b.tile_rec.as<int2>(), n_tiles,
         b.stats.as<uint32_t>());
     GCI_LAUNCH_CHECK(ctx);
   }
@@ -672,9 +684,7 @@ int gci_filter(gci_ctx* ctx, int32_t map_qual, int32_t mq_cutoff, double iden_pe
       GCI_TRY(gci_run_bam_leg(ctx, (int)i, ctx->files[i].src, map_qual, mq_cutoff, iden_percent, clip_percent));
   GCI_TRY(gci_run_join(ctx, ovlp_percent));
   unsigned long long cnt = 0;
-  GCI_CUDA_TRY(ctx, cudaMemcpyAsync(&cnt, ctx->d_err.as<unsigned long long>() + 2, sizeof cnt,
-                                    cudaMemcpyDeviceToHost, ctx->stream));
-  GCI_TRY(check_err(ctx, "gci_filter"));
+  GCI_TRY(check_err(ctx, "gci_filter", &cnt));
   ctx->n_survivors = (int64_t)cnt;
   ctx->filtered = true;
   if (n_survivors) *n_survivors = ctx->n_survivors;

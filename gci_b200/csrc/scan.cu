@@ -70,6 +70,43 @@ scan_apply_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n, co
   if (total && blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) *total = run;
 }
 
+// one block walks the whole array with a running carry: one launch for arrays up to ~10^5 items
+// (tile tables, run chunks) instead of reduce + scan + apply
+constexpr int SCAN1_THREADS = 1024;
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(SCAN1_THREADS)
+scan_single_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n, TO* __restrict__ total) {
+  __shared__ TO s_w[SCAN1_THREADS / 32];
+  __shared__ TO s_carry;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += SCAN1_THREADS) {
+    const int64_t i = base + threadIdx.x;
+    const TO v = i < n ? (TO)in[i] : (TO)0;
+    TO incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      TO t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    TO woff = 0, tot = 0;
+    for (int j = 0; j < SCAN1_THREADS / 32; j++) {
+      const TO x = s_w[j];
+      if (j < w) woff += x;
+      tot += x;
+    }
+    const TO carry = s_carry;
+    if (i < n) out[i] = carry + woff + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + tot;
+    __syncthreads();
+  }
+  if (total && threadIdx.x == 0) *total = s_carry;
+}
+
 template <typename TI, typename TO>
 static int exclusive_scan(gci_ctx* ctx, const TI* in, TO* out, int64_t n, TO* total_dev, int depth = 0) {
   if (n <= 0) {
@@ -77,8 +114,8 @@ static int exclusive_scan(gci_ctx* ctx, const TI* in, TO* out, int64_t n, TO* to
     return GCI_OK;
   }
   const int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-  if (nb == 1) {
-    scan_apply_kernel<TI, TO><<<1, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, nullptr, total_dev);
+  if (n <= 96 * 1024) {
+    scan_single_kernel<TI, TO><<<1, SCAN1_THREADS, 0, ctx->stream>>>(in, out, n, total_dev);
     GCI_LAUNCH_CHECK(ctx);
     return GCI_OK;
   }
@@ -169,27 +206,28 @@ __global__ void genome_windows_kernel(int32_t n_contigs, const int64_t* __restri
 struct RunWin {
   int64_t g0;       // global padded position of the contig start
   int64_t lo, hi;   // window in contig coordinates
-  int64_t w0;       // first word (contig-relative) = lo >> 5
-  int64_t n_words;  // words covering [lo, hi] inclusive
+  int64_t w0;       // first word (contig-relative) of the chunk layout, <= lo >> 5
+  int64_t n_words;  // words of the layout: covers [w0 * 32, hi] inclusive
 };
 
 __device__ __forceinline__ RunWin load_win(int64_t o, const int32_t* w_contig, const int64_t* w_lo, const int64_t* w_hi,
-                                           const int64_t* tile_off) {
+                                           const int64_t* lay_w0, const int64_t* tile_off) {
   RunWin w;
   w.g0 = tile_off[w_contig[o]] * GCI_TILE;
   w.lo = w_lo[o];
   w.hi = w_hi[o];
-  w.w0 = w.lo >> 5;
+  w.w0 = lay_w0[o];
   w.n_words = w.hi > w.lo ? (w.hi >> 5) - w.w0 + 1 : 0;
   return w;
 }
 
-// flag word `j` (window-relative) restricted to the window
+// flag word `j` (layout-relative) restricted to the window
 __device__ __forceinline__ uint32_t win_word(const uint32_t* __restrict__ flags, const RunWin& w, int64_t j) {
   if (j < 0 || j >= w.n_words) return 0u;
   const int64_t cw = w.w0 + j;                  // contig-relative word
-  uint32_t m = flags[(w.g0 >> 5) + cw];
   const int64_t p0 = cw << 5;
+  if (p0 + 32 <= w.lo) return 0u;
+  uint32_t m = flags[(w.g0 >> 5) + cw];
   if (p0 < w.lo) m &= 0xffffffffu << (w.lo - p0);
   if (p0 + 32 > w.hi) {
     const int64_t keep = w.hi - p0;             // bits [0, keep) stay
@@ -206,13 +244,13 @@ template <bool WRITE>
 __global__ void __launch_bounds__(RUN_THREADS)
 runs_kernel(const uint32_t* __restrict__ flags, int64_t n_owners, const int64_t* __restrict__ chunk_off,
             const int32_t* __restrict__ w_contig, const int64_t* __restrict__ w_lo, const int64_t* __restrict__ w_hi,
-            const int64_t* __restrict__ tile_off, int32_t* __restrict__ cnt_s, int32_t* __restrict__ cnt_e,
-            const int64_t* __restrict__ off_s, const int64_t* __restrict__ off_e, int32_t* __restrict__ iv_start,
-            int32_t* __restrict__ iv_end) {
+            const int64_t* __restrict__ lay_w0, const int64_t* __restrict__ tile_off, int2* __restrict__ cnt,
+            const longlong2* __restrict__ off, int32_t* __restrict__ iv_start, int32_t* __restrict__ iv_end,
+            int64_t cap) {
   __shared__ int s_ws[RUN_THREADS / 32], s_we[RUN_THREADS / 32];
   const int64_t chunk = blockIdx.x;
   const int64_t o = upper_bound_minus1<int64_t>(chunk_off, n_owners + 1, chunk);
-  const RunWin w = load_win(o, w_contig, w_lo, w_hi, tile_off);
+  const RunWin w = load_win(o, w_contig, w_lo, w_hi, lay_w0, tile_off);
   const int64_t j0 = (chunk - chunk_off[o]) * GCI_RUN_CHUNK_WORDS + (int64_t)threadIdx.x * RUN_WPT;
   uint32_t st[RUN_WPT], en[RUN_WPT];
   int ns = 0, ne = 0;
@@ -223,7 +261,7 @@ runs_kernel(const uint32_t* __restrict__ flags, int64_t n_owners, const int64_t*
     const uint32_t sh = (m << 1) | (prev >> 31);
     st[k] = m & ~sh;
     en[k] = ~m & sh;
-    // an end can only be reported on a word that exists in the window (positions <= hi)
+    // an end can only be reported on a word that exists in the layout (positions <= hi)
     if (j0 + k >= w.n_words) en[k] = 0u;
     ns += __popc(st[k]);
     ne += __popc(en[k]);
@@ -239,11 +277,13 @@ runs_kernel(const uint32_t* __restrict__ flags, int64_t n_owners, const int64_t*
     ts += s_ws[j]; te += s_we[j];
   }
   if (!WRITE) {
-    if (threadIdx.x == 0) { cnt_s[chunk] = ts; cnt_e[chunk] = te; }
+    if (threadIdx.x == 0) cnt[chunk] = make_int2(ts, te);
     return;
   }
-  int64_t ps = off_s[chunk] + bs + is - ns;
-  int64_t pe = off_e[chunk] + be + ie - ne;
+  if (ts == 0 && te == 0) return;
+  const longlong2 base = off[chunk];
+  int64_t ps = base.x + bs + is - ns;
+  int64_t pe = base.y + be + ie - ne;
 #pragma unroll
   for (int k = 0; k < RUN_WPT; k++) {
     const int64_t p0 = (w.w0 + j0 + k) << 5;
@@ -251,141 +291,193 @@ runs_kernel(const uint32_t* __restrict__ flags, int64_t n_owners, const int64_t*
     while (m) {
       const int b = __ffs(m) - 1;
       m &= m - 1;
-      iv_start[ps++] = (int32_t)(p0 + b);
+      if (ps < cap) iv_start[ps] = (int32_t)(p0 + b);
+      ps++;
     }
     m = en[k];
     while (m) {
       const int b = __ffs(m) - 1;
       m &= m - 1;
-      iv_end[pe++] = (int32_t)(p0 + b);
+      if (pe < cap) iv_end[pe] = (int32_t)(p0 + b);
+      pe++;
     }
   }
 }
 
-__global__ void owner_offsets_kernel(int64_t n_owners, const int64_t* __restrict__ chunk_off,
-                                     const int64_t* __restrict__ off_s, const int64_t* __restrict__ total_s,
-                                     int64_t n_chunks, int64_t* __restrict__ owner_off) {
-  const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (o > n_owners) return;
-  const int64_t ch = chunk_off[o];
-  owner_off[o] = (o == n_owners || ch >= n_chunks) ? *total_s : off_s[ch];
+// one block: exclusive scan of the (starts, ends) chunk counts, totals, and the per-owner interval offsets
+__global__ void __launch_bounds__(1024)
+runs_scan_kernel(const int2* __restrict__ cnt, int64_t n_chunks, longlong2* __restrict__ off, int64_t n_owners,
+                 const int64_t* __restrict__ chunk_off, int64_t* __restrict__ owner_off /* [n_owners+1 | total_s | total_e] */) {
+  __shared__ long long s_ws[32], s_we[32];
+  __shared__ long long s_cs, s_ce;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_cs = 0; s_ce = 0; }
+  __syncthreads();
+  for (int64_t base = 0; base < n_chunks; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const int2 v = i < n_chunks ? cnt[i] : make_int2(0, 0);
+    long long is = v.x, ie = v.y;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long a = __shfl_up_sync(0xffffffffu, is, d), b = __shfl_up_sync(0xffffffffu, ie, d);
+      if (lane >= d) { is += a; ie += b; }
+    }
+    if (lane == 31) { s_ws[w] = is; s_we[w] = ie; }
+    __syncthreads();
+    long long os = 0, oe = 0, ts = 0, te = 0;
+    for (int j = 0; j < 32; j++) {
+      const long long a = s_ws[j], b = s_we[j];
+      if (j < w) { os += a; oe += b; }
+      ts += a; te += b;
+    }
+    const long long cs = s_cs, ce = s_ce;
+    if (i < n_chunks) off[i] = make_longlong2(cs + os + is - v.x, ce + oe + ie - v.y);
+    __syncthreads();
+    if (threadIdx.x == 0) { s_cs = cs + ts; s_ce = ce + te; }
+    __syncthreads();
+  }
+  for (int64_t o = threadIdx.x; o <= n_owners; o += 1024) {
+    const int64_t ch = chunk_off[o];
+    owner_off[o] = (o == n_owners || ch >= n_chunks) ? s_cs : off[ch].x;
+  }
+  if (threadIdx.x == 0) { owner_off[n_owners + 1] = s_cs; owner_off[n_owners + 2] = s_ce; }
 }
 
-// shared tail of gci_scan / gci_scan_windows: windows are on the device in t.win_*
-static int extract_runs(gci_ctx* ctx, Track& t, const std::vector<int64_t>& h_lo, const std::vector<int64_t>& h_hi,
+// shared tail of gci_scan / gci_scan_windows.  The chunk layout comes from host-known bounds
+// (lay_lo[o] <= real window start, hi[o] = real window end); the real windows are on the device.
+static int extract_runs(gci_ctx* ctx, Track& t, const std::vector<int64_t>& lay_lo, const std::vector<int64_t>& h_hi,
                         int64_t* n_intervals) {
   const int64_t n_owners = t.n_owners;
-  std::vector<int64_t> chunk_off(n_owners + 1, 0);
+  std::vector<int64_t> lay(2 * (n_owners + 1), 0);     // [chunk_off (n+1) | w0 (n) ...]
+  int64_t* chunk_off = lay.data();
+  int64_t* w0 = lay.data() + n_owners + 1;
   for (int64_t o = 0; o < n_owners; o++) {
-    const int64_t nw = h_hi[o] > h_lo[o] ? (h_hi[o] >> 5) - (h_lo[o] >> 5) + 1 : 0;
+    w0[o] = lay_lo[o] >> 5;
+    const int64_t nw = h_hi[o] > lay_lo[o] ? (h_hi[o] >> 5) - w0[o] + 1 : 0;
     chunk_off[o + 1] = chunk_off[o] + (nw + GCI_RUN_CHUNK_WORDS - 1) / GCI_RUN_CHUNK_WORDS;
   }
   const int64_t n_chunks = chunk_off[n_owners];
-  GCI_TRY(gci_h2d(ctx, ctx->chunk_off, chunk_off.data(), sizeof(int64_t) * (n_owners + 1)));
-  GCI_TRY(ctx->ensure(t.owner_off, sizeof(int64_t) * (size_t)(n_owners + 1)));
+  t.h_owner_off.assign(n_owners + 1, 0);
   t.n_intervals = 0;
+  if (n_intervals) *n_intervals = 0;
+  GCI_TRY(ctx->ensure(t.owner_off, sizeof(int64_t) * (size_t)(n_owners + 3)));
   if (n_chunks == 0) {
-    GCI_CUDA_TRY(ctx, cudaMemsetAsync(t.owner_off.p, 0, sizeof(int64_t) * (n_owners + 1), ctx->stream));
-    GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (n_intervals) *n_intervals = 0;
+    GCI_CUDA_TRY(ctx, cudaMemsetAsync(t.owner_off.p, 0, sizeof(int64_t) * (n_owners + 3), ctx->stream));
     return GCI_OK;
   }
-  // chunk_cnt: [cnt_s | cnt_e] int32, scan_tmp: [off_s | off_e | total_s | total_e] int64
-  GCI_TRY(ctx->ensure(ctx->chunk_cnt, sizeof(int32_t) * 2 * (size_t)n_chunks));
-  GCI_TRY(ctx->ensure(ctx->scan_tmp, sizeof(int64_t) * (2 * (size_t)n_chunks + 2)));
-  int32_t* cnt_s = ctx->chunk_cnt.as<int32_t>();
-  int32_t* cnt_e = cnt_s + n_chunks;
-  int64_t* off_s = ctx->scan_tmp.as<int64_t>();
-  int64_t* off_e = off_s + n_chunks;
-  int64_t* tot = off_e + n_chunks;
-  runs_kernel<false><<<(unsigned)n_chunks, RUN_THREADS, 0, ctx->stream>>>(
-      t.flags.as<uint32_t>(), n_owners, ctx->chunk_off.as<int64_t>(), t.win_contig.as<int32_t>(),
-      t.win_lo.as<int64_t>(), t.win_hi.as<int64_t>(), ctx->d_tile_off.as<int64_t>(), cnt_s, cnt_e, nullptr, nullptr,
-      nullptr, nullptr);
-  GCI_LAUNCH_CHECK(ctx);
-  GCI_TRY(gci_exclusive_scan_i64_from_i32(ctx, cnt_s, off_s, n_chunks, tot));
-  GCI_TRY(gci_exclusive_scan_i64_from_i32(ctx, cnt_e, off_e, n_chunks, tot + 1));
-  int64_t h_tot[2];
-  GCI_TRY(gci_d2h(ctx, h_tot, tot, sizeof h_tot));
-  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  if (h_tot[0] != h_tot[1])
-    return ctx->fail(GCI_E_CUDA, "internal: run starts (%lld) != run ends (%lld)", (long long)h_tot[0],
-                     (long long)h_tot[1]);
-  t.n_intervals = h_tot[0];
-  GCI_TRY(ctx->ensure(t.iv_start, sizeof(int32_t) * (size_t)std::max<int64_t>(1, t.n_intervals)));
-  GCI_TRY(ctx->ensure(t.iv_end, sizeof(int32_t) * (size_t)std::max<int64_t>(1, t.n_intervals)));
-  if (t.n_intervals) {
-    runs_kernel<true><<<(unsigned)n_chunks, RUN_THREADS, 0, ctx->stream>>>(
-        t.flags.as<uint32_t>(), n_owners, ctx->chunk_off.as<int64_t>(), t.win_contig.as<int32_t>(),
-        t.win_lo.as<int64_t>(), t.win_hi.as<int64_t>(), ctx->d_tile_off.as<int64_t>(), nullptr, nullptr, off_s, off_e,
-        t.iv_start.as<int32_t>(), t.iv_end.as<int32_t>());
-    GCI_LAUNCH_CHECK(ctx);
+  if (n_chunks >= (int64_t(1) << 31)) return ctx->fail(GCI_E_ARG, "too many run chunks");
+  GCI_TRY(gci_h2d(ctx, ctx->chunk_off, lay.data(), sizeof(int64_t) * lay.size()));
+  const int64_t* d_chunk_off = ctx->chunk_off.as<int64_t>();
+  const int64_t* d_w0 = d_chunk_off + n_owners + 1;
+  GCI_TRY(ctx->ensure(ctx->chunk_cnt, sizeof(int2) * (size_t)n_chunks));
+  GCI_TRY(ctx->ensure(ctx->scan_tmp, sizeof(longlong2) * (size_t)n_chunks));
+  int2* cnt = ctx->chunk_cnt.as<int2>();
+  longlong2* off = ctx->scan_tmp.as<longlong2>();
+  if (t.iv_cap < 4096) {
+    GCI_TRY(ctx->ensure(t.iv_start, sizeof(int32_t) * 4096));
+    GCI_TRY(ctx->ensure(t.iv_end, sizeof(int32_t) * 4096));
+    t.iv_cap = 4096;
   }
-  owner_offsets_kernel<<<(unsigned)((n_owners + 1 + 255) / 256), 256, 0, ctx->stream>>>(
-      n_owners, ctx->chunk_off.as<int64_t>(), off_s, tot, n_chunks, t.owner_off.as<int64_t>());
+  runs_kernel<false><<<(unsigned)n_chunks, RUN_THREADS, 0, ctx->stream>>>(
+      t.flags.as<uint32_t>(), n_owners, d_chunk_off, t.win_contig.as<int32_t>(), t.win_lo.as<int64_t>(),
+      t.win_hi.as<int64_t>(), d_w0, ctx->d_tile_off.as<int64_t>(), cnt, nullptr, nullptr, nullptr, 0);
   GCI_LAUNCH_CHECK(ctx);
-  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  runs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, n_chunks, off, n_owners, d_chunk_off, t.owner_off.as<int64_t>());
+  GCI_LAUNCH_CHECK(ctx);
+  int64_t* h = (int64_t*)ctx->pinned(sizeof(int64_t) * (size_t)(n_owners + 3));
+  if (!h) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
+  for (int attempt = 0; attempt < 2; attempt++) {
+    runs_kernel<true><<<(unsigned)n_chunks, RUN_THREADS, 0, ctx->stream>>>(
+        t.flags.as<uint32_t>(), n_owners, d_chunk_off, t.win_contig.as<int32_t>(), t.win_lo.as<int64_t>(),
+        t.win_hi.as<int64_t>(), d_w0, ctx->d_tile_off.as<int64_t>(), nullptr, off, t.iv_start.as<int32_t>(),
+        t.iv_end.as<int32_t>(), t.iv_cap);
+    GCI_LAUNCH_CHECK(ctx);
+    if (attempt == 0) {
+      GCI_TRY(gci_d2h(ctx, h, t.owner_off.p, sizeof(int64_t) * (size_t)(n_owners + 3)));
+    }
+    GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h[n_owners + 1] != h[n_owners + 2])
+      return ctx->fail(GCI_E_CUDA, "internal: run starts (%lld) != run ends (%lld)", (long long)h[n_owners + 1],
+                       (long long)h[n_owners + 2]);
+    if (h[n_owners + 1] <= t.iv_cap) break;
+    // more intervals than the buffers hold: grow once and write again
+    const int64_t want = h[n_owners + 1] + h[n_owners + 1] / 4;
+    GCI_TRY(ctx->ensure(t.iv_start, sizeof(int32_t) * (size_t)want));
+    GCI_TRY(ctx->ensure(t.iv_end, sizeof(int32_t) * (size_t)want));
+    t.iv_cap = want;
+  }
+  t.n_intervals = h[n_owners + 1];
+  t.h_owner_off.assign(h, h + n_owners + 1);
   if (n_intervals) *n_intervals = t.n_intervals;
   return GCI_OK;
 }
 
 // ================================================================================================
-// K8  score terms: complement lengths, -dp merge count, N50 by bitwise weighted-median selection
+// K8  score terms: complement lengths, -dp merge count, N50
 // ================================================================================================
 // For owner o with window [S, E) and sorted disjoint intervals (s_i, e_i):
 //   gaps g_0 = s_0 - S, g_i = s_i - e_{i-1}, tail = E - e_last            (GCI.py:446-458)
 //   complement lengths = {g_i > 0} + {tail > 0}            or  [E - S] if there is no interval (:460)
 //   -dp merge (GCI.py:509-518) joins neighbours across every gap <= dist, starting from the sentinel
 //   (S,S) and ending at E, so the merged complement keeps exactly the gaps that are > dist (and > 0).
-//   N50 (GCI.py:473-479) = largest length v with  2 * sum{len >= v} >= total  -> found bit by bit.
-__global__ void complement_kernel(int64_t n_owners, const int64_t* __restrict__ owner_off,
-                                  const int32_t* __restrict__ iv_start, const int32_t* __restrict__ iv_end,
-                                  const int64_t* __restrict__ S, const int64_t* __restrict__ E,
-                                  const double* __restrict__ dist, int64_t* __restrict__ gaps /* [n_iv + n_owners] */,
-                                  int64_t* __restrict__ n_len, int64_t* __restrict__ n_ctg) {
-  // one block per owner; slot layout in `gaps`: owner o uses [owner_off[o] + o, owner_off[o+1] + o + 1)
+//   N50 (GCI.py:473-479) = largest length v with  2 * sum{len >= v} >= total.
+// Result buffer (int64): [ n50 (owners+1) | n_ctg (owners) | gap slots (n_intervals + owners) ];
+// owner o uses gap slots [owner_off[o] + o, owner_off[o+1] + o + 1).
+struct OwnerBounds { long long S, E; double dist; };
+
+__global__ void __launch_bounds__(256)
+complement_kernel(int64_t n_owners, const int64_t* __restrict__ owner_off, const int32_t* __restrict__ iv_start,
+                  const int32_t* __restrict__ iv_end, const OwnerBounds* __restrict__ ob, int64_t* __restrict__ res) {
+  __shared__ long long s_red[8];
   const int64_t o = blockIdx.x;
   const int64_t a = owner_off[o], b = owner_off[o + 1];
-  int64_t* g = gaps + a + o;
+  int64_t* g = res + (2 * n_owners + 1) + a + o;
   const int64_t n = b - a;
-  long long my_len = 0, my_ctg = 0;
-  const double d = dist[o];
+  const long long S = ob[o].S, E = ob[o].E;
+  const double d = ob[o].dist;
+  long long my_ctg = 0;
   if (n == 0) {
     if (threadIdx.x == 0) {
-      g[0] = E[o] - S[o];                                   // appended unconditionally (:460)
-      my_len = 1;
-      // merged = [(S,S)] then tail rule: (E - S) <= dist -> one segment (S,E) -> empty complement
-      my_ctg = ((double)(E[o] - S[o]) <= d) ? 0 : (E[o] > S[o] ? 1 : 0);
+      g[0] = E - S;                                         // appended unconditionally (:460)
+      // merged = [(S,S)] then the tail rule: (E - S) <= dist -> one segment (S,E) -> empty complement
+      my_ctg = ((double)(E - S) <= d) ? 0 : (E > S ? 1 : 0);
     }
   } else {
     for (int64_t i = threadIdx.x; i <= n; i += blockDim.x) {
       long long v;
       if (i < n) {
-        const long long prev = i == 0 ? S[o] : (long long)iv_end[a + i - 1];
+        const long long prev = i == 0 ? S : (long long)iv_end[a + i - 1];
         v = (long long)iv_start[a + i] - prev;
       } else {
-        v = E[o] - (long long)iv_end[b - 1];
+        v = E - (long long)iv_end[b - 1];
       }
       const bool emit = v > 0;
       g[i] = emit ? v : 0;
-      my_len += emit;
       my_ctg += (emit && (double)v > d);
     }
   }
-  my_len = warp_sum_ll(my_len);
   my_ctg = warp_sum_ll(my_ctg);
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd((unsigned long long*)&n_len[o], (unsigned long long)my_len);
-    atomicAdd((unsigned long long*)&n_ctg[o], (unsigned long long)my_ctg);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = my_ctg;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long tsum = 0;
+    for (int j = 0; j < 8; j++) tsum += s_red[j];
+    res[n_owners + 1 + o] = tsum;
   }
 }
 
-// N50 of the positive entries of vals[lo, hi): one block per segment
-__global__ void n50_kernel(const int64_t* __restrict__ vals, const int64_t* __restrict__ seg_lo,
-                           const int64_t* __restrict__ seg_hi, int64_t* __restrict__ out) {
-  __shared__ long long s_red[32];
+// N50 of the positive entries of one owner's gap slots (block o < n_owners) or of all slots (block n_owners)
+constexpr int N50_SMALL = 1024;
+__global__ void __launch_bounds__(256)
+n50_kernel(int64_t n_owners, const int64_t* __restrict__ owner_off, int64_t n_slots, int64_t* __restrict__ res) {
+  __shared__ long long s_red[8];
   __shared__ long long s_bcast;
-  const int64_t lo = seg_lo[blockIdx.x], hi = seg_hi[blockIdx.x];
+  __shared__ long long s_val[N50_SMALL];
+  const int64_t o = blockIdx.x;
+  const int64_t* vals = res + (2 * n_owners + 1);
+  const int64_t lo = o < n_owners ? owner_off[o] + o : 0;
+  const int64_t hi = o < n_owners ? owner_off[o + 1] + o + 1 : n_slots;
+  const int64_t n = hi - lo;
   auto block_sum = [&](long long v) -> long long {
     v = warp_sum_ll(v);
     __syncthreads();
@@ -393,26 +485,62 @@ __global__ void n50_kernel(const int64_t* __restrict__ vals, const int64_t* __re
     __syncthreads();
     if (threadIdx.x == 0) {
       long long t = 0;
-      for (int j = 0; j < (int)(blockDim.x >> 5); j++) t += s_red[j];
+      for (int j = 0; j < 8; j++) t += s_red[j];
       s_bcast = t;
     }
     __syncthreads();
     return s_bcast;
   };
-  long long part = 0;
-  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) part += vals[i] > 0 ? vals[i] : 0;
-  const long long total = block_sum(part);
+  auto block_max = [&](long long v) -> long long {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long t = 0;
+      for (int j = 0; j < 8; j++) t = max(t, s_red[j]);
+      s_bcast = t;
+    }
+    __syncthreads();
+    return s_bcast;
+  };
   long long best = 0;
-  if (total > 0) {
-    for (int bit = 40; bit >= 0; bit--) {
-      const long long cand = best | (1ll << bit);
-      part = 0;
-      for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) part += vals[i] >= cand ? vals[i] : 0;
-      const long long s = block_sum(part);
-      if (2 * s >= total) best = cand;
+  if (n <= N50_SMALL) {
+    // small list: every thread sums the lengths >= its own (shared-memory broadcast reads)
+    long long part = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const long long v = vals[lo + i] > 0 ? vals[lo + i] : 0;
+      s_val[i] = v;
+      part += v;
+    }
+    const long long total = block_sum(part);
+    long long cand = 0;
+    if (total > 0) {
+      for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long v = s_val[i];
+        if (v <= cand) continue;
+        long long s = 0;
+        for (int64_t j = 0; j < n; j++) s += s_val[j] >= v ? s_val[j] : 0;
+        if (2 * s >= total) cand = v;
+      }
+    }
+    best = block_max(cand);
+  } else {
+    long long part = 0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) part += vals[i] > 0 ? vals[i] : 0;
+    const long long total = block_sum(part);
+    if (total > 0) {
+      for (int bit = 31; bit >= 0; bit--) {
+        const long long cand = best | (1ll << bit);
+        part = 0;
+        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) part += vals[i] >= cand ? vals[i] : 0;
+        const long long s = block_sum(part);
+        if (2 * s >= total) best = cand;
+      }
     }
   }
-  if (threadIdx.x == 0) out[blockIdx.x] = best;
+  if (threadIdx.x == 0) res[o] = best;
 }
 
 extern "C" {
@@ -424,29 +552,48 @@ int gci_scan(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int32_t flank_
   if (!t.allocated) return ctx->fail(GCI_E_ARG, "gci_scan: track %d holds no depth", track);
   if (!t.flags_valid || t.flags_lo != lo || t.flags_hi != hi) GCI_TRY(gci_compute_flags(ctx, track, lo, hi));
   ctx->stage_begin(GCI_ST_RUNS);
-  // owners = selected contigs in header order
-  std::vector<int32_t> owner_of(ctx->n_contigs, -1);
+  // owners = selected contigs in header order; the owner map is cached on the device per contig table
   int64_t n_owners = 0;
-  for (int c = 0; c < ctx->n_contigs; c++)
-    if (ctx->selected[c]) owner_of[c] = (int32_t)n_owners++;
+  for (int c = 0; c < ctx->n_contigs; c++) n_owners += ctx->selected[c] ? 1 : 0;
+  if (ctx->d_owner_of.cap == 0 || ctx->owner_of_stale) {
+    std::vector<int32_t> owner_of(std::max(1, ctx->n_contigs), -1);
+    int32_t k = 0;
+    for (int c = 0; c < ctx->n_contigs; c++)
+      if (ctx->selected[c]) owner_of[c] = k++;
+    GCI_TRY(gci_h2d(ctx, ctx->d_owner_of, owner_of.data(), sizeof(int32_t) * owner_of.size()));
+    ctx->owner_of_stale = false;
+  }
   t.n_owners = n_owners;
   t.owners_are_windows = false;
+  t.scan_flank = flank_len;
   GCI_TRY(ctx->ensure(t.win_contig, sizeof(int32_t) * (size_t)std::max<int64_t>(1, n_owners)));
   GCI_TRY(ctx->ensure(t.win_lo, sizeof(int64_t) * (size_t)std::max<int64_t>(1, n_owners)));
   GCI_TRY(ctx->ensure(t.win_hi, sizeof(int64_t) * (size_t)std::max<int64_t>(1, n_owners)));
-  GCI_TRY(gci_h2d(ctx, ctx->misc, owner_of.data(), sizeof(int32_t) * ctx->n_contigs));
-  std::vector<int64_t> h_lo(n_owners), h_hi(n_owners);
+  // host-known layout bounds: the real window start is in [fl, 2*fl], its end is L - fl
+  std::vector<int64_t> lay_lo(n_owners), h_hi(n_owners);
+  t.owner_contig.assign(n_owners, 0);
+  {
+    int64_t o = 0;
+    for (int c = 0; c < ctx->n_contigs; c++) {
+      if (!ctx->selected[c]) continue;
+      const int64_t L = ctx->len[c];
+      const bool ok = flank_len >= 0 && L - 2 * (int64_t)flank_len > 0;
+      lay_lo[o] = ok ? flank_len : 0;
+      h_hi[o] = ok ? L - flank_len : 0;
+      t.owner_contig[o] = c;
+      o++;
+    }
+  }
+  int rc = GCI_OK;
   if (n_owners) {
     genome_windows_kernel<<<(ctx->n_contigs + 127) / 128, 128, 0, ctx->stream>>>(
         ctx->n_contigs, ctx->d_len.as<int64_t>(), ctx->d_selected.as<uint8_t>(), ctx->d_tile_off.as<int64_t>(),
         t.flags.as<uint32_t>(), flank_len, t.win_contig.as<int32_t>(), t.win_lo.as<int64_t>(), t.win_hi.as<int64_t>(),
-        ctx->misc.as<int32_t>());
-    GCI_LAUNCH_CHECK(ctx);
-    GCI_TRY(gci_d2h(ctx, h_lo.data(), t.win_lo.p, sizeof(int64_t) * n_owners));
-    GCI_TRY(gci_d2h(ctx, h_hi.data(), t.win_hi.p, sizeof(int64_t) * n_owners));
-    GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->d_owner_of.as<int32_t>());
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) rc = ctx->fail(GCI_E_CUDA, "genome_windows_kernel launch failed");
   }
-  int rc = extract_runs(ctx, t, h_lo, h_hi, n_intervals);
+  if (rc == GCI_OK) rc = extract_runs(ctx, t, lay_lo, h_hi, n_intervals);
   ctx->stage_end();
   return rc;
 }
@@ -477,9 +624,11 @@ int gci_scan_windows(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int64_
   }
   t.raw_lo.assign(start, start + n_windows);
   t.raw_hi.assign(end, end + n_windows);
+  t.owner_contig.assign(c2.begin(), c2.end());
   ctx->stage_begin(GCI_ST_RUNS);
   t.n_owners = n_windows;
   t.owners_are_windows = true;
+  t.scan_flank = 0;
   GCI_TRY(gci_h2d(ctx, t.win_contig, c2.data(), sizeof(int32_t) * n_windows));
   GCI_TRY(gci_h2d(ctx, t.win_lo, lo2.data(), sizeof(int64_t) * n_windows));
   GCI_TRY(gci_h2d(ctx, t.win_hi, hi2.data(), sizeof(int64_t) * n_windows));
@@ -501,13 +650,14 @@ int gci_load_intervals(gci_ctx* ctx, int32_t track, int64_t n_owners, const int3
   t.n_owners = n_owners;
   t.n_intervals = n;
   t.owners_are_windows = false;
-  std::vector<int64_t> zero(std::max<int64_t>(1, n_owners), 0);
-  GCI_TRY(gci_h2d(ctx, t.win_contig, contig, sizeof(int32_t) * n_owners));
-  GCI_TRY(gci_h2d(ctx, t.win_lo, zero.data(), sizeof(int64_t) * n_owners));
-  GCI_TRY(gci_h2d(ctx, t.win_hi, zero.data(), sizeof(int64_t) * n_owners));
-  GCI_TRY(gci_h2d(ctx, t.owner_off, owner_off, sizeof(int64_t) * (n_owners + 1)));
+  t.owner_contig.assign(contig, contig + n_owners);
+  t.h_owner_off.assign(owner_off, owner_off + n_owners + 1);
+  GCI_TRY(ctx->ensure(t.owner_off, sizeof(int64_t) * (size_t)(n_owners + 3)));
+  GCI_CUDA_TRY(ctx, cudaMemcpyAsync(t.owner_off.p, owner_off, sizeof(int64_t) * (n_owners + 1), cudaMemcpyHostToDevice,
+                                    ctx->stream));
   GCI_TRY(gci_h2d(ctx, t.iv_start, start, sizeof(int32_t) * n));
   GCI_TRY(gci_h2d(ctx, t.iv_end, end, sizeof(int32_t) * n));
+  t.iv_cap = std::max<int64_t>(t.iv_cap, n);
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return GCI_OK;
 }
@@ -518,79 +668,56 @@ int gci_score_terms(gci_ctx* ctx, int32_t track, double dist_percent, int32_t fl
   cudaSetDevice(ctx->device);
   Track& t = ctx->track[track];
   const int64_t no = t.n_owners;
-  if (no <= 0) return ctx->fail(GCI_E_ARG, "gci_score_terms: no scan on track %d", track);
-  // per-owner [S, E) and dist (GCI.py:505-508, :629-634)
-  std::vector<int32_t> wc(no);
-  std::vector<int64_t> wl(no), wh(no), S(no), E(no);
-  std::vector<double> dist(no);
-  GCI_TRY(gci_d2h(ctx, wc.data(), t.win_contig.p, sizeof(int32_t) * no));
-  GCI_TRY(gci_d2h(ctx, wl.data(), t.win_lo.p, sizeof(int64_t) * no));
-  GCI_TRY(gci_d2h(ctx, wh.data(), t.win_hi.p, sizeof(int64_t) * no));
-  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (no <= 0 || (int64_t)t.h_owner_off.size() != no + 1)
+    return ctx->fail(GCI_E_ARG, "gci_score_terms: no scan on track %d", track);
+  const int64_t n_slots = t.n_intervals + no;
+  const int64_t n_res = 2 * no + 1 + n_slots;
+  // per-owner [S, E) and dist (GCI.py:505-508, :629-634), staged through pinned memory
+  char* pin = (char*)ctx->pinned(sizeof(OwnerBounds) * (size_t)no + sizeof(int64_t) * (size_t)n_res);
+  if (!pin) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
+  OwnerBounds* ob = (OwnerBounds*)pin;
+  int64_t* h_res = (int64_t*)(pin + sizeof(OwnerBounds) * (size_t)no);
   for (int64_t o = 0; o < no; o++) {
     if (t.owners_are_windows) {
       // complement / merge use the region bounds as given (GCI.py:629-634), only the depth slice is
       // normalised (:627)
-      S[o] = t.raw_lo[o];
-      E[o] = t.raw_hi[o];
-      dist[o] = (double)(E[o] - S[o]) * dist_percent;       // targets_length = {target: exp_n50}
+      ob[o].S = t.raw_lo[o];
+      ob[o].E = t.raw_hi[o];
+      ob[o].dist = (double)(ob[o].E - ob[o].S) * dist_percent;      // targets_length = {target: exp_n50}
     } else {
-      const int64_t L = ctx->len[wc[o]];
-      S[o] = flank_len;
-      E[o] = L - flank_len;
-      dist[o] = (double)L * dist_percent;
+      const int64_t L = ctx->len[t.owner_contig[o]];
+      ob[o].S = flank_len;
+      ob[o].E = L - flank_len;
+      ob[o].dist = (double)L * dist_percent;
     }
   }
   ctx->stage_begin(GCI_ST_SCORE);
-  const int64_t n_slots = t.n_intervals + no;
-  DevBuf &dS = ctx->tmp[0], &dE = ctx->tmp[1], &dD = ctx->tmp[2], &gaps = ctx->tmp[3], &nlen = ctx->tmp[4],
-         &nctg = ctx->tmp[5], &seg = ctx->tmp[6], &n50d = ctx->tmp[7];
-  GCI_TRY(gci_h2d(ctx, dS, S.data(), 8 * no));
-  GCI_TRY(gci_h2d(ctx, dE, E.data(), 8 * no));
-  GCI_TRY(gci_h2d(ctx, dD, dist.data(), 8 * no));
-  GCI_TRY(ctx->ensure(gaps, 8 * (size_t)n_slots));
-  GCI_TRY(ctx->ensure(nlen, 8 * (size_t)no));
-  GCI_TRY(ctx->ensure(nctg, 8 * (size_t)no));
-  GCI_CUDA_TRY(ctx, cudaMemsetAsync(nlen.p, 0, 8 * no, ctx->stream));
-  GCI_CUDA_TRY(ctx, cudaMemsetAsync(nctg.p, 0, 8 * no, ctx->stream));
+  DevBuf &d_ob = ctx->tmp[0], &d_res = ctx->tmp[1];
+  GCI_TRY(gci_h2d(ctx, d_ob, ob, sizeof(OwnerBounds) * (size_t)no));
+  GCI_TRY(ctx->ensure(d_res, sizeof(int64_t) * (size_t)n_res));
   complement_kernel<<<(unsigned)no, 256, 0, ctx->stream>>>(no, t.owner_off.as<int64_t>(), t.iv_start.as<int32_t>(),
-                                                           t.iv_end.as<int32_t>(), dS.as<int64_t>(), dE.as<int64_t>(),
-                                                           dD.as<double>(), gaps.as<int64_t>(), nlen.as<int64_t>(),
-                                                           nctg.as<int64_t>());
+                                                           t.iv_end.as<int32_t>(), d_ob.as<OwnerBounds>(),
+                                                           d_res.as<int64_t>());
   GCI_LAUNCH_CHECK(ctx);
-  // segments for the N50 kernel: one per owner plus one over everything (the Genome row)
-  std::vector<int64_t> h_off(no + 1);
-  GCI_TRY(gci_d2h(ctx, h_off.data(), t.owner_off.p, 8 * (no + 1)));
-  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  std::vector<int64_t> seg_h(2 * (no + 1));
-  for (int64_t o = 0; o < no; o++) {
-    seg_h[o] = h_off[o] + o;
-    seg_h[no + 1 + o] = h_off[o + 1] + o + 1;
-  }
-  seg_h[no] = 0;
-  seg_h[2 * no + 1] = n_slots;
-  GCI_TRY(gci_h2d(ctx, seg, seg_h.data(), 8 * seg_h.size()));
-  GCI_TRY(ctx->ensure(n50d, 8 * (size_t)(no + 1)));
-  n50_kernel<<<(unsigned)(no + 1), 256, 0, ctx->stream>>>(gaps.as<int64_t>(), seg.as<int64_t>(),
-                                                          seg.as<int64_t>() + no + 1, n50d.as<int64_t>());
+  n50_kernel<<<(unsigned)(no + 1), 256, 0, ctx->stream>>>(no, t.owner_off.as<int64_t>(), n_slots, d_res.as<int64_t>());
   GCI_LAUNCH_CHECK(ctx);
+  GCI_TRY(gci_d2h(ctx, h_res, d_res.p, sizeof(int64_t) * (size_t)n_res));
   ctx->stage_end();
-  std::vector<int64_t> h_nctg(no), h_gaps(n_slots);
-  if (n50) GCI_TRY(gci_d2h(ctx, n50, n50d.p, 8 * (no + 1)));
-  GCI_TRY(gci_d2h(ctx, h_nctg.data(), nctg.p, 8 * no));
-  GCI_TRY(gci_d2h(ctx, h_gaps.data(), gaps.p, 8 * n_slots));
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n50) memcpy(n50, h_res, sizeof(int64_t) * (size_t)(no + 1));
   if (n_ctg) {
     int64_t all = 0;
-    for (int64_t o = 0; o < no; o++) { n_ctg[o] = h_nctg[o]; all += h_nctg[o]; }
+    for (int64_t o = 0; o < no; o++) { n_ctg[o] = h_res[no + 1 + o]; all += n_ctg[o]; }
     n_ctg[no] = all;
   }
   // compact the emitted lengths per owner, in position order (zero slots were not emitted, except the
   // unconditional [E - S] entry of an owner without intervals)
   int rc = GCI_OK;
   if (lengths_off || lengths) {
+    const int64_t* h_gaps = h_res + 2 * no + 1;
+    const std::vector<int64_t>& h_off = t.h_owner_off;
     int64_t k = 0;
-    for (int64_t o = 0; o < no; o++) {
+    for (int64_t o = 0; o < no && rc == GCI_OK; o++) {
       if (lengths_off) lengths_off[o] = k;
       const int64_t a = h_off[o] + o, b = h_off[o + 1] + o + 1;
       const bool empty = (h_off[o + 1] == h_off[o]);
@@ -603,9 +730,8 @@ int gci_score_terms(gci_ctx* ctx, int32_t track, double dist_percent, int32_t fl
           k++;
         }
       }
-      if (rc != GCI_OK) break;
     }
-    if (lengths_off) lengths_off[no] = k;
+    if (lengths_off && rc == GCI_OK) lengths_off[no] = k;
   }
   return rc;
 }
