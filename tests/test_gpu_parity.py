@@ -73,3 +73,27 @@ def test_bed_from_file_scores_like_reference(session, tmp_path):
     finally:
         s2.close()
     assert open(tmp_path / "B.gci").read() == open(os.path.join(GOLDEN, "mh63.gci")).read()
+
+
+def test_cli_on_real_files(tmp_path):
+    """GCI.py command line on real BAM / PAF / FASTA files written from a golden case; outputs must equal
+    the reference's."""
+    import subprocess, sys
+    from gci_b200 import io as gio
+    case, kw, expected = load_case("hifi_bam_paf")
+    names, lengths = kw["names"], kw["lengths"]
+    bam, paf = kw["hifi"]
+    gio.write_bam(str(tmp_path / "h.bam"), names, lengths, bam)
+    gio.write_paf(str(tmp_path / "h.paf"), paf, names, lengths)
+    gio.write_fasta(str(tmp_path / "ref.fa"), names, lengths, kw["n_runs"])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "GCI.py"), "-r", str(tmp_path / "ref.fa"), "--hifi",
+                        str(tmp_path / "h.bam"), str(tmp_path / "h.paf"), "-d", str(tmp_path / "out"), "-o", "T", "-t", "2",
+                        "-f"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("Used arguments:{") and r.stdout.rstrip().endswith("GCI finished!!!\nBye!!!")
+    got = {}
+    for fn in sorted(os.listdir(tmp_path / "out")):
+        p = str(tmp_path / "out" / fn)
+        got[fn] = gio.read_depth_gz(p) if fn.endswith(".depth.gz") else open(p).read()
+    assert_outputs_equal(got, expected)
