@@ -136,7 +136,10 @@ def run_reference(args, rank, world):
                                        "+=, per-base collapse loop, score rows)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
+_JSON_OUT = sys.stdout
 
 
 def main():
@@ -153,6 +156,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the contract is ONE JSON line on stdout: libraries (NCCL prints its version) write to fd 1 too, so
+    # fd 1 is pointed at stderr for the run and the JSON line goes to the saved descriptor
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -179,7 +187,8 @@ def main():
     from gci_b200.records import AlnTable
     pinned = AlnTable(*[pool.copy(getattr(tab, c)) for c in
                         ("ref_id", "ref_start", "mapq", "flag", "nm", "qlen", "read_id", "cigar_off", "cigar")])
-    depth_out = pool.empty(L[0], np.int32)
+    depth_out = pool.empty(L[0], np.uint8)
+    depth_out16 = pool.empty(L[0], np.uint16)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
     h2d_bytes = tab.nbytes()
     result = {}
@@ -203,7 +212,9 @@ def main():
         ctx.reads_begin(data.n_reads)
         ctx.upload_bam(pinned)
         n_iv = core_step()
-        ctx.fetch_depth(0, 0, depth_out)
+        got = ctx.fetch_depth_narrow(0, 0, depth_out, depth_out16)
+        result["d2h_depth_bytes"] = int(got.nbytes)
+        result["depth_dtype"] = str(got.dtype)
         ctx.fetch_intervals(0, 1)
         return n_iv
 
@@ -244,7 +255,11 @@ def main():
     ms_res = timed(resident_step, args.steps, 0)
     launches = ctx.kernel_launches - launches0
     stage = ctx.stage_report()
-    ms_e2e = timed(e2e_step, args.steps, args.warmup)
+    for _ in range(args.warmup):
+        e2e_step()
+    ctx.stage_reset()
+    ms_e2e = timed(e2e_step, args.steps, 0)
+    e2e_stage = {k: v[0] / args.steps for k, v in ctx.stage_report().items() if v[1]}
     clocks = sampler.stop() if rank == 0 else None
 
     aligned = np.array([data.aligned_bases], dtype=np.int64)
@@ -252,6 +267,9 @@ def main():
     value = total_aligned * args.steps / (ms_res * 1e-3) / 1e9
     e2e = total_aligned * args.steps / (ms_e2e * 1e-3) / 1e9
 
+    if world > 1:
+        tdist.barrier()
+        tdist.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (depth tiles) ----
@@ -261,9 +279,9 @@ def main():
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     d_ms, d_k = stage["depth"]
-    n_tiles = sum(l // 8192 + 1 for l in L)
+    n_tiles = sum(l // 1024 + 1 for l in L)            # one 1024-position tile per warp
     n_events = 2 * result["n_surv"]
-    alg_bytes = BYTES_PER_BASE * n_tiles * 8192 + 2.0 * n_events + 16.0 * n_tiles
+    alg_bytes = BYTES_PER_BASE * n_tiles * 1024 + 2.0 * n_events + 16.0 * n_tiles
     achieved = alg_bytes / (d_ms / max(1, d_k) * 1e-3) / 1e9 if d_ms > 0 else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "depth_tile_traffic.json")
@@ -287,10 +305,11 @@ def main():
                        "parallelism": "contig sharding, 1 process per GPU" if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(depth_out.nbytes + 8 * result["n_iv"] + 64),
+                    "d2h_bytes_per_step": int(result["d2h_depth_bytes"] + 8 * result["n_iv"] + 64),
+                    "depth_dtype": result["depth_dtype"], "stage_ms_per_step": e2e_stage,
                     "ms_per_step": ms_e2e / args.steps,
                     "note": "host->device copy of all record columns + CIGAR from pinned memory, full hot path, "
-                            "device->host copy of the int32 depth array, intervals and score terms"},
+                            "device->host copy of the per-base depth array (narrowed on the GPU to the smallest exact integer type), intervals and score terms"},
             "gpu_launches": int(launches),
             "roofline": roofline}
     if world == 1 and not args.no_cpu_baseline:
@@ -309,7 +328,7 @@ def main():
         line["cpu_baseline"] = {"value": data.aligned_bases * reps / dt / 1e9, "unit": UNIT, "cores": threads,
                                 "kind": "port",
                                 "sample": f"{reps} passes over the full workload (oracle/gci_oracle.c, pthreads)"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     pool.close()
 
 

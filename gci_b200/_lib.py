@@ -65,6 +65,7 @@ _SIGNATURES = {
     "gci_merge_max": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32]),
     "gci_load_depth": (C.c_int, [_p, _i32, _i32, _p, _i64]),
     "gci_fetch_depth": (C.c_int, [_p, _i32, _i32, _p, _i64]),
+    "gci_fetch_depth_narrow": (C.c_int, [_p, _i32, _i32, _p, _i64, _i32, C.POINTER(_i32)]),
     "gci_depth_sums": (C.c_int, [_p, _i32, _p]),
     "gci_depth_text": (C.c_int, [_p, _i32, _i32, _i64, _i64, _p, _i64, C.POINTER(_i64)]),
     "gci_scan": (C.c_int, [_p, _i32, _i32, _i32, _i32, C.POINTER(_i64)]),
@@ -296,6 +297,19 @@ class Context:
         assert out.dtype == np.int32 and out.size == n and out.flags.c_contiguous
         self._check(self._lib.gci_fetch_depth(self._h, track, contig, _ptr(out), n))
         return out
+
+    def fetch_depth_narrow(self, track, contig, out8=None, out16=None):
+        """Depth of one contig in the narrowest exact dtype (uint8 -> uint16 -> int32): the conversion runs on
+        the GPU, so 4x / 2x fewer bytes cross PCIe.  out8 / out16: optional preallocated (pinned) buffers."""
+        n = int(self.lengths[contig])
+        ovf = _i32()
+        for width, dt, buf in ((1, np.uint8, out8), (2, np.uint16, out16)):
+            out = buf if buf is not None else np.empty(n, dt)
+            assert out.dtype == dt and out.size == n
+            self._check(self._lib.gci_fetch_depth_narrow(self._h, track, contig, _ptr(out), n, width, C.byref(ovf)))
+            if ovf.value == 0:
+                return out
+        return self.fetch_depth(track, contig)
 
     def depth_sums(self, track):
         out = np.zeros(self.n_contigs, np.int64)

@@ -108,6 +108,7 @@ static void free_track(gci_ctx* ctx, Track& t) {
     ctx->release(*d);
   t.allocated = false;
   t.flags_valid = false;
+  t.sums_valid = false;
   t.n_intervals = t.n_owners = 0;
   t.owners_are_windows = false;
   t.raw_lo.clear();
@@ -129,6 +130,7 @@ int gci_alloc_track(gci_ctx* ctx, int track) {
   GCI_CUDA_TRY(ctx, cudaMemsetAsync(t.sums.p, 0, sizeof(int64_t) * (size_t)ctx->n_contigs, ctx->stream));
   t.allocated = true;
   t.flags_valid = false;
+  t.sums_valid = false;
   return GCI_OK;
 }
 
@@ -168,7 +170,7 @@ void gci_destroy(gci_ctx* ctx) {
   for (auto& t : ctx->track) free_track(ctx, t);
   for (DevBuf* d : {&ctx->d_len, &ctx->d_selected, &ctx->d_tile_off, &ctx->d_owner_of, &ctx->d_nr_contig, &ctx->d_nr_start,
                     &ctx->d_nr_end, &ctx->highq, &ctx->surv_contig, &ctx->surv_start, &ctx->surv_end,
-                    &ctx->tile_cnt, &ctx->tile_net, &ctx->tile_evoff, &ctx->tile_base, &ctx->events,
+                    &ctx->tile_cnt, &ctx->events,
                     &ctx->scan_tmp, &ctx->scan_tmp2, &ctx->misc, &ctx->d_err, &ctx->chunk_cnt, &ctx->chunk_off})
     ctx->release(*d);
   for (auto& d : ctx->scan_lvl) ctx->release(d);
@@ -315,11 +317,9 @@ int gci_reads_begin(gci_ctx* ctx, uint32_t n_reads) {
   if (!ctx) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  for (auto& b : ctx->bam) free_bam(ctx, b);
-  for (auto& f : ctx->files) free_table(ctx, f);
-  ctx->bam.clear();
+  ctx->n_bam = 0;                 // device buffers of the pools are kept and reused
+  ctx->n_files = 0;
   ctx->paf.clear();
-  ctx->files.clear();
   ctx->n_reads = n_reads;
   ctx->filtered = false;
   ctx->n_survivors = 0;
@@ -337,10 +337,10 @@ int gci_upload_bam(gci_ctx* ctx, int64_t n, const int32_t* ref_id, const int32_t
   if (n >= (int64_t(1) << 31)) return ctx->fail(GCI_E_ARG, "more than 2^31 records in one file");
   if (cigar_off[0] != 0 || cigar_off[n] != (uint64_t)n_ops)
     return ctx->fail(GCI_E_ARG, "cigar_off must start at 0 and end at n_ops");
-  if ((int)ctx->files.size() >= GCI_MAX_FILES) return ctx->fail(GCI_E_ARG, "too many files");
+  if ((int)ctx->n_files >= GCI_MAX_FILES) return ctx->fail(GCI_E_ARG, "too many files");
   cudaSetDevice(ctx->device);
-  ctx->bam.emplace_back();
-  BamFile& b = ctx->bam.back();
+  if (ctx->n_bam == ctx->bam.size()) ctx->bam.emplace_back();
+  BamFile& b = ctx->bam[ctx->n_bam++];
   b.n = n;
   b.n_ops = n_ops;
   ctx->stage_begin(GCI_ST_H2D);
@@ -355,11 +355,11 @@ int gci_upload_bam(gci_ctx* ctx, int64_t n, const int32_t* ref_id, const int32_t
   GCI_TRY(gci_h2d(ctx, b.cigar, cigar, 4 * n_ops));
   ctx->stage_end();
   GCI_TRY(gci_index_bam(ctx, b));   // op-tile -> record index: a property of the file, built once
-  FileTable f;
+  if (ctx->n_files == ctx->files.size()) ctx->files.emplace_back();
+  FileTable& f = ctx->files[ctx->n_files++];
   f.kind = 0;
-  f.src = (int)ctx->bam.size() - 1;
+  f.src = (int)ctx->n_bam - 1;
   f.n = n;
-  ctx->files.push_back(f);
   ctx->filtered = false;
   // the caller may reuse its host buffers as soon as we return
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -372,7 +372,7 @@ int gci_upload_paf(gci_ctx* ctx, int64_t n, const uint32_t* read_id, const int32
   if (!ctx || n < 0) return GCI_E_ARG;
   if (n && (!read_id || !qlen || !qstart || !qend || !ref_id || !tstart || !tend || !nmatch || !alnlen || !mapq))
     return GCI_E_ARG;
-  if ((int)ctx->files.size() >= GCI_MAX_FILES) return ctx->fail(GCI_E_ARG, "too many files");
+  if ((int)ctx->n_files >= GCI_MAX_FILES) return ctx->fail(GCI_E_ARG, "too many files");
   ctx->paf.emplace_back();
   PafFile& p = ctx->paf.back();
   p.n = n;
@@ -386,10 +386,11 @@ int gci_upload_paf(gci_ctx* ctx, int64_t n, const uint32_t* read_id, const int32
   p.nmatch.assign(nmatch, nmatch + n);
   p.alnlen.assign(alnlen, alnlen + n);
   p.mapq.assign(mapq, mapq + n);
-  FileTable f;
+  if (ctx->n_files == ctx->files.size()) ctx->files.emplace_back();
+  FileTable& f = ctx->files[ctx->n_files++];
   f.kind = 2;   // PAF lines awaiting the election in gci_filter
   f.src = (int)ctx->paf.size() - 1;
-  ctx->files.push_back(f);
+  f.n = 0;
   ctx->filtered = false;
   return GCI_OK;
 }
@@ -411,7 +412,7 @@ int gci_load_depth(gci_ctx* ctx, int32_t track, int32_t contig, const int32_t* d
   ctx->stage_end();
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   t.flags_valid = false;
-  // sums are recomputed lazily by gci_depth_sums (sum kernel lives in depth.cu)
+  t.sums_valid = false;   // recomputed lazily by gci_depth_sums
   return GCI_OK;
 }
 

@@ -15,8 +15,11 @@
 // The reference axis is cut into tiles of GCI_TILE positions; a tile never straddles two contigs
 // and every contig owns floor(L / TILE) + 1 tiles, so at least one padded position follows the
 // last base (the "-1" event of a read ending at L and the end of a run touching L - fl land there).
-constexpr int GCI_TILE = 8192;            // positions per depth tile (32 KB of int32)
-constexpr int GCI_TILE_THREADS = 256;
+// One warp expands one tile.  Padded positions hold depth 0 (every +1 has met its -1 by position L);
+// their flag bits are unspecified and never read (every consumer masks with the contig length).
+constexpr int GCI_TILE = 1024;            // positions per depth tile = per warp (4 KB of int32)
+constexpr int GCI_TILE_THREADS = 256;     // 8 warps = 8 independent tiles in flight per CTA
+constexpr int GCI_CHUNK = 8192;           // positions per CTA in the streaming kernels (max / flags / sum)
 constexpr int GCI_RUN_CHUNK_WORDS = 2048; // flag words (of 32 positions) per run-extraction chunk
 
 #define GCI_CUDA_TRY(ctx, expr)                                                              \
@@ -76,6 +79,7 @@ struct Track {
   bool flags_valid = false;
   int32_t flags_lo = 0, flags_hi = 0;
   DevBuf sums;             // int64[n_contigs]  sum of depth per contig
+  bool sums_valid = false; // kept up to date by gci_depth / gci_merge_max / gci_mask_gaps
   // last scan
   int64_t n_intervals = 0, n_owners = 0;
   bool owners_are_windows = false;
@@ -103,6 +107,7 @@ struct gci_ctx {
   int64_t launches = 0;
   int64_t dev_bytes = 0;
   int sm_count = 148;
+  int depth_ctas_per_sm = 0;        // resident CTAs of depth_tile_kernel per SM (occupancy query)
 
   // contigs
   int32_t n_contigs = 0;
@@ -120,9 +125,13 @@ struct gci_ctx {
 
   // read set
   uint32_t n_reads = 0;
+  // bam / files are pools: gci_reads_begin resets the used counts and keeps the device buffers, so a
+  // steady stream of read sets does not churn cudaMalloc / cudaFree
   std::vector<BamFile> bam;
+  size_t n_bam = 0;
   std::vector<PafFile> paf;
   std::vector<FileTable> files;     // join order
+  size_t n_files = 0;
   DevBuf highq;                     // uint8[n_reads]
   DevBuf surv_contig, surv_start, surv_end;   // int32[n_reads]; contig < 0 = not a survivor
   bool filtered = false;
@@ -130,7 +139,7 @@ struct gci_ctx {
   std::vector<int32_t> name_rank;   // host copy for the PAF election tie-break
 
   // depth scratch
-  DevBuf tile_cnt, tile_net, tile_evoff, tile_base, events, scan_tmp, scan_tmp2, misc, d_err;
+  DevBuf tile_cnt, events, scan_tmp, scan_tmp2, misc, d_err;
   DevBuf chunk_cnt, chunk_off;
   DevBuf scan_lvl[8];               // block sums / offsets of the recursive scan, two per level
   DevBuf tmp[10];                   // small per-call scratch (score terms, fetches)

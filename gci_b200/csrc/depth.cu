@@ -5,8 +5,7 @@
 
 #include "common.cuh"
 
-int gci_exclusive_scan_u64(gci_ctx* ctx, const unsigned long long* in, unsigned long long* out, int64_t n,
-                           unsigned long long* total_dev);
+int gci_scan_tile_pack(gci_ctx* ctx, ulonglong2* tile_ps, int64_t n);   // scan.cu: .y = exclusive scan of .x
 
 // ================================================================================================
 // K5  event buckets
@@ -42,7 +41,7 @@ constexpr unsigned long long EV_MINUS = 1ull + 0xffffffff00000000ull;  // count+
 
 __global__ void bucket_count_kernel(uint32_t n_reads, const int32_t* __restrict__ sc, const int32_t* __restrict__ ss,
                                     const int32_t* __restrict__ se, int32_t fl, const int64_t* __restrict__ len,
-                                    const int64_t* __restrict__ tile_off, unsigned long long* __restrict__ tile_pack,
+                                    const int64_t* __restrict__ tile_off, ulonglong2* __restrict__ tile_ps,
                                     long long* __restrict__ sums) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   int32_t c = -1;
@@ -51,8 +50,8 @@ __global__ void bucket_count_kernel(uint32_t n_reads, const int32_t* __restrict_
     c = sc[r];
     const Slice sl = survivor_slice(c, ss[r], se[r], fl, len, tile_off);
     if (sl.ok) {
-      atomicAdd(tile_pack + sl.tile_a, EV_PLUS);
-      atomicAdd(tile_pack + sl.tile_b, EV_MINUS);
+      atomicAdd(&tile_ps[sl.tile_a].x, EV_PLUS);
+      atomicAdd(&tile_ps[sl.tile_b].x, EV_MINUS);
       covered = sl.b - sl.a;
     } else {
       c = -1;
@@ -75,19 +74,19 @@ __global__ void bucket_count_kernel(uint32_t n_reads, const int32_t* __restrict_
 __global__ void bucket_fill_kernel(uint32_t n_reads, const int32_t* __restrict__ sc, const int32_t* __restrict__ ss,
                                    const int32_t* __restrict__ se, int32_t fl, const int64_t* __restrict__ len,
                                    const int64_t* __restrict__ tile_off,
-                                   const unsigned long long* __restrict__ tile_scan, uint32_t* __restrict__ cursor,
+                                   const ulonglong2* __restrict__ tile_ps, uint32_t* __restrict__ cursor,
                                    uint16_t* __restrict__ events) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const Slice sl = survivor_slice(sc[r], ss[r], se[r], fl, len, tile_off);
   if (!sl.ok) return;
   {
-    const uint32_t base = (uint32_t)(tile_scan[sl.tile_a] & 0xffffffffull);
+    const uint32_t base = (uint32_t)(tile_ps[sl.tile_a].y & 0xffffffffull);
     const uint32_t k = atomicAdd(cursor + sl.tile_a, 1u);
     events[base + k] = (uint16_t)(((uint32_t)(sl.a % GCI_TILE) << 1) | 0u);
   }
   {
-    const uint32_t base = (uint32_t)(tile_scan[sl.tile_b] & 0xffffffffull);
+    const uint32_t base = (uint32_t)(tile_ps[sl.tile_b].y & 0xffffffffull);
     const uint32_t k = atomicAdd(cursor + sl.tile_b, 1u);
     events[base + k] = (uint16_t)(((uint32_t)(sl.b % GCI_TILE) << 1) | 1u);
   }
@@ -102,22 +101,8 @@ __global__ void bucket_fill_kernel(uint32_t n_reads, const int32_t* __restrict__
 // tile scan, so there is no dependency between CTAs: the kernel is a pure streaming write of 4 B per
 // base (+ 1 bit per base of flags).
 
-// pack per-lane 4-bit nibbles (positions 4*lane .. 4*lane+3 of a 128-position warp row) into four
-// 32-bit words held by lanes 0, 8, 16, 24
-__device__ __forceinline__ uint32_t pack_nibbles(uint32_t nib, int lane) {
-  uint32_t w = nib << ((lane & 7) * 4);
-  w |= __shfl_xor_sync(0xffffffffu, w, 1);
-  w |= __shfl_xor_sync(0xffffffffu, w, 2);
-  w |= __shfl_xor_sync(0xffffffffu, w, 4);
-  return w;
-}
-
-// shared-memory layout of the delta tile: 4 pad words after every 32 positions, so that a lane's 8
-// consecutive positions (two LDS.128) never collide with the other lanes of its quarter-warp
-__device__ __forceinline__ int pad_idx(int p) { return p + ((p >> 5) << 2); }
-constexpr int GCI_TILE_WORDS = GCI_TILE + GCI_TILE / 8;      // 9216 words = 36 KB
-
 // 8 flag bits of one lane (positions idx..idx+7) -> 32-bit words held by lanes 0, 4, 8, ...
+// (layout of the streaming kernels: a lane owns 8 consecutive positions)
 __device__ __forceinline__ uint32_t pack_bytes(uint32_t byte, int lane) {
   uint32_t w = byte << ((lane & 3) * 8);
   w |= __shfl_xor_sync(0xffffffffu, w, 1);
@@ -132,165 +117,179 @@ __device__ __forceinline__ uint32_t flag8(const int (&o)[8], int lo1, uint32_t s
   return m;
 }
 
-// FLAGS: also emit the issue bit (lo < depth <= hi) of every position.
-// lo1 = lo + 1, span = number of admissible depth values (0 = none).
+__device__ __forceinline__ uint32_t flag4(int a, int b, int c, int d, int lo1, uint32_t span) {
+  return ((uint32_t)(a - lo1) < span ? 1u : 0u) | ((uint32_t)(b - lo1) < span ? 2u : 0u) |
+         ((uint32_t)(c - lo1) < span ? 4u : 0u) | ((uint32_t)(d - lo1) < span ? 8u : 0u);
+}
+
+// exclusive prefix over lanes of a mostly-zero per-lane value: one shuffle per non-zero lane instead of
+// the 5 dependent shuffles of a full warp scan (falls back to the scan when more than 4 lanes are set)
+__device__ __forceinline__ int sparse_excl_scan(int v, int lane, int& total) {
+  unsigned nz = __ballot_sync(0xffffffffu, v != 0);
+  int ex = 0;
+  total = 0;
+  if (__popc(nz) > 4) {
+    const int incl = warp_incl_scan(v, lane);
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    return incl - v;
+  }
+  while (nz) {
+    const int j = __ffs(nz) - 1;
+    nz &= nz - 1;
+    const int x = __shfl_sync(0xffffffffu, v, j);
+    ex += lane > j ? x : 0;
+    total += x;
+  }
+  return ex;
+}
+
+// Persistent warps, one tile (1024 positions) per warp at a time, no block-level barrier.
+// Per round of 256 positions a lane owns two quads: positions [4l, 4l+4) and [128+4l, 128+4l+4), so both
+// the shared-memory loads (LDS.128) and the global stores (STG.128) are lane-consecutive: conflict-free and
+// full 32-byte sectors.  The tile table entry and the events of the NEXT tile are fetched while the current
+// one is expanded; the depth carried into a tile comes from the tile scan, so warps never wait for each
+// other.  FLAGS: also emit the issue bit (lo < depth <= hi): lo1 = lo + 1, span = # admissible values.
 template <bool FLAGS>
 __global__ void __launch_bounds__(GCI_TILE_THREADS)
-depth_tile_kernel(const unsigned long long* __restrict__ tile_pack, const unsigned long long* __restrict__ tile_scan,
-                  const uint16_t* __restrict__ events, const int64_t* __restrict__ tile_off,
-                  const int64_t* __restrict__ len, int32_t n_contigs, int32_t* __restrict__ depth,
+depth_tile_kernel(const ulonglong2* __restrict__ tile_ps /* (pack, scan) per tile */,
+                  const uint16_t* __restrict__ events, int64_t n_tiles, int32_t* __restrict__ depth,
                   uint32_t* __restrict__ flags, int32_t lo1, uint32_t span) {
-  __shared__ __align__(16) int s_delta[GCI_TILE_WORDS];
-  __shared__ int s_part[GCI_TILE_THREADS / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t tile = blockIdx.x;
-  constexpr int PER_WARP = GCI_TILE / (GCI_TILE_THREADS / 32);   // 1024
-  constexpr int ITERS = PER_WARP / 256;                          // 4
+  __shared__ __align__(16) int s_all[(GCI_TILE_THREADS / 32) * GCI_TILE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int* __restrict__ s_delta = s_all + warp * GCI_TILE;
+  constexpr int ITERS = GCI_TILE / 256;                          // 4
 
 #pragma unroll
-  for (int v = tid; v < GCI_TILE_WORDS / 4; v += GCI_TILE_THREADS)
-    reinterpret_cast<int4*>(s_delta)[v] = make_int4(0, 0, 0, 0);
-  if (tid < GCI_TILE_THREADS / 32) s_part[tid] = 0;
-  __syncthreads();
-  const unsigned long long pk = tile_pack[tile], sc = tile_scan[tile];
-  const uint32_t n_ev = (uint32_t)(pk & 0xffffffffull);
-  const uint32_t ev0 = (uint32_t)(sc & 0xffffffffull);
-  const int base = (int)(uint32_t)(sc >> 32);                    // depth carried into the tile
-  for (uint32_t i = tid; i < n_ev; i += GCI_TILE_THREADS) {
-    const uint32_t e = events[ev0 + i];
-    const int d = (e & 1u) ? -1 : 1;
-    const int p = (int)(e >> 1);
-    atomicAdd(&s_delta[pad_idx(p)], d);
-    atomicAdd(&s_part[p / PER_WARP], d);
-  }
-  __syncthreads();
+  for (int v = lane; v < GCI_TILE / 4; v += 32) reinterpret_cast<int4*>(s_delta)[v] = make_int4(0, 0, 0, 0);
+  __syncwarp();
 
-  // contig of this tile; `valid` = positions of the tile that are real bases (the rest is padding)
-  const int64_t c = upper_bound_minus1<int64_t>(tile_off, (int64_t)n_contigs + 1, tile);
-  const int64_t left = len[c] - (tile - tile_off[c]) * GCI_TILE;
-  const int valid = left >= GCI_TILE ? GCI_TILE : (int)left;
-  int carry = base;
-  for (int j = 0; j < warp; j++) carry += s_part[j];
-  int32_t* __restrict__ out = depth + tile * GCI_TILE;
-  uint32_t* __restrict__ fout = flags + tile * (GCI_TILE / 32);
-#pragma unroll
-  for (int it = 0; it < ITERS; it++) {
-    const int idx = warp * PER_WARP + it * 256 + lane * 8;
-    const int w = pad_idx(idx);
-    const int4 v0 = *reinterpret_cast<const int4*>(&s_delta[w]);
-    const int4 v1 = *reinterpret_cast<const int4*>(&s_delta[w + 4]);
-    int o[8];
-    o[0] = v0.x; o[1] = o[0] + v0.y; o[2] = o[1] + v0.z; o[3] = o[2] + v0.w;
-    o[4] = o[3] + v1.x; o[5] = o[4] + v1.y; o[6] = o[5] + v1.z; o[7] = o[6] + v1.w;
-    const int incl = warp_incl_scan(o[7], lane);
-    const int run = carry + incl - o[7];
-    carry += __shfl_sync(0xffffffffu, incl, 31);
-#pragma unroll
-    for (int k = 0; k < 8; k++) o[k] += run;
-    if (idx + 8 > valid) {   // only the last tile of a contig: padding behind the last base stays 0
-#pragma unroll
-      for (int k = 0; k < 8; k++) if (idx + k >= valid) o[k] = 0;
+  const int64_t n_warps = (int64_t)gridDim.x * (GCI_TILE_THREADS / 32);
+  int64_t tile = (int64_t)blockIdx.x * (GCI_TILE_THREADS / 32) + warp;
+  const ulonglong2 zero2 = make_ulonglong2(0, 0);
+  ulonglong2 ps = tile < n_tiles ? tile_ps[tile] : zero2;                       // current tile
+  ulonglong2 ps1 = tile + n_warps < n_tiles ? tile_ps[tile + n_warps] : zero2;  // next tile
+  uint32_t ev = lane < (uint32_t)(ps.x & 0xffffffffull) ? events[(uint32_t)(ps.y & 0xffffffffull) + lane] : 0u;
+  for (; tile < n_tiles; tile += n_warps) {
+    const uint32_t n_ev = (uint32_t)(ps.x & 0xffffffffull);
+    const uint32_t ev0 = (uint32_t)(ps.y & 0xffffffffull);
+    int carry = (int)(uint32_t)(ps.y >> 32);                     // depth carried into the tile
+    if (lane < n_ev) atomicAdd(&s_delta[ev >> 1], (ev & 1u) ? -1 : 1);
+    for (uint32_t i = lane + 32; i < n_ev; i += 32) {            // more than 32 events in the tile: rare
+      const uint32_t e = events[ev0 + i];
+      atomicAdd(&s_delta[e >> 1], (e & 1u) ? -1 : 1);
     }
-    *reinterpret_cast<int4*>(out + idx) = make_int4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<int4*>(out + idx + 4) = make_int4(o[4], o[5], o[6], o[7]);
-    if (FLAGS) {
-      uint32_t m = flag8(o, lo1, span);
-      if (idx + 8 > valid) m &= idx >= valid ? 0u : (0xffu >> (idx + 8 - valid));
-      const uint32_t word = pack_bytes(m, lane);
-      if ((lane & 3) == 0) fout[idx >> 5] = word;
+    // software pipeline: events of the next tile, table entry of the one after
+    ps = ps1;
+    ev = lane < (uint32_t)(ps.x & 0xffffffffull) ? events[(uint32_t)(ps.y & 0xffffffffull) + lane] : 0u;
+    ps1 = tile + 2 * n_warps < n_tiles ? tile_ps[tile + 2 * n_warps] : zero2;
+    __syncwarp();
+    int32_t* __restrict__ out = depth + tile * GCI_TILE;
+#pragma unroll
+    for (int it = 0; it < ITERS; it++) {
+      const int ia = it * 256 + lane * 4, ib = ia + 128;
+      const int4 va = *reinterpret_cast<const int4*>(&s_delta[ia]);
+      const int4 vb = *reinterpret_cast<const int4*>(&s_delta[ib]);
+      const int a0 = va.x, a1 = a0 + va.y, a2 = a1 + va.z, a3 = a2 + va.w;
+      const int b0 = vb.x, b1 = b0 + vb.y, b2 = b1 + vb.z, b3 = b2 + vb.w;
+      if ((va.x | va.y | va.z | va.w) != 0) *reinterpret_cast<int4*>(&s_delta[ia]) = make_int4(0, 0, 0, 0);
+      if ((vb.x | vb.y | vb.z | vb.w) != 0) *reinterpret_cast<int4*>(&s_delta[ib]) = make_int4(0, 0, 0, 0);
+      int tot_a, tot_b;
+      const int ra = carry + sparse_excl_scan(a3, lane, tot_a);
+      const int rb = carry + tot_a + sparse_excl_scan(b3, lane, tot_b);
+      carry += tot_a + tot_b;
+      const int4 oa = make_int4(ra + a0, ra + a1, ra + a2, ra + a3);
+      const int4 ob = make_int4(rb + b0, rb + b1, rb + b2, rb + b3);
+      *reinterpret_cast<int4*>(out + ia) = oa;
+      *reinterpret_cast<int4*>(out + ib) = ob;
+      if (FLAGS) {
+        // butterfly: even lanes collect the A-half words, odd lanes the B-half words (3 shuffles for 8 words)
+        const uint32_t na = flag4(oa.x, oa.y, oa.z, oa.w, lo1, span), nb = flag4(ob.x, ob.y, ob.z, ob.w, lo1, span);
+        const bool odd = lane & 1;
+        uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? na : nb, 1);
+        uint32_t acc = odd ? (got | (nb << 4)) : (na | (got << 4));
+        got = __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc = (lane & 2) ? (got | (acc << 8)) : (acc | (got << 8));
+        got = __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc = (lane & 4) ? (got | (acc << 16)) : (acc | (got << 16));
+        if ((lane & 6) == 0)   // lanes 8g (A word g) and 8g+1 (B word g)
+          flags[tile * (GCI_TILE / 32) + it * 8 + (odd ? 4 : 0) + (lane >> 3)] = acc;
+      }
     }
+    __syncwarp();   // re-zeroing stores of all lanes are done before the next tile's events land
   }
 }
 
 // ================================================================================================
 // stand-alone flags (resume path / different thresholds), two-type max, N-run mask
 // ================================================================================================
+// flag bits of 8 consecutive positions per lane, same packing as the depth kernel
 __global__ void __launch_bounds__(GCI_TILE_THREADS)
-flags_kernel(const int32_t* __restrict__ depth, const int64_t* __restrict__ tile_off, const int64_t* __restrict__ len,
-             int32_t n_contigs, uint32_t* __restrict__ flags, int32_t lo, int32_t hi) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int64_t tile = blockIdx.x;
-  const int64_t c = upper_bound_minus1<int64_t>(tile_off, (int64_t)n_contigs + 1, tile);
-  const int64_t cpos0 = (tile - tile_off[c]) * GCI_TILE;
-  const int64_t L = len[c];
-  const int64_t gbase = tile * GCI_TILE;
+flags_kernel(const int32_t* __restrict__ depth, int64_t total, uint32_t* __restrict__ flags, int32_t lo1, uint32_t span) {
+  const int lane = threadIdx.x & 31;
+  const int64_t base = (int64_t)blockIdx.x * GCI_CHUNK;
 #pragma unroll
-  for (int it = 0; it < GCI_TILE / (GCI_TILE_THREADS * 4); it++) {
-    const int idx = it * GCI_TILE_THREADS * 4 + tid * 4;
-    const int4 m = *reinterpret_cast<const int4*>(&depth[gbase + idx]);
-    const int64_t cp = cpos0 + idx;
-    uint32_t nib = 0;
-    nib |= (m.x > lo && m.x <= hi && cp < L) ? 1u : 0u;
-    nib |= (m.y > lo && m.y <= hi && cp + 1 < L) ? 2u : 0u;
-    nib |= (m.z > lo && m.z <= hi && cp + 2 < L) ? 4u : 0u;
-    nib |= (m.w > lo && m.w <= hi && cp + 3 < L) ? 8u : 0u;
-    const uint32_t w = pack_nibbles(nib, lane);
-    if ((lane & 7) == 0) flags[(gbase + idx) >> 5] = w;
+  for (int it = 0; it < GCI_CHUNK / (GCI_TILE_THREADS * 8); it++) {
+    const int64_t idx = base + it * GCI_TILE_THREADS * 8 + threadIdx.x * 8;
+    if (idx >= total) break;                          // total is a multiple of 1024: whole warps leave together
+    const int4 a = *reinterpret_cast<const int4*>(&depth[idx]);
+    const int4 b = *reinterpret_cast<const int4*>(&depth[idx + 4]);
+    const int o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const uint32_t word = pack_bytes(flag8(o, lo1, span), lane);
+    if ((lane & 3) == 0) flags[idx >> 5] = word;
+  }
+}
+
+// per-tile sums -> per-contig sums: one warp covers one tile per round (a tile never straddles contigs)
+__device__ __forceinline__ void add_tile_sum(long long acc, int64_t tile, const int64_t* __restrict__ tile_off,
+                                             int32_t n_contigs, long long* __restrict__ sums, int lane) {
+  acc = warp_sum_ll(acc);
+  if (lane == 0 && acc) {
+    const int64_t c = upper_bound_minus1<int64_t>(tile_off, (int64_t)n_contigs + 1, tile);
+    atomicAdd((unsigned long long*)(sums + c), (unsigned long long)acc);
   }
 }
 
 __global__ void __launch_bounds__(GCI_TILE_THREADS)
-max_kernel(const int32_t* __restrict__ da, const int32_t* __restrict__ db, int32_t* __restrict__ dout,
-           const int64_t* __restrict__ tile_off, const int64_t* __restrict__ len, int32_t n_contigs,
-           uint32_t* __restrict__ flags, int32_t lo, int32_t hi, long long* __restrict__ sums) {
-  __shared__ long long s_red[GCI_TILE_THREADS / 32];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int64_t tile = blockIdx.x;
-  const int64_t c = upper_bound_minus1<int64_t>(tile_off, (int64_t)n_contigs + 1, tile);
-  const int64_t cpos0 = (tile - tile_off[c]) * GCI_TILE;
-  const int64_t L = len[c];
-  const int64_t gbase = tile * GCI_TILE;
+max_kernel(const int32_t* __restrict__ da, const int32_t* __restrict__ db, int32_t* __restrict__ dout, int64_t total,
+           const int64_t* __restrict__ tile_off, int32_t n_contigs, uint32_t* __restrict__ flags, int32_t lo1,
+           uint32_t span, long long* __restrict__ sums) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // warp w of the CTA owns tile (chunk * 8 + w): 4 rounds of 256 positions
+  const int64_t tile = (int64_t)blockIdx.x * (GCI_CHUNK / GCI_TILE) + warp;
+  if (tile * GCI_TILE >= total) return;
   long long acc = 0;
 #pragma unroll
-  for (int it = 0; it < GCI_TILE / (GCI_TILE_THREADS * 4); it++) {
-    const int idx = it * GCI_TILE_THREADS * 4 + tid * 4;
-    const int4 a = *reinterpret_cast<const int4*>(&da[gbase + idx]);
-    const int4 b = *reinterpret_cast<const int4*>(&db[gbase + idx]);
-    const int4 m = make_int4(max(a.x, b.x), max(a.y, b.y), max(a.z, b.z), max(a.w, b.w));
-    *reinterpret_cast<int4*>(&dout[gbase + idx]) = m;
-    acc += (long long)m.x + m.y + m.z + m.w;      // padding is 0 in both inputs
-    const int64_t cp = cpos0 + idx;
-    uint32_t nib = 0;
-    nib |= (m.x > lo && m.x <= hi && cp < L) ? 1u : 0u;
-    nib |= (m.y > lo && m.y <= hi && cp + 1 < L) ? 2u : 0u;
-    nib |= (m.z > lo && m.z <= hi && cp + 2 < L) ? 4u : 0u;
-    nib |= (m.w > lo && m.w <= hi && cp + 3 < L) ? 8u : 0u;
-    const uint32_t w = pack_nibbles(nib, lane);
-    if ((lane & 7) == 0) flags[(gbase + idx) >> 5] = w;
+  for (int it = 0; it < GCI_TILE / 256; it++) {
+    const int64_t idx = tile * GCI_TILE + it * 256 + lane * 8;
+    const int4 a0 = *reinterpret_cast<const int4*>(&da[idx]), a1 = *reinterpret_cast<const int4*>(&da[idx + 4]);
+    const int4 b0 = *reinterpret_cast<const int4*>(&db[idx]), b1 = *reinterpret_cast<const int4*>(&db[idx + 4]);
+    const int o[8] = {max(a0.x, b0.x), max(a0.y, b0.y), max(a0.z, b0.z), max(a0.w, b0.w),
+                      max(a1.x, b1.x), max(a1.y, b1.y), max(a1.z, b1.z), max(a1.w, b1.w)};
+    *reinterpret_cast<int4*>(&dout[idx]) = make_int4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<int4*>(&dout[idx + 4]) = make_int4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc += o[k];          // padding is 0 in both inputs
+    const uint32_t word = pack_bytes(flag8(o, lo1, span), lane);
+    if ((lane & 3) == 0) flags[idx >> 5] = word;
   }
-  acc = warp_sum_ll(acc);
-  if (lane == 0) s_red[tid >> 5] = acc;
-  __syncthreads();
-  if (tid == 0) {
-    long long t = 0;
-    for (int j = 0; j < GCI_TILE_THREADS / 32; j++) t += s_red[j];
-    if (t) atomicAdd((unsigned long long*)(sums + c), (unsigned long long)t);
-  }
+  add_tile_sum(acc, tile, tile_off, n_contigs, sums, lane);
 }
 
 // per-contig sum of a loaded track (resume path)
 __global__ void __launch_bounds__(GCI_TILE_THREADS)
-sum_kernel(const int32_t* __restrict__ depth, const int64_t* __restrict__ tile_off, int32_t n_contigs,
+sum_kernel(const int32_t* __restrict__ depth, int64_t total, const int64_t* __restrict__ tile_off, int32_t n_contigs,
            long long* __restrict__ sums) {
-  __shared__ long long s_red[GCI_TILE_THREADS / 32];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int64_t tile = blockIdx.x;
-  const int64_t c = upper_bound_minus1<int64_t>(tile_off, (int64_t)n_contigs + 1, tile);
-  const int64_t gbase = tile * GCI_TILE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tile = (int64_t)blockIdx.x * (GCI_CHUNK / GCI_TILE) + warp;
+  if (tile * GCI_TILE >= total) return;
   long long acc = 0;
 #pragma unroll
-  for (int it = 0; it < GCI_TILE / (GCI_TILE_THREADS * 4); it++) {
-    const int4 m = *reinterpret_cast<const int4*>(&depth[gbase + it * GCI_TILE_THREADS * 4 + tid * 4]);
-    acc += (long long)m.x + m.y + m.z + m.w;
+  for (int it = 0; it < GCI_TILE / 256; it++) {
+    const int64_t idx = tile * GCI_TILE + it * 256 + lane * 8;
+    const int4 a = *reinterpret_cast<const int4*>(&depth[idx]), b = *reinterpret_cast<const int4*>(&depth[idx + 4]);
+    acc += (long long)a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
   }
-  acc = warp_sum_ll(acc);
-  if (lane == 0) s_red[tid >> 5] = acc;
-  __syncthreads();
-  if (tid == 0) {
-    long long t = 0;
-    for (int j = 0; j < GCI_TILE_THREADS / 32; j++) t += s_red[j];
-    if (t) atomicAdd((unsigned long long*)(sums + c), (unsigned long long)t);
-  }
+  add_tile_sum(acc, tile, tile_off, n_contigs, sums, lane);
 }
 
 struct NRuns {
@@ -326,6 +325,30 @@ __global__ void mask_kernel(NRuns nr, const int64_t* __restrict__ tile_off, int3
     for (int j = 0; j < (int)(blockDim.x >> 5); j++) t += s_red[j];
     if (t) atomicAdd((unsigned long long*)(sums + c), (unsigned long long)(-t));
   }
+}
+
+// ================================================================================================
+// narrow fetch: depth as uint8 / uint16 when every value fits (4x / 2x fewer bytes over PCIe)
+// ================================================================================================
+template <typename T>
+__global__ void narrow_kernel(const int32_t* __restrict__ depth, int64_t n, T* __restrict__ out,
+                              unsigned int* __restrict__ overflow) {
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  constexpr unsigned MAXV = sizeof(T) == 1 ? 0xffu : 0xffffu;
+  bool bad = false;
+  if (i + 4 <= n && ((reinterpret_cast<uintptr_t>(depth + i) & 15) == 0)) {
+    const int4 v = *reinterpret_cast<const int4*>(depth + i);
+    bad = ((unsigned)v.x > MAXV) | ((unsigned)v.y > MAXV) | ((unsigned)v.z > MAXV) | ((unsigned)v.w > MAXV);
+    out[i] = (T)v.x; out[i + 1] = (T)v.y; out[i + 2] = (T)v.z; out[i + 3] = (T)v.w;
+  } else {
+    for (int64_t k = i; k < n && k < i + 4; k++) {
+      const int v = depth[k];
+      bad |= (unsigned)v > MAXV;
+      out[k] = (T)v;
+    }
+  }
+  if (__any_sync(__activemask(), bad) && bad) atomicOr(overflow, 1u);
 }
 
 // ================================================================================================
@@ -380,13 +403,29 @@ static NRuns make_nruns(gci_ctx* ctx) {
   return nr;
 }
 
+int gci_depth_occupancy(gci_ctx* ctx) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, depth_tile_kernel<true>, GCI_TILE_THREADS, 0) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = 4;
+  }
+  return n;
+}
+
+static inline int32_t flag_lo1(int32_t lo) { return lo == INT32_MAX ? INT32_MAX : lo + 1; }
+static inline uint32_t flag_span(int32_t lo, int32_t hi) {
+  return hi > lo ? (uint32_t)((int64_t)hi - (int64_t)lo) : 0u;
+}
+static inline unsigned chunk_grid(gci_ctx* ctx) {
+  return (unsigned)((ctx->total_padded + GCI_CHUNK - 1) / GCI_CHUNK);
+}
+
 int gci_compute_flags(gci_ctx* ctx, int track, int32_t lo, int32_t hi) {
   Track& t = ctx->track[track];
   ctx->stage_begin(GCI_ST_FLAGS);
   if (ctx->n_tiles) {
-    flags_kernel<<<(unsigned)ctx->n_tiles, GCI_TILE_THREADS, 0, ctx->stream>>>(
-        t.depth.as<int32_t>(), ctx->d_tile_off.as<int64_t>(), ctx->d_len.as<int64_t>(), ctx->n_contigs,
-        t.flags.as<uint32_t>(), lo, hi);
+    flags_kernel<<<chunk_grid(ctx), GCI_TILE_THREADS, 0, ctx->stream>>>(
+        t.depth.as<int32_t>(), ctx->total_padded, t.flags.as<uint32_t>(), flag_lo1(lo), flag_span(lo, hi));
     GCI_LAUNCH_CHECK(ctx);
   }
   ctx->stage_end();
@@ -415,48 +454,49 @@ int gci_depth(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo, int32_
   const uint32_t nr = ctx->n_reads;
   if (nt == 0) return GCI_OK;
   if (nt >= (int64_t(1) << 31)) return ctx->fail(GCI_E_ARG, "too many tiles");
-  // one scratch block: [packed (count, net) u64 x nt | fill cursors u32 x nt] zeroed with one memset
-  GCI_TRY(ctx->ensure(ctx->tile_cnt, 12 * (size_t)nt));
-  GCI_TRY(ctx->ensure(ctx->tile_evoff, 8 * (size_t)nt));   // exclusive scan of the packed values
+  // one scratch block zeroed with one memset: per tile (pack u64, scan u64) interleaved + fill cursor u32
+  GCI_TRY(ctx->ensure(ctx->tile_cnt, 20 * (size_t)nt));
   GCI_TRY(ctx->ensure(ctx->events, 2 * 2 * (size_t)std::max<uint32_t>(1, nr)));
-  unsigned long long* pack = ctx->tile_cnt.as<unsigned long long>();
-  uint32_t* cursor = reinterpret_cast<uint32_t*>(pack + nt);
-  unsigned long long* scan = ctx->tile_evoff.as<unsigned long long>();
+  ulonglong2* tile_ps = ctx->tile_cnt.as<ulonglong2>();
+  uint32_t* cursor = reinterpret_cast<uint32_t*>(tile_ps + nt);
   ctx->stage_begin(GCI_ST_BUCKET);
-  GCI_CUDA_TRY(ctx, cudaMemsetAsync(pack, 0, 12 * (size_t)nt, ctx->stream));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(tile_ps, 0, 20 * (size_t)nt, ctx->stream));
   GCI_CUDA_TRY(ctx, cudaMemsetAsync(t.sums.p, 0, sizeof(int64_t) * (size_t)ctx->n_contigs, ctx->stream));
   if (nr) {
     bucket_count_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(
         nr, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(), flank_len,
-        ctx->d_len.as<int64_t>(), ctx->d_tile_off.as<int64_t>(), pack, t.sums.as<long long>());
+        ctx->d_len.as<int64_t>(), ctx->d_tile_off.as<int64_t>(), tile_ps, t.sums.as<long long>());
     GCI_LAUNCH_CHECK(ctx);
   }
-  GCI_TRY(gci_exclusive_scan_u64(ctx, pack, scan, nt, nullptr));
+  GCI_TRY(gci_scan_tile_pack(ctx, tile_ps, nt));
   if (nr) {
     bucket_fill_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(
         nr, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(), flank_len,
-        ctx->d_len.as<int64_t>(), ctx->d_tile_off.as<int64_t>(), scan, cursor, ctx->events.as<uint16_t>());
+        ctx->d_len.as<int64_t>(), ctx->d_tile_off.as<int64_t>(), tile_ps, cursor, ctx->events.as<uint16_t>());
     GCI_LAUNCH_CHECK(ctx);
   }
   ctx->stage_end();
+  if (ctx->depth_ctas_per_sm <= 0) ctx->depth_ctas_per_sm = gci_depth_occupancy(ctx);
   const bool fuse = !(lo == INT32_MIN && hi == INT32_MIN);
-  const int32_t lo1 = fuse ? (int32_t)((int64_t)lo + 1 > INT32_MAX ? INT32_MAX : lo + 1) : 0;
-  const uint32_t span = (fuse && hi > lo) ? (uint32_t)((int64_t)hi - (int64_t)lo) : 0u;
+  const int32_t lo1 = fuse ? flag_lo1(lo) : 0;
+  const uint32_t span = fuse ? flag_span(lo, hi) : 0u;
   ctx->stage_begin(GCI_ST_DEPTH);
+  // persistent grid: resident CTAs per SM x SM count, 8 tiles in flight per CTA
+  const int64_t ctas_needed = (nt + GCI_TILE_THREADS / 32 - 1) / (GCI_TILE_THREADS / 32);
+  const unsigned grid = (unsigned)std::min<int64_t>(ctas_needed, (int64_t)ctx->sm_count * ctx->depth_ctas_per_sm);
   if (fuse) {
-    depth_tile_kernel<true><<<(unsigned)nt, GCI_TILE_THREADS, 0, ctx->stream>>>(
-        pack, scan, ctx->events.as<uint16_t>(), ctx->d_tile_off.as<int64_t>(), ctx->d_len.as<int64_t>(),
-        ctx->n_contigs, t.depth.as<int32_t>(), t.flags.as<uint32_t>(), lo1, span);
+    depth_tile_kernel<true><<<grid, GCI_TILE_THREADS, 0, ctx->stream>>>(
+        tile_ps, ctx->events.as<uint16_t>(), nt, t.depth.as<int32_t>(), t.flags.as<uint32_t>(), lo1, span);
   } else {
-    depth_tile_kernel<false><<<(unsigned)nt, GCI_TILE_THREADS, 0, ctx->stream>>>(
-        pack, scan, ctx->events.as<uint16_t>(), ctx->d_tile_off.as<int64_t>(), ctx->d_len.as<int64_t>(),
-        ctx->n_contigs, t.depth.as<int32_t>(), t.flags.as<uint32_t>(), lo1, span);
+    depth_tile_kernel<false><<<grid, GCI_TILE_THREADS, 0, ctx->stream>>>(
+        tile_ps, ctx->events.as<uint16_t>(), nt, t.depth.as<int32_t>(), t.flags.as<uint32_t>(), lo1, span);
   }
   GCI_LAUNCH_CHECK(ctx);
   ctx->stage_end();
   // depth and flags are both un-masked here (the reference writes the single-type .depth.gz before
   // masking, GCI.py:310 vs :993); gci_mask_gaps patches both over the N-runs
   t.flags_valid = fuse;
+  t.sums_valid = true;
   t.flags_lo = lo;
   t.flags_hi = hi;
   t.n_intervals = 0;
@@ -498,14 +538,15 @@ int gci_merge_max(gci_ctx* ctx, int32_t ta, int32_t tb, int32_t tout, int32_t lo
   const int32_t flo = (lo == INT32_MIN && hi == INT32_MIN) ? -1 : lo;
   const int32_t fhi = (lo == INT32_MIN && hi == INT32_MIN) ? 0 : hi;
   if (ctx->n_tiles) {
-    max_kernel<<<(unsigned)ctx->n_tiles, GCI_TILE_THREADS, 0, ctx->stream>>>(
+    max_kernel<<<chunk_grid(ctx), GCI_TILE_THREADS, 0, ctx->stream>>>(
         ctx->track[ta].depth.as<int32_t>(), ctx->track[tb].depth.as<int32_t>(), t.depth.as<int32_t>(),
-        ctx->d_tile_off.as<int64_t>(), ctx->d_len.as<int64_t>(), ctx->n_contigs, t.flags.as<uint32_t>(), flo, fhi,
-        t.sums.as<long long>());
+        ctx->total_padded, ctx->d_tile_off.as<int64_t>(), ctx->n_contigs, t.flags.as<uint32_t>(), flag_lo1(flo),
+        flag_span(flo, fhi), t.sums.as<long long>());
     GCI_LAUNCH_CHECK(ctx);
   }
   ctx->stage_end();
   t.flags_valid = true;
+  t.sums_valid = true;
   t.flags_lo = flo;
   t.flags_hi = fhi;
   t.n_intervals = 0;
@@ -518,15 +559,58 @@ int gci_depth_sums(gci_ctx* ctx, int32_t track, int64_t* sums) {
   cudaSetDevice(ctx->device);
   Track& t = ctx->track[track];
   if (!t.allocated) return ctx->fail(GCI_E_ARG, "gci_depth_sums: track %d holds no depth", track);
-  // recompute from the depth array: also right after gci_load_depth
+  // the sums ride along with gci_depth / gci_merge_max / gci_mask_gaps; after gci_load_depth they are
+  // recomputed from the depth array
+  if (!t.sums_valid) {
   GCI_CUDA_TRY(ctx, cudaMemsetAsync(t.sums.p, 0, sizeof(int64_t) * (size_t)ctx->n_contigs, ctx->stream));
   if (ctx->n_tiles) {
-    sum_kernel<<<(unsigned)ctx->n_tiles, GCI_TILE_THREADS, 0, ctx->stream>>>(
-        t.depth.as<int32_t>(), ctx->d_tile_off.as<int64_t>(), ctx->n_contigs, t.sums.as<long long>());
+    sum_kernel<<<chunk_grid(ctx), GCI_TILE_THREADS, 0, ctx->stream>>>(
+        t.depth.as<int32_t>(), ctx->total_padded, ctx->d_tile_off.as<int64_t>(), ctx->n_contigs,
+        t.sums.as<long long>());
     GCI_LAUNCH_CHECK(ctx);
+  }
+  t.sums_valid = true;
   }
   GCI_TRY(gci_d2h(ctx, sums, t.sums.p, sizeof(int64_t) * (size_t)ctx->n_contigs));
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return GCI_OK;
+}
+
+int gci_fetch_depth_narrow(gci_ctx* ctx, int32_t track, int32_t contig, void* out, int64_t n, int32_t width,
+                           int32_t* overflow) {
+  if (!ctx || !out || !overflow || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  Track& t = ctx->track[track];
+  if (!t.allocated) return ctx->fail(GCI_E_ARG, "track %d holds no depth", track);
+  if (contig < 0 || contig >= ctx->n_contigs || !ctx->selected[contig] || n != ctx->len[contig])
+    return ctx->fail(GCI_E_ARG, "gci_fetch_depth_narrow: contig %d / length %lld mismatch", contig, (long long)n);
+  if (width != 1 && width != 2) return ctx->fail(GCI_E_ARG, "width must be 1 or 2 (use gci_fetch_depth for int32)");
+  *overflow = 0;
+  if (n == 0) return GCI_OK;
+  const int32_t* d = t.depth.as<int32_t>() + ctx->pos_off[contig];
+  DevBuf& stage = ctx->tmp[8];
+  GCI_TRY(ctx->ensure(stage, (size_t)n * width + 16));
+  unsigned int* d_ovf = reinterpret_cast<unsigned int*>(ctx->d_err.as<unsigned long long>() + 3);
+  GCI_TRY(ctx->ensure(ctx->d_err, 4 * sizeof(unsigned long long)));
+  d_ovf = reinterpret_cast<unsigned int*>(ctx->d_err.as<unsigned long long>() + 3);
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(d_ovf, 0, sizeof(unsigned int), ctx->stream));
+  const unsigned grid = (unsigned)((n / 4 + 1 + 255) / 256);
+  ctx->stage_begin(GCI_ST_D2H);
+  if (width == 1) narrow_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(d, n, stage.as<uint8_t>(), d_ovf);
+  else narrow_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(d, n, stage.as<uint16_t>(), d_ovf);
+  GCI_LAUNCH_CHECK(ctx);
+  unsigned int* h = (unsigned int*)ctx->pinned(sizeof(unsigned int));
+  if (!h) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
+  GCI_TRY(gci_d2h(ctx, h, d_ovf, sizeof(unsigned int)));
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *overflow = (int32_t)*h;
+  if (*h == 0) {
+    GCI_TRY(gci_d2h(ctx, out, stage.p, (size_t)n * width));
+    ctx->stage_end();
+    GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  } else {
+    ctx->stage_end();
+  }
   return GCI_OK;
 }
 

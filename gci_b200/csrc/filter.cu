@@ -445,7 +445,7 @@ static int install_table(gci_ctx* ctx, FileTable& f, int64_t n, const uint32_t* 
                          const int32_t* start, const int32_t* end, const int32_t* qlen, const uint8_t* highq) {
   f.kind = 1;
   f.n = n;
-  DevBuf d_read, d_hq;
+  DevBuf &d_read = ctx->tmp[4], &d_hq = ctx->tmp[5];
   ctx->stage_begin(GCI_ST_H2D);
   GCI_TRY(gci_h2d(ctx, d_read, read_id, 4 * n));
   GCI_TRY(gci_h2d(ctx, f.ref_id, ref_id, 4 * n));
@@ -463,8 +463,6 @@ static int install_table(gci_ctx* ctx, FileTable& f, int64_t n, const uint32_t* 
     GCI_LAUNCH_CHECK(ctx);
   }
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->release(d_read);
-  ctx->release(d_hq);
   return GCI_OK;
 }
 
@@ -504,7 +502,7 @@ void merge_blocks(std::vector<std::pair<int32_t, int32_t>>& v, int64_t& total, i
 int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
   std::vector<PafKept> kept;   // the reference's `synteny`, alive across PAF files (GCI.py:214)
   uint64_t ord = 0;
-  for (size_t fi = 0; fi < ctx->files.size(); fi++) {
+  for (size_t fi = 0; fi < ctx->n_files; fi++) {
     FileTable& ft = ctx->files[fi];
     if (ft.kind != 2) continue;
     if ((int32_t)ctx->name_rank.size() != ctx->n_contigs)
@@ -590,7 +588,7 @@ int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
 int gci_run_join(gci_ctx* ctx, double op) {
   JoinArgs a;
   memset(&a, 0, sizeof a);
-  a.n_files = (int)ctx->files.size();
+  a.n_files = (int)ctx->n_files;
   for (int i = 0; i < a.n_files; i++) {
     FileTable& f = ctx->files[i];
     a.f[i].win = f.win.as<long long>();
@@ -662,24 +660,24 @@ int gci_upload_table(gci_ctx* ctx, int64_t n, const uint32_t* read_id, const int
                      const int32_t* end, const int32_t* qlen, const uint8_t* highq) {
   if (!ctx || n < 0) return GCI_E_ARG;
   if (n && (!read_id || !ref_id || !start || !end || !qlen)) return GCI_E_ARG;
-  if ((int)ctx->files.size() >= GCI_MAX_FILES) return ctx->fail(GCI_E_ARG, "too many files");
+  if ((int)ctx->n_files >= GCI_MAX_FILES) return ctx->fail(GCI_E_ARG, "too many files");
   cudaSetDevice(ctx->device);
-  ctx->files.emplace_back();
+  if (ctx->n_files == ctx->files.size()) ctx->files.emplace_back();
   ctx->filtered = false;
-  return install_table(ctx, ctx->files.back(), n, read_id, ref_id, start, end, qlen, highq);
+  return install_table(ctx, ctx->files[ctx->n_files++], n, read_id, ref_id, start, end, qlen, highq);
 }
 
 int gci_filter(gci_ctx* ctx, int32_t map_qual, int32_t mq_cutoff, double iden_percent, double clip_percent,
                double ovlp_percent, int64_t* n_survivors) {
   if (!ctx) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
-  if (ctx->files.empty()) return ctx->fail(GCI_E_ARG, "gci_filter: no files uploaded");
+  if (ctx->n_files == 0) return ctx->fail(GCI_E_ARG, "gci_filter: no files uploaded");
   GCI_TRY(reset_err(ctx));
   // PAF election first (host stage); tables uploaded by the caller are already final
   ctx->stage_begin(GCI_ST_PAF);
   ctx->stage_end();
   GCI_TRY(gci_run_paf_legs(ctx, map_qual, mq_cutoff, iden_percent));
-  for (size_t i = 0; i < ctx->files.size(); i++)
+  for (size_t i = 0; i < ctx->n_files; i++)
     if (ctx->files[i].kind == 0)
       GCI_TRY(gci_run_bam_leg(ctx, (int)i, ctx->files[i].src, map_qual, mq_cutoff, iden_percent, clip_percent));
   GCI_TRY(gci_run_join(ctx, ovlp_percent));
@@ -727,7 +725,7 @@ int gci_fetch_file_table(gci_ctx* ctx, int32_t file, int64_t cap, uint32_t* read
   if (!ctx) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
   if (!ctx->filtered) return ctx->fail(GCI_E_ARG, "gci_fetch_file_table before gci_filter");
-  if (file < 0 || file >= (int)ctx->files.size()) return ctx->fail(GCI_E_ARG, "bad file index %d", file);
+  if (file < 0 || file >= (int)ctx->n_files) return ctx->fail(GCI_E_ARG, "bad file index %d", file);
   FileTable& f = ctx->files[file];
   const uint32_t nr = ctx->n_reads;
   DevBuf mark, pos;

@@ -114,7 +114,7 @@ static int exclusive_scan(gci_ctx* ctx, const TI* in, TO* out, int64_t n, TO* to
     return GCI_OK;
   }
   const int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-  if (n <= 96 * 1024) {
+  if (n <= 8 * 1024) {
     scan_single_kernel<TI, TO><<<1, SCAN1_THREADS, 0, ctx->stream>>>(in, out, n, total_dev);
     GCI_LAUNCH_CHECK(ctx);
     return GCI_OK;
@@ -142,9 +142,76 @@ int gci_exclusive_scan_i32(gci_ctx* ctx, const int32_t* in, int32_t* out, int64_
   return exclusive_scan<int32_t, int32_t>(ctx, in, out, n, nullptr);
 }
 
-int gci_exclusive_scan_u64(gci_ctx* ctx, const unsigned long long* in, unsigned long long* out, int64_t n,
-                           unsigned long long* total_dev) {
-  return exclusive_scan<unsigned long long, unsigned long long>(ctx, in, out, n, total_dev);
+// tile table: .y = exclusive scan of .x over all tiles (packed (count, net) sums never carry between halves)
+__global__ void __launch_bounds__(SCAN_THREADS)
+tile_reduce_kernel(const ulonglong2* __restrict__ ps, int64_t n, unsigned long long* __restrict__ block_sums) {
+  __shared__ unsigned long long s_w[SCAN_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK;
+  unsigned long long v = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    const int64_t i = base + k * SCAN_THREADS + threadIdx.x;
+    if (i < n) v += ps[i].x;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; w++) t += s_w[w];
+    block_sums[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+tile_apply_kernel(ulonglong2* __restrict__ ps, int64_t n, const unsigned long long* __restrict__ block_off) {
+  __shared__ unsigned long long s_w[SCAN_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_ITEMS;
+  unsigned long long item[SCAN_ITEMS], sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    item[k] = base + k < n ? ps[base + k].x : 0ull;
+    sum += item[k];
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned long long incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) s_w[w] = incl;
+  __syncthreads();
+  unsigned long long woff = 0;
+  for (int j = 0; j < w; j++) woff += s_w[j];
+  unsigned long long run = (block_off ? block_off[blockIdx.x] : 0ull) + woff + incl - sum;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) ps[base + k].y = run;
+    run += item[k];
+  }
+}
+
+int gci_scan_tile_pack(gci_ctx* ctx, ulonglong2* tile_ps, int64_t n) {
+  if (n <= 0) return GCI_OK;
+  const int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  if (nb == 1) {
+    tile_apply_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(tile_ps, n, nullptr);
+    GCI_LAUNCH_CHECK(ctx);
+    return GCI_OK;
+  }
+  DevBuf& sums = ctx->scan_lvl[6];
+  DevBuf& offs = ctx->scan_lvl[7];
+  GCI_TRY(ctx->ensure(sums, 8 * (size_t)nb));
+  GCI_TRY(ctx->ensure(offs, 8 * (size_t)nb));
+  tile_reduce_kernel<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(tile_ps, n, sums.as<unsigned long long>());
+  GCI_LAUNCH_CHECK(ctx);
+  GCI_TRY((exclusive_scan<unsigned long long, unsigned long long>(ctx, sums.as<unsigned long long>(),
+                                                                  offs.as<unsigned long long>(), nb, nullptr, 0)));
+  tile_apply_kernel<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(tile_ps, n, offs.as<unsigned long long>());
+  GCI_LAUNCH_CHECK(ctx);
+  return GCI_OK;
 }
 
 // ================================================================================================

@@ -115,9 +115,50 @@ def exchange_file_tables(tables):
     return out
 
 
+_ROW_CAP = 8192
+_row_cache = {}
+
+
 def genome_row(sum_depth, sum_len, n_ctg, lengths):
-    """Whole-genome terms from per-rank partials: (mean depth, total curated contigs, all curated lengths)."""
-    tot = allreduce(np.array([int(sum_depth), int(sum_len), int(n_ctg)], dtype=np.int64))
-    all_len = np.concatenate(allgather_varlen(np.asarray(lengths, dtype=np.int64)))
-    mean = float(tot[0]) / float(tot[1]) if tot[1] else float("nan")
-    return mean, int(tot[2]), all_len
+    """Whole-genome terms from per-rank partials: (mean depth, total curated contigs, all curated lengths).
+
+    One fixed-size all-gather ([sum_depth, sum_len, n_ctg, n_lengths, lengths...] per rank) when the
+    curated-length list fits _ROW_CAP entries — the exchange is latency-bound, so it is a single
+    collective and a single device->host copy; longer lists take the variable-length path."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    if not is_dist():
+        mean = float(sum_depth) / float(sum_len) if sum_len else float("nan")
+        return mean, int(n_ctg), lengths.copy()
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    dev = _device()
+    fits = np.array([1 if len(lengths) <= _ROW_CAP else 0], dtype=np.int64)
+    if len(lengths) > _ROW_CAP or not _row_cache.get("all_fit", True):
+        if int(allreduce(fits, "sum")[0]) != world:        # somebody overflowed: variable-length path
+            _row_cache["all_fit"] = False
+            tot = allreduce(np.array([int(sum_depth), int(sum_len), int(n_ctg)], dtype=np.int64))
+            all_len = np.concatenate(allgather_varlen(lengths))
+            mean = float(tot[0]) / float(tot[1]) if tot[1] else float("nan")
+            return mean, int(tot[2]), all_len
+    key = (world, str(dev))
+    if key not in _row_cache:
+        pin = dev.type == "cuda"
+        _row_cache[key] = (torch.zeros(4 + _ROW_CAP, dtype=torch.int64, pin_memory=pin),
+                           torch.zeros(4 + _ROW_CAP, dtype=torch.int64, device=dev),
+                           torch.zeros(world * (4 + _ROW_CAP), dtype=torch.int64, device=dev),
+                           torch.zeros(world * (4 + _ROW_CAP), dtype=torch.int64, pin_memory=pin))
+    h_in, d_in, d_out, h_out = _row_cache[key]
+    v = h_in.numpy()
+    v[0], v[1], v[2], v[3] = int(sum_depth), int(sum_len), int(n_ctg), len(lengths)
+    v[4:4 + len(lengths)] = lengths
+    d_in.copy_(h_in, non_blocking=True)
+    dist.all_gather_into_tensor(d_out, d_in)
+    h_out.copy_(d_out, non_blocking=True)
+    if dev.type == "cuda":
+        torch.cuda.current_stream().synchronize()
+    o = h_out.numpy().reshape(world, 4 + _ROW_CAP)
+    tot_d, tot_l, tot_c = int(o[:, 0].sum()), int(o[:, 1].sum()), int(o[:, 2].sum())
+    all_len = np.concatenate([o[r, 4:4 + int(o[r, 3])] for r in range(world)])
+    mean = float(tot_d) / float(tot_l) if tot_l else float("nan")
+    return mean, tot_c, all_len

@@ -110,7 +110,7 @@ class DeviceDepths(Mapping):
     def __getitem__(self, name):
         if name not in self._names:
             raise KeyError(name)
-        return self.session.ctx.fetch_depth(self.track, self.session.index[name]).astype(np.int64)
+        return self.session.ctx.fetch_depth_narrow(self.track, self.session.index[name]).astype(np.int64)
 
     def fetch_i32(self, name):
         return self.session.ctx.fetch_depth(self.track, self.session.index[name])

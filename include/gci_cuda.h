@@ -120,6 +120,10 @@ int gci_merge_max(gci_ctx* ctx, int32_t track_a, int32_t track_b, int32_t track_
 /* resume path (utility/GCI_score.py:11-39): load one contig's depth from the host */
 int gci_load_depth(gci_ctx* ctx, int32_t track, int32_t contig, const int32_t* depth, int64_t n);
 int gci_fetch_depth(gci_ctx* ctx, int32_t track, int32_t contig, int32_t* out, int64_t n);
+/* the same values as uint8 (width 1) or uint16 (width 2) when every depth fits: 4x / 2x fewer bytes over
+   PCIe.  *overflow != 0 means some value did not fit and `out` was not written: retry wider. */
+int gci_fetch_depth_narrow(gci_ctx* ctx, int32_t track, int32_t contig, void* out, int64_t n, int32_t width,
+                           int32_t* overflow);
 /* sum of depth per contig (mean depth of GCI.py:862-868 = sum / length) */
 int gci_depth_sums(gci_ctx* ctx, int32_t track, int64_t* sums /* [n_contigs] */);
 /* decimal text of one contig's depth, one value per line (GCI.py:115-117), produced on the GPU;

@@ -253,3 +253,21 @@ def test_full_size_chr19_properties(ctx):
     for hs, he in d.holes[0]:
         k = np.searchsorted(gs, hs, side="right") - 1
         assert k >= 0 and gs[k] <= hs and ge[k] >= he
+
+
+def test_narrow_fetch_widths(ctx):
+    rng = np.random.default_rng(11)
+    L = 10_007
+    ctx.set_contigs([L, 33])
+    for hi, want in ((200, np.uint8), (60_000, np.uint16), (70_000, np.int32)):
+        d = rng.integers(0, hi + 1, L).astype(np.int32)
+        d[-1] = hi
+        ctx.load_depth(0, 0, d)
+        ctx.load_depth(0, 1, np.arange(33, dtype=np.int32))
+        got = ctx.fetch_depth_narrow(0, 0)
+        assert got.dtype == want and np.array_equal(got.astype(np.int64), d)
+        assert np.array_equal(ctx.fetch_depth_narrow(0, 1).astype(np.int64), np.arange(33))
+    d = rng.integers(-5, 5, L).astype(np.int32)
+    ctx.load_depth(0, 0, d)
+    got = ctx.fetch_depth_narrow(0, 0)
+    assert got.dtype == np.int32 and np.array_equal(got, d)
