@@ -68,6 +68,7 @@ _SIGNATURES = {
     "gci_fetch_depth_narrow": (C.c_int, [_p, _i32, _i32, _p, _i64, _i32, C.POINTER(_i32)]),
     "gci_depth_sums": (C.c_int, [_p, _i32, _p]),
     "gci_depth_text": (C.c_int, [_p, _i32, _i32, _i64, _i64, _p, _i64, C.POINTER(_i64)]),
+    "gci_depth_gzip": (C.c_int, [_p, _i32, _i32, _i64, _i64, C.c_char_p, _i32, _p, _i64, C.POINTER(_i64)]),
     "gci_scan": (C.c_int, [_p, _i32, _i32, _i32, _i32, C.POINTER(_i64)]),
     "gci_scan_windows": (C.c_int, [_p, _i32, _i32, _i32, _i64, _p, _p, _p, C.POINTER(_i64)]),
     "gci_fetch_intervals": (C.c_int, [_p, _i32, _i64, _p, _p, _p, C.POINTER(_i64)]),
@@ -326,6 +327,18 @@ class Context:
         if n.value:
             self._check(self._lib.gci_depth_text(self._h, track, contig, first, count, _ptr(buf), n.value,
                                                  C.byref(n)))
+        return buf
+
+    def depth_gzip(self, track, contig, first=0, count=None, header=b""):
+        """gzip members (compressed on the GPU) of `header` + the "%d\n" lines of depth[first:first+count]."""
+        if count is None:
+            count = int(self.lengths[contig]) - first
+        n = _i64()
+        self._check(self._lib.gci_depth_gzip(self._h, track, contig, first, count, header, len(header), None, 0,
+                                             C.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        self._check(self._lib.gci_depth_gzip(self._h, track, contig, first, count, header, len(header), _ptr(buf),
+                                             n.value, C.byref(n)))
         return buf
 
     # ---- scan / score ----

@@ -6,5 +6,5 @@ OUT="$HERE/../libgci_cuda.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O3,-Wall -shared
        -cudart static ${GCI_NVCC_EXTRA:-})
-"$NVCC" "${FLAGS[@]}" "$@" -o "$OUT" "$HERE/api.cu" "$HERE/filter.cu" "$HERE/depth.cu" "$HERE/scan.cu"
+"$NVCC" "${FLAGS[@]}" "$@" -o "$OUT" "$HERE/api.cu" "$HERE/filter.cu" "$HERE/depth.cu" "$HERE/scan.cu" "$HERE/gzip.cu"
 echo "built $OUT"

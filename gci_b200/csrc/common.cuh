@@ -145,6 +145,11 @@ struct gci_ctx {
   DevBuf tmp[10];                   // small per-call scratch (score terms, fetches)
   Track track[GCI_MAX_TRACKS];
 
+  // gci_depth_gzip: packed members of the last size query, kept until they are fetched
+  bool gz_valid = false;
+  unsigned long long gz_key = 0;
+  int64_t gz_total = 0;
+
   StageTimer timer;
   void* pinned_scratch = nullptr;
   size_t pinned_cap = 0;

@@ -153,23 +153,22 @@ def _adopt(depths, session=None, track=TRACK_HIFI) -> DeviceDepths:
 # L3: depth file
 # ------------------------------------------------------------------------------------------------
 def write_depth(directory='.', prefix='GCI', depths={}, threads=1):
-    """GCI.py:99-143: `>name` then one decimal per line, gzip (multi-member)."""
+    """GCI.py:99-143: `>name` then one decimal per line, gzip (multi-member like the reference's).
+    Text formatting and DEFLATE both run on the GPU (gci_depth_gzip); only compressed bytes reach the host."""
     depths = _adopt(depths)
     ctx = depths.session.ctx
     idx = depths.session.index
-
-    def pieces():
+    with open(f'{directory}/{prefix}.depth.gz', 'wb') as f:
         for target in depths.keys():
             c = idx[target]
             n = int(depths.session.lengths[c])
             head = f'>{target}\n'.encode('utf-8')
-            if n == 0:
-                yield head
+            if n == 0 or len(head) > 400:
+                f.write(gio._gzip_member(head, 6))
+                head = b''
             for first in range(0, n, TEXT_CHUNK):
-                txt = ctx.depth_text(depths.track, c, first, min(TEXT_CHUNK, n - first)).tobytes()
-                yield (head + txt) if first == 0 else txt
-
-    gio.write_depth_gz(f'{directory}/{prefix}.depth.gz', pieces(), threads)
+                f.write(ctx.depth_gzip(depths.track, c, first, min(TEXT_CHUNK, n - first),
+                                       head if first == 0 else b'').tobytes())
 
 
 # ------------------------------------------------------------------------------------------------

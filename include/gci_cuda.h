@@ -131,6 +131,12 @@ int gci_depth_sums(gci_ctx* ctx, int32_t track, int64_t* sums /* [n_contigs] */)
 int gci_depth_text(gci_ctx* ctx, int32_t track, int32_t contig, int64_t first, int64_t count,
                    char* out, int64_t cap, int64_t* n_bytes);
 
+/* the same text already compressed on the GPU: a sequence of complete gzip members (one per 8192 positions;
+   the reference also writes a multi-member file, GCI.py:134-143) of `header` (e.g. ">name\n", may be empty)
+   followed by the depth lines of [first, first+count).  Call with out = NULL to get the byte count. */
+int gci_depth_gzip(gci_ctx* ctx, int32_t track, int32_t contig, int64_t first, int64_t count, const char* header,
+                   int32_t header_len, char* out, int64_t cap, int64_t* n_bytes);
+
 /* ---- gap scan ----------------------------------------------------------------------------- */
 /* collapse_depth_range(depths, lo, hi, flank_len, 0) over every selected contig (GCI.py:356-390) */
 int gci_scan(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int32_t flank_len, int64_t* n_intervals);

@@ -271,3 +271,28 @@ def test_narrow_fetch_widths(ctx):
     ctx.load_depth(0, 0, d)
     got = ctx.fetch_depth_narrow(0, 0)
     assert got.dtype == np.int32 and np.array_equal(got, d)
+
+
+def test_gpu_gzip_members_decompress_to_reference_text(ctx):
+    """.depth.gz produced on the GPU: gzip.decompress of the members == the reference's text stream"""
+    import gzip
+    rng = np.random.default_rng(5)
+    L = 70_001
+    d = np.zeros(L, np.int32)
+    pos = 0
+    while pos < L:                       # runs of equal values with every digit count, incl. 1-2 line runs
+        run = int(rng.choice([1, 2, 3, 5, 86, 87, 129, 300, 5000]))
+        d[pos:pos + run] = int(rng.choice([0, 7, 23, 100, 65535, 1234567, 2147483647, -5]))
+        pos += run
+    ctx.set_contigs([L, 5])
+    ctx.load_depth(0, 0, d)
+    ctx.load_depth(0, 1, np.array([1, 1, 2, 2, 2], np.int32))
+    want = ">ctg one\n" + "".join(f"{v}\n" for v in d.tolist())
+    got = ctx.depth_gzip(0, 0, header=b">ctg one\n").tobytes()
+    assert gzip.decompress(got).decode() == want
+    assert len(got) < len(want) / 20
+    # sub-range without header, and a tiny contig
+    got = ctx.depth_gzip(0, 0, 8190, 20_000).tobytes()
+    assert gzip.decompress(got).decode() == "".join(f"{v}\n" for v in d[8190:28190].tolist())
+    assert gzip.decompress(ctx.depth_gzip(0, 1, header=b">x\n").tobytes()) == b">x\n1\n1\n2\n2\n2\n"
+    assert gzip.decompress(ctx.depth_gzip(0, 1, 0, 0, header=b">x\n").tobytes()) == b">x\n"
