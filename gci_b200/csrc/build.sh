@@ -8,3 +8,6 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
        -cudart static ${GCI_NVCC_EXTRA:-})
 "$NVCC" "${FLAGS[@]}" "$@" -o "$OUT" "$HERE/api.cu" "$HERE/filter.cu" "$HERE/depth.cu" "$HERE/scan.cu" "$HERE/gzip.cu"
 echo "built $OUT"
+CXX="${CXX:-g++}"
+"$CXX" -O3 -std=c++17 -fPIC -shared -Wall -pthread -o "$HERE/../libgci_io.so" "$HERE/io_native.cpp" -lz
+echo "built $HERE/../libgci_io.so"

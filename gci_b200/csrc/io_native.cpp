@@ -1,0 +1,453 @@
+// libgci_io.so — native (C++17, zlib, std::thread) decoders into the columnar record schema:
+// BAM/BGZF (parallel inflate + parallel record parse, CG:B,I long CIGARs, typed NM), PAF, FASTA N-runs.
+// Replaces what the reference gets from pysam / htslib / Biopython (GCI.py:150-166, :201-208, :218-229,
+// :28-35), which are not available in the image.  Host code only; the C ABI is include/gci_io.h.
+#include <fcntl.h>
+#include <stdint.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <string_view>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/gci_io.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& m) {
+  g_err = m;
+  return -1;
+}
+
+struct MappedFile {
+  const uint8_t* p = nullptr;
+  size_t n = 0;
+  int fd = -1;
+  bool open(const char* path) {
+    fd = ::open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0) return false;
+    n = (size_t)st.st_size;
+    if (n == 0) { p = nullptr; return true; }
+    void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) return false;
+    p = (const uint8_t*)m;
+    madvise(m, n, MADV_SEQUENTIAL);
+    return true;
+  }
+  ~MappedFile() {
+    if (p) munmap((void*)p, n);
+    if (fd >= 0) ::close(fd);
+  }
+};
+
+template <typename F>
+void parallel_for(int64_t n, int threads, F&& fn) {
+  threads = (int)std::max<int64_t>(1, std::min<int64_t>(threads, n));
+  if (threads == 1) { fn(0, n, 0); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; t++) th.emplace_back([&, t] { fn(n * t / threads, n * (t + 1) / threads, t); });
+  for (auto& x : th) x.join();
+}
+
+inline uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
+inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline int32_t rdi32(const uint8_t* p) { int32_t v; memcpy(&v, p, 4); return v; }
+
+}  // namespace
+
+struct gci_interner {
+  std::unordered_map<std::string, uint32_t> map;
+  std::vector<const std::string*> order;
+};
+
+struct gci_bam {
+  std::vector<uint8_t> data;                 // inflated BAM stream
+  std::vector<std::string> ref_names;
+  std::vector<int64_t> ref_lens;
+  std::vector<size_t> rec_off;               // offset of every record's block_size field
+  std::vector<uint64_t> cig_off;             // [n+1]
+  std::vector<uint8_t> cg;                   // record uses the CG tag for its CIGAR
+  std::vector<size_t> cg_off;                // offset of the CG payload (first op) when cg[i]
+  int threads = 1;
+};
+
+extern "C" {
+
+const char* gci_io_last_error(void) { return g_err.c_str(); }
+
+gci_interner* gci_interner_create(void) { return new gci_interner(); }
+void gci_interner_destroy(gci_interner* it) { delete it; }
+int64_t gci_interner_size(gci_interner* it) { return it ? (int64_t)it->map.size() : 0; }
+
+// ---- BAM ------------------------------------------------------------------------------------------
+int gci_bam_open(const char* path, int threads, gci_bam** out) {
+  if (!path || !out) return fail("bad argument");
+  *out = nullptr;
+  MappedFile f;
+  if (!f.open(path)) return fail(std::string("cannot open ") + path);
+  // pass 1: walk the BGZF block headers (BSIZE in the BC extra field, ISIZE in the trailer)
+  struct Blk { size_t src, clen, dst, ulen; };
+  std::vector<Blk> blocks;
+  size_t pos = 0, total = 0;
+  while (pos + 18 <= f.n) {
+    const uint8_t* b = f.p + pos;
+    if (!(b[0] == 0x1f && b[1] == 0x8b && b[2] == 8 && (b[3] & 4))) return fail("not a BGZF block");
+    const size_t xlen = rd16(b + 10);
+    size_t bsize = 0;
+    for (size_t k = 0; k + 4 <= xlen;) {
+      const uint8_t* e = b + 12 + k;
+      const size_t slen = rd16(e + 2);
+      if (e[0] == 66 && e[1] == 67 && slen == 2) bsize = (size_t)rd16(e + 4) + 1;
+      k += 4 + slen;
+    }
+    if (bsize == 0 || pos + bsize > f.n) return fail("BGZF block without BSIZE / truncated file");
+    const size_t ulen = rd32(b + bsize - 4);
+    blocks.push_back({pos + 12 + xlen, bsize - 12 - xlen - 8, total, ulen});
+    total += ulen;
+    pos += bsize;
+  }
+  auto* bam = new gci_bam();
+  bam->threads = std::max(1, threads);
+  bam->data.resize(total);
+  // pass 2: inflate the blocks in parallel
+  std::atomic<int> bad{0};
+  parallel_for((int64_t)blocks.size(), bam->threads, [&](int64_t a, int64_t b, int) {
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+    for (int64_t i = a; i < b; i++) {
+      const Blk& k = blocks[i];
+      if (k.ulen == 0) continue;
+      inflateReset(&zs);
+      zs.next_in = const_cast<Bytef*>(f.p + k.src);
+      zs.avail_in = (uInt)k.clen;
+      zs.next_out = bam->data.data() + k.dst;
+      zs.avail_out = (uInt)k.ulen;
+      const int rc = inflate(&zs, Z_FINISH);
+      if (rc != Z_STREAM_END || zs.avail_out != 0) { bad = 1; break; }
+    }
+    inflateEnd(&zs);
+  });
+  if (bad) { delete bam; return fail("BGZF inflate failed"); }
+  // header
+  const std::vector<uint8_t>& d = bam->data;
+  if (d.size() < 12 || memcmp(d.data(), "BAM\1", 4) != 0) { delete bam; return fail("not a BAM file"); }
+  size_t p = 8 + (size_t)rdi32(d.data() + 4);
+  if (p + 4 > d.size()) { delete bam; return fail("truncated BAM header"); }
+  const int32_t n_ref = rdi32(d.data() + p);
+  p += 4;
+  for (int32_t i = 0; i < n_ref; i++) {
+    if (p + 4 > d.size()) { delete bam; return fail("truncated BAM header"); }
+    const int32_t l_name = rdi32(d.data() + p);
+    if (p + 8 + (size_t)l_name > d.size()) { delete bam; return fail("truncated BAM header"); }
+    bam->ref_names.emplace_back((const char*)d.data() + p + 4, (size_t)std::max(0, l_name - 1));
+    bam->ref_lens.push_back(rdi32(d.data() + p + 4 + l_name));
+    p += 8 + l_name;
+  }
+  // record boundaries (sequential: each record names its own size)
+  while (p + 4 <= d.size()) {
+    const int32_t bs = rdi32(d.data() + p);
+    if (bs < 32 || p + 4 + (size_t)bs > d.size()) { delete bam; return fail("corrupt BAM record"); }
+    bam->rec_off.push_back(p);
+    p += 4 + (size_t)bs;
+  }
+  // per-record CIGAR length (CG tag aware), in parallel
+  const int64_t n = (int64_t)bam->rec_off.size();
+  bam->cig_off.assign(n + 1, 0);
+  bam->cg.assign(n, 0);
+  bam->cg_off.assign(n, 0);
+  parallel_for(n, bam->threads, [&](int64_t a, int64_t b, int) {
+    for (int64_t i = a; i < b; i++) {
+      const uint8_t* r = d.data() + bam->rec_off[i];
+      const uint32_t n_cig = rd16(r + 16);
+      uint64_t ops = n_cig;
+      if (n_cig == 2) {
+        const int32_t l_seq = rdi32(r + 20);
+        const uint8_t l_name = r[12];
+        const uint8_t* cig = r + 36 + l_name;
+        const uint32_t o0 = rd32(cig), o1 = rd32(cig + 4);
+        if ((o0 & 15) == 4 && (int32_t)(o0 >> 4) == l_seq && (o1 & 15) == 3) {
+          // long CIGAR placeholder (SAM spec §4.2.2): look for CG:B,I
+          const uint8_t* end = r + 4 + rdi32(r);
+          const uint8_t* x = cig + 8 + (l_seq + 1) / 2 + l_seq;
+          while (x + 3 <= end) {
+            const uint8_t t = x[2];
+            if (x[0] == 'C' && x[1] == 'G' && t == 'B' && x[3] == 'I') {
+              ops = rd32(x + 4);
+              bam->cg[i] = 1;
+              bam->cg_off[i] = (size_t)(x + 8 - d.data());
+              break;
+            }
+            x += 3;
+            if (t == 'A' || t == 'c' || t == 'C') x += 1;
+            else if (t == 's' || t == 'S') x += 2;
+            else if (t == 'i' || t == 'I' || t == 'f') x += 4;
+            else if (t == 'Z' || t == 'H') { while (x < end && *x) x++; x++; }
+            else if (t == 'B') {
+              const uint8_t st = x[0];
+              const uint32_t cnt = rd32(x + 1);
+              const int sz = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+              x += 5 + (size_t)cnt * sz;
+            } else break;
+          }
+        }
+      }
+      bam->cig_off[i + 1] = ops;
+    }
+  });
+  for (int64_t i = 0; i < n; i++) bam->cig_off[i + 1] += bam->cig_off[i];
+  *out = bam;
+  return 0;
+}
+
+void gci_bam_close(gci_bam* b) { delete b; }
+int32_t gci_bam_n_refs(gci_bam* b) { return b ? (int32_t)b->ref_names.size() : 0; }
+const char* gci_bam_ref_name(gci_bam* b, int32_t i) { return b->ref_names[i].c_str(); }
+int64_t gci_bam_ref_len(gci_bam* b, int32_t i) { return b->ref_lens[i]; }
+int64_t gci_bam_n_records(gci_bam* b) { return b ? (int64_t)b->rec_off.size() : 0; }
+int64_t gci_bam_n_ops(gci_bam* b) { return b && !b->cig_off.empty() ? (int64_t)b->cig_off.back() : 0; }
+
+int gci_bam_fill(gci_bam* b, gci_interner* it, int32_t* ref_id, int32_t* ref_start, uint8_t* mapq, uint16_t* flag,
+                 int32_t* nm, int32_t* qlen, uint32_t* read_id, uint64_t* cigar_off, uint32_t* cigar) {
+  if (!b || !it) return fail("bad argument");
+  const int64_t n = (int64_t)b->rec_off.size();
+  const std::vector<uint8_t>& d = b->data;
+  memcpy(cigar_off, b->cig_off.data(), sizeof(uint64_t) * (size_t)(n + 1));
+  parallel_for(n, b->threads, [&](int64_t a0, int64_t a1, int) {
+    for (int64_t i = a0; i < a1; i++) {
+      const uint8_t* r = d.data() + b->rec_off[i];
+      const uint8_t* end = r + 4 + rdi32(r);
+      ref_id[i] = rdi32(r + 4);
+      ref_start[i] = rdi32(r + 8);
+      const uint8_t l_name = r[12];
+      mapq[i] = r[13];
+      const uint32_t n_cig = rd16(r + 16);
+      flag[i] = rd16(r + 18);
+      const int32_t l_seq = rdi32(r + 20);
+      qlen[i] = l_seq;
+      const uint8_t* cig = r + 36 + l_name;
+      if (b->cg[i]) memcpy(cigar + cigar_off[i], d.data() + b->cg_off[i], 4 * (size_t)(cigar_off[i + 1] - cigar_off[i]));
+      else memcpy(cigar + cigar_off[i], cig, 4 * (size_t)n_cig);
+      // NM aux (any integer type)
+      int32_t nmv = INT32_MIN;
+      const uint8_t* x = cig + 4 * (size_t)n_cig + (l_seq + 1) / 2 + l_seq;
+      while (x + 3 <= end) {
+        const uint8_t t = x[2];
+        const bool is_nm = x[0] == 'N' && x[1] == 'M';
+        x += 3;
+        if (t == 'A' || t == 'c' || t == 'C') { if (is_nm) nmv = t == 'c' ? (int8_t)x[0] : x[0]; x += 1; }
+        else if (t == 's' || t == 'S') { if (is_nm) nmv = t == 's' ? (int16_t)rd16(x) : rd16(x); x += 2; }
+        else if (t == 'i' || t == 'I' || t == 'f') { if (is_nm && t != 'f') nmv = rdi32(x); x += 4; }
+        else if (t == 'Z' || t == 'H') { while (x < end && *x) x++; x++; }
+        else if (t == 'B') {
+          const uint8_t st = x[0];
+          const uint32_t cnt = rd32(x + 1);
+          const int sz = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+          x += 5 + (size_t)cnt * sz;
+        } else break;
+        if (is_nm && nmv != INT32_MIN) break;
+      }
+      nm[i] = nmv;
+    }
+  });
+  // read names -> dense ids, in file order (sequential: one shared table per read type)
+  for (int64_t i = 0; i < n; i++) {
+    const uint8_t* r = d.data() + b->rec_off[i];
+    const uint8_t l_name = r[12];
+    std::string name((const char*)r + 36, l_name ? (size_t)l_name - 1 : 0);
+    auto ins = it->map.emplace(std::move(name), (uint32_t)it->map.size());
+    read_id[i] = ins.first->second;
+  }
+  return 0;
+}
+
+// ---- PAF ------------------------------------------------------------------------------------------
+struct gci_paf {
+  std::vector<uint32_t> read_id;
+  std::vector<int32_t> cols[9];   // qlen qstart qend ref_id tstart tend nmatch alnlen mapq
+};
+
+static inline bool parse_int(std::string_view s, long long& v) {
+  // Python int(): optional surrounding whitespace was already stripped by split; optional sign
+  if (s.empty()) return false;
+  size_t i = 0;
+  bool neg = false;
+  if (s[0] == '+' || s[0] == '-') { neg = s[0] == '-'; i = 1; }
+  if (i >= s.size()) return false;
+  long long x = 0;
+  for (; i < s.size(); i++) {
+    if (s[i] == '_') continue;
+    if (s[i] < '0' || s[i] > '9') return false;
+    x = x * 10 + (s[i] - '0');
+  }
+  v = neg ? -x : x;
+  return true;
+}
+
+int gci_paf_open(const char* path, gci_interner* it, int32_t n_contigs, const char* const* contig_names,
+                 gci_paf** out) {
+  if (!path || !it || !out) return fail("bad argument");
+  *out = nullptr;
+  MappedFile f;
+  if (!f.open(path)) return fail(std::string("cannot open ") + path);
+  std::unordered_map<std::string_view, int32_t> cidx;
+  for (int32_t i = 0; i < n_contigs; i++) cidx.emplace(std::string_view(contig_names[i]), i);
+  auto* paf = new gci_paf();
+  const char* p = (const char*)f.p;
+  const char* end = p + f.n;
+  int64_t line_no = 0;
+  while (p < end) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+    const char* le = nl ? nl : end;
+    line_no++;
+    // line.strip().split("\t")
+    const char* a = p;
+    const char* b = le;
+    while (a < b && (*a == ' ' || *a == '\t' || *a == '\r' || *a == '\v' || *a == '\f')) a++;
+    while (b > a && (b[-1] == ' ' || b[-1] == '\t' || b[-1] == '\r' || b[-1] == '\v' || b[-1] == '\f')) b--;
+    std::string_view col[12];
+    int nc = 0;
+    const char* s = a;
+    for (const char* q = a; q <= b && nc < 12; q++) {
+      if (q == b || *q == '\t') {
+        col[nc++] = std::string_view(s, (size_t)(q - s));
+        s = q + 1;
+      }
+    }
+    if (nc < 12) { delete paf; return fail("PAF line " + std::to_string(line_no) + ": fewer than 12 columns"); }
+    long long v[12];
+    static const int want[9] = {1, 2, 3, 7, 8, 9, 10, 11, -1};
+    for (int k = 0; want[k] >= 0; k++)
+      if (!parse_int(col[want[k]], v[want[k]])) {
+        delete paf;
+        return fail("PAF line " + std::to_string(line_no) + ": invalid integer");
+      }
+    auto ins = it->map.emplace(std::string(col[0]), (uint32_t)it->map.size());
+    paf->read_id.push_back(ins.first->second);
+    auto c = cidx.find(col[5]);
+    paf->cols[0].push_back((int32_t)v[1]);
+    paf->cols[1].push_back((int32_t)v[2]);
+    paf->cols[2].push_back((int32_t)v[3]);
+    paf->cols[3].push_back(c == cidx.end() ? -1 : c->second);
+    paf->cols[4].push_back((int32_t)v[7]);
+    paf->cols[5].push_back((int32_t)v[8]);
+    paf->cols[6].push_back((int32_t)v[9]);
+    paf->cols[7].push_back((int32_t)v[10]);
+    paf->cols[8].push_back((int32_t)v[11]);
+    p = nl ? nl + 1 : end;
+  }
+  *out = paf;
+  return 0;
+}
+
+int64_t gci_paf_n_lines(gci_paf* p) { return p ? (int64_t)p->read_id.size() : 0; }
+void gci_paf_close(gci_paf* p) { delete p; }
+int gci_paf_fill(gci_paf* p, uint32_t* read_id, int32_t* qlen, int32_t* qstart, int32_t* qend, int32_t* ref_id,
+                 int32_t* tstart, int32_t* tend, int32_t* nmatch, int32_t* alnlen, int32_t* mapq) {
+  if (!p) return fail("bad argument");
+  const size_t n = p->read_id.size();
+  memcpy(read_id, p->read_id.data(), 4 * n);
+  int32_t* dst[9] = {qlen, qstart, qend, ref_id, tstart, tend, nmatch, alnlen, mapq};
+  for (int k = 0; k < 9; k++) memcpy(dst[k], p->cols[k].data(), 4 * n);
+  return 0;
+}
+
+// ---- FASTA: record ids and N/n runs (GCI.py:28-35, :939-941) ------------------------------------------
+struct gci_fasta {
+  std::vector<std::string> ids;
+  std::vector<int32_t> run_rec;
+  std::vector<int64_t> run_start, run_end;
+};
+
+int gci_fasta_open(const char* path, gci_fasta** out) {
+  if (!path || !out) return fail("bad argument");
+  *out = nullptr;
+  // plain or gzip: gzread handles both transparently
+  gzFile g = gzopen(path, "rb");
+  if (!g) return fail(std::string("cannot open ") + path);
+  gzbuffer(g, 1 << 20);
+  auto* fa = new gci_fasta();
+  std::vector<char> buf(1 << 22);
+  bool in_header = false, at_line_start = true;
+  std::string header;
+  int64_t pos = 0, run0 = -1;
+  auto close_run = [&]() {
+    if (run0 >= 0) {
+      fa->run_rec.push_back((int32_t)fa->ids.size() - 1);
+      fa->run_start.push_back(run0);
+      fa->run_end.push_back(pos);
+      run0 = -1;
+    }
+  };
+  for (;;) {
+    const int got = gzread(g, buf.data(), (unsigned)buf.size());
+    if (got < 0) { gzclose(g); delete fa; return fail("read error"); }
+    if (got == 0) break;
+    for (int i = 0; i < got; i++) {
+      const char c = buf[i];
+      if (in_header) {
+        if (c == '\n') {
+          size_t a = 0;
+          while (a < header.size() && (header[a] == ' ' || header[a] == '\t')) a++;
+          size_t b = a;
+          while (b < header.size() && header[b] != ' ' && header[b] != '\t' && header[b] != '\r') b++;
+          fa->ids.emplace_back(header.substr(a, b - a));
+          in_header = false;
+          at_line_start = true;
+          pos = 0;
+        } else header.push_back(c);
+        continue;
+      }
+      if (at_line_start && c == '>') {
+        close_run();
+        in_header = true;
+        header.clear();
+        continue;
+      }
+      if (c == '\n') { at_line_start = true; continue; }
+      at_line_start = false;
+      if (c == '\r' || c == ' ' || c == '\t') continue;      // line.strip()
+      if (fa->ids.empty()) continue;                          // text before the first header
+      if (c == 'N' || c == 'n') { if (run0 < 0) run0 = pos; }
+      else close_run();
+      pos++;
+    }
+  }
+  if (in_header) {   // header without trailing newline
+    size_t b = 0;
+    while (b < header.size() && header[b] != ' ' && header[b] != '\t' && header[b] != '\r') b++;
+    fa->ids.emplace_back(header.substr(0, b));
+    pos = 0;
+  }
+  close_run();
+  gzclose(g);
+  *out = fa;
+  return 0;
+}
+
+int32_t gci_fasta_n_records(gci_fasta* f) { return f ? (int32_t)f->ids.size() : 0; }
+const char* gci_fasta_id(gci_fasta* f, int32_t i) { return f->ids[i].c_str(); }
+int64_t gci_fasta_n_runs(gci_fasta* f) { return f ? (int64_t)f->run_rec.size() : 0; }
+int gci_fasta_runs(gci_fasta* f, int32_t* rec, int64_t* start, int64_t* end) {
+  if (!f) return fail("bad argument");
+  const size_t n = f->run_rec.size();
+  memcpy(rec, f->run_rec.data(), 4 * n);
+  memcpy(start, f->run_start.data(), 8 * n);
+  memcpy(end, f->run_end.data(), 8 * n);
+  return 0;
+}
+void gci_fasta_close(gci_fasta* f) { delete f; }
+
+}  // extern "C"

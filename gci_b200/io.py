@@ -61,12 +61,37 @@ def _bgzf_blocks(payload: bytes, level=6):
     yield _BGZF_EOF
 
 
-def read_bam_header(path):
-    """(names, lengths) of the BAM header (GCI.py:201-207, :963-965)."""
-    # headers are small: decompress block by block until the reference list is complete
-    data = bgzf_decompress(path)
+def read_bam_header_py(path):
+    """(names, lengths) of the BAM header (GCI.py:201-207, :963-965): inflates only the leading BGZF blocks."""
+    data = b""
+    with open(path, "rb") as f:
+        while True:
+            head = f.read(18)
+            if len(head) < 18:
+                break
+            xlen = struct.unpack_from("<H", head, 10)[0]
+            extra = head[12:] + f.read(max(0, xlen - 6))
+            bsize = None
+            k = 0
+            while k + 4 <= xlen:
+                slen = struct.unpack_from("<H", extra, k + 2)[0]
+                if extra[k] == 66 and extra[k + 1] == 67 and slen == 2:
+                    bsize = struct.unpack_from("<H", extra, k + 4)[0] + 1
+                k += 4 + slen
+            if bsize is None:
+                raise ValueError(f"{path}: BGZF block without BSIZE")
+            rest = f.read(bsize - 12 - xlen)
+            data += zlib.decompress(rest[:-8], -15)
+            try:
+                names, lengths, _ = _parse_bam_header(data)
+                return names, lengths
+            except (struct.error, IndexError):
+                continue
     names, lengths, _ = _parse_bam_header(data)
     return names, lengths
+
+
+read_bam_header = read_bam_header_py
 
 
 def _parse_bam_header(data):
@@ -114,7 +139,7 @@ def _scan_aux(data, pos, end):
     return nm, cg
 
 
-def read_bam(path, intern=None):
+def read_bam_py(path, intern=None):
     """Decode a BAM file into (names, lengths, AlnTable).  `intern` maps read names to dense ids and
     is shared by all files of one read type (it is updated in place)."""
     if intern is None:
@@ -151,6 +176,45 @@ def read_bam(path, intern=None):
     cigar = np.concatenate(cig).astype(np.uint32) if cig else np.zeros(0, np.uint32)
     tab = AlnTable(ref_id, start, mapq, flag, nm, qlen, rid, off, cigar)
     return names, lengths, tab
+
+
+class NameTable:
+    """Read-name interning shared by the files of one read type: native table when libgci_io.so is built,
+    a dict otherwise (the pure-Python decoders are kept as a cross-check of the native ones)."""
+
+    def __init__(self, native=None):
+        from . import io_native
+        self.native = io_native.available() if native is None else native
+        self.table = io_native.Interner() if self.native else {}
+
+    def __len__(self):
+        return len(self.table)
+
+
+def read_bam(path, names: "NameTable" = None, threads=1):
+    """Decode a BAM file -> (contig names, lengths, AlnTable)."""
+    names = names or NameTable()
+    if names.native:
+        from . import io_native
+        return io_native.read_bam(path, names.table, threads)
+    n, l, tab = read_bam_py(path, names.table)
+    tab.contig_names, tab.contig_lengths = n, l
+    return n, l, tab
+
+
+def read_paf(path, contig_names, names: "NameTable" = None) -> PafTable:
+    names = names or NameTable()
+    if names.native:
+        from . import io_native
+        return io_native.read_paf(path, list(contig_names), names.table)
+    return read_paf_py(path, {c: i for i, c in enumerate(contig_names)}, names.table)
+
+
+def read_fasta_gaps(path):
+    from . import io_native
+    if io_native.available():
+        return io_native.read_fasta_gaps(path)
+    return read_fasta_gaps_py(path)
 
 
 def write_bam(path, names, lengths, tab: AlnTable, read_names=None, level=1, long_cigar_as_cg=True):
@@ -191,7 +255,7 @@ def write_bam(path, names, lengths, tab: AlnTable, read_names=None, level=1, lon
 # PAF / FASTA / BED
 # ------------------------------------------------------------------------------------------------
 
-def read_paf(path, contig_index, intern=None) -> PafTable:
+def read_paf_py(path, contig_index, intern=None) -> PafTable:
     """Columns 0,1,2,3,5,7,8,9,10,11 of a PAF file (GCI.py:218-229); `line.strip().split('\\t')`."""
     if intern is None:
         intern = {}
@@ -225,7 +289,7 @@ def write_paf(path, tab: PafTable, names, lengths, read_names=None):
 _N_RUN = re.compile(rb"[Nn]+")
 
 
-def read_fasta_gaps(path):
+def read_fasta_gaps_py(path):
     """(record ids in file order, {id: [(start, end), ...]} of N/n runs) — GCI.py:28-35, :939-941.
     The id is the first whitespace-delimited token of the header like Biopython's `record.id`."""
     ids, gaps = [], {}

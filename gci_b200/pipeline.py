@@ -174,9 +174,9 @@ def write_depth(directory='.', prefix='GCI', depths={}, threads=1):
 # ------------------------------------------------------------------------------------------------
 # L2 + L3: filter
 # ------------------------------------------------------------------------------------------------
-def _load_inputs(paf_files, bam_files):
+def _load_inputs(paf_files, bam_files, threads=1):
     """Decode / collect the files of one read type.  Returns (names, lengths, paf tables, bam tables, n_reads)."""
-    intern = {}
+    intern = gio.NameTable()
     bams, pafs = [], []
     names = lengths = None
     for f in bam_files:
@@ -186,13 +186,12 @@ def _load_inputs(paf_files, bam_files):
             if n is None:
                 raise ValueError("in-memory AlnTable needs .contig_names / .contig_lengths")
         else:
-            n, l, t = gio.read_bam(f, intern)
+            n, l, t = gio.read_bam(f, intern, threads)
         if names is None:
             names, lengths = list(n), [int(x) for x in l]     # header of the first BAM (GCI.py:201)
         bams.append(t)
-    index = {n: i for i, n in enumerate(names)}
     for f in paf_files:
-        pafs.append(f if isinstance(f, PafTable) else gio.read_paf(f, index, intern))
+        pafs.append(f if isinstance(f, PafTable) else gio.read_paf(f, names, intern))
     n_reads = len(intern)
     for t in bams + pafs:
         if t.n_records:
@@ -209,7 +208,7 @@ def filter(paf_files=[], bam_files=[], prefix='GCI', map_qual=30, mq_cutoff=50, 
     print(f'Filtering {log_reads_type} alignment files ...')
     session = session or default_session()
     ctx = session.ctx
-    names, lengths, pafs, bams, n_reads = _load_inputs(paf_files, bam_files)
+    names, lengths, pafs, bams, n_reads = _load_inputs(paf_files, bam_files, threads)
     session.configure(names, lengths, chrs_list)
     targets_length = {n: l for n, l, s in zip(names, lengths, session.selected) if s}
     track = TRACK_NANO if log_reads_type == 'ONT' else TRACK_HIFI

@@ -62,12 +62,17 @@ def test_bam_roundtrip(tmp_path):
     names, lengths = gio.read_bam_header(p)
     assert names == d.contigs.names and lengths == [int(x) for x in d.contigs.lengths]
     intern = {}
-    _, _, t = gio.read_bam(p, intern)
+    _, _, t = gio.read_bam_py(p, intern)
     for col in ("ref_id", "ref_start", "mapq", "flag", "nm", "qlen", "cigar_off", "cigar"):
         assert np.array_equal(getattr(t, col), getattr(d.bam, col)), col
     # interned ids follow first appearance; names map back to the synthetic ids
     back = {v: int(k.decode()[4:]) for k, v in intern.items()}
     assert [back[int(i)] for i in t.read_id] == [int(i) for i in d.bam.read_id]
+    # the native decoder (libgci_io.so, parallel inflate) gives the same table
+    for threads in (1, 4):
+        _, _, tn = gio.read_bam(p, gio.NameTable(native=True), threads)
+        for col in ("ref_id", "ref_start", "mapq", "flag", "nm", "qlen", "read_id", "cigar_off", "cigar"):
+            assert np.array_equal(getattr(tn, col), getattr(t, col)), col
 
 
 def test_bam_long_cigar_cg_tag(tmp_path):
@@ -75,8 +80,9 @@ def test_bam_long_cigar_cg_tag(tmp_path):
     t = AlnTable([0], [5], [60], [0], [40000], [160000], [0], np.array([0, len(ops)], np.uint64), ops)
     p = str(tmp_path / "long.bam")
     gio.write_bam(p, ["c"], [500000], t)
-    _, _, back = gio.read_bam(p)
-    assert np.array_equal(back.cigar, ops) and int(back.qlen[0]) == 160000
+    for native in (False, True):
+        _, _, back = gio.read_bam(p, gio.NameTable(native=native))
+        assert np.array_equal(back.cigar, ops) and int(back.qlen[0]) == 160000 and int(back.nm[0]) == 40000
 
 
 def test_paf_fasta_depth_roundtrip(tmp_path):
@@ -84,18 +90,42 @@ def test_paf_fasta_depth_roundtrip(tmp_path):
     paf = synth.aln_to_paf(d.bam)
     p = str(tmp_path / "x.paf")
     gio.write_paf(p, paf, d.contigs.names, d.contigs.lengths)
-    intern = {}
-    back = gio.read_paf(p, {"chr1": 0}, intern)
-    for col in ("qlen", "qstart", "qend", "ref_id", "tstart", "tend", "nmatch", "alnlen", "mapq"):
-        assert np.array_equal(getattr(back, col), getattr(paf, col)), col
+    for native in (False, True):
+        back = gio.read_paf(p, ["chr1"], gio.NameTable(native=native))
+        for col in ("qlen", "qstart", "qend", "ref_id", "tstart", "tend", "nmatch", "alnlen", "mapq"):
+            assert np.array_equal(getattr(back, col), getattr(paf, col)), (native, col)
     fa = str(tmp_path / "r.fa")
     gio.write_fasta(fa, ["chr1", "chr2"], [50_000, 3000], [[(100, 200), (4000, 4010)], []])
-    ids, gaps = gio.read_fasta_gaps(fa)
-    assert ids == ["chr1", "chr2"] and gaps == {"chr1": [(100, 200), (4000, 4010)]}
+    for reader in (gio.read_fasta_gaps_py, gio.read_fasta_gaps):
+        ids, gaps = reader(fa)
+        assert ids == ["chr1", "chr2"] and gaps == {"chr1": [(100, 200), (4000, 4010)]}
     dz = str(tmp_path / "d.depth.gz")
     gio.write_depth_gz(dz, [b">c1\n", b"0\n1\n2\n", b"3\n", b">c2\n7\n"], threads=3)
     got = gio.read_depth_gz(dz)
     assert list(got) == ["c1", "c2"] and got["c1"].tolist() == [0, 1, 2, 3] and got["c2"].tolist() == [7]
+
+
+def test_native_io_exports_every_header_symbol():
+    from gci_b200 import io_native
+    hdr = open(os.path.join(ROOT, "include", "gci_io.h")).read()
+    declared = set(re.findall(r"\b(gci_[a-z0-9_]+)\s*\(", hdr))
+    L = io_native.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(io_native.exported_symbols())
+
+
+def test_native_nm_types_and_missing(tmp_path):
+    """NM stored as c / C / s / S / i / I and a record without NM"""
+    import struct
+    names, lengths = ["c"], [1000]
+    t = AlnTable([0] * 3, [10, 20, 30], [60] * 3, [0] * 3, [5, 300, -(2 ** 31)], [50] * 3, [0, 1, 2],
+                 np.array([0, 1, 2, 3], np.uint64), np.array([(50 << 4)] * 3, np.uint32))
+    p = str(tmp_path / "nm.bam")
+    gio.write_bam(p, names, lengths, t)
+    for native in (False, True):
+        _, _, back = gio.read_bam(p, gio.NameTable(native=native))
+        assert back.nm.tolist() == [5, 300, -(2 ** 31)]
 
 
 def test_host_n50_matches_oracle():
