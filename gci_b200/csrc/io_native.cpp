@@ -4,6 +4,7 @@
 // :28-35), which are not available in the image.  Host code only; the C ABI is include/gci_io.h.
 #include <fcntl.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -73,7 +74,9 @@ struct gci_interner {
 };
 
 struct gci_bam {
-  std::vector<uint8_t> data;                 // inflated BAM stream
+  uint8_t* data = nullptr;                   // inflated BAM stream (uninitialised allocation: the inflate
+  size_t data_n = 0;                         // threads fault the pages in parallel)
+  ~gci_bam() { free(data); }
   std::vector<std::string> ref_names;
   std::vector<int64_t> ref_lens;
   std::vector<size_t> rec_off;               // offset of every record's block_size field
@@ -120,7 +123,9 @@ int gci_bam_open(const char* path, int threads, gci_bam** out) {
   }
   auto* bam = new gci_bam();
   bam->threads = std::max(1, threads);
-  bam->data.resize(total);
+  bam->data = (uint8_t*)malloc(total ? total : 1);
+  bam->data_n = total;
+  if (!bam->data) { delete bam; return fail("out of memory"); }
   // pass 2: inflate the blocks in parallel
   std::atomic<int> bad{0};
   parallel_for((int64_t)blocks.size(), bam->threads, [&](int64_t a, int64_t b, int) {
@@ -133,7 +138,7 @@ int gci_bam_open(const char* path, int threads, gci_bam** out) {
       inflateReset(&zs);
       zs.next_in = const_cast<Bytef*>(f.p + k.src);
       zs.avail_in = (uInt)k.clen;
-      zs.next_out = bam->data.data() + k.dst;
+      zs.next_out = bam->data + k.dst;
       zs.avail_out = (uInt)k.ulen;
       const int rc = inflate(&zs, Z_FINISH);
       if (rc != Z_STREAM_END || zs.avail_out != 0) { bad = 1; break; }
@@ -142,7 +147,8 @@ int gci_bam_open(const char* path, int threads, gci_bam** out) {
   });
   if (bad) { delete bam; return fail("BGZF inflate failed"); }
   // header
-  const std::vector<uint8_t>& d = bam->data;
+  struct View { const uint8_t* p; size_t n; const uint8_t* data() const { return p; } size_t size() const { return n; } };
+  const View d{bam->data, bam->data_n};
   if (d.size() < 12 || memcmp(d.data(), "BAM\1", 4) != 0) { delete bam; return fail("not a BAM file"); }
   size_t p = 8 + (size_t)rdi32(d.data() + 4);
   if (p + 4 > d.size()) { delete bam; return fail("truncated BAM header"); }
@@ -223,7 +229,8 @@ int gci_bam_fill(gci_bam* b, gci_interner* it, int32_t* ref_id, int32_t* ref_sta
                  int32_t* nm, int32_t* qlen, uint32_t* read_id, uint64_t* cigar_off, uint32_t* cigar) {
   if (!b || !it) return fail("bad argument");
   const int64_t n = (int64_t)b->rec_off.size();
-  const std::vector<uint8_t>& d = b->data;
+  struct View { const uint8_t* p; const uint8_t* data() const { return p; } };
+  const View d{b->data};
   memcpy(cigar_off, b->cig_off.data(), sizeof(uint64_t) * (size_t)(n + 1));
   parallel_for(n, b->threads, [&](int64_t a0, int64_t a1, int) {
     for (int64_t i = a0; i < a1; i++) {
