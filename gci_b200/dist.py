@@ -97,22 +97,12 @@ def assign_contigs(lengths, weights, world):
 
 def exchange_file_tables(tables):
     """tables: per file, the tuple (read_id, contig, start, end, qlen, highq) of THIS rank's winners
-    (Context.fetch_file_table).  Returns the same per file with every rank's rows concatenated; a read
-    that won on two ranks (duplicate primary names on different contigs) keeps the row of the
-    higher contig index, which is the reference's fetch order (GCI.py:260-269)."""
-    out = []
-    for cols in tables:
-        gathered = [np.concatenate(allgather_varlen(np.ascontiguousarray(c))) for c in cols]
-        r, c = gathered[0], gathered[1]
-        if len(r):
-            order = np.lexsort((c, r))              # by read, then contig: the last of each read wins
-            last = np.ones(len(r), bool)
-            rs = r[order]
-            last[:-1] = rs[1:] != rs[:-1]
-            keep = order[last]
-            gathered = [g[keep] for g in gathered]
-        out.append(tuple(gathered))
-    return out
+    (Context.fetch_file_table).  Returns the same per file with every rank's rows merged; a read that won on
+    two ranks (duplicate primary names on different contigs) keeps the row of the higher contig index, which is
+    the reference's fetch order (GCI.py:260-269); high-quality marks are OR-ed per read."""
+    from .sharded import merge_tables
+    gathered = [tuple(np.concatenate(allgather_varlen(np.ascontiguousarray(c))) for c in cols) for cols in tables]
+    return merge_tables([gathered])
 
 
 _ROW_CAP = 8192
