@@ -83,18 +83,23 @@ __global__ void cigar_tile_index_kernel(const uint64_t* __restrict__ off, int64_
 struct CigAcc {
   uint32_t tot, i, d, n, s;   // tot = M + '=' + X + I + D
   __device__ __forceinline__ void clear() { tot = i = d = n = s = 0; }
+  // branch-free: a branch per op costs more than the five selects
   __device__ __forceinline__ void add(uint32_t op) {
     const uint32_t c = op & 15u, l = op >> 4;
-    if ((0xFE78u >> c) & 1u) {          // N, S, H, P, B (and invalid codes): rare, at read ends
-      n += (c == 3u) ? l : 0u;
-      s += (c == 4u) ? l : 0u;
-    } else {                            // M, I, D, '=', X
-      tot += l;
-      i += (c == 1u) ? l : 0u;
-      d += (c == 2u) ? l : 0u;
-    }
+    tot += l * ((0x187u >> c) & 1u);          // op codes 0 (M), 1 (I), 2 (D), 7 (=), 8 (X)
+    i += (c == 1u) ? l : 0u;
+    d += (c == 2u) ? l : 0u;
+    n += (c == 3u) ? l : 0u;
+    s += (c == 4u) ? l : 0u;
   }
   __device__ __forceinline__ bool any() const { return (tot | n | s) != 0; }
+  __device__ __forceinline__ void warp_reduce() {   // REDUX.SUM: one instruction per counter
+    tot = __reduce_add_sync(0xffffffffu, tot);
+    i = __reduce_add_sync(0xffffffffu, i);
+    d = __reduce_add_sync(0xffffffffu, d);
+    n = __reduce_add_sync(0xffffffffu, n);
+    s = __reduce_add_sync(0xffffffffu, s);
+  }
   // stats layout: [Mx, I, D, N, S]
   __device__ __forceinline__ void flush(uint32_t* p) const {
     const uint32_t mx = tot - i - d;
@@ -122,9 +127,50 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
   const int2 tr = tile_rec[tile];
   const int64_t r_lo = tr.x;                      // first / last record with an op in this tile
   const int n_loc = tr.y - tr.x + 1;
+
+  if (n_loc == 1) {
+    // the whole tile lies inside one record (the common ONT case: thousands of ops per record): which
+    // thread sums which op does not matter -> lane-consecutive 16-byte loads straight from HBM, one
+    // block-wide reduction, no staging
+    CigAcc acc;
+    acc.clear();
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(cigar + o0);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int v = h * CIG_THREADS + tid;        // uint4 index inside the tile
+      if (v * 4 + 4 <= tile_n) {
+        const uint4 q = src[v];
+        acc.add(q.x); acc.add(q.y); acc.add(q.z); acc.add(q.w);
+      } else {
+        for (int k = v * 4; k < tile_n; k++) acc.add(cigar[o0 + k]);
+      }
+    }
+    acc.warp_reduce();
+    uint32_t* red = s_acc;                        // [8 warps][5]
+    if (lane == 0) {
+      red[(tid >> 5) * 5 + 0] = acc.tot; red[(tid >> 5) * 5 + 1] = acc.i; red[(tid >> 5) * 5 + 2] = acc.d;
+      red[(tid >> 5) * 5 + 3] = acc.n; red[(tid >> 5) * 5 + 4] = acc.s;
+    }
+    __syncthreads();
+    if (tid < 5) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int w = 0; w < CIG_THREADS / 32; w++) v += red[w * 5 + tid];
+      red[40 + tid] = v;
+    }
+    __syncthreads();
+    if (tid < 5) {
+      const uint32_t tot = red[40], ci = red[41], cd = red[42];
+      const uint32_t val = tid == 0 ? tot - ci - cd : red[40 + tid];
+      const bool complete = off[r_lo] >= (uint64_t)o0 && off[r_lo + 1] <= (uint64_t)(o0 + tile_n);
+      uint32_t* g = stats + r_lo * 8 + tid;
+      if (complete) *g = val; else if (val) atomicAdd(g, val);
+    }
+    return;
+  }
+
   const int first = tid * CIG_OPT;
   const int nb = min(CIG_OPT, tile_n - first);    // my ops (<= 0: none)
-
   if (n_loc > CIG_CAP) {
     // pathological tile (more than 1024 records in 2048 ops): global atomics, no staging
     if (nb > 0) {
@@ -196,9 +242,8 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
       if (k < nb) acc.add(ops[k]);
   }
   if (warp_one) {
-    // the whole warp sits inside one record (ONT): shuffle-reduce, one flush per warp
-    acc.tot = warp_sum(acc.tot); acc.i = warp_sum(acc.i); acc.d = warp_sum(acc.d);
-    acc.n = warp_sum(acc.n); acc.s = warp_sum(acc.s);
+    // the whole warp sits inside one record: one flush per warp
+    acc.warp_reduce();
     if (lane == 0) acc.flush(&s_acc[rl * 5]);
   } else if (simple) {
     acc.flush(&s_acc[rl * 5]);

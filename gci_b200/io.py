@@ -193,7 +193,7 @@ class NameTable:
 
 def read_bam(path, names: "NameTable" = None, threads=1):
     """Decode a BAM file -> (contig names, lengths, AlnTable)."""
-    names = names or NameTable()
+    names = NameTable() if names is None else names
     if names.native:
         from . import io_native
         return io_native.read_bam(path, names.table, threads)
@@ -203,7 +203,7 @@ def read_bam(path, names: "NameTable" = None, threads=1):
 
 
 def read_paf(path, contig_names, names: "NameTable" = None) -> PafTable:
-    names = names or NameTable()
+    names = NameTable() if names is None else names
     if names.native:
         from . import io_native
         return io_native.read_paf(path, list(contig_names), names.table)

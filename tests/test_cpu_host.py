@@ -135,3 +135,23 @@ def test_host_n50_matches_oracle():
     for _ in range(200):
         v = rng.integers(1, 50, int(rng.integers(0, 12))).tolist()
         assert compute_n50(v) == O.n50(v)
+
+
+def test_name_table_is_shared_between_files(tmp_path):
+    """BAM and PAF of one read type must intern names into the same table (ids line up across files)"""
+    d = synth.make_reads(synth.SynthSpec([40_000], coverage=6, seed=2, read_mean=3000, read_min=500, read_max=8000))
+    bam = synth.drop_reads(d.bam, 0.3, 1)
+    paf = synth.aln_to_paf(d.bam)
+    gio.write_bam(str(tmp_path / "a.bam"), d.contigs.names, d.contigs.lengths, bam)
+    gio.write_paf(str(tmp_path / "a.paf"), paf, d.contigs.names, d.contigs.lengths)
+    for native in (False, True):
+        nt = gio.NameTable(native=native)
+        _, _, b = gio.read_bam(str(tmp_path / "a.bam"), nt)
+        n_after_bam = len(nt)
+        p = gio.read_paf(str(tmp_path / "a.paf"), d.contigs.names, nt)
+        assert n_after_bam == len(np.unique(bam.read_id))
+        assert len(nt) == len(np.union1d(bam.read_id, paf.read_id))
+        # the same read gets the same id in both files: synthetic name -> id maps agree
+        m_b = dict(zip(bam.read_id.tolist(), b.read_id.tolist()))
+        m_p = dict(zip(paf.read_id.tolist(), p.read_id.tolist()))
+        assert all(m_p[k] == v for k, v in m_b.items())
