@@ -154,4 +154,5 @@ def test_name_table_is_shared_between_files(tmp_path):
         # the same read gets the same id in both files: synthetic name -> id maps agree
         m_b = dict(zip(bam.read_id.tolist(), b.read_id.tolist()))
         m_p = dict(zip(paf.read_id.tolist(), p.read_id.tolist()))
-        assert all(m_p[k] == v for k, v in m_b.items())
+        common = set(m_b) & set(m_p)
+        assert len(common) > 20 and all(m_p[k] == m_b[k] for k in common)
