@@ -24,7 +24,7 @@
 constexpr int CIG_THREADS = 256;
 constexpr int CIG_OPT = 8;                       // ops per thread
 constexpr int CIG_TILE = CIG_THREADS * CIG_OPT;  // 2048 ops = 8 KB
-constexpr int CIG_CAP = 1024;                    // records per tile handled through shared memory
+constexpr int CIG_CAP = 512;                     // records per tile handled through shared memory
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -92,6 +92,25 @@ struct CigAcc {
     n += (c == 3u) ? l : 0u;
     s += (c == 4u) ? l : 0u;
   }
+  // 8 ops of one thread.  N, S, H, P, B only occur at the ends of a read, so the common case needs three
+  // counters (tot, I, D); one test on the OR of the one-hot op codes decides per thread.
+  __device__ __forceinline__ void add8(const uint32_t (&op)[8]) {
+    uint32_t seen = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) seen |= 1u << (op[k] & 15u);
+    if (seen & 0xFE78u) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) add(op[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const uint32_t c = op[k] & 15u, l = op[k] >> 4;
+        tot += l;
+        i += (c == 1u) ? l : 0u;
+        d += (c == 2u) ? l : 0u;
+      }
+    }
+  }
   __device__ __forceinline__ bool any() const { return (tot | n | s) != 0; }
   __device__ __forceinline__ void warp_reduce() {   // REDUX.SUM: one instruction per counter
     tot = __reduce_add_sync(0xffffffffu, tot);
@@ -135,14 +154,20 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
     CigAcc acc;
     acc.clear();
     const uint4* __restrict__ src = reinterpret_cast<const uint4*>(cigar + o0);
+    if (tile_n == CIG_TILE) {
+      const uint4 q0 = src[tid], q1 = src[CIG_THREADS + tid];
+      const uint32_t op[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      acc.add8(op);
+    } else {
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int v = h * CIG_THREADS + tid;        // uint4 index inside the tile
-      if (v * 4 + 4 <= tile_n) {
-        const uint4 q = src[v];
-        acc.add(q.x); acc.add(q.y); acc.add(q.z); acc.add(q.w);
-      } else {
-        for (int k = v * 4; k < tile_n; k++) acc.add(cigar[o0 + k]);
+      for (int h = 0; h < 2; h++) {
+        const int v = h * CIG_THREADS + tid;      // uint4 index inside the tile
+        if (v * 4 + 4 <= tile_n) {
+          const uint4 q = src[v];
+          acc.add(q.x); acc.add(q.y); acc.add(q.z); acc.add(q.w);
+        } else {
+          for (int k = v * 4; k < tile_n; k++) acc.add(cigar[o0 + k]);
+        }
       }
     }
     acc.warp_reduce();
@@ -237,9 +262,13 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
   const int rl0 = __shfl_sync(0xffffffffu, rl, 0);
   const bool warp_one = __all_sync(0xffffffffu, simple && nb == CIG_OPT && rl == rl0);
   if (simple) {
+    if (nb == CIG_OPT) {
+      acc.add8(ops);
+    } else {
 #pragma unroll
-    for (int k = 0; k < CIG_OPT; k++)
-      if (k < nb) acc.add(ops[k]);
+      for (int k = 0; k < CIG_OPT; k++)
+        if (k < nb) acc.add(ops[k]);             // unrolled: ops[] must stay in registers
+    }
   }
   if (warp_one) {
     // the whole warp sits inside one record: one flush per warp
