@@ -183,6 +183,8 @@ def main():
     ctx = Context(local)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_contigs(L)
+    if world > 1:
+        D.init_native_comm(ctx)
     pool = PinnedPool()
     from gci_b200.records import AlnTable
     pinned = AlnTable(*[pool.copy(getattr(tab, c)) for c in
@@ -197,11 +199,12 @@ def main():
         n_surv = ctx.filter(**PARAMS)
         ctx.depth(0, FLANK, -1, THRESHOLD)
         n_iv = ctx.scan(0, -1, THRESHOLD, FLANK)
-        n50, nctg, lens, _ = ctx.score_terms(0, 1, n_iv, DIST, FLANK)
         if world > 1:
-            sums = ctx.depth_sums(0)
-            mean, all_ctg, all_len = D.genome_row(int(sums.sum()), sum(L), int(nctg[-1]), lens)
+            # score terms of this rank's contig + the genome row: one ncclAllGather on the library's stream
+            n50, nctg, sums, mean, all_ctg, all_len = ctx.genome_row(0, 1, sum(L), DIST, FLANK)
             result["mean_depth"] = mean
+        else:
+            n50, nctg, lens, _ = ctx.score_terms(0, 1, n_iv, DIST, FLANK)
         result.update(n_surv=n_surv, n_iv=n_iv, n50=int(n50[0]), nctg=int(nctg[0]))
         return n_iv
 
@@ -245,6 +248,17 @@ def main():
     # records resident in HBM for the `value` region
     ctx.reads_begin(data.n_reads)
     ctx.upload_bam(pinned)
+    if world > 1:
+        # once, outside the timed region: the library's NCCL exchange equals the torch.distributed one
+        n_surv = ctx.filter(**PARAMS)
+        ctx.depth(0, FLANK, -1, THRESHOLD)
+        n_iv = ctx.scan(0, -1, THRESHOLD, FLANK)
+        a50, actg, lens, _, asum = ctx.score_terms(0, 1, n_iv, DIST, FLANK, with_sums=True)
+        want = D.genome_row(int(asum[-1]), sum(L), int(actg[-1]), lens)
+        b50, bctg, bsum, mean, all_ctg, all_len = ctx.genome_row(0, 1, sum(L), DIST, FLANK)
+        assert (a50 == b50).all() and (actg == bctg).all() and (asum == bsum).all()
+        assert mean == want[0] and all_ctg == want[1] and sorted(all_len.tolist()) == sorted(want[2].tolist()), \
+            "native NCCL genome row differs from the torch.distributed exchange"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

@@ -74,6 +74,10 @@ _SIGNATURES = {
     "gci_fetch_intervals": (C.c_int, [_p, _i32, _i64, _p, _p, _p, C.POINTER(_i64)]),
     "gci_load_intervals": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _p]),
     "gci_score_terms": (C.c_int, [_p, _i32, _f64, _i32, _p, _p, _i64, _p, _p]),
+    "gci_comm_unique_id": (C.c_int, [_p]),
+    "gci_comm_init": (C.c_int, [_p, _p, _i32, _i32]),
+    "gci_genome_row": (C.c_int, [_p, _i32, _f64, _i32, _i64, _i64, _p, _p, _p, _p]),
+    "gci_score_terms_sums": (C.c_int, [_p, _i32, _f64, _i32, _p, _p, _i64, _p, _p, _p]),
 }
 
 
@@ -363,19 +367,53 @@ class Context:
         self._check(self._lib.gci_fetch_intervals(self._h, track, k, _ptr(s), _ptr(e), _ptr(off), C.byref(n)))
         return s, e, off
 
+    # ---- multi-GPU ----
+    @staticmethod
+    def comm_unique_id():
+        buf = np.zeros(128, np.uint8)
+        if load_library().gci_comm_unique_id(_ptr(buf)) != 0:
+            raise GciError(-1, "ncclGetUniqueId failed (libnccl not loadable?)")
+        return buf
+
+    def comm_init(self, unique_id, rank, world):
+        uid = _arr(unique_id, np.uint8)
+        assert uid.size == 128
+        self._check(self._lib.gci_comm_init(self._h, _ptr(uid), int(rank), int(world)))
+        self.comm_world = int(world)
+
+    def genome_row(self, track, n_owners, sum_len, dist_percent=0.005, flank_len=15, cap=2048):
+        """Score terms of this rank's contigs + one NCCL all-gather of every rank's genome-row terms.
+        -> (n50, n_ctg, depth_sums, mean_depth, total curated contigs, all curated lengths)"""
+        world = self.comm_world
+        n50, nctg, sums = (np.zeros(n_owners + 1, np.int64) for _ in range(3))
+        rows = np.zeros(world * (4 + cap), np.int64)
+        self._check(self._lib.gci_genome_row(self._h, track, float(dist_percent), int(flank_len), int(sum_len), cap,
+                                             _ptr(n50), _ptr(nctg), _ptr(sums), _ptr(rows)))
+        o = rows.reshape(world, 4 + cap)
+        head = o[:, :4].sum(axis=0)
+        all_len = o[:, 4:][np.arange(cap)[None, :] < o[:, 3:4]]
+        mean = float(head[0]) / float(head[1]) if head[1] else float("nan")
+        return n50, nctg, sums, mean, int(head[2]), all_len
+
     def load_intervals(self, track, contig, owner_off, start, end):
         contig, owner_off = _arr(contig, np.int32), _arr(owner_off, np.int64)
         start, end = _arr(start, np.int32), _arr(end, np.int32)
         self._check(self._lib.gci_load_intervals(self._h, track, len(contig), _ptr(contig), _ptr(owner_off),
                                                  _ptr(start), _ptr(end)))
 
-    def score_terms(self, track, n_owners, n_intervals, dist_percent=0.005, flank_len=15):
+    def score_terms(self, track, n_owners, n_intervals, dist_percent=0.005, flank_len=15, with_sums=False):
         """-> (n50[owners+1], n_ctg[owners+1], lengths, lengths_off[owners+1]); the last n50 / n_ctg entry is
-        over all owners together (the Genome / All_regions row)."""
+        over all owners together (the Genome / All_regions row).  with_sums: also the per-contig depth sums
+        (+ total) from the same device->host copy."""
         n50 = np.zeros(n_owners + 1, np.int64)
         nctg = np.zeros(n_owners + 1, np.int64)
         off = np.zeros(n_owners + 1, np.int64)
         lengths = np.zeros(int(n_intervals) + n_owners + 1, np.int64)
+        if with_sums:
+            sums = np.zeros(n_owners + 1, np.int64)
+            self._check(self._lib.gci_score_terms_sums(self._h, track, float(dist_percent), int(flank_len), _ptr(n50),
+                                                       _ptr(nctg), len(lengths), _ptr(lengths), _ptr(off), _ptr(sums)))
+            return n50, nctg, lengths[:int(off[-1])], off, sums
         self._check(self._lib.gci_score_terms(self._h, track, float(dist_percent), int(flank_len), _ptr(n50),
                                               _ptr(nctg), len(lengths), _ptr(lengths), _ptr(off)))
         return n50, nctg, lengths[:int(off[-1])], off

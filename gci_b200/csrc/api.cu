@@ -156,6 +156,7 @@ int gci_create(int device, gci_ctx** out) {
     return GCI_E_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming);
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   *out = ctx;
   return GCI_OK;
@@ -165,6 +166,7 @@ void gci_destroy(gci_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  gci_comm_destroy_internal(ctx);
   for (auto& b : ctx->bam) free_bam(ctx, b);
   for (auto& f : ctx->files) free_table(ctx, f);
   for (auto& t : ctx->track) free_track(ctx, t);
@@ -177,6 +179,7 @@ void gci_destroy(gci_ctx* ctx) {
   for (auto& d : ctx->tmp) ctx->release(d);
   for (cudaEvent_t e : ctx->timer.pool) cudaEventDestroy(e);
   if (ctx->pinned_scratch) cudaFreeHost(ctx->pinned_scratch);
+  if (ctx->h2d_done) cudaEventDestroy(ctx->h2d_done);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }

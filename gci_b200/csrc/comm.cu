@@ -1,0 +1,149 @@
+// Multi-GPU exchange of the genome-row terms over NCCL (NVLink / NVSwitch), on the context's own stream.
+//
+// Contigs shard across GPUs; what the ranks have to share for the final `.gci` genome row and the mean
+// depth is tiny: (sum depth, sum length, curated-contig count, curated lengths) per rank (GCI.py:572-587,
+// :862-868).  The score kernels leave those terms on the device; one pack kernel builds a fixed-size row,
+// one ncclAllGather moves it, one device->host copy returns every rank's row together with this rank's own
+// per-contig terms: a single synchronisation per step.  NCCL is resolved at run time with dlopen so that the
+// process uses the NCCL that is already loaded (torch's) and the library has no link-time dependency on it.
+#include <dlfcn.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, gci_nccl_id, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+
+bool load_nccl(std::string& err) {
+  if (g_nccl.ok) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // the copy torch already loaded
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+  g_nccl.h = h;
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, gci_nccl_id, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) {
+    err = "libnccl lacks an expected symbol";
+    return false;
+  }
+  g_nccl.ok = true;
+  return true;
+}
+constexpr int NCCL_INT64 = 4;   // ncclInt64 (nccl.h)
+}  // namespace
+
+// row = [sum depth, sum length, curated contigs, n lengths, lengths ... (cap)] from the score result buffer
+// res = [n50 (no+1) | n_ctg (no) | depth sum (no) | gap slots (n_slots)]; the order of lengths is irrelevant
+// for an N50, so they are appended with an atomic cursor
+__global__ void pack_row_kernel(const int64_t* __restrict__ res, int64_t no, int64_t n_slots,
+                                const int64_t* __restrict__ owner_off, long long sum_len, int64_t cap,
+                                long long* __restrict__ row) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i == 0) {
+    long long sd = 0, sc = 0;
+    for (int64_t o = 0; o < no; o++) { sc += res[no + 1 + o]; sd += res[2 * no + 1 + o]; }
+    row[0] = sd;
+    row[1] = sum_len;
+    row[2] = sc;
+  }
+  if (i >= n_slots) return;
+  // non-positive slots were not emitted by the reference (or, for an owner without intervals, are a
+  // non-positive [E - S] that can never be an N50): only positive lengths travel
+  const long long v = res[3 * no + 1 + i];
+  if (v > 0) {
+    const unsigned long long k = atomicAdd((unsigned long long*)&row[3], 1ull);
+    if ((int64_t)k < cap) row[4 + k] = v;
+  }
+}
+
+extern "C" {
+
+int gci_comm_unique_id(gci_nccl_id* out) {
+  std::string err;
+  if (!out || !load_nccl(err)) return GCI_E_CUDA;
+  return g_nccl.GetUniqueId(out) == 0 ? GCI_OK : GCI_E_CUDA;
+}
+
+int gci_comm_init(gci_ctx* ctx, const gci_nccl_id* id, int32_t rank, int32_t world) {
+  if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  std::string err;
+  if (!load_nccl(err)) return ctx->fail(GCI_E_CUDA, "%s", err.c_str());
+  if (ctx->nccl_comm) { g_nccl.CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+  const int rc = g_nccl.CommInitRank(&ctx->nccl_comm, world, *id, rank);
+  if (rc != 0)
+    return ctx->fail(GCI_E_CUDA, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  ctx->comm_rank = rank;
+  ctx->comm_world = world;
+  return GCI_OK;
+}
+
+void gci_comm_destroy_internal(gci_ctx* ctx) {
+  if (ctx && ctx->nccl_comm && g_nccl.ok) g_nccl.CommDestroy(ctx->nccl_comm);
+  if (ctx) ctx->nccl_comm = nullptr;
+}
+
+int gci_genome_row(gci_ctx* ctx, int32_t track, double dist_percent, int32_t flank_len, int64_t sum_len, int64_t cap,
+                   int64_t* n50, int64_t* n_ctg, int64_t* depth_sums, int64_t* rows) {
+  if (!ctx || !rows || cap < 1 || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (!ctx->nccl_comm) return ctx->fail(GCI_E_ARG, "gci_genome_row: gci_comm_init has not been called");
+  Track& t = ctx->track[track];
+  if (t.owners_are_windows || !t.sums_valid)
+    return ctx->fail(GCI_E_ARG, "gci_genome_row needs a whole-contig scan of a track with valid depth sums");
+  int64_t no = 0, n_slots = 0;
+  ctx->stage_begin(GCI_ST_SCORE);
+  GCI_TRY(gci_launch_score_kernels(ctx, t, dist_percent, flank_len, &no, &n_slots));
+  const int64_t row_n = 4 + cap;
+  const int world = ctx->comm_world;
+  DevBuf &d_res = ctx->tmp[1], &d_row = ctx->tmp[2], &d_all = ctx->tmp[5];
+  GCI_TRY(ctx->ensure(d_row, 8 * (size_t)row_n));
+  GCI_TRY(ctx->ensure(d_all, 8 * (size_t)row_n * world));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(d_row.p, 0, 8 * (size_t)row_n, ctx->stream));
+  pack_row_kernel<<<(unsigned)((std::max<int64_t>(1, n_slots) + 255) / 256), 256, 0, ctx->stream>>>(
+      d_res.as<int64_t>(), no, n_slots, t.owner_off.as<int64_t>(), (long long)sum_len, cap, d_row.as<long long>());
+  GCI_LAUNCH_CHECK(ctx);
+  const int rc = g_nccl.AllGather(d_row.p, d_all.p, (size_t)row_n, NCCL_INT64, ctx->nccl_comm, ctx->stream);
+  if (rc != 0)
+    return ctx->fail(GCI_E_CUDA, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  ctx->launches++;
+  const int64_t n_own = 3 * no + 1;
+  int64_t* h = (int64_t*)ctx->pinned(8 * (size_t)(n_own + row_n * world));
+  if (!h) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
+  GCI_TRY(gci_d2h(ctx, h, d_res.p, 8 * (size_t)n_own));
+  GCI_TRY(gci_d2h(ctx, h + n_own, d_all.p, 8 * (size_t)row_n * world));
+  ctx->stage_end();
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n50) memcpy(n50, h, 8 * (size_t)(no + 1));
+  long long all_c = 0, all_d = 0;
+  for (int64_t o = 0; o < no; o++) {
+    if (n_ctg) n_ctg[o] = h[no + 1 + o];
+    if (depth_sums) depth_sums[o] = h[2 * no + 1 + o];
+    all_c += h[no + 1 + o];
+    all_d += h[2 * no + 1 + o];
+  }
+  if (n_ctg) n_ctg[no] = all_c;
+  if (depth_sums) depth_sums[no] = all_d;
+  memcpy(rows, h + n_own, 8 * (size_t)row_n * world);
+  for (int r = 0; r < world; r++)
+    if (rows[(size_t)r * row_n + 3] > cap)
+      return ctx->fail(GCI_E_ARG, "gci_genome_row: rank %d has %lld curated lengths, more than cap %lld", r,
+                       (long long)rows[(size_t)r * row_n + 3], (long long)cap);
+  return GCI_OK;
+}
+
+}  // extern "C"

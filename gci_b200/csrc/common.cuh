@@ -103,6 +103,7 @@ struct StageTimer {
 struct gci_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t h2d_done = nullptr;
   std::string err;
   int64_t launches = 0;
   int64_t dev_bytes = 0;
@@ -150,6 +151,10 @@ struct gci_ctx {
   unsigned long long gz_key = 0;
   int64_t gz_total = 0;
 
+  // NCCL communicator of a multi-GPU run (comm.cu; resolved with dlopen)
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+
   StageTimer timer;
   void* pinned_scratch = nullptr;
   size_t pinned_cap = 0;
@@ -177,6 +182,9 @@ int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip);
 int gci_run_join(gci_ctx* ctx, double op);
 int gci_alloc_track(gci_ctx* ctx, int track);
 int gci_compute_flags(gci_ctx* ctx, int track, int32_t lo, int32_t hi);
+int gci_launch_score_kernels(gci_ctx* ctx, Track& t, double dist_percent, int32_t flank_len, int64_t* n_owners,
+                             int64_t* n_slots);   // scan.cu: result stays in ctx->tmp[1], no sync
+extern "C" void gci_comm_destroy_internal(gci_ctx* ctx);
 
 #define GCI_LAUNCH_CHECK(ctx)                      \
   do {                                             \

@@ -488,18 +488,20 @@ static int extract_runs(gci_ctx* ctx, Track& t, const std::vector<int64_t>& lay_
 //   -dp merge (GCI.py:509-518) joins neighbours across every gap <= dist, starting from the sentinel
 //   (S,S) and ending at E, so the merged complement keeps exactly the gaps that are > dist (and > 0).
 //   N50 (GCI.py:473-479) = largest length v with  2 * sum{len >= v} >= total.
-// Result buffer (int64): [ n50 (owners+1) | n_ctg (owners) | gap slots (n_intervals + owners) ];
+// Result buffer (int64): [ n50 (owners+1) | n_ctg (owners) | depth sum (owners) | gap slots (n_intervals + owners) ];
 // owner o uses gap slots [owner_off[o] + o, owner_off[o+1] + o + 1).
 struct OwnerBounds { long long S, E; double dist; };
 
 __global__ void __launch_bounds__(256)
 complement_kernel(int64_t n_owners, const int64_t* __restrict__ owner_off, const int32_t* __restrict__ iv_start,
-                  const int32_t* __restrict__ iv_end, const OwnerBounds* __restrict__ ob, int64_t* __restrict__ res) {
+                  const int32_t* __restrict__ iv_end, const OwnerBounds* __restrict__ ob, int64_t* __restrict__ res,
+                  const long long* __restrict__ sums, const int32_t* __restrict__ owner_contig) {
   __shared__ long long s_red[8];
   const int64_t o = blockIdx.x;
   const int64_t a = owner_off[o], b = owner_off[o + 1];
-  int64_t* g = res + (2 * n_owners + 1) + a + o;
+  int64_t* g = res + (3 * n_owners + 1) + a + o;
   const int64_t n = b - a;
+  if (threadIdx.x == 0) res[2 * n_owners + 1 + o] = sums ? sums[owner_contig[o]] : 0;   // depth sum of the contig
   const long long S = ob[o].S, E = ob[o].E;
   const double d = ob[o].dist;
   long long my_ctg = 0;
@@ -541,7 +543,7 @@ n50_kernel(int64_t n_owners, const int64_t* __restrict__ owner_off, int64_t n_sl
   __shared__ long long s_bcast;
   __shared__ long long s_val[N50_SMALL];
   const int64_t o = blockIdx.x;
-  const int64_t* vals = res + (2 * n_owners + 1);
+  const int64_t* vals = res + (3 * n_owners + 1);
   const int64_t lo = o < n_owners ? owner_off[o] + o : 0;
   const int64_t hi = o < n_owners ? owner_off[o + 1] + o + 1 : n_slots;
   const int64_t n = hi - lo;
@@ -608,6 +610,48 @@ n50_kernel(int64_t n_owners, const int64_t* __restrict__ owner_off, int64_t n_sl
     }
   }
   if (threadIdx.x == 0) res[o] = best;
+}
+
+// score kernels of one track's last scan; the result buffer stays on the device in ctx->tmp[1]
+int gci_launch_score_kernels(gci_ctx* ctx, Track& t, double dist_percent, int32_t flank_len, int64_t* n_owners,
+                             int64_t* n_slots_out) {
+  const int64_t no = t.n_owners;
+  if (no <= 0 || (int64_t)t.h_owner_off.size() != no + 1) return ctx->fail(GCI_E_ARG, "score terms: no scan on this track");
+  const int64_t n_slots = t.n_intervals + no;
+  const int64_t n_res = 3 * no + 1 + n_slots;
+  // per-owner [S, E) and dist (GCI.py:505-508, :629-634), staged through pinned memory
+  OwnerBounds* ob = (OwnerBounds*)ctx->pinned(sizeof(OwnerBounds) * (size_t)no);
+  if (!ob) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
+  for (int64_t o = 0; o < no; o++) {
+    if (t.owners_are_windows) {
+      // complement / merge use the region bounds as given (GCI.py:629-634), only the depth slice is
+      // normalised (:627)
+      ob[o].S = t.raw_lo[o];
+      ob[o].E = t.raw_hi[o];
+      ob[o].dist = (double)(ob[o].E - ob[o].S) * dist_percent;      // targets_length = {target: exp_n50}
+    } else {
+      const int64_t L = ctx->len[t.owner_contig[o]];
+      ob[o].S = flank_len;
+      ob[o].E = L - flank_len;
+      ob[o].dist = (double)L * dist_percent;
+    }
+  }
+  DevBuf &d_ob = ctx->tmp[0], &d_res = ctx->tmp[1];
+  GCI_TRY(gci_h2d(ctx, d_ob, ob, sizeof(OwnerBounds) * (size_t)no));
+  // the pinned staging buffer is reused by the caller: the copy above must have left the host first
+  GCI_CUDA_TRY(ctx, cudaEventRecord(ctx->h2d_done, ctx->stream));
+  GCI_TRY(ctx->ensure(d_res, sizeof(int64_t) * (size_t)n_res));
+  complement_kernel<<<(unsigned)no, 256, 0, ctx->stream>>>(
+      no, t.owner_off.as<int64_t>(), t.iv_start.as<int32_t>(), t.iv_end.as<int32_t>(), d_ob.as<OwnerBounds>(),
+      d_res.as<int64_t>(), (!t.owners_are_windows && t.sums_valid) ? t.sums.as<long long>() : nullptr,
+      t.win_contig.as<int32_t>());
+  GCI_LAUNCH_CHECK(ctx);
+  n50_kernel<<<(unsigned)(no + 1), 256, 0, ctx->stream>>>(no, t.owner_off.as<int64_t>(), n_slots, d_res.as<int64_t>());
+  GCI_LAUNCH_CHECK(ctx);
+  GCI_CUDA_TRY(ctx, cudaEventSynchronize(ctx->h2d_done));
+  *n_owners = no;
+  *n_slots_out = n_slots;
+  return GCI_OK;
 }
 
 extern "C" {
@@ -720,6 +764,7 @@ int gci_load_intervals(gci_ctx* ctx, int32_t track, int64_t n_owners, const int3
   t.owner_contig.assign(contig, contig + n_owners);
   t.h_owner_off.assign(owner_off, owner_off + n_owners + 1);
   GCI_TRY(ctx->ensure(t.owner_off, sizeof(int64_t) * (size_t)(n_owners + 3)));
+  GCI_TRY(gci_h2d(ctx, t.win_contig, contig, sizeof(int32_t) * n_owners));
   GCI_CUDA_TRY(ctx, cudaMemcpyAsync(t.owner_off.p, owner_off, sizeof(int64_t) * (n_owners + 1), cudaMemcpyHostToDevice,
                                     ctx->stream));
   GCI_TRY(gci_h2d(ctx, t.iv_start, start, sizeof(int32_t) * n));
@@ -731,44 +776,23 @@ int gci_load_intervals(gci_ctx* ctx, int32_t track, int64_t n_owners, const int3
 
 int gci_score_terms(gci_ctx* ctx, int32_t track, double dist_percent, int32_t flank_len, int64_t* n50,
                     int64_t* n_ctg, int64_t cap_lengths, int64_t* lengths, int64_t* lengths_off) {
+  return gci_score_terms_sums(ctx, track, dist_percent, flank_len, n50, n_ctg, cap_lengths, lengths, lengths_off,
+                              nullptr);
+}
+
+int gci_score_terms_sums(gci_ctx* ctx, int32_t track, double dist_percent, int32_t flank_len, int64_t* n50,
+                         int64_t* n_ctg, int64_t cap_lengths, int64_t* lengths, int64_t* lengths_off,
+                         int64_t* depth_sums) {
   if (!ctx || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
   Track& t = ctx->track[track];
-  const int64_t no = t.n_owners;
-  if (no <= 0 || (int64_t)t.h_owner_off.size() != no + 1)
-    return ctx->fail(GCI_E_ARG, "gci_score_terms: no scan on track %d", track);
-  const int64_t n_slots = t.n_intervals + no;
-  const int64_t n_res = 2 * no + 1 + n_slots;
-  // per-owner [S, E) and dist (GCI.py:505-508, :629-634), staged through pinned memory
-  char* pin = (char*)ctx->pinned(sizeof(OwnerBounds) * (size_t)no + sizeof(int64_t) * (size_t)n_res);
-  if (!pin) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
-  OwnerBounds* ob = (OwnerBounds*)pin;
-  int64_t* h_res = (int64_t*)(pin + sizeof(OwnerBounds) * (size_t)no);
-  for (int64_t o = 0; o < no; o++) {
-    if (t.owners_are_windows) {
-      // complement / merge use the region bounds as given (GCI.py:629-634), only the depth slice is
-      // normalised (:627)
-      ob[o].S = t.raw_lo[o];
-      ob[o].E = t.raw_hi[o];
-      ob[o].dist = (double)(ob[o].E - ob[o].S) * dist_percent;      // targets_length = {target: exp_n50}
-    } else {
-      const int64_t L = ctx->len[t.owner_contig[o]];
-      ob[o].S = flank_len;
-      ob[o].E = L - flank_len;
-      ob[o].dist = (double)L * dist_percent;
-    }
-  }
+  int64_t no = 0, n_slots = 0;
   ctx->stage_begin(GCI_ST_SCORE);
-  DevBuf &d_ob = ctx->tmp[0], &d_res = ctx->tmp[1];
-  GCI_TRY(gci_h2d(ctx, d_ob, ob, sizeof(OwnerBounds) * (size_t)no));
-  GCI_TRY(ctx->ensure(d_res, sizeof(int64_t) * (size_t)n_res));
-  complement_kernel<<<(unsigned)no, 256, 0, ctx->stream>>>(no, t.owner_off.as<int64_t>(), t.iv_start.as<int32_t>(),
-                                                           t.iv_end.as<int32_t>(), d_ob.as<OwnerBounds>(),
-                                                           d_res.as<int64_t>());
-  GCI_LAUNCH_CHECK(ctx);
-  n50_kernel<<<(unsigned)(no + 1), 256, 0, ctx->stream>>>(no, t.owner_off.as<int64_t>(), n_slots, d_res.as<int64_t>());
-  GCI_LAUNCH_CHECK(ctx);
-  GCI_TRY(gci_d2h(ctx, h_res, d_res.p, sizeof(int64_t) * (size_t)n_res));
+  GCI_TRY(gci_launch_score_kernels(ctx, t, dist_percent, flank_len, &no, &n_slots));
+  const int64_t n_res = 3 * no + 1 + n_slots;
+  int64_t* h_res = (int64_t*)ctx->pinned(sizeof(int64_t) * (size_t)n_res);
+  if (!h_res) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
+  GCI_TRY(gci_d2h(ctx, h_res, ctx->tmp[1].p, sizeof(int64_t) * (size_t)n_res));
   ctx->stage_end();
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (n50) memcpy(n50, h_res, sizeof(int64_t) * (size_t)(no + 1));
@@ -777,11 +801,18 @@ int gci_score_terms(gci_ctx* ctx, int32_t track, double dist_percent, int32_t fl
     for (int64_t o = 0; o < no; o++) { n_ctg[o] = h_res[no + 1 + o]; all += n_ctg[o]; }
     n_ctg[no] = all;
   }
+  if (depth_sums) {
+    if (t.owners_are_windows || !t.sums_valid)
+      return ctx->fail(GCI_E_ARG, "depth sums ride along only for a whole-contig scan of a track with valid sums");
+    int64_t all = 0;
+    for (int64_t o = 0; o < no; o++) { depth_sums[o] = h_res[2 * no + 1 + o]; all += depth_sums[o]; }
+    depth_sums[no] = all;
+  }
   // compact the emitted lengths per owner, in position order (zero slots were not emitted, except the
   // unconditional [E - S] entry of an owner without intervals)
   int rc = GCI_OK;
   if (lengths_off || lengths) {
-    const int64_t* h_gaps = h_res + 2 * no + 1;
+    const int64_t* h_gaps = h_res + 3 * no + 1;
     const std::vector<int64_t>& h_off = t.h_owner_off;
     int64_t k = 0;
     for (int64_t o = 0; o < no && rc == GCI_OK; o++) {

@@ -83,6 +83,15 @@ def allgather_varlen(arr):
     return [o[:s].cpu().numpy().astype(orig) for o, s in zip(outs, sizes)]
 
 
+def init_native_comm(ctx):
+    """Create the library's own NCCL communicator (Context.genome_row): rank 0 makes the id, everybody gets it."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = ctx.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)
+    uid = allreduce(uid.astype(np.int64), "sum").astype(np.uint8)
+    ctx.comm_init(uid, rank, world)
+
+
 def assign_contigs(lengths, weights, world):
     """LPT bin packing of contigs onto ranks by (aligned bases, length).  Returns owner[contig]."""
     order = sorted(range(len(lengths)), key=lambda i: (-(weights[i] if weights is not None else 0), -lengths[i], i))
@@ -105,7 +114,7 @@ def exchange_file_tables(tables):
     return merge_tables([gathered])
 
 
-_ROW_CAP = 8192
+_ROW_CAP = 2048
 _row_cache = {}
 
 
@@ -148,7 +157,9 @@ def genome_row(sum_depth, sum_len, n_ctg, lengths):
     if dev.type == "cuda":
         torch.cuda.current_stream().synchronize()
     o = h_out.numpy().reshape(world, 4 + _ROW_CAP)
-    tot_d, tot_l, tot_c = int(o[:, 0].sum()), int(o[:, 1].sum()), int(o[:, 2].sum())
-    all_len = np.concatenate([o[r, 4:4 + int(o[r, 3])] for r in range(world)])
+    head = o[:, :4].sum(axis=0)
+    tot_d, tot_l, tot_c = int(head[0]), int(head[1]), int(head[2])
+    body = o[:, 4:]
+    all_len = body[np.arange(_ROW_CAP)[None, :] < o[:, 3:4]]
     mean = float(tot_d) / float(tot_l) if tot_l else float("nan")
     return mean, tot_c, all_len

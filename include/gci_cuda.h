@@ -162,6 +162,26 @@ int gci_score_terms(gci_ctx* ctx, int32_t track, double dist_percent, int32_t fl
                     int64_t* n50 /* [owners] */, int64_t* n_ctg /* [owners] */,
                     int64_t cap_lengths, int64_t* lengths, int64_t* lengths_off /* [owners+1] */);
 
+/* same, plus the per-contig depth sums (and their total) in the same device->host copy: the terms of the
+   genome row / mean depth that ranks exchange in a multi-GPU run.  Whole-contig scans only. */
+int gci_score_terms_sums(gci_ctx* ctx, int32_t track, double dist_percent, int32_t flank_len, int64_t* n50,
+                         int64_t* n_ctg, int64_t cap_lengths, int64_t* lengths, int64_t* lengths_off,
+                         int64_t* depth_sums /* [owners+1] */);
+
+/* ---- multi-GPU: one process per GPU, contigs sharded across ranks ---------------------------------- */
+/* NCCL (resolved at run time with dlopen: the copy torch.distributed already loaded, else the system one).
+   Rank 0 creates the id, the host layer broadcasts its 128 bytes, every rank calls gci_comm_init. */
+typedef struct { char internal[128]; } gci_nccl_id;
+int gci_comm_unique_id(gci_nccl_id* out);
+int gci_comm_init(gci_ctx* ctx, const gci_nccl_id* id, int32_t rank, int32_t world);
+/* gci_score_terms_sums for this rank's contigs + ONE ncclAllGather (on the context's stream) of the terms
+   every rank needs for the genome row / mean depth (GCI.py:572-587, :862-868):
+   rows[r * (4 + cap) ...] = { sum depth, sum length, curated contigs, n lengths, curated lengths[cap] } of rank r.
+   One device->host copy, one synchronisation. */
+int gci_genome_row(gci_ctx* ctx, int32_t track, double dist_percent, int32_t flank_len, int64_t sum_len, int64_t cap,
+                   int64_t* n50 /* [owners+1] */, int64_t* n_ctg /* [owners+1] */, int64_t* depth_sums /* [owners+1] */,
+                   int64_t* rows /* [world * (4 + cap)] */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,9 @@ def _check(ctx, names, lengths, pafs, bams, n_reads, selected=None, fl=15, ts=0,
         all_obs += obs
         all_ctg += len(new)
     assert int(n50[-1]) == O.n50(all_obs) and int(nctg[-1]) == all_ctg
+    with_sums = ctx.score_terms(0, len(owners), n_iv, dp, fl, with_sums=True)[4]
+    assert with_sums[:-1].tolist() == [int(want_d[i].sum()) for i in owners] and int(with_sums[-1]) == sum(
+        int(want_d[i].sum()) for i in owners)
 
 
 @pytest.mark.parametrize("seed", range(6))
