@@ -169,6 +169,14 @@ void gci_destroy(gci_ctx* ctx) {
   gci_comm_destroy_internal(ctx);
   for (auto& b : ctx->bam) free_bam(ctx, b);
   for (auto& f : ctx->files) free_table(ctx, f);
+  for (auto& p : ctx->paf)
+    for (DevBuf* d : {&p.read_id, &p.qlen, &p.qstart, &p.qend, &p.ref_id, &p.tstart, &p.tend, &p.nmatch, &p.alnlen, &p.mapq})
+      ctx->release(*d);
+  {
+    PafKept& k = ctx->paf_kept;
+    for (DevBuf* d : {&k.read, &k.ref, &k.qlen, &k.q0, &k.q1, &k.t0, &k.t1, &k.ident, &k.ord, &k.count}) ctx->release(*d);
+  }
+  ctx->release(ctx->d_name_rank);
   for (auto& t : ctx->track) free_track(ctx, t);
   for (DevBuf* d : {&ctx->d_len, &ctx->d_selected, &ctx->d_tile_off, &ctx->d_owner_of, &ctx->d_nr_contig, &ctx->d_nr_start,
                     &ctx->d_nr_end, &ctx->highq, &ctx->surv_contig, &ctx->surv_start, &ctx->surv_end,
@@ -275,7 +283,10 @@ int gci_set_contigs(gci_ctx* ctx, int32_t n, const int64_t* lengths, const uint8
 
 int gci_set_name_rank(gci_ctx* ctx, const int32_t* name_rank) {
   if (!ctx || !name_rank) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
   ctx->name_rank.assign(name_rank, name_rank + ctx->n_contigs);
+  GCI_TRY(gci_h2d(ctx, ctx->d_name_rank, name_rank, sizeof(int32_t) * (size_t)ctx->n_contigs));
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return GCI_OK;
 }
 
@@ -322,7 +333,8 @@ int gci_reads_begin(gci_ctx* ctx, uint32_t n_reads) {
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->n_bam = 0;                 // device buffers of the pools are kept and reused
   ctx->n_files = 0;
-  ctx->paf.clear();
+  ctx->n_paf = 0;
+  ctx->paf_kept.lines_seen = 0;
   ctx->n_reads = n_reads;
   ctx->filtered = false;
   ctx->n_survivors = 0;
@@ -376,25 +388,30 @@ int gci_upload_paf(gci_ctx* ctx, int64_t n, const uint32_t* read_id, const int32
   if (n && (!read_id || !qlen || !qstart || !qend || !ref_id || !tstart || !tend || !nmatch || !alnlen || !mapq))
     return GCI_E_ARG;
   if ((int)ctx->n_files >= GCI_MAX_FILES) return ctx->fail(GCI_E_ARG, "too many files");
-  ctx->paf.emplace_back();
-  PafFile& p = ctx->paf.back();
+  if (n >= (int64_t(1) << 31)) return ctx->fail(GCI_E_ARG, "more than 2^31 lines in one PAF file");
+  cudaSetDevice(ctx->device);
+  if (ctx->n_paf == ctx->paf.size()) ctx->paf.emplace_back();
+  PafFile& p = ctx->paf[ctx->n_paf++];
   p.n = n;
-  p.read_id.assign(read_id, read_id + n);
-  p.qlen.assign(qlen, qlen + n);
-  p.qstart.assign(qstart, qstart + n);
-  p.qend.assign(qend, qend + n);
-  p.ref_id.assign(ref_id, ref_id + n);
-  p.tstart.assign(tstart, tstart + n);
-  p.tend.assign(tend, tend + n);
-  p.nmatch.assign(nmatch, nmatch + n);
-  p.alnlen.assign(alnlen, alnlen + n);
-  p.mapq.assign(mapq, mapq + n);
+  ctx->stage_begin(GCI_ST_H2D);
+  GCI_TRY(gci_h2d(ctx, p.read_id, read_id, 4 * n));
+  GCI_TRY(gci_h2d(ctx, p.qlen, qlen, 4 * n));
+  GCI_TRY(gci_h2d(ctx, p.qstart, qstart, 4 * n));
+  GCI_TRY(gci_h2d(ctx, p.qend, qend, 4 * n));
+  GCI_TRY(gci_h2d(ctx, p.ref_id, ref_id, 4 * n));
+  GCI_TRY(gci_h2d(ctx, p.tstart, tstart, 4 * n));
+  GCI_TRY(gci_h2d(ctx, p.tend, tend, 4 * n));
+  GCI_TRY(gci_h2d(ctx, p.nmatch, nmatch, 4 * n));
+  GCI_TRY(gci_h2d(ctx, p.alnlen, alnlen, 4 * n));
+  GCI_TRY(gci_h2d(ctx, p.mapq, mapq, 4 * n));
+  ctx->stage_end();
   if (ctx->n_files == ctx->files.size()) ctx->files.emplace_back();
   FileTable& f = ctx->files[ctx->n_files++];
   f.kind = 2;   // PAF lines awaiting the election in gci_filter
-  f.src = (int)ctx->paf.size() - 1;
+  f.src = (int)ctx->n_paf - 1;
   f.n = 0;
   ctx->filtered = false;
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return GCI_OK;
 }
 

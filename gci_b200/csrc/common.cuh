@@ -55,12 +55,18 @@ struct BamFile {
   DevBuf tile_rec; // int2[n_op_tiles]: first / last record of every CIGAR op tile (built at upload)
 };
 
-// PAF lines stay on the host: the per-read primary-target election (GCI.py:241-254) is a
-// host stage in this round (SURVEY.md §8a-3 "host C++ first"); its result is uploaded as a table.
+// PAF lines of one file, resident on the device (columns 0,1,2,3,5,7,8,9,10,11 of GCI.py:218-229)
 struct PafFile {
   int64_t n = 0;
-  std::vector<uint32_t> read_id;
-  std::vector<int32_t> qlen, qstart, qend, ref_id, tstart, tend, nmatch, alnlen, mapq;
+  DevBuf read_id, qlen, qstart, qend, ref_id, tstart, tend, nmatch, alnlen, mapq;
+};
+
+// lines of all PAF files of the read set that passed the per-line gate, in arrival order (the reference's
+// `synteny` dict is created once per filter() call and therefore accumulates across PAF files, GCI.py:214)
+struct PafKept {
+  int64_t cap = 0;        // capacity in lines
+  int64_t lines_seen = 0; // host-side upper bound of the kept count
+  DevBuf read, ref, qlen, q0, q1, t0, t1, ident, ord, count;   // count: device cursor (u64)
 };
 
 // one file after its per-file leg: at most one entry per read
@@ -131,6 +137,9 @@ struct gci_ctx {
   std::vector<BamFile> bam;
   size_t n_bam = 0;
   std::vector<PafFile> paf;
+  size_t n_paf = 0;
+  PafKept paf_kept;
+  DevBuf d_name_rank;
   std::vector<FileTable> files;     // join order
   size_t n_files = 0;
   DevBuf highq;                     // uint8[n_reads]

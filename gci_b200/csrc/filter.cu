@@ -2,7 +2,6 @@
 // cross-file same-read join.  Reference: GCI.py:146-169 (read_sam), :211-254 (PAF leg),
 // :257-301 (fan-out merge + join).
 #include <algorithm>
-#include <map>
 
 #include "common.cuh"
 
@@ -462,7 +461,8 @@ static int check_err(gci_ctx* ctx, const char* where, unsigned long long* count)
                      : (h[0] & 2) ? "ZeroDivisionError at GCI.py:165 (clip ratio: no M/=/X/I/S bases)"
                      : (h[0] & 4) ? "ZeroDivisionError at GCI.py:165 (identity: no M/=/X/I/D bases)"
                      : (h[0] & 8) ? "ZeroDivisionError at GCI.py:292 (query_length 0 in the join)"
-                                  : "ZeroDivisionError at GCI.py:231 (PAF alignment length 0)";
+                     : (h[0] & 16) ? "ZeroDivisionError at GCI.py:231 (PAF alignment length 0)"
+                                   : "ZeroDivisionError at GCI.py:247 (PAF query length 0)";
   return ctx->fail(GCI_E_REFERENCE_RAISES, "%s: the reference raises here: %s [first index %llu]", where, what, h[1]);
 }
 
@@ -540,122 +540,229 @@ static int install_table(gci_ctx* ctx, FileTable& f, int64_t n, const uint32_t* 
   return GCI_OK;
 }
 
-// ---- PAF leg (host stage, GCI.py:211-254) -----------------------------------------------------------
-namespace {
-struct PafKept {
-  uint32_t read;
-  int32_t ref, qlen, q0, q1, t0, t1;
-  double ident;
-  uint64_t ord;
+// ================================================================================================
+// K3  PAF leg on the GPU (GCI.py:211-254)
+// ================================================================================================
+// per line: contig selected, identity = nmatch / alnlen (fp64), keep iff mapq >= -mq and identity >= -ip;
+// kept lines are appended to the read set's cumulative list with their arrival ordinal
+struct PafCols {
+  const uint32_t* read_id;
+  const int32_t *qlen, *qstart, *qend, *ref_id, *tstart, *tend, *nmatch, *alnlen, *mapq;
+};
+struct KeptCols {
+  uint32_t* read;
+  int32_t *ref, *qlen, *q0, *q1, *t0, *t1;
+  double* ident;
+  unsigned long long* ord;
+  unsigned long long* count;
 };
 
-// GCI.py:64-96 on (lo,hi) pairs: total merged length and the longest merged block (first on ties)
-void merge_blocks(std::vector<std::pair<int32_t, int32_t>>& v, int64_t& total, int32_t& best_lo, int32_t& best_hi) {
-  std::sort(v.begin(), v.end());
-  total = 0;
-  int64_t best_len = -1;
-  int32_t lo = v[0].first, hi = v[0].second;
-  auto close_block = [&]() {
-    int64_t len = (int64_t)hi - lo;
-    total += len;
-    if (len > best_len) { best_len = len; best_lo = lo; best_hi = hi; }
-  };
-  for (auto& p : v) {
-    if (hi >= p.first) {
-      if (hi < p.second) hi = p.second;
+__global__ void paf_gate_kernel(int64_t n, PafCols p, unsigned long long ord0, const uint8_t* __restrict__ selected,
+                                int32_t n_contigs, uint32_t n_reads, int32_t map_qual, int32_t mq_cutoff, double ip,
+                                KeptCols k, uint8_t* __restrict__ highq, unsigned long long* __restrict__ err) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t t = p.ref_id[i];
+  if (t < 0 || t >= n_contigs || !selected[t]) return;                 // :220
+  const int32_t al = p.alnlen[i];
+  if (al == 0) {                                                        // ZeroDivisionError :231
+    atomicOr(err, 16ull);
+    atomicMin(err + 1, (unsigned long long)i);
+    return;
+  }
+  const double ident = (double)p.nmatch[i] / (double)al;               // :231
+  const int32_t mq = p.mapq[i];
+  if (!(mq >= map_qual && ident >= ip)) return;                         // :232
+  const uint32_t q = p.read_id[i];
+  if (q >= n_reads) return;
+  const unsigned long long slot = atomicAdd(k.count, 1ull);
+  k.read[slot] = q; k.ref[slot] = t; k.qlen[slot] = p.qlen[i];
+  k.q0[slot] = p.qstart[i]; k.q1[slot] = p.qend[i]; k.t0[slot] = p.tstart[i]; k.t1[slot] = p.tend[i];
+  k.ident[slot] = ident;
+  k.ord[slot] = ord0 + (unsigned long long)i;
+  if (mq >= mq_cutoff) highq[q] = 1;                                    // :238
+}
+
+__global__ void paf_count_kernel(const unsigned long long* __restrict__ count, const uint32_t* __restrict__ read,
+                                 int32_t* __restrict__ cnt) {
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i < *count) atomicAdd(&cnt[read[i]], 1);
+}
+
+__global__ void paf_fill_kernel(const unsigned long long* __restrict__ count, const uint32_t* __restrict__ read,
+                                const int32_t* __restrict__ off, int32_t* __restrict__ cur, int32_t* __restrict__ idx) {
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= *count) return;
+  const uint32_t q = read[i];
+  idx[off[q] + atomicAdd(&cur[q], 1)] = (int32_t)i;
+}
+
+// GCI.py:64-96 over the members `seg[0..g)` that sit on contig `ref`: walk the (lo, hi) pairs in sorted
+// order by repeated selection of the next smallest (lo, hi, position) triple (groups are tiny), merge
+// touching / overlapping blocks, return the total merged length and the longest block (first on ties).
+struct Blocks { long long total; int32_t lo, hi; };
+__device__ Blocks merged_blocks(const int32_t* __restrict__ seg, int g, const int32_t* __restrict__ kref, int32_t ref,
+                                const int32_t* __restrict__ a, const int32_t* __restrict__ b) {
+  Blocks r{0, 0, 0};
+  long long best_len = -1;
+  bool have_cur = false, have_last = false;
+  int32_t cur_lo = 0, cur_hi = 0, last_lo = 0, last_hi = 0;
+  int last_pos = -1;
+  for (;;) {
+    // next pair in (lo, hi, position) order after (last_lo, last_hi, last_pos)
+    int pick = -1;
+    int32_t p_lo = 0, p_hi = 0;
+    for (int j = 0; j < g; j++) {
+      const int32_t e = seg[j];
+      if (kref[e] != ref) continue;
+      const int32_t lo = a[e], hi = b[e];
+      if (have_last) {
+        const bool after = lo > last_lo || (lo == last_lo && (hi > last_hi || (hi == last_hi && j > last_pos)));
+        if (!after) continue;
+      }
+      if (pick < 0 || lo < p_lo || (lo == p_lo && (hi < p_hi))) { pick = j; p_lo = lo; p_hi = hi; }
+    }
+    if (pick < 0) break;
+    have_last = true; last_lo = p_lo; last_hi = p_hi; last_pos = pick;
+    if (!have_cur) { have_cur = true; cur_lo = p_lo; cur_hi = p_hi; continue; }
+    if (cur_hi >= p_lo) {
+      if (cur_hi < p_hi) cur_hi = p_hi;
     } else {
-      close_block();
-      lo = p.first;
-      hi = p.second;
+      const long long len = (long long)cur_hi - cur_lo;
+      r.total += len;
+      if (len > best_len) { best_len = len; r.lo = cur_lo; r.hi = cur_hi; }
+      cur_lo = p_lo; cur_hi = p_hi;
     }
   }
-  close_block();
+  if (have_cur) {
+    const long long len = (long long)cur_hi - cur_lo;
+    r.total += len;
+    if (len > best_len) { r.lo = cur_lo; r.hi = cur_hi; }
+  }
+  return r;
 }
-}  // namespace
+
+// one thread per read: order its kept lines by arrival, score every contig, keep the primary target
+__global__ void paf_elect_kernel(uint32_t n_reads, const int32_t* __restrict__ off, int32_t* __restrict__ idx,
+                                 KeptCols k, const int32_t* __restrict__ name_rank, int32_t* __restrict__ t_ref,
+                                 int32_t* __restrict__ t_start, int32_t* __restrict__ t_end, int32_t* __restrict__ t_qlen,
+                                 long long* __restrict__ win, unsigned long long* __restrict__ err) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const int32_t a0 = off[r], g = off[r + 1] - a0;
+  if (g == 0) { win[r] = -1; return; }
+  int32_t* seg = idx + a0;
+  for (int i = 1; i < g; i++) {            // insertion sort by arrival ordinal (file order, :237)
+    const int32_t e = seg[i];
+    const unsigned long long o = k.ord[e];
+    int j = i - 1;
+    while (j >= 0 && k.ord[seg[j]] > o) { seg[j + 1] = seg[j]; j--; }
+    seg[j + 1] = e;
+  }
+  bool have = false;
+  double best_score = 0;
+  int32_t best_rank = 0, b_ref = 0, b_s = 0, b_e = 0, b_q = 0;
+  for (int i = 0; i < g; i++) {
+    const int32_t ref = k.ref[seg[i]];
+    bool seen = false;
+    for (int j = 0; j < i && !seen; j++) seen = k.ref[seg[j]] == ref;
+    if (seen) continue;
+    double sum = 0;                          // Python sum() starts from int 0; 0 + x is exact
+    int cnt = 0;
+    for (int j = i; j < g; j++)
+      if (k.ref[seg[j]] == ref) { sum = sum + k.ident[seg[j]]; cnt++; }
+    const int32_t qlen = k.qlen[seg[i]];     // alns[0][0], :246
+    if (qlen == 0) {                         // ZeroDivisionError :247
+      atomicOr(err, 32ull);
+      atomicMin(err + 1, (unsigned long long)r);
+      win[r] = -1;
+      return;
+    }
+    const Blocks bq = merged_blocks(seg, g, k.ref, ref, k.q0, k.q1);
+    const Blocks bt = merged_blocks(seg, g, k.ref, ref, k.t0, k.t1);
+    const double rate = (double)bq.total / (double)qlen;               // :247
+    const double score = (sum / (double)cnt) * rate;                   // :248-249
+    const int32_t rank = name_rank[ref];
+    if (!have || score > best_score || (score == best_score && rank > best_rank)) {   // :252
+      have = true;
+      best_score = score; best_rank = rank;
+      b_ref = ref; b_s = bt.lo; b_e = bt.hi; b_q = qlen;
+    }
+  }
+  t_ref[r] = b_ref; t_start[r] = b_s; t_end[r] = b_e; t_qlen[r] = b_q;
+  win[r] = (long long)r;                     // table entries are indexed by read id
+}
 
 int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
-  std::vector<PafKept> kept;   // the reference's `synteny`, alive across PAF files (GCI.py:214)
-  uint64_t ord = 0;
+  PafKept& kp = ctx->paf_kept;
+  bool any = false;
+  for (size_t fi = 0; fi < ctx->n_files; fi++) any |= ctx->files[fi].kind == 2;
+  if (!any) return GCI_OK;
+  if ((int32_t)ctx->name_rank.size() != ctx->n_contigs)
+    return ctx->fail(GCI_E_ARG, "gci_set_name_rank must be called before filtering PAF files");
+  int64_t total_lines = 0;
+  for (size_t i = 0; i < ctx->n_paf; i++) total_lines += ctx->paf[i].n;
+  const size_t cap = (size_t)std::max<int64_t>(1, total_lines);
+  GCI_TRY(ctx->ensure(kp.read, 4 * cap)); GCI_TRY(ctx->ensure(kp.ref, 4 * cap)); GCI_TRY(ctx->ensure(kp.qlen, 4 * cap));
+  GCI_TRY(ctx->ensure(kp.q0, 4 * cap)); GCI_TRY(ctx->ensure(kp.q1, 4 * cap)); GCI_TRY(ctx->ensure(kp.t0, 4 * cap));
+  GCI_TRY(ctx->ensure(kp.t1, 4 * cap)); GCI_TRY(ctx->ensure(kp.ident, 8 * cap)); GCI_TRY(ctx->ensure(kp.ord, 8 * cap));
+  GCI_TRY(ctx->ensure(kp.count, 8));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(kp.count.p, 0, 8, ctx->stream));
+  KeptCols k{kp.read.as<uint32_t>(), kp.ref.as<int32_t>(), kp.qlen.as<int32_t>(), kp.q0.as<int32_t>(),
+             kp.q1.as<int32_t>(), kp.t0.as<int32_t>(), kp.t1.as<int32_t>(), kp.ident.as<double>(),
+             kp.ord.as<unsigned long long>(), kp.count.as<unsigned long long>()};
+  const size_t nr = std::max<uint32_t>(1, ctx->n_reads);
+  DevBuf &cnt = ctx->tmp[6], &off = ctx->tmp[7], &idx = ctx->tmp[8];
+  GCI_TRY(ctx->ensure(cnt, 4 * (nr + 1) * 2));     // counts | fill cursors
+  GCI_TRY(ctx->ensure(off, 4 * (nr + 1)));
+  GCI_TRY(ctx->ensure(idx, 4 * cap));
+  ctx->stage_begin(GCI_ST_PAF);
+  unsigned long long ord0 = 0;
+  int64_t seen = 0;
   for (size_t fi = 0; fi < ctx->n_files; fi++) {
     FileTable& ft = ctx->files[fi];
     if (ft.kind != 2) continue;
-    if ((int32_t)ctx->name_rank.size() != ctx->n_contigs)
-      return ctx->fail(GCI_E_ARG, "gci_set_name_rank must be called before filtering PAF files");
-    const PafFile& p = ctx->paf[ft.src];
-    std::vector<uint32_t> hq_reads;
-    for (int64_t i = 0; i < p.n; i++, ord++) {
-      const int32_t t = p.ref_id[i];
-      if (t < 0 || t >= ctx->n_contigs || !ctx->selected[t]) continue;        // :220
-      if (p.alnlen[i] == 0)
-        return ctx->fail(GCI_E_REFERENCE_RAISES,
-                         "PAF line %lld: the reference raises here: ZeroDivisionError at GCI.py:231", (long long)i);
-      const double ident = (double)p.nmatch[i] / (double)p.alnlen[i];          // :231
-      if (p.mapq[i] >= mq && ident >= ip) {                                     // :232
-        kept.push_back({p.read_id[i], t, p.qlen[i], p.qstart[i], p.qend[i], p.tstart[i], p.tend[i], ident, ord});
-        if (p.mapq[i] >= mq_cutoff) hq_reads.push_back(p.read_id[i]);           // :238
-      }
-    }
-    std::sort(kept.begin(), kept.end(), [](const PafKept& a, const PafKept& b) {
-      if (a.read != b.read) return a.read < b.read;
-      if (a.ref != b.ref) return a.ref < b.ref;
-      return a.ord < b.ord;
-    });
-    std::vector<uint32_t> o_read;
-    std::vector<int32_t> o_ref, o_s, o_e, o_q;
-    std::vector<std::pair<int32_t, int32_t>> qv, tv;
-    size_t i = 0;
-    while (i < kept.size()) {
-      const uint32_t read = kept[i].read;
-      bool have = false;
-      double best_score = 0;
-      int32_t best_rank = 0, b_ref = 0, b_s = 0, b_e = 0, b_q = 0;
-      while (i < kept.size() && kept[i].read == read) {
-        const int32_t ref = kept[i].ref;
-        size_t j = i;
-        double sum = 0;   // Python sum() starts from int 0; 0 + x is exact
-        qv.clear();
-        tv.clear();
-        for (; j < kept.size() && kept[j].read == read && kept[j].ref == ref; j++) {
-          sum = sum + kept[j].ident;
-          qv.emplace_back(kept[j].q0, kept[j].q1);
-          tv.emplace_back(kept[j].t0, kept[j].t1);
-        }
-        const int32_t qlen = kept[i].qlen;                                      // alns[0][0], :246
-        if (qlen == 0)
-          return ctx->fail(GCI_E_REFERENCE_RAISES, "the reference raises here: ZeroDivisionError at GCI.py:247");
-        int64_t mapped, dummy;
-        int32_t lo, hi, tlo, thi;
-        merge_blocks(qv, mapped, lo, hi);
-        merge_blocks(tv, dummy, tlo, thi);
-        const double rate = (double)mapped / (double)qlen;                     // :247
-        const double score = (sum / (double)(j - i)) * rate;                   // :248-249
-        const int32_t rank = ctx->name_rank[ref];
-        if (!have || score > best_score || (score == best_score && rank > best_rank)) {   // :252
-          have = true;
-          best_score = score; best_rank = rank;
-          b_ref = ref; b_s = tlo; b_e = thi; b_q = qlen;
-        }
-        i = j;
-      }
-      o_read.push_back(read); o_ref.push_back(b_ref); o_s.push_back(b_s); o_e.push_back(b_e); o_q.push_back(b_q);
-    }
-    // high-quality marks ride along as a second tiny table
-    GCI_TRY(install_table(ctx, ft, (int64_t)o_read.size(), o_read.data(), o_ref.data(), o_s.data(), o_e.data(),
-                          o_q.data(), nullptr));
-    if (!hq_reads.empty()) {
-      std::vector<uint8_t> one(hq_reads.size(), 1);
-      DevBuf d_r, d_h, d_w;
-      GCI_TRY(gci_h2d(ctx, d_r, hq_reads.data(), 4 * hq_reads.size()));
-      GCI_TRY(gci_h2d(ctx, d_h, one.data(), one.size()));
-      GCI_TRY(ctx->ensure(d_w, sizeof(long long) * (size_t)std::max<uint32_t>(1, ctx->n_reads)));
-      table_win_kernel<<<(unsigned)((hq_reads.size() + 255) / 256), 256, 0, ctx->stream>>>(
-          (int64_t)hq_reads.size(), d_r.as<uint32_t>(), ctx->n_reads, d_h.as<uint8_t>(), d_w.as<long long>(),
-          ctx->highq.as<uint8_t>());
+    const PafFile& pf = ctx->paf[ft.src];
+    PafCols pc{pf.read_id.as<uint32_t>(), pf.qlen.as<int32_t>(), pf.qstart.as<int32_t>(), pf.qend.as<int32_t>(),
+               pf.ref_id.as<int32_t>(), pf.tstart.as<int32_t>(), pf.tend.as<int32_t>(), pf.nmatch.as<int32_t>(),
+               pf.alnlen.as<int32_t>(), pf.mapq.as<int32_t>()};
+    if (pf.n) {
+      paf_gate_kernel<<<(unsigned)((pf.n + 255) / 256), 256, 0, ctx->stream>>>(
+          pf.n, pc, ord0, ctx->d_selected.as<uint8_t>(), ctx->n_contigs, ctx->n_reads, mq, mq_cutoff, ip, k,
+          ctx->highq.as<uint8_t>(), ctx->d_err.as<unsigned long long>());
       GCI_LAUNCH_CHECK(ctx);
-      GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-      ctx->release(d_r); ctx->release(d_h); ctx->release(d_w);
+    }
+    ord0 += (unsigned long long)pf.n;
+    seen += pf.n;
+    // group the kept lines (of this and all earlier PAF files) by read: CSR over read ids
+    GCI_CUDA_TRY(ctx, cudaMemsetAsync(cnt.p, 0, 4 * (nr + 1) * 2, ctx->stream));
+    int32_t* d_cnt = cnt.as<int32_t>();
+    int32_t* d_cur = d_cnt + (nr + 1);
+    if (seen) {
+      const unsigned grid = (unsigned)((seen + 255) / 256);
+      paf_count_kernel<<<grid, 256, 0, ctx->stream>>>(k.count, k.read, d_cnt);
+      GCI_LAUNCH_CHECK(ctx);
+      GCI_TRY(gci_exclusive_scan_i32(ctx, d_cnt, off.as<int32_t>(), (int64_t)ctx->n_reads + 1));
+      paf_fill_kernel<<<grid, 256, 0, ctx->stream>>>(k.count, k.read, off.as<int32_t>(), d_cur, idx.as<int32_t>());
+      GCI_LAUNCH_CHECK(ctx);
+    } else {
+      GCI_CUDA_TRY(ctx, cudaMemsetAsync(off.p, 0, 4 * (nr + 1), ctx->stream));
+    }
+    // the file's table: one entry per read id
+    ft.kind = 1;
+    ft.n = ctx->n_reads;
+    GCI_TRY(ctx->ensure(ft.ref_id, 4 * nr)); GCI_TRY(ctx->ensure(ft.start, 4 * nr));
+    GCI_TRY(ctx->ensure(ft.end, 4 * nr)); GCI_TRY(ctx->ensure(ft.qlen, 4 * nr));
+    GCI_TRY(ctx->ensure(ft.win, 8 * nr));
+    if (ctx->n_reads) {
+      paf_elect_kernel<<<(ctx->n_reads + 127) / 128, 128, 0, ctx->stream>>>(
+          ctx->n_reads, off.as<int32_t>(), idx.as<int32_t>(), k, ctx->d_name_rank.as<int32_t>(),
+          ft.ref_id.as<int32_t>(), ft.start.as<int32_t>(), ft.end.as<int32_t>(), ft.qlen.as<int32_t>(),
+          ft.win.as<long long>(), ctx->d_err.as<unsigned long long>());
+      GCI_LAUNCH_CHECK(ctx);
     }
   }
+  ctx->stage_end();
   return GCI_OK;
 }
 
@@ -747,9 +854,7 @@ int gci_filter(gci_ctx* ctx, int32_t map_qual, int32_t mq_cutoff, double iden_pe
   cudaSetDevice(ctx->device);
   if (ctx->n_files == 0) return ctx->fail(GCI_E_ARG, "gci_filter: no files uploaded");
   GCI_TRY(reset_err(ctx));
-  // PAF election first (host stage); tables uploaded by the caller are already final
-  ctx->stage_begin(GCI_ST_PAF);
-  ctx->stage_end();
+  // PAF election first (files join in upload order); tables uploaded by the caller are already final
   GCI_TRY(gci_run_paf_legs(ctx, map_qual, mq_cutoff, iden_percent));
   for (size_t i = 0; i < ctx->n_files; i++)
     if (ctx->files[i].kind == 0)

@@ -338,3 +338,44 @@ def test_contig_sharded_two_ranks_equal_single_gpu(seed):
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_paf_election_known_cases(ctx):
+    """PAF leg on the GPU: multi-block merge (touching blocks merge), longest target block with ties, equal scores
+    decided by the contig NAME (not its index), query length of the first line, duplicates, two PAF files."""
+    names = ["zeta", "alpha", "mid"]          # name order differs from index order
+    lengths = [50_000, 50_000, 50_000]
+
+    def line(read, ref, q0, q1, t0, t1, nmatch=None, alnlen=None, mapq=60, qlen=10_000):
+        n = q1 - q0
+        return dict(read_id=read, qlen=qlen, qstart=q0, qend=q1, ref_id=ref, tstart=t0, tend=t1,
+                    nmatch=n if nmatch is None else nmatch, alnlen=n if alnlen is None else alnlen, mapq=mapq)
+
+    p1 = PafTable.from_rows([
+        # read 0: identical evidence on zeta (0) and alpha (1) -> equal scores -> 'zeta' > 'alpha' wins
+        line(0, 0, 0, 5000, 1000, 6000), line(0, 1, 0, 5000, 2000, 7000),
+        # read 1: three blocks on mid: [0,3000) and [3000,5000) touch -> merge; [7000,9000) separate;
+        #         target blocks [100,3100),[3100,5100) merge to length 5000, [20000,22000) shorter
+        line(1, 2, 0, 3000, 100, 3100), line(1, 2, 3000, 5000, 3100, 5100), line(1, 2, 7000, 9000, 20000, 22000),
+        # read 2: two equally long target blocks -> the first in sorted order wins; duplicate line
+        line(2, 1, 0, 2000, 30000, 32000), line(2, 1, 4000, 6000, 10000, 12000), line(2, 1, 4000, 6000, 10000, 12000),
+        # read 3: low identity line dropped, low mapq line dropped, remaining one kept; qlen differs per line
+        line(3, 0, 0, 4000, 500, 4500, nmatch=3000), line(3, 0, 0, 4000, 600, 4600, mapq=10),
+        line(3, 2, 100, 4100, 700, 4700, qlen=8000),
+        # read 4: only in the first PAF (leaks into the second one's table)
+        line(4, 1, 0, 9000, 40000, 49000, mapq=40),
+        # read 5: unknown contig
+        line(5, -1, 0, 9000, 0, 9000),
+    ])
+    p2 = PafTable.from_rows([line(0, 1, 5000, 9000, 7000, 11000), line(1, 2, 0, 9000, 100, 9100, mapq=35),
+                             line(6, 0, 0, 9000, 100, 9100, mapq=35)])
+    rows = []
+    for rid, (ref, st, ln) in enumerate([(0, 1000, 5000), (2, 100, 5000), (1, 10000, 2000), (2, 700, 4000),
+                                         (1, 40000, 9000), (0, 0, 9000), (0, 100, 9000)]):
+        rows.append(dict(ref_id=ref, ref_start=st, cigar=f"{ln}M", read_id=rid, mapq=45, qlen=ln))
+    bam = _bam(rows)
+    for pafs in ([p1], [p1, p2], [p2, p1]):
+        _check(ctx, names, lengths, pafs, [bam], 8, params=dict(ovlp_percent=0.3))
+    with pytest.raises(Exception):
+        bad = PafTable.from_rows([line(0, 0, 0, 100, 0, 100, alnlen=0, nmatch=0)])
+        _run_gpu(ctx, names, lengths, [bad], [bam], 8)
