@@ -11,8 +11,8 @@ HiFi, one BAM, seeded generator gci_b200.synth (seed 20240634 + rank).  At N > 1
 such contig (contig sharding, weak scaling) and the ranks exchange only the genome-row terms.
 
 A step = one pass of the hot path over the batch:
-    gci_filter (CIGAR stats, gates, dedup, join) -> gci_depth (buckets, depth tiles + fused flags)
-    -> gci_scan (issue intervals) -> gci_score_terms (+ the genome-row all-reduce at N > 1)
+    gci_pipeline = gci_filter (CIGAR stats, gates, dedup, join) -> gci_depth (buckets, depth tiles + fused
+    flags) -> gci_scan (issue intervals) -> gci_score_terms_sums   (+ gci_genome_row at N > 1)
 `value`  : records already resident in HBM, CUDA events per step, L2 flushed between steps.
 `e2e`    : the same through the C ABI with HOST (pinned) buffers: H2D of the record columns, the
            step, D2H of the depth array, the intervals and the score terms inside the timed region.
@@ -196,15 +196,14 @@ def main():
     result = {}
 
     def core_step():
-        n_surv = ctx.filter(**PARAMS)
-        ctx.depth(0, FLANK, -1, THRESHOLD)
-        n_iv = ctx.scan(0, -1, THRESHOLD, FLANK)
+        # the whole path in one library call (one host synchronisation): gci_pipeline = gci_filter + gci_depth +
+        # gci_scan + gci_score_terms_sums
+        n_surv, n_iv, n50, nctg, sums = ctx.pipeline(0, 1, flank_len=FLANK, lo=-1, hi=THRESHOLD, dist_percent=DIST,
+                                                     **PARAMS)
         if world > 1:
-            # score terms of this rank's contig + the genome row: one ncclAllGather on the library's stream
+            # genome row: one ncclAllGather on the library's stream
             n50, nctg, sums, mean, all_ctg, all_len = ctx.genome_row(0, 1, sum(L), DIST, FLANK)
             result["mean_depth"] = mean
-        else:
-            n50, nctg, lens, _ = ctx.score_terms(0, 1, n_iv, DIST, FLANK)
         result.update(n_surv=n_surv, n_iv=n_iv, n50=int(n50[0]), nctg=int(nctg[0]))
         return n_iv
 

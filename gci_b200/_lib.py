@@ -74,6 +74,8 @@ _SIGNATURES = {
     "gci_fetch_intervals": (C.c_int, [_p, _i32, _i64, _p, _p, _p, C.POINTER(_i64)]),
     "gci_load_intervals": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _p]),
     "gci_score_terms": (C.c_int, [_p, _i32, _f64, _i32, _p, _p, _i64, _p, _p]),
+    "gci_pipeline": (C.c_int, [_p, _i32, _i32, _i32, _f64, _f64, _f64, _i32, _i32, _i32, _f64, C.POINTER(_i64),
+                               C.POINTER(_i64), _p, _p, _p]),
     "gci_comm_unique_id": (C.c_int, [_p]),
     "gci_comm_init": (C.c_int, [_p, _p, _i32, _i32]),
     "gci_genome_row": (C.c_int, [_p, _i32, _f64, _i32, _i64, _i64, _p, _p, _p, _p]),
@@ -366,6 +368,18 @@ class Context:
         off = np.zeros(n_owners + 1, np.int64)
         self._check(self._lib.gci_fetch_intervals(self._h, track, k, _ptr(s), _ptr(e), _ptr(off), C.byref(n)))
         return s, e, off
+
+    def pipeline(self, track, n_owners, map_qual=30, mq_cutoff=50, iden_percent=0.9, clip_percent=0.1,
+                 ovlp_percent=0.9, flank_len=15, lo=-1, hi=0, dist_percent=0.005):
+        """filter -> depth -> scan -> score terms in one call, one host synchronisation.
+        -> (n_survivors, n_intervals, n50[owners+1], n_ctg[owners+1], depth_sums[owners+1])"""
+        ns, ni = _i64(), _i64()
+        n50, nctg, sums = (np.zeros(n_owners + 1, np.int64) for _ in range(3))
+        self._check(self._lib.gci_pipeline(self._h, track, int(map_qual), int(mq_cutoff), float(iden_percent),
+                                           float(clip_percent), float(ovlp_percent), int(flank_len), int(lo), int(hi),
+                                           float(dist_percent), C.byref(ns), C.byref(ni), _ptr(n50), _ptr(nctg),
+                                           _ptr(sums)))
+        return ns.value, ni.value, n50, nctg, sums
 
     # ---- multi-GPU ----
     @staticmethod

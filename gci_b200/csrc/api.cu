@@ -187,6 +187,7 @@ void gci_destroy(gci_ctx* ctx) {
   for (auto& d : ctx->tmp) ctx->release(d);
   for (cudaEvent_t e : ctx->timer.pool) cudaEventDestroy(e);
   if (ctx->pinned_scratch) cudaFreeHost(ctx->pinned_scratch);
+  if (ctx->pipe_pin) cudaFreeHost(ctx->pipe_pin);
   if (ctx->h2d_done) cudaEventDestroy(ctx->h2d_done);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -278,6 +279,8 @@ int gci_set_contigs(gci_ctx* ctx, int32_t n, const int64_t* lengths, const uint8
   ctx->n_nruns = 0;
   ctx->name_rank.clear();
   ctx->owner_of_stale = true;
+  ctx->lay_cache.clear();
+  ctx->ob_cache.clear();
   return GCI_OK;
 }
 
@@ -374,6 +377,7 @@ int gci_upload_bam(gci_ctx* ctx, int64_t n, const int32_t* ref_id, const int32_t
   FileTable& f = ctx->files[ctx->n_files++];
   f.kind = 0;
   f.src = (int)ctx->n_bam - 1;
+  f.paf = -1;
   f.n = n;
   ctx->filtered = false;
   // the caller may reuse its host buffers as soon as we return
@@ -407,8 +411,9 @@ int gci_upload_paf(gci_ctx* ctx, int64_t n, const uint32_t* read_id, const int32
   ctx->stage_end();
   if (ctx->n_files == ctx->files.size()) ctx->files.emplace_back();
   FileTable& f = ctx->files[ctx->n_files++];
-  f.kind = 2;   // PAF lines awaiting the election in gci_filter
-  f.src = (int)ctx->n_paf - 1;
+  f.kind = 1;   // a table, rebuilt from the PAF lines by every gci_filter (the gates are filter arguments)
+  f.src = -1;
+  f.paf = (int)ctx->n_paf - 1;
   f.n = 0;
   ctx->filtered = false;
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -107,7 +107,7 @@ int gci_genome_row(gci_ctx* ctx, int32_t track, double dist_percent, int32_t fla
     return ctx->fail(GCI_E_ARG, "gci_genome_row needs a whole-contig scan of a track with valid depth sums");
   int64_t no = 0, n_slots = 0;
   ctx->stage_begin(GCI_ST_SCORE);
-  GCI_TRY(gci_launch_score_kernels(ctx, t, dist_percent, flank_len, &no, &n_slots));
+  GCI_TRY(gci_launch_score_kernels(ctx, t, dist_percent, flank_len, &no, &n_slots, false));
   const int64_t row_n = 4 + cap;
   const int world = ctx->comm_world;
   DevBuf &d_res = ctx->tmp[1], &d_row = ctx->tmp[2], &d_all = ctx->tmp[5];

@@ -73,6 +73,7 @@ struct PafKept {
 struct FileTable {
   int kind = 0;            // 0 = BAM (entries are records of bam[src]), 1 = table (own columns)
   int src = -1;
+  int paf = -1;            // >= 0: the table is (re)built from PAF file paf[...] by every gci_filter
   int64_t n = 0;
   DevBuf ref_id, start, end, qlen;   // for kind==1; for BAM these alias the BamFile columns
   DevBuf win;              // int64[n_reads]: winning entry key per read (-1 = absent)
@@ -164,6 +165,11 @@ struct gci_ctx {
   void* nccl_comm = nullptr;
   int comm_rank = 0, comm_world = 1;
 
+  std::vector<int64_t> lay_cache;   // last run-chunk layout uploaded to chunk_off
+  std::vector<char> ob_cache;       // last OwnerBounds uploaded to tmp[0]
+  void* pipe_pin = nullptr;         // persistent pinned block of gci_pipeline
+  size_t pipe_pin_cap = 0;
+
   StageTimer timer;
   void* pinned_scratch = nullptr;
   size_t pinned_cap = 0;
@@ -192,7 +198,9 @@ int gci_run_join(gci_ctx* ctx, double op);
 int gci_alloc_track(gci_ctx* ctx, int track);
 int gci_compute_flags(gci_ctx* ctx, int track, int32_t lo, int32_t hi);
 int gci_launch_score_kernels(gci_ctx* ctx, Track& t, double dist_percent, int32_t flank_len, int64_t* n_owners,
-                             int64_t* n_slots);   // scan.cu: result stays in ctx->tmp[1], no sync
+                             int64_t* n_slots, bool pending);   // scan.cu: result stays in ctx->tmp[1], no sync
+int gci_scan_enqueue(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int32_t flank_len, int64_t* pin);
+int gci_scan_finish(gci_ctx* ctx, int32_t track, const int64_t* pin, bool* overflow);
 extern "C" void gci_comm_destroy_internal(gci_ctx* ctx);
 
 #define GCI_LAUNCH_CHECK(ctx)                      \

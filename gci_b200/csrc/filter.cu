@@ -518,6 +518,7 @@ int gci_run_bam_leg(gci_ctx* ctx, int file_idx, int bam_idx, int32_t mq, int32_t
 static int install_table(gci_ctx* ctx, FileTable& f, int64_t n, const uint32_t* read_id, const int32_t* ref_id,
                          const int32_t* start, const int32_t* end, const int32_t* qlen, const uint8_t* highq) {
   f.kind = 1;
+  f.paf = -1;
   f.n = n;
   DevBuf &d_read = ctx->tmp[4], &d_hq = ctx->tmp[5];
   ctx->stage_begin(GCI_ST_H2D);
@@ -696,7 +697,7 @@ __global__ void paf_elect_kernel(uint32_t n_reads, const int32_t* __restrict__ o
 int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
   PafKept& kp = ctx->paf_kept;
   bool any = false;
-  for (size_t fi = 0; fi < ctx->n_files; fi++) any |= ctx->files[fi].kind == 2;
+  for (size_t fi = 0; fi < ctx->n_files; fi++) any |= ctx->files[fi].paf >= 0;
   if (!any) return GCI_OK;
   if ((int32_t)ctx->name_rank.size() != ctx->n_contigs)
     return ctx->fail(GCI_E_ARG, "gci_set_name_rank must be called before filtering PAF files");
@@ -721,8 +722,8 @@ int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
   int64_t seen = 0;
   for (size_t fi = 0; fi < ctx->n_files; fi++) {
     FileTable& ft = ctx->files[fi];
-    if (ft.kind != 2) continue;
-    const PafFile& pf = ctx->paf[ft.src];
+    if (ft.paf < 0) continue;
+    const PafFile& pf = ctx->paf[ft.paf];
     PafCols pc{pf.read_id.as<uint32_t>(), pf.qlen.as<int32_t>(), pf.qstart.as<int32_t>(), pf.qend.as<int32_t>(),
                pf.ref_id.as<int32_t>(), pf.tstart.as<int32_t>(), pf.tend.as<int32_t>(), pf.nmatch.as<int32_t>(),
                pf.alnlen.as<int32_t>(), pf.mapq.as<int32_t>()};
@@ -957,6 +958,81 @@ int gci_fetch_file_table(gci_ctx* ctx, int32_t file, int64_t cap, uint32_t* read
   ctx->release(mark);
   ctx->release(pos);
   return rc;
+}
+
+
+// filter -> depth -> scan -> score terms with ONE host synchronisation: nothing between the stages needs the
+// host (the interval buffers keep their capacity from earlier scans; if a run produces more intervals than
+// fit, the scan + score part is redone through the synchronous entry points).
+int gci_pipeline(gci_ctx* ctx, int32_t track, int32_t map_qual, int32_t mq_cutoff, double iden_percent,
+                 double clip_percent, double ovlp_percent, int32_t flank_len, int32_t lo, int32_t hi,
+                 double dist_percent, int64_t* n_survivors, int64_t* n_intervals, int64_t* n50, int64_t* n_ctg,
+                 int64_t* depth_sums) {
+  if (!ctx || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->n_files == 0) return ctx->fail(GCI_E_ARG, "gci_pipeline: no files uploaded");
+  int64_t n_sel = 0;
+  for (int c = 0; c < ctx->n_contigs; c++) n_sel += ctx->selected[c] ? 1 : 0;
+  if (n_sel == 0) return ctx->fail(GCI_E_ARG, "gci_pipeline: no contigs");
+  GCI_TRY(reset_err(ctx));
+  GCI_TRY(gci_run_paf_legs(ctx, map_qual, mq_cutoff, iden_percent));
+  for (size_t i = 0; i < ctx->n_files; i++)
+    if (ctx->files[i].kind == 0)
+      GCI_TRY(gci_run_bam_leg(ctx, (int)i, ctx->files[i].src, map_qual, mq_cutoff, iden_percent, clip_percent));
+  GCI_TRY(gci_run_join(ctx, ovlp_percent));
+  ctx->filtered = true;
+  GCI_TRY(gci_depth(ctx, track, flank_len, lo, hi));
+  Track& t = ctx->track[track];
+  // persistent pinned block: [err 4 x u64 | owner_off n_sel+3 | score result]
+  const int64_t res_bound = 3 * n_sel + 1 + std::max<int64_t>(t.iv_cap, 4096) + n_sel;
+  const size_t need = 8 * (size_t)(4 + (n_sel + 3) + res_bound);
+  if (ctx->pipe_pin_cap < need) {
+    if (ctx->pipe_pin) cudaFreeHost(ctx->pipe_pin);
+    ctx->pipe_pin = nullptr;
+    ctx->pipe_pin_cap = 0;
+    if (cudaHostAlloc(&ctx->pipe_pin, need, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      return ctx->fail(GCI_E_NOMEM, "pinned allocation failed");
+    }
+    ctx->pipe_pin_cap = need;
+  }
+  unsigned long long* h_err = (unsigned long long*)ctx->pipe_pin;
+  int64_t* h_off = (int64_t*)(h_err + 4);
+  int64_t* h_res = h_off + (n_sel + 3);
+  GCI_TRY(gci_scan_enqueue(ctx, track, lo, hi, flank_len, h_off));
+  int64_t no = 0, n_slots = 0;
+  ctx->stage_begin(GCI_ST_SCORE);
+  GCI_TRY(gci_launch_score_kernels(ctx, t, dist_percent, flank_len, &no, &n_slots, true));
+  GCI_TRY(gci_d2h(ctx, h_res, ctx->tmp[1].p, 8 * (size_t)(3 * no + 1 + n_slots)));
+  GCI_TRY(gci_d2h(ctx, h_err, ctx->d_err.p, 4 * sizeof(unsigned long long)));
+  ctx->stage_end();
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h_err[0] != 0) {
+    ctx->filtered = false;
+    unsigned long long dummy;
+    return check_err(ctx, "gci_pipeline", &dummy);
+  }
+  ctx->n_survivors = (int64_t)h_err[2];
+  if (n_survivors) *n_survivors = ctx->n_survivors;
+  bool overflow = false;
+  GCI_TRY(gci_scan_finish(ctx, track, h_off, &overflow));
+  if (overflow) {
+    // rare: redo the scan with grown buffers and the score terms through the synchronous entry points
+    GCI_TRY(gci_scan(ctx, track, lo, hi, flank_len, n_intervals));
+    return gci_score_terms_sums(ctx, track, dist_percent, flank_len, n50, n_ctg, 0, nullptr, nullptr, depth_sums);
+  }
+  if (n_intervals) *n_intervals = t.n_intervals;
+  long long all_c = 0, all_d = 0;
+  for (int64_t o = 0; o < no; o++) {
+    if (n_ctg) n_ctg[o] = h_res[no + 1 + o];
+    if (depth_sums) depth_sums[o] = h_res[2 * no + 1 + o];
+    all_c += h_res[no + 1 + o];
+    all_d += h_res[2 * no + 1 + o];
+  }
+  if (n50) memcpy(n50, h_res, 8 * (size_t)(no + 1));
+  if (n_ctg) n_ctg[no] = all_c;
+  if (depth_sums) depth_sums[no] = all_d;
+  return GCI_OK;
 }
 
 }  // extern "C"

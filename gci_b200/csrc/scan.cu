@@ -412,8 +412,10 @@ runs_scan_kernel(const int2* __restrict__ cnt, int64_t n_chunks, longlong2* __re
 
 // shared tail of gci_scan / gci_scan_windows.  The chunk layout comes from host-known bounds
 // (lay_lo[o] <= real window start, hi[o] = real window end); the real windows are on the device.
+// defer_pin != NULL: enqueue only — the interval offsets / totals are copied to defer_pin[n_owners + 3] and the
+// caller synchronises later and calls finish_runs()
 static int extract_runs(gci_ctx* ctx, Track& t, const std::vector<int64_t>& lay_lo, const std::vector<int64_t>& h_hi,
-                        int64_t* n_intervals) {
+                        int64_t* n_intervals, int64_t* defer_pin = nullptr) {
   const int64_t n_owners = t.n_owners;
   std::vector<int64_t> lay(2 * (n_owners + 1), 0);     // [chunk_off (n+1) | w0 (n) ...]
   int64_t* chunk_off = lay.data();
@@ -430,10 +432,14 @@ static int extract_runs(gci_ctx* ctx, Track& t, const std::vector<int64_t>& lay_
   GCI_TRY(ctx->ensure(t.owner_off, sizeof(int64_t) * (size_t)(n_owners + 3)));
   if (n_chunks == 0) {
     GCI_CUDA_TRY(ctx, cudaMemsetAsync(t.owner_off.p, 0, sizeof(int64_t) * (n_owners + 3), ctx->stream));
+    if (defer_pin) memset(defer_pin, 0, sizeof(int64_t) * (size_t)(n_owners + 3));
     return GCI_OK;
   }
   if (n_chunks >= (int64_t(1) << 31)) return ctx->fail(GCI_E_ARG, "too many run chunks");
-  GCI_TRY(gci_h2d(ctx, ctx->chunk_off, lay.data(), sizeof(int64_t) * lay.size()));
+  if (lay != ctx->lay_cache) {   // the chunk layout only changes with the contig table / flank / regions
+    GCI_TRY(gci_h2d(ctx, ctx->chunk_off, lay.data(), sizeof(int64_t) * lay.size()));
+    ctx->lay_cache = lay;
+  }
   const int64_t* d_chunk_off = ctx->chunk_off.as<int64_t>();
   const int64_t* d_w0 = d_chunk_off + n_owners + 1;
   GCI_TRY(ctx->ensure(ctx->chunk_cnt, sizeof(int2) * (size_t)n_chunks));
@@ -451,6 +457,15 @@ static int extract_runs(gci_ctx* ctx, Track& t, const std::vector<int64_t>& lay_
   GCI_LAUNCH_CHECK(ctx);
   runs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, n_chunks, off, n_owners, d_chunk_off, t.owner_off.as<int64_t>());
   GCI_LAUNCH_CHECK(ctx);
+  if (defer_pin) {
+    runs_kernel<true><<<(unsigned)n_chunks, RUN_THREADS, 0, ctx->stream>>>(
+        t.flags.as<uint32_t>(), n_owners, d_chunk_off, t.win_contig.as<int32_t>(), t.win_lo.as<int64_t>(),
+        t.win_hi.as<int64_t>(), d_w0, ctx->d_tile_off.as<int64_t>(), nullptr, off, t.iv_start.as<int32_t>(),
+        t.iv_end.as<int32_t>(), t.iv_cap);
+    GCI_LAUNCH_CHECK(ctx);
+    GCI_TRY(gci_d2h(ctx, defer_pin, t.owner_off.p, sizeof(int64_t) * (size_t)(n_owners + 3)));
+    return GCI_OK;
+  }
   int64_t* h = (int64_t*)ctx->pinned(sizeof(int64_t) * (size_t)(n_owners + 3));
   if (!h) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
   for (int attempt = 0; attempt < 2; attempt++) {
@@ -495,9 +510,10 @@ struct OwnerBounds { long long S, E; double dist; };
 __global__ void __launch_bounds__(256)
 complement_kernel(int64_t n_owners, const int64_t* __restrict__ owner_off, const int32_t* __restrict__ iv_start,
                   const int32_t* __restrict__ iv_end, const OwnerBounds* __restrict__ ob, int64_t* __restrict__ res,
-                  const long long* __restrict__ sums, const int32_t* __restrict__ owner_contig) {
+                  const long long* __restrict__ sums, const int32_t* __restrict__ owner_contig, int64_t iv_cap) {
   __shared__ long long s_red[8];
   const int64_t o = blockIdx.x;
+  if (owner_off[n_owners] > iv_cap) return;   // more intervals than were stored: the host redoes the scan
   const int64_t a = owner_off[o], b = owner_off[o + 1];
   int64_t* g = res + (3 * n_owners + 1) + a + o;
   const int64_t n = b - a;
@@ -538,8 +554,10 @@ complement_kernel(int64_t n_owners, const int64_t* __restrict__ owner_off, const
 // N50 of the positive entries of one owner's gap slots (block o < n_owners) or of all slots (block n_owners)
 constexpr int N50_SMALL = 1024;
 __global__ void __launch_bounds__(256)
-n50_kernel(int64_t n_owners, const int64_t* __restrict__ owner_off, int64_t n_slots, int64_t* __restrict__ res) {
+n50_kernel(int64_t n_owners, const int64_t* __restrict__ owner_off, int64_t iv_cap, int64_t* __restrict__ res) {
   __shared__ long long s_red[8];
+  if (owner_off[n_owners] > iv_cap) return;
+  const int64_t n_slots = owner_off[n_owners] + n_owners;
   __shared__ long long s_bcast;
   __shared__ long long s_val[N50_SMALL];
   const int64_t o = blockIdx.x;
@@ -612,16 +630,17 @@ n50_kernel(int64_t n_owners, const int64_t* __restrict__ owner_off, int64_t n_sl
   if (threadIdx.x == 0) res[o] = best;
 }
 
-// score kernels of one track's last scan; the result buffer stays on the device in ctx->tmp[1]
+// score kernels of one track's last scan; the result buffer stays on the device in ctx->tmp[1].
+// pending: the scan's interval count has not reached the host yet -> sizes are bounded by the capacity.
 int gci_launch_score_kernels(gci_ctx* ctx, Track& t, double dist_percent, int32_t flank_len, int64_t* n_owners,
-                             int64_t* n_slots_out) {
+                             int64_t* n_slots_out, bool pending) {
   const int64_t no = t.n_owners;
-  if (no <= 0 || (int64_t)t.h_owner_off.size() != no + 1) return ctx->fail(GCI_E_ARG, "score terms: no scan on this track");
-  const int64_t n_slots = t.n_intervals + no;
+  if (no <= 0 || (!pending && (int64_t)t.h_owner_off.size() != no + 1))
+    return ctx->fail(GCI_E_ARG, "score terms: no scan on this track");
+  const int64_t n_slots = (pending ? t.iv_cap : t.n_intervals) + no;
   const int64_t n_res = 3 * no + 1 + n_slots;
-  // per-owner [S, E) and dist (GCI.py:505-508, :629-634), staged through pinned memory
-  OwnerBounds* ob = (OwnerBounds*)ctx->pinned(sizeof(OwnerBounds) * (size_t)no);
-  if (!ob) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
+  // per-owner [S, E) and dist (GCI.py:505-508, :629-634); uploaded only when they change
+  std::vector<OwnerBounds> ob((size_t)no);
   for (int64_t o = 0; o < no; o++) {
     if (t.owners_are_windows) {
       // complement / merge use the region bounds as given (GCI.py:629-634), only the depth slice is
@@ -637,26 +656,63 @@ int gci_launch_score_kernels(gci_ctx* ctx, Track& t, double dist_percent, int32_
     }
   }
   DevBuf &d_ob = ctx->tmp[0], &d_res = ctx->tmp[1];
-  GCI_TRY(gci_h2d(ctx, d_ob, ob, sizeof(OwnerBounds) * (size_t)no));
-  // the pinned staging buffer is reused by the caller: the copy above must have left the host first
-  GCI_CUDA_TRY(ctx, cudaEventRecord(ctx->h2d_done, ctx->stream));
+  const size_t ob_bytes = sizeof(OwnerBounds) * (size_t)no;
+  if (ctx->ob_cache.size() != ob_bytes || memcmp(ctx->ob_cache.data(), ob.data(), ob_bytes) != 0) {
+    GCI_TRY(gci_h2d(ctx, d_ob, ob.data(), ob_bytes));
+    GCI_CUDA_TRY(ctx, cudaEventRecord(ctx->h2d_done, ctx->stream));
+    GCI_CUDA_TRY(ctx, cudaEventSynchronize(ctx->h2d_done));   // `ob` is a local: the copy must have left the host
+    ctx->ob_cache.assign((const char*)ob.data(), (const char*)ob.data() + ob_bytes);
+  }
   GCI_TRY(ctx->ensure(d_res, sizeof(int64_t) * (size_t)n_res));
   complement_kernel<<<(unsigned)no, 256, 0, ctx->stream>>>(
       no, t.owner_off.as<int64_t>(), t.iv_start.as<int32_t>(), t.iv_end.as<int32_t>(), d_ob.as<OwnerBounds>(),
       d_res.as<int64_t>(), (!t.owners_are_windows && t.sums_valid) ? t.sums.as<long long>() : nullptr,
-      t.win_contig.as<int32_t>());
+      t.win_contig.as<int32_t>(), t.iv_cap);
   GCI_LAUNCH_CHECK(ctx);
-  n50_kernel<<<(unsigned)(no + 1), 256, 0, ctx->stream>>>(no, t.owner_off.as<int64_t>(), n_slots, d_res.as<int64_t>());
+  n50_kernel<<<(unsigned)(no + 1), 256, 0, ctx->stream>>>(no, t.owner_off.as<int64_t>(), t.iv_cap, d_res.as<int64_t>());
   GCI_LAUNCH_CHECK(ctx);
-  GCI_CUDA_TRY(ctx, cudaEventSynchronize(ctx->h2d_done));
   *n_owners = no;
   *n_slots_out = n_slots;
   return GCI_OK;
 }
 
+// whole-genome scan, enqueue only (gci_pipeline): windows kernel + run extraction, results into `pin`
+int gci_scan_enqueue(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int32_t flank_len, int64_t* pin);
+int gci_scan_finish(gci_ctx* ctx, int32_t track, const int64_t* pin, bool* overflow);
+
 extern "C" {
 
+static int scan_genome(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int32_t flank_len, int64_t* n_intervals,
+                       int64_t* defer_pin);
+
 int gci_scan(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int32_t flank_len, int64_t* n_intervals) {
+  return scan_genome(ctx, track, lo, hi, flank_len, n_intervals, nullptr);
+}
+
+}  // extern "C"
+
+int gci_scan_enqueue(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int32_t flank_len, int64_t* pin) {
+  return scan_genome(ctx, track, lo, hi, flank_len, nullptr, pin);
+}
+
+int gci_scan_finish(gci_ctx* ctx, int32_t track, const int64_t* pin, bool* overflow) {
+  Track& t = ctx->track[track];
+  const int64_t no = t.n_owners;
+  *overflow = false;
+  if (pin[no + 1] != pin[no + 2])
+    return ctx->fail(GCI_E_CUDA, "internal: run starts (%lld) != run ends (%lld)", (long long)pin[no + 1],
+                     (long long)pin[no + 2]);
+  if (pin[no + 1] > t.iv_cap) {
+    *overflow = true;
+    return GCI_OK;
+  }
+  t.n_intervals = pin[no + 1];
+  t.h_owner_off.assign(pin, pin + no + 1);
+  return GCI_OK;
+}
+
+static int scan_genome(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int32_t flank_len, int64_t* n_intervals,
+                       int64_t* defer_pin) {
   if (!ctx || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
   Track& t = ctx->track[track];
@@ -704,10 +760,12 @@ int gci_scan(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int32_t flank_
     ctx->launches++;
     if (cudaGetLastError() != cudaSuccess) rc = ctx->fail(GCI_E_CUDA, "genome_windows_kernel launch failed");
   }
-  if (rc == GCI_OK) rc = extract_runs(ctx, t, lay_lo, h_hi, n_intervals);
+  if (rc == GCI_OK) rc = extract_runs(ctx, t, lay_lo, h_hi, n_intervals, defer_pin);
   ctx->stage_end();
   return rc;
 }
+
+extern "C" {
 
 int gci_scan_windows(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int64_t n_windows, const int32_t* contig,
                      const int64_t* start, const int64_t* end, int64_t* n_intervals) {
@@ -788,7 +846,7 @@ int gci_score_terms_sums(gci_ctx* ctx, int32_t track, double dist_percent, int32
   Track& t = ctx->track[track];
   int64_t no = 0, n_slots = 0;
   ctx->stage_begin(GCI_ST_SCORE);
-  GCI_TRY(gci_launch_score_kernels(ctx, t, dist_percent, flank_len, &no, &n_slots));
+  GCI_TRY(gci_launch_score_kernels(ctx, t, dist_percent, flank_len, &no, &n_slots, false));
   const int64_t n_res = 3 * no + 1 + n_slots;
   int64_t* h_res = (int64_t*)ctx->pinned(sizeof(int64_t) * (size_t)n_res);
   if (!h_res) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");

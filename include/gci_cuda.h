@@ -168,6 +168,14 @@ int gci_score_terms_sums(gci_ctx* ctx, int32_t track, double dist_percent, int32
                          int64_t* n_ctg, int64_t cap_lengths, int64_t* lengths, int64_t* lengths_off,
                          int64_t* depth_sums /* [owners+1] */);
 
+/* ---- the whole path in one call ---------------------------------------------------------------------- */
+/* gci_filter + gci_depth + gci_scan + gci_score_terms_sums on the uploaded read set with ONE host
+   synchronisation (the stages only hand device buffers to each other).  Same results as the four calls. */
+int gci_pipeline(gci_ctx* ctx, int32_t track, int32_t map_qual, int32_t mq_cutoff, double iden_percent,
+                 double clip_percent, double ovlp_percent, int32_t flank_len, int32_t lo, int32_t hi,
+                 double dist_percent, int64_t* n_survivors, int64_t* n_intervals, int64_t* n50 /* [owners+1] */,
+                 int64_t* n_ctg /* [owners+1] */, int64_t* depth_sums /* [owners+1] */);
+
 /* ---- multi-GPU: one process per GPU, contigs sharded across ranks ---------------------------------- */
 /* NCCL (resolved at run time with dlopen: the copy torch.distributed already loaded, else the system one).
    Rank 0 creates the id, the host layer broadcasts its 128 bytes, every rank calls gci_comm_init. */

@@ -379,3 +379,63 @@ def test_paf_election_known_cases(ctx):
     with pytest.raises(Exception):
         bad = PafTable.from_rows([line(0, 0, 0, 100, 0, 100, alnlen=0, nmatch=0)])
         _run_gpu(ctx, names, lengths, [bad], [bam], 8)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_fused_pipeline_equals_staged_calls(ctx, seed):
+    """gci_pipeline (one synchronisation) == gci_filter + gci_depth + gci_scan + gci_score_terms_sums, also when
+    the interval buffers are too small for the result (the retry path)"""
+    from gci_b200._lib import Context
+    lengths = [120_000, 70_000, 30_000]
+    d = synth.make_reads(synth.SynthSpec(lengths, coverage=[25, 3, 12][seed], seed=700 + seed, read_mean=5000,
+                                         read_min=800, read_max=12000, hole_fraction=0.03, hole_mean=300))
+    files = [d.bam] + ([synth.second_aligner(d, seed=seed)] if seed else [])
+    pafs = [synth.aln_to_paf(synth.second_aligner(d, seed=40))] if seed == 2 else []
+    c2 = Context(0)     # fresh context: first pipeline call runs with the minimum interval capacity
+    try:
+        for c in (ctx, c2):
+            c.set_contigs(lengths)
+            c.set_name_rank(_name_rank(d.contigs.names))
+            c.reads_begin(d.n_reads)
+            for t in pafs:
+                c.upload_paf(t)
+            for t in files:
+                c.upload_bam(t)
+        ts = 1
+        n_surv = ctx.filter()
+        ctx.depth(0, 15, -1, ts)
+        n_iv = ctx.scan(0, -1, ts, 15)
+        a50, actg, _, _, asum = ctx.score_terms(0, 3, n_iv, 0.005, 15, with_sums=True)
+        for rep in range(2):
+            got = c2.pipeline(0, 3, hi=ts)
+            assert got[0] == n_surv and got[1] == n_iv
+            assert (got[2] == a50).all() and (got[3] == actg).all() and (got[4] == asum).all()
+            gs, ge, off = c2.fetch_intervals(0, 3)
+            ws, we, woff = ctx.fetch_intervals(0, 3)
+            assert (gs == ws).all() and (ge == we).all() and (off == woff).all()
+            for i in range(3):
+                assert np.array_equal(c2.fetch_depth(0, i), ctx.fetch_depth(0, i))
+        # more issue intervals than the initial capacity (4096) of a fresh context: the fused call redoes the scan
+        c3 = Context(0)
+        try:
+            n = 6000
+            many = _bam([dict(ref_start=i * 100, cigar="60M", read_id=i) for i in range(n)])
+            L = n * 100 + 50
+            for c in (ctx, c3):
+                c.set_contigs([L])
+                c.reads_begin(n)
+                c.upload_bam(many)
+            ctx.filter()
+            ctx.depth(0, 5, -1, 0)
+            n_iv = ctx.scan(0, -1, 0, 5)
+            assert n_iv > 4096
+            a50, actg, _, _, asum = ctx.score_terms(0, 1, n_iv, 0.005, 5, with_sums=True)
+            got = c3.pipeline(0, 1, flank_len=5, hi=0)
+            assert got[1] == n_iv and (got[2] == a50).all() and (got[3] == actg).all() and (got[4] == asum).all()
+            assert all((x == y).all() for x, y in zip(c3.fetch_intervals(0, 1), ctx.fetch_intervals(0, 1)))
+            got = c3.pipeline(0, 1, flank_len=5, hi=0)      # second call: buffers are large enough now
+            assert got[1] == n_iv and (got[2] == a50).all()
+        finally:
+            c3.close()
+    finally:
+        c2.close()
