@@ -196,14 +196,14 @@ def main():
     result = {}
 
     def core_step():
-        # the whole path in one library call (one host synchronisation): gci_pipeline = gci_filter + gci_depth +
-        # gci_scan + gci_score_terms_sums
-        n_surv, n_iv, n50, nctg, sums = ctx.pipeline(0, 1, flank_len=FLANK, lo=-1, hi=THRESHOLD, dist_percent=DIST,
-                                                     **PARAMS)
+        # the whole path in one library call, one host synchronisation: gci_pipeline = gci_filter + gci_depth +
+        # gci_scan + gci_score_terms_sums (+ at N > 1 the genome row: one ncclAllGather on the library's stream)
+        kw = dict(flank_len=FLANK, lo=-1, hi=THRESHOLD, dist_percent=DIST, **PARAMS)
         if world > 1:
-            # genome row: one ncclAllGather on the library's stream
-            n50, nctg, sums, mean, all_ctg, all_len = ctx.genome_row(0, 1, sum(L), DIST, FLANK)
+            n_surv, n_iv, n50, nctg, sums, mean, all_ctg, all_len = ctx.pipeline_row(0, 1, sum(L), **kw)
             result["mean_depth"] = mean
+        else:
+            n_surv, n_iv, n50, nctg, sums = ctx.pipeline(0, 1, **kw)
         result.update(n_surv=n_surv, n_iv=n_iv, n50=int(n50[0]), nctg=int(nctg[0]))
         return n_iv
 
@@ -254,10 +254,12 @@ def main():
         n_iv = ctx.scan(0, -1, THRESHOLD, FLANK)
         a50, actg, lens, _, asum = ctx.score_terms(0, 1, n_iv, DIST, FLANK, with_sums=True)
         want = D.genome_row(int(asum[-1]), sum(L), int(actg[-1]), lens)
-        b50, bctg, bsum, mean, all_ctg, all_len = ctx.genome_row(0, 1, sum(L), DIST, FLANK)
-        assert (a50 == b50).all() and (actg == bctg).all() and (asum == bsum).all()
-        assert mean == want[0] and all_ctg == want[1] and sorted(all_len.tolist()) == sorted(want[2].tolist()), \
-            "native NCCL genome row differs from the torch.distributed exchange"
+        for got in (ctx.genome_row(0, 1, sum(L), DIST, FLANK),
+                    ctx.pipeline_row(0, 1, sum(L), flank_len=FLANK, lo=-1, hi=THRESHOLD, dist_percent=DIST, **PARAMS)[2:]):
+            b50, bctg, bsum, mean, all_ctg, all_len = got
+            assert (a50 == b50).all() and (actg == bctg).all() and (asum == bsum).all()
+            assert mean == want[0] and all_ctg == want[1] and sorted(all_len.tolist()) == sorted(want[2].tolist()), \
+                "native NCCL genome row differs from the torch.distributed exchange"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

@@ -76,6 +76,8 @@ _SIGNATURES = {
     "gci_score_terms": (C.c_int, [_p, _i32, _f64, _i32, _p, _p, _i64, _p, _p]),
     "gci_pipeline": (C.c_int, [_p, _i32, _i32, _i32, _f64, _f64, _f64, _i32, _i32, _i32, _f64, C.POINTER(_i64),
                                C.POINTER(_i64), _p, _p, _p]),
+    "gci_pipeline_row": (C.c_int, [_p, _i32, _i32, _i32, _f64, _f64, _f64, _i32, _i32, _i32, _f64, C.POINTER(_i64),
+                                   C.POINTER(_i64), _p, _p, _p, _i64, _i64, _p]),
     "gci_comm_unique_id": (C.c_int, [_p]),
     "gci_comm_init": (C.c_int, [_p, _p, _i32, _i32]),
     "gci_genome_row": (C.c_int, [_p, _i32, _f64, _i32, _i64, _i64, _p, _p, _p, _p]),
@@ -380,6 +382,24 @@ class Context:
                                            float(dist_percent), C.byref(ns), C.byref(ni), _ptr(n50), _ptr(nctg),
                                            _ptr(sums)))
         return ns.value, ni.value, n50, nctg, sums
+
+    def pipeline_row(self, track, n_owners, sum_len, cap=2048, map_qual=30, mq_cutoff=50, iden_percent=0.9,
+                     clip_percent=0.1, ovlp_percent=0.9, flank_len=15, lo=-1, hi=0, dist_percent=0.005):
+        """`pipeline` + the multi-GPU genome row (one ncclAllGather) in the same single synchronisation.
+        -> (n_survivors, n_intervals, n50, n_ctg, depth_sums, mean_depth, total curated contigs, all lengths)"""
+        world = self.comm_world
+        ns, ni = _i64(), _i64()
+        n50, nctg, sums = (np.zeros(n_owners + 1, np.int64) for _ in range(3))
+        rows = np.zeros(world * (4 + cap), np.int64)
+        self._check(self._lib.gci_pipeline_row(self._h, track, int(map_qual), int(mq_cutoff), float(iden_percent),
+                                               float(clip_percent), float(ovlp_percent), int(flank_len), int(lo),
+                                               int(hi), float(dist_percent), C.byref(ns), C.byref(ni), _ptr(n50),
+                                               _ptr(nctg), _ptr(sums), int(sum_len), cap, _ptr(rows)))
+        o = rows.reshape(world, 4 + cap)
+        head = o[:, :4].sum(axis=0)
+        all_len = o[:, 4:][np.arange(cap)[None, :] < o[:, 3:4]]
+        mean = float(head[0]) / float(head[1]) if head[1] else float("nan")
+        return ns.value, ni.value, n50, nctg, sums, mean, int(head[2]), all_len
 
     # ---- multi-GPU ----
     @staticmethod

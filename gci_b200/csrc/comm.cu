@@ -49,10 +49,12 @@ constexpr int NCCL_INT64 = 4;   // ncclInt64 (nccl.h)
 // row = [sum depth, sum length, curated contigs, n lengths, lengths ... (cap)] from the score result buffer
 // res = [n50 (no+1) | n_ctg (no) | depth sum (no) | gap slots (n_slots)]; the order of lengths is irrelevant
 // for an N50, so they are appended with an atomic cursor
-__global__ void pack_row_kernel(const int64_t* __restrict__ res, int64_t no, int64_t n_slots,
+__global__ void pack_row_kernel(const int64_t* __restrict__ res, int64_t no, int64_t n_slots_bound,
                                 const int64_t* __restrict__ owner_off, long long sum_len, int64_t cap,
-                                long long* __restrict__ row) {
+                                long long* __restrict__ row, int64_t iv_cap) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (owner_off[no] > iv_cap) return;                      // scan overflow: the host redoes this step
+  const int64_t n_slots = min(n_slots_bound, owner_off[no] + no);
   if (i == 0) {
     long long sd = 0, sc = 0;
     for (int64_t o = 0; o < no; o++) { sc += res[no + 1 + o]; sd += res[2 * no + 1 + o]; }
@@ -68,6 +70,27 @@ __global__ void pack_row_kernel(const int64_t* __restrict__ res, int64_t no, int
     const unsigned long long k = atomicAdd((unsigned long long*)&row[3], 1ull);
     if ((int64_t)k < cap) row[4 + k] = v;
   }
+}
+
+// pack + all-gather + copy of every rank's row into `h_rows` (pinned), all enqueued on the context's stream
+int gci_enqueue_genome_row(gci_ctx* ctx, Track& t, int64_t no, int64_t sum_len, int64_t cap, int64_t* h_rows) {
+  const int64_t row_n = 4 + cap;
+  const int world = ctx->comm_world;
+  const int64_t n_slots_bound = t.iv_cap + no;
+  DevBuf &d_res = ctx->tmp[1], &d_row = ctx->tmp[2], &d_all = ctx->tmp[5];
+  GCI_TRY(ctx->ensure(d_row, 8 * (size_t)row_n));
+  GCI_TRY(ctx->ensure(d_all, 8 * (size_t)row_n * world));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(d_row.p, 0, 8 * (size_t)row_n, ctx->stream));
+  pack_row_kernel<<<(unsigned)((std::max<int64_t>(1, n_slots_bound) + 255) / 256), 256, 0, ctx->stream>>>(
+      d_res.as<int64_t>(), no, n_slots_bound, t.owner_off.as<int64_t>(), (long long)sum_len, cap,
+      d_row.as<long long>(), t.iv_cap);
+  GCI_LAUNCH_CHECK(ctx);
+  const int rc = g_nccl.AllGather(d_row.p, d_all.p, (size_t)row_n, NCCL_INT64, ctx->nccl_comm, ctx->stream);
+  if (rc != 0)
+    return ctx->fail(GCI_E_CUDA, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  ctx->launches++;
+  GCI_TRY(gci_d2h(ctx, h_rows, d_all.p, 8 * (size_t)row_n * world));
+  return GCI_OK;
 }
 
 extern "C" {
@@ -110,22 +133,11 @@ int gci_genome_row(gci_ctx* ctx, int32_t track, double dist_percent, int32_t fla
   GCI_TRY(gci_launch_score_kernels(ctx, t, dist_percent, flank_len, &no, &n_slots, false));
   const int64_t row_n = 4 + cap;
   const int world = ctx->comm_world;
-  DevBuf &d_res = ctx->tmp[1], &d_row = ctx->tmp[2], &d_all = ctx->tmp[5];
-  GCI_TRY(ctx->ensure(d_row, 8 * (size_t)row_n));
-  GCI_TRY(ctx->ensure(d_all, 8 * (size_t)row_n * world));
-  GCI_CUDA_TRY(ctx, cudaMemsetAsync(d_row.p, 0, 8 * (size_t)row_n, ctx->stream));
-  pack_row_kernel<<<(unsigned)((std::max<int64_t>(1, n_slots) + 255) / 256), 256, 0, ctx->stream>>>(
-      d_res.as<int64_t>(), no, n_slots, t.owner_off.as<int64_t>(), (long long)sum_len, cap, d_row.as<long long>());
-  GCI_LAUNCH_CHECK(ctx);
-  const int rc = g_nccl.AllGather(d_row.p, d_all.p, (size_t)row_n, NCCL_INT64, ctx->nccl_comm, ctx->stream);
-  if (rc != 0)
-    return ctx->fail(GCI_E_CUDA, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
-  ctx->launches++;
   const int64_t n_own = 3 * no + 1;
   int64_t* h = (int64_t*)ctx->pinned(8 * (size_t)(n_own + row_n * world));
   if (!h) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
-  GCI_TRY(gci_d2h(ctx, h, d_res.p, 8 * (size_t)n_own));
-  GCI_TRY(gci_d2h(ctx, h + n_own, d_all.p, 8 * (size_t)row_n * world));
+  GCI_TRY(gci_enqueue_genome_row(ctx, t, no, sum_len, cap, h + n_own));
+  GCI_TRY(gci_d2h(ctx, h, ctx->tmp[1].p, 8 * (size_t)n_own));
   ctx->stage_end();
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (n50) memcpy(n50, h, 8 * (size_t)(no + 1));

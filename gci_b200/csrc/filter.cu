@@ -968,7 +968,20 @@ int gci_pipeline(gci_ctx* ctx, int32_t track, int32_t map_qual, int32_t mq_cutof
                  double clip_percent, double ovlp_percent, int32_t flank_len, int32_t lo, int32_t hi,
                  double dist_percent, int64_t* n_survivors, int64_t* n_intervals, int64_t* n50, int64_t* n_ctg,
                  int64_t* depth_sums) {
+  return gci_pipeline_row(ctx, track, map_qual, mq_cutoff, iden_percent, clip_percent, ovlp_percent, flank_len, lo, hi,
+                          dist_percent, n_survivors, n_intervals, n50, n_ctg, depth_sums, 0, 0, nullptr);
+}
+
+// the same with the multi-GPU genome row in the same synchronisation: rows != NULL adds one ncclAllGather
+// (gci_comm_init must have been called) between the score kernels and the device->host copy
+int gci_pipeline_row(gci_ctx* ctx, int32_t track, int32_t map_qual, int32_t mq_cutoff, double iden_percent,
+                     double clip_percent, double ovlp_percent, int32_t flank_len, int32_t lo, int32_t hi,
+                     double dist_percent, int64_t* n_survivors, int64_t* n_intervals, int64_t* n50, int64_t* n_ctg,
+                     int64_t* depth_sums, int64_t sum_len, int64_t cap, int64_t* rows) {
   if (!ctx || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
+  if (rows && (!ctx->nccl_comm || cap < 1)) return ctx->fail(GCI_E_ARG, "gci_pipeline_row: gci_comm_init / cap missing");
+  const int64_t row_n = rows ? 4 + cap : 0;
+  const int world = rows ? ctx->comm_world : 0;
   cudaSetDevice(ctx->device);
   if (ctx->n_files == 0) return ctx->fail(GCI_E_ARG, "gci_pipeline: no files uploaded");
   int64_t n_sel = 0;
@@ -985,7 +998,7 @@ int gci_pipeline(gci_ctx* ctx, int32_t track, int32_t map_qual, int32_t mq_cutof
   Track& t = ctx->track[track];
   // persistent pinned block: [err 4 x u64 | owner_off n_sel+3 | score result]
   const int64_t res_bound = 3 * n_sel + 1 + std::max<int64_t>(t.iv_cap, 4096) + n_sel;
-  const size_t need = 8 * (size_t)(4 + (n_sel + 3) + res_bound);
+  const size_t need = 8 * (size_t)(4 + (n_sel + 3) + res_bound + row_n * world);
   if (ctx->pipe_pin_cap < need) {
     if (ctx->pipe_pin) cudaFreeHost(ctx->pipe_pin);
     ctx->pipe_pin = nullptr;
@@ -1003,6 +1016,8 @@ int gci_pipeline(gci_ctx* ctx, int32_t track, int32_t map_qual, int32_t mq_cutof
   int64_t no = 0, n_slots = 0;
   ctx->stage_begin(GCI_ST_SCORE);
   GCI_TRY(gci_launch_score_kernels(ctx, t, dist_percent, flank_len, &no, &n_slots, true));
+  int64_t* h_rows = h_res + res_bound;
+  if (rows) GCI_TRY(gci_enqueue_genome_row(ctx, t, no, sum_len, cap, h_rows));
   GCI_TRY(gci_d2h(ctx, h_res, ctx->tmp[1].p, 8 * (size_t)(3 * no + 1 + n_slots)));
   GCI_TRY(gci_d2h(ctx, h_err, ctx->d_err.p, 4 * sizeof(unsigned long long)));
   ctx->stage_end();
@@ -1019,7 +1034,14 @@ int gci_pipeline(gci_ctx* ctx, int32_t track, int32_t map_qual, int32_t mq_cutof
   if (overflow) {
     // rare: redo the scan with grown buffers and the score terms through the synchronous entry points
     GCI_TRY(gci_scan(ctx, track, lo, hi, flank_len, n_intervals));
+    if (rows) return gci_genome_row(ctx, track, dist_percent, flank_len, sum_len, cap, n50, n_ctg, depth_sums, rows);
     return gci_score_terms_sums(ctx, track, dist_percent, flank_len, n50, n_ctg, 0, nullptr, nullptr, depth_sums);
+  }
+  if (rows) {
+    memcpy(rows, h_rows, 8 * (size_t)row_n * world);
+    for (int r = 0; r < world; r++)
+      if (rows[(size_t)r * row_n + 3] > cap)
+        return ctx->fail(GCI_E_ARG, "gci_pipeline_row: rank %d has more curated lengths than cap", r);
   }
   if (n_intervals) *n_intervals = t.n_intervals;
   long long all_c = 0, all_d = 0;

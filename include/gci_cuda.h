@@ -190,6 +190,12 @@ int gci_genome_row(gci_ctx* ctx, int32_t track, double dist_percent, int32_t fla
                    int64_t* n50 /* [owners+1] */, int64_t* n_ctg /* [owners+1] */, int64_t* depth_sums /* [owners+1] */,
                    int64_t* rows /* [world * (4 + cap)] */);
 
+/* gci_pipeline + the genome row of gci_genome_row in the same single synchronisation (rows as in gci_genome_row) */
+int gci_pipeline_row(gci_ctx* ctx, int32_t track, int32_t map_qual, int32_t mq_cutoff, double iden_percent,
+                     double clip_percent, double ovlp_percent, int32_t flank_len, int32_t lo, int32_t hi,
+                     double dist_percent, int64_t* n_survivors, int64_t* n_intervals, int64_t* n50, int64_t* n_ctg,
+                     int64_t* depth_sums, int64_t sum_len, int64_t cap, int64_t* rows);
+
 #ifdef __cplusplus
 }
 #endif
