@@ -179,7 +179,7 @@ void gci_destroy(gci_ctx* ctx) {
   ctx->release(ctx->d_name_rank);
   for (auto& t : ctx->track) free_track(ctx, t);
   for (DevBuf* d : {&ctx->d_len, &ctx->d_selected, &ctx->d_tile_off, &ctx->d_owner_of, &ctx->d_nr_contig, &ctx->d_nr_start,
-                    &ctx->d_nr_end, &ctx->highq, &ctx->surv_contig, &ctx->surv_start, &ctx->surv_end,
+                    &ctx->d_nr_end, &ctx->highq, &ctx->highq_base, &ctx->surv_contig, &ctx->surv_start, &ctx->surv_end,
                     &ctx->tile_cnt, &ctx->events,
                     &ctx->scan_tmp, &ctx->scan_tmp2, &ctx->misc, &ctx->d_err, &ctx->chunk_cnt, &ctx->chunk_off})
     ctx->release(*d);
@@ -342,7 +342,9 @@ int gci_reads_begin(gci_ctx* ctx, uint32_t n_reads) {
   ctx->filtered = false;
   ctx->n_survivors = 0;
   GCI_TRY(ctx->ensure(ctx->highq, n_reads));
+  GCI_TRY(ctx->ensure(ctx->highq_base, n_reads));
   GCI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->highq.p, 0, n_reads ? n_reads : 1, ctx->stream));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->highq_base.p, 0, n_reads ? n_reads : 1, ctx->stream));
   return GCI_OK;
 }
 

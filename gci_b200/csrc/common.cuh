@@ -143,7 +143,8 @@ struct gci_ctx {
   DevBuf d_name_rank;
   std::vector<FileTable> files;     // join order
   size_t n_files = 0;
-  DevBuf highq;                     // uint8[n_reads]
+  DevBuf highq;                     // uint8[n_reads]  high-quality set of the current gci_filter run
+  DevBuf highq_base;                // uint8[n_reads]  marks that came with uploaded tables (kept across runs)
   DevBuf surv_contig, surv_start, surv_end;   // int32[n_reads]; contig < 0 = not a survivor
   bool filtered = false;
   int64_t n_survivors = 0;

@@ -467,6 +467,11 @@ static int check_err(gci_ctx* ctx, const char* where, unsigned long long* count)
 }
 
 static int reset_err(gci_ctx* ctx) {
+  // every filter run starts from the marks that came with uploaded tables: the high-quality set depends on
+  // the run's own --mq-cutoff, so marks of an earlier run on the same read set must not survive
+  if (ctx->n_reads)
+    GCI_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->highq.p, ctx->highq_base.p, ctx->n_reads, cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
   GCI_TRY(ctx->ensure(ctx->d_err, 4 * sizeof(unsigned long long)));
   // [0] error mask = 0, [1] first offending index = ~0, [2] survivor count = 0
   GCI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_err.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
@@ -534,7 +539,7 @@ static int install_table(gci_ctx* ctx, FileTable& f, int64_t n, const uint32_t* 
   if (n) {
     table_win_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
         n, d_read.as<uint32_t>(), ctx->n_reads, highq ? d_hq.as<uint8_t>() : nullptr, f.win.as<long long>(),
-        ctx->highq.as<uint8_t>());
+        ctx->highq_base.as<uint8_t>());
     GCI_LAUNCH_CHECK(ctx);
   }
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

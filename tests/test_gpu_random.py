@@ -439,3 +439,28 @@ def test_fused_pipeline_equals_staged_calls(ctx, seed):
             c3.close()
     finally:
         c2.close()
+
+
+def test_refilter_same_read_set_with_other_cutoffs(ctx):
+    """gci_filter twice on one uploaded read set with different gates: the second run must not inherit the
+    high-quality set (or anything else) of the first"""
+    lengths = [120_000, 60_000]
+    d = synth.make_reads(synth.SynthSpec(lengths, coverage=20, seed=4242, read_mean=6000, read_min=1000, read_max=15000))
+    b2 = synth.second_aligner(d, seed=3)
+    paf = synth.aln_to_paf(synth.second_aligner(d, seed=8))
+    ctx.set_contigs(lengths)
+    ctx.set_name_rank(_name_rank(d.contigs.names))
+    ctx.reads_begin(d.n_reads)
+    ctx.upload_paf(paf)
+    ctx.upload_bam(d.bam)
+    ctx.upload_bam(b2)
+    for p in (dict(mq_cutoff=20, map_qual=10, iden_percent=0.8), dict(mq_cutoff=60, map_qual=30, iden_percent=0.95),
+              dict(mq_cutoff=35, ovlp_percent=0.5)):
+        kw = dict(map_qual=30, mq_cutoff=50, iden_percent=0.9, clip_percent=0.1, ovlp_percent=0.9)
+        kw.update(p)
+        n = ctx.filter(**kw)
+        want_d, want_s = O.filter_depth([paf], [d.bam, b2], d.contigs.names, lengths, **kw)
+        assert n == len(want_s), p
+        ctx.depth(0, 15)
+        for i in range(2):
+            assert np.array_equal(ctx.fetch_depth(0, i).astype(np.int64), want_d[i]), p
