@@ -447,72 +447,77 @@ def _header(f):
     return dict(zip(n, l))
 
 
+def _load_regions(regions):
+    """GCI.py:902-912."""
+    if regions is None:
+        return {}
+    if isinstance(regions, dict):
+        return regions
+    if not (os.path.exists(regions) and os.access(regions, os.R_OK)):
+        sys.exit(f'ERROR!!! "{regions}" is not an available file')
+    return gio.read_regions_bed(regions)
+
+
+def _prepare_directory(directory, prefix):
+    """GCI.py:914-925."""
+    if directory.endswith('/'):
+        directory = '/'.join(directory.split('/')[:-1])
+    if not os.path.exists(directory):
+        os.makedirs(directory)
+    else:
+        for mode, what in ((os.R_OK, 'read'), (os.W_OK, 'write')):
+            if not os.access(directory, mode):
+                sys.exit(f'ERROR!!! The path "{directory}" is unable to {what}')
+    if prefix.endswith('/'):
+        sys.exit(f'ERROR!!! The prefix "{prefix}" is not allowed')
+    return directory
+
+
+def _check_names(ref_refs, chrs_list, regions_bed):
+    """GCI.py:942-952."""
+    for what, names in (('--chrs', chrs_list), ('--regions', list(regions_bed.keys()))):
+        for i in names:
+            if i not in ref_refs:
+                sys.exit(f'ERROR!!! Chromosome "{i}" provided by `{what}` is not in the reference')
+    if len(chrs_list) > 0 and len(regions_bed) > 0 and not all(i in chrs_list for i in regions_bed.keys()):
+        sys.exit(f'ERROR!!! Chromosomes in the regions bed file are inconsistent with the provided list of chromosomes\nPlease read the help message use "-h" or "--help"')
+
+
+class _ReadType:
+    """The alignment files of one read type, split like GCI.py:959-980."""
+
+    def __init__(self, files, label, ref_refs):
+        self.given = files is not None
+        self.bam, self.paf, self.refs_lengths = [], [], {}
+        if not self.given:
+            return
+        for file in files:
+            if _is_bam(file):
+                self.bam.append(file)
+                self.refs_lengths = _header(file)          # the last BAM's header, like the reference
+            else:
+                self.paf.append(file)
+        if set(self.refs_lengths.keys()) != set(ref_refs):
+            sys.exit(f'ERROR!!! The targets in {label} alignment files are inconsistent with the reference file\nPlease check both {label} alignment files and the reference')
+
+
 def GCI(hifi=[], nano=[], directory='.', prefix='GCI', map_qual=30, mq_cutoff=50, iden_percent=0.9, ovlp_percent=0.9,
         clip_percent=0.1, flank_len=15, threshold=0, plot=False, depth_min=0.1, depth_max=4.0, window_size=50000,
         image_type='png', force=False, dist_percent=0.005, reference=None, regions=None, chrs=None, threads=1,
         session=None):
-    """GCI.py:897-1028 (plotting, `-p`, is outside the hot path and not provided)."""
-    chrs_list = []
-    if chrs != None:
-        chrs_list = chrs.strip().split(',')
-
-    regions_bed = {}
-    if regions != None:
-        if isinstance(regions, dict):
-            regions_bed = regions
-        elif os.path.exists(regions) and os.access(regions, os.R_OK):
-            regions_bed = gio.read_regions_bed(regions)
-        else:
-            sys.exit(f'ERROR!!! "{regions}" is not an available file')
-
-    if directory.endswith('/'):
-        directory = '/'.join(directory.split('/')[:-1])
-    if os.path.exists(directory):
-        if not os.access(directory, os.R_OK):
-            sys.exit(f'ERROR!!! The path "{directory}" is unable to read')
-        if not os.access(directory, os.W_OK):
-            sys.exit(f'ERROR!!! The path "{directory}" is unable to write')
-    else:
-        os.makedirs(directory)
-
-    if prefix.endswith('/'):
-        sys.exit(f'ERROR!!! The prefix "{prefix}" is not allowed')
+    """The reference's driver (GCI.py:897-1028) on the GPU path: same keyword arguments, output files, progress
+    lines and exit texts; plotting (`-p`) is outside the hot path and not provided."""
+    chrs_list = chrs.strip().split(',') if chrs != None else []
+    regions_bed = _load_regions(regions)
+    directory = _prepare_directory(directory, prefix)
     if plot == True:
         sys.exit('ERROR!!! Plotting (-p) is not part of the GPU hot path; run the reference\'s utility/plot_depth.py on the .depth.gz outputs')
 
-    parsed_ref = _read_reference(reference)
+    parsed_ref = _read_reference(reference)       # one pass over the FASTA: record ids + N-runs
     ref_refs = parsed_ref[0]
-    if len(chrs_list) > 0:
-        for i in chrs_list:
-            if i not in ref_refs:
-                sys.exit(f'ERROR!!! Chromosome "{i}" provided by `--chrs` is not in the reference')
-    if len(regions_bed) > 0:
-        for i in regions_bed.keys():
-            if i not in ref_refs:
-                sys.exit(f'ERROR!!! Chromosome "{i}" provided by `--regions` is not in the reference')
-    if len(chrs_list) > 0 and len(regions_bed) > 0:
-        if not all(i in chrs_list for i in regions_bed.keys()):
-            sys.exit(f'ERROR!!! Chromosomes in the regions bed file are inconsistent with the provided list of chromosomes\nPlease read the help message use "-h" or "--help"')
-    hifi_bam, hifi_paf, nano_bam, nano_paf = [], [], [], []
-    hifi_refs_lengths, nano_refs_lengths = {}, {}
-    if hifi != None:
-        for file in hifi:
-            if _is_bam(file):
-                hifi_bam.append(file)
-                hifi_refs_lengths = _header(file)
-            else:
-                hifi_paf.append(file)
-        if set(hifi_refs_lengths.keys()) != set(ref_refs):
-            sys.exit('ERROR!!! The targets in hifi alignment files are inconsistent with the reference file\nPlease check both hifi alignment files and the reference')
-    if nano != None:
-        for file in nano:
-            if _is_bam(file):
-                nano_bam.append(file)
-                nano_refs_lengths = _header(file)
-            else:
-                nano_paf.append(file)
-        if set(nano_refs_lengths.keys()) != set(ref_refs):
-            sys.exit('ERROR!!! The targets in ont alignment files are inconsistent with the reference file\nPlease check both ont alignment files and the reference')
+    _check_names(ref_refs, chrs_list, regions_bed)
+    H = _ReadType(hifi, 'hifi', ref_refs)
+    N = _ReadType(nano, 'ont', ref_refs)
 
     print('Finding gaps ...')
     Ns_bed, Ns_bed_file = get_Ns_ref(reference, prefix, directory, force, _parsed=parsed_ref)
@@ -523,43 +528,40 @@ def GCI(hifi=[], nano=[], directory='.', prefix='GCI', map_qual=30, mq_cutoff=50
 
     session = session or default_session()
     session.scan_hint = (-1, threshold)      # the depth kernels emit the issue flags in the same pass
-    common = dict(map_qual=map_qual, mq_cutoff=mq_cutoff, iden_percent=iden_percent, clip_percent=clip_percent,
-                  ovlp_percent=ovlp_percent, flank_len=flank_len, directory=directory, force=force,
-                  chrs_list=chrs_list, threads=threads, session=session)
+    gates = dict(map_qual=map_qual, mq_cutoff=mq_cutoff, iden_percent=iden_percent, clip_percent=clip_percent,
+                 ovlp_percent=ovlp_percent, flank_len=flank_len, directory=directory, force=force,
+                 chrs_list=chrs_list, threads=threads, session=session)
+
+    def one_type(rt, out_prefix, log_name):
+        depths, targets_length = filter(rt.paf, rt.bam, out_prefix, log_reads_type=log_name, **gates)
+        return merge_gaps_depths(depths, Ns_bed), targets_length
+
+    def issues(depths, out_prefix, log_name):
+        return merge_depth(depths, out_prefix, threshold, flank_len, directory, force, log_name)
+
+    def index(targets_length, beds, labels, tracks):
+        compute_index(targets_length, prefix, directory, force, beds, labels, flank_len, dist_percent, regions_bed,
+                      tracks, threshold, chrs_list, session=session)
+
     try:
-        if nano == None:
-            depths, targets_length = filter(hifi_paf, hifi_bam, prefix, log_reads_type='HiFi', **common)
-            depths = merge_gaps_depths(depths, Ns_bed)
-            merged_depth_bed = merge_depth(depths, prefix, threshold, flank_len, directory, force, 'HiFi')
-            compute_index(targets_length, prefix, directory, force, [merged_depth_bed], ['HiFi'], flank_len, dist_percent,
-                          regions_bed, [depths], threshold, chrs_list, session=session)
-        elif hifi == None:
-            depths, targets_length = filter(nano_paf, nano_bam, prefix, log_reads_type='ONT', **common)
-            depths = merge_gaps_depths(depths, Ns_bed)
-            merged_depth_bed = merge_depth(depths, prefix, threshold, flank_len, directory, force, 'ONT')
-            compute_index(targets_length, prefix, directory, force, [merged_depth_bed], ['Nano'], flank_len, dist_percent,
-                          regions_bed, [depths], threshold, chrs_list, session=session)
+        if not (H.given and N.given):
+            rt, log_name, label = (H, 'HiFi', 'HiFi') if H.given else (N, 'ONT', 'Nano')
+            depths, targets_length = one_type(rt, prefix, log_name)
+            index(targets_length, [issues(depths, prefix, log_name)], [label], [depths])
         else:
-            if set(hifi_refs_lengths.keys()) != set(nano_refs_lengths.keys()):
+            if set(H.refs_lengths.keys()) != set(N.refs_lengths.keys()):
                 sys.exit(f'ERROR!!! The targets in hifi and nano alignment files are inconsistent\nPlease check the reference used in mapping both hifi and ont reads')
-            for target, length in hifi_refs_lengths.items():
-                if length != nano_refs_lengths[target]:
-                    sys.exit(f'ERROR!!! The element "{target}:{length}" in hifi alignment files are inconsistent with that in ont alignment files which is "{target}:{nano_refs_lengths[target]}"\nPlease check the reference used in mapping both hifi and ont reads')
-
-            hifi_depths, targets_length = filter(hifi_paf, hifi_bam, prefix + '_hifi', log_reads_type='HiFi', **common)
-            hifi_depths = merge_gaps_depths(hifi_depths, Ns_bed)
-            nano_depths, targets_length = filter(nano_paf, nano_bam, prefix + '_nano', log_reads_type='ONT', **common)
-            nano_depths = merge_gaps_depths(nano_depths, Ns_bed)
-            merged_two_type_depths = merge_two_type_depth(hifi_depths, nano_depths, prefix + '_two_type', directory, force, threads)
-            merged_two_type_depths = merge_gaps_depths(merged_two_type_depths, Ns_bed)
-
-            hifi_merged_depth_bed = merge_depth(hifi_depths, prefix + '_hifi', threshold, flank_len, directory, force, 'HiFi')
-            nano_merged_depth_bed = merge_depth(nano_depths, prefix + '_nano', threshold, flank_len, directory, force, 'ONT')
-            two_type_merged_depth_bed = merge_depth(merged_two_type_depths, prefix + '_two_type', threshold, flank_len, directory, force, 'two_types')
-            compute_index(targets_length, prefix, directory, force,
-                          [hifi_merged_depth_bed, nano_merged_depth_bed, two_type_merged_depth_bed],
-                          ['HiFi', 'Nano', 'HiFi + Nano'], flank_len, dist_percent, regions_bed,
-                          [hifi_depths, nano_depths, merged_two_type_depths], threshold, chrs_list, session=session)
+            for target, length in H.refs_lengths.items():
+                if length != N.refs_lengths[target]:
+                    sys.exit(f'ERROR!!! The element "{target}:{length}" in hifi alignment files are inconsistent with that in ont alignment files which is "{target}:{N.refs_lengths[target]}"\nPlease check the reference used in mapping both hifi and ont reads')
+            hifi_depths, targets_length = one_type(H, prefix + '_hifi', 'HiFi')
+            nano_depths, targets_length = one_type(N, prefix + '_nano', 'ONT')
+            both = merge_two_type_depth(hifi_depths, nano_depths, prefix + '_two_type', directory, force, threads)
+            both = merge_gaps_depths(both, Ns_bed)
+            tracks = [hifi_depths, nano_depths, both]
+            beds = [issues(d, prefix + sfx, log_name) for d, sfx, log_name in
+                    zip(tracks, ('_hifi', '_nano', '_two_type'), ('HiFi', 'ONT', 'two_types'))]
+            index(targets_length, beds, ['HiFi', 'Nano', 'HiFi + Nano'], tracks)
     finally:
         session.scan_hint = None
     print('GCI finished!!!\nBye!!!')
