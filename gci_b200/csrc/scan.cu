@@ -664,6 +664,8 @@ int gci_launch_score_kernels(gci_ctx* ctx, Track& t, double dist_percent, int32_
     ctx->ob_cache.assign((const char*)ob.data(), (const char*)ob.data() + ob_bytes);
   }
   GCI_TRY(ctx->ensure(d_res, sizeof(int64_t) * (size_t)n_res));
+  // pending: the copy back is sized by the capacity, not by the (still unknown) interval count
+  if (pending) GCI_CUDA_TRY(ctx, cudaMemsetAsync(d_res.p, 0, sizeof(int64_t) * (size_t)n_res, ctx->stream));
   complement_kernel<<<(unsigned)no, 256, 0, ctx->stream>>>(
       no, t.owner_off.as<int64_t>(), t.iv_start.as<int32_t>(), t.iv_end.as<int32_t>(), d_ob.as<OwnerBounds>(),
       d_res.as<int64_t>(), (!t.owners_are_windows && t.sums_valid) ? t.sums.as<long long>() : nullptr,
