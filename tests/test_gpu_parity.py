@@ -97,3 +97,27 @@ def test_cli_on_real_files(tmp_path):
         p = str(tmp_path / "out" / fn)
         got[fn] = gio.read_depth_gz(p) if fn.endswith(".depth.gz") else open(p).read()
     assert_outputs_equal(got, expected)
+
+
+def test_resume_from_depth_gz_tool(tmp_path):
+    """tools/gci_score.py (the reference's utility/GCI_score.py entry): saved .depth.gz files + FASTA ->
+    the same BED / .gci as the full run of the dual golden case"""
+    import gzip, subprocess, sys
+    from gci_b200 import io as gio
+    case, kw, expected = load_case("dual")
+    names, lengths = kw["names"], kw["lengths"]
+    for sfx in ("_hifi", "_nano"):
+        with gzip.open(tmp_path / f"T{sfx}.depth.gz", "wb") as f:
+            for n in names:
+                f.write(f">{n}\n".encode() + "".join(f"{int(v)}\n" for v in expected[f"T{sfx}.depth.gz"][n]).encode())
+    gio.write_fasta(str(tmp_path / "ref.fa"), names, lengths, kw["n_runs"])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gci_score.py"), "--hifi", str(tmp_path / "T_hifi.depth.gz"),
+                        "--nano", str(tmp_path / "T_nano.depth.gz"), "-r", str(tmp_path / "ref.fa"), "-d",
+                        str(tmp_path / "out"), "-o", "T", "-f"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for fn in ("T.gci", "T_hifi.0.depth.bed", "T_nano.0.depth.bed", "T_two_type.0.depth.bed"):
+        assert open(tmp_path / "out" / fn).read() == expected[fn], fn
+    got = gio.read_depth_gz(str(tmp_path / "out" / "T_two_type.depth.gz"))
+    for n in names:
+        assert np.array_equal(got[n], expected["T_two_type.depth.gz"][n])
