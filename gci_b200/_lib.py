@@ -58,6 +58,7 @@ _SIGNATURES = {
     "gci_upload_paf": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gci_upload_table": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p]),
     "gci_filter": (C.c_int, [_p, _i32, _i32, _f64, _f64, _f64, C.POINTER(_i64)]),
+    "gci_fetch_cigar_stats": (C.c_int, [_p, _i32, _i64, _p, _p]),
     "gci_fetch_survivors": (C.c_int, [_p, _i64, _p, _p, _p, _p, C.POINTER(_i64)]),
     "gci_fetch_file_table": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _p, _p, _p, C.POINTER(_i64)]),
     "gci_depth": (C.c_int, [_p, _i32, _i32, _i32, _i32]),
@@ -262,6 +263,13 @@ class Context:
         self._check(self._lib.gci_filter(self._h, int(map_qual), int(mq_cutoff), float(iden_percent),
                                          float(clip_percent), float(ovlp_percent), C.byref(n)))
         return n.value
+
+    def fetch_cigar_stats(self, bam_idx, n_records):
+        """-> (uint32[n][5] bases in (M+=+X, I, D, N, S), int32[n] reference_end) of one BAM upload"""
+        st = np.zeros((int(n_records), 5), np.uint32)
+        end = np.zeros(int(n_records), np.int32)
+        self._check(self._lib.gci_fetch_cigar_stats(self._h, bam_idx, int(n_records), _ptr(st), _ptr(end)))
+        return st, end
 
     def fetch_survivors(self):
         n = _i64()

@@ -94,7 +94,7 @@ int gci_d2h(gci_ctx* ctx, void* dst, const void* src, size_t bytes) {
 
 static void free_bam(gci_ctx* ctx, BamFile& b) {
   for (DevBuf* d : {&b.ref_id, &b.ref_start, &b.mapq, &b.flag, &b.nm, &b.qlen, &b.read_id, &b.cigar_off,
-                    &b.cigar, &b.stats, &b.ref_end, &b.tile_rec})
+                    &b.cigar, &b.stats, &b.ref_end, &b.tile_rec, &b.dense_list})
     ctx->release(*d);
 }
 
@@ -384,6 +384,7 @@ int gci_upload_bam(gci_ctx* ctx, int64_t n, const int32_t* ref_id, const int32_t
   ctx->filtered = false;
   // the caller may reuse its host buffers as soon as we return
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  gci_index_bam_finish(ctx, b);
   return GCI_OK;
 }
 

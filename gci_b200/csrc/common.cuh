@@ -53,6 +53,8 @@ struct BamFile {
   DevBuf stats;    // uint32[n][8]: Mx(M+=+X), I, D, N, S, pad..   (K1 output)
   DevBuf ref_end;  // int32[n]                                      (K2 output)
   DevBuf tile_rec; // int2[n_op_tiles]: first / last record of every CIGAR op tile (built at upload)
+  DevBuf dense_list; // int32[n_op_tiles] + counter: tiles of the staged CIGAR kernel (the others stream)
+  int64_t n_dense = 0; // number of entries of dense_list (-1: the count is still on its way to the host)
 };
 
 // PAF lines of one file, resident on the device (columns 0,1,2,3,5,7,8,9,10,11 of GCI.py:218-229)
@@ -193,6 +195,7 @@ int gci_exclusive_scan_i32(gci_ctx* ctx, const int32_t* in, int32_t* out, int64_
 
 // stage entry points
 int gci_index_bam(gci_ctx* ctx, BamFile& b);
+void gci_index_bam_finish(gci_ctx* ctx, BamFile& b);
 int gci_run_bam_leg(gci_ctx* ctx, int file_idx, int bam_idx, int32_t mq, int32_t mq_cutoff, double ip, double cp);
 int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip);
 int gci_run_join(gci_ctx* ctx, double op);

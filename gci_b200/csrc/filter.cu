@@ -24,6 +24,7 @@ constexpr int CIG_THREADS = 256;
 constexpr int CIG_OPT = 8;                       // ops per thread
 constexpr int CIG_TILE = CIG_THREADS * CIG_OPT;  // 2048 ops = 8 KB
 constexpr int CIG_CAP = 512;                     // records per tile handled through shared memory
+constexpr int CST_MAX_LOC = 8;                   // tiles touching at most this many records stream (K1b)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -79,6 +80,16 @@ __global__ void cigar_tile_index_kernel(const uint64_t* __restrict__ off, int64_
   if ((int64_t)b == n_ops) tile_rec[n_tiles - 1].y = (int32_t)r;
 }
 
+// tiles touching more than CST_MAX_LOC records go to the staged kernel (K1a), the others stream (K1b);
+// the list order is arbitrary: both kernels only ever ADD u32 partial sums, which commute exactly
+__global__ void cigar_tile_class_kernel(const int2* __restrict__ tile_rec, int64_t n_tiles,
+                                        int32_t* __restrict__ dense_list, unsigned int* __restrict__ n_dense) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const int2 tr = tile_rec[t];
+  if (tr.y - tr.x + 1 > CST_MAX_LOC) dense_list[atomicAdd(n_dense, 1u)] = (int32_t)t;
+}
+
 struct CigAcc {
   uint32_t tot, i, d, n, s;   // tot = M + '=' + X + I + D
   __device__ __forceinline__ void clear() { tot = i = d = n = s = 0; }
@@ -110,6 +121,31 @@ struct CigAcc {
       }
     }
   }
+  // 16 ops of one lane (four 16-byte loads).  1 << (w & 31) marks bit c or c + 16 (bit 4 of w is the low
+  // bit of the length): one funnel shift per op instead of mask + shift
+  __device__ __forceinline__ void add16(const uint4 (&q)[4]) {
+    uint32_t seen = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      seen |= __funnelshift_l(0u, 1u, q[k].x) | __funnelshift_l(0u, 1u, q[k].y) | __funnelshift_l(0u, 1u, q[k].z) |
+              __funnelshift_l(0u, 1u, q[k].w);
+    if ((seen | (seen >> 16)) & 0xFE78u) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) { add(q[k].x); add(q[k].y); add(q[k].z); add(q[k].w); }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t w[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t c = w[j] & 15u, l = w[j] >> 4;
+          tot += l;
+          i += (c == 1u) ? l : 0u;
+          d += (c == 2u) ? l : 0u;
+        }
+      }
+    }
+  }
   __device__ __forceinline__ bool any() const { return (tot | n | s) != 0; }
   __device__ __forceinline__ void warp_reduce() {   // REDUX.SUM: one instruction per counter
     tot = __reduce_add_sync(0xffffffffu, tot);
@@ -127,11 +163,17 @@ struct CigAcc {
     if (n) atomicAdd(p + 3, n);
     if (s) atomicAdd(p + 4, s);
   }
+  // after warp_reduce(): lanes 0..4 add one counter each
+  __device__ __forceinline__ void flush_warp(uint32_t* p, int lane) const {
+    const uint32_t v = lane == 0 ? tot - i - d : lane == 1 ? i : lane == 2 ? d : lane == 3 ? n : s;
+    if (lane < 5 && v) atomicAdd(p + lane, v);
+  }
 };
 
+// K1a  staged kernel: tiles holding many records (HiFi: ~70 records per 2048 ops)
 __global__ void __launch_bounds__(CIG_THREADS)
 cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restrict__ off, int64_t n_rec,
-                   int64_t n_ops, const int2* __restrict__ tile_rec, int64_t n_tiles,
+                   int64_t n_ops, const int2* __restrict__ tile_rec, const int32_t* __restrict__ tile_list,
                    uint32_t* __restrict__ stats /* [n_rec][8] */) {
   __shared__ __align__(128) uint32_t s_ops[CIG_TILE];
   __shared__ int32_t s_off[CIG_CAP + 2];          // record starts relative to the tile, clamped
@@ -139,64 +181,26 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
   __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x, lane = tid & 31;
-  const int64_t tile = blockIdx.x;
+  const int64_t tile = tile_list ? (int64_t)tile_list[blockIdx.x] : (int64_t)blockIdx.x;
   const int64_t o0 = tile * CIG_TILE;
   const int tile_n = (int)min((int64_t)CIG_TILE, n_ops - o0);
+#if GCI_USE_TMA
+  // the bulk copy depends on nothing but the tile number: it flies while the record table is read
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    const uint32_t bytes = (uint32_t)((tile_n * 4 + 15) & ~15);
+    mbar_expect_tx(&s_bar, bytes);
+    tma_load_1d(s_ops, cigar + o0, bytes, &s_bar);
+  }
+#endif
   const int2 tr = tile_rec[tile];
   const int64_t r_lo = tr.x;                      // first / last record with an op in this tile
   const int n_loc = tr.y - tr.x + 1;
 
-  if (n_loc == 1) {
-    // the whole tile lies inside one record (the common ONT case: thousands of ops per record): which
-    // thread sums which op does not matter -> lane-consecutive 16-byte loads straight from HBM, one
-    // block-wide reduction, no staging
-    CigAcc acc;
-    acc.clear();
-    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(cigar + o0);
-    if (tile_n == CIG_TILE) {
-      const uint4 q0 = src[tid], q1 = src[CIG_THREADS + tid];
-      const uint32_t op[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-      acc.add8(op);
-    } else {
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int v = h * CIG_THREADS + tid;      // uint4 index inside the tile
-        if (v * 4 + 4 <= tile_n) {
-          const uint4 q = src[v];
-          acc.add(q.x); acc.add(q.y); acc.add(q.z); acc.add(q.w);
-        } else {
-          for (int k = v * 4; k < tile_n; k++) acc.add(cigar[o0 + k]);
-        }
-      }
-    }
-    acc.warp_reduce();
-    uint32_t* red = s_acc;                        // [8 warps][5]
-    if (lane == 0) {
-      red[(tid >> 5) * 5 + 0] = acc.tot; red[(tid >> 5) * 5 + 1] = acc.i; red[(tid >> 5) * 5 + 2] = acc.d;
-      red[(tid >> 5) * 5 + 3] = acc.n; red[(tid >> 5) * 5 + 4] = acc.s;
-    }
-    __syncthreads();
-    if (tid < 5) {
-      uint32_t v = 0;
-#pragma unroll
-      for (int w = 0; w < CIG_THREADS / 32; w++) v += red[w * 5 + tid];
-      red[40 + tid] = v;
-    }
-    __syncthreads();
-    if (tid < 5) {
-      const uint32_t tot = red[40], ci = red[41], cd = red[42];
-      const uint32_t val = tid == 0 ? tot - ci - cd : red[40 + tid];
-      const bool complete = off[r_lo] >= (uint64_t)o0 && off[r_lo + 1] <= (uint64_t)(o0 + tile_n);
-      uint32_t* g = stats + r_lo * 8 + tid;
-      if (complete) *g = val; else if (val) atomicAdd(g, val);
-    }
-    return;
-  }
-
   const int first = tid * CIG_OPT;
   const int nb = min(CIG_OPT, tile_n - first);    // my ops (<= 0: none)
   if (n_loc > CIG_CAP) {
-    // pathological tile (more than 1024 records in 2048 ops): global atomics, no staging
+    // pathological tile (more than 512 records in 2048 ops): global atomics, no staging
     if (nb > 0) {
       int64_t rl = upper_bound_minus1<uint64_t>(off + r_lo, n_loc, (uint64_t)(o0 + first));
       CigAcc acc;
@@ -212,21 +216,15 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
       }
       if (acc.any()) acc.flush(stats + (r_lo + rl) * 8);
     }
+#if GCI_USE_TMA
+    __syncthreads();                              // s_bar initialised before anyone polls it
+    mbar_wait(&s_bar, 0);                         // never leave with a bulk copy in flight into our smem
+#endif
     return;
   }
 
-#if GCI_USE_TMA
-  if (tid == 0) mbar_init(&s_bar, 1);
-#endif
   for (int i = tid; i < n_loc * 5; i += CIG_THREADS) s_acc[i] = 0u;
-  __syncthreads();
-#if GCI_USE_TMA
-  if (tid == 0) {
-    const uint32_t bytes = (uint32_t)((tile_n * 4 + 15) & ~15);
-    mbar_expect_tx(&s_bar, bytes);
-    tma_load_1d(s_ops, cigar + o0, bytes, &s_bar);
-  }
-#else
+#if !GCI_USE_TMA
   for (int v = tid; v * 4 < tile_n; v += CIG_THREADS)
     reinterpret_cast<uint4*>(s_ops)[v] = reinterpret_cast<const uint4*>(cigar + o0)[v];
 #endif
@@ -234,10 +232,10 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
     const long long rel = (long long)off[r_lo + i] - (long long)o0;
     s_off[i] = (int32_t)max(-1ll, min(rel, (long long)CIG_TILE + 1));
   }
+  __syncthreads();                                // s_acc, s_off and the mbarrier are set up
 #if GCI_USE_TMA
   mbar_wait(&s_bar, 0);
 #endif
-  __syncthreads();
 
   const bool active = nb > 0;
   int rl = 0, next = 0;
@@ -302,6 +300,95 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
       for (int k = 0; k < 5; k++)
         if (p[k]) atomicAdd(g + k, p[k]);
     }
+  }
+}
+
+// K1b  streaming kernel: tiles touching at most CST_MAX_LOC records (ONT: thousands of ops per record).
+// One warp per 2048-op tile, no shared memory, no block barrier: 16 rounds of lane-consecutive 16-byte
+// loads (512 B per warp instruction), four rounds in flight; the sums stay in registers until a record
+// ends (one REDUX per counter, five atomics), which happens a few times per tile at most.
+constexpr int CST_WARPS = 8;
+
+__global__ void __launch_bounds__(CST_WARPS * 32)
+cigar_stream_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restrict__ off, int64_t n_ops,
+                    const int2* __restrict__ tile_rec, int64_t n_tiles, uint32_t* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = (int64_t)blockIdx.x * CST_WARPS + (threadIdx.x >> 5);
+  if (tile >= n_tiles) return;
+  const int64_t o0 = tile * CIG_TILE;
+  const int tile_n = (int)min((int64_t)CIG_TILE, n_ops - o0);
+  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(cigar + o0);
+  const int2 tr = tile_rec[tile];
+  const bool full = tile_n == CIG_TILE;
+  auto load_group = [&](int g, uint4 (&q)[4]) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) q[j] = __ldcs(src + g * 128 + j * 32 + lane);
+      return;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {                 // last tile of the op stream: absent ops read as 0 (M of length 0)
+      const int v = g * 128 + j * 32 + lane;      // 16-byte word of the tile
+      const int p = v * 4;
+      q[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (p < tile_n) q[j].x = cigar[o0 + p];
+      if (p + 1 < tile_n) q[j].y = cigar[o0 + p + 1];
+      if (p + 2 < tile_n) q[j].z = cigar[o0 + p + 2];
+      if (p + 3 < tile_n) q[j].w = cigar[o0 + p + 3];
+    }
+  };
+  uint4 qa[4], qb[4];
+  load_group(0, qa);                              // in flight while the record table is read
+  const int n_loc = tr.y - tr.x + 1;
+  if (n_loc > CST_MAX_LOC) return;                // a tile of the staged kernel
+  // lane i keeps the end of record tr.x + i, relative to the tile (the last one may lie beyond it)
+  int my_end = CIG_TILE + 1;
+  if (lane < n_loc) my_end = (int)min((long long)off[tr.x + lane + 1] - (long long)o0, (long long)CIG_TILE + 1);
+  int r = 0;                                      // current record (local index), warp-uniform
+  int nxt = __shfl_sync(0xffffffffu, my_end, 0);  // its end
+  CigAcc acc;
+  acc.clear();
+  auto process_group = [&](int g, const uint4 (&q)[4]) {
+    const int gbase = g * 512;
+    if (nxt >= gbase + 512) {                     // the whole group lies inside the current record
+      acc.add16(q);
+      return;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int ibase = gbase + j * 128;
+      const int p = ibase + lane * 4;
+      const uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+      int cur = ibase;                            // ops before `cur` are accounted for
+      while (nxt < ibase + 128) {                 // a record ends inside this round (warp-uniform)
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (p + k >= cur && p + k < nxt) acc.add(w[k]);
+        acc.warp_reduce();
+        acc.flush_warp(stats + (int64_t)(tr.x + r) * 8, lane);
+        acc.clear();
+        cur = nxt;
+        r++;
+        nxt = r < n_loc ? __shfl_sync(0xffffffffu, my_end, r) : CIG_TILE + 1;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (p + k >= cur) acc.add(w[k]);
+    }
+  };
+  // two groups per trip, ping-pong buffers: the next 512 ops are in flight while the current ones are summed
+#pragma unroll 1
+  for (int g = 0; g < CIG_TILE / 512; g += 2) {
+    if (g * 512 >= tile_n) break;
+    if ((g + 1) * 512 < tile_n) load_group(g + 1, qb);
+    process_group(g, qa);
+    if ((g + 1) * 512 >= tile_n) break;
+    if (g + 2 < CIG_TILE / 512 && (g + 2) * 512 < tile_n) load_group(g + 2, qa);
+    process_group(g + 1, qb);
+  }
+  if (r < n_loc) {
+    acc.warp_reduce();
+    acc.flush_warp(stats + (int64_t)(tr.x + r) * 8, lane);
   }
 }
 
@@ -481,13 +568,32 @@ static int reset_err(gci_ctx* ctx) {
 }
 
 int gci_index_bam(gci_ctx* ctx, BamFile& b) {
+  b.n_dense = 0;
   if (b.n == 0 || b.n_ops == 0) return GCI_OK;
   const int64_t n_tiles = (b.n_ops + CIG_TILE - 1) / CIG_TILE;
   GCI_TRY(ctx->ensure(b.tile_rec, sizeof(int2) * (size_t)(n_tiles + 1)));
   cigar_tile_index_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, ctx->stream>>>(
       b.cigar_off.as<uint64_t>(), b.n, b.tile_rec.as<int2>(), n_tiles, b.n_ops);
   GCI_LAUNCH_CHECK(ctx);
+  // split the tiles between the staged (many records per tile) and the streaming kernel; the count of
+  // staged tiles reaches the host with the synchronisation that ends the upload (gci_index_bam_finish)
+  if (n_tiles >= (int64_t(1) << 31)) return ctx->fail(GCI_E_ARG, "too many CIGAR op tiles");
+  GCI_TRY(ctx->ensure(b.dense_list, sizeof(int32_t) * (size_t)n_tiles + 16));
+  unsigned int* d_cnt = reinterpret_cast<unsigned int*>(b.dense_list.as<int32_t>() + n_tiles);
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned int), ctx->stream));
+  cigar_tile_class_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, ctx->stream>>>(
+      b.tile_rec.as<int2>(), n_tiles, b.dense_list.as<int32_t>(), d_cnt);
+  GCI_LAUNCH_CHECK(ctx);
+  unsigned int* h = (unsigned int*)ctx->pinned(sizeof(unsigned int));
+  if (!h) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
+  GCI_TRY(gci_d2h(ctx, h, d_cnt, sizeof(unsigned int)));
+  b.n_dense = -1;                                 // pending
   return GCI_OK;
+}
+
+// after the stream synchronisation that follows gci_index_bam
+void gci_index_bam_finish(gci_ctx* ctx, BamFile& b) {
+  if (b.n_dense == -1) b.n_dense = (int64_t)*(const unsigned int*)ctx->pinned_scratch;
 }
 
 int gci_run_bam_leg(gci_ctx* ctx, int file_idx, int bam_idx, int32_t mq, int32_t mq_cutoff, double ip, double cp) {
@@ -503,10 +609,19 @@ int gci_run_bam_leg(gci_ctx* ctx, int file_idx, int bam_idx, int32_t mq, int32_t
   GCI_CUDA_TRY(ctx, cudaMemsetAsync(b.stats.p, 0, 32 * (size_t)n, ctx->stream));
   if (b.n_ops > 0) {
     const int64_t n_tiles = (b.n_ops + CIG_TILE - 1) / CIG_TILE;
-    cigar_stats_kernel<<<(unsigned)n_tiles, CIG_THREADS, 0, ctx->stream>>>(
-        b.cigar.as<uint32_t>(), b.cigar_off.as<uint64_t>(), n, b.n_ops, b.tile_rec.as<int2>(), n_tiles,
-        b.stats.as<uint32_t>());
-    GCI_LAUNCH_CHECK(ctx);
+    if (b.n_dense < 0 || b.n_dense > n_tiles) return ctx->fail(GCI_E_ARG, "internal: CIGAR tile index is not built");
+    if (b.n_dense > 0) {
+      cigar_stats_kernel<<<(unsigned)b.n_dense, CIG_THREADS, 0, ctx->stream>>>(
+          b.cigar.as<uint32_t>(), b.cigar_off.as<uint64_t>(), n, b.n_ops, b.tile_rec.as<int2>(),
+          b.n_dense == n_tiles ? nullptr : b.dense_list.as<int32_t>(), b.stats.as<uint32_t>());
+      GCI_LAUNCH_CHECK(ctx);
+    }
+    if (b.n_dense < n_tiles) {
+      cigar_stream_kernel<<<(unsigned)((n_tiles + CST_WARPS - 1) / CST_WARPS), CST_WARPS * 32, 0, ctx->stream>>>(
+          b.cigar.as<uint32_t>(), b.cigar_off.as<uint64_t>(), b.n_ops, b.tile_rec.as<int2>(), n_tiles,
+          b.stats.as<uint32_t>());
+      GCI_LAUNCH_CHECK(ctx);
+    }
   }
   ctx->stage_end();
   ctx->stage_begin(GCI_ST_GATE);
@@ -871,6 +986,30 @@ int gci_filter(gci_ctx* ctx, int32_t map_qual, int32_t mq_cutoff, double iden_pe
   ctx->n_survivors = (int64_t)cnt;
   ctx->filtered = true;
   if (n_survivors) *n_survivors = ctx->n_survivors;
+  return GCI_OK;
+}
+
+int gci_fetch_cigar_stats(gci_ctx* ctx, int32_t bam, int64_t n_records, uint32_t* stats, int32_t* ref_end) {
+  if (!ctx) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (!ctx->filtered) return ctx->fail(GCI_E_ARG, "gci_fetch_cigar_stats before gci_filter");
+  if (bam < 0 || (size_t)bam >= ctx->n_bam) return ctx->fail(GCI_E_ARG, "no BAM upload %d", bam);
+  const BamFile& b = ctx->bam[bam];
+  if (n_records != b.n) return ctx->fail(GCI_E_ARG, "BAM upload %d holds %lld records", bam, (long long)b.n);
+  if (b.n == 0) return GCI_OK;
+  if (stats) {
+    // device rows are 8 words wide (one 32-byte sector per record); the caller gets the 5 used ones
+    uint32_t* h = (uint32_t*)ctx->pinned(32 * (size_t)b.n);
+    if (!h) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
+    GCI_TRY(gci_d2h(ctx, h, b.stats.p, 32 * (size_t)b.n));
+    GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int64_t r = 0; r < b.n; r++)
+      for (int k = 0; k < 5; k++) stats[r * 5 + k] = h[r * 8 + k];
+  }
+  if (ref_end) {
+    GCI_TRY(gci_d2h(ctx, ref_end, b.ref_end.p, 4 * (size_t)b.n));
+    GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   return GCI_OK;
 }
 

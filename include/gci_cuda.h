@@ -99,6 +99,11 @@ int gci_upload_table(gci_ctx* ctx, int64_t n, const uint32_t* read_id, const int
    and the cross-file join (:272-301).  n_survivors = len(file1). */
 int gci_filter(gci_ctx* ctx, int32_t map_qual, int32_t mq_cutoff, double iden_percent,
                double clip_percent, double ovlp_percent, int64_t* n_survivors);
+/* per-record CIGAR statistics of BAM upload number `bam` (0-based, upload order) after gci_filter: what
+   pysam's get_cigar_stats()[0] and reference_end give the reference (GCI.py:157-162, :166).
+   stats[r*5 .. r*5+4] = bases in (M + '=' + X, I, D, N, S) — the reference only ever uses M, '=' and X
+   as one sum (:164-165); ref_end[r] = htslib bam_endpos.  Either pointer may be NULL. */
+int gci_fetch_cigar_stats(gci_ctx* ctx, int32_t bam, int64_t n_records, uint32_t* stats, int32_t* ref_end);
 /* survivors as (read_id, contig, start, end) in read_id order; pass NULL pointers to get the count */
 int gci_fetch_survivors(gci_ctx* ctx, int64_t cap, uint32_t* read_id, int32_t* contig, int32_t* start,
                         int32_t* end, int64_t* n);

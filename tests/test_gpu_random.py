@@ -464,3 +464,44 @@ def test_refilter_same_read_set_with_other_cutoffs(ctx):
         ctx.depth(0, 15)
         for i in range(2):
             assert np.array_equal(ctx.fetch_depth(0, i).astype(np.int64), want_d[i]), p
+
+
+@pytest.mark.parametrize("kind", ["long", "mixed", "edges", "short"])
+def test_cigar_stats_match_op_sums(ctx, kind):
+    """gci_fetch_cigar_stats (what pysam's get_cigar_stats / reference_end give the reference, GCI.py:157-166)
+    against a numpy per-op sum: record lengths that put record ends on every 128- / 512- / 2048-op border of the
+    streaming kernel, tiles mixing many short and a few long records, rare ops (N, S, H, P) in the middle."""
+    rng = np.random.default_rng({"long": 1, "mixed": 2, "edges": 3, "short": 4}[kind])
+    if kind == "long":
+        n_ops = rng.integers(1500, 30_000, 60)
+    elif kind == "mixed":
+        n_ops = np.concatenate([rng.integers(0, 60, 700), rng.integers(1000, 9000, 40), rng.integers(100, 400, 60)])
+        rng.shuffle(n_ops)
+    elif kind == "edges":
+        n_ops = rng.choice([0, 1, 2, 127, 128, 129, 383, 384, 511, 512, 513, 1023, 1024, 2047, 2048, 2049, 4096,
+                            6143, 6144], 300)
+    else:
+        n_ops = rng.integers(1, 50, 4000)
+    off = np.concatenate([[0], np.cumsum(n_ops)]).astype(np.uint64)
+    c = int(off[-1])
+    op = rng.choice([0, 0, 0, 0, 1, 2, 7, 8], c)
+    rare = rng.random(c) < (0.002 if kind != "short" else 0.05)
+    op[rare] = rng.choice([3, 4, 5, 6], int(rare.sum()))
+    ln = rng.integers(1, 60, c)
+    big = rng.random(c) < 0.001
+    ln[big] = rng.integers(1 << 16, 1 << 20, int(big.sum()))          # lengths beyond 16 bits
+    cigar = ((ln.astype(np.uint32) << 4) | op.astype(np.uint32)).astype(np.uint32)
+    a = len(n_ops)
+    t = AlnTable(np.zeros(a, np.int32), rng.integers(0, 1000, a).astype(np.int32), np.full(a, 60, np.uint8),
+                 np.full(a, 4, np.uint16), np.zeros(a, np.int32), np.full(a, 100, np.int32),
+                 np.arange(a, dtype=np.uint32), off, cigar)   # flag 0x4: the statistics are computed, the gates skipped
+    ctx.set_contigs([2_000_000_000])
+    ctx.reads_begin(a)
+    ctx.upload_bam(t)
+    assert ctx.filter() == 0
+    got, got_end = ctx.fetch_cigar_stats(0, a)
+    sums = t.op_sums()
+    want = np.stack([sums[:, 0] + sums[:, 7] + sums[:, 8], sums[:, 1], sums[:, 2], sums[:, 3], sums[:, 4]], axis=1)
+    assert np.array_equal(got.astype(np.int64), want & 0xFFFFFFFF)
+    rlen = want[:, 0] + want[:, 2] + want[:, 3]
+    assert np.array_equal(got_end.astype(np.int64), t.ref_start.astype(np.int64) + np.maximum(rlen, 1))
