@@ -43,6 +43,7 @@ _SIGNATURES = {
     "gci_destroy": (None, [_p]),
     "gci_last_error": (C.c_char_p, [_p]),
     "gci_set_stream": (C.c_int, [_p, _p]),
+    "gci_set_timing": (C.c_int, [_p, _i32]),
     "gci_sync": (C.c_int, [_p]),
     "gci_host_alloc": (_p, [C.c_uint64]),
     "gci_host_free": (None, [_p]),
@@ -50,6 +51,7 @@ _SIGNATURES = {
     "gci_stage_ms": (C.c_int, [_p, C.c_int, C.POINTER(_f64), C.POINTER(_i64)]),
     "gci_kernel_launches": (_i64, [_p]),
     "gci_device_bytes": (_i64, [_p]),
+    "gci_graph_replays": (_i64, [_p]),
     "gci_set_contigs": (C.c_int, [_p, _i32, _p, _p]),
     "gci_set_n_runs": (C.c_int, [_p, _i64, _p, _p, _p]),
     "gci_reads_begin": (C.c_int, [_p, _u32]),
@@ -193,6 +195,12 @@ class Context:
     def set_stream(self, cuda_stream_handle):
         self._check(self._lib.gci_set_stream(self._h, _p(cuda_stream_handle)))
 
+    def set_timing(self, on):
+        """Stage timers on (default): every stage is bracketed by a CUDA event pair and `pipeline` launches its
+        kernels one by one.  Off: `pipeline` / `pipeline_row` replay a CUDA graph of the step once it has been
+        seen twice with the same arguments and read-set shape (stage_report() then stays empty)."""
+        self._check(self._lib.gci_set_timing(self._h, 1 if on else 0))
+
     def sync(self):
         self._check(self._lib.gci_sync(self._h))
 
@@ -211,6 +219,10 @@ class Context:
     @property
     def kernel_launches(self):
         return int(self._lib.gci_kernel_launches(self._h))
+
+    @property
+    def graph_replays(self):
+        return int(self._lib.gci_graph_replays(self._h))
 
     @property
     def device_bytes(self):

@@ -1,5 +1,6 @@
 // libgci_cuda.so — context, memory, uploads and fetches (the C ABI of include/gci_cuda.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <numeric>
@@ -17,9 +18,17 @@ int gci_ctx::fail(int code, const char* fmt, ...) {
   return code;
 }
 
+void gci_ctx::drop_graph() {
+  if (pipe_exec) cudaGraphExecDestroy(pipe_exec);
+  pipe_exec = nullptr;
+  pipe_sig.clear();
+}
+
 int gci_ctx::ensure(DevBuf& b, size_t bytes) {
   if (bytes == 0) bytes = 16;
   if (b.cap >= bytes) return GCI_OK;
+  alloc_gen++;
+  if (capturing) capture_abort = true;   // a buffer moved while its old address may already sit in the graph
   if (b.p) {
     cudaFree(b.p);
     dev_bytes -= (int64_t)b.cap;
@@ -40,6 +49,7 @@ int gci_ctx::ensure(DevBuf& b, size_t bytes) {
 
 void gci_ctx::release(DevBuf& b) {
   if (b.p) {
+    alloc_gen++;
     cudaFree(b.p);
     dev_bytes -= (int64_t)b.cap;
   }
@@ -49,6 +59,8 @@ void gci_ctx::release(DevBuf& b) {
 
 void* gci_ctx::pinned(size_t bytes) {
   if (pinned_cap >= bytes) return pinned_scratch;
+  alloc_gen++;
+  if (capturing) capture_abort = true;
   if (pinned_scratch) cudaFreeHost(pinned_scratch);
   pinned_scratch = nullptr;
   pinned_cap = 0;
@@ -63,6 +75,7 @@ void* gci_ctx::pinned(size_t bytes) {
 }
 
 void gci_ctx::stage_begin(int stage) {
+  if (!timing) return;
   StageTimer& t = timer;
   if (t.next + 2 > t.pool.size()) {
     for (int i = 0; i < 64; i++) {
@@ -78,10 +91,13 @@ void gci_ctx::stage_begin(int stage) {
 }
 
 void gci_ctx::stage_end() {
+  if (!timing) return;
   if (!timer.spans.empty()) cudaEventRecord(timer.spans.back().b, stream);
 }
 
 int gci_h2d(gci_ctx* ctx, DevBuf& dst, const void* src, size_t bytes) {
+  // a host->device copy (of a possibly short-lived host buffer) must never become a graph node
+  if (ctx->capturing) ctx->capture_abort = true;
   GCI_TRY(ctx->ensure(dst, bytes));
   if (bytes) GCI_CUDA_TRY(ctx, cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return GCI_OK;
@@ -156,6 +172,10 @@ int gci_create(int device, gci_ctx** out) {
     return GCI_E_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  {
+    const char* g = getenv("GCI_GRAPH");
+    ctx->graph_ok = !(g && g[0] == '0');
+  }
   cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming);
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   *out = ctx;
@@ -166,6 +186,7 @@ void gci_destroy(gci_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  ctx->drop_graph();
   gci_comm_destroy_internal(ctx);
   for (auto& b : ctx->bam) free_bam(ctx, b);
   for (auto& f : ctx->files) free_table(ctx, f);
@@ -199,6 +220,16 @@ int gci_set_stream(gci_ctx* ctx, void* s) {
   if (!ctx) return GCI_E_ARG;
   cudaStreamSynchronize(ctx->stream);
   ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  ctx->epoch++;
+  return GCI_OK;
+}
+
+int gci_set_timing(gci_ctx* ctx, int32_t on) {
+  if (!ctx) return GCI_E_ARG;
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->timing = on != 0;
+  ctx->timer.spans.clear();
+  ctx->timer.next = 0;
   return GCI_OK;
 }
 
@@ -251,11 +282,13 @@ int gci_stage_ms(gci_ctx* ctx, int stage, double* ms, int64_t* launches) {
 
 int64_t gci_kernel_launches(gci_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int64_t gci_device_bytes(gci_ctx* ctx) { return ctx ? ctx->dev_bytes : 0; }
+int64_t gci_graph_replays(gci_ctx* ctx) { return ctx ? ctx->graph_replays : 0; }
 
 // ---- contigs ------------------------------------------------------------------------------------
 int gci_set_contigs(gci_ctx* ctx, int32_t n, const int64_t* lengths, const uint8_t* selected) {
   if (!ctx || n < 0 || (n && !lengths)) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
+  ctx->epoch++;
   for (auto& t : ctx->track) free_track(ctx, t);
   ctx->n_contigs = n;
   ctx->len.assign(lengths, lengths + n);
@@ -287,6 +320,7 @@ int gci_set_contigs(gci_ctx* ctx, int32_t n, const int64_t* lengths, const uint8
 int gci_set_name_rank(gci_ctx* ctx, const int32_t* name_rank) {
   if (!ctx || !name_rank) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
+  ctx->epoch++;
   ctx->name_rank.assign(name_rank, name_rank + ctx->n_contigs);
   GCI_TRY(gci_h2d(ctx, ctx->d_name_rank, name_rank, sizeof(int32_t) * (size_t)ctx->n_contigs));
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -296,6 +330,7 @@ int gci_set_name_rank(gci_ctx* ctx, const int32_t* name_rank) {
 int gci_set_n_runs(gci_ctx* ctx, int64_t n, const int32_t* contig, const int64_t* start, const int64_t* end) {
   if (!ctx || n < 0 || (n && (!contig || !start || !end))) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
+  ctx->epoch++;
   // keep only runs on selected contigs, normalise like a Python slice assignment, sort by (contig,start)
   std::vector<int64_t> idx;
   std::vector<int64_t> s2(n), e2(n);
@@ -430,6 +465,7 @@ int gci_upload_table(gci_ctx* ctx, int64_t n, const uint32_t* read_id, const int
 int gci_load_depth(gci_ctx* ctx, int32_t track, int32_t contig, const int32_t* depth, int64_t n) {
   if (!ctx || !depth) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
+  ctx->epoch++;
   GCI_TRY(gci_alloc_track(ctx, track));
   if (contig < 0 || contig >= ctx->n_contigs || !ctx->selected[contig] || n != ctx->len[contig])
     return ctx->fail(GCI_E_ARG, "gci_load_depth: contig %d / length %lld mismatch", contig, (long long)n);

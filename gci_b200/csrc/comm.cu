@@ -104,6 +104,7 @@ int gci_comm_unique_id(gci_nccl_id* out) {
 int gci_comm_init(gci_ctx* ctx, const gci_nccl_id* id, int32_t rank, int32_t world) {
   if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
+  ctx->epoch++;
   std::string err;
   if (!load_nccl(err)) return ctx->fail(GCI_E_CUDA, "%s", err.c_str());
   if (ctx->nccl_comm) { g_nccl.CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
@@ -124,6 +125,7 @@ int gci_genome_row(gci_ctx* ctx, int32_t track, double dist_percent, int32_t fla
                    int64_t* n50, int64_t* n_ctg, int64_t* depth_sums, int64_t* rows) {
   if (!ctx || !rows || cap < 1 || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
+  ctx->epoch++;
   if (!ctx->nccl_comm) return ctx->fail(GCI_E_ARG, "gci_genome_row: gci_comm_init has not been called");
   Track& t = ctx->track[track];
   if (t.owners_are_windows || !t.sums_valid)

@@ -168,6 +168,20 @@ struct gci_ctx {
   void* nccl_comm = nullptr;
   int comm_rank = 0, comm_world = 1;
 
+  // CUDA-graph replay of gci_pipeline / gci_pipeline_row (filter.cu).  With the stage timers off, the second
+  // call with an unchanged signature (arguments, read-set sizes, device buffers, `epoch`) is captured into a
+  // graph and every further one replays it: one cudaGraphLaunch instead of ~40 stream operations.
+  bool timing = true;               // stage timers on: eager launches, one event pair per stage
+  bool graph_ok = true;             // GCI_GRAPH=0 in the environment turns the replay off
+  bool capturing = false, capture_abort = false;
+  uint64_t alloc_gen = 0;           // bumped by every device / pinned (re)allocation or release
+  uint64_t epoch = 0;               // bumped by every entry point that changes state the graph depends on
+  std::vector<char> pipe_sig, pipe_sig_seen, pipe_sig_bad;
+  cudaGraphExec_t pipe_exec = nullptr;
+  int64_t pipe_launches = 0;        // kernels inside the captured graph
+  int64_t pipe_no = 0, pipe_slots = 0;
+  int64_t graph_replays = 0;        // steps that ran as a graph launch
+
   std::vector<int64_t> lay_cache;   // last run-chunk layout uploaded to chunk_off
   std::vector<char> ob_cache;       // last OwnerBounds uploaded to tmp[0]
   void* pipe_pin = nullptr;         // persistent pinned block of gci_pipeline
@@ -177,6 +191,7 @@ struct gci_ctx {
   void* pinned_scratch = nullptr;
   size_t pinned_cap = 0;
 
+  void drop_graph();
   int fail(int code, const char* fmt, ...);
   int ensure(DevBuf& b, size_t bytes);            // grow-only
   void release(DevBuf& b);
@@ -200,6 +215,7 @@ int gci_run_bam_leg(gci_ctx* ctx, int file_idx, int bam_idx, int32_t mq, int32_t
 int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip);
 int gci_run_join(gci_ctx* ctx, double op);
 int gci_alloc_track(gci_ctx* ctx, int track);
+int gci_depth_enqueue(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo, int32_t hi);   // depth.cu
 int gci_compute_flags(gci_ctx* ctx, int track, int32_t lo, int32_t hi);
 int gci_launch_score_kernels(gci_ctx* ctx, Track& t, double dist_percent, int32_t flank_len, int64_t* n_owners,
                              int64_t* n_slots, bool pending);   // scan.cu: result stays in ctx->tmp[1], no sync

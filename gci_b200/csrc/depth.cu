@@ -435,9 +435,8 @@ int gci_compute_flags(gci_ctx* ctx, int track, int32_t lo, int32_t hi) {
   return GCI_OK;
 }
 
-extern "C" {
-
-int gci_depth(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo, int32_t hi) {
+// body of gci_depth; gci_pipeline calls it directly (it must not bump ctx->epoch)
+int gci_depth_enqueue(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo, int32_t hi) {
   if (!ctx || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
   if (!ctx->filtered) return ctx->fail(GCI_E_ARG, "gci_depth before gci_filter");
@@ -504,8 +503,16 @@ int gci_depth(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo, int32_
   return GCI_OK;
 }
 
+extern "C" {
+
+int gci_depth(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo, int32_t hi) {
+  if (ctx) ctx->epoch++;
+  return gci_depth_enqueue(ctx, track, flank_len, lo, hi);
+}
+
 int gci_mask_gaps(gci_ctx* ctx, int32_t track) {
   if (!ctx || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
+  ctx->epoch++;
   cudaSetDevice(ctx->device);
   Track& t = ctx->track[track];
   if (!t.allocated) return ctx->fail(GCI_E_ARG, "gci_mask_gaps: track %d holds no depth", track);
@@ -524,6 +531,7 @@ int gci_merge_max(gci_ctx* ctx, int32_t ta, int32_t tb, int32_t tout, int32_t lo
   if (!ctx || ta < 0 || tb < 0 || tout < 0 || ta >= GCI_MAX_TRACKS || tb >= GCI_MAX_TRACKS || tout >= GCI_MAX_TRACKS)
     return GCI_E_ARG;
   cudaSetDevice(ctx->device);
+  ctx->epoch++;
   if (!ctx->track[ta].allocated || !ctx->track[tb].allocated)
     return ctx->fail(GCI_E_ARG, "gci_merge_max: input tracks hold no depth");
   Track& t = ctx->track[tout];
@@ -618,6 +626,7 @@ int gci_depth_text(gci_ctx* ctx, int32_t track, int32_t contig, int64_t first, i
                    int64_t* n_bytes) {
   if (!ctx || track < 0 || track >= GCI_MAX_TRACKS || !n_bytes) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
+  ctx->epoch++;
   Track& t = ctx->track[track];
   if (!t.allocated) return ctx->fail(GCI_E_ARG, "gci_depth_text: track %d holds no depth", track);
   if (contig < 0 || contig >= ctx->n_contigs || !ctx->selected[contig] || first < 0 || count < 0 ||

@@ -964,6 +964,7 @@ int gci_upload_table(gci_ctx* ctx, int64_t n, const uint32_t* read_id, const int
   if (n && (!read_id || !ref_id || !start || !end || !qlen)) return GCI_E_ARG;
   if ((int)ctx->n_files >= GCI_MAX_FILES) return ctx->fail(GCI_E_ARG, "too many files");
   cudaSetDevice(ctx->device);
+  ctx->epoch++;
   if (ctx->n_files == ctx->files.size()) ctx->files.emplace_back();
   ctx->filtered = false;
   return install_table(ctx, ctx->files[ctx->n_files++], n, read_id, ref_id, start, end, qlen, highq);
@@ -973,6 +974,7 @@ int gci_filter(gci_ctx* ctx, int32_t map_qual, int32_t mq_cutoff, double iden_pe
                double ovlp_percent, int64_t* n_survivors) {
   if (!ctx) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
+  ctx->epoch++;
   if (ctx->n_files == 0) return ctx->fail(GCI_E_ARG, "gci_filter: no files uploaded");
   GCI_TRY(reset_err(ctx));
   // PAF election first (files join in upload order); tables uploaded by the caller are already final
@@ -1105,6 +1107,90 @@ int gci_fetch_file_table(gci_ctx* ctx, int32_t file, int64_t cap, uint32_t* read
 }
 
 
+}  // extern "C"
+
+// ---- gci_pipeline internals -----------------------------------------------------------------------
+struct PipeArgs {
+  int32_t track, map_qual, mq_cutoff, flank_len, lo, hi;
+  double ip, cp, op, dp;
+  bool with_rows;
+  int64_t sum_len, cap, row_n, n_sel;
+  int world;
+};
+struct PipeOut {           // where the step's results land in the persistent pinned block
+  unsigned long long* h_err;
+  int64_t *h_off, *h_res, *h_rows;
+  int64_t no, n_slots;
+};
+
+// pinned block: [err 4 x u64 | owner_off n_sel+3 | score result | genome rows]
+static void pipeline_layout(gci_ctx* ctx, const PipeArgs& a, const Track& t, int64_t no, int64_t n_slots, PipeOut* o) {
+  const int64_t res_bound = 3 * a.n_sel + 1 + std::max<int64_t>(t.iv_cap, 4096) + a.n_sel;
+  o->h_err = (unsigned long long*)ctx->pipe_pin;
+  o->h_off = (int64_t*)(o->h_err + 4);
+  o->h_res = o->h_off + (a.n_sel + 3);
+  o->h_rows = o->h_res + res_bound;
+  o->no = no;
+  o->n_slots = n_slots;
+}
+
+// everything the enqueued work depends on besides device memory contents
+static std::vector<char> pipeline_signature(gci_ctx* ctx, const PipeArgs& a) {
+  std::vector<char> sig;
+  auto put = [&sig](const void* p, size_t n) { sig.insert(sig.end(), (const char*)p, (const char*)p + n); };
+  auto put64 = [&put](int64_t v) { put(&v, sizeof v); };
+  put64(a.track); put64(a.map_qual); put64(a.mq_cutoff); put64(a.flank_len); put64(a.lo); put64(a.hi);
+  put(&a.ip, 8); put(&a.cp, 8); put(&a.op, 8); put(&a.dp, 8);
+  put64(a.with_rows); put64(a.sum_len); put64(a.cap); put64(a.world); put64(a.n_sel);
+  put64((int64_t)ctx->epoch); put64((int64_t)ctx->alloc_gen); put64((int64_t)(intptr_t)ctx->stream);
+  put64((int64_t)(intptr_t)ctx->nccl_comm); put64(ctx->n_reads); put64((int64_t)ctx->n_files);
+  put64((int64_t)ctx->n_bam); put64((int64_t)ctx->n_paf);
+  for (size_t i = 0; i < ctx->n_files; i++) {
+    const FileTable& f = ctx->files[i];
+    put64(f.paf >= 0 ? 2 : f.kind); put64(f.src); put64(f.paf); put64(f.paf >= 0 ? 0 : f.n);
+  }
+  for (size_t i = 0; i < ctx->n_bam; i++) { put64(ctx->bam[i].n); put64(ctx->bam[i].n_ops); put64(ctx->bam[i].n_dense); }
+  for (size_t i = 0; i < ctx->n_paf; i++) put64(ctx->paf[i].n);
+  return sig;
+}
+
+static int pipeline_enqueue(gci_ctx* ctx, const PipeArgs& a, PipeOut* out) {
+  GCI_TRY(reset_err(ctx));
+  GCI_TRY(gci_run_paf_legs(ctx, a.map_qual, a.mq_cutoff, a.ip));
+  for (size_t i = 0; i < ctx->n_files; i++)
+    if (ctx->files[i].kind == 0)
+      GCI_TRY(gci_run_bam_leg(ctx, (int)i, ctx->files[i].src, a.map_qual, a.mq_cutoff, a.ip, a.cp));
+  GCI_TRY(gci_run_join(ctx, a.op));
+  ctx->filtered = true;
+  GCI_TRY(gci_depth_enqueue(ctx, a.track, a.flank_len, a.lo, a.hi));
+  Track& t = ctx->track[a.track];
+  const int64_t res_bound = 3 * a.n_sel + 1 + std::max<int64_t>(t.iv_cap, 4096) + a.n_sel;
+  const size_t need = 8 * (size_t)(4 + (a.n_sel + 3) + res_bound + a.row_n * a.world);
+  if (ctx->pipe_pin_cap < need) {
+    ctx->alloc_gen++;
+    if (ctx->capturing) ctx->capture_abort = true;
+    if (ctx->pipe_pin) cudaFreeHost(ctx->pipe_pin);
+    ctx->pipe_pin = nullptr;
+    ctx->pipe_pin_cap = 0;
+    if (cudaHostAlloc(&ctx->pipe_pin, need, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      return ctx->fail(GCI_E_NOMEM, "pinned allocation failed");
+    }
+    ctx->pipe_pin_cap = need;
+  }
+  pipeline_layout(ctx, a, t, 0, 0, out);
+  GCI_TRY(gci_scan_enqueue(ctx, a.track, a.lo, a.hi, a.flank_len, out->h_off));
+  ctx->stage_begin(GCI_ST_SCORE);
+  GCI_TRY(gci_launch_score_kernels(ctx, t, a.dp, a.flank_len, &out->no, &out->n_slots, true));
+  if (a.with_rows) GCI_TRY(gci_enqueue_genome_row(ctx, t, out->no, a.sum_len, a.cap, out->h_rows));
+  GCI_TRY(gci_d2h(ctx, out->h_res, ctx->tmp[1].p, 8 * (size_t)(3 * out->no + 1 + out->n_slots)));
+  GCI_TRY(gci_d2h(ctx, out->h_err, ctx->d_err.p, 4 * sizeof(unsigned long long)));
+  ctx->stage_end();
+  return GCI_OK;
+}
+
+extern "C" {
+
 // filter -> depth -> scan -> score terms with ONE host synchronisation: nothing between the stages needs the
 // host (the interval buffers keep their capacity from earlier scans; if a run produces more intervals than
 // fit, the scan + score part is redone through the synchronous entry points).
@@ -1124,78 +1210,104 @@ int gci_pipeline_row(gci_ctx* ctx, int32_t track, int32_t map_qual, int32_t mq_c
                      int64_t* depth_sums, int64_t sum_len, int64_t cap, int64_t* rows) {
   if (!ctx || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
   if (rows && (!ctx->nccl_comm || cap < 1)) return ctx->fail(GCI_E_ARG, "gci_pipeline_row: gci_comm_init / cap missing");
-  const int64_t row_n = rows ? 4 + cap : 0;
-  const int world = rows ? ctx->comm_world : 0;
   cudaSetDevice(ctx->device);
   if (ctx->n_files == 0) return ctx->fail(GCI_E_ARG, "gci_pipeline: no files uploaded");
-  int64_t n_sel = 0;
-  for (int c = 0; c < ctx->n_contigs; c++) n_sel += ctx->selected[c] ? 1 : 0;
-  if (n_sel == 0) return ctx->fail(GCI_E_ARG, "gci_pipeline: no contigs");
-  GCI_TRY(reset_err(ctx));
-  GCI_TRY(gci_run_paf_legs(ctx, map_qual, mq_cutoff, iden_percent));
-  for (size_t i = 0; i < ctx->n_files; i++)
-    if (ctx->files[i].kind == 0)
-      GCI_TRY(gci_run_bam_leg(ctx, (int)i, ctx->files[i].src, map_qual, mq_cutoff, iden_percent, clip_percent));
-  GCI_TRY(gci_run_join(ctx, ovlp_percent));
-  ctx->filtered = true;
-  GCI_TRY(gci_depth(ctx, track, flank_len, lo, hi));
+  PipeArgs a;
+  a.track = track; a.map_qual = map_qual; a.mq_cutoff = mq_cutoff; a.flank_len = flank_len; a.lo = lo; a.hi = hi;
+  a.ip = iden_percent; a.cp = clip_percent; a.op = ovlp_percent; a.dp = dist_percent;
+  a.with_rows = rows != nullptr; a.sum_len = sum_len; a.cap = cap;
+  a.row_n = rows ? 4 + cap : 0;
+  a.world = rows ? ctx->comm_world : 0;
+  a.n_sel = 0;
+  for (int c = 0; c < ctx->n_contigs; c++) a.n_sel += ctx->selected[c] ? 1 : 0;
+  if (a.n_sel == 0) return ctx->fail(GCI_E_ARG, "gci_pipeline: no contigs");
   Track& t = ctx->track[track];
-  // persistent pinned block: [err 4 x u64 | owner_off n_sel+3 | score result]
-  const int64_t res_bound = 3 * n_sel + 1 + std::max<int64_t>(t.iv_cap, 4096) + n_sel;
-  const size_t need = 8 * (size_t)(4 + (n_sel + 3) + res_bound + row_n * world);
-  if (ctx->pipe_pin_cap < need) {
-    if (ctx->pipe_pin) cudaFreeHost(ctx->pipe_pin);
-    ctx->pipe_pin = nullptr;
-    ctx->pipe_pin_cap = 0;
-    if (cudaHostAlloc(&ctx->pipe_pin, need, cudaHostAllocDefault) != cudaSuccess) {
-      cudaGetLastError();
-      return ctx->fail(GCI_E_NOMEM, "pinned allocation failed");
+
+  // ---- enqueue: eagerly, or as one graph launch when this exact step has been seen before ----
+  std::vector<char> sig;
+  const bool graphs = !ctx->timing && ctx->graph_ok;
+  if (graphs) sig = pipeline_signature(ctx, a);
+  PipeOut out;
+  if (graphs && ctx->pipe_exec && sig == ctx->pipe_sig) {
+    GCI_CUDA_TRY(ctx, cudaGraphLaunch(ctx->pipe_exec, ctx->stream));
+    ctx->graph_replays++;
+    ctx->launches += ctx->pipe_launches;
+    ctx->filtered = true;
+    pipeline_layout(ctx, a, t, ctx->pipe_no, ctx->pipe_slots, &out);
+  } else {
+    ctx->drop_graph();
+    bool done = false;
+    if (graphs && sig == ctx->pipe_sig_seen && sig != ctx->pipe_sig_bad) {
+      // second identical step: record it.  Everything it allocates exists since the first one; if a buffer
+      // moves or a host->device copy shows up all the same, the capture is thrown away.
+      const int64_t launches0 = ctx->launches;
+      const uint64_t gen0 = ctx->alloc_gen;
+      ctx->capture_abort = false;
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+      if (ok) {
+        ctx->capturing = true;
+        const int rc = pipeline_enqueue(ctx, a, &out);
+        ctx->capturing = false;
+        ok = cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && graph != nullptr;
+        ok = ok && rc == GCI_OK && !ctx->capture_abort && gen0 == ctx->alloc_gen;
+        ok = ok && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+      }
+      if (ok && cudaGraphLaunch(exec, ctx->stream) == cudaSuccess) {
+        ctx->pipe_exec = exec;
+        ctx->pipe_sig = sig;
+        ctx->pipe_launches = ctx->launches - launches0;
+        ctx->pipe_no = out.no;
+        ctx->pipe_slots = out.n_slots;
+        ctx->graph_replays++;
+        done = true;
+      } else {
+        if (exec) cudaGraphExecDestroy(exec);
+        cudaGetLastError();
+        ctx->launches = launches0;
+        ctx->pipe_sig_bad = sig;          // do not try again for this step shape
+      }
     }
-    ctx->pipe_pin_cap = need;
+    if (!done) GCI_TRY(pipeline_enqueue(ctx, a, &out));
+    if (graphs) ctx->pipe_sig_seen = graphs && !done ? pipeline_signature(ctx, a) : sig;
   }
-  unsigned long long* h_err = (unsigned long long*)ctx->pipe_pin;
-  int64_t* h_off = (int64_t*)(h_err + 4);
-  int64_t* h_res = h_off + (n_sel + 3);
-  GCI_TRY(gci_scan_enqueue(ctx, track, lo, hi, flank_len, h_off));
-  int64_t no = 0, n_slots = 0;
-  ctx->stage_begin(GCI_ST_SCORE);
-  GCI_TRY(gci_launch_score_kernels(ctx, t, dist_percent, flank_len, &no, &n_slots, true));
-  int64_t* h_rows = h_res + res_bound;
-  if (rows) GCI_TRY(gci_enqueue_genome_row(ctx, t, no, sum_len, cap, h_rows));
-  GCI_TRY(gci_d2h(ctx, h_res, ctx->tmp[1].p, 8 * (size_t)(3 * no + 1 + n_slots)));
-  GCI_TRY(gci_d2h(ctx, h_err, ctx->d_err.p, 4 * sizeof(unsigned long long)));
-  ctx->stage_end();
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  if (h_err[0] != 0) {
+
+  // ---- finish on the host ----
+  const int64_t no = out.no;
+  if (out.h_err[0] != 0) {
     ctx->filtered = false;
     unsigned long long dummy;
     return check_err(ctx, "gci_pipeline", &dummy);
   }
-  ctx->n_survivors = (int64_t)h_err[2];
+  ctx->n_survivors = (int64_t)out.h_err[2];
   if (n_survivors) *n_survivors = ctx->n_survivors;
   bool overflow = false;
-  GCI_TRY(gci_scan_finish(ctx, track, h_off, &overflow));
+  GCI_TRY(gci_scan_finish(ctx, track, out.h_off, &overflow));
   if (overflow) {
     // rare: redo the scan with grown buffers and the score terms through the synchronous entry points
+    ctx->drop_graph();
     GCI_TRY(gci_scan(ctx, track, lo, hi, flank_len, n_intervals));
     if (rows) return gci_genome_row(ctx, track, dist_percent, flank_len, sum_len, cap, n50, n_ctg, depth_sums, rows);
     return gci_score_terms_sums(ctx, track, dist_percent, flank_len, n50, n_ctg, 0, nullptr, nullptr, depth_sums);
   }
   if (rows) {
-    memcpy(rows, h_rows, 8 * (size_t)row_n * world);
-    for (int r = 0; r < world; r++)
-      if (rows[(size_t)r * row_n + 3] > cap)
+    memcpy(rows, out.h_rows, 8 * (size_t)a.row_n * a.world);
+    for (int r = 0; r < a.world; r++)
+      if (rows[(size_t)r * a.row_n + 3] > cap)
         return ctx->fail(GCI_E_ARG, "gci_pipeline_row: rank %d has more curated lengths than cap", r);
   }
   if (n_intervals) *n_intervals = t.n_intervals;
   long long all_c = 0, all_d = 0;
   for (int64_t o = 0; o < no; o++) {
-    if (n_ctg) n_ctg[o] = h_res[no + 1 + o];
-    if (depth_sums) depth_sums[o] = h_res[2 * no + 1 + o];
-    all_c += h_res[no + 1 + o];
-    all_d += h_res[2 * no + 1 + o];
+    if (n_ctg) n_ctg[o] = out.h_res[no + 1 + o];
+    if (depth_sums) depth_sums[o] = out.h_res[2 * no + 1 + o];
+    all_c += out.h_res[no + 1 + o];
+    all_d += out.h_res[2 * no + 1 + o];
   }
-  if (n50) memcpy(n50, h_res, 8 * (size_t)(no + 1));
+  if (n50) memcpy(n50, out.h_res, 8 * (size_t)(no + 1));
   if (n_ctg) n_ctg[no] = all_c;
   if (depth_sums) depth_sums[no] = all_d;
   return GCI_OK;

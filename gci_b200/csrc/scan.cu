@@ -277,10 +277,10 @@ struct RunWin {
   int64_t n_words;  // words of the layout: covers [w0 * 32, hi] inclusive
 };
 
-__device__ __forceinline__ RunWin load_win(int64_t o, const int32_t* w_contig, const int64_t* w_lo, const int64_t* w_hi,
-                                           const int64_t* lay_w0, const int64_t* tile_off) {
+__device__ __forceinline__ RunWin load_win(int64_t o, const int64_t* w_lo, const int64_t* w_hi, const int64_t* lay_w0,
+                                           const int64_t* lay_g0) {
   RunWin w;
-  w.g0 = tile_off[w_contig[o]] * GCI_TILE;
+  w.g0 = lay_g0[o];
   w.lo = w_lo[o];
   w.hi = w_hi[o];
   w.w0 = lay_w0[o];
@@ -306,33 +306,51 @@ __device__ __forceinline__ uint32_t win_word(const uint32_t* __restrict__ flags,
 constexpr int RUN_THREADS = 256;
 constexpr int RUN_WPT = GCI_RUN_CHUNK_WORDS / RUN_THREADS;   // words per thread (8)
 
-// chunk -> owner by binary search on chunk_off[n_owners+1]
+// chunk -> owner through a host-built table (the chunk layout only depends on the contig table / regions):
+// one load instead of a binary search, and the contig's first flag word comes with the layout, so a CTA sees
+// two dependent global loads before its flag words instead of eight.
+// WRITE pass: chunks without a run start or end (almost all of them) leave after reading their counts.
 template <bool WRITE>
 __global__ void __launch_bounds__(RUN_THREADS)
-runs_kernel(const uint32_t* __restrict__ flags, int64_t n_owners, const int64_t* __restrict__ chunk_off,
-            const int32_t* __restrict__ w_contig, const int64_t* __restrict__ w_lo, const int64_t* __restrict__ w_hi,
-            const int64_t* __restrict__ lay_w0, const int64_t* __restrict__ tile_off, int2* __restrict__ cnt,
+runs_kernel(const uint32_t* __restrict__ flags, const int32_t* __restrict__ chunk_owner,
+            const int64_t* __restrict__ chunk_off, const int64_t* __restrict__ w_lo, const int64_t* __restrict__ w_hi,
+            const int64_t* __restrict__ lay_w0, const int64_t* __restrict__ lay_g0, int2* __restrict__ cnt,
             const longlong2* __restrict__ off, int32_t* __restrict__ iv_start, int32_t* __restrict__ iv_end,
             int64_t cap) {
   __shared__ int s_ws[RUN_THREADS / 32], s_we[RUN_THREADS / 32];
   const int64_t chunk = blockIdx.x;
-  const int64_t o = upper_bound_minus1<int64_t>(chunk_off, n_owners + 1, chunk);
-  const RunWin w = load_win(o, w_contig, w_lo, w_hi, lay_w0, tile_off);
+  if (WRITE) {
+    const int2 c = cnt[chunk];
+    if (c.x == 0 && c.y == 0) return;
+  }
+  const int64_t o = chunk_owner[chunk];
+  const RunWin w = load_win(o, w_lo, w_hi, lay_w0, lay_g0);
   const int64_t j0 = (chunk - chunk_off[o]) * GCI_RUN_CHUNK_WORDS + (int64_t)threadIdx.x * RUN_WPT;
-  uint32_t st[RUN_WPT], en[RUN_WPT];
+  uint32_t st[RUN_WPT], en[RUN_WPT], m[RUN_WPT];
   int ns = 0, ne = 0;
-  uint32_t prev = win_word(flags, w, j0 - 1);
+  uint32_t prev;
+  // my 8 words and the one before them lie completely inside the window: two 16-byte loads, no masking
+  const int64_t p0w = (w.w0 + j0) << 5;
+  const int64_t gw = (w.g0 >> 5) + w.w0 + j0;
+  if (j0 >= 1 && j0 + RUN_WPT <= w.n_words && p0w - 32 >= w.lo && p0w + RUN_WPT * 32 <= w.hi && (gw & 3) == 0) {
+    const uint4 a = *reinterpret_cast<const uint4*>(flags + gw), b = *reinterpret_cast<const uint4*>(flags + gw + 4);
+    prev = flags[gw - 1];
+    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+  } else {
+    prev = win_word(flags, w, j0 - 1);
+#pragma unroll
+    for (int k = 0; k < RUN_WPT; k++) m[k] = win_word(flags, w, j0 + k);
+  }
 #pragma unroll
   for (int k = 0; k < RUN_WPT; k++) {
-    const uint32_t m = win_word(flags, w, j0 + k);
-    const uint32_t sh = (m << 1) | (prev >> 31);
-    st[k] = m & ~sh;
-    en[k] = ~m & sh;
+    const uint32_t sh = (m[k] << 1) | (prev >> 31);
+    st[k] = m[k] & ~sh;
+    en[k] = ~m[k] & sh;
     // an end can only be reported on a word that exists in the layout (positions <= hi)
     if (j0 + k >= w.n_words) en[k] = 0u;
     ns += __popc(st[k]);
     ne += __popc(en[k]);
-    prev = m;
+    prev = m[k];
   }
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const int is = warp_incl_scan(ns, lane), ie = warp_incl_scan(ne, lane);
@@ -417,15 +435,27 @@ runs_scan_kernel(const int2* __restrict__ cnt, int64_t n_chunks, longlong2* __re
 static int extract_runs(gci_ctx* ctx, Track& t, const std::vector<int64_t>& lay_lo, const std::vector<int64_t>& h_hi,
                         int64_t* n_intervals, int64_t* defer_pin = nullptr) {
   const int64_t n_owners = t.n_owners;
-  std::vector<int64_t> lay(2 * (n_owners + 1), 0);     // [chunk_off (n+1) | w0 (n) ...]
-  int64_t* chunk_off = lay.data();
-  int64_t* w0 = lay.data() + n_owners + 1;
-  for (int64_t o = 0; o < n_owners; o++) {
-    w0[o] = lay_lo[o] >> 5;
-    const int64_t nw = h_hi[o] > lay_lo[o] ? (h_hi[o] >> 5) - w0[o] + 1 : 0;
-    chunk_off[o + 1] = chunk_off[o] + (nw + GCI_RUN_CHUNK_WORDS - 1) / GCI_RUN_CHUNK_WORDS;
+  // layout, int64 words: [chunk_off (n+1) | w0 (n) | g0 (n) | chunk_owner (int32 x n_chunks)]
+  std::vector<int64_t> lay(3 * (n_owners + 1), 0);
+  {
+    int64_t* chunk_off = lay.data();
+    int64_t* w0 = lay.data() + n_owners + 1;
+    int64_t* g0 = w0 + n_owners;
+    for (int64_t o = 0; o < n_owners; o++) {
+      w0[o] = lay_lo[o] >> 5;
+      g0[o] = ctx->pos_off[t.owner_contig[o]];
+      const int64_t nw = h_hi[o] > lay_lo[o] ? (h_hi[o] >> 5) - w0[o] + 1 : 0;
+      chunk_off[o + 1] = chunk_off[o] + (nw + GCI_RUN_CHUNK_WORDS - 1) / GCI_RUN_CHUNK_WORDS;
+    }
   }
-  const int64_t n_chunks = chunk_off[n_owners];
+  const int64_t n_chunks = lay[n_owners];
+  const size_t lay_head = lay.size();
+  if (n_chunks > 0 && n_chunks < (int64_t(1) << 31)) {
+    lay.resize(lay_head + (size_t)(n_chunks + 1) / 2, 0);
+    int32_t* owner = reinterpret_cast<int32_t*>(lay.data() + lay_head);
+    for (int64_t o = 0; o < n_owners; o++)
+      for (int64_t c = lay[o]; c < lay[o + 1]; c++) owner[c] = (int32_t)o;
+  }
   t.h_owner_off.assign(n_owners + 1, 0);
   t.n_intervals = 0;
   if (n_intervals) *n_intervals = 0;
@@ -442,6 +472,8 @@ static int extract_runs(gci_ctx* ctx, Track& t, const std::vector<int64_t>& lay_
   }
   const int64_t* d_chunk_off = ctx->chunk_off.as<int64_t>();
   const int64_t* d_w0 = d_chunk_off + n_owners + 1;
+  const int64_t* d_g0 = d_w0 + n_owners;
+  const int32_t* d_chunk_owner = reinterpret_cast<const int32_t*>(d_chunk_off + lay_head);
   GCI_TRY(ctx->ensure(ctx->chunk_cnt, sizeof(int2) * (size_t)n_chunks));
   GCI_TRY(ctx->ensure(ctx->scan_tmp, sizeof(longlong2) * (size_t)n_chunks));
   int2* cnt = ctx->chunk_cnt.as<int2>();
@@ -452,16 +484,15 @@ static int extract_runs(gci_ctx* ctx, Track& t, const std::vector<int64_t>& lay_
     t.iv_cap = 4096;
   }
   runs_kernel<false><<<(unsigned)n_chunks, RUN_THREADS, 0, ctx->stream>>>(
-      t.flags.as<uint32_t>(), n_owners, d_chunk_off, t.win_contig.as<int32_t>(), t.win_lo.as<int64_t>(),
-      t.win_hi.as<int64_t>(), d_w0, ctx->d_tile_off.as<int64_t>(), cnt, nullptr, nullptr, nullptr, 0);
+      t.flags.as<uint32_t>(), d_chunk_owner, d_chunk_off, t.win_lo.as<int64_t>(), t.win_hi.as<int64_t>(), d_w0, d_g0,
+      cnt, nullptr, nullptr, nullptr, 0);
   GCI_LAUNCH_CHECK(ctx);
   runs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, n_chunks, off, n_owners, d_chunk_off, t.owner_off.as<int64_t>());
   GCI_LAUNCH_CHECK(ctx);
   if (defer_pin) {
     runs_kernel<true><<<(unsigned)n_chunks, RUN_THREADS, 0, ctx->stream>>>(
-        t.flags.as<uint32_t>(), n_owners, d_chunk_off, t.win_contig.as<int32_t>(), t.win_lo.as<int64_t>(),
-        t.win_hi.as<int64_t>(), d_w0, ctx->d_tile_off.as<int64_t>(), nullptr, off, t.iv_start.as<int32_t>(),
-        t.iv_end.as<int32_t>(), t.iv_cap);
+        t.flags.as<uint32_t>(), d_chunk_owner, d_chunk_off, t.win_lo.as<int64_t>(), t.win_hi.as<int64_t>(), d_w0, d_g0,
+        cnt, off, t.iv_start.as<int32_t>(), t.iv_end.as<int32_t>(), t.iv_cap);
     GCI_LAUNCH_CHECK(ctx);
     GCI_TRY(gci_d2h(ctx, defer_pin, t.owner_off.p, sizeof(int64_t) * (size_t)(n_owners + 3)));
     return GCI_OK;
@@ -470,9 +501,8 @@ static int extract_runs(gci_ctx* ctx, Track& t, const std::vector<int64_t>& lay_
   if (!h) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
   for (int attempt = 0; attempt < 2; attempt++) {
     runs_kernel<true><<<(unsigned)n_chunks, RUN_THREADS, 0, ctx->stream>>>(
-        t.flags.as<uint32_t>(), n_owners, d_chunk_off, t.win_contig.as<int32_t>(), t.win_lo.as<int64_t>(),
-        t.win_hi.as<int64_t>(), d_w0, ctx->d_tile_off.as<int64_t>(), nullptr, off, t.iv_start.as<int32_t>(),
-        t.iv_end.as<int32_t>(), t.iv_cap);
+        t.flags.as<uint32_t>(), d_chunk_owner, d_chunk_off, t.win_lo.as<int64_t>(), t.win_hi.as<int64_t>(), d_w0, d_g0,
+        cnt, off, t.iv_start.as<int32_t>(), t.iv_end.as<int32_t>(), t.iv_cap);
     GCI_LAUNCH_CHECK(ctx);
     if (attempt == 0) {
       GCI_TRY(gci_d2h(ctx, h, t.owner_off.p, sizeof(int64_t) * (size_t)(n_owners + 3)));
@@ -688,6 +718,7 @@ static int scan_genome(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int3
                        int64_t* defer_pin);
 
 int gci_scan(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int32_t flank_len, int64_t* n_intervals) {
+  if (ctx) ctx->epoch++;
   return scan_genome(ctx, track, lo, hi, flank_len, n_intervals, nullptr);
 }
 
@@ -774,6 +805,7 @@ int gci_scan_windows(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int64_
   if (!ctx || track < 0 || track >= GCI_MAX_TRACKS || n_windows < 0) return GCI_E_ARG;
   if (n_windows && (!contig || !start || !end)) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
+  ctx->epoch++;
   Track& t = ctx->track[track];
   if (!t.allocated) return ctx->fail(GCI_E_ARG, "gci_scan_windows: track %d holds no depth", track);
   if (!t.flags_valid || t.flags_lo != lo || t.flags_hi != hi) GCI_TRY(gci_compute_flags(ctx, track, lo, hi));
@@ -813,6 +845,7 @@ int gci_load_intervals(gci_ctx* ctx, int32_t track, int64_t n_owners, const int3
   if (!ctx || track < 0 || track >= GCI_MAX_TRACKS || n_owners < 0 || !owner_off) return GCI_E_ARG;
   if (n_owners && !contig) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
+  ctx->epoch++;
   Track& t = ctx->track[track];
   const int64_t n = owner_off[n_owners];
   if (n && (!start || !end)) return GCI_E_ARG;
@@ -845,6 +878,7 @@ int gci_score_terms_sums(gci_ctx* ctx, int32_t track, double dist_percent, int32
                          int64_t* depth_sums) {
   if (!ctx || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
+  ctx->epoch++;
   Track& t = ctx->track[track];
   int64_t no = 0, n_slots = 0;
   ctx->stage_begin(GCI_ST_SCORE);

@@ -57,6 +57,12 @@ void gci_destroy(gci_ctx* ctx);
 const char* gci_last_error(gci_ctx* ctx);
 /* run on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = the context's own */
 int gci_set_stream(gci_ctx* ctx, void* cuda_stream);
+/* Stage timers (gci_stage_ms) on / off; on by default.  With the timers off gci_pipeline and
+   gci_pipeline_row record the step into a CUDA graph the second time they see the same arguments and
+   read-set shape and replay it afterwards (one launch instead of ~40 stream operations); anything that
+   changes the inputs of the step (contigs, uploads of another shape, another entry point touching the
+   track) drops the graph.  GCI_GRAPH=0 in the environment disables the replay. */
+int gci_set_timing(gci_ctx* ctx, int32_t on);
 int gci_sync(gci_ctx* ctx);
 /* pinned host memory so H2D/D2H copies run at PCIe speed */
 void* gci_host_alloc(uint64_t bytes);
@@ -66,6 +72,7 @@ int gci_stage_reset(gci_ctx* ctx);
 int gci_stage_ms(gci_ctx* ctx, int stage, double* ms, int64_t* launches);
 int64_t gci_kernel_launches(gci_ctx* ctx);       /* kernels launched by this context so far */
 int64_t gci_device_bytes(gci_ctx* ctx);          /* device memory currently owned */
+int64_t gci_graph_replays(gci_ctx* ctx);         /* gci_pipeline steps that ran as one CUDA graph launch */
 
 /* ---- contig table: GCI.py:201-207 (targets_length / depths keys, --chrs selection) -------- */
 /* lengths[n]; selected[n] (NULL = all): contigs named by --chrs; unselected contigs get no

@@ -505,3 +505,73 @@ def test_cigar_stats_match_op_sums(ctx, kind):
     assert np.array_equal(got.astype(np.int64), want & 0xFFFFFFFF)
     rlen = want[:, 0] + want[:, 2] + want[:, 3]
     assert np.array_equal(got_end.astype(np.int64), t.ref_start.astype(np.int64) + np.maximum(rlen, 1))
+
+
+def test_pipeline_graph_replay_follows_the_data(ctx):
+    """stage timers off: gci_pipeline records the step into a CUDA graph on its second run and replays it; the
+    replay must see new record CONTENTS of the same shape, and any change of shape / arguments must drop it"""
+    from gci_b200._lib import Context
+    lengths = [150_000, 60_000]
+    d = synth.make_reads(synth.SynthSpec(lengths, coverage=20, seed=909, read_mean=5000, read_min=800, read_max=12000,
+                                         hole_fraction=0.02, hole_mean=300))
+    b2 = synth.second_aligner(d, seed=4)
+    rng = np.random.default_rng(5)
+
+    def variant(t, k):
+        if k == 0:
+            return t
+        mapq = t.mapq.copy()
+        mapq[rng.random(len(mapq)) < 0.2 * k] = 5          # same shape, other survivors
+        return AlnTable(t.ref_id, t.ref_start, mapq, t.flag, t.nm, t.qlen, t.read_id, t.cigar_off, t.cigar)
+
+    def staged(files, ts, fl):
+        ctx.set_contigs(lengths)
+        ctx.reads_begin(d.n_reads)
+        for t in files:
+            ctx.upload_bam(t)
+        n_surv = ctx.filter()
+        ctx.depth(0, fl, -1, ts)
+        n_iv = ctx.scan(0, -1, ts, fl)
+        a50, actg, _, _, asum = ctx.score_terms(0, 2, n_iv, 0.005, fl, with_sums=True)
+        return n_surv, n_iv, a50, actg, asum, [ctx.fetch_depth(0, i) for i in range(2)], ctx.fetch_intervals(0, 2)
+
+    c = Context(0)
+    try:
+        c.set_timing(False)
+        c.set_contigs(lengths)
+        replays = 0
+        for k in range(4):                      # four read sets of one shape, four steps each
+            files = [variant(d.bam, k), b2]
+            want = staged(files, 1, 15)
+            for rep in range(4):
+                c.reads_begin(d.n_reads)
+                for t in files:
+                    c.upload_bam(t)
+                got = c.pipeline(0, 2, hi=1)
+                assert got[0] == want[0] and got[1] == want[1], (k, rep)
+                assert all((x == y).all() for x, y in zip(got[2:5], want[2:5])), (k, rep)
+                assert all(np.array_equal(c.fetch_depth(0, i), want[5][i]) for i in range(2)), (k, rep)
+                assert all((x == y).all() for x, y in zip(c.fetch_intervals(0, 2), want[6])), (k, rep)
+        replays = c.graph_replays
+        assert replays >= 12, replays           # everything after the first two steps ran as a graph
+        # other arguments: eager again, then a new graph
+        want = staged([variant(d.bam, 0), b2], 3, 20)
+        for rep in range(3):
+            got = c.pipeline(0, 2, hi=3, flank_len=20)
+            assert got[0] == want[0] and got[1] == want[1]
+            assert all((x == y).all() for x, y in zip(got[2:5], want[2:5]))
+        # other shape (one file instead of two)
+        want = staged([d.bam], 1, 15)
+        for rep in range(3):
+            c.reads_begin(d.n_reads)
+            c.upload_bam(d.bam)
+            got = c.pipeline(0, 2, hi=1)
+            assert got[0] == want[0] and got[1] == want[1]
+            assert all(np.array_equal(c.fetch_depth(0, i), want[5][i]) for i in range(2))
+        # an entry point that touches the track between two steps drops the graph, results stay right
+        c.scan_windows(0, [0], [1000], [50_000], lo=-1, hi=1)
+        got = c.pipeline(0, 2, hi=1)
+        assert got[1] == want[1] and all((x == y).all() for x, y in zip(c.fetch_intervals(0, 2), want[6]))
+        assert c.graph_replays > replays
+    finally:
+        c.close()
