@@ -149,6 +149,8 @@ struct gci_ctx {
   DevBuf highq_base;                // uint8[n_reads]  marks that came with uploaded tables (kept across runs)
   DevBuf surv_contig, surv_start, surv_end;   // int32[n_reads]; contig < 0 = not a survivor
   bool filtered = false;
+  // the join kernel already counted the depth events of (track, flank) into the tile table (gci_pipeline)
+  int32_t counted_track = -1, counted_flank = 0;
   int64_t n_survivors = 0;
   std::vector<int32_t> name_rank;   // host copy for the PAF election tie-break
 
@@ -216,6 +218,8 @@ int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip);
 int gci_run_join(gci_ctx* ctx, double op);
 int gci_alloc_track(gci_ctx* ctx, int track);
 int gci_depth_enqueue(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo, int32_t hi);   // depth.cu
+int gci_depth_prepare(gci_ctx* ctx, int32_t track, int32_t flank_len, struct BucketArgs* bk);        // depth.cu
+int gci_run_join_counting(gci_ctx* ctx, double op, int32_t track, int32_t flank_len);                // filter.cu
 int gci_compute_flags(gci_ctx* ctx, int track, int32_t lo, int32_t hi);
 int gci_launch_score_kernels(gci_ctx* ctx, Track& t, double dist_percent, int32_t flank_len, int64_t* n_owners,
                              int64_t* n_slots, bool pending);   // scan.cu: result stays in ctx->tmp[1], no sync
@@ -272,4 +276,65 @@ __device__ __forceinline__ long long py_slice_index(long long i, long long len) 
     i = len;
   }
   return i;
+}
+
+// ---- survivor -> depth events (shared by the join kernel and the depth stage) -----------------------
+// Every survivor contributes +1 at a = start+fl and -1 at b = end-fl+1, both normalised like a Python slice
+// (GCI.py:304-306); the events are bucketed per depth tile (depth.cu).
+struct Slice { long long a, b; int64_t tile_a, tile_b; bool ok; };
+
+__device__ __forceinline__ Slice survivor_slice(int32_t c, int32_t s, int32_t e, int32_t fl,
+                                                const int64_t* __restrict__ len, const int64_t* __restrict__ tile_off) {
+  Slice r;
+  r.ok = false;
+  if (c < 0) return r;
+  const long long L = len[c];
+  r.a = py_slice_index((long long)s + fl, L);
+  r.b = py_slice_index((long long)e - fl + 1, L);
+  if (r.a >= r.b) return r;
+  const int64_t t0 = tile_off[c];
+  if (tile_off[c + 1] == t0) return r;   // contig without depth storage (not selected / not owned)
+  r.ok = true;
+  r.tile_a = t0 + r.a / GCI_TILE;
+  r.tile_b = t0 + r.b / GCI_TILE;
+  return r;
+}
+
+constexpr unsigned long long EV_PLUS = 1ull + (1ull << 32);            // count+1, net+1
+constexpr unsigned long long EV_MINUS = 1ull + 0xffffffff00000000ull;  // count+1, net-1
+
+struct BucketArgs {
+  int32_t fl;
+  const int64_t* len;
+  const int64_t* tile_off;
+  ulonglong2* tile_ps;     // NULL: no counting
+  long long* sums;         // per-contig depth sums
+};
+
+// count the two events of one survivor (c < 0: none) into the tile table and add its slice length to the
+// contig's depth sum; warp-collective: every lane of the warp must call it
+__device__ __forceinline__ void bucket_count_one(const BucketArgs& bk, int32_t c, int32_t s, int32_t e) {
+  long long covered = 0;
+  if (c >= 0) {
+    const Slice sl = survivor_slice(c, s, e, bk.fl, bk.len, bk.tile_off);
+    if (sl.ok) {
+      atomicAdd(&bk.tile_ps[sl.tile_a].x, EV_PLUS);
+      atomicAdd(&bk.tile_ps[sl.tile_b].x, EV_MINUS);
+      covered = sl.b - sl.a;
+    } else {
+      c = -1;
+    }
+  }
+  // sum of depth per contig = sum of slice lengths; aggregate per warp when the warp agrees on a contig
+  const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
+  if (act == 0) return;
+  const int leader = __ffs(act) - 1;
+  const int32_t c0 = __shfl_sync(0xffffffffu, c, leader);
+  const bool uniform = __all_sync(0xffffffffu, c < 0 || c == c0);
+  if (uniform) {
+    const long long t = warp_sum_ll(covered);
+    if ((threadIdx.x & 31) == leader) atomicAdd((unsigned long long*)(bk.sums + c0), (unsigned long long)t);
+  } else if (c >= 0) {
+    atomicAdd((unsigned long long*)(bk.sums + c), (unsigned long long)covered);
+  }
 }

@@ -17,58 +17,11 @@ int gci_scan_tile_pack(gci_ctx* ctx, ulonglong2* tile_ps, int64_t n);   // scan.
 // carried into it (high word: sum of all earlier nets; a contig's nets sum to zero, so the carry
 // restarts at 0 on every contig without any segmentation).
 
-struct Slice { long long a, b; int64_t tile_a, tile_b; bool ok; };
-
-__device__ __forceinline__ Slice survivor_slice(int32_t c, int32_t s, int32_t e, int32_t fl,
-                                                const int64_t* __restrict__ len, const int64_t* __restrict__ tile_off) {
-  Slice r;
-  r.ok = false;
-  if (c < 0) return r;
-  const long long L = len[c];
-  r.a = py_slice_index((long long)s + fl, L);
-  r.b = py_slice_index((long long)e - fl + 1, L);
-  if (r.a >= r.b) return r;
-  const int64_t t0 = tile_off[c];
-  if (tile_off[c + 1] == t0) return r;   // contig without depth storage (not selected / not owned)
-  r.ok = true;
-  r.tile_a = t0 + r.a / GCI_TILE;
-  r.tile_b = t0 + r.b / GCI_TILE;
-  return r;
-}
-
-constexpr unsigned long long EV_PLUS = 1ull + (1ull << 32);            // count+1, net+1
-constexpr unsigned long long EV_MINUS = 1ull + 0xffffffff00000000ull;  // count+1, net-1
-
 __global__ void bucket_count_kernel(uint32_t n_reads, const int32_t* __restrict__ sc, const int32_t* __restrict__ ss,
-                                    const int32_t* __restrict__ se, int32_t fl, const int64_t* __restrict__ len,
-                                    const int64_t* __restrict__ tile_off, ulonglong2* __restrict__ tile_ps,
-                                    long long* __restrict__ sums) {
+                                    const int32_t* __restrict__ se, BucketArgs bk) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  int32_t c = -1;
-  long long covered = 0;
-  if (r < n_reads) {
-    c = sc[r];
-    const Slice sl = survivor_slice(c, ss[r], se[r], fl, len, tile_off);
-    if (sl.ok) {
-      atomicAdd(&tile_ps[sl.tile_a].x, EV_PLUS);
-      atomicAdd(&tile_ps[sl.tile_b].x, EV_MINUS);
-      covered = sl.b - sl.a;
-    } else {
-      c = -1;
-    }
-  }
-  // sum of depth per contig = sum of slice lengths; aggregate per warp when the warp agrees on a contig
-  const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
-  if (act == 0) return;
-  const int leader = __ffs(act) - 1;
-  const int32_t c0 = __shfl_sync(0xffffffffu, c, leader);
-  const bool uniform = __all_sync(0xffffffffu, c < 0 || c == c0);
-  if (uniform) {
-    const long long t = warp_sum_ll(covered);
-    if ((threadIdx.x & 31) == leader) atomicAdd((unsigned long long*)(sums + c0), (unsigned long long)t);
-  } else if (c >= 0) {
-    atomicAdd((unsigned long long*)(sums + c), (unsigned long long)covered);
-  }
+  const bool in = r < n_reads;
+  bucket_count_one(bk, in ? sc[r] : -1, in ? ss[r] : 0, in ? se[r] : 0);
 }
 
 __global__ void bucket_fill_kernel(uint32_t n_reads, const int32_t* __restrict__ sc, const int32_t* __restrict__ ss,
@@ -435,11 +388,10 @@ int gci_compute_flags(gci_ctx* ctx, int track, int32_t lo, int32_t hi) {
   return GCI_OK;
 }
 
-// body of gci_depth; gci_pipeline calls it directly (it must not bump ctx->epoch)
-int gci_depth_enqueue(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo, int32_t hi) {
+// allocate the track and the tile table, zero the table and the depth sums; *bk describes the event counting
+// for whoever does it (bucket_count_kernel, or the join kernel in gci_pipeline)
+int gci_depth_prepare(gci_ctx* ctx, int32_t track, int32_t flank_len, BucketArgs* bk) {
   if (!ctx || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
-  cudaSetDevice(ctx->device);
-  if (!ctx->filtered) return ctx->fail(GCI_E_ARG, "gci_depth before gci_filter");
   Track& t = ctx->track[track];
   if (!t.allocated) {
     // allocate without the zero fill: every position of the track is written by the tile kernel
@@ -450,23 +402,48 @@ int gci_depth_enqueue(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo
     t.allocated = true;
   }
   const int64_t nt = ctx->n_tiles;
-  const uint32_t nr = ctx->n_reads;
+  memset(bk, 0, sizeof *bk);
   if (nt == 0) return GCI_OK;
   if (nt >= (int64_t(1) << 31)) return ctx->fail(GCI_E_ARG, "too many tiles");
   // one scratch block zeroed with one memset: per tile (pack u64, scan u64) interleaved + fill cursor u32
   GCI_TRY(ctx->ensure(ctx->tile_cnt, 20 * (size_t)nt));
-  GCI_TRY(ctx->ensure(ctx->events, 2 * 2 * (size_t)std::max<uint32_t>(1, nr)));
+  GCI_TRY(ctx->ensure(ctx->events, 2 * 2 * (size_t)std::max<uint32_t>(1, ctx->n_reads)));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->tile_cnt.p, 0, 20 * (size_t)nt, ctx->stream));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(t.sums.p, 0, sizeof(int64_t) * (size_t)ctx->n_contigs, ctx->stream));
+  bk->fl = flank_len;
+  bk->len = ctx->d_len.as<int64_t>();
+  bk->tile_off = ctx->d_tile_off.as<int64_t>();
+  bk->tile_ps = ctx->tile_cnt.as<ulonglong2>();
+  bk->sums = t.sums.as<long long>();
+  return GCI_OK;
+}
+
+// body of gci_depth; gci_pipeline calls it directly (it must not bump ctx->epoch)
+int gci_depth_enqueue(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo, int32_t hi) {
+  if (!ctx || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (!ctx->filtered) return ctx->fail(GCI_E_ARG, "gci_depth before gci_filter");
+  Track& t = ctx->track[track];
+  const int64_t nt = ctx->n_tiles;
+  const uint32_t nr = ctx->n_reads;
+  const bool counted = ctx->counted_track == track && ctx->counted_flank == flank_len;
+  ctx->counted_track = -1;
+  ctx->stage_begin(GCI_ST_BUCKET);
+  if (!counted) {
+    BucketArgs bk;
+    GCI_TRY(gci_depth_prepare(ctx, track, flank_len, &bk));
+    if (nr && nt) {
+      bucket_count_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(
+          nr, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(), bk);
+      GCI_LAUNCH_CHECK(ctx);
+    }
+  }
+  if (nt == 0) {
+    ctx->stage_end();
+    return GCI_OK;
+  }
   ulonglong2* tile_ps = ctx->tile_cnt.as<ulonglong2>();
   uint32_t* cursor = reinterpret_cast<uint32_t*>(tile_ps + nt);
-  ctx->stage_begin(GCI_ST_BUCKET);
-  GCI_CUDA_TRY(ctx, cudaMemsetAsync(tile_ps, 0, 20 * (size_t)nt, ctx->stream));
-  GCI_CUDA_TRY(ctx, cudaMemsetAsync(t.sums.p, 0, sizeof(int64_t) * (size_t)ctx->n_contigs, ctx->stream));
-  if (nr) {
-    bucket_count_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(
-        nr, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(), flank_len,
-        ctx->d_len.as<int64_t>(), ctx->d_tile_off.as<int64_t>(), tile_ps, t.sums.as<long long>());
-    GCI_LAUNCH_CHECK(ctx);
-  }
   GCI_TRY(gci_scan_tile_pack(ctx, tile_ps, nt));
   if (nr) {
     bucket_fill_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(

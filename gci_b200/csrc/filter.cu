@@ -475,7 +475,8 @@ struct JoinArgs {
 
 __global__ void join_kernel(JoinArgs a, uint32_t n_reads, const uint8_t* __restrict__ highq, double op,
                             int32_t* __restrict__ s_contig, int32_t* __restrict__ s_start, int32_t* __restrict__ s_end,
-                            unsigned long long* __restrict__ count, unsigned long long* __restrict__ err) {
+                            unsigned long long* __restrict__ count, unsigned long long* __restrict__ err,
+                            BucketArgs bk) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   bool have = false;
   int32_t c = -1, s = 0, e = 0;
@@ -530,6 +531,8 @@ __global__ void join_kernel(JoinArgs a, uint32_t n_reads, const uint8_t* __restr
   }
   const unsigned m = __ballot_sync(0xffffffffu, have);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+  // gci_pipeline: the depth events of the survivor are counted right here (no second pass over the survivors)
+  if (bk.tile_ps) bucket_count_one(bk, have ? c : -1, s, e);
 }
 
 // ================================================================================================
@@ -887,7 +890,15 @@ int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
   return GCI_OK;
 }
 
-int gci_run_join(gci_ctx* ctx, double op) {
+int gci_run_join(gci_ctx* ctx, double op) { return gci_run_join_counting(ctx, op, -1, 0); }
+
+// track >= 0: also count the depth events of (track, flank_len) into the tile table (gci_depth_enqueue then
+// skips its own counting pass)
+int gci_run_join_counting(gci_ctx* ctx, double op, int32_t track, int32_t flank_len) {
+  ctx->counted_track = -1;
+  BucketArgs bk;
+  memset(&bk, 0, sizeof bk);
+  if (track >= 0) GCI_TRY(gci_depth_prepare(ctx, track, flank_len, &bk));
   JoinArgs a;
   memset(&a, 0, sizeof a);
   a.n_files = (int)ctx->n_files;
@@ -916,10 +927,14 @@ int gci_run_join(gci_ctx* ctx, double op) {
   if (ctx->n_reads) {
     join_kernel<<<(ctx->n_reads + 255) / 256, 256, 0, ctx->stream>>>(
         a, ctx->n_reads, ctx->highq.as<uint8_t>(), op, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(),
-        ctx->surv_end.as<int32_t>(), cnt, ctx->d_err.as<unsigned long long>());
+        ctx->surv_end.as<int32_t>(), cnt, ctx->d_err.as<unsigned long long>(), bk);
     GCI_LAUNCH_CHECK(ctx);
   }
   ctx->stage_end();
+  if (track >= 0) {
+    ctx->counted_track = track;
+    ctx->counted_flank = flank_len;
+  }
   return GCI_OK;
 }
 
@@ -1160,7 +1175,7 @@ static int pipeline_enqueue(gci_ctx* ctx, const PipeArgs& a, PipeOut* out) {
   for (size_t i = 0; i < ctx->n_files; i++)
     if (ctx->files[i].kind == 0)
       GCI_TRY(gci_run_bam_leg(ctx, (int)i, ctx->files[i].src, a.map_qual, a.mq_cutoff, a.ip, a.cp));
-  GCI_TRY(gci_run_join(ctx, a.op));
+  GCI_TRY(gci_run_join_counting(ctx, a.op, a.track, a.flank_len));
   ctx->filtered = true;
   GCI_TRY(gci_depth_enqueue(ctx, a.track, a.flank_len, a.lo, a.hi));
   Track& t = ctx->track[a.track];

@@ -164,9 +164,20 @@ tile_reduce_kernel(const ulonglong2* __restrict__ ps, int64_t n, unsigned long l
   }
 }
 
+// block b first sums the block totals before it (at most a few thousand values: 10 Gbp = 4 768 blocks), so
+// no separate scan of the block totals is needed between the reduce and the apply pass
 __global__ void __launch_bounds__(SCAN_THREADS)
-tile_apply_kernel(ulonglong2* __restrict__ ps, int64_t n, const unsigned long long* __restrict__ block_off) {
+tile_apply_kernel(ulonglong2* __restrict__ ps, int64_t n, const unsigned long long* __restrict__ block_sums) {
   __shared__ unsigned long long s_w[SCAN_THREADS / 32];
+  __shared__ unsigned long long s_b[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned long long before = 0;
+  if (block_sums) {
+    for (int64_t i = threadIdx.x; i < (int64_t)blockIdx.x; i += SCAN_THREADS) before += block_sums[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(0xffffffffu, before, d);
+    if (lane == 0) s_b[w] = before;
+  }
   const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_ITEMS;
   unsigned long long item[SCAN_ITEMS], sum = 0;
 #pragma unroll
@@ -174,7 +185,6 @@ tile_apply_kernel(ulonglong2* __restrict__ ps, int64_t n, const unsigned long lo
     item[k] = base + k < n ? ps[base + k].x : 0ull;
     sum += item[k];
   }
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   unsigned long long incl = sum;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -185,7 +195,9 @@ tile_apply_kernel(ulonglong2* __restrict__ ps, int64_t n, const unsigned long lo
   __syncthreads();
   unsigned long long woff = 0;
   for (int j = 0; j < w; j++) woff += s_w[j];
-  unsigned long long run = (block_off ? block_off[blockIdx.x] : 0ull) + woff + incl - sum;
+  if (block_sums)
+    for (int j = 0; j < SCAN_THREADS / 32; j++) woff += s_b[j];
+  unsigned long long run = woff + incl - sum;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) {
     if (base + k < n) ps[base + k].y = run;
@@ -202,14 +214,10 @@ int gci_scan_tile_pack(gci_ctx* ctx, ulonglong2* tile_ps, int64_t n) {
     return GCI_OK;
   }
   DevBuf& sums = ctx->scan_lvl[6];
-  DevBuf& offs = ctx->scan_lvl[7];
   GCI_TRY(ctx->ensure(sums, 8 * (size_t)nb));
-  GCI_TRY(ctx->ensure(offs, 8 * (size_t)nb));
   tile_reduce_kernel<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(tile_ps, n, sums.as<unsigned long long>());
   GCI_LAUNCH_CHECK(ctx);
-  GCI_TRY((exclusive_scan<unsigned long long, unsigned long long>(ctx, sums.as<unsigned long long>(),
-                                                                  offs.as<unsigned long long>(), nb, nullptr, 0)));
-  tile_apply_kernel<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(tile_ps, n, offs.as<unsigned long long>());
+  tile_apply_kernel<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(tile_ps, n, sums.as<unsigned long long>());
   GCI_LAUNCH_CHECK(ctx);
   return GCI_OK;
 }
