@@ -7,7 +7,7 @@ O=gpurun_out
 mkdir -p $O
 step() { echo "== $1" | tee -a $O/${TAG}_steps.log; shift; "$@"; echo "   exit $?" | tee -a $O/${TAG}_steps.log; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/${TAG}_gpu.csv 2>&1
-step "pytest gpu" timeout 900 python -m pytest tests -x -q -m gpu > $O/${TAG}_pytest.log 2>&1
+step "pytest gpu" timeout 600 python -m pytest tests -x -q -m gpu > $O/${TAG}_pytest.log 2>&1
 tail -5 $O/${TAG}_pytest.log
 step "bench graph" timeout 400 python bench.py --steps 100 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
 step "bench eager" timeout 300 env GCI_GRAPH=0 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > $O/${TAG}_bench_eager.json 2> $O/${TAG}_bench_eager.err
