@@ -330,6 +330,51 @@ def make_filter_cases(ref):
         json.dump(meta, f, indent=1)
 
 
+def make_random_cases(ref, n_cases=16):
+    """Seeded random small cases over the whole argument space (gates, flank, threshold, -dp, file mixes, --chrs,
+    -R regions, contig lengths next to tile borders and below 2 * flank) -> filter_cases_rand.{npz,json}."""
+    store, meta = {}, {"cases": [], "reference_commit": "455e19c7"}
+    rng = np.random.default_rng(20240633)
+    combos = [("bam",), ("bam", "bam"), ("bam", "paf"), ("paf", "bam"), ("bam", "paf", "bam"), ("bam", "bam", "bam"),
+              ("paf", "paf", "bam")]
+    special = [1023, 1024, 1025, 2047, 2048, 2049, 3072, 4000, 40, 90]
+    for k in range(n_cases):
+        n_ctg = int(rng.integers(2, 5))
+        lengths = [int(rng.integers(6_000, 45_000)) for _ in range(n_ctg)]
+        lengths[int(rng.integers(0, n_ctg))] = int(rng.choice(special)) + (5000 if rng.random() < 0.5 else 0)
+        args = dict(map_qual=int(rng.choice([0, 10, 30, 45])), mq_cutoff=int(rng.choice([20, 50, 60])),
+                    iden_percent=float(rng.choice([0.8, 0.9, 0.99, 0.999])),
+                    clip_percent=float(rng.choice([0.0, 0.05, 0.1, 0.3])),
+                    ovlp_percent=float(rng.choice([0.0, 0.5, 0.9, 1.0])),
+                    flank_len=int(rng.choice([0, 1, 15, 15, 40, 200])), threshold=int(rng.choice([0, 0, 1, 3, 10])),
+                    dist_percent=float(rng.choice([0.0, 0.001, 0.005, 0.05, 0.5])))
+        hifi = combos[int(rng.integers(0, len(combos)))] if rng.random() < 0.85 else None
+        nano = combos[int(rng.integers(0, len(combos)))] if (hifi is None or rng.random() < 0.4) else None
+        names = [f"ctg{chr(65 + i)}" for i in range(n_ctg)]
+        chrs = None
+        if rng.random() < 0.3:
+            keep = sorted(rng.choice(n_ctg, int(rng.integers(1, n_ctg + 1)), replace=False).tolist())
+            chrs = ",".join(names[i] for i in keep)
+        regions = None
+        if rng.random() < 0.4:
+            ok = [i for i in range(n_ctg) if chrs is None or names[i] in chrs.split(",")]
+            regions = []
+            for _ in range(int(rng.integers(1, 5))):
+                c = int(rng.choice(ok))
+                a, b = sorted(int(x) for x in rng.integers(0, lengths[c] + 1, 2))
+                regions.append((names[c], a, b))
+        try:
+            make_case(ref, f"rand{k:02d}", store, meta, lengths=lengths, seed=500 + k, hifi=hifi, nano=nano, args=args,
+                      chrs=chrs, regions=regions, coverage=float(rng.choice([6.0, 12.0, 25.0])))
+        except (Exception, SystemExit) as e:   # the reference itself gives up on this input: not a parity case
+            print(f"case rand{k:02d}: reference raised {type(e).__name__}: {e}")
+            for key in [x for x in store if x.startswith(f"rand{k:02d}.")]:
+                del store[key]
+    np.savez_compressed(os.path.join(HERE, "filter_cases_rand.npz"), **store)
+    with open(os.path.join(HERE, "filter_cases_rand.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+
+
 def make_mh63():
     data = gzip.open(os.path.join(REF, "example", "MH63.depth.gz"), "rb").read()
     names, vals, runs, lens = [], [], [], []
@@ -352,5 +397,9 @@ def make_mh63():
 
 if __name__ == "__main__":
     ref = import_reference()
-    make_filter_cases(ref)
-    make_mh63()
+    if len(sys.argv) > 1 and sys.argv[1] == "rand":
+        make_random_cases(ref)
+    else:
+        make_filter_cases(ref)
+        make_random_cases(ref)
+        make_mh63()

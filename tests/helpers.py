@@ -16,11 +16,29 @@ _PAF_COLS = ("read_id", "qlen", "qstart", "qend", "ref_id", "tstart", "tend", "n
 _cache = {}
 
 
+class _Stores:
+    """the hand-picked cases (filter_cases) and the seeded random ones (filter_cases_rand) behind one mapping"""
+
+    def __init__(self, stores):
+        self.stores = stores
+
+    def __getitem__(self, key):
+        for s in self.stores:
+            if key in s.files:
+                return s[key]
+        raise KeyError(key)
+
+
 def golden_store():
     if "store" not in _cache:
-        _cache["store"] = np.load(os.path.join(GOLDEN, "filter_cases.npz"))
-        with open(os.path.join(GOLDEN, "filter_cases.json")) as f:
-            _cache["meta"] = json.load(f)
+        stores, cases = [], []
+        for stem in ("filter_cases", "filter_cases_rand"):
+            stores.append(np.load(os.path.join(GOLDEN, stem + ".npz")))
+            with open(os.path.join(GOLDEN, stem + ".json")) as f:
+                meta = json.load(f)
+            cases += meta["cases"]
+        _cache["store"] = _Stores(stores)
+        _cache["meta"] = {"cases": cases, "reference_commit": meta["reference_commit"]}
     return _cache["store"], _cache["meta"]
 
 
