@@ -80,14 +80,16 @@ __global__ void cigar_tile_index_kernel(const uint64_t* __restrict__ off, int64_
   if ((int64_t)b == n_ops) tile_rec[n_tiles - 1].y = (int32_t)r;
 }
 
-// tiles touching more than CST_MAX_LOC records go to the staged kernel (K1a), the others stream (K1b);
-// the list order is arbitrary: both kernels only ever ADD u32 partial sums, which commute exactly
+// tiles touching more than CST_MAX_LOC records go to the staged kernel (K1a), the others stream (K1b): the
+// staged tiles fill the list from the front, the streaming ones from the back.  The order inside either part
+// is arbitrary: both kernels only ever ADD u32 partial sums, which commute exactly.
 __global__ void cigar_tile_class_kernel(const int2* __restrict__ tile_rec, int64_t n_tiles,
-                                        int32_t* __restrict__ dense_list, unsigned int* __restrict__ n_dense) {
+                                        int32_t* __restrict__ list, unsigned int* __restrict__ counts /* [2] */) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
   const int2 tr = tile_rec[t];
-  if (tr.y - tr.x + 1 > CST_MAX_LOC) dense_list[atomicAdd(n_dense, 1u)] = (int32_t)t;
+  if (tr.y - tr.x + 1 > CST_MAX_LOC) list[atomicAdd(counts, 1u)] = (int32_t)t;
+  else list[n_tiles - 1 - (int64_t)atomicAdd(counts + 1, 1u)] = (int32_t)t;
 }
 
 struct CigAcc {
@@ -170,17 +172,24 @@ struct CigAcc {
   }
 };
 
-// K1a  staged kernel: tiles holding many records (HiFi: ~70 records per 2048 ops)
+// K1a  staged kernel: tiles holding many records (HiFi: ~70 records per 2048 ops).
+// The tile is staged with one TMA bulk copy; every thread sums its 8 consecutive ops into three counters
+// (all lengths, I, D), a block-wide exclusive scan turns them into prefix sums at every 8th op, and one thread
+// per record takes prefix(end) - prefix(start) (re-adding at most 7 ops at either end from shared memory): no
+// atomics, no search and no divergence on the common path.  N, S, H, P, B ops are rare (read ends): the thread
+// that meets one looks up its record and adds it to a small per-record side table.
 __global__ void __launch_bounds__(CIG_THREADS)
 cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restrict__ off, int64_t n_rec,
                    int64_t n_ops, const int2* __restrict__ tile_rec, const int32_t* __restrict__ tile_list,
                    uint32_t* __restrict__ stats /* [n_rec][8] */) {
   __shared__ __align__(128) uint32_t s_ops[CIG_TILE];
   __shared__ int32_t s_off[CIG_CAP + 2];          // record starts relative to the tile, clamped
-  __shared__ uint32_t s_acc[CIG_CAP * 5];
+  __shared__ uint32_t s_pre[(CIG_THREADS + 1) * 3];   // exclusive prefix (all, I, D) before thread t's ops; [256] = totals
+  __shared__ uint32_t s_rare[CIG_CAP * 3];        // per record: N, S, other (H, P, B)
+  __shared__ uint32_t s_wsum[(CIG_THREADS / 32) * 3];
   __shared__ __align__(8) uint64_t s_bar;
 
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
   const int64_t tile = tile_list ? (int64_t)tile_list[blockIdx.x] : (int64_t)blockIdx.x;
   const int64_t o0 = tile * CIG_TILE;
   const int tile_n = (int)min((int64_t)CIG_TILE, n_ops - o0);
@@ -223,7 +232,7 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
     return;
   }
 
-  for (int i = tid; i < n_loc * 5; i += CIG_THREADS) s_acc[i] = 0u;
+  for (int i = tid; i < n_loc * 3; i += CIG_THREADS) s_rare[i] = 0u;
 #if !GCI_USE_TMA
   for (int v = tid; v * 4 < tile_n; v += CIG_THREADS)
     reinterpret_cast<uint4*>(s_ops)[v] = reinterpret_cast<const uint4*>(cigar + o0)[v];
@@ -232,163 +241,243 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
     const long long rel = (long long)off[r_lo + i] - (long long)o0;
     s_off[i] = (int32_t)max(-1ll, min(rel, (long long)CIG_TILE + 1));
   }
-  __syncthreads();                                // s_acc, s_off and the mbarrier are set up
+  __syncthreads();                                // s_rare, s_off and the mbarrier are set up
 #if GCI_USE_TMA
   mbar_wait(&s_bar, 0);
 #endif
 
-  const bool active = nb > 0;
-  int rl = 0, next = 0;
-  uint32_t ops[CIG_OPT];
-  if (active) {
-    int lo = 0, hi = n_loc;                       // s_off[lo] <= first < s_off[hi] (virtual)
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (s_off[mid] <= first) lo = mid; else hi = mid;
-    }
-    rl = lo;
-    next = s_off[rl + 1];
-    const uint4 a = reinterpret_cast<const uint4*>(s_ops)[tid * 2];
-    const uint4 b = reinterpret_cast<const uint4*>(s_ops)[tid * 2 + 1];
-    ops[0] = a.x; ops[1] = a.y; ops[2] = a.z; ops[3] = a.w;
-    ops[4] = b.x; ops[5] = b.y; ops[6] = b.z; ops[7] = b.w;
-  }
-  CigAcc acc;
-  acc.clear();
-  const bool simple = active && next >= first + nb;                 // all my ops belong to record rl
-  const int rl0 = __shfl_sync(0xffffffffu, rl, 0);
-  const bool warp_one = __all_sync(0xffffffffu, simple && nb == CIG_OPT && rl == rl0);
-  if (simple) {
-    if (nb == CIG_OPT) {
-      acc.add8(ops);
-    } else {
+  // ---- phase 1: 8 ops per thread -> (all, I, D); rare ops -> side table ----
+  uint32_t tot = 0, ci = 0, cd = 0;
+  if (nb > 0) {
+    const uint4 qa = reinterpret_cast<const uint4*>(s_ops)[tid * 2];
+    const uint4 qb = reinterpret_cast<const uint4*>(s_ops)[tid * 2 + 1];
+    uint32_t ops[CIG_OPT] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+    if (nb < CIG_OPT) {
 #pragma unroll
       for (int k = 0; k < CIG_OPT; k++)
-        if (k < nb) acc.add(ops[k]);             // unrolled: ops[] must stay in registers
+        if (k >= nb) ops[k] = 0u;                 // beyond the end of the op stream: M of length 0
     }
-  }
-  if (warp_one) {
-    // the whole warp sits inside one record: one flush per warp
-    acc.warp_reduce();
-    if (lane == 0) acc.flush(&s_acc[rl * 5]);
-  } else if (simple) {
-    acc.flush(&s_acc[rl * 5]);
-  } else if (active) {
+    uint32_t seen = 0;
 #pragma unroll
     for (int k = 0; k < CIG_OPT; k++) {
-      if (k < nb) {
-        if (first + k >= next) {                  // crossed into the next record (skip zero-op records)
-          if (acc.any()) acc.flush(&s_acc[rl * 5]);
-          acc.clear();
-          do { rl++; next = s_off[rl + 1]; } while (first + k >= next);
+      const uint32_t c = ops[k] & 15u, l = ops[k] >> 4;
+      seen |= __funnelshift_l(0u, 1u, ops[k]);
+      tot += l;
+      ci += (c == 1u) ? l : 0u;
+      cd += (c == 2u) ? l : 0u;
+    }
+    if ((seen | (seen >> 16)) & 0xFE78u) {
+#pragma unroll 1
+      for (int k = 0; k < nb; k++) {              // re-read from shared memory: ops[] stays in registers
+        const uint32_t w = s_ops[first + k], c = w & 15u, l = w >> 4;
+        if (!((0xFE78u >> c) & 1u) || l == 0u) continue;
+        int lo = 0, hi = n_loc;                   // s_off[lo] <= first + k < s_off[hi] (virtual)
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (s_off[mid] <= first + k) lo = mid; else hi = mid;
         }
-        acc.add(ops[k]);
+        atomicAdd(&s_rare[lo * 3 + (c == 3u ? 0 : c == 4u ? 1 : 2)], l);
       }
     }
-    if (acc.any()) acc.flush(&s_acc[rl * 5]);
+  }
+  // ---- block-wide exclusive scan of the three counters ----
+  uint32_t it = tot, ii = ci, id = cd;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t a = __shfl_up_sync(0xffffffffu, it, d), b = __shfl_up_sync(0xffffffffu, ii, d),
+                   c = __shfl_up_sync(0xffffffffu, id, d);
+    if (lane >= d) { it += a; ii += b; id += c; }
+  }
+  if (lane == 31) { s_wsum[wp * 3] = it; s_wsum[wp * 3 + 1] = ii; s_wsum[wp * 3 + 2] = id; }
+  __syncthreads();
+  uint32_t wt = 0, wi = 0, wd = 0;
+  for (int j = 0; j < wp; j++) { wt += s_wsum[j * 3]; wi += s_wsum[j * 3 + 1]; wd += s_wsum[j * 3 + 2]; }
+  s_pre[tid * 3] = wt + it - tot;
+  s_pre[tid * 3 + 1] = wi + ii - ci;
+  s_pre[tid * 3 + 2] = wd + id - cd;
+  if (tid == CIG_THREADS - 1) {
+    s_pre[CIG_THREADS * 3] = wt + it;
+    s_pre[CIG_THREADS * 3 + 1] = wi + ii;
+    s_pre[CIG_THREADS * 3 + 2] = wd + id;
   }
   __syncthreads();
+  // ---- phase 2: one thread per record ----
+  auto prefix = [&](int p, uint32_t& t, uint32_t& i, uint32_t& d) {
+    const int blk = p >> 3;
+    t = s_pre[blk * 3];
+    i = s_pre[blk * 3 + 1];
+    d = s_pre[blk * 3 + 2];
+    for (int k = blk * 8; k < p; k++) {
+      const uint32_t w = s_ops[k], c = w & 15u, l = w >> 4;
+      t += l;
+      i += (c == 1u) ? l : 0u;
+      d += (c == 2u) ? l : 0u;
+    }
+  };
   for (int i = tid; i < n_loc; i += CIG_THREADS) {
+    const int a = max(s_off[i], 0), b = min(s_off[i + 1], tile_n);
+    if (b <= a) continue;                         // no op of this record here (its row is zero already)
+    uint32_t ta, ia, da, tb, ib, db;
+    prefix(a, ta, ia, da);
+    prefix(b, tb, ib, db);
+    const uint32_t rn = s_rare[i * 3], rs = s_rare[i * 3 + 1], ro = s_rare[i * 3 + 2];
+    const uint32_t vi = ib - ia, vd = db - da;
+    const uint32_t mx = (tb - ta) - vi - vd - rn - rs - ro;
     const bool complete = s_off[i] >= 0 && s_off[i + 1] <= tile_n;
     uint32_t* g = stats + (r_lo + i) * 8;
-    const uint32_t* p = &s_acc[i * 5];
     if (complete) {
-      *reinterpret_cast<uint4*>(g) = make_uint4(p[0], p[1], p[2], p[3]);
-      g[4] = p[4];
+      *reinterpret_cast<uint4*>(g) = make_uint4(mx, vi, vd, rn);
+      g[4] = rs;
     } else {
-#pragma unroll
-      for (int k = 0; k < 5; k++)
-        if (p[k]) atomicAdd(g + k, p[k]);
+      if (mx) atomicAdd(g + 0, mx);
+      if (vi) atomicAdd(g + 1, vi);
+      if (vd) atomicAdd(g + 2, vd);
+      if (rn) atomicAdd(g + 3, rn);
+      if (rs) atomicAdd(g + 4, rs);
     }
   }
 }
 
 // K1b  streaming kernel: tiles touching at most CST_MAX_LOC records (ONT: thousands of ops per record).
-// One warp per 2048-op tile, no shared memory, no block barrier: 16 rounds of lane-consecutive 16-byte
-// loads (512 B per warp instruction), four rounds in flight; the sums stay in registers until a record
-// ends (one REDUX per counter, five atomics), which happens a few times per tile at most.
+// Persistent warps, one 2048-op tile per warp at a time, no shared memory, no block barrier.  A tile is 4 groups
+// of 512 ops = 4 lane-consecutive 16-byte loads per lane (512 B per warp instruction); the next group (of this
+// tile or of the warp's next tile) is always in flight while the current one is summed, and the next tile's
+// record table is fetched one tile ahead, so a warp never sits on a cold dependent load.  The sums stay in
+// registers until a record ends (one REDUX per counter, five atomics): a few times per tile at most.
 constexpr int CST_WARPS = 8;
 
-__global__ void __launch_bounds__(CST_WARPS * 32)
+struct CstTile {
+  int64_t o0;        // first op of the tile
+  int tile_n;        // ops in the tile (2048 except for the last tile of the stream)
+  int x, n_loc;      // first record with an op in the tile, number of records touching it
+};
+
+__device__ __forceinline__ void cst_load_group(const uint32_t* __restrict__ cigar, const CstTile& t, int g, int lane,
+                                               uint4 (&q)[4]) {
+  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(cigar + t.o0);
+  if (t.tile_n == CIG_TILE) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) q[j] = __ldcs(src + g * 128 + j * 32 + lane);
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {                   // last tile of the op stream: absent ops read as 0 (M of length 0)
+    const int p = (g * 128 + j * 32 + lane) * 4;
+    q[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (p < t.tile_n) q[j].x = cigar[t.o0 + p];
+    if (p + 1 < t.tile_n) q[j].y = cigar[t.o0 + p + 1];
+    if (p + 2 < t.tile_n) q[j].z = cigar[t.o0 + p + 2];
+    if (p + 3 < t.tile_n) q[j].w = cigar[t.o0 + p + 3];
+  }
+}
+
+__global__ void __launch_bounds__(CST_WARPS * 32, 3)
 cigar_stream_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restrict__ off, int64_t n_ops,
-                    const int2* __restrict__ tile_rec, int64_t n_tiles, uint32_t* __restrict__ stats) {
+                    const int2* __restrict__ tile_rec, const int32_t* __restrict__ tile_list, int64_t n_list,
+                    uint32_t* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
-  const int64_t tile = (int64_t)blockIdx.x * CST_WARPS + (threadIdx.x >> 5);
-  if (tile >= n_tiles) return;
-  const int64_t o0 = tile * CIG_TILE;
-  const int tile_n = (int)min((int64_t)CIG_TILE, n_ops - o0);
-  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(cigar + o0);
-  const int2 tr = tile_rec[tile];
-  const bool full = tile_n == CIG_TILE;
-  auto load_group = [&](int g, uint4 (&q)[4]) {
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 4; j++) q[j] = __ldcs(src + g * 128 + j * 32 + lane);
-      return;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {                 // last tile of the op stream: absent ops read as 0 (M of length 0)
-      const int v = g * 128 + j * 32 + lane;      // 16-byte word of the tile
-      const int p = v * 4;
-      q[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (p < tile_n) q[j].x = cigar[o0 + p];
-      if (p + 1 < tile_n) q[j].y = cigar[o0 + p + 1];
-      if (p + 2 < tile_n) q[j].z = cigar[o0 + p + 2];
-      if (p + 3 < tile_n) q[j].w = cigar[o0 + p + 3];
-    }
+  const int64_t n_warps = (int64_t)gridDim.x * CST_WARPS;
+  int64_t idx = (int64_t)blockIdx.x * CST_WARPS + (threadIdx.x >> 5);
+  if (idx >= n_list) return;
+  auto tile_of = [&](int64_t i) -> int64_t { return tile_list ? (int64_t)tile_list[i] : i; };
+  auto describe = [&](int64_t tile, int2 tr) {
+    CstTile t;
+    t.o0 = tile * CIG_TILE;
+    t.tile_n = (int)min((int64_t)CIG_TILE, n_ops - t.o0);
+    t.x = tr.x;
+    t.n_loc = tr.y - tr.x + 1;
+    return t;
   };
+  // lane i keeps the end of record t.x + i, relative to the tile (the last one may lie beyond it)
+  auto load_ends = [&](const CstTile& t) -> int {
+    int e = CIG_TILE + 1;
+    if (lane < t.n_loc) e = (int)min((long long)off[t.x + lane + 1] - (long long)t.o0, (long long)CIG_TILE + 1);
+    return e;
+  };
+
+  int64_t tile = tile_of(idx);
+  CstTile cur = describe(tile, tile_rec[tile]);
   uint4 qa[4], qb[4];
-  load_group(0, qa);                              // in flight while the record table is read
-  const int n_loc = tr.y - tr.x + 1;
-  if (n_loc > CST_MAX_LOC) return;                // a tile of the staged kernel
-  // lane i keeps the end of record tr.x + i, relative to the tile (the last one may lie beyond it)
-  int my_end = CIG_TILE + 1;
-  if (lane < n_loc) my_end = (int)min((long long)off[tr.x + lane + 1] - (long long)o0, (long long)CIG_TILE + 1);
-  int r = 0;                                      // current record (local index), warp-uniform
-  int nxt = __shfl_sync(0xffffffffu, my_end, 0);  // its end
-  CigAcc acc;
-  acc.clear();
-  auto process_group = [&](int g, const uint4 (&q)[4]) {
-    const int gbase = g * 512;
-    if (nxt >= gbase + 512) {                     // the whole group lies inside the current record
-      acc.add16(q);
-      return;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int ibase = gbase + j * 128;
-      const int p = ibase + lane * 4;
-      const uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
-      int cur = ibase;                            // ops before `cur` are accounted for
-      while (nxt < ibase + 128) {                 // a record ends inside this round (warp-uniform)
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-          if (p + k >= cur && p + k < nxt) acc.add(w[k]);
-        acc.warp_reduce();
-        acc.flush_warp(stats + (int64_t)(tr.x + r) * 8, lane);
-        acc.clear();
-        cur = nxt;
-        r++;
-        nxt = r < n_loc ? __shfl_sync(0xffffffffu, my_end, r) : CIG_TILE + 1;
-      }
+  cst_load_group(cigar, cur, 0, lane, qa);
+  int my_end = load_ends(cur);
+  for (;;) {
+    const int64_t idx_n = idx + n_warps;
+    const bool more = idx_n < n_list;
+    const int64_t tile_n1 = more ? tile_of(idx_n) : 0;
+    int2 tr_n = make_int2(0, 0);
+    if (more) tr_n = tile_rec[tile_n1];           // needed after group 1: a whole group of work hides it
+    CstTile nxt_t = cur;
+    int my_end_n = CIG_TILE + 1;
+
+    int r = 0;                                    // current record (local index), warp-uniform
+    int nxt = __shfl_sync(0xffffffffu, my_end, 0);   // its end
+    CigAcc acc;
+    acc.clear();
+    auto process_group = [&](int g, const uint4 (&q)[4]) {
+      const int gbase = g * 512;
+      if (gbase >= cur.tile_n) return;
+      uint32_t seen = 0;
 #pragma unroll
       for (int k = 0; k < 4; k++)
-        if (p + k >= cur) acc.add(w[k]);
+        seen |= __funnelshift_l(0u, 1u, q[k].x) | __funnelshift_l(0u, 1u, q[k].y) | __funnelshift_l(0u, 1u, q[k].z) |
+                __funnelshift_l(0u, 1u, q[k].w);
+      const bool rare = ((seen | (seen >> 16)) & 0xFE78u) != 0;      // N, S, H, P, B among my 16 ops
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int ibase = gbase + j * 128;
+        const uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+        if (nxt >= ibase + 128) {                 // the whole round lies inside the current record (warp-uniform)
+          if (rare) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) acc.add(w[k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const uint32_t c = w[k] & 15u, l = w[k] >> 4;
+              acc.tot += l;
+              acc.i += (c == 1u) ? l : 0u;
+              acc.d += (c == 2u) ? l : 0u;
+            }
+          }
+          continue;
+        }
+        const int p = ibase + lane * 4;
+        int done = ibase;                         // ops before `done` are accounted for
+        while (nxt < ibase + 128) {               // a record ends inside this round (warp-uniform)
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (p + k >= done && p + k < nxt) acc.add(w[k]);
+          acc.warp_reduce();
+          acc.flush_warp(stats + (int64_t)(cur.x + r) * 8, lane);
+          acc.clear();
+          done = nxt;
+          r++;
+          nxt = r < cur.n_loc ? __shfl_sync(0xffffffffu, my_end, r) : CIG_TILE + 1;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (p + k >= done) acc.add(w[k]);
+      }
+    };
+    // four groups, ping-pong buffers; the group after the last one of this tile is group 0 of the next tile
+    if (512 < cur.tile_n) cst_load_group(cigar, cur, 1, lane, qb);
+    process_group(0, qa);
+    if (1024 < cur.tile_n) cst_load_group(cigar, cur, 2, lane, qa);
+    process_group(1, qb);
+    if (more) nxt_t = describe(tile_n1, tr_n);
+    if (1536 < cur.tile_n) cst_load_group(cigar, cur, 3, lane, qb);
+    if (more) my_end_n = load_ends(nxt_t);
+    process_group(2, qa);
+    if (more) cst_load_group(cigar, nxt_t, 0, lane, qa);
+    process_group(3, qb);
+    if (r < cur.n_loc) {
+      acc.warp_reduce();
+      acc.flush_warp(stats + (int64_t)(cur.x + r) * 8, lane);
     }
-  };
-  // two groups per trip, ping-pong buffers: the next 512 ops are in flight while the current ones are summed
-#pragma unroll 1
-  for (int g = 0; g < CIG_TILE / 512; g += 2) {
-    if (g * 512 >= tile_n) break;
-    if ((g + 1) * 512 < tile_n) load_group(g + 1, qb);
-    process_group(g, qa);
-    if ((g + 1) * 512 >= tile_n) break;
-    if (g + 2 < CIG_TILE / 512 && (g + 2) * 512 < tile_n) load_group(g + 2, qa);
-    process_group(g + 1, qb);
-  }
-  if (r < n_loc) {
-    acc.warp_reduce();
-    acc.flush_warp(stats + (int64_t)(tr.x + r) * 8, lane);
+    if (!more) break;
+    idx = idx_n;
+    cur = nxt_t;
+    my_end = my_end_n;
   }
 }
 
@@ -583,7 +672,7 @@ int gci_index_bam(gci_ctx* ctx, BamFile& b) {
   if (n_tiles >= (int64_t(1) << 31)) return ctx->fail(GCI_E_ARG, "too many CIGAR op tiles");
   GCI_TRY(ctx->ensure(b.dense_list, sizeof(int32_t) * (size_t)n_tiles + 16));
   unsigned int* d_cnt = reinterpret_cast<unsigned int*>(b.dense_list.as<int32_t>() + n_tiles);
-  GCI_CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned int), ctx->stream));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned int), ctx->stream));
   cigar_tile_class_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, ctx->stream>>>(
       b.tile_rec.as<int2>(), n_tiles, b.dense_list.as<int32_t>(), d_cnt);
   GCI_LAUNCH_CHECK(ctx);
@@ -620,9 +709,18 @@ int gci_run_bam_leg(gci_ctx* ctx, int file_idx, int bam_idx, int32_t mq, int32_t
       GCI_LAUNCH_CHECK(ctx);
     }
     if (b.n_dense < n_tiles) {
-      cigar_stream_kernel<<<(unsigned)((n_tiles + CST_WARPS - 1) / CST_WARPS), CST_WARPS * 32, 0, ctx->stream>>>(
-          b.cigar.as<uint32_t>(), b.cigar_off.as<uint64_t>(), b.n_ops, b.tile_rec.as<int2>(), n_tiles,
-          b.stats.as<uint32_t>());
+      // persistent warps: resident CTAs per SM x SM count (fewer when the stream is short)
+      static int per_sm = 0;
+      if (per_sm <= 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cigar_stream_kernel, CST_WARPS * 32, 0) !=
+                              cudaSuccess || per_sm < 1)) {
+        cudaGetLastError();
+        per_sm = 2;
+      }
+      const int64_t n_stream = n_tiles - b.n_dense;
+      const int64_t grid = std::min<int64_t>((n_stream + CST_WARPS - 1) / CST_WARPS, (int64_t)ctx->sm_count * per_sm);
+      cigar_stream_kernel<<<(unsigned)grid, CST_WARPS * 32, 0, ctx->stream>>>(
+          b.cigar.as<uint32_t>(), b.cigar_off.as<uint64_t>(), b.n_ops, b.tile_rec.as<int2>(),
+          b.n_dense == 0 ? nullptr : b.dense_list.as<int32_t>() + b.n_dense, n_stream, b.stats.as<uint32_t>());
       GCI_LAUNCH_CHECK(ctx);
     }
   }

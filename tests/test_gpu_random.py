@@ -556,6 +556,9 @@ def test_pipeline_graph_replay_follows_the_data(ctx):
         assert replays >= 12, replays           # everything after the first two steps ran as a graph
         # other arguments: eager again, then a new graph
         want = staged([variant(d.bam, 0), b2], 3, 20)
+        c.reads_begin(d.n_reads)
+        for t in (d.bam, b2):
+            c.upload_bam(t)
         for rep in range(3):
             got = c.pipeline(0, 2, hi=3, flank_len=20)
             assert got[0] == want[0] and got[1] == want[1]
