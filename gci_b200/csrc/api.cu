@@ -110,7 +110,7 @@ int gci_d2h(gci_ctx* ctx, void* dst, const void* src, size_t bytes) {
 
 static void free_bam(gci_ctx* ctx, BamFile& b) {
   for (DevBuf* d : {&b.ref_id, &b.ref_start, &b.mapq, &b.flag, &b.nm, &b.qlen, &b.read_id, &b.cigar_off,
-                    &b.cigar, &b.stats, &b.ref_end, &b.tile_rec, &b.dense_list})
+                    &b.cigar, &b.stats, &b.ref_end, &b.tile_rec, &b.dense_list, &b.span_list})
     ctx->release(*d);
 }
 

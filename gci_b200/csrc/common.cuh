@@ -55,6 +55,8 @@ struct BamFile {
   DevBuf tile_rec; // int2[n_op_tiles]: first / last record of every CIGAR op tile (built at upload)
   DevBuf dense_list; // int32[n_op_tiles] + counter: tiles of the staged CIGAR kernel (the others stream)
   int64_t n_dense = 0; // number of entries of dense_list (-1: the count is still on its way to the host)
+  DevBuf span_list;  // int32[n]: records gated from their HBM row (no ops / cut by a tile border / streaming tile)
+  int64_t n_span = 0;
 };
 
 // PAF lines of one file, resident on the device (columns 0,1,2,3,5,7,8,9,10,11 of GCI.py:218-229)

@@ -172,16 +172,83 @@ struct CigAcc {
   }
 };
 
+// K2  gate + dedup of ONE record from its CIGAR sums (GCI.py:153-168).  Runs inside the staged CIGAR kernel
+// for records that lie completely inside one tile (their sums never reach HBM) and in gate_span_kernel for
+// the others (records cut by a tile border, records of streaming tiles, records without ops).
+// d_err layout: [0] bit mask (1 = NM missing, 2 = zero clip denominator, 4 = zero identity denominator,
+//               8 = zero query length in the join, 16 = zero PAF aln length), [1] first offending index
+struct GateArgs {
+  const int32_t* ref_id;
+  const int32_t* ref_start;
+  const uint8_t* mapq;
+  const uint16_t* flag;
+  const int32_t* nm;
+  const uint32_t* read_id;
+  const uint8_t* selected;
+  int32_t n_contigs;
+  uint32_t n_reads;
+  int32_t map_qual, mq_cutoff;
+  double ip, cp;
+  int32_t* ref_end;
+  long long* win;
+  uint8_t* highq;
+  unsigned long long* err;
+};
+
+__device__ __forceinline__ void gate_one(const GateArgs& g, int64_t r, uint32_t sMx, uint32_t sI, uint32_t sD,
+                                         uint32_t sN, uint32_t sS) {
+  const long long Mx = sMx, I = sI, D = sD, N = sN, S = sS;
+  long long rlen = Mx + D + N;                       // htslib bam_cigar2rlen
+  if (rlen == 0) rlen = 1;                           // htslib bam_endpos
+  const int32_t start = g.ref_start[r];
+  g.ref_end[r] = (int32_t)(start + rlen);
+  const int32_t c = g.ref_id[r];
+  if (c < 0 || c >= g.n_contigs || !g.selected[c]) return;       // never fetched (GCI.py:151, :202-207)
+  const uint32_t f = g.flag[r];
+  if (f & (0x4u | 0x100u | 0x800u)) return;                      // :153-156
+  const int32_t mq = g.mapq[r];
+  if (mq < g.map_qual) return;                                   // :156
+  const int32_t nmv = g.nm[r];
+  if (nmv == INT32_MIN) {                                        // KeyError at :163
+    atomicOr(g.err, 1ull);
+    atomicMin(g.err + 1, (unsigned long long)r);
+    return;
+  }
+  const long long mm = (long long)nmv - (I + D);                 // :164
+  const long long d1 = Mx + I + S;
+  if (d1 == 0) {
+    atomicOr(g.err, 2ull);
+    atomicMin(g.err + 1, (unsigned long long)r);
+    return;
+  }
+  if (!((double)S / (double)d1 <= g.cp)) return;                 // :165, fp64 div.rn like Python int/int
+  const long long d2 = Mx + I + D;
+  if (d2 == 0) {
+    atomicOr(g.err, 4ull);
+    atomicMin(g.err + 1, (unsigned long long)r);
+    return;
+  }
+  if (!((double)(Mx - mm) / (double)d2 >= g.ip)) return;
+  const uint32_t q = g.read_id[r];
+  if (q >= g.n_reads) return;
+  // fetch order = contigs in header order, file order inside: the later record wins (:166, :269)
+  atomicMax(g.win + q, ((long long)c << 32) | (long long)r);
+  if (mq >= g.mq_cutoff) g.highq[q] = 1;                         // :167-168
+}
+
 // K1a  staged kernel: tiles holding many records (HiFi: ~70 records per 2048 ops).
 // The tile is staged with one TMA bulk copy; every thread sums its 8 consecutive ops into three counters
 // (all lengths, I, D), a block-wide exclusive scan turns them into prefix sums at every 8th op, and one thread
 // per record takes prefix(end) - prefix(start) (re-adding at most 7 ops at either end from shared memory): no
 // atomics, no search and no divergence on the common path.  N, S, H, P, B ops are rare (read ends): the thread
 // that meets one looks up its record and adds it to a small per-record side table.
+// GATE: records that lie completely inside the tile are gated right here (gate_one) and their sums are not
+// stored; !GATE (gci_fetch_cigar_stats): every record's sums are stored, nothing is gated.
+template <bool GATE>
 __global__ void __launch_bounds__(CIG_THREADS)
 cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restrict__ off, int64_t n_rec,
                    int64_t n_ops, const int2* __restrict__ tile_rec, const int32_t* __restrict__ tile_list,
-                   uint32_t* __restrict__ stats /* [n_rec][8] */) {
+                   uint32_t* __restrict__ stats /* [n_rec][8] */, GateArgs gate) {
   __shared__ __align__(128) uint32_t s_ops[CIG_TILE];
   __shared__ int32_t s_off[CIG_CAP + 2];          // record starts relative to the tile, clamped
   __shared__ uint32_t s_pre[(CIG_THREADS + 1) * 3];   // exclusive prefix (all, I, D) before thread t's ops; [256] = totals
@@ -326,8 +393,12 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
     const bool complete = s_off[i] >= 0 && s_off[i + 1] <= tile_n;
     uint32_t* g = stats + (r_lo + i) * 8;
     if (complete) {
-      *reinterpret_cast<uint4*>(g) = make_uint4(mx, vi, vd, rn);
-      g[4] = rs;
+      if (GATE) {
+        gate_one(gate, r_lo + i, mx, vi, vd, rn, rs);
+      } else {
+        *reinterpret_cast<uint4*>(g) = make_uint4(mx, vi, vd, rn);
+        g[4] = rs;
+      }
     } else {
       if (mx) atomicAdd(g + 0, mx);
       if (vi) atomicAdd(g + 1, vi);
@@ -482,58 +553,42 @@ cigar_stream_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restri
 }
 
 // ================================================================================================
-// K2  gate + dedup  (GCI.py:153-168)
+// K2  gate of the records the staged kernel did not see completely (GCI.py:153-168)
 // ================================================================================================
-// d_err layout: [0] bit mask (1 = NM missing, 2 = zero clip denominator, 4 = zero identity denominator,
-//               8 = zero query length in the join, 16 = zero PAF aln length), [1] first offending index
-__global__ void gate_kernel(int64_t n, const int32_t* __restrict__ ref_id, const int32_t* __restrict__ ref_start,
-                            const uint8_t* __restrict__ mapq, const uint16_t* __restrict__ flag,
-                            const int32_t* __restrict__ nm, const uint32_t* __restrict__ read_id,
-                            const uint32_t* __restrict__ stats, const uint8_t* __restrict__ selected,
-                            int32_t n_contigs, uint32_t n_reads, int32_t map_qual, int32_t mq_cutoff, double ip,
-                            double cp, int32_t* __restrict__ ref_end, long long* __restrict__ win,
-                            uint8_t* __restrict__ highq, unsigned long long* __restrict__ err) {
-  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (r >= n) return;
+// span_list (built at upload): records without ops, records cut by a tile border, records of streaming tiles
+// and of pathological tiles.  list == NULL: all n records (every row of `stats` is valid then).
+__global__ void gate_span_kernel(const int32_t* __restrict__ list, int64_t n, const uint32_t* __restrict__ stats,
+                                 GateArgs gate) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int64_t r = list ? (int64_t)list[k] : k;
   const uint4 st = *reinterpret_cast<const uint4*>(stats + r * 8);
-  const uint32_t S = stats[r * 8 + 4];
-  const long long Mx = st.x, I = st.y, D = st.z, N = st.w;
-  long long rlen = Mx + D + N;                       // htslib bam_cigar2rlen
-  if (rlen == 0) rlen = 1;                           // htslib bam_endpos
-  const int32_t start = ref_start[r];
-  ref_end[r] = (int32_t)(start + rlen);
-  const int32_t c = ref_id[r];
-  if (c < 0 || c >= n_contigs || !selected[c]) return;          // never fetched (GCI.py:151, :202-207)
-  const uint32_t f = flag[r];
-  if (f & (0x4u | 0x100u | 0x800u)) return;                      // :153-156
-  const int32_t mq = mapq[r];
-  if (mq < map_qual) return;                                     // :156
-  const int32_t nmv = nm[r];
-  if (nmv == INT32_MIN) {                                        // KeyError at :163
-    atomicOr(err, 1ull);
-    atomicMin(err + 1, (unsigned long long)r);
-    return;
+  gate_one(gate, r, st.x, st.y, st.z, st.w, stats[r * 8 + 4]);
+}
+
+__global__ void zero_rows_kernel(const int32_t* __restrict__ list, int64_t n, uint32_t* __restrict__ stats) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;      // two threads per 32-byte row
+  if (k >= 2 * n) return;
+  reinterpret_cast<uint4*>(stats + (int64_t)list[k >> 1] * 8)[k & 1] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// which records does the staged kernel gate itself?  Those with at least one op, all of them inside one tile,
+// that tile being a staged one handled through shared memory.  Everything else goes to span_list.
+__global__ void cigar_record_class_kernel(const uint64_t* __restrict__ off, int64_t n, const int2* __restrict__ tile_rec,
+                                          int32_t* __restrict__ span_list, unsigned int* __restrict__ n_span) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint64_t a = off[r], b = off[r + 1];
+  bool local = false;
+  if (b > a) {
+    const int64_t t0 = (int64_t)(a / CIG_TILE), t1 = (int64_t)((b - 1) / CIG_TILE);
+    if (t0 == t1) {
+      const int2 tr = tile_rec[t0];
+      const int n_loc = tr.y - tr.x + 1;
+      local = n_loc > CST_MAX_LOC && n_loc <= CIG_CAP;
+    }
   }
-  const long long mm = (long long)nmv - (I + D);                 // :164
-  const long long d1 = Mx + I + (long long)S;
-  if (d1 == 0) {
-    atomicOr(err, 2ull);
-    atomicMin(err + 1, (unsigned long long)r);
-    return;
-  }
-  if (!((double)S / (double)d1 <= cp)) return;                   // :165, fp64 div.rn like Python int/int
-  const long long d2 = Mx + I + D;
-  if (d2 == 0) {
-    atomicOr(err, 4ull);
-    atomicMin(err + 1, (unsigned long long)r);
-    return;
-  }
-  if (!((double)(Mx - mm) / (double)d2 >= ip)) return;
-  const uint32_t q = read_id[r];
-  if (q >= n_reads) return;
-  // fetch order = contigs in header order, file order inside: the later record wins (:166, :269)
-  atomicMax(win + q, ((long long)c << 32) | (long long)r);
-  if (mq >= mq_cutoff) highq[q] = 1;                             // :167-168
+  if (!local) span_list[atomicAdd(n_span, 1u)] = (int32_t)r;
 }
 
 __global__ void table_win_kernel(int64_t n, const uint32_t* __restrict__ read_id, uint32_t n_reads,
@@ -661,6 +716,7 @@ static int reset_err(gci_ctx* ctx) {
 
 int gci_index_bam(gci_ctx* ctx, BamFile& b) {
   b.n_dense = 0;
+  b.n_span = b.n;                                 // no op stream: every record is gated from its (zero) row
   if (b.n == 0 || b.n_ops == 0) return GCI_OK;
   const int64_t n_tiles = (b.n_ops + CIG_TILE - 1) / CIG_TILE;
   GCI_TRY(ctx->ensure(b.tile_rec, sizeof(int2) * (size_t)(n_tiles + 1)));
@@ -671,21 +727,69 @@ int gci_index_bam(gci_ctx* ctx, BamFile& b) {
   // staged tiles reaches the host with the synchronisation that ends the upload (gci_index_bam_finish)
   if (n_tiles >= (int64_t(1) << 31)) return ctx->fail(GCI_E_ARG, "too many CIGAR op tiles");
   GCI_TRY(ctx->ensure(b.dense_list, sizeof(int32_t) * (size_t)n_tiles + 16));
-  unsigned int* d_cnt = reinterpret_cast<unsigned int*>(b.dense_list.as<int32_t>() + n_tiles);
-  GCI_CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned int), ctx->stream));
+  unsigned int* d_cnt = reinterpret_cast<unsigned int*>(b.dense_list.as<int32_t>() + n_tiles);   // [dense, stream, span, -]
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned int), ctx->stream));
   cigar_tile_class_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, ctx->stream>>>(
       b.tile_rec.as<int2>(), n_tiles, b.dense_list.as<int32_t>(), d_cnt);
   GCI_LAUNCH_CHECK(ctx);
-  unsigned int* h = (unsigned int*)ctx->pinned(sizeof(unsigned int));
+  // records the staged kernel cannot gate on its own (see cigar_record_class_kernel)
+  GCI_TRY(ctx->ensure(b.span_list, sizeof(int32_t) * (size_t)b.n));
+  cigar_record_class_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, ctx->stream>>>(
+      b.cigar_off.as<uint64_t>(), b.n, b.tile_rec.as<int2>(), b.span_list.as<int32_t>(), d_cnt + 2);
+  GCI_LAUNCH_CHECK(ctx);
+  unsigned int* h = (unsigned int*)ctx->pinned(4 * sizeof(unsigned int));
   if (!h) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
-  GCI_TRY(gci_d2h(ctx, h, d_cnt, sizeof(unsigned int)));
+  GCI_TRY(gci_d2h(ctx, h, d_cnt, 4 * sizeof(unsigned int)));
   b.n_dense = -1;                                 // pending
   return GCI_OK;
 }
 
 // after the stream synchronisation that follows gci_index_bam
 void gci_index_bam_finish(gci_ctx* ctx, BamFile& b) {
-  if (b.n_dense == -1) b.n_dense = (int64_t)*(const unsigned int*)ctx->pinned_scratch;
+  if (b.n_dense == -1) {
+    const unsigned int* h = (const unsigned int*)ctx->pinned_scratch;
+    b.n_dense = (int64_t)h[0];
+    b.n_span = (int64_t)h[2];
+  }
+}
+
+// the CIGAR kernels of one BAM upload.  gate != NULL: the staged kernel gates the records it sees completely
+// and stores nothing for them; gate == NULL: every record's sums are stored (gci_fetch_cigar_stats).
+static int run_cigar_kernels(gci_ctx* ctx, BamFile& b, const GateArgs* gate) {
+  if (b.n_ops <= 0) return GCI_OK;
+  const int64_t n_tiles = (b.n_ops + CIG_TILE - 1) / CIG_TILE;
+  if (b.n_dense < 0 || b.n_dense > n_tiles) return ctx->fail(GCI_E_ARG, "internal: CIGAR tile index is not built");
+  if (b.n_dense > 0) {
+    const int32_t* list = b.n_dense == n_tiles ? nullptr : b.dense_list.as<int32_t>();
+    if (gate) {
+      cigar_stats_kernel<true><<<(unsigned)b.n_dense, CIG_THREADS, 0, ctx->stream>>>(
+          b.cigar.as<uint32_t>(), b.cigar_off.as<uint64_t>(), b.n, b.n_ops, b.tile_rec.as<int2>(), list,
+          b.stats.as<uint32_t>(), *gate);
+    } else {
+      GateArgs none;
+      memset(&none, 0, sizeof none);
+      cigar_stats_kernel<false><<<(unsigned)b.n_dense, CIG_THREADS, 0, ctx->stream>>>(
+          b.cigar.as<uint32_t>(), b.cigar_off.as<uint64_t>(), b.n, b.n_ops, b.tile_rec.as<int2>(), list,
+          b.stats.as<uint32_t>(), none);
+    }
+    GCI_LAUNCH_CHECK(ctx);
+  }
+  if (b.n_dense < n_tiles) {
+    // persistent warps: resident CTAs per SM x SM count (fewer when the stream is short)
+    static int per_sm = 0;
+    if (per_sm <= 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cigar_stream_kernel, CST_WARPS * 32, 0) !=
+                            cudaSuccess || per_sm < 1)) {
+      cudaGetLastError();
+      per_sm = 2;
+    }
+    const int64_t n_stream = n_tiles - b.n_dense;
+    const int64_t grid = std::min<int64_t>((n_stream + CST_WARPS - 1) / CST_WARPS, (int64_t)ctx->sm_count * per_sm);
+    cigar_stream_kernel<<<(unsigned)grid, CST_WARPS * 32, 0, ctx->stream>>>(
+        b.cigar.as<uint32_t>(), b.cigar_off.as<uint64_t>(), b.n_ops, b.tile_rec.as<int2>(),
+        b.n_dense == 0 ? nullptr : b.dense_list.as<int32_t>() + b.n_dense, n_stream, b.stats.as<uint32_t>());
+    GCI_LAUNCH_CHECK(ctx);
+  }
+  return GCI_OK;
 }
 
 int gci_run_bam_leg(gci_ctx* ctx, int file_idx, int bam_idx, int32_t mq, int32_t mq_cutoff, double ip, double cp) {
@@ -697,41 +801,33 @@ int gci_run_bam_leg(gci_ctx* ctx, int file_idx, int bam_idx, int32_t mq, int32_t
   GCI_TRY(ctx->ensure(b.stats, 32 * (size_t)std::max<int64_t>(1, n)));
   GCI_TRY(ctx->ensure(b.ref_end, 4 * (size_t)std::max<int64_t>(1, n)));
   if (n == 0) return GCI_OK;
+  if (b.n_span < 0 || b.n_span > n) return ctx->fail(GCI_E_ARG, "internal: CIGAR record index is not built");
+  GateArgs g;
+  g.ref_id = b.ref_id.as<int32_t>(); g.ref_start = b.ref_start.as<int32_t>(); g.mapq = b.mapq.as<uint8_t>();
+  g.flag = b.flag.as<uint16_t>(); g.nm = b.nm.as<int32_t>(); g.read_id = b.read_id.as<uint32_t>();
+  g.selected = ctx->d_selected.as<uint8_t>(); g.n_contigs = ctx->n_contigs; g.n_reads = ctx->n_reads;
+  g.map_qual = mq; g.mq_cutoff = mq_cutoff; g.ip = ip; g.cp = cp;
+  g.ref_end = b.ref_end.as<int32_t>(); g.win = ft.win.as<long long>(); g.highq = ctx->highq.as<uint8_t>();
+  g.err = ctx->d_err.as<unsigned long long>();
   ctx->stage_begin(GCI_ST_CIGAR);
-  GCI_CUDA_TRY(ctx, cudaMemsetAsync(b.stats.p, 0, 32 * (size_t)n, ctx->stream));
-  if (b.n_ops > 0) {
-    const int64_t n_tiles = (b.n_ops + CIG_TILE - 1) / CIG_TILE;
-    if (b.n_dense < 0 || b.n_dense > n_tiles) return ctx->fail(GCI_E_ARG, "internal: CIGAR tile index is not built");
-    if (b.n_dense > 0) {
-      cigar_stats_kernel<<<(unsigned)b.n_dense, CIG_THREADS, 0, ctx->stream>>>(
-          b.cigar.as<uint32_t>(), b.cigar_off.as<uint64_t>(), n, b.n_ops, b.tile_rec.as<int2>(),
-          b.n_dense == n_tiles ? nullptr : b.dense_list.as<int32_t>(), b.stats.as<uint32_t>());
-      GCI_LAUNCH_CHECK(ctx);
-    }
-    if (b.n_dense < n_tiles) {
-      // persistent warps: resident CTAs per SM x SM count (fewer when the stream is short)
-      static int per_sm = 0;
-      if (per_sm <= 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cigar_stream_kernel, CST_WARPS * 32, 0) !=
-                              cudaSuccess || per_sm < 1)) {
-        cudaGetLastError();
-        per_sm = 2;
-      }
-      const int64_t n_stream = n_tiles - b.n_dense;
-      const int64_t grid = std::min<int64_t>((n_stream + CST_WARPS - 1) / CST_WARPS, (int64_t)ctx->sm_count * per_sm);
-      cigar_stream_kernel<<<(unsigned)grid, CST_WARPS * 32, 0, ctx->stream>>>(
-          b.cigar.as<uint32_t>(), b.cigar_off.as<uint64_t>(), b.n_ops, b.tile_rec.as<int2>(),
-          b.n_dense == 0 ? nullptr : b.dense_list.as<int32_t>() + b.n_dense, n_stream, b.stats.as<uint32_t>());
-      GCI_LAUNCH_CHECK(ctx);
-    }
+  // only the rows of the records gated from HBM (span_list) are ever read: zero those (all of them when they
+  // are a large share, as for ONT)
+  const bool all_rows = b.n_span * 4 > n;
+  if (all_rows) {
+    GCI_CUDA_TRY(ctx, cudaMemsetAsync(b.stats.p, 0, 32 * (size_t)n, ctx->stream));
+  } else if (b.n_span > 0) {
+    zero_rows_kernel<<<(unsigned)((2 * b.n_span + 255) / 256), 256, 0, ctx->stream>>>(
+        b.span_list.as<int32_t>(), b.n_span, b.stats.as<uint32_t>());
+    GCI_LAUNCH_CHECK(ctx);
   }
+  GCI_TRY(run_cigar_kernels(ctx, b, &g));
   ctx->stage_end();
   ctx->stage_begin(GCI_ST_GATE);
-  gate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
-      n, b.ref_id.as<int32_t>(), b.ref_start.as<int32_t>(), b.mapq.as<uint8_t>(), b.flag.as<uint16_t>(),
-      b.nm.as<int32_t>(), b.read_id.as<uint32_t>(), b.stats.as<uint32_t>(), ctx->d_selected.as<uint8_t>(),
-      ctx->n_contigs, ctx->n_reads, mq, mq_cutoff, ip, cp, b.ref_end.as<int32_t>(), ft.win.as<long long>(),
-      ctx->highq.as<uint8_t>(), ctx->d_err.as<unsigned long long>());
-  GCI_LAUNCH_CHECK(ctx);
+  if (b.n_span > 0) {
+    gate_span_kernel<<<(unsigned)((b.n_span + 255) / 256), 256, 0, ctx->stream>>>(
+        b.n_span == n ? nullptr : b.span_list.as<int32_t>(), b.n_span, b.stats.as<uint32_t>(), g);
+    GCI_LAUNCH_CHECK(ctx);
+  }
   ctx->stage_end();
   return GCI_OK;
 }
@@ -1109,10 +1205,13 @@ int gci_fetch_cigar_stats(gci_ctx* ctx, int32_t bam, int64_t n_records, uint32_t
   cudaSetDevice(ctx->device);
   if (!ctx->filtered) return ctx->fail(GCI_E_ARG, "gci_fetch_cigar_stats before gci_filter");
   if (bam < 0 || (size_t)bam >= ctx->n_bam) return ctx->fail(GCI_E_ARG, "no BAM upload %d", bam);
-  const BamFile& b = ctx->bam[bam];
+  BamFile& b = ctx->bam[bam];
   if (n_records != b.n) return ctx->fail(GCI_E_ARG, "BAM upload %d holds %lld records", bam, (long long)b.n);
   if (b.n == 0) return GCI_OK;
   if (stats) {
+    // the filter keeps the sums of most records on chip: run the CIGAR kernels once more, storing every row
+    GCI_CUDA_TRY(ctx, cudaMemsetAsync(b.stats.p, 0, 32 * (size_t)b.n, ctx->stream));
+    GCI_TRY(run_cigar_kernels(ctx, b, nullptr));
     // device rows are 8 words wide (one 32-byte sector per record); the caller gets the 5 used ones
     uint32_t* h = (uint32_t*)ctx->pinned(32 * (size_t)b.n);
     if (!h) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
