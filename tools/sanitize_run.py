@@ -50,4 +50,12 @@ with Context(0) as ctx:
     ctx.reads_begin(d.n_reads)
     ctx.upload_bam(d.bam)
     ctx.pipeline(0, 3)
-    print("sanitize run ok", n)
+    ctx.fetch_cigar_stats(0, d.bam.n_records)
+    ctx.set_timing(False)               # third call replays the step as a CUDA graph
+    for _ in range(3):
+        ctx.pipeline(0, 3)
+    ctx.reads_begin(ont.n_reads)
+    ctx.upload_bam(ont.bam)
+    ctx.pipeline(0, 3)
+    ctx.fetch_cigar_stats(0, ont.bam.n_records)
+    print("sanitize run ok", n, "graph replays", ctx.graph_replays)
