@@ -238,22 +238,22 @@ __device__ __forceinline__ void gate_one(const GateArgs& g, int64_t r, uint32_t 
 
 // K1a  staged kernel: tiles holding many records (HiFi: ~70 records per 2048 ops).
 // The tile is staged with one TMA bulk copy; every thread sums its 8 consecutive ops into three counters
-// (all lengths, I, D), a block-wide exclusive scan turns them into prefix sums at every 8th op, and one thread
-// per record takes prefix(end) - prefix(start) (re-adding at most 7 ops at either end from shared memory): no
-// atomics, no search and no divergence on the common path.  N, S, H, P, B ops are rare (read ends): the thread
+// (all lengths, I, D, S), a block-wide exclusive scan turns them into prefix sums at every 8th op, and one
+// thread per record takes prefix(end) - prefix(start) (re-adding at most 7 ops at either end from shared
+// memory): no atomics, no search and no divergence on the common path.  N, H, P, B ops are rare: the thread
 // that meets one looks up its record and adds it to a small per-record side table.
 // GATE: records that lie completely inside the tile are gated right here (gate_one) and their sums are not
 // stored; !GATE (gci_fetch_cigar_stats): every record's sums are stored, nothing is gated.
 template <bool GATE>
-__global__ void __launch_bounds__(CIG_THREADS)
+__global__ void __launch_bounds__(CIG_THREADS, 8)
 cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restrict__ off, int64_t n_rec,
                    int64_t n_ops, const int2* __restrict__ tile_rec, const int32_t* __restrict__ tile_list,
                    uint32_t* __restrict__ stats /* [n_rec][8] */, GateArgs gate) {
   __shared__ __align__(128) uint32_t s_ops[CIG_TILE];
   __shared__ int32_t s_off[CIG_CAP + 2];          // record starts relative to the tile, clamped
-  __shared__ uint32_t s_pre[(CIG_THREADS + 1) * 3];   // exclusive prefix (all, I, D) before thread t's ops; [256] = totals
-  __shared__ uint32_t s_rare[CIG_CAP * 3];        // per record: N, S, other (H, P, B)
-  __shared__ uint32_t s_wsum[(CIG_THREADS / 32) * 3];
+  __shared__ uint4 s_pre[CIG_THREADS + 1];        // exclusive prefix (all, I, D, S) before thread t's ops; [256] = totals
+  __shared__ uint32_t s_rare[CIG_CAP * 2];        // per record: N, other (H, P, B)
+  __shared__ uint4 s_wsum[CIG_THREADS / 32];
   __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
@@ -299,7 +299,7 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
     return;
   }
 
-  for (int i = tid; i < n_loc * 3; i += CIG_THREADS) s_rare[i] = 0u;
+  for (int i = tid; i < n_loc * 2; i += CIG_THREADS) s_rare[i] = 0u;
 #if !GCI_USE_TMA
   for (int v = tid; v * 4 < tile_n; v += CIG_THREADS)
     reinterpret_cast<uint4*>(s_ops)[v] = reinterpret_cast<const uint4*>(cigar + o0)[v];
@@ -313,8 +313,8 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
   mbar_wait(&s_bar, 0);
 #endif
 
-  // ---- phase 1: 8 ops per thread -> (all, I, D); rare ops -> side table ----
-  uint32_t tot = 0, ci = 0, cd = 0;
+  // ---- phase 1: 8 ops per thread -> (all, I, D, S); rare ops -> side table ----
+  uint32_t tot = 0, ci = 0, cd = 0, cs = 0;
   if (nb > 0) {
     const uint4 qa = reinterpret_cast<const uint4*>(s_ops)[tid * 2];
     const uint4 qb = reinterpret_cast<const uint4*>(s_ops)[tid * 2 + 1];
@@ -332,64 +332,59 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
       tot += l;
       ci += (c == 1u) ? l : 0u;
       cd += (c == 2u) ? l : 0u;
+      cs += (c == 4u) ? l : 0u;
     }
-    if ((seen | (seen >> 16)) & 0xFE78u) {
+    if ((seen | (seen >> 16)) & 0xFE68u) {        // N, H, P, B (or an undefined code)
 #pragma unroll 1
       for (int k = 0; k < nb; k++) {              // re-read from shared memory: ops[] stays in registers
         const uint32_t w = s_ops[first + k], c = w & 15u, l = w >> 4;
-        if (!((0xFE78u >> c) & 1u) || l == 0u) continue;
+        if (!((0xFE68u >> c) & 1u) || l == 0u) continue;
         int lo = 0, hi = n_loc;                   // s_off[lo] <= first + k < s_off[hi] (virtual)
         while (hi - lo > 1) {
           const int mid = (lo + hi) >> 1;
           if (s_off[mid] <= first + k) lo = mid; else hi = mid;
         }
-        atomicAdd(&s_rare[lo * 3 + (c == 3u ? 0 : c == 4u ? 1 : 2)], l);
+        atomicAdd(&s_rare[lo * 2 + (c == 3u ? 0 : 1)], l);
       }
     }
   }
-  // ---- block-wide exclusive scan of the three counters ----
-  uint32_t it = tot, ii = ci, id = cd;
+  // ---- block-wide exclusive scan of the four counters ----
+  uint32_t it = tot, ii = ci, id = cd, is = cs;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const uint32_t a = __shfl_up_sync(0xffffffffu, it, d), b = __shfl_up_sync(0xffffffffu, ii, d),
-                   c = __shfl_up_sync(0xffffffffu, id, d);
-    if (lane >= d) { it += a; ii += b; id += c; }
+                   c = __shfl_up_sync(0xffffffffu, id, d), e = __shfl_up_sync(0xffffffffu, is, d);
+    if (lane >= d) { it += a; ii += b; id += c; is += e; }
   }
-  if (lane == 31) { s_wsum[wp * 3] = it; s_wsum[wp * 3 + 1] = ii; s_wsum[wp * 3 + 2] = id; }
+  if (lane == 31) s_wsum[wp] = make_uint4(it, ii, id, is);
   __syncthreads();
-  uint32_t wt = 0, wi = 0, wd = 0;
-  for (int j = 0; j < wp; j++) { wt += s_wsum[j * 3]; wi += s_wsum[j * 3 + 1]; wd += s_wsum[j * 3 + 2]; }
-  s_pre[tid * 3] = wt + it - tot;
-  s_pre[tid * 3 + 1] = wi + ii - ci;
-  s_pre[tid * 3 + 2] = wd + id - cd;
-  if (tid == CIG_THREADS - 1) {
-    s_pre[CIG_THREADS * 3] = wt + it;
-    s_pre[CIG_THREADS * 3 + 1] = wi + ii;
-    s_pre[CIG_THREADS * 3 + 2] = wd + id;
+  uint4 wo = make_uint4(0u, 0u, 0u, 0u);
+  for (int j = 0; j < wp; j++) {
+    const uint4 v = s_wsum[j];
+    wo.x += v.x; wo.y += v.y; wo.z += v.z; wo.w += v.w;
   }
+  s_pre[tid] = make_uint4(wo.x + it - tot, wo.y + ii - ci, wo.z + id - cd, wo.w + is - cs);
+  if (tid == CIG_THREADS - 1) s_pre[CIG_THREADS] = make_uint4(wo.x + it, wo.y + ii, wo.z + id, wo.w + is);
   __syncthreads();
   // ---- phase 2: one thread per record ----
-  auto prefix = [&](int p, uint32_t& t, uint32_t& i, uint32_t& d) {
-    const int blk = p >> 3;
-    t = s_pre[blk * 3];
-    i = s_pre[blk * 3 + 1];
-    d = s_pre[blk * 3 + 2];
-    for (int k = blk * 8; k < p; k++) {
+  auto prefix = [&](int p) -> uint4 {
+    uint4 v = s_pre[p >> 3];
+    for (int k = p & ~7; k < p; k++) {
       const uint32_t w = s_ops[k], c = w & 15u, l = w >> 4;
-      t += l;
-      i += (c == 1u) ? l : 0u;
-      d += (c == 2u) ? l : 0u;
+      v.x += l;
+      v.y += (c == 1u) ? l : 0u;
+      v.z += (c == 2u) ? l : 0u;
+      v.w += (c == 4u) ? l : 0u;
     }
+    return v;
   };
   for (int i = tid; i < n_loc; i += CIG_THREADS) {
     const int a = max(s_off[i], 0), b = min(s_off[i + 1], tile_n);
     if (b <= a) continue;                         // no op of this record here (its row is zero already)
-    uint32_t ta, ia, da, tb, ib, db;
-    prefix(a, ta, ia, da);
-    prefix(b, tb, ib, db);
-    const uint32_t rn = s_rare[i * 3], rs = s_rare[i * 3 + 1], ro = s_rare[i * 3 + 2];
-    const uint32_t vi = ib - ia, vd = db - da;
-    const uint32_t mx = (tb - ta) - vi - vd - rn - rs - ro;
+    const uint4 pa = prefix(a), pb = prefix(b);
+    const uint32_t rn = s_rare[i * 2], ro = s_rare[i * 2 + 1];
+    const uint32_t vi = pb.y - pa.y, vd = pb.z - pa.z, rs = pb.w - pa.w;
+    const uint32_t mx = (pb.x - pa.x) - vi - vd - rs - rn - ro;
     const bool complete = s_off[i] >= 0 && s_off[i + 1] <= tile_n;
     uint32_t* g = stats + (r_lo + i) * 8;
     if (complete) {
@@ -410,12 +405,14 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
 }
 
 // K1b  streaming kernel: tiles touching at most CST_MAX_LOC records (ONT: thousands of ops per record).
-// Persistent warps, one 2048-op tile per warp at a time, no shared memory, no block barrier.  A tile is 4 groups
-// of 512 ops = 4 lane-consecutive 16-byte loads per lane (512 B per warp instruction); the next group (of this
-// tile or of the warp's next tile) is always in flight while the current one is summed, and the next tile's
-// record table is fetched one tile ahead, so a warp never sits on a cold dependent load.  The sums stay in
-// registers until a record ends (one REDUX per counter, five atomics): a few times per tile at most.
-constexpr int CST_WARPS = 8;
+// Persistent warps, one 2048-op tile per warp at a time, no block barrier.  Every warp owns a ring of CST_NST
+// shared-memory stages of 512 ops (2 KB) filled by TMA bulk copies (cp.async.bulk -> SASS UBLKCP, one
+// mbarrier per stage): three stages = 6 KB per warp are in flight while the fourth is summed, across tile
+// borders, and they cost no registers.  The next tile's record table is fetched one tile ahead.  The sums stay
+// in registers until a record ends (one REDUX per counter, five atomics): a few times per tile at most.
+constexpr int CST_WARPS = 4;          // warps per CTA (32 KB of ring: six CTAs = 24 warps and 192 KB per SM)
+constexpr int CST_NST = 4;            // ring stages per warp
+constexpr int CST_GROUP = 512;        // ops per stage
 
 struct CstTile {
   int64_t o0;        // first op of the tile
@@ -423,33 +420,23 @@ struct CstTile {
   int x, n_loc;      // first record with an op in the tile, number of records touching it
 };
 
-__device__ __forceinline__ void cst_load_group(const uint32_t* __restrict__ cigar, const CstTile& t, int g, int lane,
-                                               uint4 (&q)[4]) {
-  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(cigar + t.o0);
-  if (t.tile_n == CIG_TILE) {
-#pragma unroll
-    for (int j = 0; j < 4; j++) q[j] = __ldcs(src + g * 128 + j * 32 + lane);
-    return;
-  }
-#pragma unroll
-  for (int j = 0; j < 4; j++) {                   // last tile of the op stream: absent ops read as 0 (M of length 0)
-    const int p = (g * 128 + j * 32 + lane) * 4;
-    q[j] = make_uint4(0u, 0u, 0u, 0u);
-    if (p < t.tile_n) q[j].x = cigar[t.o0 + p];
-    if (p + 1 < t.tile_n) q[j].y = cigar[t.o0 + p + 1];
-    if (p + 2 < t.tile_n) q[j].z = cigar[t.o0 + p + 2];
-    if (p + 3 < t.tile_n) q[j].w = cigar[t.o0 + p + 3];
-  }
-}
-
-__global__ void __launch_bounds__(CST_WARPS * 32, 3)
+__global__ void __launch_bounds__(CST_WARPS * 32, 6)
 cigar_stream_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restrict__ off, int64_t n_ops,
                     const int2* __restrict__ tile_rec, const int32_t* __restrict__ tile_list, int64_t n_list,
                     uint32_t* __restrict__ stats) {
-  const int lane = threadIdx.x & 31;
+  __shared__ __align__(128) uint32_t s_ring[CST_WARPS][CST_NST][CST_GROUP];
+  __shared__ __align__(8) uint64_t s_bar[CST_WARPS][CST_NST];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const int64_t n_warps = (int64_t)gridDim.x * CST_WARPS;
-  int64_t idx = (int64_t)blockIdx.x * CST_WARPS + (threadIdx.x >> 5);
-  if (idx >= n_list) return;
+  int64_t idx = (int64_t)blockIdx.x * CST_WARPS + wp;
+  if (idx >= n_list) return;                      // whole warps leave; nothing below is block-wide
+  uint32_t (*ring)[CST_GROUP] = s_ring[wp];
+  uint64_t* bar = s_bar[wp];
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < CST_NST; st++) mbar_init(&bar[st], 1);
+  }
+  __syncwarp();
   auto tile_of = [&](int64_t i) -> int64_t { return tile_list ? (int64_t)tile_list[i] : i; };
   auto describe = [&](int64_t tile, int2 tr) {
     CstTile t;
@@ -466,11 +453,41 @@ cigar_stream_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restri
     return e;
   };
 
+  // ---- producer (lane 0 issues; the bookkeeping is warp-uniform): groups in the order the warp consumes them ----
+  int64_t p_idx = idx;                            // position of the producer's tile in the warp's tile sequence
+  int64_t p_o0 = tile_of(idx) * CIG_TILE;
+  int p_g = 0;                                    // next group of that tile
+  uint32_t p_cnt = 0;                             // groups issued so far
+  auto produce = [&]() {
+    if (p_idx >= n_list) return;                  // the consumer never waits for groups behind the last tile
+    if (lane == 0) {
+      const int slot = p_cnt % CST_NST;
+      const long long left = min((long long)CIG_TILE, (long long)(n_ops - p_o0)) - (long long)p_g * CST_GROUP;
+      const uint32_t n = (uint32_t)max(0ll, min(left, (long long)CST_GROUP));
+      const uint32_t bytes = (n * 4u + 15u) & ~15u;
+      if (bytes) {
+        // the stage was read (generic proxy) by the whole warp before the __syncwarp that precedes this call
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&bar[slot], bytes);
+        tma_load_1d(ring[slot], cigar + p_o0 + (int64_t)p_g * CST_GROUP, bytes, &bar[slot]);
+      } else {                                    // group behind the end of the op stream: complete the phase empty
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar[slot])) : "memory");
+      }
+    }
+    p_cnt++;
+    if (++p_g == CIG_TILE / CST_GROUP) {
+      p_g = 0;
+      p_idx += n_warps;
+      if (p_idx < n_list) p_o0 = tile_of(p_idx) * CIG_TILE;
+    }
+  };
+#pragma unroll
+  for (int k = 0; k < CST_NST - 1; k++) produce();
+
   int64_t tile = tile_of(idx);
   CstTile cur = describe(tile, tile_rec[tile]);
-  uint4 qa[4], qb[4];
-  cst_load_group(cigar, cur, 0, lane, qa);
   int my_end = load_ends(cur);
+  uint32_t c_cnt = 0;                             // groups consumed so far
   for (;;) {
     const int64_t idx_n = idx + n_warps;
     const bool more = idx_n < n_list;
@@ -484,63 +501,78 @@ cigar_stream_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restri
     int nxt = __shfl_sync(0xffffffffu, my_end, 0);   // its end
     CigAcc acc;
     acc.clear();
-    auto process_group = [&](int g, const uint4 (&q)[4]) {
-      const int gbase = g * 512;
-      if (gbase >= cur.tile_n) return;
-      uint32_t seen = 0;
+#pragma unroll 1
+    for (int g = 0; g < CIG_TILE / CST_GROUP; g++) {
+      produce();                                  // refills the stage consumed in the previous round
+      const int slot = c_cnt % CST_NST;
+      mbar_wait(&bar[slot], (c_cnt / CST_NST) & 1u);
+      c_cnt++;
+      const int gbase = g * CST_GROUP;
+      if (gbase < cur.tile_n) {
+        uint4 q[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++)
-        seen |= __funnelshift_l(0u, 1u, q[k].x) | __funnelshift_l(0u, 1u, q[k].y) | __funnelshift_l(0u, 1u, q[k].z) |
-                __funnelshift_l(0u, 1u, q[k].w);
-      const bool rare = ((seen | (seen >> 16)) & 0xFE78u) != 0;      // N, S, H, P, B among my 16 ops
+        for (int j = 0; j < 4; j++) q[j] = reinterpret_cast<const uint4*>(ring[slot])[j * 32 + lane];
+        if (gbase + CST_GROUP > cur.tile_n) {     // last tile of the stream: absent ops read as 0 (M of length 0)
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int ibase = gbase + j * 128;
-        const uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
-        if (nxt >= ibase + 128) {                 // the whole round lies inside the current record (warp-uniform)
-          if (rare) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) acc.add(w[k]);
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              const uint32_t c = w[k] & 15u, l = w[k] >> 4;
-              acc.tot += l;
-              acc.i += (c == 1u) ? l : 0u;
-              acc.d += (c == 2u) ? l : 0u;
-            }
+          for (int j = 0; j < 4; j++) {
+            const int p = gbase + j * 128 + lane * 4;
+            if (p >= cur.tile_n) q[j].x = 0u;
+            if (p + 1 >= cur.tile_n) q[j].y = 0u;
+            if (p + 2 >= cur.tile_n) q[j].z = 0u;
+            if (p + 3 >= cur.tile_n) q[j].w = 0u;
           }
-          continue;
         }
-        const int p = ibase + lane * 4;
-        int done = ibase;                         // ops before `done` are accounted for
-        while (nxt < ibase + 128) {               // a record ends inside this round (warp-uniform)
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            if (p + k >= done && p + k < nxt) acc.add(w[k]);
-          acc.warp_reduce();
-          acc.flush_warp(stats + (int64_t)(cur.x + r) * 8, lane);
-          acc.clear();
-          done = nxt;
-          r++;
-          nxt = r < cur.n_loc ? __shfl_sync(0xffffffffu, my_end, r) : CIG_TILE + 1;
-        }
+        uint32_t seen = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++)
-          if (p + k >= done) acc.add(w[k]);
+          seen |= __funnelshift_l(0u, 1u, q[k].x) | __funnelshift_l(0u, 1u, q[k].y) | __funnelshift_l(0u, 1u, q[k].z) |
+                  __funnelshift_l(0u, 1u, q[k].w);
+        const bool rare = ((seen | (seen >> 16)) & 0xFE68u) != 0;    // N, H, P, B among my 16 ops (S is common)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int ibase = gbase + j * 128;
+          const uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+          if (nxt >= ibase + 128) {               // the whole round lies inside the current record (warp-uniform)
+            if (rare) {
+#pragma unroll
+              for (int k = 0; k < 4; k++) acc.add(w[k]);
+            } else {
+              uint32_t all = 0, sc = 0;
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const uint32_t c = w[k] & 15u, l = w[k] >> 4;
+                all += l;
+                acc.i += (c == 1u) ? l : 0u;
+                acc.d += (c == 2u) ? l : 0u;
+                sc += (c == 4u) ? l : 0u;
+              }
+              acc.tot += all - sc;
+              acc.s += sc;
+            }
+            continue;
+          }
+          const int p = ibase + lane * 4;
+          int done = ibase;                       // ops before `done` are accounted for
+          while (nxt < ibase + 128) {             // a record ends inside this round (warp-uniform)
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              if (p + k >= done && p + k < nxt) acc.add(w[k]);
+            acc.warp_reduce();
+            acc.flush_warp(stats + (int64_t)(cur.x + r) * 8, lane);
+            acc.clear();
+            done = nxt;
+            r++;
+            nxt = r < cur.n_loc ? __shfl_sync(0xffffffffu, my_end, r) : CIG_TILE + 1;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (p + k >= done) acc.add(w[k]);
+        }
       }
-    };
-    // four groups, ping-pong buffers; the group after the last one of this tile is group 0 of the next tile
-    if (512 < cur.tile_n) cst_load_group(cigar, cur, 1, lane, qb);
-    process_group(0, qa);
-    if (1024 < cur.tile_n) cst_load_group(cigar, cur, 2, lane, qa);
-    process_group(1, qb);
-    if (more) nxt_t = describe(tile_n1, tr_n);
-    if (1536 < cur.tile_n) cst_load_group(cigar, cur, 3, lane, qb);
-    if (more) my_end_n = load_ends(nxt_t);
-    process_group(2, qa);
-    if (more) cst_load_group(cigar, nxt_t, 0, lane, qa);
-    process_group(3, qb);
+      __syncwarp();                               // every lane is done with the stage before it is refilled
+      if (g == 1 && more) nxt_t = describe(tile_n1, tr_n);
+      if (g == 2 && more) my_end_n = load_ends(nxt_t);
+    }
     if (r < cur.n_loc) {
       acc.warp_reduce();
       acc.flush_warp(stats + (int64_t)(cur.x + r) * 8, lane);

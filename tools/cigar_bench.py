@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--sigma", type=float, default=0.6)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--clip-frac", type=float, default=0.3, help="share of records that open with a soft clip")
+    ap.add_argument("--hard-frac", type=float, default=0.02, help="share of records that open with a hard clip")
     a = ap.parse_args()
     rng = np.random.default_rng(a.seed)
     mu = np.log(a.mean_ops) - a.sigma ** 2 / 2
@@ -33,7 +35,10 @@ def main():
     c = int(off[-1])
     op = rng.choice(np.array([0, 0, 0, 0, 0, 1, 2, 7, 8], np.uint32), c)
     ln = rng.integers(1, 40, c, dtype=np.uint32)
-    op[off[:-1].astype(np.int64)] = 4                      # a soft clip opens every record
+    starts = off[:-1].astype(np.int64)
+    u = rng.random(a.records)
+    op[starts[u < a.clip_frac]] = 4                        # soft clip at the start of the read
+    op[starts[u > 1.0 - a.hard_frac]] = 5                  # hard clip (supplementary-style record)
     cigar = (ln << np.uint32(4)) | op
     n = a.records
     tab = AlnTable(np.zeros(n, np.int32), np.zeros(n, np.int32), np.full(n, 60, np.uint8), np.full(n, 4, np.uint16),
