@@ -97,11 +97,15 @@ __device__ __forceinline__ int sparse_excl_scan(int v, int lane, int& total) {
 }
 
 // Persistent warps, one tile (1024 positions) per warp at a time, no block-level barrier.
-// Per round of 256 positions a lane owns two quads: positions [4l, 4l+4) and [128+4l, 128+4l+4), so both
-// the shared-memory loads (LDS.128) and the global stores (STG.128) are lane-consecutive: conflict-free and
-// full 32-byte sectors.  The tile table entry and the events of the NEXT tile are fetched while the current
-// one is expanded; the depth carried into a tile comes from the tile scan, so warps never wait for each
-// other.  FLAGS: also emit the issue bit (lo < depth <= hi): lo1 = lo + 1, span = # admissible values.
+// A tile is eight half-rounds of 128 positions; in a half-round a lane owns the quad [4l, 4l+4), so the
+// shared-memory loads (LDS.128) and the global stores (STG.128) are lane-consecutive: conflict-free and full
+// 32-byte sectors.  Events are sparse (a few per tile), so the warp first ORs together which half-rounds hold
+// an event at all (one REDUX): a half-round without one is a constant run of the carried depth -- one STG.128
+// per lane and four flag words per warp, no shared-memory traffic, no scan -- and only the others go through
+// load -> re-zero -> lane prefix -> sparse warp scan -> store -> flag packing.  The tile table entry and the
+// events of the NEXT tile are fetched while the current one is expanded; the depth carried into a tile comes
+// from the tile scan, so warps never wait for each other.
+// FLAGS: also emit the issue bit (lo < depth <= hi): lo1 = lo + 1, span = # admissible values.
 template <bool FLAGS>
 __global__ void __launch_bounds__(GCI_TILE_THREADS)
 depth_tile_kernel(const ulonglong2* __restrict__ tile_ps /* (pack, scan) per tile */,
@@ -110,7 +114,7 @@ depth_tile_kernel(const ulonglong2* __restrict__ tile_ps /* (pack, scan) per til
   __shared__ __align__(16) int s_all[(GCI_TILE_THREADS / 32) * GCI_TILE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* __restrict__ s_delta = s_all + warp * GCI_TILE;
-  constexpr int ITERS = GCI_TILE / 256;                          // 4
+  constexpr int HALVES = GCI_TILE / 128;                         // 8
 
 #pragma unroll
   for (int v = lane; v < GCI_TILE / 4; v += 32) reinterpret_cast<int4*>(s_delta)[v] = make_int4(0, 0, 0, 0);
@@ -126,46 +130,49 @@ depth_tile_kernel(const ulonglong2* __restrict__ tile_ps /* (pack, scan) per til
     const uint32_t n_ev = (uint32_t)(ps.x & 0xffffffffull);
     const uint32_t ev0 = (uint32_t)(ps.y & 0xffffffffull);
     int carry = (int)(uint32_t)(ps.y >> 32);                     // depth carried into the tile
-    if (lane < n_ev) atomicAdd(&s_delta[ev >> 1], (ev & 1u) ? -1 : 1);
+    uint32_t hot = 0;                                            // half-rounds holding an event (ev = pos << 1 | end)
+    if (lane < n_ev) {
+      atomicAdd(&s_delta[ev >> 1], (ev & 1u) ? -1 : 1);
+      hot = 1u << (ev >> 8);
+    }
     for (uint32_t i = lane + 32; i < n_ev; i += 32) {            // more than 32 events in the tile: rare
       const uint32_t e = events[ev0 + i];
       atomicAdd(&s_delta[e >> 1], (e & 1u) ? -1 : 1);
+      hot |= 1u << (e >> 8);
     }
+    hot = __reduce_or_sync(0xffffffffu, hot);
     // software pipeline: events of the next tile, table entry of the one after
     ps = ps1;
     ev = lane < (uint32_t)(ps.x & 0xffffffffull) ? events[(uint32_t)(ps.y & 0xffffffffull) + lane] : 0u;
     ps1 = tile + 2 * n_warps < n_tiles ? tile_ps[tile + 2 * n_warps] : zero2;
     __syncwarp();
     int32_t* __restrict__ out = depth + tile * GCI_TILE;
+    uint32_t* __restrict__ fl = flags + tile * (GCI_TILE / 32);
 #pragma unroll
-    for (int it = 0; it < ITERS; it++) {
-      const int ia = it * 256 + lane * 4, ib = ia + 128;
-      const int4 va = *reinterpret_cast<const int4*>(&s_delta[ia]);
-      const int4 vb = *reinterpret_cast<const int4*>(&s_delta[ib]);
-      const int a0 = va.x, a1 = a0 + va.y, a2 = a1 + va.z, a3 = a2 + va.w;
-      const int b0 = vb.x, b1 = b0 + vb.y, b2 = b1 + vb.z, b3 = b2 + vb.w;
-      if ((va.x | va.y | va.z | va.w) != 0) *reinterpret_cast<int4*>(&s_delta[ia]) = make_int4(0, 0, 0, 0);
-      if ((vb.x | vb.y | vb.z | vb.w) != 0) *reinterpret_cast<int4*>(&s_delta[ib]) = make_int4(0, 0, 0, 0);
-      int tot_a, tot_b;
-      const int ra = carry + sparse_excl_scan(a3, lane, tot_a);
-      const int rb = carry + tot_a + sparse_excl_scan(b3, lane, tot_b);
-      carry += tot_a + tot_b;
-      const int4 oa = make_int4(ra + a0, ra + a1, ra + a2, ra + a3);
-      const int4 ob = make_int4(rb + b0, rb + b1, rb + b2, rb + b3);
-      *reinterpret_cast<int4*>(out + ia) = oa;
-      *reinterpret_cast<int4*>(out + ib) = ob;
-      if (FLAGS) {
-        // butterfly: even lanes collect the A-half words, odd lanes the B-half words (3 shuffles for 8 words)
-        const uint32_t na = flag4(oa.x, oa.y, oa.z, oa.w, lo1, span), nb = flag4(ob.x, ob.y, ob.z, ob.w, lo1, span);
-        const bool odd = lane & 1;
-        uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? na : nb, 1);
-        uint32_t acc = odd ? (got | (nb << 4)) : (na | (got << 4));
-        got = __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc = (lane & 2) ? (got | (acc << 8)) : (acc | (got << 8));
-        got = __shfl_xor_sync(0xffffffffu, acc, 4);
-        acc = (lane & 4) ? (got | (acc << 16)) : (acc | (got << 16));
-        if ((lane & 6) == 0)   // lanes 8g (A word g) and 8g+1 (B word g)
-          flags[tile * (GCI_TILE / 32) + it * 8 + (odd ? 4 : 0) + (lane >> 3)] = acc;
+    for (int h = 0; h < HALVES; h++) {
+      const int ia = h * 128 + lane * 4;
+      if (hot & (1u << h)) {                                     // warp-uniform
+        const int4 va = *reinterpret_cast<const int4*>(&s_delta[ia]);
+        const int a0 = va.x, a1 = a0 + va.y, a2 = a1 + va.z, a3 = a2 + va.w;
+        if ((va.x | va.y | va.z | va.w) != 0) *reinterpret_cast<int4*>(&s_delta[ia]) = make_int4(0, 0, 0, 0);
+        int tot;
+        const int ra = carry + sparse_excl_scan(a3, lane, tot);
+        carry += tot;
+        const int4 oa = make_int4(ra + a0, ra + a1, ra + a2, ra + a3);
+        *reinterpret_cast<int4*>(out + ia) = oa;
+        if (FLAGS) {
+          // eight lanes' nibbles make one 32-position word
+          uint32_t w = flag4(oa.x, oa.y, oa.z, oa.w, lo1, span) << ((lane & 7) * 4);
+          w |= __shfl_xor_sync(0xffffffffu, w, 1);
+          w |= __shfl_xor_sync(0xffffffffu, w, 2);
+          w |= __shfl_xor_sync(0xffffffffu, w, 4);
+          if ((lane & 7) == 0) fl[h * 4 + (lane >> 3)] = w;
+        }
+      } else {                                                   // a constant run of the carried depth
+        *reinterpret_cast<int4*>(out + ia) = make_int4(carry, carry, carry, carry);
+        if (FLAGS) {
+          if (lane < 4) fl[h * 4 + lane] = ((uint32_t)(carry - lo1) < span) ? 0xffffffffu : 0u;
+        }
       }
     }
     __syncwarp();   // re-zeroing stores of all lanes are done before the next tile's events land

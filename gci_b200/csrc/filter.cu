@@ -238,9 +238,9 @@ __device__ __forceinline__ void gate_one(const GateArgs& g, int64_t r, uint32_t 
 
 // K1a  staged kernel: tiles holding many records (HiFi: ~70 records per 2048 ops).
 // The tile is staged with one TMA bulk copy; every thread sums its 8 consecutive ops into three counters
-// (all lengths, I, D, S), a block-wide exclusive scan turns them into prefix sums at every 8th op, and one
-// thread per record takes prefix(end) - prefix(start) (re-adding at most 7 ops at either end from shared
-// memory): no atomics, no search and no divergence on the common path.  N, H, P, B ops are rare: the thread
+// (all lengths, I, D, S) and leaves them in shared memory; one thread per record then adds the partial sums of
+// the 8-op blocks its record covers and the ragged ends (at most 7 ops at either side) straight from the
+// staged ops: no atomics, no search and no divergence on the common path.  N, H, P, B ops are rare: the thread
 // that meets one looks up its record and adds it to a small per-record side table.
 // GATE: records that lie completely inside the tile are gated right here (gate_one) and their sums are not
 // stored; !GATE (gci_fetch_cigar_stats): every record's sums are stored, nothing is gated.
@@ -251,12 +251,11 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
                    uint32_t* __restrict__ stats /* [n_rec][8] */, GateArgs gate) {
   __shared__ __align__(128) uint32_t s_ops[CIG_TILE];
   __shared__ int32_t s_off[CIG_CAP + 2];          // record starts relative to the tile, clamped
-  __shared__ uint4 s_pre[CIG_THREADS + 1];        // exclusive prefix (all, I, D, S) before thread t's ops; [256] = totals
+  __shared__ uint4 s_part[CIG_THREADS];           // (all, I, D, S) of thread t's 8 ops
   __shared__ uint32_t s_rare[CIG_CAP * 2];        // per record: N, other (H, P, B)
-  __shared__ uint4 s_wsum[CIG_THREADS / 32];
   __shared__ __align__(8) uint64_t s_bar;
 
-  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  const int tid = threadIdx.x;
   const int64_t tile = tile_list ? (int64_t)tile_list[blockIdx.x] : (int64_t)blockIdx.x;
   const int64_t o0 = tile * CIG_TILE;
   const int tile_n = (int)min((int64_t)CIG_TILE, n_ops - o0);
@@ -348,43 +347,36 @@ cigar_stats_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restric
       }
     }
   }
-  // ---- block-wide exclusive scan of the four counters ----
-  uint32_t it = tot, ii = ci, id = cd, is = cs;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t a = __shfl_up_sync(0xffffffffu, it, d), b = __shfl_up_sync(0xffffffffu, ii, d),
-                   c = __shfl_up_sync(0xffffffffu, id, d), e = __shfl_up_sync(0xffffffffu, is, d);
-    if (lane >= d) { it += a; ii += b; id += c; is += e; }
-  }
-  if (lane == 31) s_wsum[wp] = make_uint4(it, ii, id, is);
+  s_part[tid] = make_uint4(tot, ci, cd, cs);
   __syncthreads();
-  uint4 wo = make_uint4(0u, 0u, 0u, 0u);
-  for (int j = 0; j < wp; j++) {
-    const uint4 v = s_wsum[j];
-    wo.x += v.x; wo.y += v.y; wo.z += v.z; wo.w += v.w;
-  }
-  s_pre[tid] = make_uint4(wo.x + it - tot, wo.y + ii - ci, wo.z + id - cd, wo.w + is - cs);
-  if (tid == CIG_THREADS - 1) s_pre[CIG_THREADS] = make_uint4(wo.x + it, wo.y + ii, wo.z + id, wo.w + is);
-  __syncthreads();
-  // ---- phase 2: one thread per record ----
-  auto prefix = [&](int p) -> uint4 {
-    uint4 v = s_pre[p >> 3];
-    for (int k = p & ~7; k < p; k++) {
+  // ---- phase 2: one thread per record: whole 8-op blocks come from s_part, the ragged ends from s_ops ----
+  auto add_ops = [&](int p0, int p1, uint4& v) {
+    for (int k = p0; k < p1; k++) {
       const uint32_t w = s_ops[k], c = w & 15u, l = w >> 4;
       v.x += l;
       v.y += (c == 1u) ? l : 0u;
       v.z += (c == 2u) ? l : 0u;
       v.w += (c == 4u) ? l : 0u;
     }
-    return v;
   };
   for (int i = tid; i < n_loc; i += CIG_THREADS) {
     const int a = max(s_off[i], 0), b = min(s_off[i + 1], tile_n);
     if (b <= a) continue;                         // no op of this record here (its row is zero already)
-    const uint4 pa = prefix(a), pb = prefix(b);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    const int ta = (a + 7) >> 3, tb = b >> 3;     // threads whose 8 ops lie completely inside [a, b)
+    if (ta <= tb) {
+      add_ops(a, ta * 8, v);
+      for (int t = ta; t < tb; t++) {
+        const uint4 q = s_part[t];
+        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+      }
+      add_ops(tb * 8, b, v);
+    } else {
+      add_ops(a, b, v);
+    }
     const uint32_t rn = s_rare[i * 2], ro = s_rare[i * 2 + 1];
-    const uint32_t vi = pb.y - pa.y, vd = pb.z - pa.z, rs = pb.w - pa.w;
-    const uint32_t mx = (pb.x - pa.x) - vi - vd - rs - rn - ro;
+    const uint32_t vi = v.y, vd = v.z, rs = v.w;
+    const uint32_t mx = v.x - vi - vd - rs - rn - ro;
     const bool complete = s_off[i] >= 0 && s_off[i + 1] <= tile_n;
     uint32_t* g = stats + (r_lo + i) * 8;
     if (complete) {
@@ -453,47 +445,41 @@ cigar_stream_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restri
     return e;
   };
 
-  // ---- producer (lane 0 issues; the bookkeeping is warp-uniform): groups in the order the warp consumes them ----
-  int64_t p_idx = idx;                            // position of the producer's tile in the warp's tile sequence
-  int64_t p_o0 = tile_of(idx) * CIG_TILE;
-  int p_g = 0;                                    // next group of that tile
-  uint32_t p_cnt = 0;                             // groups issued so far
-  auto produce = [&]() {
-    if (p_idx >= n_list) return;                  // the consumer never waits for groups behind the last tile
-    if (lane == 0) {
-      const int slot = p_cnt % CST_NST;
-      const long long left = min((long long)CIG_TILE, (long long)(n_ops - p_o0)) - (long long)p_g * CST_GROUP;
-      const uint32_t n = (uint32_t)max(0ll, min(left, (long long)CST_GROUP));
-      const uint32_t bytes = (n * 4u + 15u) & ~15u;
-      if (bytes) {
-        // the stage was read (generic proxy) by the whole warp before the __syncwarp that precedes this call
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&bar[slot], bytes);
-        tma_load_1d(ring[slot], cigar + p_o0 + (int64_t)p_g * CST_GROUP, bytes, &bar[slot]);
-      } else {                                    // group behind the end of the op stream: complete the phase empty
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar[slot])) : "memory");
-      }
-    }
-    p_cnt++;
-    if (++p_g == CIG_TILE / CST_GROUP) {
-      p_g = 0;
-      p_idx += n_warps;
-      if (p_idx < n_list) p_o0 = tile_of(p_idx) * CIG_TILE;
+  // ---- producer: lane 0 issues group g of the tile starting at op o0 into stage g.  A tile has as many groups
+  // as the ring has stages, so group g always lives in stage g and its barrier flips once per tile. ----
+  static_assert(CIG_TILE / CST_GROUP == CST_NST, "one ring stage per group of a tile");
+  auto produce = [&](int64_t o0, int tile_n, int g) {
+    if (lane != 0) return;
+    const int n = max(0, min(tile_n - g * CST_GROUP, CST_GROUP));
+    const uint32_t bytes = ((uint32_t)n * 4u + 15u) & ~15u;
+    if (bytes) {
+      // the stage was read (generic proxy) by the whole warp before the __syncwarp that precedes this call
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&bar[g], bytes);
+      tma_load_1d(ring[g], cigar + o0 + g * CST_GROUP, bytes, &bar[g]);
+    } else {                                      // group behind the end of the op stream: complete the phase empty
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar[g])) : "memory");
     }
   };
-#pragma unroll
-  for (int k = 0; k < CST_NST - 1; k++) produce();
 
   int64_t tile = tile_of(idx);
+  {
+    const int64_t o0 = tile * CIG_TILE;
+    const int tn = (int)min((int64_t)CIG_TILE, n_ops - o0);
+#pragma unroll
+    for (int g = 0; g < CST_NST - 1; g++) produce(o0, tn, g);
+  }
   CstTile cur = describe(tile, tile_rec[tile]);
   int my_end = load_ends(cur);
-  uint32_t c_cnt = 0;                             // groups consumed so far
+  uint32_t phase = 0;                             // parity of the barriers for the current tile
   for (;;) {
     const int64_t idx_n = idx + n_warps;
     const bool more = idx_n < n_list;
     const int64_t tile_n1 = more ? tile_of(idx_n) : 0;
     int2 tr_n = make_int2(0, 0);
     if (more) tr_n = tile_rec[tile_n1];           // needed after group 1: a whole group of work hides it
+    const int64_t o0_n = tile_n1 * CIG_TILE;
+    const int tn_n = more ? (int)min((int64_t)CIG_TILE, n_ops - o0_n) : 0;
     CstTile nxt_t = cur;
     int my_end_n = CIG_TILE + 1;
 
@@ -503,10 +489,12 @@ cigar_stream_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restri
     acc.clear();
 #pragma unroll 1
     for (int g = 0; g < CIG_TILE / CST_GROUP; g++) {
-      produce();                                  // refills the stage consumed in the previous round
-      const int slot = c_cnt % CST_NST;
-      mbar_wait(&bar[slot], (c_cnt / CST_NST) & 1u);
-      c_cnt++;
+      // three groups ahead: the last group of this tile, then the first three of the next one; the stage it
+      // goes to was consumed in the previous round
+      if (g == 0) produce(cur.o0, cur.tile_n, CST_NST - 1);
+      else if (more) produce(o0_n, tn_n, g - 1);
+      const int slot = g;
+      mbar_wait(&bar[slot], phase);
       const int gbase = g * CST_GROUP;
       if (gbase < cur.tile_n) {
         uint4 q[4];
@@ -581,6 +569,7 @@ cigar_stream_kernel(const uint32_t* __restrict__ cigar, const uint64_t* __restri
     idx = idx_n;
     cur = nxt_t;
     my_end = my_end_n;
+    phase ^= 1u;
   }
 }
 
