@@ -175,8 +175,6 @@ int gci_create(int device, gci_ctx** out) {
   {
     const char* g = getenv("GCI_GRAPH");
     ctx->graph_ok = !(g && g[0] == '0');
-    const char* f = getenv("GCI_DEPTH_FLAT");
-    ctx->depth_flat = !(f && f[0] == '0');
   }
   cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming);
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);

@@ -120,7 +120,6 @@ struct gci_ctx {
   int64_t dev_bytes = 0;
   int sm_count = 148;
   int depth_ctas_per_sm = 0;        // resident CTAs of depth_tile_kernel per SM (occupancy query)
-  bool depth_flat = true;           // depth_tile_kernel takes the constant-run shortcut (GCI_DEPTH_FLAT=0: off)
 
   // contigs
   int32_t n_contigs = 0;
