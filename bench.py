@@ -334,7 +334,9 @@ def main():
                        "timing": "CUDA events per step on the library's stream, max over ranks",
                        "launch": "the step is replayed as a CUDA graph (captured on its second run): " +
                                  ("off (GCI_GRAPH=0)" if os.environ.get("GCI_GRAPH", "1").startswith("0") else "on"),
-                       "parallelism": "contig sharding, 1 process per GPU" if world > 1 else "single GPU"},
+                       "parallelism": "contig sharding, 1 process per GPU" if world > 1 else "single GPU",
+                       "graph_replays": int(ctx.graph_replays),
+                       "row_exchange": getattr(ctx, "row_exchange", None) if world > 1 else None},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(result["d2h_depth_bytes"] + 8 * result["n_iv"] + 64),

@@ -83,6 +83,9 @@ _SIGNATURES = {
                                    C.POINTER(_i64), _p, _p, _p, _i64, _i64, _p]),
     "gci_comm_unique_id": (C.c_int, [_p]),
     "gci_comm_init": (C.c_int, [_p, _p, _i32, _i32]),
+    "gci_comm_p2p_alloc": (C.c_int, [_p, _i64, _p]),
+    "gci_comm_p2p_open": (C.c_int, [_p, _p]),
+    "gci_comm_p2p_disable": (C.c_int, [_p]),
     "gci_genome_row": (C.c_int, [_p, _i32, _f64, _i32, _i64, _i64, _p, _p, _p, _p]),
     "gci_score_terms_sums": (C.c_int, [_p, _i32, _f64, _i32, _p, _p, _i64, _p, _p, _p]),
 }
@@ -434,6 +437,21 @@ class Context:
         assert uid.size == 128
         self._check(self._lib.gci_comm_init(self._h, _ptr(uid), int(rank), int(world)))
         self.comm_world = int(world)
+
+    def comm_p2p_alloc(self, cap=2048):
+        """-> 64-byte CUDA IPC handle of this rank's receive area for the peer-memory genome row"""
+        h = np.zeros(64, np.uint8)
+        self._check(self._lib.gci_comm_p2p_alloc(self._h, int(cap), _ptr(h)))
+        return h
+
+    def comm_p2p_open(self, handles):
+        """handles: uint8[world, 64], row r = what rank r got from comm_p2p_alloc"""
+        h = _arr(handles, np.uint8)
+        assert h.size == 64 * self.comm_world
+        self._check(self._lib.gci_comm_p2p_open(self._h, _ptr(h)))
+
+    def comm_p2p_disable(self):
+        self._check(self._lib.gci_comm_p2p_disable(self._h))
 
     def genome_row(self, track, n_owners, sum_len, dist_percent=0.005, flank_len=15, cap=2048):
         """Score terms of this rank's contigs + one NCCL all-gather of every rank's genome-row terms.

@@ -21,6 +21,7 @@ constexpr int GCI_TILE = 1024;            // positions per depth tile = per warp
 constexpr int GCI_TILE_THREADS = 256;     // 8 warps = 8 independent tiles in flight per CTA
 constexpr int GCI_CHUNK = 8192;           // positions per CTA in the streaming kernels (max / flags / sum)
 constexpr int GCI_RUN_CHUNK_WORDS = 2048; // flag words (of 32 positions) per run-extraction chunk
+constexpr int GCI_MAX_RANKS = 16;         // GPUs of one NVLink domain taking part in the peer-memory row exchange
 
 #define GCI_CUDA_TRY(ctx, expr)                                                              \
   do {                                                                                       \
@@ -171,6 +172,11 @@ struct gci_ctx {
   // NCCL communicator of a multi-GPU run (comm.cu; resolved with dlopen)
   void* nccl_comm = nullptr;
   int comm_rank = 0, comm_world = 1;
+  // genome row over NVLink peer memory (comm.cu): every rank's receive area is mapped into all the others
+  DevBuf p2p_buf;                     // [2 parities][world][p2p_row_cap] int64 + arrival flags [2][world] u64 + epoch u64
+  void* p2p_peer[GCI_MAX_RANKS] = {}; // receive areas as mapped in this process (own rank: p2p_buf.p)
+  int64_t p2p_row_cap = 0;            // int64 words per row the area was sized for
+  bool p2p_ok = false;                // all peers mapped: gci_enqueue_genome_row pushes instead of calling NCCL
 
   // CUDA-graph replay of gci_pipeline / gci_pipeline_row (filter.cu).  With the stage timers off, the second
   // call with an unchanged signature (arguments, read-set sizes, device buffers, `epoch`) is captured into a

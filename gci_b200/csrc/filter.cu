@@ -1376,7 +1376,7 @@ static std::vector<char> pipeline_signature(gci_ctx* ctx, const PipeArgs& a) {
   put(&a.ip, 8); put(&a.cp, 8); put(&a.op, 8); put(&a.dp, 8);
   put64(a.with_rows); put64(a.sum_len); put64(a.cap); put64(a.world); put64(a.n_sel);
   put64((int64_t)ctx->epoch); put64((int64_t)ctx->alloc_gen); put64((int64_t)(intptr_t)ctx->stream);
-  put64((int64_t)(intptr_t)ctx->nccl_comm); put64(ctx->n_reads); put64((int64_t)ctx->n_files);
+  put64((int64_t)(intptr_t)ctx->nccl_comm); put64(ctx->p2p_ok); put64(ctx->n_reads); put64((int64_t)ctx->n_files);
   put64((int64_t)ctx->n_bam); put64((int64_t)ctx->n_paf);
   for (size_t i = 0; i < ctx->n_files; i++) {
     const FileTable& f = ctx->files[i];
@@ -1528,6 +1528,12 @@ int gci_pipeline_row(gci_ctx* ctx, int32_t track, int32_t map_qual, int32_t mq_c
   }
   if (rows) {
     memcpy(rows, out.h_rows, 8 * (size_t)a.row_n * a.world);
+    for (int r = 0; r < a.world; r++)
+      if (rows[(size_t)r * a.row_n + 3] < 0) {
+        ctx->p2p_ok = false;
+        ctx->drop_graph();
+        return ctx->fail(GCI_E_CUDA, "gci_pipeline_row: rank %d did not deliver its row over peer memory in time", r);
+      }
     for (int r = 0; r < a.world; r++)
       if (rows[(size_t)r * a.row_n + 3] > cap)
         return ctx->fail(GCI_E_ARG, "gci_pipeline_row: rank %d has more curated lengths than cap", r);

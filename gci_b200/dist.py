@@ -83,13 +83,36 @@ def allgather_varlen(arr):
     return [o[:s].cpu().numpy().astype(orig) for o, s in zip(outs, sizes)]
 
 
-def init_native_comm(ctx):
+def init_native_comm(ctx, p2p=True, cap=2048):
     """Create the library's own NCCL communicator (Context.genome_row): rank 0 makes the id, everybody gets it."""
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
     uid = ctx.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)
     uid = allreduce(uid.astype(np.int64), "sum").astype(np.uint8)
     ctx.comm_init(uid, rank, world)
+    ctx.row_exchange = "ncclAllGather"
+    import os
+    if os.environ.get("GCI_P2P", "1").startswith("0"):
+        p2p = False
+    if world > 1 and p2p:
+        # genome row over NVLink peer memory: all-gather the CUDA IPC handles of the receive areas, map the peers.
+        # Every rank must end up on the same path, so the outcome is agreed on before anybody uses it.
+        handles = np.zeros((world, 64), np.int64)
+        ok = 1
+        try:
+            handles[rank] = ctx.comm_p2p_alloc(cap)
+        except Exception:
+            ok = 0
+        handles = allreduce(handles, "sum").astype(np.uint8)
+        if int(allreduce(np.array([1 - ok], np.int64), "max")[0]) == 0:
+            try:
+                ctx.comm_p2p_open(handles)
+            except Exception:
+                ok = 0
+        if int(allreduce(np.array([1 - ok], np.int64), "max")[0]) != 0:
+            ctx.comm_p2p_disable()
+        else:
+            ctx.row_exchange = "stores into NVLink peer memory (CUDA IPC), one kernel"
 
 
 def assign_contigs(lengths, weights, world):

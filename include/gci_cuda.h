@@ -194,6 +194,14 @@ int gci_pipeline(gci_ctx* ctx, int32_t track, int32_t map_qual, int32_t mq_cutof
 typedef struct { char internal[128]; } gci_nccl_id;
 int gci_comm_unique_id(gci_nccl_id* out);
 int gci_comm_init(gci_ctx* ctx, const gci_nccl_id* id, int32_t rank, int32_t world);
+/* Optional, after gci_comm_init: exchange the genome row over NVLink peer memory instead of ncclAllGather
+   (the exchange is 16 KB per rank, i.e. pure latency).  Every rank allocates a receive area for rows of up to
+   4 + cap words and gets its CUDA IPC handle; the caller all-gathers the handles (any transport) and every
+   rank maps its peers.  If mapping fails the NCCL exchange stays in use. */
+typedef struct { char internal[64]; } gci_ipc_handle;
+int gci_comm_p2p_alloc(gci_ctx* ctx, int64_t cap, gci_ipc_handle* out);
+int gci_comm_p2p_open(gci_ctx* ctx, const gci_ipc_handle* handles /* [world] */);
+int gci_comm_p2p_disable(gci_ctx* ctx);          /* back to ncclAllGather (every rank must do the same) */
 /* gci_score_terms_sums for this rank's contigs + ONE ncclAllGather (on the context's stream) of the terms
    every rank needs for the genome row / mean depth (GCI.py:572-587, :862-868):
    rows[r * (4 + cap) ...] = { sum depth, sum length, curated contigs, n lengths, curated lengths[cap] } of rank r.
