@@ -7,8 +7,8 @@ mkdir -p $O
 run() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 "$@"; }
 echo "== bench graph x$N" >> $O/${TAG}_steps.log
 run bench.py --gpus $N --steps 100 --warmup 5 > $O/${TAG}_bench_x$N.json 2> $O/${TAG}_bench_x$N.err; echo "   exit $?" >> $O/${TAG}_steps.log
-echo "== bench eager x$N" >> $O/${TAG}_steps.log
-GCI_GRAPH=0 run bench.py --gpus $N --steps 100 --warmup 5 > $O/${TAG}_bench_eager_x$N.json 2> $O/${TAG}_bench_eager_x$N.err; echo "   exit $?" >> $O/${TAG}_steps.log
+echo "== bench nccl x$N" >> $O/${TAG}_steps.log
+GCI_P2P=0 run bench.py --gpus $N --steps 100 --warmup 5 > $O/${TAG}_bench_nccl_x$N.json 2> $O/${TAG}_bench_nccl_x$N.err; echo "   exit $?" >> $O/${TAG}_steps.log
 echo "== bench graph x1" >> $O/${TAG}_steps.log
 timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > $O/${TAG}_bench_x1.json 2> $O/${TAG}_bench_x1.err; echo "   exit $?" >> $O/${TAG}_steps.log
 echo "== pytest two ranks" >> $O/${TAG}_steps.log
