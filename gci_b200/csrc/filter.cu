@@ -197,18 +197,21 @@ struct GateArgs {
 
 __device__ __forceinline__ void gate_one(const GateArgs& g, int64_t r, uint32_t sMx, uint32_t sI, uint32_t sD,
                                          uint32_t sN, uint32_t sS) {
+  // every column of the record is requested up front: behind the early returns below the loads would be issued
+  // one after the other, six DRAM round trips deep
+  const int32_t start = g.ref_start[r];
+  const int32_t c = g.ref_id[r];
+  const uint32_t f = g.flag[r];
+  const int32_t mq = g.mapq[r];
+  const int32_t nmv = g.nm[r];
+  const uint32_t q = g.read_id[r];
   const long long Mx = sMx, I = sI, D = sD, N = sN, S = sS;
   long long rlen = Mx + D + N;                       // htslib bam_cigar2rlen
   if (rlen == 0) rlen = 1;                           // htslib bam_endpos
-  const int32_t start = g.ref_start[r];
   g.ref_end[r] = (int32_t)(start + rlen);
-  const int32_t c = g.ref_id[r];
   if (c < 0 || c >= g.n_contigs || !g.selected[c]) return;       // never fetched (GCI.py:151, :202-207)
-  const uint32_t f = g.flag[r];
   if (f & (0x4u | 0x100u | 0x800u)) return;                      // :153-156
-  const int32_t mq = g.mapq[r];
   if (mq < g.map_qual) return;                                   // :156
-  const int32_t nmv = g.nm[r];
   if (nmv == INT32_MIN) {                                        // KeyError at :163
     atomicOr(g.err, 1ull);
     atomicMin(g.err + 1, (unsigned long long)r);
@@ -229,7 +232,6 @@ __device__ __forceinline__ void gate_one(const GateArgs& g, int64_t r, uint32_t 
     return;
   }
   if (!((double)(Mx - mm) / (double)d2 >= g.ip)) return;
-  const uint32_t q = g.read_id[r];
   if (q >= g.n_reads) return;
   // fetch order = contigs in header order, file order inside: the later record wins (:166, :269)
   atomicMax(g.win + q, ((long long)c << 32) | (long long)r);
