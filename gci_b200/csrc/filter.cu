@@ -1384,7 +1384,10 @@ static std::vector<char> pipeline_signature(gci_ctx* ctx, const PipeArgs& a) {
     const FileTable& f = ctx->files[i];
     put64(f.paf >= 0 ? 2 : f.kind); put64(f.src); put64(f.paf); put64(f.paf >= 0 ? 0 : f.n);
   }
-  for (size_t i = 0; i < ctx->n_bam; i++) { put64(ctx->bam[i].n); put64(ctx->bam[i].n_ops); put64(ctx->bam[i].n_dense); }
+  for (size_t i = 0; i < ctx->n_bam; i++) {
+    const BamFile& b = ctx->bam[i];
+    put64(b.n); put64(b.n_ops); put64(b.n_dense); put64(b.n_span);   // grids and list lengths of the CIGAR / gate kernels
+  }
   for (size_t i = 0; i < ctx->n_paf; i++) put64(ctx->paf[i].n);
   return sig;
 }
@@ -1503,6 +1506,11 @@ int gci_pipeline_row(gci_ctx* ctx, int32_t track, int32_t map_qual, int32_t mq_c
         cudaGetLastError();
         ctx->launches = launches0;
         ctx->pipe_sig_bad = sig;          // do not try again for this step shape
+        // nothing recorded has run: a table upload that was captured (it is what aborts a capture) never
+        // reached the device, so the host-side "already uploaded" marks must not survive
+        ctx->lay_cache.clear();
+        ctx->ob_cache.clear();
+        ctx->owner_of_stale = true;
       }
     }
     if (!done) GCI_TRY(pipeline_enqueue(ctx, a, &out));

@@ -1,6 +1,7 @@
 #!/bin/bash
-# Shorter GPU call: parity tests, bench, CIGAR stage benches, 3.1 Gbp stage table, sanitizer, ncu of the CIGAR kernels.
-TAG="${1:-run}"
+# One gpurun call that produces the evidence set copied to profiles/ by tools/collect_profiles.py: parity tests, bench
+# + reference arm, CIGAR stage benches, 3.1 Gbp stage table, sanitizer, ncu launch list and --set full captures.
+#   gpurun --timeout 1000 -- "bash tools/gpu_evidence.sh r02a"
 O=gpurun_out
 mkdir -p $O
 step() { echo "== $1" >> $O/${TAG}_steps.log; shift; "$@"; echo "   exit $?" >> $O/${TAG}_steps.log; }

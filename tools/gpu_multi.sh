@@ -1,6 +1,6 @@
 #!/bin/bash
-# N-GPU call: the bench through torchrun (graph replay incl. the NCCL genome row) and eager for comparison,
-# plus the two-rank GPU test.   gpurun --gpus 2 --timeout 600 -- 'bash tools/gpu_round_multi.sh r01k 2'
+# N-GPU call: the bench through torchrun with the peer-memory row exchange and with ncclAllGather (GCI_P2P=0),
+# the single-GPU line of the same box, the two-rank GPU test.   gpurun --gpus 2 --timeout 600 -- "bash tools/gpu_multi.sh r02b 2"
 TAG="${1:-run}"; N="${2:-2}"
 O=gpurun_out
 mkdir -p $O
