@@ -2,6 +2,7 @@
 # One gpurun call that produces the evidence set copied to profiles/ by tools/collect_profiles.py: parity tests, bench
 # + reference arm, CIGAR stage benches, 3.1 Gbp stage table, sanitizer, ncu launch list and --set full captures.
 #   gpurun --timeout 1000 -- "bash tools/gpu_evidence.sh r02a"
+TAG="${1:-run}"   # tag of the output files under gpurun_out/
 O=gpurun_out
 mkdir -p $O
 step() { echo "== $1" >> $O/${TAG}_steps.log; shift; "$@"; echo "   exit $?" >> $O/${TAG}_steps.log; }
