@@ -165,16 +165,28 @@ def _fasta_parse(path, fmt):
 
 
 def import_reference():
-    for n in ["pysam", "Bio", "Bio.SeqIO", "matplotlib", "matplotlib.pyplot", "matplotlib.lines", "matplotlib.ticker"]:
+    """The unmodified reference as a module (under its own name: the repo's drop-in CLI is a `GCI` module too).
+    The shims only have to be in sys.modules while the reference's `import` statements run."""
+    import importlib.util
+    shim_names = ["pysam", "Bio", "Bio.SeqIO", "matplotlib", "matplotlib.pyplot", "matplotlib.lines", "matplotlib.ticker"]
+    saved = {n: sys.modules.get(n) for n in shim_names}
+    for n in shim_names:
         sys.modules[n] = types.ModuleType(n)
     sys.modules["pysam"].AlignmentFile = AlignmentFile
     sys.modules["Bio.SeqIO"].parse = _fasta_parse
     sys.modules["Bio"].SeqIO = sys.modules["Bio.SeqIO"]
     sys.modules["matplotlib.ticker"].AutoMinorLocator = object
-    tmp = tempfile.mkdtemp(prefix="gci_ref_")
-    shutil.copy(os.path.join(REF, "GCI.py"), os.path.join(tmp, "GCI.py"))
-    sys.path.insert(0, tmp)
-    import GCI as ref  # the unmodified reference
+    try:
+        spec = importlib.util.spec_from_file_location("gci_reference_unmodified", os.path.join(REF, "GCI.py"))
+        ref = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = ref   # multiprocessing pickles read_sam by module name (GCI.py:267-270)
+        spec.loader.exec_module(ref)   # the unmodified reference, read where it lies
+    finally:
+        for n, m in saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m
     return ref
 
 
@@ -330,11 +342,11 @@ def make_filter_cases(ref):
         json.dump(meta, f, indent=1)
 
 
-def make_random_cases(ref, n_cases=16):
+def make_random_cases(ref, n_cases=16, seed=20240633, prefix="rand", save=True):
     """Seeded random small cases over the whole argument space (gates, flank, threshold, -dp, file mixes, --chrs,
     -R regions, contig lengths next to tile borders and below 2 * flank) -> filter_cases_rand.{npz,json}."""
     store, meta = {}, {"cases": [], "reference_commit": "455e19c7"}
-    rng = np.random.default_rng(20240633)
+    rng = np.random.default_rng(seed)
     combos = [("bam",), ("bam", "bam"), ("bam", "paf"), ("paf", "bam"), ("bam", "paf", "bam"), ("bam", "bam", "bam"),
               ("paf", "paf", "bam")]
     special = [1023, 1024, 1025, 2047, 2048, 2049, 3072, 4000, 40, 90]
@@ -364,15 +376,17 @@ def make_random_cases(ref, n_cases=16):
                 a, b = sorted(int(x) for x in rng.integers(0, lengths[c] + 1, 2))
                 regions.append((names[c], a, b))
         try:
-            make_case(ref, f"rand{k:02d}", store, meta, lengths=lengths, seed=500 + k, hifi=hifi, nano=nano, args=args,
+            make_case(ref, f"{prefix}{k:02d}", store, meta, lengths=lengths, seed=(0 if seed == 20240633 else seed % 100000) + 500 + k, hifi=hifi, nano=nano, args=args,
                       chrs=chrs, regions=regions, coverage=float(rng.choice([6.0, 12.0, 25.0])))
         except (Exception, SystemExit) as e:   # the reference itself gives up on this input: not a parity case
-            print(f"case rand{k:02d}: reference raised {type(e).__name__}: {e}")
-            for key in [x for x in store if x.startswith(f"rand{k:02d}.")]:
+            print(f"case {prefix}{k:02d}: reference raised {type(e).__name__}: {e}")
+            for key in [x for x in store if x.startswith(f"{prefix}{k:02d}.")]:
                 del store[key]
-    np.savez_compressed(os.path.join(HERE, "filter_cases_rand.npz"), **store)
-    with open(os.path.join(HERE, "filter_cases_rand.json"), "w") as f:
-        json.dump(meta, f, indent=1)
+    if save:
+        np.savez_compressed(os.path.join(HERE, "filter_cases_rand.npz"), **store)
+        with open(os.path.join(HERE, "filter_cases_rand.json"), "w") as f:
+            json.dump(meta, f, indent=1)
+    return store, meta
 
 
 def make_mh63():

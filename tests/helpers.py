@@ -47,9 +47,11 @@ def case_names():
     return [c["name"] for c in meta["cases"]]
 
 
-def load_case(name):
-    """-> (case meta, kwargs for run_gci-style drivers, expected outputs)."""
-    store, meta = golden_store()
+def load_case(name, store=None, meta=None):
+    """-> (case meta, kwargs for run_gci-style drivers, expected outputs); from the committed fixtures unless a
+    freshly generated (store, meta) pair is given."""
+    if store is None:
+        store, meta = golden_store()
     case = next(c for c in meta["cases"] if c["name"] == name)
     kw = dict(names=case["names"], lengths=case["lengths"], n_runs=[[tuple(iv) for iv in r] for r in case["n_runs"]],
               chrs=case["chrs"], regions=[tuple(r) for r in case["regions"]] if case["regions"] else None,
