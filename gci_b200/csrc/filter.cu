@@ -12,14 +12,14 @@
 // ================================================================================================
 // K1  cigar_stats: segmented sum of CIGAR op lengths per record, tiled over the op stream
 // ================================================================================================
-// The packed op stream (uint32 `len << 4 | op`, BAM native) is cut into tiles of CIG_TILE ops.  One
-// CTA stages its tile in shared memory with a single TMA bulk copy (cp.async.bulk, 8 KB), each
-// thread walks 8 consecutive ops and accumulates five class sums
+// The packed op stream (uint32 `len << 4 | op`, BAM native) is cut into tiles of CIG_TILE ops and summed
+// into five classes per record
 //     Mx = M + '=' + X,  I,  D,  N,  S
-// (the reference only ever uses M+eq+X as one quantity: GCI.py:164-165; N is needed for
-// reference_end).  Records that lie completely inside the tile are written with plain stores, records
-// cut by a tile border are combined with global atomics.  Work per CTA is constant whatever the
-// ops-per-record distribution (HiFi ~30, ONT 10^3..10^5).
+// (the reference only ever uses M+eq+X as one quantity: GCI.py:164-165; N is needed for reference_end).
+// Two kernels share the tiles (split once at upload, cigar_tile_class_kernel): K1a takes the tiles that touch
+// many records (HiFi: ~70 records per tile) and gates the records it sees completely on the spot; K1b streams
+// the tiles that lie inside one or a few long records (ONT: thousands of ops per record).  Work per tile is
+// constant whatever the ops-per-record distribution.
 constexpr int CIG_THREADS = 256;
 constexpr int CIG_OPT = 8;                       // ops per thread
 constexpr int CIG_TILE = CIG_THREADS * CIG_OPT;  // 2048 ops = 8 KB
@@ -103,50 +103,6 @@ struct CigAcc {
     d += (c == 2u) ? l : 0u;
     n += (c == 3u) ? l : 0u;
     s += (c == 4u) ? l : 0u;
-  }
-  // 8 ops of one thread.  N, S, H, P, B only occur at the ends of a read, so the common case needs three
-  // counters (tot, I, D); one test on the OR of the one-hot op codes decides per thread.
-  __device__ __forceinline__ void add8(const uint32_t (&op)[8]) {
-    uint32_t seen = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) seen |= 1u << (op[k] & 15u);
-    if (seen & 0xFE78u) {
-#pragma unroll
-      for (int k = 0; k < 8; k++) add(op[k]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const uint32_t c = op[k] & 15u, l = op[k] >> 4;
-        tot += l;
-        i += (c == 1u) ? l : 0u;
-        d += (c == 2u) ? l : 0u;
-      }
-    }
-  }
-  // 16 ops of one lane (four 16-byte loads).  1 << (w & 31) marks bit c or c + 16 (bit 4 of w is the low
-  // bit of the length): one funnel shift per op instead of mask + shift
-  __device__ __forceinline__ void add16(const uint4 (&q)[4]) {
-    uint32_t seen = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      seen |= __funnelshift_l(0u, 1u, q[k].x) | __funnelshift_l(0u, 1u, q[k].y) | __funnelshift_l(0u, 1u, q[k].z) |
-              __funnelshift_l(0u, 1u, q[k].w);
-    if ((seen | (seen >> 16)) & 0xFE78u) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) { add(q[k].x); add(q[k].y); add(q[k].z); add(q[k].w); }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t w[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint32_t c = w[j] & 15u, l = w[j] >> 4;
-          tot += l;
-          i += (c == 1u) ? l : 0u;
-          d += (c == 2u) ? l : 0u;
-        }
-      }
-    }
   }
   __device__ __forceinline__ bool any() const { return (tot | n | s) != 0; }
   __device__ __forceinline__ void warp_reduce() {   // REDUX.SUM: one instruction per counter
