@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <string>
 #include <string_view>
 #include <thread>
@@ -73,18 +74,92 @@ struct gci_interner {
   std::vector<const std::string*> order;
 };
 
+// One BAM file decoded into columns.  The file is never inflated as a whole: gci_bam_open streams it through a
+// window of a few hundred MB (parallel inflate of the window's BGZF blocks, sequential walk over the record
+// sizes, parallel field extraction into the columns; a record cut by the window border is carried into the
+// next window), so host memory stays bounded for BAMs of any size.
 struct gci_bam {
-  uint8_t* data = nullptr;                   // inflated BAM stream (uninitialised allocation: the inflate
-  size_t data_n = 0;                         // threads fault the pages in parallel)
-  ~gci_bam() { free(data); }
   std::vector<std::string> ref_names;
   std::vector<int64_t> ref_lens;
-  std::vector<size_t> rec_off;               // offset of every record's block_size field
+  std::vector<int32_t> ref_id, ref_start, nm, qlen;
+  std::vector<uint8_t> mapq;
+  std::vector<uint16_t> flag;
   std::vector<uint64_t> cig_off;             // [n+1]
-  std::vector<uint8_t> cg;                   // record uses the CG tag for its CIGAR
-  std::vector<size_t> cg_off;                // offset of the CG payload (first op) when cg[i]
+  std::vector<uint32_t> cigar;
+  std::vector<uint64_t> name_off;            // [n+1] into names
+  std::vector<char> names;                   // read names back to back (no terminators)
   int threads = 1;
 };
+
+namespace {
+// inflated bytes per window (plus the carried tail); GCI_IO_WINDOW_BYTES overrides it (tests use tiny windows)
+inline size_t bam_window_bytes() {
+  const char* e = getenv("GCI_IO_WINDOW_BYTES");
+  const long long v = e ? atoll(e) : 0;
+  return v > 0 ? (size_t)v : size_t(256) << 20;
+}
+
+// number of CIGAR ops of the record at r (CG:B,I long-CIGAR convention, SAM spec §4.2.2); *cg = first op of the
+// CG payload or NULL
+inline uint64_t bam_record_ops(const uint8_t* r, const uint8_t** cg) {
+  *cg = nullptr;
+  const uint32_t n_cig = rd16(r + 16);
+  if (n_cig != 2) return n_cig;
+  const int32_t l_seq = rdi32(r + 20);
+  const uint8_t l_name = r[12];
+  const uint8_t* cig = r + 36 + l_name;
+  const uint32_t o0 = rd32(cig), o1 = rd32(cig + 4);
+  if (!((o0 & 15) == 4 && (int32_t)(o0 >> 4) == l_seq && (o1 & 15) == 3)) return n_cig;
+  const uint8_t* end = r + 4 + rdi32(r);
+  const uint8_t* x = cig + 8 + (l_seq + 1) / 2 + l_seq;
+  while (x + 3 <= end) {
+    const uint8_t t = x[2];
+    if (x[0] == 'C' && x[1] == 'G' && t == 'B' && x[3] == 'I') {
+      *cg = x + 8;
+      return rd32(x + 4);
+    }
+    x += 3;
+    if (t == 'A' || t == 'c' || t == 'C') x += 1;
+    else if (t == 's' || t == 'S') x += 2;
+    else if (t == 'i' || t == 'I' || t == 'f') x += 4;
+    else if (t == 'Z' || t == 'H') { while (x < end && *x) x++; x++; }
+    else if (t == 'B') {
+      const uint8_t st = x[0];
+      const uint32_t cnt = rd32(x + 1);
+      const int sz = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+      x += 5 + (size_t)cnt * sz;
+    } else break;
+  }
+  return n_cig;
+}
+
+// NM aux value of the record at r (any integer type), INT32_MIN if absent
+inline int32_t bam_record_nm(const uint8_t* r) {
+  const uint8_t* end = r + 4 + rdi32(r);
+  const uint8_t l_name = r[12];
+  const uint32_t n_cig = rd16(r + 16);
+  const int32_t l_seq = rdi32(r + 20);
+  int32_t nmv = INT32_MIN;
+  const uint8_t* x = r + 36 + l_name + 4 * (size_t)n_cig + (l_seq + 1) / 2 + l_seq;
+  while (x + 3 <= end) {
+    const uint8_t t = x[2];
+    const bool is_nm = x[0] == 'N' && x[1] == 'M';
+    x += 3;
+    if (t == 'A' || t == 'c' || t == 'C') { if (is_nm) nmv = t == 'c' ? (int8_t)x[0] : x[0]; x += 1; }
+    else if (t == 's' || t == 'S') { if (is_nm) nmv = t == 's' ? (int16_t)rd16(x) : rd16(x); x += 2; }
+    else if (t == 'i' || t == 'I' || t == 'f') { if (is_nm && t != 'f') nmv = rdi32(x); x += 4; }
+    else if (t == 'Z' || t == 'H') { while (x < end && *x) x++; x++; }
+    else if (t == 'B') {
+      const uint8_t st = x[0];
+      const uint32_t cnt = rd32(x + 1);
+      const int sz = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+      x += 5 + (size_t)cnt * sz;
+    } else break;
+    if (is_nm && nmv != INT32_MIN) break;
+  }
+  return nmv;
+}
+}  // namespace
 
 extern "C" {
 
@@ -101,9 +176,9 @@ int gci_bam_open(const char* path, int threads, gci_bam** out) {
   MappedFile f;
   if (!f.open(path)) return fail(std::string("cannot open ") + path);
   // pass 1: walk the BGZF block headers (BSIZE in the BC extra field, ISIZE in the trailer)
-  struct Blk { size_t src, clen, dst, ulen; };
+  struct Blk { size_t src, clen, ulen; };
   std::vector<Blk> blocks;
-  size_t pos = 0, total = 0;
+  size_t pos = 0;
   while (pos + 18 <= f.n) {
     const uint8_t* b = f.p + pos;
     if (!(b[0] == 0x1f && b[1] == 0x8b && b[2] == 8 && (b[3] & 4))) return fail("not a BGZF block");
@@ -116,105 +191,150 @@ int gci_bam_open(const char* path, int threads, gci_bam** out) {
       k += 4 + slen;
     }
     if (bsize == 0 || pos + bsize > f.n) return fail("BGZF block without BSIZE / truncated file");
-    const size_t ulen = rd32(b + bsize - 4);
-    blocks.push_back({pos + 12 + xlen, bsize - 12 - xlen - 8, total, ulen});
-    total += ulen;
+    blocks.push_back({pos + 12 + xlen, bsize - 12 - xlen - 8, (size_t)rd32(b + bsize - 4)});
     pos += bsize;
   }
-  auto* bam = new gci_bam();
+  std::unique_ptr<gci_bam> bam(new gci_bam());
   bam->threads = std::max(1, threads);
-  bam->data = (uint8_t*)malloc(total ? total : 1);
-  bam->data_n = total;
-  if (!bam->data) { delete bam; return fail("out of memory"); }
-  // pass 2: inflate the blocks in parallel
-  std::atomic<int> bad{0};
-  parallel_for((int64_t)blocks.size(), bam->threads, [&](int64_t a, int64_t b, int) {
-    z_stream zs;
-    memset(&zs, 0, sizeof zs);
-    if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
-    for (int64_t i = a; i < b; i++) {
-      const Blk& k = blocks[i];
-      if (k.ulen == 0) continue;
-      inflateReset(&zs);
-      zs.next_in = const_cast<Bytef*>(f.p + k.src);
-      zs.avail_in = (uInt)k.clen;
-      zs.next_out = bam->data + k.dst;
-      zs.avail_out = (uInt)k.ulen;
-      const int rc = inflate(&zs, Z_FINISH);
-      if (rc != Z_STREAM_END || zs.avail_out != 0) { bad = 1; break; }
+  bam->cig_off.push_back(0);
+  bam->name_off.push_back(0);
+
+  // pass 2: window by window
+  uint8_t* buf = nullptr;                    // [carried tail of the previous window | this window, inflated]
+  size_t buf_cap = 0, carry = 0;
+  struct Free { uint8_t*& p; ~Free() { free(p); } } free_buf{buf};
+  bool header_done = false;
+  const size_t window_bytes = bam_window_bytes();
+  std::vector<size_t> dst, rec_off;
+  std::vector<uint64_t> ops;
+  std::vector<const uint8_t*> cg;
+  for (size_t w0 = 0; w0 < blocks.size();) {
+    size_t w1 = w0, win = 0;
+    dst.clear();
+    while (w1 < blocks.size() && (w1 == w0 || win + blocks[w1].ulen <= window_bytes)) {
+      dst.push_back(win);
+      win += blocks[w1].ulen;
+      w1++;
     }
-    inflateEnd(&zs);
-  });
-  if (bad) { delete bam; return fail("BGZF inflate failed"); }
-  // header
-  struct View { const uint8_t* p; size_t n; const uint8_t* data() const { return p; } size_t size() const { return n; } };
-  const View d{bam->data, bam->data_n};
-  if (d.size() < 12 || memcmp(d.data(), "BAM\1", 4) != 0) { delete bam; return fail("not a BAM file"); }
-  size_t p = 8 + (size_t)rdi32(d.data() + 4);
-  if (p + 4 > d.size()) { delete bam; return fail("truncated BAM header"); }
-  const int32_t n_ref = rdi32(d.data() + p);
-  p += 4;
-  for (int32_t i = 0; i < n_ref; i++) {
-    if (p + 4 > d.size()) { delete bam; return fail("truncated BAM header"); }
-    const int32_t l_name = rdi32(d.data() + p);
-    if (p + 8 + (size_t)l_name > d.size()) { delete bam; return fail("truncated BAM header"); }
-    bam->ref_names.emplace_back((const char*)d.data() + p + 4, (size_t)std::max(0, l_name - 1));
-    bam->ref_lens.push_back(rdi32(d.data() + p + 4 + l_name));
-    p += 8 + l_name;
-  }
-  // record boundaries (sequential: each record names its own size)
-  while (p + 4 <= d.size()) {
-    const int32_t bs = rdi32(d.data() + p);
-    if (bs < 32 || p + 4 + (size_t)bs > d.size()) { delete bam; return fail("corrupt BAM record"); }
-    bam->rec_off.push_back(p);
-    p += 4 + (size_t)bs;
-  }
-  // per-record CIGAR length (CG tag aware), in parallel
-  const int64_t n = (int64_t)bam->rec_off.size();
-  bam->cig_off.assign(n + 1, 0);
-  bam->cg.assign(n, 0);
-  bam->cg_off.assign(n, 0);
-  parallel_for(n, bam->threads, [&](int64_t a, int64_t b, int) {
-    for (int64_t i = a; i < b; i++) {
-      const uint8_t* r = d.data() + bam->rec_off[i];
-      const uint32_t n_cig = rd16(r + 16);
-      uint64_t ops = n_cig;
-      if (n_cig == 2) {
-        const int32_t l_seq = rdi32(r + 20);
-        const uint8_t l_name = r[12];
-        const uint8_t* cig = r + 36 + l_name;
-        const uint32_t o0 = rd32(cig), o1 = rd32(cig + 4);
-        if ((o0 & 15) == 4 && (int32_t)(o0 >> 4) == l_seq && (o1 & 15) == 3) {
-          // long CIGAR placeholder (SAM spec §4.2.2): look for CG:B,I
-          const uint8_t* end = r + 4 + rdi32(r);
-          const uint8_t* x = cig + 8 + (l_seq + 1) / 2 + l_seq;
-          while (x + 3 <= end) {
-            const uint8_t t = x[2];
-            if (x[0] == 'C' && x[1] == 'G' && t == 'B' && x[3] == 'I') {
-              ops = rd32(x + 4);
-              bam->cg[i] = 1;
-              bam->cg_off[i] = (size_t)(x + 8 - d.data());
-              break;
-            }
-            x += 3;
-            if (t == 'A' || t == 'c' || t == 'C') x += 1;
-            else if (t == 's' || t == 'S') x += 2;
-            else if (t == 'i' || t == 'I' || t == 'f') x += 4;
-            else if (t == 'Z' || t == 'H') { while (x < end && *x) x++; x++; }
-            else if (t == 'B') {
-              const uint8_t st = x[0];
-              const uint32_t cnt = rd32(x + 1);
-              const int sz = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
-              x += 5 + (size_t)cnt * sz;
-            } else break;
-          }
-        }
+    if (carry + win > buf_cap) {
+      const size_t want = carry + win + (carry + win) / 8;
+      uint8_t* nb = (uint8_t*)malloc(want);       // malloc + memcpy of the tail: realloc would copy everything
+      if (!nb) return fail("out of memory");
+      if (carry) memcpy(nb, buf, carry);
+      free(buf);
+      buf = nb;
+      buf_cap = want;
+    }
+    std::atomic<int> bad{0};
+    parallel_for((int64_t)(w1 - w0), bam->threads, [&](int64_t a, int64_t b, int) {
+      z_stream zs;
+      memset(&zs, 0, sizeof zs);
+      if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+      for (int64_t i = a; i < b; i++) {
+        const Blk& k = blocks[w0 + i];
+        if (k.ulen == 0) continue;
+        inflateReset(&zs);
+        zs.next_in = const_cast<Bytef*>(f.p + k.src);
+        zs.avail_in = (uInt)k.clen;
+        zs.next_out = buf + carry + dst[i];
+        zs.avail_out = (uInt)k.ulen;
+        const int rc = inflate(&zs, Z_FINISH);
+        if (rc != Z_STREAM_END || zs.avail_out != 0) { bad = 1; break; }
       }
-      bam->cig_off[i + 1] = ops;
+      inflateEnd(&zs);
+    });
+    if (bad) return fail("BGZF inflate failed");
+    const size_t avail = carry + win;
+    size_t p = 0;
+    if (!header_done) {
+      // magic, l_text, text, n_ref, (l_name, name, l_ref) x n_ref: parse only once it is completely here
+      bool complete = false;
+      do {
+        if (avail < 12) break;
+        if (memcmp(buf, "BAM\1", 4) != 0) return fail("not a BAM file");
+        const int32_t l_text = rdi32(buf + 4);
+        if (l_text < 0) return fail("corrupt BAM header");
+        size_t q = 8 + (size_t)l_text;
+        if (q + 4 > avail) break;
+        const int32_t n_ref = rdi32(buf + q);
+        if (n_ref < 0) return fail("corrupt BAM header");
+        q += 4;
+        std::vector<std::string> names;
+        std::vector<int64_t> lens;
+        bool cut = false;
+        for (int32_t i = 0; i < n_ref; i++) {
+          if (q + 4 > avail) { cut = true; break; }
+          const int32_t l_name = rdi32(buf + q);
+          if (l_name < 0) return fail("corrupt BAM header");
+          if (q + 8 + (size_t)l_name > avail) { cut = true; break; }
+          names.emplace_back((const char*)buf + q + 4, (size_t)std::max(0, l_name - 1));
+          lens.push_back(rdi32(buf + q + 4 + l_name));
+          q += 8 + (size_t)l_name;
+        }
+        if (cut) break;
+        bam->ref_names.swap(names);
+        bam->ref_lens.swap(lens);
+        p = q;
+        complete = true;
+      } while (false);
+      if (!complete) {                           // header longer than what has been inflated so far
+        carry = avail;
+        w0 = w1;
+        continue;
+      }
+      header_done = true;
     }
-  });
-  for (int64_t i = 0; i < n; i++) bam->cig_off[i + 1] += bam->cig_off[i];
-  *out = bam;
+    // record boundaries (sequential: each record names its own size)
+    rec_off.clear();
+    while (p + 4 <= avail) {
+      const int32_t bs = rdi32(buf + p);
+      if (bs < 32) return fail("corrupt BAM record");
+      if (p + 4 + (size_t)bs > avail) break;      // cut by the window border: carried over
+      rec_off.push_back(p);
+      p += 4 + (size_t)bs;
+    }
+    const int64_t m = (int64_t)rec_off.size();
+    const size_t n0 = bam->ref_id.size();
+    // CIGAR and name sizes of the window's records, then their places in the columns
+    ops.assign((size_t)m, 0);
+    cg.assign((size_t)m, nullptr);
+    parallel_for(m, bam->threads, [&](int64_t a, int64_t b, int) {
+      for (int64_t i = a; i < b; i++) ops[i] = bam_record_ops(buf + rec_off[i], &cg[i]);
+    });
+    bam->cig_off.resize(n0 + m + 1);
+    bam->name_off.resize(n0 + m + 1);
+    for (int64_t i = 0; i < m; i++) {
+      const uint8_t l_name = buf[rec_off[i] + 12];
+      bam->cig_off[n0 + i + 1] = bam->cig_off[n0 + i] + ops[i];
+      bam->name_off[n0 + i + 1] = bam->name_off[n0 + i] + (l_name ? (uint64_t)l_name - 1 : 0);
+    }
+    bam->ref_id.resize(n0 + m); bam->ref_start.resize(n0 + m); bam->nm.resize(n0 + m); bam->qlen.resize(n0 + m);
+    bam->mapq.resize(n0 + m); bam->flag.resize(n0 + m);
+    bam->cigar.resize((size_t)bam->cig_off[n0 + m]);
+    bam->names.resize((size_t)bam->name_off[n0 + m]);
+    parallel_for(m, bam->threads, [&](int64_t a, int64_t b, int) {
+      for (int64_t i = a; i < b; i++) {
+        const uint8_t* r = buf + rec_off[i];
+        const size_t k = n0 + (size_t)i;
+        const uint8_t l_name = r[12];
+        bam->ref_id[k] = rdi32(r + 4);
+        bam->ref_start[k] = rdi32(r + 8);
+        bam->mapq[k] = r[13];
+        bam->flag[k] = rd16(r + 18);
+        bam->qlen[k] = rdi32(r + 20);
+        const uint8_t* cig = cg[i] ? cg[i] : r + 36 + l_name;
+        memcpy(bam->cigar.data() + bam->cig_off[k], cig, 4 * (size_t)ops[i]);
+        bam->nm[k] = bam_record_nm(r);
+        memcpy(bam->names.data() + bam->name_off[k], r + 36, (size_t)(bam->name_off[k + 1] - bam->name_off[k]));
+      }
+    });
+    carry = avail - p;
+    if (carry) memmove(buf, buf + p, carry);
+    w0 = w1;
+  }
+  if (!header_done) return fail(blocks.empty() ? "not a BAM file" : "truncated BAM header");
+  if (carry) return fail("corrupt BAM record");   // bytes after the last complete record
+  *out = bam.release();
   return 0;
 }
 
@@ -222,58 +342,26 @@ void gci_bam_close(gci_bam* b) { delete b; }
 int32_t gci_bam_n_refs(gci_bam* b) { return b ? (int32_t)b->ref_names.size() : 0; }
 const char* gci_bam_ref_name(gci_bam* b, int32_t i) { return b->ref_names[i].c_str(); }
 int64_t gci_bam_ref_len(gci_bam* b, int32_t i) { return b->ref_lens[i]; }
-int64_t gci_bam_n_records(gci_bam* b) { return b ? (int64_t)b->rec_off.size() : 0; }
-int64_t gci_bam_n_ops(gci_bam* b) { return b && !b->cig_off.empty() ? (int64_t)b->cig_off.back() : 0; }
+int64_t gci_bam_n_records(gci_bam* b) { return b ? (int64_t)b->ref_id.size() : 0; }
+int64_t gci_bam_n_ops(gci_bam* b) { return b ? (int64_t)b->cigar.size() : 0; }
 
 int gci_bam_fill(gci_bam* b, gci_interner* it, int32_t* ref_id, int32_t* ref_start, uint8_t* mapq, uint16_t* flag,
                  int32_t* nm, int32_t* qlen, uint32_t* read_id, uint64_t* cigar_off, uint32_t* cigar) {
   if (!b || !it) return fail("bad argument");
-  const int64_t n = (int64_t)b->rec_off.size();
-  struct View { const uint8_t* p; const uint8_t* data() const { return p; } };
-  const View d{b->data};
-  memcpy(cigar_off, b->cig_off.data(), sizeof(uint64_t) * (size_t)(n + 1));
-  parallel_for(n, b->threads, [&](int64_t a0, int64_t a1, int) {
-    for (int64_t i = a0; i < a1; i++) {
-      const uint8_t* r = d.data() + b->rec_off[i];
-      const uint8_t* end = r + 4 + rdi32(r);
-      ref_id[i] = rdi32(r + 4);
-      ref_start[i] = rdi32(r + 8);
-      const uint8_t l_name = r[12];
-      mapq[i] = r[13];
-      const uint32_t n_cig = rd16(r + 16);
-      flag[i] = rd16(r + 18);
-      const int32_t l_seq = rdi32(r + 20);
-      qlen[i] = l_seq;
-      const uint8_t* cig = r + 36 + l_name;
-      if (b->cg[i]) memcpy(cigar + cigar_off[i], d.data() + b->cg_off[i], 4 * (size_t)(cigar_off[i + 1] - cigar_off[i]));
-      else memcpy(cigar + cigar_off[i], cig, 4 * (size_t)n_cig);
-      // NM aux (any integer type)
-      int32_t nmv = INT32_MIN;
-      const uint8_t* x = cig + 4 * (size_t)n_cig + (l_seq + 1) / 2 + l_seq;
-      while (x + 3 <= end) {
-        const uint8_t t = x[2];
-        const bool is_nm = x[0] == 'N' && x[1] == 'M';
-        x += 3;
-        if (t == 'A' || t == 'c' || t == 'C') { if (is_nm) nmv = t == 'c' ? (int8_t)x[0] : x[0]; x += 1; }
-        else if (t == 's' || t == 'S') { if (is_nm) nmv = t == 's' ? (int16_t)rd16(x) : rd16(x); x += 2; }
-        else if (t == 'i' || t == 'I' || t == 'f') { if (is_nm && t != 'f') nmv = rdi32(x); x += 4; }
-        else if (t == 'Z' || t == 'H') { while (x < end && *x) x++; x++; }
-        else if (t == 'B') {
-          const uint8_t st = x[0];
-          const uint32_t cnt = rd32(x + 1);
-          const int sz = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
-          x += 5 + (size_t)cnt * sz;
-        } else break;
-        if (is_nm && nmv != INT32_MIN) break;
-      }
-      nm[i] = nmv;
-    }
-  });
+  const size_t n = b->ref_id.size();
+  memcpy(cigar_off, b->cig_off.data(), sizeof(uint64_t) * (n + 1));
+  if (n) {
+    memcpy(ref_id, b->ref_id.data(), 4 * n);
+    memcpy(ref_start, b->ref_start.data(), 4 * n);
+    memcpy(mapq, b->mapq.data(), n);
+    memcpy(flag, b->flag.data(), 2 * n);
+    memcpy(nm, b->nm.data(), 4 * n);
+    memcpy(qlen, b->qlen.data(), 4 * n);
+  }
+  if (!b->cigar.empty()) memcpy(cigar, b->cigar.data(), 4 * b->cigar.size());
   // read names -> dense ids, in file order (sequential: one shared table per read type)
-  for (int64_t i = 0; i < n; i++) {
-    const uint8_t* r = d.data() + b->rec_off[i];
-    const uint8_t l_name = r[12];
-    std::string name((const char*)r + 36, l_name ? (size_t)l_name - 1 : 0);
+  for (size_t i = 0; i < n; i++) {
+    std::string name(b->names.data() + b->name_off[i], (size_t)(b->name_off[i + 1] - b->name_off[i]));
     auto ins = it->map.emplace(std::move(name), (uint32_t)it->map.size());
     read_id[i] = ins.first->second;
   }
