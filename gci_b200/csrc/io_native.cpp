@@ -69,9 +69,57 @@ inline int32_t rdi32(const uint8_t* p) { int32_t v; memcpy(&v, p, 4); return v; 
 
 }  // namespace
 
+// Read name -> dense id in order of first appearance, shared by all files of a read type.  Open addressing over
+// (hash, arena offset): a lookup touches one cache line and allocates nothing; the 64-bit hashes are computed by
+// the decoders' parallel phases, only the probing runs in file order.
+inline uint64_t name_hash(const char* s, size_t n) {
+  uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)n;
+  while (n >= 8) {
+    uint64_t w;
+    memcpy(&w, s, 8);
+    h = (h ^ w) * 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32;
+    s += 8;
+    n -= 8;
+  }
+  uint64_t w = 0;
+  memcpy(&w, s, n);
+  h = (h ^ w) * 0xD6E8FEB86659FD93ull;
+  h ^= h >> 29;
+  h *= 0x94D049BB133111EBull;
+  return h ^ (h >> 32);
+}
+
 struct gci_interner {
-  std::unordered_map<std::string, uint32_t> map;
-  std::vector<const std::string*> order;
+  struct Slot { uint64_t hash, off; uint32_t len, id; };   // id == UINT32_MAX: empty
+  std::vector<Slot> slots;
+  std::vector<char> arena;                  // the distinct names back to back
+  uint32_t count = 0;
+
+  void grow() {
+    const size_t cap = slots.empty() ? (size_t)1 << 16 : slots.size() * 2;
+    std::vector<Slot> fresh(cap, Slot{0, 0, 0, UINT32_MAX});
+    for (const Slot& s : slots) {
+      if (s.id == UINT32_MAX) continue;
+      size_t i = (size_t)s.hash & (cap - 1);
+      while (fresh[i].id != UINT32_MAX) i = (i + 1) & (cap - 1);
+      fresh[i] = s;
+    }
+    slots.swap(fresh);
+  }
+  uint32_t intern(const char* s, size_t n, uint64_t h) {
+    if ((size_t)(count + 1) * 10 > slots.size() * 7) grow();          // load factor <= 0.7
+    const size_t mask = slots.size() - 1;
+    for (size_t i = (size_t)h & mask;; i = (i + 1) & mask) {
+      Slot& sl = slots[i];
+      if (sl.id == UINT32_MAX) {
+        sl = Slot{h, (uint64_t)arena.size(), (uint32_t)n, count};
+        arena.insert(arena.end(), s, s + n);
+        return count++;
+      }
+      if (sl.hash == h && sl.len == n && memcmp(arena.data() + sl.off, s, n) == 0) return sl.id;
+    }
+  }
 };
 
 // One BAM file decoded into columns.  The file is never inflated as a whole: gci_bam_open streams it through a
@@ -88,6 +136,7 @@ struct gci_bam {
   std::vector<uint32_t> cigar;
   std::vector<uint64_t> name_off;            // [n+1] into names
   std::vector<char> names;                   // read names back to back (no terminators)
+  std::vector<uint64_t> name_hash;           // [n] name_hash() of every read name
   int threads = 1;
 };
 
@@ -167,7 +216,7 @@ const char* gci_io_last_error(void) { return g_err.c_str(); }
 
 gci_interner* gci_interner_create(void) { return new gci_interner(); }
 void gci_interner_destroy(gci_interner* it) { delete it; }
-int64_t gci_interner_size(gci_interner* it) { return it ? (int64_t)it->map.size() : 0; }
+int64_t gci_interner_size(gci_interner* it) { return it ? (int64_t)it->count : 0; }
 
 // ---- BAM ------------------------------------------------------------------------------------------
 int gci_bam_open(const char* path, int threads, gci_bam** out) {
@@ -309,7 +358,7 @@ int gci_bam_open(const char* path, int threads, gci_bam** out) {
       bam->name_off[n0 + i + 1] = bam->name_off[n0 + i] + (l_name ? (uint64_t)l_name - 1 : 0);
     }
     bam->ref_id.resize(n0 + m); bam->ref_start.resize(n0 + m); bam->nm.resize(n0 + m); bam->qlen.resize(n0 + m);
-    bam->mapq.resize(n0 + m); bam->flag.resize(n0 + m);
+    bam->mapq.resize(n0 + m); bam->flag.resize(n0 + m); bam->name_hash.resize(n0 + m);
     bam->cigar.resize((size_t)bam->cig_off[n0 + m]);
     bam->names.resize((size_t)bam->name_off[n0 + m]);
     parallel_for(m, bam->threads, [&](int64_t a, int64_t b, int) {
@@ -325,7 +374,9 @@ int gci_bam_open(const char* path, int threads, gci_bam** out) {
         const uint8_t* cig = cg[i] ? cg[i] : r + 36 + l_name;
         memcpy(bam->cigar.data() + bam->cig_off[k], cig, 4 * (size_t)ops[i]);
         bam->nm[k] = bam_record_nm(r);
-        memcpy(bam->names.data() + bam->name_off[k], r + 36, (size_t)(bam->name_off[k + 1] - bam->name_off[k]));
+        const size_t name_n = (size_t)(bam->name_off[k + 1] - bam->name_off[k]);
+        memcpy(bam->names.data() + bam->name_off[k], r + 36, name_n);
+        bam->name_hash[k] = name_hash((const char*)r + 36, name_n);
       }
     });
     carry = avail - p;
@@ -360,11 +411,9 @@ int gci_bam_fill(gci_bam* b, gci_interner* it, int32_t* ref_id, int32_t* ref_sta
   }
   if (!b->cigar.empty()) memcpy(cigar, b->cigar.data(), 4 * b->cigar.size());
   // read names -> dense ids, in file order (sequential: one shared table per read type)
-  for (size_t i = 0; i < n; i++) {
-    std::string name(b->names.data() + b->name_off[i], (size_t)(b->name_off[i + 1] - b->name_off[i]));
-    auto ins = it->map.emplace(std::move(name), (uint32_t)it->map.size());
-    read_id[i] = ins.first->second;
-  }
+  for (size_t i = 0; i < n; i++)
+    read_id[i] = it->intern(b->names.data() + b->name_off[i], (size_t)(b->name_off[i + 1] - b->name_off[i]),
+                            b->name_hash[i]);
   return 0;
 }
 
@@ -391,6 +440,17 @@ static inline bool parse_int(std::string_view s, long long& v) {
   return true;
 }
 
+// host threads for the text decoders (PAF lines, FASTA); GCI_IO_THREADS overrides the hardware count
+static int io_threads() {
+  const char* e = getenv("GCI_IO_THREADS");
+  int t = e ? atoi(e) : 0;
+  if (t <= 0) t = (int)std::thread::hardware_concurrency();
+  return std::max(1, std::min(t, 64));
+}
+
+// The file is cut into one chunk per thread at line starts; every thread parses its lines into its own
+// columns (read names as views into the mapping), the parts are appended in file order and the names are
+// interned sequentially, so ids follow first appearance exactly as in a single pass.
 int gci_paf_open(const char* path, gci_interner* it, int32_t n_contigs, const char* const* contig_names,
                  gci_paf** out) {
   if (!path || !it || !out) return fail("bad argument");
@@ -399,51 +459,86 @@ int gci_paf_open(const char* path, gci_interner* it, int32_t n_contigs, const ch
   if (!f.open(path)) return fail(std::string("cannot open ") + path);
   std::unordered_map<std::string_view, int32_t> cidx;
   for (int32_t i = 0; i < n_contigs; i++) cidx.emplace(std::string_view(contig_names[i]), i);
-  auto* paf = new gci_paf();
-  const char* p = (const char*)f.p;
-  const char* end = p + f.n;
-  int64_t line_no = 0;
-  while (p < end) {
-    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
-    const char* le = nl ? nl : end;
-    line_no++;
-    // line.strip().split("\t")
-    const char* a = p;
-    const char* b = le;
-    while (a < b && (*a == ' ' || *a == '\t' || *a == '\r' || *a == '\v' || *a == '\f')) a++;
-    while (b > a && (b[-1] == ' ' || b[-1] == '\t' || b[-1] == '\r' || b[-1] == '\v' || b[-1] == '\f')) b--;
-    std::string_view col[12];
-    int nc = 0;
-    const char* s = a;
-    for (const char* q = a; q <= b && nc < 12; q++) {
-      if (q == b || *q == '\t') {
-        col[nc++] = std::string_view(s, (size_t)(q - s));
-        s = q + 1;
+  const char* const begin = (const char*)f.p;
+  const char* const end = begin + f.n;
+  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(io_threads(), (int64_t)(f.n >> 16) + 1));
+  std::vector<const char*> cut((size_t)T + 1, end);
+  cut[0] = begin;
+  for (int t = 1; t < T; t++) {
+    const char* q = begin + f.n / (size_t)T * (size_t)t;
+    if (q < cut[t - 1]) q = cut[t - 1];
+    const char* nl = q < end ? (const char*)memchr(q, '\n', (size_t)(end - q)) : nullptr;
+    cut[t] = nl ? nl + 1 : end;
+  }
+  struct Part {
+    std::vector<int32_t> cols[9];   // qlen qstart qend ref_id tstart tend nmatch alnlen mapq
+    std::vector<std::string_view> names;
+    std::vector<uint64_t> hashes;
+    int64_t lines = 0, bad_line = -1;
+    const char* bad_what = nullptr;
+  };
+  std::vector<Part> parts((size_t)T);
+  parallel_for(T, T, [&](int64_t t0, int64_t t1, int) {
+    for (int64_t t = t0; t < t1; t++) {
+      Part& pt = parts[(size_t)t];
+      const char* p = cut[(size_t)t];
+      const char* const pe = cut[(size_t)t + 1];
+      while (p < pe) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(pe - p));
+        const char* le = nl ? nl : pe;
+        pt.lines++;
+        // line.strip().split("\t")
+        const char* a = p;
+        const char* b = le;
+        while (a < b && (*a == ' ' || *a == '\t' || *a == '\r' || *a == '\v' || *a == '\f')) a++;
+        while (b > a && (b[-1] == ' ' || b[-1] == '\t' || b[-1] == '\r' || b[-1] == '\v' || b[-1] == '\f')) b--;
+        std::string_view col[12];
+        int nc = 0;
+        const char* s = a;
+        for (const char* q = a; q <= b && nc < 12; q++) {
+          if (q == b || *q == '\t') {
+            col[nc++] = std::string_view(s, (size_t)(q - s));
+            s = q + 1;
+          }
+        }
+        if (nc < 12) { pt.bad_line = pt.lines; pt.bad_what = "fewer than 12 columns"; break; }
+        long long v[12];
+        static const int want[9] = {1, 2, 3, 7, 8, 9, 10, 11, -1};
+        bool ok = true;
+        for (int k = 0; want[k] >= 0; k++) ok = ok && parse_int(col[want[k]], v[want[k]]);
+        if (!ok) { pt.bad_line = pt.lines; pt.bad_what = "invalid integer"; break; }
+        pt.names.push_back(col[0]);
+        pt.hashes.push_back(name_hash(col[0].data(), col[0].size()));
+        auto c = cidx.find(col[5]);
+        pt.cols[0].push_back((int32_t)v[1]);
+        pt.cols[1].push_back((int32_t)v[2]);
+        pt.cols[2].push_back((int32_t)v[3]);
+        pt.cols[3].push_back(c == cidx.end() ? -1 : c->second);
+        pt.cols[4].push_back((int32_t)v[7]);
+        pt.cols[5].push_back((int32_t)v[8]);
+        pt.cols[6].push_back((int32_t)v[9]);
+        pt.cols[7].push_back((int32_t)v[10]);
+        pt.cols[8].push_back((int32_t)v[11]);
+        p = nl ? nl + 1 : pe;
       }
     }
-    if (nc < 12) { delete paf; return fail("PAF line " + std::to_string(line_no) + ": fewer than 12 columns"); }
-    long long v[12];
-    static const int want[9] = {1, 2, 3, 7, 8, 9, 10, 11, -1};
-    for (int k = 0; want[k] >= 0; k++)
-      if (!parse_int(col[want[k]], v[want[k]])) {
-        delete paf;
-        return fail("PAF line " + std::to_string(line_no) + ": invalid integer");
-      }
-    auto ins = it->map.emplace(std::string(col[0]), (uint32_t)it->map.size());
-    paf->read_id.push_back(ins.first->second);
-    auto c = cidx.find(col[5]);
-    paf->cols[0].push_back((int32_t)v[1]);
-    paf->cols[1].push_back((int32_t)v[2]);
-    paf->cols[2].push_back((int32_t)v[3]);
-    paf->cols[3].push_back(c == cidx.end() ? -1 : c->second);
-    paf->cols[4].push_back((int32_t)v[7]);
-    paf->cols[5].push_back((int32_t)v[8]);
-    paf->cols[6].push_back((int32_t)v[9]);
-    paf->cols[7].push_back((int32_t)v[10]);
-    paf->cols[8].push_back((int32_t)v[11]);
-    p = nl ? nl + 1 : end;
+  });
+  int64_t line0 = 0;
+  size_t total = 0;
+  for (const Part& pt : parts) {                // the first offending line in file order, like a single pass
+    if (pt.bad_line >= 0) return fail("PAF line " + std::to_string(line0 + pt.bad_line) + ": " + pt.bad_what);
+    line0 += pt.lines;
+    total += pt.names.size();
   }
-  *out = paf;
+  std::unique_ptr<gci_paf> paf(new gci_paf());
+  paf->read_id.reserve(total);
+  for (auto& c : paf->cols) c.reserve(total);
+  for (const Part& pt : parts) {
+    for (int k = 0; k < 9; k++) paf->cols[k].insert(paf->cols[k].end(), pt.cols[k].begin(), pt.cols[k].end());
+    for (size_t i = 0; i < pt.names.size(); i++)
+      paf->read_id.push_back(it->intern(pt.names[i].data(), pt.names[i].size(), pt.hashes[i]));
+  }
+  *out = paf.release();
   return 0;
 }
 

@@ -102,6 +102,37 @@ def test_bam_streaming_windows(tmp_path, monkeypatch):
                 assert np.array_equal(getattr(got, col), getattr(one, col)), (window, threads, col)
 
 
+def test_paf_parallel_chunks(tmp_path, monkeypatch):
+    """the native PAF parser cuts the file into one chunk per thread at line starts: same table and same read ids
+    as the line-by-line Python reader for any thread count, and the first bad line is reported by its number"""
+    rng = np.random.default_rng(3)
+    n = 30_000
+    reads = rng.integers(0, 9000, n)                               # repeated names: ids follow first appearance
+    lines = []
+    for i in range(n):
+        ctg = ["chr1", "chr2", "unplaced"][int(rng.integers(0, 3))]
+        s0 = int(rng.integers(0, 10**6))
+        lines.append("\t".join(map(str, [f"read/{int(reads[i])}/ccs", 20000, 5, 19990, "+-"[i & 1], ctg, 10**7, s0,
+                                          s0 + 19985, 19000 + i % 900, 19985, int(rng.integers(0, 61))])) +
+                     ("\ttp:A:P\tcm:i:5" if i % 3 else ""))
+    p = str(tmp_path / "big.paf")
+    open(p, "w").write("\n".join(lines) + "\n")
+    want = gio.read_paf_py(p, {"chr1": 0, "chr2": 1})
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("GCI_IO_THREADS", threads)
+        got = gio.read_paf(p, ["chr1", "chr2"], gio.NameTable(native=True))
+        for col in ("read_id", "qlen", "qstart", "qend", "ref_id", "tstart", "tend", "nmatch", "alnlen", "mapq"):
+            assert np.array_equal(getattr(got, col), getattr(want, col)), (threads, col)
+    bad = lines[:]
+    bad[25_000] = bad[25_000].replace("\t20000\t", "\t20k\t", 1)
+    bad[29_000] = "too\tshort"
+    open(p, "w").write("\n".join(bad))                            # and no newline at the end of the file
+    for threads in ("1", "8"):
+        monkeypatch.setenv("GCI_IO_THREADS", threads)
+        with pytest.raises(ValueError, match="PAF line 25001: invalid integer"):
+            gio.read_paf(p, ["chr1", "chr2"], gio.NameTable(native=True))
+
+
 def test_bam_long_cigar_cg_tag(tmp_path):
     ops = np.array([(3 << 4) | 0, (1 << 4) | 1] * 40000, dtype=np.uint32)     # 80000 ops > 65535
     t = AlnTable([0], [5], [60], [0], [40000], [160000], [0], np.array([0, len(ops)], np.uint64), ops)
