@@ -163,6 +163,46 @@ def test_paf_fasta_depth_roundtrip(tmp_path):
     assert list(got) == ["c1", "c2"] and got["c1"].tolist() == [0, 1, 2, 3] and got["c2"].tolist() == [7]
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_fasta_scanner_on_messy_files(tmp_path, seed):
+    """native line-based N-run scanner == the Python reader on CRLF / blank lines / trailing blanks / lower-case n /
+    runs crossing line ends / unwrapped records longer than the read buffer / text before the first header /
+    no final newline / gzip"""
+    import gzip as _gz
+    rng = np.random.default_rng(seed)
+    out = [b"; a comment before the first record\n"] if seed % 2 else []
+    n_rec = int(rng.integers(1, 6))
+    for r in range(n_rec):
+        L = int(rng.integers(0, 30_000)) if seed != 5 else int(rng.integers(5_000_000, 6_000_000))
+        seq = rng.choice(np.frombuffer(b"ACGTacgt", np.uint8), L)
+        for _ in range(int(rng.integers(0, 6))):
+            a = int(rng.integers(0, max(1, L)))
+            b = min(L, a + int(rng.integers(1, 400)))
+            seq[a:b] = rng.choice(np.frombuffer(b"Nn", np.uint8), b - a)
+        if L and rng.random() < 0.5:
+            seq[:int(rng.integers(1, 10))] = ord("N")                # run at the very start
+        if L and rng.random() < 0.5:
+            seq[L - int(rng.integers(1, min(10, L) + 1)):] = ord("n")   # and at the very end
+        eol = b"\r\n" if seed == 1 else b"\n"
+        out.append(b">" + (b"  " if seed == 2 else b"") + f"ctg{r}".encode() + (b" some description" if r % 2 else b"") + eol)
+        width = 60 if seed != 3 else max(1, L)                         # seed 3: unwrapped
+        txt = seq.tobytes()
+        for i in range(0, L, width):
+            out.append(txt[i:i + width] + (b" \t" if seed == 4 and i % 7 == 0 else b"") + eol)
+            if seed == 4 and i % 11 == 0:
+                out.append(eol)                                        # blank line inside a record
+    data = b"".join(out)
+    if seed % 3 == 0 and data.endswith(b"\n"):
+        data = data[:-1]                                               # no newline at the end of the file
+    plain, zipped = str(tmp_path / "m.fa"), str(tmp_path / "m.fa.gz")
+    open(plain, "wb").write(data)
+    with _gz.open(zipped, "wb") as f:
+        f.write(data)
+    want = gio.read_fasta_gaps_py(plain)
+    assert gio.read_fasta_gaps(plain) == want
+    assert gio.read_fasta_gaps(zipped) == want
+
+
 def test_native_io_exports_every_header_symbol():
     from gci_b200 import io_native
     hdr = open(os.path.join(ROOT, "include", "gci_io.h")).read()
