@@ -24,7 +24,10 @@ gci_interner* gci_interner_create(void);
 void gci_interner_destroy(gci_interner* it);
 int64_t gci_interner_size(gci_interner* it);
 
-/* read + inflate (BGZF blocks in parallel on `threads` threads) + index the records of a BAM file */
+/* decode a BAM file into columns: the file is streamed through a window of 256 MB of inflated data (BGZF blocks
+   inflated in parallel on `threads` threads, record sizes walked in file order, fields extracted in parallel; a
+   record cut by the window border is carried into the next window), so memory is bounded whatever the file size.
+   GCI_IO_WINDOW_BYTES in the environment overrides the window (tests). */
 int gci_bam_open(const char* path, int threads, gci_bam** out);
 void gci_bam_close(gci_bam* b);
 int32_t gci_bam_n_refs(gci_bam* b);
@@ -36,7 +39,9 @@ int64_t gci_bam_n_ops(gci_bam* b);          /* CIGAR ops after resolving CG:B,I 
 int gci_bam_fill(gci_bam* b, gci_interner* it, int32_t* ref_id, int32_t* ref_start, uint8_t* mapq, uint16_t* flag,
                  int32_t* nm, int32_t* qlen, uint32_t* read_id, uint64_t* cigar_off, uint32_t* cigar);
 
-/* PAF columns 0,1,2,3,5,7,8,9,10,11; ref_id = index into contig_names or -1 */
+/* PAF columns 0,1,2,3,5,7,8,9,10,11; ref_id = index into contig_names or -1.  Lines are parsed in one chunk per
+   host thread (GCI_IO_THREADS overrides the hardware count); read ids follow first appearance in file order and
+   a malformed line is reported by its number. */
 int gci_paf_open(const char* path, gci_interner* it, int32_t n_contigs, const char* const* contig_names,
                  gci_paf** out);
 int64_t gci_paf_n_lines(gci_paf* p);
