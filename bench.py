@@ -16,6 +16,10 @@ A step = one pass of the hot path over the batch:
 `value`  : records already resident in HBM, CUDA events per step, L2 flushed between steps.
 `e2e`    : the same through the C ABI with HOST (pinned) buffers: H2D of the record columns, the
            step, D2H of the depth array, the intervals and the score terms inside the timed region.
+Both timed loops run with the library's stage timers off, so from its third run on the step is ONE CUDA-graph
+launch (GCI_GRAPH=0: eager launches); the per-stage table and the dominant kernel's duration for `roofline` come
+from a separate eager pass of <= 20 steps with one CUDA-event pair per stage, in the same run on the same data.
+At N > 1 the genome row travels as stores into NVLink peer memory (GCI_P2P=0: ncclAllGather).
 """
 from __future__ import annotations
 
