@@ -648,4 +648,200 @@ int gci_fasta_runs(gci_fasta* f, int32_t* rec, int64_t* start, int64_t* end) {
 }
 void gci_fasta_close(gci_fasta* f) { delete f; }
 
+// ---- .depth.gz: ">name" lines followed by one decimal depth per line (GCI.py:110-117; reader contract
+// utility/GCI_score.py:25-37) ------------------------------------------------------------------------------
+// The (multi-member) gzip stream is inflated through a window; the number tokens of a window are counted and
+// then parsed by all threads, each writing its slice of the contig's array.
+// growable int32 array without the zero fill of std::vector::resize (realloc of a large block is a remap)
+struct DepthArray {
+  int32_t* p = nullptr;
+  size_t n = 0, cap = 0;
+  DepthArray() = default;
+  DepthArray(const DepthArray&) = delete;
+  DepthArray& operator=(const DepthArray&) = delete;
+  DepthArray(DepthArray&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+  ~DepthArray() { free(p); }
+  bool grow(size_t extra) {
+    if (n + extra > cap) {
+      const size_t want = std::max(n + extra, cap + cap / 2 + 1024);
+      int32_t* q = (int32_t*)realloc(p, want * sizeof(int32_t));
+      if (!q) return false;
+      p = q;
+      cap = want;
+    }
+    n += extra;
+    return true;
+  }
+};
+
+struct gci_depth {
+  std::vector<std::string> names;
+  std::vector<DepthArray> depth;
+};
+
+namespace {
+// blank = anything up to ' ' (newline, CR, tab, VT, FF, space; other control bytes are not valid in the file anyway)
+inline bool is_blank(char c) { return (unsigned char)c <= ' '; }
+
+// tokens (maximal runs of non-blank bytes) that START inside [a, b); branch-free so that it vectorises
+int64_t count_tokens(const char* base, const char* a, const char* b) {
+  if (a >= b) return 0;
+  int64_t n = (a == base || is_blank(a[-1])) && !is_blank(a[0]);
+  const unsigned char* u = (const unsigned char*)a;
+  const int64_t len = b - a;
+  for (int64_t i = 1; i < len; i++) n += (u[i] > ' ') & (u[i - 1] <= ' ');
+  return n;
+}
+
+// parse the tokens that start inside [a, b) into out[0..]; returns false on a token that is not a Python int
+bool parse_tokens(const char* base, const char* a, const char* b, const char* end, int32_t* out) {
+  const char* p = a;
+  if (p != base && !is_blank(p[-1]))            // in the middle of a token that belongs to the previous slice
+    while (p < b && !is_blank(*p)) p++;
+  for (;;) {
+    while (p < b && is_blank(*p)) p++;
+    if (p >= b) break;
+    // fast path: plain digits up to a blank (or the end of the data)
+    uint32_t x = 0;
+    const char* q = p;
+    unsigned d;
+    while (q < end && (d = (unsigned)(*q - '0')) <= 9u && q - p < 9) { x = x * 10u + d; q++; }
+    if (q > p && (q == end || is_blank(*q))) {
+      *out++ = (int32_t)x;
+      p = q;
+      continue;
+    }
+    // anything else Python's int() takes: sign, underscores, ten digits
+    bool neg = false;
+    if (*p == '+' || *p == '-') { neg = *p == '-'; p++; }
+    long long v = 0;
+    int digits = 0;
+    while (p < end && !is_blank(*p)) {
+      if (*p == '_') { p++; continue; }
+      if (*p < '0' || *p > '9') return false;
+      v = v * 10 + (*p - '0');
+      if (v > 0x7fffffffll + 1) return false;     // does not fit the int32 depth tracks
+      digits++;
+      p++;
+    }
+    if (!digits) return false;
+    v = neg ? -v : v;
+    if (v > 0x7fffffffll) return false;
+    *out++ = (int32_t)v;
+  }
+  return true;
+}
+}  // namespace
+
+int gci_depth_open(const char* path, int threads, gci_depth** out) {
+  if (!path || !out) return fail("bad argument");
+  *out = nullptr;
+  MappedFile f;
+  if (!f.open(path)) return fail(std::string("cannot open ") + path);
+  threads = std::max(1, threads);
+  std::unique_ptr<gci_depth> dp(new gci_depth());
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  if (inflateInit2(&zs, 15 + 32) != Z_OK) return fail("zlib init failed");
+  struct End { z_stream* z; ~End() { inflateEnd(z); } } end_zs{&zs};
+  const size_t window = bam_window_bytes();
+  std::vector<char> buf(std::max<size_t>(window, 1 << 16) + (1 << 16));
+  size_t have = 0, in_pos = 0;
+  bool stream_done = f.n == 0;
+  std::atomic<int> bad{0};
+  auto numbers = [&](const char* a, const char* b) -> bool {      // [a, b): complete lines without a header
+    if (a >= b) return true;
+    const int64_t span = b - a;
+    const int T = (int)std::max<int64_t>(1, std::min<int64_t>(threads, span >> 16));
+    std::vector<int64_t> cnt((size_t)T + 1, 0);
+    parallel_for(T, T, [&](int64_t t0, int64_t t1, int) {
+      for (int64_t t = t0; t < t1; t++) cnt[(size_t)t + 1] = count_tokens(a, a + span * t / T, a + span * (t + 1) / T);
+    });
+    for (int t = 0; t < T; t++) cnt[(size_t)t + 1] += cnt[(size_t)t];
+    if (cnt[(size_t)T] == 0) return true;
+    if (dp->depth.empty()) return false;                           // numbers before the first ">name" line
+    DepthArray& v = dp->depth.back();
+    const size_t n0 = v.n;
+    if (!v.grow((size_t)cnt[(size_t)T])) return false;
+    parallel_for(T, T, [&](int64_t t0, int64_t t1, int) {
+      for (int64_t t = t0; t < t1; t++)
+        if (!parse_tokens(a, a + span * t / T, a + span * (t + 1) / T, b, v.p + n0 + cnt[(size_t)t])) bad = 1;
+    });
+    return bad == 0;
+  };
+  auto lines = [&](const char* a, const char* b) -> bool {          // [a, b): complete lines
+    const char* p = a;
+    while (p < b) {
+      const char* h = (const char*)memchr(p, '>', (size_t)(b - p));
+      if (!h) return numbers(p, b);
+      const char* ls = h;                                           // start of the header's line
+      while (ls > p && ls[-1] != '\n') ls--;
+      if (!numbers(p, ls)) return false;
+      const char* nl = (const char*)memchr(h, '\n', (size_t)(b - h));
+      const char* le = nl ? nl : b;
+      // item = line.strip(); must start with '>'; target = item.split('>')[-1]
+      const char* s0 = ls;
+      const char* s1 = le;
+      while (s0 < s1 && is_blank(*s0)) s0++;
+      while (s1 > s0 && is_blank(s1[-1])) s1--;
+      if (s0 >= s1 || *s0 != '>') return false;
+      const char* last = s1;
+      while (last > s0 && last[-1] != '>') last--;
+      dp->names.emplace_back(last, (size_t)(s1 - last));
+      dp->depth.emplace_back();
+      p = nl ? nl + 1 : b;
+    }
+    return true;
+  };
+  while (!stream_done || have) {
+    // fill the window
+    while (!stream_done && have < window) {
+      zs.next_in = const_cast<Bytef*>(f.p + in_pos);
+      zs.avail_in = (uInt)std::min<size_t>(f.n - in_pos, (size_t)1 << 30);
+      zs.next_out = (Bytef*)buf.data() + have;
+      zs.avail_out = (uInt)std::min<size_t>(buf.size() - have, (size_t)1 << 30);
+      const uInt in0 = zs.avail_in, out0 = zs.avail_out;
+      const int rc = inflate(&zs, Z_NO_FLUSH);
+      in_pos += in0 - zs.avail_in;
+      have += out0 - zs.avail_out;
+      if (rc == Z_STREAM_END) {
+        if (in_pos >= f.n) stream_done = true;
+        else if (inflateReset(&zs) != Z_OK) return fail("zlib reset failed");   // next gzip member
+      } else if (rc != Z_OK && rc != Z_BUF_ERROR) {
+        return fail("not a gzip stream / corrupt .depth.gz");
+      } else if (in0 == zs.avail_in && out0 == zs.avail_out) {
+        if (in_pos >= f.n) return fail("truncated .depth.gz");
+        break;                                                       // output window full
+      }
+      if (have >= buf.size()) break;
+    }
+    // complete lines of the window; the rest is carried over (everything, once the stream has ended)
+    size_t upto = have;
+    if (!stream_done) {
+      while (upto > 0 && buf[upto - 1] != '\n') upto--;
+      if (upto == 0) {                                               // one line longer than the window
+        if (have == buf.size()) buf.resize(buf.size() * 2);
+        continue;
+      }
+    }
+    if (!lines(buf.data(), buf.data() + upto)) return fail("malformed .depth.gz (a line is neither '>name' nor an integer)");
+    have -= upto;
+    if (have) memmove(buf.data(), buf.data() + upto, have);
+    if (stream_done && have == 0) break;
+  }
+  *out = dp.release();
+  return 0;
+}
+
+int32_t gci_depth_n_contigs(gci_depth* d) { return d ? (int32_t)d->names.size() : 0; }
+const char* gci_depth_name(gci_depth* d, int32_t i) { return d->names[(size_t)i].c_str(); }
+int64_t gci_depth_len(gci_depth* d, int32_t i) { return (int64_t)d->depth[(size_t)i].n; }
+int gci_depth_fill(gci_depth* d, int32_t i, int32_t* out) {
+  if (!d || i < 0 || (size_t)i >= d->depth.size()) return fail("bad argument");
+  const DepthArray& v = d->depth[(size_t)i];
+  if (v.n) memcpy(out, v.p, 4 * v.n);
+  return 0;
+}
+void gci_depth_close(gci_depth* d) { delete d; }
+
 }  // extern "C"

@@ -363,12 +363,27 @@ def write_depth_gz(path, pieces, threads=1, level=6):
             f.write(fut.result())
 
 
-def read_depth_gz(path):
-    """utility/GCI_score.py:11-39 — {name: int32 array} in file order."""
+def read_depth_gz(path, threads=0):
+    """utility/GCI_score.py:11-39 — {name: int32 array} in file order (native parser; `read_depth_gz_py` is the
+    pure-Python cross-check)."""
+    from . import io_native
+    return io_native.read_depth_gz(path, threads)
+
+
+def read_depth_gz_py(path):
+    """utility/GCI_score.py:11-39, line by line like the reference: `item = line.strip()`; a line starting with
+    '>' opens the target `item.split('>')[-1]`, any other line is one `int(item)`.  (Blank lines, on which the
+    reference raises, are skipped.)  Small files only: the product reads with the native parser."""
     with gzip.open(path, "rb") as f:
         data = f.read()
-    out = {}
-    for part in data.split(b">")[1:]:
-        nl = part.index(b"\n")
-        out[part[:nl].decode().strip()] = np.array(part[nl + 1:].split(), dtype=np.int64).astype(np.int32)
-    return out
+    out, cur = {}, None
+    for raw in data.split(b"\n"):
+        item = raw.strip()
+        if not item:
+            continue
+        if item.startswith(b">"):
+            cur = []
+            out[item.split(b">")[-1].decode()] = cur
+        else:
+            cur.append(int(item))
+    return {k: np.asarray(v, dtype=np.int64).astype(np.int32) for k, v in out.items()}

@@ -36,6 +36,12 @@ _SIG = {
     "gci_fasta_n_runs": (C.c_int64, [_p]),
     "gci_fasta_runs": (C.c_int, [_p, _p, _p, _p]),
     "gci_fasta_close": (None, [_p]),
+    "gci_depth_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_p)]),
+    "gci_depth_n_contigs": (C.c_int32, [_p]),
+    "gci_depth_name": (C.c_char_p, [_p, C.c_int32]),
+    "gci_depth_len": (C.c_int64, [_p, C.c_int32]),
+    "gci_depth_fill": (C.c_int, [_p, C.c_int32, _p]),
+    "gci_depth_close": (None, [_p]),
 }
 
 
@@ -149,3 +155,21 @@ def read_fasta_gaps(path):
     for r, a, b in zip(rec.tolist(), s.tolist(), e.tolist()):
         gaps.setdefault(ids[r], []).append((a, b))
     return ids, gaps
+
+
+def read_depth_gz(path, threads=0):
+    """utility/GCI_score.py:11-39 — {name: int32 array} in file order, parsed by libgci_io.so"""
+    L = lib()
+    h = _p()
+    if L.gci_depth_open(os.fsencode(path), int(threads) or (os.cpu_count() or 1), C.byref(h)) != 0:
+        raise ValueError(f"{path}: {_err()}")
+    try:
+        out = {}
+        for i in range(L.gci_depth_n_contigs(h)):
+            a = np.empty(int(L.gci_depth_len(h, i)), np.int32)
+            if L.gci_depth_fill(h, i, _ptr(a)) != 0:
+                raise ValueError(f"{path}: {_err()}")
+            out[L.gci_depth_name(h, i).decode()] = a
+        return out
+    finally:
+        L.gci_depth_close(h)

@@ -57,6 +57,16 @@ int64_t gci_fasta_n_runs(gci_fasta* f);
 int gci_fasta_runs(gci_fasta* f, int32_t* rec, int64_t* start, int64_t* end);
 void gci_fasta_close(gci_fasta* f);
 
+/* .depth.gz (the resume point of utility/GCI_score.py:11-39): ">name" lines, then one decimal depth per line;
+   multi-member gzip.  Inflated through a window, the numbers parsed on `threads` threads. */
+typedef struct gci_depth gci_depth;
+int gci_depth_open(const char* path, int threads, gci_depth** out);
+int32_t gci_depth_n_contigs(gci_depth* d);
+const char* gci_depth_name(gci_depth* d, int32_t i);
+int64_t gci_depth_len(gci_depth* d, int32_t i);
+int gci_depth_fill(gci_depth* d, int32_t i, int32_t* out);
+void gci_depth_close(gci_depth* d);
+
 #ifdef __cplusplus
 }
 #endif

@@ -203,6 +203,50 @@ def test_fasta_scanner_on_messy_files(tmp_path, seed):
     assert gio.read_fasta_gaps(zipped) == want
 
 
+def test_depth_gz_native_reader(tmp_path, monkeypatch):
+    """native .depth.gz reader == the pure-Python one on multi-member files, tiny windows (lines cut by the window
+    border), CRLF, a header holding several '>' (the reference keeps the text after the last one), no final
+    newline; malformed lines are refused"""
+    rng = np.random.default_rng(11)
+    a = rng.integers(0, 3, 70_000)
+    a[1000:1200] = rng.integers(90, 2_000_000, 200)                # several digits
+    b = rng.integers(0, 60, 12_345)
+    parts = [b">ctgA\n", "".join(f"{v}\n" for v in a[:30_000]).encode(), "".join(f"{v}\n" for v in a[30_000:]).encode(),
+             b">old>ctgB\r\n", "".join(f"{v}\r\n" for v in b).encode()[:-2]]
+    p = str(tmp_path / "x.depth.gz")
+    gio.write_depth_gz(p, parts, threads=3)
+    want = gio.read_depth_gz_py(p)
+    assert list(want) == ["ctgA", "ctgB"] and np.array_equal(want["ctgA"], a) and np.array_equal(want["ctgB"], b)
+    for window in (None, "1000", "70000"):
+        if window:
+            monkeypatch.setenv("GCI_IO_WINDOW_BYTES", window)
+        for threads in (1, 5):
+            got = gio.read_depth_gz(p, threads)
+            assert list(got) == ["ctgA", "ctgB"]                  # item.split('>')[-1], utility/GCI_score.py:31
+            assert np.array_equal(got["ctgA"], a) and np.array_equal(got["ctgB"], b)
+    monkeypatch.delenv("GCI_IO_WINDOW_BYTES", raising=False)
+    for bad in (b">c\n1\nx2\n", b"5\n>c\n1\n", b">c\n1\n99999999999\n"):
+        gio.write_depth_gz(p, [bad], threads=1)
+        with pytest.raises(ValueError):
+            gio.read_depth_gz(p)
+    gio.write_depth_gz(p, [b">empty\n", b">c\n7\n"], threads=1)
+    got = gio.read_depth_gz(p)
+    assert list(got) == ["empty", "c"] and len(got["empty"]) == 0 and got["c"].tolist() == [7]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/example/MH63.depth.gz"),
+                    reason="the reference's example is only mounted in the build container")
+def test_depth_gz_native_reader_on_the_reference_example():
+    """the reference's own example/MH63.depth.gz (395 765 488 depth lines) through the native reader equals the
+    committed run-length fixture of the same file"""
+    from helpers import mh63_depths
+    names, lengths, depths = mh63_depths()
+    got = gio.read_depth_gz("/root/reference/example/MH63.depth.gz")
+    assert list(got) == names
+    for n, d in zip(names, depths):
+        assert np.array_equal(got[n], d), n
+
+
 def test_native_io_exports_every_header_symbol():
     from gci_b200 import io_native
     hdr = open(os.path.join(ROOT, "include", "gci_io.h")).read()
