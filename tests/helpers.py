@@ -144,5 +144,5 @@ def run_product(kw, workdir, session=None, threads=2):
     outs = {}
     for fn in sorted(os.listdir(out_dir)):
         p = os.path.join(out_dir, fn)
-        outs[fn] = gio.read_depth_gz(p) if fn.endswith(".depth.gz") else open(p).read()
+        outs[fn] = gio.read_depth_gz_py(p) if fn.endswith(".depth.gz") else open(p).read()
     return outs, buf.getvalue()

@@ -95,7 +95,7 @@ def test_cli_on_real_files(tmp_path):
     got = {}
     for fn in sorted(os.listdir(tmp_path / "out")):
         p = str(tmp_path / "out" / fn)
-        got[fn] = gio.read_depth_gz(p) if fn.endswith(".depth.gz") else open(p).read()
+        got[fn] = gio.read_depth_gz_py(p) if fn.endswith(".depth.gz") else open(p).read()
     assert_outputs_equal(got, expected)
 
 
@@ -118,6 +118,6 @@ def test_resume_from_depth_gz_tool(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     for fn in ("T.gci", "T_hifi.0.depth.bed", "T_nano.0.depth.bed", "T_two_type.0.depth.bed"):
         assert open(tmp_path / "out" / fn).read() == expected[fn], fn
-    got = gio.read_depth_gz(str(tmp_path / "out" / "T_two_type.depth.gz"))
+    got = gio.read_depth_gz_py(str(tmp_path / "out" / "T_two_type.depth.gz"))
     for n in names:
         assert np.array_equal(got[n], expected["T_two_type.depth.gz"][n])
