@@ -370,20 +370,26 @@ def read_depth_gz(path, threads=0):
     return io_native.read_depth_gz(path, threads)
 
 
+_DEPTH_HEADER = re.compile(rb"^[ \t\r\f\v]*>[^\n]*$", re.M)
+
+
 def read_depth_gz_py(path):
-    """utility/GCI_score.py:11-39, line by line like the reference: `item = line.strip()`; a line starting with
-    '>' opens the target `item.split('>')[-1]`, any other line is one `int(item)`.  (Blank lines, on which the
-    reference raises, are skipped.)  Small files only: the product reads with the native parser."""
+    """utility/GCI_score.py:11-39 without the native library: a line whose stripped text starts with '>' opens the
+    target `item.split('>')[-1]`, every other line is one integer.  (Blank lines, on which the reference raises,
+    are skipped.)  Independent cross-check of the native parser; the tests read the product's files with it."""
     with gzip.open(path, "rb") as f:
         data = f.read()
-    out, cur = {}, None
-    for raw in data.split(b"\n"):
-        item = raw.strip()
-        if not item:
-            continue
-        if item.startswith(b">"):
-            cur = []
-            out[item.split(b">")[-1].decode()] = cur
-        else:
-            cur.append(int(item))
-    return {k: np.asarray(v, dtype=np.int64).astype(np.int32) for k, v in out.items()}
+    out, cur, pos = {}, None, 0
+
+    def numbers(body):
+        tok = body.split()
+        if tok:
+            out[cur].append(np.array(tok, dtype=np.int64))      # KeyError on numbers before the first header
+
+    for m in _DEPTH_HEADER.finditer(data):
+        numbers(data[pos:m.start()])
+        cur = m.group().strip().split(b">")[-1].decode()
+        out[cur] = []
+        pos = m.end()
+    numbers(data[pos:])
+    return {k: (np.concatenate(v) if v else np.zeros(0, np.int64)).astype(np.int32) for k, v in out.items()}
