@@ -389,6 +389,28 @@ def make_random_cases(ref, n_cases=16, seed=20240633, prefix="rand", save=True):
     return store, meta
 
 
+def make_sliding_window_kats(ref, n_cases=24):
+    """known answers of the reference's sliding_window_average_depth (GCI.py:660-705) -> sliding_window_kat.json"""
+    import contextlib
+    rng = np.random.default_rng(660705)
+    cases = []
+    for k in range(n_cases):
+        n = int(rng.integers(0, 300))
+        w = int(rng.choice([1, 2, 3, 7, 50, 1000]))
+        d = rng.integers(1, 40, n)
+        d[rng.random(n) < rng.choice([0.0, 0.05, 0.3, 0.9])] = 0
+        md = [3, 10.5, 100.0, 7][k % 4]
+        st = int(rng.integers(0, 10**7))
+        err = io.StringIO()
+        with contextlib.redirect_stderr(err):
+            pos, val = ref.sliding_window_average_depth(d.tolist(), w, md, st, "ctgA")
+        cases.append({"depths": d.tolist(), "window_size": w, "max_depth": md, "start": st, "target": "ctgA",
+                      "positions": pos, "values": val.tolist(), "dtype": str(val.dtype), "stderr": err.getvalue()})
+    with open(os.path.join(HERE, "sliding_window_kat.json"), "w") as f:
+        json.dump({"reference_commit": "455e19c7", "cases": cases}, f)
+    print("sliding window KATs:", len(cases))
+
+
 def make_mh63():
     data = gzip.open(os.path.join(REF, "example", "MH63.depth.gz"), "rb").read()
     names, vals, runs, lens = [], [], [], []
@@ -413,7 +435,10 @@ if __name__ == "__main__":
     ref = import_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "rand":
         make_random_cases(ref)
+    elif len(sys.argv) > 1 and sys.argv[1] == "window":
+        make_sliding_window_kats(ref)
     else:
+        make_sliding_window_kats(ref)
         make_filter_cases(ref)
         make_random_cases(ref)
         make_mh63()
