@@ -1,7 +1,7 @@
 """Plot feed: the data behind the reference's depth plots, without matplotlib.
 
-`sliding_window_average_depth` is `GCI.py:660-705` restated with numpy instead of a per-base Python loop (the
-reference spends about a second per Mbp there): same arguments, same stderr warning, same return value — the
+`sliding_window_average_depth` is `GCI.py:660-705` restated with numpy instead of a per-base Python loop:
+same arguments, same stderr warning, same return value — the
 positions in Mbp as a list and the averaged depths as an array — so the reference's plotting code can be fed
 from it unchanged.  Plotting itself stays out of scope.  Host code: nothing here is on the scored hot path.
 """
