@@ -38,7 +38,7 @@ CLI = {
         (('-fl', '--flank-len'), dict(_INT, default=15, help='The flanking length of the clipped bases [15]')),
     ],
     "Plot Options": [
-        (('-p', '--plot'), dict(_SWITCH, help='Visualize the finally filtered whole genome (and regions if providing the option `-R`) depth [False]')),
+        (('-p', '--plot'), dict(_SWITCH, help='Visualize the finally filtered whole genome (and regions if providing the option `-R`) depth [False]\n(not provided by the GPU build: a warning is printed, every other output is written)')),
         (('-dmin', '--depth-min'), dict(_FLOAT, default=0.1, help='Minimum depth in folds of mean coverage for plotting [0.1]')),
         (('-dmax', '--depth-max'), dict(_FLOAT, default=4.0, help='Maximum depth in folds of mean coverage for plotting [4.0]')),
         (('-ws', '--window-size'), dict(_INT, default=50000, help='The window size when plotting [50000]')),

@@ -313,7 +313,7 @@ def read_fasta_gaps_py(path):
                 ids.append(name)
                 chunks = []
             else:
-                chunks.append(line.strip())
+                chunks.append(line.strip().replace(b" ", b"").replace(b"\r", b""))   # like SimpleFastaParser
     flush()
     return ids, gaps
 

@@ -174,8 +174,38 @@ def write_depth(directory='.', prefix='GCI', depths={}, threads=1):
 # ------------------------------------------------------------------------------------------------
 # L2 + L3: filter
 # ------------------------------------------------------------------------------------------------
+def _remap_by_name(t, names, base_names):
+    """A later file's `ref_id`s live in that file's own @SQ order: bring them onto `base_names` by NAME, the way
+    the reference addresses contigs (`fetch(contig=target)`, GCI.py:150-151).  Contigs the base does not know are
+    never fetched by the reference (-> -1)."""
+    names = list(names)
+    if names == list(base_names):
+        return t
+    base = {n: i for i, n in enumerate(base_names)}
+    lut = np.full(len(names) + 1, -1, np.int32)             # last slot: ref_id outside the header stays -1
+    for i, n in enumerate(names):
+        lut[i] = base.get(n, -1)
+    rid = np.asarray(t.ref_id, np.int64)
+    rid = np.where((rid < 0) | (rid >= len(names)), len(names), rid)
+    out = AlnTable(lut[rid], t.ref_start, t.mapq, t.flag, t.nm, t.qlen, t.read_id, t.cigar_off, t.cigar)
+    return out
+
+
+def _remap_paf_by_name(t, names, base_names):
+    if list(names) == list(base_names):
+        return t
+    base = {n: i for i, n in enumerate(base_names)}
+    lut = np.full(len(names) + 1, -1, np.int32)
+    for i, n in enumerate(names):
+        lut[i] = base.get(n, -1)
+    rid = np.asarray(t.ref_id, np.int64)
+    rid = np.where((rid < 0) | (rid >= len(names)), len(names), rid)
+    return PafTable(t.read_id, t.qlen, t.qstart, t.qend, lut[rid], t.tstart, t.tend, t.nmatch, t.alnlen, t.mapq)
+
+
 def _load_inputs(paf_files, bam_files, threads=1):
-    """Decode / collect the files of one read type.  Returns (names, lengths, paf tables, bam tables, n_reads)."""
+    """Decode / collect the files of one read type.  Returns (names, lengths, paf tables, bam tables, n_reads).
+    Contig names and lengths are the first BAM's (GCI.py:201); every later BAM is remapped onto them by name."""
     intern = gio.NameTable()
     bams, pafs = [], []
     names = lengths = None
@@ -189,6 +219,8 @@ def _load_inputs(paf_files, bam_files, threads=1):
             n, l, t = gio.read_bam(f, intern, threads)
         if names is None:
             names, lengths = list(n), [int(x) for x in l]     # header of the first BAM (GCI.py:201)
+        else:
+            t = _remap_by_name(t, n, names)
         bams.append(t)
     for f in paf_files:
         pafs.append(f if isinstance(f, PafTable) else gio.read_paf(f, names, intern))
@@ -209,8 +241,21 @@ def filter(paf_files=[], bam_files=[], prefix='GCI', map_qual=30, mq_cutoff=50, 
     session = session or default_session()
     ctx = session.ctx
     names, lengths, pafs, bams, n_reads = _load_inputs(paf_files, bam_files, threads)
+    out_order = None
+    if session.names is not None and names != session.names and sorted(names) == sorted(session.names) \
+            and dict(zip(names, lengths)) == dict(zip(session.names, session.lengths)):
+        # same contigs in another @SQ order (e.g. the ONT BAM of a HiFi + ONT run): the tracks already held by the
+        # session stay valid, the records move onto its order by name; the outputs keep THIS file's order, like
+        # the reference's `depths` dict (GCI.py:201-207)
+        bams = [_remap_by_name(t, names, session.names) for t in bams]
+        pafs = [_remap_paf_by_name(t, names, session.names) for t in pafs]
+        out_order = list(names)
+        names, lengths = list(session.names), list(session.lengths)
     session.configure(names, lengths, chrs_list)
-    targets_length = {n: l for n, l, s in zip(names, lengths, session.selected) if s}
+    if out_order is None:
+        out_order = names
+    sel = dict(zip(names, session.selected))
+    targets_length = {n: l for n, l in zip(out_order, (dict(zip(names, lengths))[x] for x in out_order)) if sel[n]}
     track = TRACK_NANO if log_reads_type == 'ONT' else TRACK_HIFI
 
     ctx.reads_begin(n_reads)
@@ -222,12 +267,13 @@ def filter(paf_files=[], bam_files=[], prefix='GCI', map_qual=30, mq_cutoff=50, 
     lo, hi = session.scan_hint if session.scan_hint is not None else (NO_FLAGS, NO_FLAGS)
     ctx.depth(track, flank_len, lo, hi)
     depths = DeviceDepths(session, track)
+    depths._names = list(targets_length.keys())
 
     print(f'Filtering {log_reads_type} alignment files done!!!')
-    print(f'Writing depths into "{directory}/{prefix}.depth.gz" ...')
     if write:
+        print(f'Writing depths into "{directory}/{prefix}.depth.gz" ...')
         write_depth(directory, prefix, depths, threads)
-    print(f'Writing depths done!!!\n\n')
+        print(f'Writing depths done!!!\n\n')
     return depths, targets_length
 
 
@@ -253,6 +299,7 @@ def merge_two_type_depth(hifi_depths={}, nano_depths={}, prefix='GCI_two_type', 
     lo, hi = session.scan_hint if session.scan_hint is not None else (NO_FLAGS, NO_FLAGS)
     session.ctx.merge_max(hifi_depths.track, nano_depths.track, TRACK_MERGED, lo, hi)
     merged = DeviceDepths(session, TRACK_MERGED)
+    merged._names = list(hifi_depths.keys())
     if write:
         write_depth(directory, prefix, merged, threads)
     print('Merging HiFi and ONT depth file done!!!\n\n')
@@ -277,9 +324,12 @@ def collapse_depth_range(depths={}, leftmost=-1, rightmost=0, flank_len=15, star
     s, e, off = ctx.fetch_intervals(depths.track, len(owners))
     bed = DeviceBed()
     sl, el = s.tolist(), e.tolist()
+    by_name = {}
     for o, name in enumerate(owners):
         a, b = int(off[o]), int(off[o + 1])
-        bed[name] = list(zip(sl[a:b], el[a:b]))
+        by_name[name] = list(zip(sl[a:b], el[a:b]))
+    for name in depths.keys():           # the depth mapping's own order (a permuted @SQ order keeps its file's)
+        bed[name] = by_name[name]
     _scan_counter[0] += 1
     bed.session, bed.track, bed.scan_id = session, depths.track, _scan_counter[0]
     session.__dict__.setdefault("_last_scan", {})[depths.track] = (bed.scan_id, len(s))
@@ -511,7 +561,8 @@ def GCI(hifi=[], nano=[], directory='.', prefix='GCI', map_qual=30, mq_cutoff=50
     regions_bed = _load_regions(regions)
     directory = _prepare_directory(directory, prefix)
     if plot == True:
-        sys.exit('ERROR!!! Plotting (-p) is not part of the GPU hot path; run the reference\'s utility/plot_depth.py on the .depth.gz outputs')
+        # plotting is outside the hot path: the run goes ahead and writes every other output
+        print('WARNING!!! Plotting (-p) is not provided by the GPU build and is skipped; run the reference\'s utility/plot_depth.py on the .depth.gz outputs', file=sys.stderr)
 
     parsed_ref = _read_reference(reference)       # one pass over the FASTA: record ids + N-runs
     ref_refs = parsed_ref[0]

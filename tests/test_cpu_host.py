@@ -298,3 +298,22 @@ def test_name_table_is_shared_between_files(tmp_path):
         m_p = dict(zip(paf.read_id.tolist(), p.read_id.tolist()))
         common = set(m_b) & set(m_p)
         assert len(common) > 20 and all(m_p[k] == m_b[k] for k in common)
+
+
+def test_later_bam_with_permuted_sq_order_is_remapped_by_name():
+    """the reference addresses contigs by NAME (fetch(contig=target), GCI.py:150-151); a later BAM whose
+    @SQ order differs must land on the first BAM's contig indices, unknown contigs on -1."""
+    from gci_b200 import pipeline as P
+    a = AlnTable.from_rows([dict(ref_id=0, ref_start=5, mapq=60, flag=0, nm=0, qlen=10, read_id=0, cigar="10M"),
+                            dict(ref_id=1, ref_start=7, mapq=60, flag=0, nm=0, qlen=10, read_id=1, cigar="10M")])
+    a.contig_names, a.contig_lengths = ["chr1", "chr2"], [100, 200]
+    b = AlnTable.from_rows([dict(ref_id=0, ref_start=5, mapq=60, flag=0, nm=0, qlen=10, read_id=1, cigar="10M"),
+                            dict(ref_id=1, ref_start=7, mapq=60, flag=0, nm=0, qlen=10, read_id=0, cigar="10M"),
+                            dict(ref_id=2, ref_start=1, mapq=60, flag=0, nm=0, qlen=10, read_id=2, cigar="10M"),
+                            dict(ref_id=-1, ref_start=0, mapq=0, flag=4, nm=0, qlen=10, read_id=3, cigar="*")])
+    b.contig_names, b.contig_lengths = ["chr2", "chr1", "chrUn"], [200, 100, 50]
+    names, lengths, pafs, bams, n_reads = P._load_inputs([], [a, b])
+    assert names == ["chr1", "chr2"] and lengths == [100, 200] and n_reads == 4
+    assert bams[0].ref_id.tolist() == [0, 1]
+    assert bams[1].ref_id.tolist() == [1, 0, -1, -1]
+    assert bams[1].ref_start.tolist() == [5, 7, 1, 0]
