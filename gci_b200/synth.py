@@ -280,3 +280,168 @@ def drop_reads(tab: AlnTable, frac: float, seed: int) -> AlnTable:
     rng = np.random.default_rng(seed)
     keep = np.flatnonzero(rng.random(tab.n_records) >= frac)
     return tab.take(keep)
+
+
+# ---------------------------------------------------------------------------------------------------
+# whole-genome workloads (BASELINE.json configs 2-4): one BAM (+ one PAF from a second aligner)
+# ---------------------------------------------------------------------------------------------------
+# CHM13v2.0-like chromosome lengths (chr1..chr22, chrX, chrY): 24 contigs, 3.117 Gbp
+CHM13_NAMES = [f"chr{i}" for i in range(1, 23)] + ["chrX", "chrY"]
+CHM13_LENGTHS = [248_387_328, 242_696_752, 201_105_948, 193_574_945, 182_045_439, 172_126_628, 160_567_428,
+                 146_259_331, 150_617_247, 134_758_134, 135_127_769, 133_324_548, 113_566_686, 101_161_492,
+                 99_753_195, 96_330_374, 84_276_897, 80_542_538, 61_707_364, 66_210_255, 45_090_682, 51_324_926,
+                 154_259_566, 62_460_029]
+
+
+def paf_second_aligner(paf: PafTable, lengths, seed: int, split_frac=0.03, alt_frac=0.02, tie_frac=0.003) -> PafTable:
+    """The reads of `paf` (one line per BAM record, `aln_to_paf`) as a second aligner would report them
+    (SURVEY.md §8d): 2 % missing, 5 % shifted by U(0, 0.2 len), 3 % placed on another contig, own MAPQ for a
+    tenth; plus what only a PAF has (GCI.py:211-254 elects among them): `split_frac` of the lines come as two
+    blocks of the same read on the same contig, `alt_frac` of the reads carry a weaker extra line on another
+    contig, `tie_frac` an identical line on another contig (equal score: the contig NAME decides, :252)."""
+    rng = np.random.default_rng(seed)
+    lengths = np.asarray(lengths, np.int64)
+    n = paf.n_records
+    nct = len(lengths)
+    cols = {k: getattr(paf, k).astype(np.int64) for k in
+            ("read_id", "qlen", "qstart", "qend", "ref_id", "tstart", "tend", "nmatch", "alnlen", "mapq")}
+    span = cols["tend"] - cols["tstart"]
+    u = rng.random(n)
+    keep = u >= 0.02
+    shift = (u >= 0.02) & (u < 0.07)
+    move = (u >= 0.07) & (u < 0.10)
+    dlt = (rng.random(n) * 0.2 * span).astype(np.int64) * np.where(rng.random(n) < 0.5, -1, 1)
+    ts = np.where(shift, cols["tstart"] + dlt, cols["tstart"])
+    ref = cols["ref_id"].copy()
+    if nct > 1:
+        ref = np.where(move, (ref + 1 + rng.integers(0, nct - 1, n)) % nct, ref)
+    else:
+        ts = np.where(move, ts + span + 1000, ts)
+    ts = np.clip(ts, 0, np.maximum(0, lengths[ref] - span))
+    keep &= (ts + span) <= lengths[ref]
+    cols["tstart"], cols["tend"], cols["ref_id"] = ts, ts + span, ref
+    re_mq = rng.random(n) < 0.1
+    cols["mapq"] = np.where(re_mq, rng.choice(np.array([0, 20, 35, 45, 60]), n), cols["mapq"])
+
+    def rows(mask):
+        idx = np.flatnonzero(mask & keep)
+        return {k: v[idx] for k, v in cols.items()}, idx
+
+    base, base_idx = rows(np.ones(n, bool))
+    parts = [base]
+    order_key = [base_idx.astype(np.float64)]
+    # split lines: [q0, qm) + [qm - ov, q1) on the query, the same cut on the target
+    v = rng.random(n)
+    sp, sp_idx = rows(v < split_frac)
+    if len(sp_idx):
+        frac = rng.uniform(0.2, 0.8, len(sp_idx))
+        qcut = (sp["qstart"] + (sp["qend"] - sp["qstart"]) * frac).astype(np.int64)
+        tcut = (sp["tstart"] + (sp["tend"] - sp["tstart"]) * frac).astype(np.int64)
+        ov = rng.integers(-50, 50, len(sp_idx))
+        a_len = (sp["alnlen"] * frac).astype(np.int64).clip(1)
+        a_match = (sp["nmatch"] * frac).astype(np.int64).clip(0)
+        first = dict(sp, qend=qcut, tend=tcut, alnlen=a_len, nmatch=np.minimum(a_match, a_len))
+        b_len = (sp["alnlen"] - a_len).clip(1)
+        second = dict(sp, qstart=np.maximum(sp["qstart"], qcut - ov), tstart=np.maximum(sp["tstart"], tcut - ov),
+                      alnlen=b_len, nmatch=np.minimum((sp["nmatch"] - a_match).clip(0), b_len))
+        # the whole line of these reads is replaced by the two blocks
+        gone = np.isin(base_idx, sp_idx)
+        parts[0] = {k: x[~gone] for k, x in base.items()}
+        order_key[0] = order_key[0][~gone]
+        parts += [first, second]
+        order_key += [sp_idx + 0.1, sp_idx + 0.2]
+    if nct > 1:
+        for lo, hi, tie in ((split_frac, split_frac + alt_frac, False),
+                            (split_frac + alt_frac, split_frac + alt_frac + tie_frac, True)):
+            al, al_idx = rows((v >= lo) & (v < hi))
+            if not len(al_idx):
+                continue
+            other = (al["ref_id"] + 1 + rng.integers(0, nct - 1, len(al_idx))) % nct
+            sp_len = al["tend"] - al["tstart"]
+            t0 = (rng.random(len(al_idx)) * np.maximum(1, lengths[other] - sp_len)).astype(np.int64)
+            ok = t0 + sp_len <= lengths[other]
+            extra = dict(al, ref_id=other, tstart=t0, tend=t0 + sp_len)
+            if not tie:
+                cover = rng.uniform(0.3, 1.0, len(al_idx))
+                extra["qend"] = (al["qstart"] + (al["qend"] - al["qstart"]) * cover).astype(np.int64)
+                extra["nmatch"] = (al["nmatch"] * rng.uniform(0.93, 1.0, len(al_idx))).astype(np.int64)
+            extra = {k: x[ok] for k, x in extra.items()}
+            parts.append(extra)
+            # half of the extra lines arrive before the read's main line, half after
+            order_key.append(al_idx[ok] + np.where(rng.random(int(ok.sum())) < 0.5, -0.5, 0.5))
+    key = np.concatenate(order_key)
+    order = np.argsort(key, kind="stable")
+    out = {k: np.concatenate([p[k] for p in parts])[order] for k in cols}
+    return PafTable(out["read_id"], out["qlen"], out["qstart"], out["qend"], out["ref_id"], out["tstart"], out["tend"],
+                    out["nmatch"], out["alnlen"], out["mapq"])
+
+
+@dataclass
+class GenomeWorkload:
+    contigs: ContigTable
+    bam: AlnTable                     # first aligner, coordinate sorted
+    paf: PafTable                     # second aligner (None without `with_paf`)
+    n_reads: int
+    holes: list
+    n_runs: list
+    aligned_bases: int                # sum over the records of BOTH files of ref_end - ref_start (SURVEY.md §8d)
+
+
+def concat_aln(tabs) -> AlnTable:
+    ops = np.cumsum([0] + [t.n_ops for t in tabs])
+    off = np.concatenate([np.zeros(1, np.uint64)] + [t.cigar_off[1:] + np.uint64(o) for t, o in zip(tabs, ops)])
+    return AlnTable(*[np.concatenate([getattr(t, k) for t in tabs]) for k in
+                      ("ref_id", "ref_start", "mapq", "flag", "nm", "qlen", "read_id")], off,
+                    np.concatenate([t.cigar for t in tabs]))
+
+
+def concat_paf(tabs) -> PafTable:
+    return PafTable(*[np.concatenate([getattr(t, k) for t in tabs]) for k in
+                      ("read_id", "qlen", "qstart", "qend", "ref_id", "tstart", "tend", "nmatch", "alnlen", "mapq")])
+
+
+def make_genome(lengths, names=None, coverage=30.0, seed=20240635, with_paf=True, drop_first=0.02, threads=0,
+                contig_ids=None, **spec_kw) -> GenomeWorkload:
+    """One synthetic read set over a whole genome, generated contig by contig (seed + contig index) on a thread
+    pool: a minimap2-like BAM and, with `with_paf`, the same reads as a winnowmap-like PAF.  `contig_ids`
+    restricts the BAM to those contigs (a rank's shard of a multi-GPU run; read ids stay global)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    lengths = [int(x) for x in lengths]
+    nct = len(lengths)
+    names = list(names) if names is not None else [f"chr{i + 1}" for i in range(nct)]
+    todo = list(range(nct)) if contig_ids is None else list(contig_ids)
+
+    def one(c):
+        d = make_reads(SynthSpec([lengths[c]], coverage=coverage, seed=seed + c, **spec_kw))
+        paf = aln_to_paf(d.bam) if with_paf else None
+        bam = drop_reads(d.bam, drop_first, seed + 1000 + c) if drop_first > 0 else d.bam
+        return d, bam, paf
+
+    threads = threads or min(len(todo), os.cpu_count() or 1)
+    with ThreadPoolExecutor(max(1, threads)) as ex:
+        parts = list(ex.map(one, todo))
+    # global read ids: contig c's reads start at the sum of the earlier contigs' record budgets (an upper bound of
+    # their read counts that needs no generation), so a shard sees the same ids as the whole genome
+    budget = np.maximum(1, (np.asarray(lengths, np.float64) * coverage /
+                            spec_kw.get("read_mean", SynthSpec.read_mean)).astype(np.int64))
+    base = np.concatenate([[0], np.cumsum(budget)])
+    n_reads = int(base[-1])
+    bams, pafs, holes, n_runs, aligned = [], [], [None] * nct, [None] * nct, 0
+    for c, (d, bam, paf) in zip(todo, parts):
+        assert d.n_reads <= budget[c]
+        bam.ref_id[:] = c
+        bam.read_id += np.uint32(base[c])
+        if paf is not None:
+            paf.ref_id[:] = c
+            paf.read_id += np.uint32(base[c])
+            pafs.append(paf)
+        bams.append(bam)
+        holes[c], n_runs[c] = d.holes[0], d.n_runs[0]
+        aligned += int(bam.ref_len().sum())
+    bam = concat_aln(bams)
+    paf = None
+    if with_paf:
+        paf = paf_second_aligner(concat_paf(pafs), lengths, seed + 7)
+        aligned += int((paf.tend.astype(np.int64) - paf.tstart).sum())
+    return GenomeWorkload(ContigTable(names, lengths), bam, paf, n_reads, holes, n_runs, aligned)

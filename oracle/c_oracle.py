@@ -28,6 +28,7 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.orc_collapse.restype = C.c_int64
         _lib.orc_max_threads.restype = C.c_int
+        _lib.orc_depth_hash.restype = C.c_uint64
     return _lib
 
 
@@ -112,12 +113,54 @@ def collapse(depth_arr, leftmost=-1, rightmost=0, flank_len=15, start_pos=0):
         cap = int(n)
 
 
+def paf_leg(pafs, selected, name_rank, n_reads, map_qual=30, mq_cutoff=50, iden_percent=0.9, threads=1):
+    """GCI.py:211-254 over all PAF files of a read type -> ([per file (contig or -1, start, end, qlen)], highq)"""
+    L = lib()
+    f = len(pafs)
+    off = np.concatenate([[0], np.cumsum([t.n_records for t in pafs])]).astype(np.int64)
+    cat = lambda k, dt: np.ascontiguousarray(np.concatenate([getattr(t, k) for t in pafs]) if f else np.zeros(0, dt), dt)
+    cols = [cat("read_id", np.uint32)] + [cat(k, np.int32) for k in
+                                          ("qlen", "qstart", "qend", "ref_id", "tstart", "tend", "nmatch", "alnlen", "mapq")]
+    sel = np.ascontiguousarray(selected, dtype=np.uint8)
+    rank = np.ascontiguousarray(name_rank, dtype=np.int32)
+    nr = max(1, n_reads)
+    oc, os_, oe, oq = (np.zeros(max(1, f) * nr, np.int32) for _ in range(4))
+    highq = np.zeros(nr, np.uint8)
+    bad = L.orc_paf_leg(C.c_int32(f), _ptr(off), *[_ptr(c) for c in cols], _ptr(sel), C.c_int32(len(sel)), _ptr(rank),
+                        C.c_uint32(n_reads), C.c_int32(map_qual), C.c_int32(mq_cutoff), C.c_double(iden_percent),
+                        _ptr(oc), _ptr(os_), _ptr(oe), _ptr(oq), _ptr(highq), C.c_int(threads))
+    if bad:
+        raise RaisesLikeReference(f"the reference raises on this input (mask {bad})")
+    tabs = [tuple(x[i * nr:i * nr + n_reads] for x in (oc, os_, oe, oq)) for i in range(f)]
+    return tabs, highq[:n_reads]
+
+
+def depth_hash(depth_arr, threads=1):
+    """order-independent 64-bit checksum of one depth array; gci_depth_hash computes the same on the GPU"""
+    d = np.ascontiguousarray(depth_arr, np.int64)
+    return int(lib().orc_depth_hash(_ptr(d), C.c_int64(len(d)), C.c_int(threads)))
+
+
+def name_rank(names):
+    order = sorted(range(len(names)), key=lambda i: names[i])
+    rank = np.empty(len(names), np.int32)
+    rank[order] = np.arange(len(names), dtype=np.int32)
+    return rank
+
+
 def hot_path(bams, lengths, n_reads, selected=None, map_qual=30, mq_cutoff=50, iden_percent=0.9, clip_percent=0.1,
-             ovlp_percent=0.9, flank_len=15, threshold=0, threads=1):
-    """BAM-only hot path: gates -> dedup -> join -> depth -> collapse.  Returns (depths, beds, n_survivors)."""
+             ovlp_percent=0.9, flank_len=15, threshold=0, threads=1, pafs=(), names=None):
+    """Whole hot path on the CPU: PAF election + BAM gates -> dedup -> join (PAFs first, GCI.py:272) -> depth ->
+    collapse.  Returns (depths, beds, n_survivors)."""
     if selected is None:
         selected = np.ones(len(lengths), bool)
     tables, hq = [], np.zeros(n_reads, np.uint8)
+    if len(pafs):
+        if names is None:
+            names = [f"chr{i + 1}" for i in range(len(lengths))]
+        ptabs, phq = paf_leg(list(pafs), selected, name_rank(names), n_reads, map_qual, mq_cutoff, iden_percent, threads)
+        tables += ptabs
+        hq |= phq
     for t in bams:
         c, s, e, q, h = bam_leg(t, selected, n_reads, map_qual, mq_cutoff, iden_percent, clip_percent, threads)
         tables.append((c, s, e, q))

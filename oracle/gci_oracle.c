@@ -230,6 +230,185 @@ void orc_max(const int64_t* a, const int64_t* b, int64_t* out, int64_t n, int th
   run_parallel(max_part, &m, threads);
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * PAF leg, GCI.py:211-254 with merge_alns_properties (:64-96) and get_average_identity (:49-61).
+ * Lines of all PAF files are given concatenated (file f = lines [file_off[f], file_off[f+1])); the
+ * reference's `synteny` dict is created once (:214), so file f elects over the kept lines of files 0..f.
+ * Output per file and read: oc (contig or -1), os / oe (largest merged target block), oq (query length).
+ * name_rank[c] = rank of contig c's name under str ordering (the (score, name) sort key of :252).
+ * Returns a bit mask: 16 = ZeroDivisionError at :231 (alnlen 0), 32 = at :247 (query length 0).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { int32_t lo, hi; } orc_pair;
+static int pair_cmp(const void* a, const void* b) {
+  const orc_pair *x = (const orc_pair*)a, *y = (const orc_pair*)b;
+  if (x->lo != y->lo) return x->lo < y->lo ? -1 : 1;
+  if (x->hi != y->hi) return x->hi < y->hi ? -1 : 1;
+  return 0;
+}
+/* GCI.py:64-96: sorted pairs, merge touching / overlapping blocks; total merged length, and the longest block
+   (the first one on ties: sorted(..., key=len, reverse=True) is stable) */
+static int64_t merge_blocks(orc_pair* p, int n, int32_t* best_lo, int32_t* best_hi) {
+  qsort(p, (size_t)n, sizeof(orc_pair), pair_cmp);
+  int64_t total = 0, best = -1;
+  int32_t lo = p[0].lo, hi = p[0].hi;
+  for (int i = 0; i < n; i++) {
+    if (hi >= p[i].lo) { if (hi < p[i].hi) hi = p[i].hi; }
+    else {
+      const int64_t len = (int64_t)hi - lo;
+      total += len;
+      if (len > best) { best = len; *best_lo = lo; *best_hi = hi; }
+      lo = p[i].lo; hi = p[i].hi;
+    }
+  }
+  const int64_t len = (int64_t)hi - lo;
+  total += len;
+  if (len > best) { *best_lo = lo; *best_hi = hi; }
+  return total;
+}
+
+typedef struct {
+  int32_t n_files; const int64_t* file_off; const uint32_t* read_id; const int32_t *qlen, *q0, *q1, *ref, *t0, *t1, *nmatch,
+      *alnlen, *mapq; const uint8_t* selected; int32_t n_contigs; const int32_t* name_rank; uint32_t n_reads;
+  int32_t map_qual, mq_cutoff; double ip;
+  int8_t* keep; double* ident;                 /* per line */
+  const int64_t* grp_off; const int64_t* grp;  /* kept lines grouped by read, in line order */
+  int32_t *oc, *os, *oe, *oq; uint8_t* highq; int bad[256];
+} paf_args;
+
+static void paf_gate_part(int tid, int nt, void* p) {
+  paf_args* a = (paf_args*)p;
+  const int64_t n = a->file_off[a->n_files];
+  int bad = 0;
+  for (int64_t i = n * tid / nt; i < n * (tid + 1) / nt; i++) {
+    a->keep[i] = 0;
+    const int32_t t = a->ref[i];
+    if (t < 0 || t >= a->n_contigs || !a->selected[t]) continue;           /* :220 */
+    if (a->alnlen[i] == 0) { bad |= 16; continue; }                         /* :231 raises */
+    const double id = (double)a->nmatch[i] / (double)a->alnlen[i];
+    a->ident[i] = id;
+    if (a->mapq[i] >= a->map_qual && id >= a->ip && a->read_id[i] < a->n_reads) a->keep[i] = 1;   /* :232 */
+  }
+  a->bad[tid] |= bad;
+}
+
+static void paf_elect_part(int tid, int nt, void* p) {
+  paf_args* a = (paf_args*)p;
+  int bad = 0;
+  int cap = 64;
+  orc_pair* pr = (orc_pair*)malloc(sizeof(orc_pair) * (size_t)cap);
+  const uint32_t r0 = (uint32_t)((uint64_t)a->n_reads * tid / nt), r1 = (uint32_t)((uint64_t)a->n_reads * (tid + 1) / nt);
+  for (int32_t f = 0; f < a->n_files; f++) {
+    const int64_t limit = a->file_off[f + 1];
+    int32_t *oc = a->oc + (size_t)f * a->n_reads, *os = a->os + (size_t)f * a->n_reads,
+            *oe = a->oe + (size_t)f * a->n_reads, *oq = a->oq + (size_t)f * a->n_reads;
+    for (uint32_t r = r0; r < r1; r++) {
+      const int64_t* g = a->grp + a->grp_off[r];
+      int n = 0;
+      const int64_t gn = a->grp_off[r + 1] - a->grp_off[r];
+      while (n < gn && g[n] < limit) n++;                                   /* lines of files 0..f */
+      oc[r] = -1; os[r] = 0; oe[r] = 0; oq[r] = 0;
+      if (n == 0) continue;
+      if (n > cap) { cap = n * 2; pr = (orc_pair*)realloc(pr, sizeof(orc_pair) * (size_t)cap); }
+      int have = 0, failed = 0;
+      double best_score = 0;
+      int32_t best_rank = 0;
+      for (int i = 0; i < n && !failed; i++) {
+        const int32_t t = a->ref[g[i]];
+        int seen = 0;
+        for (int j = 0; j < i && !seen; j++) seen = a->ref[g[j]] == t;
+        if (seen) continue;                                                 /* dict order = first appearance */
+        double sum = 0;
+        int cnt = 0, m = 0;
+        for (int j = i; j < n; j++)
+          if (a->ref[g[j]] == t) { sum = sum + a->ident[g[j]]; cnt++; pr[m].lo = a->q0[g[j]]; pr[m].hi = a->q1[g[j]]; m++; }
+        const int32_t ql = a->qlen[g[i]];                                   /* alns[0][0], :246 */
+        if (ql == 0) { bad |= 32; failed = 1; break; }
+        int32_t dl = 0, dh = 0;
+        const int64_t mapped = merge_blocks(pr, m, &dl, &dh);
+        const double rate = (double)mapped / (double)ql;                   /* :247 */
+        const double score = (sum / (double)cnt) * rate;                   /* :248-249 */
+        m = 0;
+        for (int j = i; j < n; j++)
+          if (a->ref[g[j]] == t) { pr[m].lo = a->t0[g[j]]; pr[m].hi = a->t1[g[j]]; m++; }
+        int32_t tl = 0, th = 0;
+        merge_blocks(pr, m, &tl, &th);
+        const int32_t rank = a->name_rank[t];
+        if (!have || score > best_score || (score == best_score && rank > best_rank)) {   /* :252 */
+          have = 1; best_score = score; best_rank = rank;
+          oc[r] = t; os[r] = tl; oe[r] = th; oq[r] = ql;
+        }
+      }
+      if (failed) oc[r] = -1;
+    }
+  }
+  free(pr);
+  a->bad[tid] |= bad;
+}
+
+int orc_paf_leg(int32_t n_files, const int64_t* file_off, const uint32_t* read_id, const int32_t* qlen, const int32_t* q0,
+                const int32_t* q1, const int32_t* ref, const int32_t* t0, const int32_t* t1, const int32_t* nmatch,
+                const int32_t* alnlen, const int32_t* mapq, const uint8_t* selected, int32_t n_contigs,
+                const int32_t* name_rank, uint32_t n_reads, int32_t map_qual, int32_t mq_cutoff, double ip, int32_t* oc,
+                int32_t* os, int32_t* oe, int32_t* oq, uint8_t* highq, int threads) {
+  const int64_t n = file_off[n_files];
+  paf_args a;
+  memset(&a, 0, sizeof a);
+  a.n_files = n_files; a.file_off = file_off; a.read_id = read_id; a.qlen = qlen; a.q0 = q0; a.q1 = q1; a.ref = ref;
+  a.t0 = t0; a.t1 = t1; a.nmatch = nmatch; a.alnlen = alnlen; a.mapq = mapq; a.selected = selected;
+  a.n_contigs = n_contigs; a.name_rank = name_rank; a.n_reads = n_reads; a.map_qual = map_qual; a.mq_cutoff = mq_cutoff;
+  a.ip = ip; a.oc = oc; a.os = os; a.oe = oe; a.oq = oq; a.highq = highq;
+  a.keep = (int8_t*)malloc((size_t)(n > 0 ? n : 1));
+  a.ident = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  if (threads > 256) threads = 256;
+  run_parallel(paf_gate_part, &a, threads);
+  /* group the kept lines by read, in line order (a counting sort: stable) */
+  int64_t* goff = (int64_t*)calloc((size_t)n_reads + 2, sizeof(int64_t));
+  for (int64_t i = 0; i < n; i++)
+    if (a.keep[i]) { goff[read_id[i] + 1]++; if (mapq[i] >= mq_cutoff) highq[read_id[i]] = 1; }   /* :238 */
+  for (uint32_t r = 0; r < n_reads; r++) goff[r + 1] += goff[r];
+  int64_t* cur = (int64_t*)malloc(sizeof(int64_t) * ((size_t)n_reads + 1));
+  memcpy(cur, goff, sizeof(int64_t) * ((size_t)n_reads + 1));
+  int64_t* grp = (int64_t*)malloc(sizeof(int64_t) * (size_t)(goff[n_reads] > 0 ? goff[n_reads] : 1));
+  for (int64_t i = 0; i < n; i++)
+    if (a.keep[i]) grp[cur[read_id[i]]++] = i;
+  a.grp_off = goff; a.grp = grp;
+  run_parallel(paf_elect_part, &a, threads);
+  int bad = 0;
+  for (int t = 0; t < 256; t++) bad |= a.bad[t];
+  free(a.keep); free(a.ident); free(goff); free(cur); free(grp);
+  return bad;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Order-independent 64-bit checksum of one depth array (test / bench parity gate at sizes where whole
+ * arrays are not compared): sum over positions of (depth + 1) * splitmix64(position), mod 2^64.
+ * The CUDA side computes the same number (gci_depth_hash).
+ * ---------------------------------------------------------------------------------------------- */
+static inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+typedef struct { const int64_t* d; int64_t n; uint64_t part[256]; } hash_args;
+static void hash_part(int tid, int nt, void* p) {
+  hash_args* a = (hash_args*)p;
+  uint64_t h = 0;
+  for (int64_t i = a->n * tid / nt; i < a->n * (tid + 1) / nt; i++) h += (uint64_t)(a->d[i] + 1) * splitmix64((uint64_t)i);
+  a->part[tid] = h;
+}
+uint64_t orc_depth_hash(const int64_t* depth, int64_t n, int threads) {
+  hash_args a;
+  memset(&a, 0, sizeof a);
+  a.d = depth; a.n = n;
+  if (threads > 256) threads = 256;
+  if (threads < 1) threads = 1;
+  run_parallel(hash_part, &a, threads);
+  uint64_t h = 0;
+  for (int t = 0; t < threads; t++) h += a.part[t];
+  return h;
+}
+
 int orc_max_threads(void) {
   long n = sysconf(_SC_NPROCESSORS_ONLN);
   return n > 0 ? (int)n : 1;

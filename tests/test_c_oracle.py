@@ -28,3 +28,49 @@ def test_c_collapse_equals_loop():
         d = (rng.random(n) < rng.random()).astype(np.int64) * rng.integers(1, 4, n)
         ts = int(rng.integers(0, 3))
         assert CO.collapse(d, -1, ts, fl, 3) == O.collapse_depth_range_loop(d, -1, ts, fl, 3)
+
+
+@pytest.mark.parametrize("seed,threads,n_paf", [(0, 1, 1), (1, 4, 2), (2, 3, 3)])
+def test_c_paf_leg_equals_python_oracle(seed, threads, n_paf):
+    """orc_paf_leg (GCI.py:211-254 incl. the synteny dict leaking across PAF files) against the Python oracle,
+    on reads with split lines, weaker lines on other contigs and exact score ties (contig name decides)."""
+    lengths = [x // 300 for x in synth.CHM13_LENGTHS[:7]]
+    names = ["chr10", "chr9", "chrB", "chrA", "chr1", "chr2", "chr11"]         # str order differs from index order
+    w = synth.make_genome(lengths, names, coverage=12, seed=40 + seed, read_mean=6000, read_min=800, read_max=15000)
+    pafs = [w.paf] + [synth.paf_second_aligner(w.paf, lengths, 90 + seed + k, split_frac=0.1, alt_frac=0.1,
+                                               tie_frac=0.05) for k in range(1, n_paf)]
+    sel = np.ones(len(lengths), bool)
+    sel[3] = seed != 2
+    want, want_hq = O.paf_leg(pafs, sel, names, 30, 0.9, 50)
+    got, got_hq = CO.paf_leg(pafs, sel, CO.name_rank(names), w.n_reads, threads=threads)
+    assert sorted(want_hq) == np.flatnonzero(got_hq).tolist()
+    for f in range(n_paf):
+        c, s, e, q = got[f]
+        have = np.flatnonzero(c >= 0)
+        assert sorted(want[f]) == have.tolist()
+        for r in have.tolist():
+            assert want[f][r] == (int(c[r]), int(s[r]), int(e[r]), int(q[r])), (f, r)
+    # and the whole path with the PAFs joined first (GCI.py:272)
+    want_d, want_s = O.filter_depth(pafs, [w.bam], names, lengths, selected=sel)
+    got_d, got_b, n_surv = CO.hot_path([w.bam], lengths, w.n_reads, selected=sel, threads=threads, pafs=pafs, names=names)
+    assert n_surv == len(want_s)
+    for i in range(len(lengths)):
+        assert np.array_equal(got_d[i], want_d[i])
+
+
+def test_c_depth_hash_is_position_sensitive():
+    rng = np.random.default_rng(5)
+    d = rng.integers(0, 60, 100_000).astype(np.int64)
+    h = CO.depth_hash(d, threads=3)
+    assert h == CO.depth_hash(d, threads=1)
+    x = d.copy(); x[[10, 11]] = x[[11, 10]]
+    assert (CO.depth_hash(x) == h) == (d[10] == d[11])
+    y = d.copy(); y[77] += 1; y[78] -= 1
+    assert CO.depth_hash(y) != h
+    # the definition the CUDA side restates: sum (depth + 1) * splitmix64(position) mod 2^64
+    def sm(v):
+        v = (v + 0x9E3779B97F4A7C15) & (2**64 - 1)
+        v = ((v ^ (v >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
+        v = ((v ^ (v >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
+        return v ^ (v >> 31)
+    assert CO.depth_hash(d[:50]) == sum((int(v) + 1) * sm(i) for i, v in enumerate(d[:50])) % 2**64
