@@ -70,6 +70,7 @@ _SIGNATURES = {
     "gci_fetch_depth": (C.c_int, [_p, _i32, _i32, _p, _i64]),
     "gci_fetch_depth_narrow": (C.c_int, [_p, _i32, _i32, _p, _i64, _i32, C.POINTER(_i32)]),
     "gci_depth_sums": (C.c_int, [_p, _i32, _p]),
+    "gci_depth_hash": (C.c_int, [_p, _i32, _p]),
     "gci_depth_text": (C.c_int, [_p, _i32, _i32, _i64, _i64, _p, _i64, C.POINTER(_i64)]),
     "gci_depth_gzip": (C.c_int, [_p, _i32, _i32, _i64, _i64, C.c_char_p, _i32, _p, _i64, C.POINTER(_i64)]),
     "gci_scan": (C.c_int, [_p, _i32, _i32, _i32, _i32, C.POINTER(_i64)]),
@@ -348,6 +349,12 @@ class Context:
         self._check(self._lib.gci_depth_sums(self._h, track, _ptr(out)))
         return out
 
+    def depth_hash(self, track):
+        """per contig: sum (depth + 1) * splitmix64(position) mod 2^64 (oracle: c_oracle.depth_hash)"""
+        out = np.zeros(self.n_contigs, np.uint64)
+        self._check(self._lib.gci_depth_hash(self._h, track, _ptr(out)))
+        return out
+
     def depth_text(self, track, contig, first=0, count=None):
         """ASCII `"%d\\n"` lines of depth[first:first+count], formatted on the GPU."""
         if count is None:
@@ -371,6 +378,23 @@ class Context:
         self._check(self._lib.gci_depth_gzip(self._h, track, contig, first, count, header, len(header), _ptr(buf),
                                              n.value, C.byref(n)))
         return buf
+
+    def depth_gzip_into(self, track, contig, header, out, at=0, chunk=1 << 24):
+        """gzip members of one whole contig (header + depth lines) written into the caller's (pinned) uint8 buffer
+        `out` from offset `at`; -> bytes written"""
+        n = int(self.lengths[contig])
+        pos = at
+        k = _i64()
+        for first in range(0, max(n, 1), chunk):
+            cnt = min(chunk, n - first)
+            hdr = header if first == 0 else b""
+            self._check(self._lib.gci_depth_gzip(self._h, track, contig, first, cnt, hdr, len(hdr), None, 0, C.byref(k)))
+            if pos + k.value > out.size:
+                raise GciError(-2, f"depth_gzip_into: buffer too small ({out.size} < {pos + k.value})")
+            self._check(self._lib.gci_depth_gzip(self._h, track, contig, first, cnt, hdr, len(hdr),
+                                                 _p(out.ctypes.data + pos), out.size - pos, C.byref(k)))
+            pos += k.value
+        return pos - at
 
     # ---- scan / score ----
     def scan(self, track, lo=-1, hi=0, flank_len=15):

@@ -245,6 +245,38 @@ sum_kernel(const int32_t* __restrict__ depth, int64_t total, const int64_t* __re
   add_tile_sum(acc, tile, tile_off, n_contigs, sums, lane);
 }
 
+// order-independent 64-bit checksum per contig: sum over positions of (depth + 1) * splitmix64(position) mod 2^64
+// (parity gate at sizes where whole arrays do not travel; the oracle's orc_depth_hash is the same sum)
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(GCI_TILE_THREADS)
+depth_hash_kernel(const int32_t* __restrict__ depth, int64_t n_tiles, const int64_t* __restrict__ tile_off,
+                  const int64_t* __restrict__ len, int32_t n_contigs, unsigned long long* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tile = (int64_t)blockIdx.x * (GCI_TILE_THREADS / 32) + warp;
+  if (tile >= n_tiles) return;
+  const int64_t c = upper_bound_minus1<int64_t>(tile_off, (int64_t)n_contigs + 1, tile);
+  const int64_t p0 = (tile - tile_off[c]) * GCI_TILE, L = len[c];
+  unsigned long long h = 0;
+#pragma unroll
+  for (int it = 0; it < GCI_TILE / 128; it++) {
+    const int64_t p = p0 + it * 128 + lane * 4;
+    const int4 v = *reinterpret_cast<const int4*>(depth + tile * GCI_TILE + it * 128 + lane * 4);
+    const int d[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (p + k < L) h += (unsigned long long)((long long)d[k] + 1) * splitmix64((unsigned long long)(p + k));
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) h += __shfl_xor_sync(0xffffffffu, h, s);
+  if (lane == 0 && h) atomicAdd(out + c, h);
+}
+
 struct NRuns {
   const int32_t* contig;
   const int64_t* start;
@@ -555,6 +587,25 @@ int gci_depth_sums(gci_ctx* ctx, int32_t track, int64_t* sums) {
   t.sums_valid = true;
   }
   GCI_TRY(gci_d2h(ctx, sums, t.sums.p, sizeof(int64_t) * (size_t)ctx->n_contigs));
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return GCI_OK;
+}
+
+int gci_depth_hash(gci_ctx* ctx, int32_t track, uint64_t* out) {
+  if (!ctx || !out || track < 0 || track >= GCI_MAX_TRACKS) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  Track& t = ctx->track[track];
+  if (!t.allocated) return ctx->fail(GCI_E_ARG, "gci_depth_hash: track %d holds no depth", track);
+  DevBuf& d_out = ctx->misc;
+  GCI_TRY(ctx->ensure(d_out, 8 * (size_t)std::max(1, ctx->n_contigs)));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(d_out.p, 0, 8 * (size_t)std::max(1, ctx->n_contigs), ctx->stream));
+  if (ctx->n_tiles) {
+    depth_hash_kernel<<<(unsigned)((ctx->n_tiles + 7) / 8), GCI_TILE_THREADS, 0, ctx->stream>>>(
+        t.depth.as<int32_t>(), ctx->n_tiles, ctx->d_tile_off.as<int64_t>(), ctx->d_len.as<int64_t>(), ctx->n_contigs,
+        d_out.as<unsigned long long>());
+    GCI_LAUNCH_CHECK(ctx);
+  }
+  GCI_TRY(gci_d2h(ctx, out, d_out.p, 8 * (size_t)ctx->n_contigs));
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return GCI_OK;
 }

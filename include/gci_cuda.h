@@ -138,6 +138,10 @@ int gci_fetch_depth_narrow(gci_ctx* ctx, int32_t track, int32_t contig, void* ou
                            int32_t* overflow);
 /* sum of depth per contig (mean depth of GCI.py:862-868 = sum / length) */
 int gci_depth_sums(gci_ctx* ctx, int32_t track, int64_t* sums /* [n_contigs] */);
+/* order-independent 64-bit checksum of every contig's depth array: sum over positions p of
+   (depth[p] + 1) * splitmix64(p) mod 2^64 (0 for unselected contigs).  Lets a caller compare whole tracks with
+   another implementation of GCI.py:302-306 without moving them (3.1 Gbp = 12 GB) over PCIe. */
+int gci_depth_hash(gci_ctx* ctx, int32_t track, uint64_t* out /* [n_contigs] */);
 /* decimal text of one contig's depth, one value per line (GCI.py:115-117), produced on the GPU;
    call with out = NULL to get the byte count first */
 int gci_depth_text(gci_ctx* ctx, int32_t track, int32_t contig, int64_t first, int64_t count,

@@ -148,10 +148,9 @@ def name_rank(names):
     return rank
 
 
-def hot_path(bams, lengths, n_reads, selected=None, map_qual=30, mq_cutoff=50, iden_percent=0.9, clip_percent=0.1,
-             ovlp_percent=0.9, flank_len=15, threshold=0, threads=1, pafs=(), names=None):
-    """Whole hot path on the CPU: PAF election + BAM gates -> dedup -> join (PAFs first, GCI.py:272) -> depth ->
-    collapse.  Returns (depths, beds, n_survivors)."""
+def survivors(bams, lengths, n_reads, selected=None, map_qual=30, mq_cutoff=50, iden_percent=0.9, clip_percent=0.1,
+              ovlp_percent=0.9, threads=1, pafs=(), names=None):
+    """PAF election + BAM gates -> dedup -> join (PAFs first, GCI.py:272): per read (contig or -1, start, end)"""
     if selected is None:
         selected = np.ones(len(lengths), bool)
     tables, hq = [], np.zeros(n_reads, np.uint8)
@@ -165,8 +164,42 @@ def hot_path(bams, lengths, n_reads, selected=None, map_qual=30, mq_cutoff=50, i
         c, s, e, q, h = bam_leg(t, selected, n_reads, map_qual, mq_cutoff, iden_percent, clip_percent, threads)
         tables.append((c, s, e, q))
         hq |= h
-    sc, ss, se = join(tables, hq, ovlp_percent, threads)
+    return join(tables, hq, ovlp_percent, threads)
+
+
+def hot_path(bams, lengths, n_reads, selected=None, map_qual=30, mq_cutoff=50, iden_percent=0.9, clip_percent=0.1,
+             ovlp_percent=0.9, flank_len=15, threshold=0, threads=1, pafs=(), names=None):
+    """Whole hot path on the CPU: filter -> depth -> collapse.  Returns (depths, beds, n_survivors)."""
+    if selected is None:
+        selected = np.ones(len(lengths), bool)
+    sc, ss, se = survivors(bams, lengths, n_reads, selected, map_qual, mq_cutoff, iden_percent, clip_percent,
+                           ovlp_percent, threads, pafs, names)
     lens = [int(l) if selected[i] else 0 for i, l in enumerate(lengths)]
     depths = depth(sc, ss, se, lens, flank_len, threads)
     beds = [collapse(d, -1, threshold, flank_len, 0) for d in depths]
     return depths, beds, int((sc >= 0).sum())
+
+
+def hot_path_summary(bams, lengths, n_reads, selected=None, flank_len=15, threshold=0, threads=1, pafs=(), names=None,
+                     with_hash=True, **gates):
+    """The same path with one contig's depth array alive at a time (a 3.1 Gbp genome is 25 GB of int64 otherwise):
+    -> (beds, depth checksums (orc_depth_hash) or None, depth sums, n_survivors, seconds spent on the checksums)"""
+    import time
+    if selected is None:
+        selected = np.ones(len(lengths), bool)
+    sc, ss, se = survivors(bams, lengths, n_reads, selected, threads=threads, pafs=pafs, names=names, **gates)
+    order = np.argsort(sc, kind="stable")
+    bounds = np.searchsorted(sc[order], np.arange(len(lengths) + 1))
+    beds, hashes, sums, t_hash = [], [], [], 0.0
+    for c, L in enumerate(lengths):
+        if not selected[c]:
+            beds.append([]); hashes.append(0); sums.append(0)
+            continue
+        idx = order[bounds[c]:bounds[c + 1]]
+        d = depth(np.zeros(len(idx), np.int32), ss[idx], se[idx], [int(L)], flank_len, threads)[0]
+        beds.append(collapse(d, -1, threshold, flank_len, 0))
+        t0 = time.perf_counter()
+        hashes.append(depth_hash(d, threads) if with_hash else 0)
+        sums.append(int(d.sum()))
+        t_hash += time.perf_counter() - t0
+    return beds, (hashes if with_hash else None), sums, int((sc >= 0).sum()), t_hash
