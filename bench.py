@@ -291,10 +291,9 @@ def main():
     def e2e_step():
         upload()
         core_step()
-        gz = 0
-        for c in range(nct):                  # what write_depth() puts on disk (GCI.py:99-143), compressed on the GPU
-            gz += ctx.depth_gzip_into(0, c, headers[c], gz_out)
-        result["d2h_gz_bytes"] = gz
+        # what write_depth() puts on disk (GCI.py:99-143): text + DEFLATE + CRC-32 on the GPU, bytes into pinned memory
+        blob, _ = ctx.depth_gzip_track(0, headers, gz_out)
+        result["d2h_gz_bytes"] = int(blob.size)
         result["intervals"] = ctx.fetch_intervals(0, nct)
 
     def barrier():

@@ -73,6 +73,7 @@ _SIGNATURES = {
     "gci_depth_hash": (C.c_int, [_p, _i32, _p]),
     "gci_depth_text": (C.c_int, [_p, _i32, _i32, _i64, _i64, _p, _i64, C.POINTER(_i64)]),
     "gci_depth_gzip": (C.c_int, [_p, _i32, _i32, _i64, _i64, C.c_char_p, _i32, _p, _i64, C.POINTER(_i64)]),
+    "gci_depth_gzip_track": (C.c_int, [_p, _i32, C.c_char_p, _p, _p, _i64, C.POINTER(_i64), _p]),
     "gci_scan": (C.c_int, [_p, _i32, _i32, _i32, _i32, C.POINTER(_i64)]),
     "gci_scan_windows": (C.c_int, [_p, _i32, _i32, _i32, _i64, _p, _p, _p, C.POINTER(_i64)]),
     "gci_fetch_intervals": (C.c_int, [_p, _i32, _i64, _p, _p, _p, C.POINTER(_i64)]),
@@ -379,22 +380,22 @@ class Context:
                                              n.value, C.byref(n)))
         return buf
 
-    def depth_gzip_into(self, track, contig, header, out, at=0, chunk=1 << 24):
-        """gzip members of one whole contig (header + depth lines) written into the caller's (pinned) uint8 buffer
-        `out` from offset `at`; -> bytes written"""
-        n = int(self.lengths[contig])
-        pos = at
-        k = _i64()
-        for first in range(0, max(n, 1), chunk):
-            cnt = min(chunk, n - first)
-            hdr = header if first == 0 else b""
-            self._check(self._lib.gci_depth_gzip(self._h, track, contig, first, cnt, hdr, len(hdr), None, 0, C.byref(k)))
-            if pos + k.value > out.size:
-                raise GciError(-2, f"depth_gzip_into: buffer too small ({out.size} < {pos + k.value})")
-            self._check(self._lib.gci_depth_gzip(self._h, track, contig, first, cnt, hdr, len(hdr),
-                                                 _p(out.ctypes.data + pos), out.size - pos, C.byref(k)))
-            pos += k.value
-        return pos - at
+    def depth_gzip_track(self, track, headers, out=None):
+        """`.depth.gz` bytes of every selected contig of the track in one pass: headers[c] (bytes, e.g. b">chr1\n")
+        then the contig's depth lines, as gzip members in contig order.  out: optional (pinned) uint8 buffer.
+        -> (uint8 view of the bytes, byte offset of every contig [n_contigs + 1])"""
+        assert len(headers) == self.n_contigs
+        blob = b"".join(headers)
+        off = np.zeros(self.n_contigs + 1, np.int64)
+        off[1:] = np.cumsum([len(h) for h in headers])
+        cb = np.zeros(self.n_contigs + 1, np.int64)
+        n = _i64()
+        if out is None:
+            self._check(self._lib.gci_depth_gzip_track(self._h, track, blob, _ptr(off), None, 0, C.byref(n), None))
+            out = np.empty(max(1, n.value), np.uint8)
+        rc = self._lib.gci_depth_gzip_track(self._h, track, blob, _ptr(off), _ptr(out), out.size, C.byref(n), _ptr(cb))
+        self._check(rc)
+        return out[:n.value], cb
 
     # ---- scan / score ----
     def scan(self, track, lo=-1, hi=0, flank_len=15):

@@ -164,10 +164,12 @@ struct gci_ctx {
   DevBuf tmp[10];                   // small per-call scratch (score terms, fetches)
   Track track[GCI_MAX_TRACKS];
 
-  // gci_depth_gzip: packed members of the last size query, kept until they are fetched
+  // gci_depth_gzip: packed members of the last size query, kept until they are fetched; the encoder's own scratch
+  // (gzip.cu: CRC / power tables, range descriptors, run-start bitmask, run list, member sizes and offsets)
   bool gz_valid = false;
   unsigned long long gz_key = 0;
   int64_t gz_total = 0;
+  DevBuf gz_tables, gz_seg, gz_hdr, gz_bits, gz_tile_cnt, gz_tile_run, gz_run_pos, gz_run_val, gz_msize, gz_moff, gz_packed;
 
   // NCCL communicator of a multi-GPU run (comm.cu; resolved with dlopen)
   void* nccl_comm = nullptr;

@@ -30,7 +30,6 @@ from . import io as gio
 from ._lib import Context, NO_FLAGS, TRACK_HIFI, TRACK_NANO, TRACK_MERGED
 from .records import AlnTable, PafTable
 
-TEXT_CHUNK = 1 << 24      # positions per gci_depth_text call
 
 
 # ------------------------------------------------------------------------------------------------
@@ -154,21 +153,25 @@ def _adopt(depths, session=None, track=TRACK_HIFI) -> DeviceDepths:
 # ------------------------------------------------------------------------------------------------
 def write_depth(directory='.', prefix='GCI', depths={}, threads=1):
     """GCI.py:99-143: `>name` then one decimal per line, gzip (multi-member like the reference's).
-    Text formatting and DEFLATE both run on the GPU (gci_depth_gzip); only compressed bytes reach the host."""
+    Text formatting, DEFLATE and CRC-32 all run on the GPU (gci_depth_gzip_track: one pass over the track); only
+    compressed bytes reach the host."""
     depths = _adopt(depths)
-    ctx = depths.session.ctx
-    idx = depths.session.index
+    session, ctx = depths.session, depths.session.ctx
+    idx = session.index
+    heads = {target: f'>{target}\n'.encode('utf-8') for target in depths.keys()}
     with open(f'{directory}/{prefix}.depth.gz', 'wb') as f:
-        for target in depths.keys():
+        if list(depths.keys()) == session.selected_names() and all(len(h) <= 4096 for h in heads.values()):
+            blob, _ = ctx.depth_gzip_track(depths.track, [heads.get(n, b'') for n in session.names])
+            f.write(blob.tobytes())
+            return
+        for target in depths.keys():         # another contig order than the session's (or an over-long name)
             c = idx[target]
-            n = int(depths.session.lengths[c])
-            head = f'>{target}\n'.encode('utf-8')
-            if n == 0 or len(head) > 400:
+            n = int(session.lengths[c])
+            head = heads[target]
+            if len(head) > 4096:
                 f.write(gio._gzip_member(head, 6))
                 head = b''
-            for first in range(0, n, TEXT_CHUNK):
-                f.write(ctx.depth_gzip(depths.track, c, first, min(TEXT_CHUNK, n - first),
-                                       head if first == 0 else b'').tobytes())
+            f.write(ctx.depth_gzip(depths.track, c, 0, n, head).tobytes())
 
 
 # ------------------------------------------------------------------------------------------------

@@ -147,11 +147,18 @@ int gci_depth_hash(gci_ctx* ctx, int32_t track, uint64_t* out /* [n_contigs] */)
 int gci_depth_text(gci_ctx* ctx, int32_t track, int32_t contig, int64_t first, int64_t count,
                    char* out, int64_t cap, int64_t* n_bytes);
 
-/* the same text already compressed on the GPU: a sequence of complete gzip members (one per 8192 positions;
+/* the same text already compressed on the GPU (run-based encoder, gzip.cu): a sequence of complete gzip members (one per 8192 positions;
    the reference also writes a multi-member file, GCI.py:134-143) of `header` (e.g. ">name\n", may be empty)
    followed by the depth lines of [first, first+count).  Call with out = NULL to get the byte count. */
 int gci_depth_gzip(gci_ctx* ctx, int32_t track, int32_t contig, int64_t first, int64_t count, const char* header,
                    int32_t header_len, char* out, int64_t cap, int64_t* n_bytes);
+
+/* the whole track in one pass (what write_depth() puts on disk, GCI.py:99-143): for every selected contig c, in
+   contig order, the gzip members of header c (bytes [header_off[c], header_off[c+1]) of `headers`, e.g. ">name\n")
+   followed by its depth lines.  contig_bytes[n_contigs+1] (optional) = byte offset of every contig's first member.
+   out == NULL: only the sizes.  A cap smaller than *n_bytes is an error (nothing is copied). */
+int gci_depth_gzip_track(gci_ctx* ctx, int32_t track, const char* headers, const int64_t* header_off /* [n_contigs+1] */,
+                         char* out, int64_t cap, int64_t* n_bytes, int64_t* contig_bytes);
 
 /* ---- gap scan ----------------------------------------------------------------------------- */
 /* collapse_depth_range(depths, lo, hi, flank_len, 0) over every selected contig (GCI.py:356-390) */

@@ -301,6 +301,41 @@ def test_gpu_gzip_members_decompress_to_reference_text(ctx):
     assert gzip.decompress(ctx.depth_gzip(0, 1, 0, 0, header=b">x\n").tobytes()) == b">x\n"
 
 
+def test_gpu_gzip_whole_track_one_pass(ctx):
+    """gci_depth_gzip_track: every selected contig in one pass (headers + members in contig order), per-contig byte
+    offsets, an unselected contig in the middle, a zero-length contig, depth from the real pipeline."""
+    import gzip
+    lengths = [100_000, 40_000, 0, 8192, 8193, 30_000]
+    sel = [True, False, True, True, True, True]
+    d = synth.make_reads(synth.SynthSpec([100_000], coverage=25, seed=4, read_mean=6000, read_min=800, read_max=15000,
+                                         hole_fraction=0.05))
+    ctx.set_contigs(lengths, sel)
+    ctx.reads_begin(d.n_reads)
+    ctx.upload_bam(d.bam)
+    ctx.filter()
+    ctx.depth(0, 15, -1, 0)
+    rng = np.random.default_rng(8)
+    extra = {3: np.repeat(rng.integers(0, 3, 90), 100)[:8192].astype(np.int32),
+             4: np.full(8193, 41, np.int32),
+             5: np.repeat(rng.integers(-3, 2000, 300), 100).astype(np.int32)}
+    for c, v in extra.items():
+        ctx.load_depth(0, c, v)
+    headers = [f">ctg{c} len={l}\n".encode() for c, l in enumerate(lengths)]
+    blob, off = ctx.depth_gzip_track(0, headers)
+    assert off[0] == 0 and off[-1] == len(blob) and off[1] == off[2]            # contig 1 is not selected
+    depth0 = ctx.fetch_depth(0, 0)
+    want = {0: depth0, 2: np.zeros(0, np.int32), **extra}
+    whole = b""
+    for c in (0, 2, 3, 4, 5):
+        text = headers[c] + b"".join(b"%d\n" % int(v) for v in want[c])
+        assert gzip.decompress(blob[off[c]:off[c + 1]].tobytes()) == text, c
+        whole += text
+    assert gzip.decompress(blob.tobytes()) == whole
+    assert len(blob) < len(whole) / 15
+    # the per-contig entry point produces the same members
+    assert ctx.depth_gzip(0, 0, header=headers[0]).tobytes() == blob[off[0]:off[1]].tobytes()
+
+
 @pytest.mark.parametrize("seed", range(3))
 def test_contig_sharded_two_ranks_equal_single_gpu(seed):
     """multi-file read set split over two 'ranks' by contig (two contexts on one GPU): the exchanged-table
