@@ -193,10 +193,7 @@ void gci_destroy(gci_ctx* ctx) {
   for (auto& p : ctx->paf)
     for (DevBuf* d : {&p.read_id, &p.qlen, &p.qstart, &p.qend, &p.ref_id, &p.tstart, &p.tend, &p.nmatch, &p.alnlen, &p.mapq})
       ctx->release(*d);
-  {
-    PafKept& k = ctx->paf_kept;
-    for (DevBuf* d : {&k.read, &k.ref, &k.qlen, &k.q0, &k.q1, &k.t0, &k.t1, &k.ident, &k.ord, &k.count}) ctx->release(*d);
-  }
+  ctx->release(ctx->paf_keep);
   ctx->release(ctx->d_name_rank);
   for (auto& t : ctx->track) free_track(ctx, t);
   for (DevBuf* d : {&ctx->d_len, &ctx->d_selected, &ctx->d_tile_off, &ctx->d_owner_of, &ctx->d_nr_contig, &ctx->d_nr_start,
@@ -375,7 +372,6 @@ int gci_reads_begin(gci_ctx* ctx, uint32_t n_reads) {
   ctx->n_bam = 0;                 // device buffers of the pools are kept and reused
   ctx->n_files = 0;
   ctx->n_paf = 0;
-  ctx->paf_kept.lines_seen = 0;
   ctx->n_reads = n_reads;
   ctx->filtered = false;
   ctx->n_survivors = 0;

@@ -66,14 +66,6 @@ struct PafFile {
   DevBuf read_id, qlen, qstart, qend, ref_id, tstart, tend, nmatch, alnlen, mapq;
 };
 
-// lines of all PAF files of the read set that passed the per-line gate, in arrival order (the reference's
-// `synteny` dict is created once per filter() call and therefore accumulates across PAF files, GCI.py:214)
-struct PafKept {
-  int64_t cap = 0;        // capacity in lines
-  int64_t lines_seen = 0; // host-side upper bound of the kept count
-  DevBuf read, ref, qlen, q0, q1, t0, t1, ident, ord, count;   // count: device cursor (u64)
-};
-
 // one file after its per-file leg: at most one entry per read
 struct FileTable {
   int kind = 0;            // 0 = BAM (entries are records of bam[src]), 1 = table (own columns)
@@ -144,7 +136,7 @@ struct gci_ctx {
   size_t n_bam = 0;
   std::vector<PafFile> paf;
   size_t n_paf = 0;
-  PafKept paf_kept;
+  DevBuf paf_keep;                  // uint8 per PAF line (all files of the read set): passed the per-line gate
   DevBuf d_name_rank;
   std::vector<FileTable> files;     // join order
   size_t n_files = 0;

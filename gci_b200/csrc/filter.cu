@@ -840,66 +840,75 @@ static int install_table(gci_ctx* ctx, FileTable& f, int64_t n, const uint32_t* 
 // ================================================================================================
 // K3  PAF leg on the GPU (GCI.py:211-254)
 // ================================================================================================
-// per line: contig selected, identity = nmatch / alnlen (fp64), keep iff mapq >= -mq and identity >= -ip;
-// kept lines are appended to the read set's cumulative list with their arrival ordinal
+// Lines of all PAF files of the read set share one index space (global line id = lines of the earlier files + line
+// number), which is also their arrival order.  Per line: contig selected, identity = nmatch / alnlen (fp64), keep iff
+// mapq >= -mq and identity >= -ip.  Nothing is compacted: the kept lines are grouped by read as a CSR over line ids
+// (count -> scan -> fill) and the election reads the original columns.  A read with ONE kept line (almost all of
+// them) is its own result; the others are elected like the reference does.  The reference's `synteny` dict is
+// created once per filter() call (:214), so the table of PAF file f is elected over the lines of files 0..f.
 struct PafCols {
   const uint32_t* read_id;
   const int32_t *qlen, *qstart, *qend, *ref_id, *tstart, *tend, *nmatch, *alnlen, *mapq;
 };
-struct KeptCols {
-  uint32_t* read;
-  int32_t *ref, *qlen, *q0, *q1, *t0, *t1;
-  double* ident;
-  unsigned long long* ord;
-  unsigned long long* count;
+struct PafSet {
+  PafCols f[GCI_MAX_FILES];
+  int64_t off[GCI_MAX_FILES + 1];     // first global line id of every file
+  int n;
 };
+struct PafLine { int32_t ref, qlen, q0, q1, t0, t1; double ident; };
 
-__global__ void paf_gate_kernel(int64_t n, PafCols p, unsigned long long ord0, const uint8_t* __restrict__ selected,
+__device__ __forceinline__ PafLine paf_line(const PafSet& ps, int32_t g) {
+  int k = 0;
+  while (k + 1 < ps.n && (int64_t)g >= ps.off[k + 1]) k++;
+  const int64_t i = (int64_t)g - ps.off[k];
+  const PafCols& p = ps.f[k];
+  PafLine l;
+  l.ref = p.ref_id[i]; l.qlen = p.qlen[i]; l.q0 = p.qstart[i]; l.q1 = p.qend[i]; l.t0 = p.tstart[i]; l.t1 = p.tend[i];
+  l.ident = (double)p.nmatch[i] / (double)p.alnlen[i];                 // :231 (kept lines have alnlen != 0)
+  return l;
+}
+
+__global__ void paf_mark_kernel(int64_t n, PafCols p, int64_t line0, const uint8_t* __restrict__ selected,
                                 int32_t n_contigs, uint32_t n_reads, int32_t map_qual, int32_t mq_cutoff, double ip,
-                                KeptCols k, uint8_t* __restrict__ highq, unsigned long long* __restrict__ err) {
+                                uint8_t* __restrict__ keep, int32_t* __restrict__ cnt, uint8_t* __restrict__ highq,
+                                unsigned long long* __restrict__ err) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
+  uint8_t k = 0;
   const int32_t t = p.ref_id[i];
-  if (t < 0 || t >= n_contigs || !selected[t]) return;                 // :220
-  const int32_t al = p.alnlen[i];
-  if (al == 0) {                                                        // ZeroDivisionError :231
-    atomicOr(err, 16ull);
-    atomicMin(err + 1, (unsigned long long)i);
-    return;
-  }
-  const double ident = (double)p.nmatch[i] / (double)al;               // :231
-  const int32_t mq = p.mapq[i];
-  if (!(mq >= map_qual && ident >= ip)) return;                         // :232
+  const int32_t al = p.alnlen[i], nm = p.nmatch[i], mq = p.mapq[i];
   const uint32_t q = p.read_id[i];
-  if (q >= n_reads) return;
-  const unsigned long long slot = atomicAdd(k.count, 1ull);
-  k.read[slot] = q; k.ref[slot] = t; k.qlen[slot] = p.qlen[i];
-  k.q0[slot] = p.qstart[i]; k.q1[slot] = p.qend[i]; k.t0[slot] = p.tstart[i]; k.t1[slot] = p.tend[i];
-  k.ident[slot] = ident;
-  k.ord[slot] = ord0 + (unsigned long long)i;
-  if (mq >= mq_cutoff) highq[q] = 1;                                    // :238
+  if (t >= 0 && t < n_contigs && selected[t]) {                         // :220
+    if (al == 0) {                                                      // ZeroDivisionError :231
+      atomicOr(err, 16ull);
+      atomicMin(err + 1, (unsigned long long)i);
+    } else {
+      const double ident = (double)nm / (double)al;                    // :231
+      if (mq >= map_qual && ident >= ip && q < n_reads) {               // :232
+        k = 1;
+        atomicAdd(&cnt[q], 1);
+        if (mq >= mq_cutoff) highq[q] = 1;                              // :238
+      }
+    }
+  }
+  keep[line0 + i] = k;
 }
 
-__global__ void paf_count_kernel(const unsigned long long* __restrict__ count, const uint32_t* __restrict__ read,
-                                 int32_t* __restrict__ cnt) {
-  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  if (i < *count) atomicAdd(&cnt[read[i]], 1);
-}
-
-__global__ void paf_fill_kernel(const unsigned long long* __restrict__ count, const uint32_t* __restrict__ read,
-                                const int32_t* __restrict__ off, int32_t* __restrict__ cur, int32_t* __restrict__ idx) {
-  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  if (i >= *count) return;
-  const uint32_t q = read[i];
-  idx[off[q] + atomicAdd(&cur[q], 1)] = (int32_t)i;
+__global__ void paf_fill_kernel(int64_t n, const uint32_t* __restrict__ read_id, int64_t line0,
+                                const uint8_t* __restrict__ keep, const int32_t* __restrict__ off,
+                                int32_t* __restrict__ cur, int32_t* __restrict__ idx) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n || !keep[line0 + i]) return;
+  const uint32_t q = read_id[i];
+  idx[off[q] + atomicAdd(&cur[q], 1)] = (int32_t)(line0 + i);
 }
 
 // GCI.py:64-96 over the members `seg[0..g)` that sit on contig `ref`: walk the (lo, hi) pairs in sorted
 // order by repeated selection of the next smallest (lo, hi, position) triple (groups are tiny), merge
 // touching / overlapping blocks, return the total merged length and the longest block (first on ties).
 struct Blocks { long long total; int32_t lo, hi; };
-__device__ Blocks merged_blocks(const int32_t* __restrict__ seg, int g, const int32_t* __restrict__ kref, int32_t ref,
-                                const int32_t* __restrict__ a, const int32_t* __restrict__ b) {
+template <bool TARGET>
+__device__ Blocks merged_blocks(const PafSet& ps, const int32_t* __restrict__ seg, int g, int32_t ref) {
   Blocks r{0, 0, 0};
   long long best_len = -1;
   bool have_cur = false, have_last = false;
@@ -910,9 +919,9 @@ __device__ Blocks merged_blocks(const int32_t* __restrict__ seg, int g, const in
     int pick = -1;
     int32_t p_lo = 0, p_hi = 0;
     for (int j = 0; j < g; j++) {
-      const int32_t e = seg[j];
-      if (kref[e] != ref) continue;
-      const int32_t lo = a[e], hi = b[e];
+      const PafLine l = paf_line(ps, seg[j]);
+      if (l.ref != ref) continue;
+      const int32_t lo = TARGET ? l.t0 : l.q0, hi = TARGET ? l.t1 : l.q1;
       if (have_last) {
         const bool after = lo > last_lo || (lo == last_lo && (hi > last_hi || (hi == last_hi && j > last_pos)));
         if (!after) continue;
@@ -939,9 +948,9 @@ __device__ Blocks merged_blocks(const int32_t* __restrict__ seg, int g, const in
   return r;
 }
 
-// one thread per read: order its kept lines by arrival, score every contig, keep the primary target
-__global__ void paf_elect_kernel(uint32_t n_reads, const int32_t* __restrict__ off, int32_t* __restrict__ idx,
-                                 KeptCols k, const int32_t* __restrict__ name_rank, int32_t* __restrict__ t_ref,
+// one thread per read: a single kept line is the result; more lines are ordered by arrival and every contig scored
+__global__ void paf_elect_kernel(uint32_t n_reads, PafSet ps, const int32_t* __restrict__ off, int32_t* __restrict__ idx,
+                                 const int32_t* __restrict__ name_rank, int32_t* __restrict__ t_ref,
                                  int32_t* __restrict__ t_start, int32_t* __restrict__ t_end, int32_t* __restrict__ t_qlen,
                                  long long* __restrict__ win, unsigned long long* __restrict__ err) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -949,34 +958,48 @@ __global__ void paf_elect_kernel(uint32_t n_reads, const int32_t* __restrict__ o
   const int32_t a0 = off[r], g = off[r + 1] - a0;
   if (g == 0) { win[r] = -1; return; }
   int32_t* seg = idx + a0;
-  for (int i = 1; i < g; i++) {            // insertion sort by arrival ordinal (file order, :237)
+  if (g == 1) {
+    const PafLine l = paf_line(ps, seg[0]);
+    if (l.qlen == 0) {                       // ZeroDivisionError :247
+      atomicOr(err, 32ull);
+      atomicMin(err + 1, (unsigned long long)r);
+      win[r] = -1;
+      return;
+    }
+    t_ref[r] = l.ref; t_start[r] = l.t0; t_end[r] = l.t1; t_qlen[r] = l.qlen;
+    win[r] = (long long)r;
+    return;
+  }
+  for (int i = 1; i < g; i++) {              // insertion sort by line id = arrival order (file order, :237)
     const int32_t e = seg[i];
-    const unsigned long long o = k.ord[e];
     int j = i - 1;
-    while (j >= 0 && k.ord[seg[j]] > o) { seg[j + 1] = seg[j]; j--; }
+    while (j >= 0 && seg[j] > e) { seg[j + 1] = seg[j]; j--; }
     seg[j + 1] = e;
   }
   bool have = false;
   double best_score = 0;
   int32_t best_rank = 0, b_ref = 0, b_s = 0, b_e = 0, b_q = 0;
   for (int i = 0; i < g; i++) {
-    const int32_t ref = k.ref[seg[i]];
+    const PafLine li = paf_line(ps, seg[i]);
+    const int32_t ref = li.ref;
     bool seen = false;
-    for (int j = 0; j < i && !seen; j++) seen = k.ref[seg[j]] == ref;
+    for (int j = 0; j < i && !seen; j++) seen = paf_line(ps, seg[j]).ref == ref;
     if (seen) continue;
     double sum = 0;                          // Python sum() starts from int 0; 0 + x is exact
     int cnt = 0;
-    for (int j = i; j < g; j++)
-      if (k.ref[seg[j]] == ref) { sum = sum + k.ident[seg[j]]; cnt++; }
-    const int32_t qlen = k.qlen[seg[i]];     // alns[0][0], :246
+    for (int j = i; j < g; j++) {
+      const PafLine lj = paf_line(ps, seg[j]);
+      if (lj.ref == ref) { sum = sum + lj.ident; cnt++; }
+    }
+    const int32_t qlen = li.qlen;            // alns[0][0], :246
     if (qlen == 0) {                         // ZeroDivisionError :247
       atomicOr(err, 32ull);
       atomicMin(err + 1, (unsigned long long)r);
       win[r] = -1;
       return;
     }
-    const Blocks bq = merged_blocks(seg, g, k.ref, ref, k.q0, k.q1);
-    const Blocks bt = merged_blocks(seg, g, k.ref, ref, k.t0, k.t1);
+    const Blocks bq = merged_blocks<false>(ps, seg, g, ref);
+    const Blocks bt = merged_blocks<true>(ps, seg, g, ref);
     const double rate = (double)bq.total / (double)qlen;               // :247
     const double score = (sum / (double)cnt) * rate;                   // :248-249
     const int32_t rank = name_rank[ref];
@@ -991,59 +1014,56 @@ __global__ void paf_elect_kernel(uint32_t n_reads, const int32_t* __restrict__ o
 }
 
 int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
-  PafKept& kp = ctx->paf_kept;
   bool any = false;
   for (size_t fi = 0; fi < ctx->n_files; fi++) any |= ctx->files[fi].paf >= 0;
   if (!any) return GCI_OK;
   if ((int32_t)ctx->name_rank.size() != ctx->n_contigs)
     return ctx->fail(GCI_E_ARG, "gci_set_name_rank must be called before filtering PAF files");
-  int64_t total_lines = 0;
-  for (size_t i = 0; i < ctx->n_paf; i++) total_lines += ctx->paf[i].n;
-  const size_t cap = (size_t)std::max<int64_t>(1, total_lines);
-  GCI_TRY(ctx->ensure(kp.read, 4 * cap)); GCI_TRY(ctx->ensure(kp.ref, 4 * cap)); GCI_TRY(ctx->ensure(kp.qlen, 4 * cap));
-  GCI_TRY(ctx->ensure(kp.q0, 4 * cap)); GCI_TRY(ctx->ensure(kp.q1, 4 * cap)); GCI_TRY(ctx->ensure(kp.t0, 4 * cap));
-  GCI_TRY(ctx->ensure(kp.t1, 4 * cap)); GCI_TRY(ctx->ensure(kp.ident, 8 * cap)); GCI_TRY(ctx->ensure(kp.ord, 8 * cap));
-  GCI_TRY(ctx->ensure(kp.count, 8));
-  GCI_CUDA_TRY(ctx, cudaMemsetAsync(kp.count.p, 0, 8, ctx->stream));
-  KeptCols k{kp.read.as<uint32_t>(), kp.ref.as<int32_t>(), kp.qlen.as<int32_t>(), kp.q0.as<int32_t>(),
-             kp.q1.as<int32_t>(), kp.t0.as<int32_t>(), kp.t1.as<int32_t>(), kp.ident.as<double>(),
-             kp.ord.as<unsigned long long>(), kp.count.as<unsigned long long>()};
-  const size_t nr = std::max<uint32_t>(1, ctx->n_reads);
-  DevBuf &cnt = ctx->tmp[6], &off = ctx->tmp[7], &idx = ctx->tmp[8];
-  GCI_TRY(ctx->ensure(cnt, 4 * (nr + 1) * 2));     // counts | fill cursors
-  GCI_TRY(ctx->ensure(off, 4 * (nr + 1)));
-  GCI_TRY(ctx->ensure(idx, 4 * cap));
-  ctx->stage_begin(GCI_ST_PAF);
-  unsigned long long ord0 = 0;
-  int64_t seen = 0;
+  PafSet ps;
+  memset(&ps, 0, sizeof ps);
+  std::vector<int> file_of;                  // FileTable index of PAF file k (join order)
   for (size_t fi = 0; fi < ctx->n_files; fi++) {
     FileTable& ft = ctx->files[fi];
     if (ft.paf < 0) continue;
     const PafFile& pf = ctx->paf[ft.paf];
-    PafCols pc{pf.read_id.as<uint32_t>(), pf.qlen.as<int32_t>(), pf.qstart.as<int32_t>(), pf.qend.as<int32_t>(),
-               pf.ref_id.as<int32_t>(), pf.tstart.as<int32_t>(), pf.tend.as<int32_t>(), pf.nmatch.as<int32_t>(),
-               pf.alnlen.as<int32_t>(), pf.mapq.as<int32_t>()};
-    if (pf.n) {
-      paf_gate_kernel<<<(unsigned)((pf.n + 255) / 256), 256, 0, ctx->stream>>>(
-          pf.n, pc, ord0, ctx->d_selected.as<uint8_t>(), ctx->n_contigs, ctx->n_reads, mq, mq_cutoff, ip, k,
-          ctx->highq.as<uint8_t>(), ctx->d_err.as<unsigned long long>());
+    const int k = ps.n++;
+    ps.f[k] = PafCols{pf.read_id.as<uint32_t>(), pf.qlen.as<int32_t>(), pf.qstart.as<int32_t>(), pf.qend.as<int32_t>(),
+                      pf.ref_id.as<int32_t>(), pf.tstart.as<int32_t>(), pf.tend.as<int32_t>(), pf.nmatch.as<int32_t>(),
+                      pf.alnlen.as<int32_t>(), pf.mapq.as<int32_t>()};
+    ps.off[k + 1] = ps.off[k] + pf.n;
+    file_of.push_back((int)fi);
+  }
+  const int64_t total_lines = ps.off[ps.n];
+  if (total_lines >= (int64_t(1) << 31)) return ctx->fail(GCI_E_ARG, "more than 2^31 PAF lines in one read set");
+  const size_t cap = (size_t)std::max<int64_t>(1, total_lines);
+  const size_t nr = std::max<uint32_t>(1, ctx->n_reads);
+  DevBuf &cnt = ctx->tmp[6], &off = ctx->tmp[7], &idx = ctx->tmp[8], &keep = ctx->paf_keep;
+  GCI_TRY(ctx->ensure(cnt, 4 * (nr + 1) * 2));     // counts | fill cursors
+  GCI_TRY(ctx->ensure(off, 4 * (nr + 1)));
+  GCI_TRY(ctx->ensure(idx, 4 * cap));
+  GCI_TRY(ctx->ensure(keep, cap));
+  int32_t* d_cnt = cnt.as<int32_t>();
+  int32_t* d_cur = d_cnt + (nr + 1);
+  ctx->stage_begin(GCI_ST_PAF);
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, 4 * (nr + 1), ctx->stream));
+  for (int k = 0; k < ps.n; k++) {
+    FileTable& ft = ctx->files[file_of[k]];
+    const int64_t n = ps.off[k + 1] - ps.off[k];
+    if (n) {
+      paf_mark_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+          n, ps.f[k], ps.off[k], ctx->d_selected.as<uint8_t>(), ctx->n_contigs, ctx->n_reads, mq, mq_cutoff, ip,
+          keep.as<uint8_t>(), d_cnt, ctx->highq.as<uint8_t>(), ctx->d_err.as<unsigned long long>());
       GCI_LAUNCH_CHECK(ctx);
     }
-    ord0 += (unsigned long long)pf.n;
-    seen += pf.n;
-    // group the kept lines (of this and all earlier PAF files) by read: CSR over read ids
-    GCI_CUDA_TRY(ctx, cudaMemsetAsync(cnt.p, 0, 4 * (nr + 1) * 2, ctx->stream));
-    int32_t* d_cnt = cnt.as<int32_t>();
-    int32_t* d_cur = d_cnt + (nr + 1);
-    if (seen) {
-      const unsigned grid = (unsigned)((seen + 255) / 256);
-      paf_count_kernel<<<grid, 256, 0, ctx->stream>>>(k.count, k.read, d_cnt);
+    // group the kept lines of files 0..k by read: CSR over read ids (the counts accumulate across the files)
+    GCI_TRY(gci_exclusive_scan_i32(ctx, d_cnt, off.as<int32_t>(), (int64_t)ctx->n_reads + 1));
+    GCI_CUDA_TRY(ctx, cudaMemsetAsync(d_cur, 0, 4 * (nr + 1), ctx->stream));
+    for (int j = 0; j <= k; j++) {
+      const int64_t nj = ps.off[j + 1] - ps.off[j];
+      if (!nj) continue;
+      paf_fill_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, ctx->stream>>>(
+          nj, ps.f[j].read_id, ps.off[j], keep.as<uint8_t>(), off.as<int32_t>(), d_cur, idx.as<int32_t>());
       GCI_LAUNCH_CHECK(ctx);
-      GCI_TRY(gci_exclusive_scan_i32(ctx, d_cnt, off.as<int32_t>(), (int64_t)ctx->n_reads + 1));
-      paf_fill_kernel<<<grid, 256, 0, ctx->stream>>>(k.count, k.read, off.as<int32_t>(), d_cur, idx.as<int32_t>());
-      GCI_LAUNCH_CHECK(ctx);
-    } else {
-      GCI_CUDA_TRY(ctx, cudaMemsetAsync(off.p, 0, 4 * (nr + 1), ctx->stream));
     }
     // the file's table: one entry per read id
     ft.kind = 1;
@@ -1052,8 +1072,10 @@ int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
     GCI_TRY(ctx->ensure(ft.end, 4 * nr)); GCI_TRY(ctx->ensure(ft.qlen, 4 * nr));
     GCI_TRY(ctx->ensure(ft.win, 8 * nr));
     if (ctx->n_reads) {
+      PafSet upto = ps;
+      upto.n = k + 1;
       paf_elect_kernel<<<(ctx->n_reads + 127) / 128, 128, 0, ctx->stream>>>(
-          ctx->n_reads, off.as<int32_t>(), idx.as<int32_t>(), k, ctx->d_name_rank.as<int32_t>(),
+          ctx->n_reads, upto, off.as<int32_t>(), idx.as<int32_t>(), ctx->d_name_rank.as<int32_t>(),
           ft.ref_id.as<int32_t>(), ft.start.as<int32_t>(), ft.end.as<int32_t>(), ft.qlen.as<int32_t>(),
           ft.win.as<long long>(), ctx->d_err.as<unsigned long long>());
       GCI_LAUNCH_CHECK(ctx);

@@ -397,43 +397,51 @@ runs_kernel(const uint32_t* __restrict__ flags, const int32_t* __restrict__ chun
   }
 }
 
-// one block: exclusive scan of the (starts, ends) chunk counts, totals, and the per-owner interval offsets
+// one block: exclusive scan of the (starts, ends) chunk counts, totals, and the per-owner interval offsets.
+// Every thread owns a contiguous strip of chunks: strip sums -> one block-wide scan of the 1024 strip totals ->
+// strip-serial write (two passes over an L2-resident array instead of one block barrier per 1024 chunks).
 __global__ void __launch_bounds__(1024)
 runs_scan_kernel(const int2* __restrict__ cnt, int64_t n_chunks, longlong2* __restrict__ off, int64_t n_owners,
                  const int64_t* __restrict__ chunk_off, int64_t* __restrict__ owner_off /* [n_owners+1 | total_s | total_e] */) {
   __shared__ long long s_ws[32], s_we[32];
-  __shared__ long long s_cs, s_ce;
+  __shared__ long long s_ts, s_te;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { s_cs = 0; s_ce = 0; }
-  __syncthreads();
-  for (int64_t base = 0; base < n_chunks; base += 1024) {
-    const int64_t i = base + threadIdx.x;
-    const int2 v = i < n_chunks ? cnt[i] : make_int2(0, 0);
-    long long is = v.x, ie = v.y;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const long long a = __shfl_up_sync(0xffffffffu, is, d), b = __shfl_up_sync(0xffffffffu, ie, d);
-      if (lane >= d) { is += a; ie += b; }
-    }
-    if (lane == 31) { s_ws[w] = is; s_we[w] = ie; }
-    __syncthreads();
-    long long os = 0, oe = 0, ts = 0, te = 0;
-    for (int j = 0; j < 32; j++) {
-      const long long a = s_ws[j], b = s_we[j];
-      if (j < w) { os += a; oe += b; }
-      ts += a; te += b;
-    }
-    const long long cs = s_cs, ce = s_ce;
-    if (i < n_chunks) off[i] = make_longlong2(cs + os + is - v.x, ce + oe + ie - v.y);
-    __syncthreads();
-    if (threadIdx.x == 0) { s_cs = cs + ts; s_ce = ce + te; }
-    __syncthreads();
+  const int64_t strip = (n_chunks + 1023) / 1024;
+  const int64_t i0 = min(n_chunks, (int64_t)threadIdx.x * strip), i1 = min(n_chunks, i0 + strip);
+  long long ss = 0, se = 0;
+  for (int64_t i = i0; i < i1; i++) {
+    const int2 v = cnt[i];
+    ss += v.x;
+    se += v.y;
   }
+  long long is = ss, ie = se;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const long long a = __shfl_up_sync(0xffffffffu, is, d), b = __shfl_up_sync(0xffffffffu, ie, d);
+    if (lane >= d) { is += a; ie += b; }
+  }
+  if (lane == 31) { s_ws[w] = is; s_we[w] = ie; }
+  __syncthreads();
+  long long os = 0, oe = 0, ts = 0, te = 0;
+  for (int j = 0; j < 32; j++) {
+    const long long a = s_ws[j], b = s_we[j];
+    if (j < w) { os += a; oe += b; }
+    ts += a; te += b;
+  }
+  long long rs = os + is - ss, re = oe + ie - se;          // exclusive prefix of my strip
+  for (int64_t i = i0; i < i1; i++) {
+    const int2 v = cnt[i];
+    off[i] = make_longlong2(rs, re);
+    rs += v.x;
+    re += v.y;
+  }
+  if (threadIdx.x == 0) { s_ts = ts; s_te = te; }
+  __syncthreads();                                          // off[] of the whole block is written (same block reads it)
   for (int64_t o = threadIdx.x; o <= n_owners; o += 1024) {
     const int64_t ch = chunk_off[o];
-    owner_off[o] = (o == n_owners || ch >= n_chunks) ? s_cs : off[ch].x;
+    owner_off[o] = (o == n_owners || ch >= n_chunks) ? s_ts : off[ch].x;
   }
-  if (threadIdx.x == 0) { owner_off[n_owners + 1] = s_cs; owner_off[n_owners + 2] = s_ce; }
+  if (threadIdx.x == 0) { owner_off[n_owners + 1] = s_ts; owner_off[n_owners + 2] = s_te; }
 }
 
 // shared tail of gci_scan / gci_scan_windows.  The chunk layout comes from host-known bounds

@@ -414,6 +414,14 @@ def make_genome(lengths, names=None, coverage=30.0, seed=20240635, with_paf=True
 
     def one(c):
         d = make_reads(SynthSpec([lengths[c]], coverage=coverage, seed=seed + c, **spec_kw))
+        # read ids in order of first appearance in the coordinate-sorted BAM: what the decoder's name interner
+        # hands out when it reads the file (gci_b200/io.py), so records of one neighbourhood carry neighbouring ids
+        n = d.bam.n_records
+        first = np.full(d.n_reads, n, np.int64)
+        np.minimum.at(first, d.bam.read_id, np.arange(n, dtype=np.int64))
+        new_id = np.empty(d.n_reads, np.uint32)
+        new_id[np.argsort(first, kind="stable")] = np.arange(d.n_reads, dtype=np.uint32)
+        d.bam.read_id = new_id[d.bam.read_id]
         paf = aln_to_paf(d.bam) if with_paf else None
         bam = drop_reads(d.bam, drop_first, seed + 1000 + c) if drop_first > 0 else d.bam
         return d, bam, paf
