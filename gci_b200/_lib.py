@@ -90,6 +90,11 @@ _SIGNATURES = {
     "gci_comm_p2p_disable": (C.c_int, [_p]),
     "gci_genome_row": (C.c_int, [_p, _i32, _f64, _i32, _i64, _i64, _p, _p, _p, _p]),
     "gci_score_terms_sums": (C.c_int, [_p, _i32, _f64, _i32, _p, _p, _i64, _p, _p, _p]),
+    "gci_shard_config": (C.c_int, [_p, _i32, _i32, _p, _p]),
+    "gci_shard_alloc": (C.c_int, [_p, _u32, _i32, _p]),
+    "gci_shard_open": (C.c_int, [_p, _p]),
+    "gci_shard_area": (_p, [_p]),
+    "gci_shard_attach": (C.c_int, [_p, _p]),
 }
 
 
@@ -477,6 +482,32 @@ class Context:
 
     def comm_p2p_disable(self):
         self._check(self._lib.gci_comm_p2p_disable(self._h))
+
+    # ---- read sets sharded over ranks (contig owners, read homes) ----
+    def shard_config(self, rank, world, contig_owner, gate_selected=None):
+        owner = _arr(contig_owner, np.int32)
+        assert len(owner) == self.n_contigs
+        gs = None if gate_selected is None else _arr(np.asarray(gate_selected, dtype=bool), np.uint8)
+        self._check(self._lib.gci_shard_config(self._h, int(rank), int(world), _ptr(owner), _ptr(gs)))
+        self.shard_rank, self.shard_world = int(rank), int(world)
+
+    def shard_alloc(self, max_reads, max_bam_files=2):
+        """-> 64-byte CUDA IPC handle of this rank's exchange area"""
+        h = np.zeros(64, np.uint8)
+        self._check(self._lib.gci_shard_alloc(self._h, int(max_reads), int(max_bam_files), _ptr(h)))
+        return h
+
+    def shard_open(self, handles):
+        h = _arr(handles, np.uint8)
+        assert h.size == 64 * self.shard_world
+        self._check(self._lib.gci_shard_open(self._h, _ptr(h)))
+
+    def shard_area(self):
+        return int(self._lib.gci_shard_area(self._h) or 0)
+
+    def shard_attach(self, areas):
+        arr = (C.c_void_p * len(areas))(*[C.c_void_p(a) for a in areas])
+        self._check(self._lib.gci_shard_attach(self._h, arr))
 
     def genome_row(self, track, n_owners, sum_len, dist_percent=0.005, flank_len=15, cap=2048):
         """Score terms of this rank's contigs + one NCCL all-gather of every rank's genome-row terms.

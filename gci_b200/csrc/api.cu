@@ -188,6 +188,8 @@ void gci_destroy(gci_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   ctx->drop_graph();
   gci_comm_destroy_internal(ctx);
+  gci_shard_destroy_internal(ctx);
+  ctx->release(ctx->d_gate_sel);
   for (auto& b : ctx->bam) free_bam(ctx, b);
   for (auto& f : ctx->files) free_table(ctx, f);
   for (auto& p : ctx->paf)
@@ -307,6 +309,8 @@ int gci_set_contigs(gci_ctx* ctx, int32_t n, const int64_t* lengths, const uint8
   ctx->total_padded = ctx->n_tiles * GCI_TILE;
   GCI_TRY(gci_h2d(ctx, ctx->d_len, ctx->len.data(), sizeof(int64_t) * n));
   GCI_TRY(gci_h2d(ctx, ctx->d_selected, ctx->selected.data(), n));
+  GCI_TRY(gci_h2d(ctx, ctx->d_gate_sel, ctx->selected.data(), n));      // gci_shard_config may widen it
+  ctx->shard.on = false;                                                // sharding is configured per contig table
   GCI_TRY(gci_h2d(ctx, ctx->d_tile_off, ctx->tile_off.data(), sizeof(int64_t) * (n + 1)));
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->n_nruns = 0;
@@ -373,6 +377,12 @@ int gci_reads_begin(gci_ctx* ctx, uint32_t n_reads) {
   ctx->n_files = 0;
   ctx->n_paf = 0;
   ctx->n_reads = n_reads;
+  if (ctx->shard.on) {
+    gci_ctx::Shard& sh = ctx->shard;
+    sh.n_home = n_reads > (uint32_t)sh.rank ? (n_reads - sh.rank + sh.world - 1) / sh.world : 0;
+    if (sh.area.p && (int64_t)sh.n_home > sh.cap1)
+      return ctx->fail(GCI_E_ARG, "gci_reads_begin: %u reads exceed the exchange area (gci_shard_alloc)", n_reads);
+  }
   ctx->filtered = false;
   ctx->n_survivors = 0;
   GCI_TRY(ctx->ensure(ctx->highq, n_reads));

@@ -172,6 +172,27 @@ struct gci_ctx {
   int64_t p2p_row_cap = 0;            // int64 words per row the area was sized for
   bool p2p_ok = false;                // all peers mapped: gci_enqueue_genome_row pushes instead of calling NCCL
 
+  // read-set sharding over several GPUs (shard.cu): contigs have an owner rank, reads a home rank (id % world)
+  struct Shard {
+    bool on = false;
+    int rank = 0, world = 1, max_files = 0;
+    uint32_t n_home = 0;              // reads this rank is home to: ids rank, rank + world, ...
+    int64_t cap1 = 0, cap2 = 0;       // rows per (file, source rank) / per source rank in the inboxes
+    int64_t surv_slots = 0;           // survivor slots behind surv_contig / surv_start / surv_end (world * cap2)
+    std::vector<int32_t> owner;       // host copy of the contig owners
+    DevBuf d_owner;                   // int32[n_contigs]
+    DevBuf area;                      // this rank's exchange area (header + inboxes), shared with the peers
+    size_t area_bytes = 0;
+    void* peer[GCI_MAX_RANKS] = {};   // every rank's area as mapped here (own rank: area.p)
+    bool mapped[GCI_MAX_RANKS] = {};  // peer[r] came from cudaIpcOpenMemHandle
+    bool opened = false;
+    DevBuf send_cnt;                  // u32[max_files * world + world]: rows sent per (file, destination) / destination
+    DevBuf hq_home;                   // u8[n_home]: high-quality marks of the home reads
+    DevBuf hwin[GCI_MAX_FILES];       // per BAM upload: int64[n_home] winning inbox row per home read
+  } shard;
+  DevBuf d_gate_sel;                  // uint8[n_contigs]: contigs the gates accept (== selected unless sharded: the
+                                      // PAF election must see every selected contig, not only the owned ones)
+
   // CUDA-graph replay of gci_pipeline / gci_pipeline_row (filter.cu).  With the stage timers off, the second
   // call with an unchanged signature (arguments, read-set sizes, device buffers, `epoch`) is captured into a
   // graph and every further one replays it: one cudaGraphLaunch instead of ~40 stream operations.
@@ -226,6 +247,8 @@ int gci_compute_flags(gci_ctx* ctx, int track, int32_t lo, int32_t hi);
 int gci_launch_score_kernels(gci_ctx* ctx, Track& t, double dist_percent, int32_t flank_len, int64_t* n_owners,
                              int64_t* n_slots, bool pending);   // scan.cu: result stays in ctx->tmp[1], no sync
 int gci_enqueue_genome_row(gci_ctx* ctx, Track& t, int64_t no, int64_t sum_len, int64_t cap, int64_t* h_rows);   // comm.cu
+int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t flank_len);           // shard.cu
+void gci_shard_destroy_internal(gci_ctx* ctx);                                                      // shard.cu
 int gci_scan_enqueue(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int32_t flank_len, int64_t* pin);
 int gci_scan_finish(gci_ctx* ctx, int32_t track, const int64_t* pin, bool* overflow);
 extern "C" void gci_comm_destroy_internal(gci_ctx* ctx);
@@ -314,29 +337,59 @@ struct BucketArgs {
 };
 
 // count the two events of one survivor (c < 0: none) into the tile table and add its slice length to the
-// contig's depth sum; warp-collective: every lane of the warp must call it
-__device__ __forceinline__ void bucket_count_one(const BucketArgs& bk, int32_t c, int32_t s, int32_t e) {
+// contig's depth sum.  Block-collective (every thread of the CTA must call it, blockDim.x <= 1024): the depth sums
+// and the survivor count are reduced per warp, then per CTA in shared memory, so that a launch over millions of
+// reads sends one atomic per CTA to those few hot addresses instead of one per warp.
+// count != NULL: also adds the number of threads with `have` to *count.
+__device__ __forceinline__ void bucket_count_one(const BucketArgs& bk, int32_t c, int32_t s, int32_t e, bool have,
+                                                 unsigned long long* count) {
+  __shared__ long long s_cov[32];
+  __shared__ int32_t s_ctg[32];
+  __shared__ int s_have[32];
   long long covered = 0;
-  if (c >= 0) {
-    const Slice sl = survivor_slice(c, s, e, bk.fl, bk.len, bk.tile_off);
-    if (sl.ok) {
-      atomicAdd(&bk.tile_ps[sl.tile_a].x, EV_PLUS);
-      atomicAdd(&bk.tile_ps[sl.tile_b].x, EV_MINUS);
-      covered = sl.b - sl.a;
-    } else {
-      c = -1;
+  if (bk.tile_ps) {
+    if (c >= 0) {
+      const Slice sl = survivor_slice(c, s, e, bk.fl, bk.len, bk.tile_off);
+      if (sl.ok) {
+        atomicAdd(&bk.tile_ps[sl.tile_a].x, EV_PLUS);
+        atomicAdd(&bk.tile_ps[sl.tile_b].x, EV_MINUS);
+        covered = sl.b - sl.a;
+      } else {
+        c = -1;
+      }
     }
+  } else {
+    c = -1;
   }
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, n_wp = (blockDim.x + 31) >> 5;
   // sum of depth per contig = sum of slice lengths; aggregate per warp when the warp agrees on a contig
   const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
-  if (act == 0) return;
-  const int leader = __ffs(act) - 1;
-  const int32_t c0 = __shfl_sync(0xffffffffu, c, leader);
-  const bool uniform = __all_sync(0xffffffffu, c < 0 || c == c0);
-  if (uniform) {
-    const long long t = warp_sum_ll(covered);
-    if ((threadIdx.x & 31) == leader) atomicAdd((unsigned long long*)(bk.sums + c0), (unsigned long long)t);
-  } else if (c >= 0) {
-    atomicAdd((unsigned long long*)(bk.sums + c), (unsigned long long)covered);
+  int32_t c0 = -1;
+  long long t = 0;
+  if (act) {
+    const int leader = __ffs(act) - 1;
+    c0 = __shfl_sync(0xffffffffu, c, leader);
+    const bool uniform = __all_sync(0xffffffffu, c < 0 || c == c0);
+    if (uniform) {
+      t = warp_sum_ll(covered);
+    } else {
+      if (c >= 0) atomicAdd((unsigned long long*)(bk.sums + c), (unsigned long long)covered);
+      c0 = -1;
+    }
+  }
+  const unsigned hv = __ballot_sync(0xffffffffu, have);
+  if (lane == 0) { s_cov[wp] = t; s_ctg[wp] = c0; s_have[wp] = __popc(hv); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n_have = 0;
+    for (int i = 0; i < n_wp; i++) {
+      n_have += s_have[i];
+      if (s_ctg[i] < 0) continue;
+      long long sum = s_cov[i];
+      for (int j = i + 1; j < n_wp; j++)
+        if (s_ctg[j] == s_ctg[i]) { sum += s_cov[j]; s_ctg[j] = -1; }
+      if (sum) atomicAdd((unsigned long long*)(bk.sums + s_ctg[i]), (unsigned long long)sum);
+    }
+    if (count && n_have) atomicAdd(count, (unsigned long long)n_have);
   }
 }

@@ -21,7 +21,7 @@ __global__ void bucket_count_kernel(uint32_t n_reads, const int32_t* __restrict_
                                     const int32_t* __restrict__ se, BucketArgs bk) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = r < n_reads;
-  bucket_count_one(bk, in ? sc[r] : -1, in ? ss[r] : 0, in ? se[r] : 0);
+  bucket_count_one(bk, in ? sc[r] : -1, in ? ss[r] : 0, in ? se[r] : 0, false, nullptr);
 }
 
 __global__ void bucket_fill_kernel(uint32_t n_reads, const int32_t* __restrict__ sc, const int32_t* __restrict__ ss,
@@ -439,7 +439,7 @@ int gci_depth_prepare(gci_ctx* ctx, int32_t track, int32_t flank_len, BucketArgs
   if (nt >= (int64_t(1) << 31)) return ctx->fail(GCI_E_ARG, "too many tiles");
   // one scratch block zeroed with one memset: per tile (pack u64, scan u64) interleaved + fill cursor u32
   GCI_TRY(ctx->ensure(ctx->tile_cnt, 20 * (size_t)nt));
-  GCI_TRY(ctx->ensure(ctx->events, 2 * 2 * (size_t)std::max<uint32_t>(1, ctx->n_reads)));
+  GCI_TRY(ctx->ensure(ctx->events, 2 * 2 * (size_t)std::max<int64_t>(1, ctx->shard.on ? ctx->shard.surv_slots : (int64_t)ctx->n_reads)));
   GCI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->tile_cnt.p, 0, 20 * (size_t)nt, ctx->stream));
   GCI_CUDA_TRY(ctx, cudaMemsetAsync(t.sums.p, 0, sizeof(int64_t) * (size_t)ctx->n_contigs, ctx->stream));
   bk->fl = flank_len;
@@ -457,7 +457,8 @@ int gci_depth_enqueue(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo
   if (!ctx->filtered) return ctx->fail(GCI_E_ARG, "gci_depth before gci_filter");
   Track& t = ctx->track[track];
   const int64_t nt = ctx->n_tiles;
-  const uint32_t nr = ctx->n_reads;
+  // survivor slots: one per read, or for a sharded read set one per inbox slot (shard.cu)
+  const uint32_t nr = ctx->shard.on ? (uint32_t)ctx->shard.surv_slots : ctx->n_reads;
   const bool counted = ctx->counted_track == track && ctx->counted_flank == flank_len;
   ctx->counted_track = -1;
   ctx->stage_begin(GCI_ST_BUCKET);

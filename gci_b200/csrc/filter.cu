@@ -652,10 +652,9 @@ __global__ void join_kernel(JoinArgs a, uint32_t n_reads, const uint8_t* __restr
     s_start[r] = s;
     s_end[r] = e;
   }
-  const unsigned m = __ballot_sync(0xffffffffu, have);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
-  // gci_pipeline: the depth events of the survivor are counted right here (no second pass over the survivors)
-  if (bk.tile_ps) bucket_count_one(bk, have ? c : -1, s, e);
+  // the survivor count, and for gci_pipeline the depth events of the survivor, are counted right here (no second
+  // pass over the survivors); block-collective
+  bucket_count_one(bk, have ? c : -1, s, e, have, count);
 }
 
 // ================================================================================================
@@ -676,6 +675,9 @@ static int check_err(gci_ctx* ctx, const char* where, unsigned long long* count)
                      : (h[0] & 8) ? "ZeroDivisionError at GCI.py:292 (query_length 0 in the join)"
                      : (h[0] & 16) ? "ZeroDivisionError at GCI.py:231 (PAF alignment length 0)"
                                    : "ZeroDivisionError at GCI.py:247 (PAF query length 0)";
+  if (h[0] & (64 | 128))
+    return ctx->fail(GCI_E_CUDA, "%s: read-set exchange failed (%s)", where,
+                     (h[0] & 64) ? "a peer rank did not arrive in time" : "an inbox overflowed");
   return ctx->fail(GCI_E_REFERENCE_RAISES, "%s: the reference raises here: %s [first index %llu]", where, what, h[1]);
 }
 
@@ -685,6 +687,8 @@ static int reset_err(gci_ctx* ctx) {
   if (ctx->n_reads)
     GCI_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->highq.p, ctx->highq_base.p, ctx->n_reads, cudaMemcpyDeviceToDevice,
                                       ctx->stream));
+  if (ctx->shard.on && ctx->shard.n_home)     // marks of the home reads: PAF election and inbox merge set them
+    GCI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->shard.hq_home.p, 0, ctx->shard.n_home, ctx->stream));
   GCI_TRY(ctx->ensure(ctx->d_err, 4 * sizeof(unsigned long long)));
   // [0] error mask = 0, [1] first offending index = ~0, [2] survivor count = 0
   GCI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_err.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
@@ -784,7 +788,7 @@ int gci_run_bam_leg(gci_ctx* ctx, int file_idx, int bam_idx, int32_t mq, int32_t
   GateArgs g;
   g.ref_id = b.ref_id.as<int32_t>(); g.ref_start = b.ref_start.as<int32_t>(); g.mapq = b.mapq.as<uint8_t>();
   g.flag = b.flag.as<uint16_t>(); g.nm = b.nm.as<int32_t>(); g.read_id = b.read_id.as<uint32_t>();
-  g.selected = ctx->d_selected.as<uint8_t>(); g.n_contigs = ctx->n_contigs; g.n_reads = ctx->n_reads;
+  g.selected = ctx->d_gate_sel.as<uint8_t>(); g.n_contigs = ctx->n_contigs; g.n_reads = ctx->n_reads;
   g.map_qual = mq; g.mq_cutoff = mq_cutoff; g.ip = ip; g.cp = cp;
   g.ref_end = b.ref_end.as<int32_t>(); g.win = ft.win.as<long long>(); g.highq = ctx->highq.as<uint8_t>();
   g.err = ctx->d_err.as<unsigned long long>();
@@ -903,12 +907,12 @@ __global__ void paf_fill_kernel(int64_t n, const uint32_t* __restrict__ read_id,
   idx[off[q] + atomicAdd(&cur[q], 1)] = (int32_t)(line0 + i);
 }
 
-// GCI.py:64-96 over the members `seg[0..g)` that sit on contig `ref`: walk the (lo, hi) pairs in sorted
+// GCI.py:64-96 over the lines get(0..g) that sit on contig `ref`: walk the (lo, hi) pairs in sorted
 // order by repeated selection of the next smallest (lo, hi, position) triple (groups are tiny), merge
 // touching / overlapping blocks, return the total merged length and the longest block (first on ties).
 struct Blocks { long long total; int32_t lo, hi; };
-template <bool TARGET>
-__device__ Blocks merged_blocks(const PafSet& ps, const int32_t* __restrict__ seg, int g, int32_t ref) {
+template <bool TARGET, class Get>
+__device__ Blocks merged_blocks(const Get& get, int g, int32_t ref) {
   Blocks r{0, 0, 0};
   long long best_len = -1;
   bool have_cur = false, have_last = false;
@@ -919,7 +923,7 @@ __device__ Blocks merged_blocks(const PafSet& ps, const int32_t* __restrict__ se
     int pick = -1;
     int32_t p_lo = 0, p_hi = 0;
     for (int j = 0; j < g; j++) {
-      const PafLine l = paf_line(ps, seg[j]);
+      const PafLine l = get(j);
       if (l.ref != ref) continue;
       const int32_t lo = TARGET ? l.t0 : l.q0, hi = TARGET ? l.t1 : l.q1;
       if (have_last) {
@@ -948,58 +952,39 @@ __device__ Blocks merged_blocks(const PafSet& ps, const int32_t* __restrict__ se
   return r;
 }
 
-// one thread per read: a single kept line is the result; more lines are ordered by arrival and every contig scored
-__global__ void paf_elect_kernel(uint32_t n_reads, PafSet ps, const int32_t* __restrict__ off, int32_t* __restrict__ idx,
-                                 const int32_t* __restrict__ name_rank, int32_t* __restrict__ t_ref,
-                                 int32_t* __restrict__ t_start, int32_t* __restrict__ t_end, int32_t* __restrict__ t_qlen,
-                                 long long* __restrict__ win, unsigned long long* __restrict__ err) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_reads) return;
-  const int32_t a0 = off[r], g = off[r + 1] - a0;
-  if (g == 0) { win[r] = -1; return; }
-  int32_t* seg = idx + a0;
-  if (g == 1) {
-    const PafLine l = paf_line(ps, seg[0]);
-    if (l.qlen == 0) {                       // ZeroDivisionError :247
-      atomicOr(err, 32ull);
-      atomicMin(err + 1, (unsigned long long)r);
-      win[r] = -1;
-      return;
-    }
-    t_ref[r] = l.ref; t_start[r] = l.t0; t_end[r] = l.t1; t_qlen[r] = l.qlen;
-    win[r] = (long long)r;
-    return;
-  }
-  for (int i = 1; i < g; i++) {              // insertion sort by line id = arrival order (file order, :237)
-    const int32_t e = seg[i];
-    int j = i - 1;
-    while (j >= 0 && seg[j] > e) { seg[j + 1] = seg[j]; j--; }
-    seg[j + 1] = e;
-  }
+struct PafTableOut {
+  int32_t *ref, *start, *end, *qlen;
+  long long* win;
+};
+
+// the election of one read over its g >= 2 kept lines, get(j) = j-th line in arrival order (GCI.py:241-254)
+template <class Get>
+__device__ void paf_elect_read(uint32_t r, int g, const Get& get, const int32_t* __restrict__ name_rank,
+                               const PafTableOut& o, unsigned long long* __restrict__ err) {
   bool have = false;
   double best_score = 0;
   int32_t best_rank = 0, b_ref = 0, b_s = 0, b_e = 0, b_q = 0;
   for (int i = 0; i < g; i++) {
-    const PafLine li = paf_line(ps, seg[i]);
+    const PafLine li = get(i);
     const int32_t ref = li.ref;
     bool seen = false;
-    for (int j = 0; j < i && !seen; j++) seen = paf_line(ps, seg[j]).ref == ref;
+    for (int j = 0; j < i && !seen; j++) seen = get(j).ref == ref;
     if (seen) continue;
     double sum = 0;                          // Python sum() starts from int 0; 0 + x is exact
     int cnt = 0;
     for (int j = i; j < g; j++) {
-      const PafLine lj = paf_line(ps, seg[j]);
+      const PafLine lj = get(j);
       if (lj.ref == ref) { sum = sum + lj.ident; cnt++; }
     }
     const int32_t qlen = li.qlen;            // alns[0][0], :246
     if (qlen == 0) {                         // ZeroDivisionError :247
       atomicOr(err, 32ull);
       atomicMin(err + 1, (unsigned long long)r);
-      win[r] = -1;
+      o.win[r] = -1;
       return;
     }
-    const Blocks bq = merged_blocks<false>(ps, seg, g, ref);
-    const Blocks bt = merged_blocks<true>(ps, seg, g, ref);
+    const Blocks bq = merged_blocks<false>(get, g, ref);
+    const Blocks bt = merged_blocks<true>(get, g, ref);
     const double rate = (double)bq.total / (double)qlen;               // :247
     const double score = (sum / (double)cnt) * rate;                   // :248-249
     const int32_t rank = name_rank[ref];
@@ -1009,8 +994,73 @@ __global__ void paf_elect_kernel(uint32_t n_reads, PafSet ps, const int32_t* __r
       b_ref = ref; b_s = bt.lo; b_e = bt.hi; b_q = qlen;
     }
   }
-  t_ref[r] = b_ref; t_start[r] = b_s; t_end[r] = b_e; t_qlen[r] = b_q;
-  win[r] = (long long)r;                     // table entries are indexed by read id
+  o.ref[r] = b_ref; o.start[r] = b_s; o.end[r] = b_e; o.qlen[r] = b_q;
+  o.win[r] = (long long)r;                   // table entries are indexed by read id
+}
+
+// one thread per read: no kept line -> absent; ONE kept line (almost every read) -> that line is the result;
+// more -> the read goes to the list of paf_elect_multi_kernel, so no warp waits for a lane walking a group
+__global__ void paf_elect_kernel(uint32_t n_reads, PafSet ps, const int32_t* __restrict__ off,
+                                 const int32_t* __restrict__ idx, PafTableOut o, int32_t* __restrict__ multi,
+                                 unsigned int* __restrict__ n_multi, unsigned long long* __restrict__ err) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  int g = 0;
+  int32_t a0 = 0;
+  if (r < n_reads) {
+    a0 = off[r];
+    g = off[r + 1] - a0;
+  }
+  if (r < n_reads && g == 0) o.win[r] = -1;
+  if (g == 1) {
+    const int32_t line = idx[a0];
+    int k = 0;
+    while (k + 1 < ps.n && (int64_t)line >= ps.off[k + 1]) k++;
+    const int64_t i = (int64_t)line - ps.off[k];
+    const PafCols& p = ps.f[k];
+    const int32_t ql = p.qlen[i];
+    if (ql == 0) {                           // ZeroDivisionError :247
+      atomicOr(err, 32ull);
+      atomicMin(err + 1, (unsigned long long)r);
+      o.win[r] = -1;
+    } else {
+      o.ref[r] = p.ref_id[i]; o.start[r] = p.tstart[i]; o.end[r] = p.tend[i]; o.qlen[r] = ql;
+      o.win[r] = (long long)r;
+    }
+  }
+  const unsigned many = __ballot_sync(0xffffffffu, g >= 2);
+  if (many) {
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(n_multi, (unsigned)__popc(many));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (g >= 2) multi[base + __popc(many & ((1u << lane) - 1u))] = (int32_t)r;
+  }
+}
+
+constexpr int PAF_LOCAL = 8;                 // lines of one read kept in registers / local memory
+__global__ void __launch_bounds__(128)
+paf_elect_multi_kernel(PafSet ps, const int32_t* __restrict__ off, int32_t* __restrict__ idx,
+                       const int32_t* __restrict__ name_rank, PafTableOut o, const int32_t* __restrict__ multi,
+                       const unsigned int* __restrict__ n_multi, unsigned long long* __restrict__ err) {
+  const unsigned n = *n_multi;
+  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)multi[k];
+    const int32_t a0 = off[r], g = off[r + 1] - a0;
+    int32_t* seg = idx + a0;
+    for (int i = 1; i < g; i++) {            // insertion sort by line id = arrival order (file order, :237)
+      const int32_t e = seg[i];
+      int j = i - 1;
+      while (j >= 0 && seg[j] > e) { seg[j + 1] = seg[j]; j--; }
+      seg[j + 1] = e;
+    }
+    if (g <= PAF_LOCAL) {
+      PafLine L[PAF_LOCAL];
+      for (int j = 0; j < g; j++) L[j] = paf_line(ps, seg[j]);
+      paf_elect_read(r, g, [&L](int j) { return L[j]; }, name_rank, o, err);
+    } else {
+      paf_elect_read(r, g, [&ps, seg](int j) { return paf_line(ps, seg[j]); }, name_rank, o, err);
+    }
+  }
 }
 
 int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
@@ -1036,8 +1086,12 @@ int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
   const int64_t total_lines = ps.off[ps.n];
   if (total_lines >= (int64_t(1) << 31)) return ctx->fail(GCI_E_ARG, "more than 2^31 PAF lines in one read set");
   const size_t cap = (size_t)std::max<int64_t>(1, total_lines);
-  const size_t nr = std::max<uint32_t>(1, ctx->n_reads);
-  DevBuf &cnt = ctx->tmp[6], &off = ctx->tmp[7], &idx = ctx->tmp[8], &keep = ctx->paf_keep;
+  // sharded read sets upload PAF lines with home-local read ids (id / world): the tables are indexed by those
+  const uint32_t n_reads = ctx->shard.on ? ctx->shard.n_home : ctx->n_reads;
+  uint8_t* highq = ctx->shard.on ? ctx->shard.hq_home.as<uint8_t>() : ctx->highq.as<uint8_t>();
+  const size_t nr = std::max<uint32_t>(1, n_reads);
+  DevBuf &cnt = ctx->tmp[6], &off = ctx->tmp[7], &idx = ctx->tmp[8], &keep = ctx->paf_keep, &multi_buf = ctx->tmp[9];
+  GCI_TRY(ctx->ensure(multi_buf, 4 * (nr + 1)));
   GCI_TRY(ctx->ensure(cnt, 4 * (nr + 1) * 2));     // counts | fill cursors
   GCI_TRY(ctx->ensure(off, 4 * (nr + 1)));
   GCI_TRY(ctx->ensure(idx, 4 * cap));
@@ -1051,12 +1105,12 @@ int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
     const int64_t n = ps.off[k + 1] - ps.off[k];
     if (n) {
       paf_mark_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
-          n, ps.f[k], ps.off[k], ctx->d_selected.as<uint8_t>(), ctx->n_contigs, ctx->n_reads, mq, mq_cutoff, ip,
-          keep.as<uint8_t>(), d_cnt, ctx->highq.as<uint8_t>(), ctx->d_err.as<unsigned long long>());
+          n, ps.f[k], ps.off[k], ctx->d_gate_sel.as<uint8_t>(), ctx->n_contigs, n_reads, mq, mq_cutoff, ip,
+          keep.as<uint8_t>(), d_cnt, highq, ctx->d_err.as<unsigned long long>());
       GCI_LAUNCH_CHECK(ctx);
     }
     // group the kept lines of files 0..k by read: CSR over read ids (the counts accumulate across the files)
-    GCI_TRY(gci_exclusive_scan_i32(ctx, d_cnt, off.as<int32_t>(), (int64_t)ctx->n_reads + 1));
+    GCI_TRY(gci_exclusive_scan_i32(ctx, d_cnt, off.as<int32_t>(), (int64_t)n_reads + 1));
     GCI_CUDA_TRY(ctx, cudaMemsetAsync(d_cur, 0, 4 * (nr + 1), ctx->stream));
     for (int j = 0; j <= k; j++) {
       const int64_t nj = ps.off[j + 1] - ps.off[j];
@@ -1067,17 +1121,25 @@ int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
     }
     // the file's table: one entry per read id
     ft.kind = 1;
-    ft.n = ctx->n_reads;
+    ft.n = n_reads;
     GCI_TRY(ctx->ensure(ft.ref_id, 4 * nr)); GCI_TRY(ctx->ensure(ft.start, 4 * nr));
     GCI_TRY(ctx->ensure(ft.end, 4 * nr)); GCI_TRY(ctx->ensure(ft.qlen, 4 * nr));
     GCI_TRY(ctx->ensure(ft.win, 8 * nr));
-    if (ctx->n_reads) {
+    if (n_reads) {
       PafSet upto = ps;
       upto.n = k + 1;
-      paf_elect_kernel<<<(ctx->n_reads + 127) / 128, 128, 0, ctx->stream>>>(
-          ctx->n_reads, upto, off.as<int32_t>(), idx.as<int32_t>(), ctx->d_name_rank.as<int32_t>(),
-          ft.ref_id.as<int32_t>(), ft.start.as<int32_t>(), ft.end.as<int32_t>(), ft.qlen.as<int32_t>(),
-          ft.win.as<long long>(), ctx->d_err.as<unsigned long long>());
+      PafTableOut o{ft.ref_id.as<int32_t>(), ft.start.as<int32_t>(), ft.end.as<int32_t>(), ft.qlen.as<int32_t>(),
+                    ft.win.as<long long>()};
+      int32_t* multi = multi_buf.as<int32_t>();
+      unsigned int* n_multi = reinterpret_cast<unsigned int*>(multi + nr);
+      GCI_CUDA_TRY(ctx, cudaMemsetAsync(n_multi, 0, 4, ctx->stream));
+      paf_elect_kernel<<<(n_reads + 127) / 128, 128, 0, ctx->stream>>>(
+          n_reads, upto, off.as<int32_t>(), idx.as<int32_t>(), o, multi, n_multi, ctx->d_err.as<unsigned long long>());
+      GCI_LAUNCH_CHECK(ctx);
+      const unsigned mgrid = (unsigned)std::min<int64_t>((n_reads + 127) / 128, (int64_t)ctx->sm_count * 8);
+      paf_elect_multi_kernel<<<mgrid, 128, 0, ctx->stream>>>(
+          upto, off.as<int32_t>(), idx.as<int32_t>(), ctx->d_name_rank.as<int32_t>(), o, multi, n_multi,
+          ctx->d_err.as<unsigned long long>());
       GCI_LAUNCH_CHECK(ctx);
     }
   }
@@ -1186,6 +1248,7 @@ int gci_filter(gci_ctx* ctx, int32_t map_qual, int32_t mq_cutoff, double iden_pe
   cudaSetDevice(ctx->device);
   ctx->epoch++;
   if (ctx->n_files == 0) return ctx->fail(GCI_E_ARG, "gci_filter: no files uploaded");
+  if (ctx->shard.on) return ctx->fail(GCI_E_ARG, "gci_filter: a sharded read set runs through gci_pipeline");
   GCI_TRY(reset_err(ctx));
   // PAF election first (files join in upload order); tables uploaded by the caller are already final
   GCI_TRY(gci_run_paf_legs(ctx, map_qual, mq_cutoff, iden_percent));
@@ -1233,6 +1296,7 @@ int gci_fetch_survivors(gci_ctx* ctx, int64_t cap, uint32_t* read_id, int32_t* c
   if (!ctx) return GCI_E_ARG;
   cudaSetDevice(ctx->device);
   if (!ctx->filtered) return ctx->fail(GCI_E_ARG, "gci_fetch_survivors before gci_filter");
+  if (ctx->shard.on) return ctx->fail(GCI_E_ARG, "gci_fetch_survivors: not available for a sharded read set");
   if (n) *n = ctx->n_survivors;
   if (!read_id && !contig && !start && !end) return GCI_OK;
   if (cap < ctx->n_survivors) return ctx->fail(GCI_E_ARG, "survivor buffer too small");
@@ -1358,6 +1422,7 @@ static std::vector<char> pipeline_signature(gci_ctx* ctx, const PipeArgs& a) {
   put64((int64_t)ctx->epoch); put64((int64_t)ctx->alloc_gen); put64((int64_t)(intptr_t)ctx->stream);
   put64((int64_t)(intptr_t)ctx->nccl_comm); put64(ctx->p2p_ok); put64(ctx->n_reads); put64((int64_t)ctx->n_files);
   put64((int64_t)ctx->n_bam); put64((int64_t)ctx->n_paf);
+  put64(ctx->shard.on); put64(ctx->shard.rank); put64(ctx->shard.world); put64(ctx->shard.cap1); put64(ctx->shard.opened);
   for (size_t i = 0; i < ctx->n_files; i++) {
     const FileTable& f = ctx->files[i];
     put64(f.paf >= 0 ? 2 : f.kind); put64(f.src); put64(f.paf); put64(f.paf >= 0 ? 0 : f.n);
@@ -1376,7 +1441,8 @@ static int pipeline_enqueue(gci_ctx* ctx, const PipeArgs& a, PipeOut* out) {
   for (size_t i = 0; i < ctx->n_files; i++)
     if (ctx->files[i].kind == 0)
       GCI_TRY(gci_run_bam_leg(ctx, (int)i, ctx->files[i].src, a.map_qual, a.mq_cutoff, a.ip, a.cp));
-  GCI_TRY(gci_run_join_counting(ctx, a.op, a.track, a.flank_len));
+  if (ctx->shard.on) GCI_TRY(gci_shard_exchange_enqueue(ctx, a.op, a.track, a.flank_len));   // join at the read homes
+  else GCI_TRY(gci_run_join_counting(ctx, a.op, a.track, a.flank_len));
   ctx->filtered = true;
   GCI_TRY(gci_depth_enqueue(ctx, a.track, a.flank_len, a.lo, a.hi));
   Track& t = ctx->track[a.track];

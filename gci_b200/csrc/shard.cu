@@ -1,0 +1,490 @@
+// Read-set sharding over the GPUs of one NVLink domain (the reference's analogue is the Pool fan-out
+// plus dict merge of GCI.py:257-301).
+//
+// Contigs are owned by ranks (depth, scan and score are per contig), but the cross-file join (GCI.py:272-301) is
+// keyed by READ: a read's records may sit on contigs of different owners.  Instead of gathering every table on every
+// rank, every read has a HOME rank (read id % world) and the step moves each piece of data exactly once:
+//
+//   owner of the contig      BAM gates + last-record-wins dedup on the records it holds
+//        |   dispatch 1      every per-file winner row (read, contig, start, end, qlen, high-quality mark) is stored
+//        v                   straight into the inbox of the read's home over NVLink peer memory
+//   home of the read         PAF election for its reads (the host deals PAF lines by read), merge of the inbox rows
+//        |                   (highest contig wins, GCI.py:268-270), the join of all files for its reads
+//        |   dispatch 2      every survivor (contig, start, end) is stored into the inbox of the contig's owner
+//        v
+//   owner of the contig      depth events -> depth tiles -> scan -> score, as on one GPU
+//
+// Both dispatches are all-to-all exchanges written as plain kernels over peer pointers (CUDA IPC between processes):
+// rows go to slots claimed from per-destination counters, then every rank publishes its counts and an epoch flag
+// in the peers' headers and waits for theirs.  Two receive areas alternate by epoch parity (a rank can be at most
+// one step ahead of a peer), the epoch lives in device memory, so the step replays inside a CUDA graph.
+#include <algorithm>
+
+#include "common.cuh"
+
+struct XRow1 { uint32_t read; int32_t contig, start, end, qlen; uint32_t hq; };   // 24 B: a file's winner for one read
+struct XRow2 { int32_t contig, start, end, pad; };                                // 16 B: a survivor
+
+// geometry of one rank's exchange area (identical on every rank)
+struct XLayout {
+  int world, files;
+  long long cap1, cap2;
+  // header, in 8-byte words: [epoch | flag[2 phases][2 parities][world] | err]
+  __host__ __device__ long long flag_word(int phase, int par, int src) const { return 1 + ((phase * 2 + par) * world + src); }
+  __host__ __device__ long long err_word() const { return 1 + 4LL * world; }
+  // then counts (u32): cnt1[2 parities][files][world], cnt2[2 parities][world]
+  __host__ __device__ long long cnt_base() const { return (err_word() + 1) * 8; }
+  __host__ __device__ long long cnt1_off(int par, int f, int src) const { return cnt_base() + 4LL * ((par * files + f) * world + src); }
+  __host__ __device__ long long cnt2_off(int par, int src) const { return cnt_base() + 4LL * (2LL * files * world + par * world + src); }
+  __host__ __device__ long long rows1_base() const { return (cnt_base() + 4LL * (2LL * files * world + 2LL * world) + 255) & ~255LL; }
+  __host__ __device__ long long rows1_off(int par, int f, int src) const {
+    return rows1_base() + (long long)sizeof(XRow1) * cap1 * ((par * files + f) * (long long)world + src);
+  }
+  __host__ __device__ long long rows2_base() const { return (rows1_off(2, 0, 0) + 255) & ~255LL; }
+  __host__ __device__ long long rows2_off(int par, int src) const {
+    return rows2_base() + (long long)sizeof(XRow2) * cap2 * (par * (long long)world + src);
+  }
+  __host__ __device__ long long total() const { return rows2_off(2, 0); }
+};
+
+struct XPeers { char* area[GCI_MAX_RANKS]; };
+constexpr unsigned long long XCHG_TIMEOUT_NS = 8000000000ull;
+
+// ---- step begin: advance the epoch, clear the send cursors --------------------------------------------------
+__global__ void xchg_begin_kernel(char* mine, uint32_t* send_cnt, int n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *reinterpret_cast<unsigned long long*>(mine) += 1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) send_cnt[i] = 0;
+}
+
+// slot for one row per destination rank: rows of one CTA are counted in shared memory, one global atomic per
+// (CTA, destination) claims the range.  Block-collective.
+__device__ __forceinline__ uint32_t claim_slot(uint32_t* cursor /* [world] */, int dst, bool active, int world) {
+  __shared__ uint32_t s_cnt[GCI_MAX_RANKS], s_base[GCI_MAX_RANKS];
+  if (threadIdx.x < GCI_MAX_RANKS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t local = 0;
+  if (active) local = atomicAdd(&s_cnt[dst], 1u);
+  __syncthreads();
+  if ((int)threadIdx.x < world && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], s_cnt[threadIdx.x]);
+  __syncthreads();
+  const uint32_t slot = active ? s_base[dst] + local : 0u;
+  __syncthreads();                                   // the shared counters are reused by the next call
+  return slot;
+}
+
+// ---- dispatch 1: per-file winners to the home of their read --------------------------------------------------
+__global__ void __launch_bounds__(256)
+dispatch1_kernel(XLayout lay, XPeers peers, int me, int f, uint32_t n_reads, const long long* __restrict__ win,
+                 const int32_t* __restrict__ ref_id, const int32_t* __restrict__ start, const int32_t* __restrict__ end,
+                 const int32_t* __restrict__ qlen, const uint8_t* __restrict__ highq, uint32_t* __restrict__ send_cnt,
+                 unsigned long long* __restrict__ err) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long epoch = *reinterpret_cast<const unsigned long long*>(peers.area[me]);
+  const int par = (int)(epoch & 1ull);
+  long long k = -1;
+  if (q < n_reads) k = win[q];
+  const bool act = k >= 0;
+  const int dst = (int)(q % (uint32_t)lay.world);
+  const uint32_t slot = claim_slot(send_cnt + f * lay.world, dst, act, lay.world);
+  if (!act) return;
+  const uint32_t i = (uint32_t)(k & 0xffffffffll);
+  XRow1 row{q, ref_id[i], start[i], end[i], qlen[i], (uint32_t)highq[q]};
+  if ((long long)slot >= lay.cap1) {                 // cannot happen: a source sends at most one row per home read
+    atomicOr(err, 128ull);
+    return;
+  }
+  XRow1* dstp = reinterpret_cast<XRow1*>(peers.area[dst] + lay.rows1_off(par, f, me)) + slot;
+  // 24 bytes as three 8-byte stores (rows are 8-byte aligned)
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&row);
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(dstp);
+  d[0] = src[0]; d[1] = src[1]; d[2] = src[2];
+}
+
+// ---- publish the counts of one phase at every peer, then raise the flag ----------------------------------------
+__global__ void xchg_signal_kernel(XLayout lay, XPeers peers, int me, int phase, int n_files, const uint32_t* send_cnt) {
+  const int dst = threadIdx.x;
+  if (dst >= lay.world) return;
+  const unsigned long long epoch = *reinterpret_cast<const unsigned long long*>(peers.area[me]);
+  const int par = (int)(epoch & 1ull);
+  __threadfence_system();
+  char* area = peers.area[dst];
+  if (phase == 0) {
+    for (int f = 0; f < n_files; f++)
+      *reinterpret_cast<volatile uint32_t*>(area + lay.cnt1_off(par, f, me)) = send_cnt[f * lay.world + dst];
+  } else {
+    *reinterpret_cast<volatile uint32_t*>(area + lay.cnt2_off(par, me)) = send_cnt[lay.files * lay.world + dst];
+  }
+  __threadfence_system();
+  *(reinterpret_cast<volatile unsigned long long*>(area) + lay.flag_word(phase, par, me)) = epoch;
+}
+
+// ---- wait until every source's flag of this phase shows the step's epoch ---------------------------------------
+__global__ void xchg_wait_kernel(XLayout lay, char* mine, int phase, unsigned long long* __restrict__ err) {
+  const int src = threadIdx.x;
+  if (src >= lay.world) return;
+  volatile unsigned long long* hdr = reinterpret_cast<volatile unsigned long long*>(mine);
+  const unsigned long long epoch = hdr[0];
+  const int par = (int)(epoch & 1ull);
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (hdr[lay.flag_word(phase, par, src)] < epoch) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > XCHG_TIMEOUT_NS) {                  // a peer never arrived: report instead of hanging the GPU
+      atomicOr(err, 64ull);
+      break;
+    }
+    __nanosleep(100);
+  }
+  __threadfence_system();
+}
+
+// ---- home: merge the inbox rows of one file (highest contig wins, the reference's fetch order) ----------------
+__global__ void __launch_bounds__(256)
+merge1_kernel(XLayout lay, const char* __restrict__ mine, int f, long long* __restrict__ hwin, uint8_t* __restrict__ hq_home) {
+  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;       // (source, slot)
+  const int src = (int)(g / lay.cap1);
+  const long long slot = g - (long long)src * lay.cap1;
+  if (src >= lay.world) return;
+  const int par = (int)(*reinterpret_cast<const unsigned long long*>(mine) & 1ull);
+  if (slot >= (long long)*reinterpret_cast<const uint32_t*>(mine + lay.cnt1_off(par, f, src))) return;
+  // row index over the whole rows1 block (both parities, all files): what home_join_kernel dereferences
+  const long long G = (lay.rows1_off(par, f, 0) - lay.rows1_base()) / (long long)sizeof(XRow1) + g;
+  const XRow1 r = reinterpret_cast<const XRow1*>(mine + lay.rows1_base())[G];
+  const uint32_t h = r.read / (uint32_t)lay.world;
+  atomicMax(hwin + h, ((long long)r.contig << 32) | G);
+  if (r.hq) hq_home[h] = 1;
+}
+
+// ---- home: the join of all files for the reads homed here (GCI.py:272-301), survivors to their contig's owner ---
+struct HomeFile {
+  const long long* win;       // [n_home]: entry of the home read (low 32 bits), < 0 = absent in this file
+  const int32_t *c, *s, *e, *q;   // fields of entry 0
+  int stride;                 // int32 words between entries (1: separate columns, 6: inbox rows)
+};
+struct HomeArgs {
+  HomeFile f[GCI_MAX_FILES];
+  int n_files;
+};
+
+__global__ void __launch_bounds__(256)
+home_join_kernel(XLayout lay, XPeers peers, int me, HomeArgs a, uint32_t n_home, const uint8_t* __restrict__ hq_home,
+                 double op, const int32_t* __restrict__ owner, int32_t n_contigs, uint32_t* __restrict__ send_cnt,
+                 unsigned long long* __restrict__ count, unsigned long long* __restrict__ err) {
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  const int par = (int)(*reinterpret_cast<const unsigned long long*>(peers.area[me]) & 1ull);
+  bool have = false;
+  int32_t c = -1, s = 0, e = 0;
+  auto entry = [&a](int f, long long k, int32_t& cf, int32_t& sf, int32_t& ef, int32_t& qf) {
+    const HomeFile& hf = a.f[f];
+    const long long i = (long long)(uint32_t)(k & 0xffffffffll) * hf.stride;
+    cf = hf.c[i]; sf = hf.s[i]; ef = hf.e[i]; qf = hf.q[i];
+  };
+  if (h < n_home) {
+    const long long k0 = a.f[0].win[h];
+    int32_t cf, sf, ef, qf;
+    if (a.n_files == 1) {                                                 // :300-301
+      if (k0 >= 0) { entry(0, k0, cf, sf, ef, qf); have = true; c = cf; s = sf; e = ef; }
+    } else {
+      bool comm = true;
+      for (int f = 0; f < a.n_files; f++) comm = comm && (a.f[f].win[h] >= 0);           // :274-277
+      const bool hq = hq_home[h] != 0;
+      if (k0 >= 0 && (hq || comm)) {                                                     // :279-280
+        entry(0, k0, cf, sf, ef, qf);
+        have = true; c = cf; s = sf; e = ef;
+      }
+      for (int f = 1; f < a.n_files; f++) {                                               // :281-299
+        const long long k = a.f[f].win[h];
+        if (k < 0) continue;
+        entry(f, k, cf, sf, ef, qf);
+        if (have) {
+          if (cf == c) {
+            const long long ov = (long long)min(ef, e) - (long long)max(sf, s);
+            if (qf == 0) {                                                                // ZeroDivisionError :292
+              atomicOr(err, 8ull);
+              atomicMin(err + 1, (unsigned long long)h * lay.world + me);
+              have = false;
+            } else if ((double)ov / (double)qf < op) {
+              have = false;
+            } else {
+              s = max(sf, s);
+              e = min(ef, e);
+            }
+          } else {
+            have = false;
+          }
+        } else if (hq) {
+          have = true;
+          c = cf; s = sf; e = ef;
+        }
+      }
+    }
+  }
+  const bool send = have && c >= 0 && c < n_contigs;
+  const int dst = send ? owner[c] : 0;
+  const bool act = send && dst >= 0 && dst < lay.world;
+  const uint32_t slot = claim_slot(send_cnt + lay.files * lay.world, act ? dst : 0, act, lay.world);
+  if (act) {
+    if ((long long)slot < lay.cap2) {
+      XRow2* p = reinterpret_cast<XRow2*>(peers.area[dst] + lay.rows2_off(par, me)) + slot;
+      *reinterpret_cast<int4*>(p) = make_int4(c, s, e, 0);
+    } else {
+      atomicOr(err, 128ull);
+    }
+  }
+  // survivors evaluated here (the global count is the sum over the ranks)
+  const unsigned m = __ballot_sync(0xffffffffu, have);
+  __shared__ int s_n[8];
+  if ((threadIdx.x & 31) == 0) s_n[threadIdx.x >> 5] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) n += s_n[i];
+    if (n) atomicAdd(count, (unsigned long long)n);
+  }
+}
+
+// ---- owner: survivors of the inbox into the survivor slots, depth events counted on the way ---------------------
+__global__ void __launch_bounds__(256)
+consume2_kernel(XLayout lay, const char* __restrict__ mine, int32_t* __restrict__ s_contig, int32_t* __restrict__ s_start,
+                int32_t* __restrict__ s_end, BucketArgs bk) {
+  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;       // (source, slot)
+  const int src = (int)(g / lay.cap2);
+  const long long slot = g - (long long)src * lay.cap2;
+  const int par = (int)(*reinterpret_cast<const unsigned long long*>(mine) & 1ull);
+  int32_t c = -1, s = 0, e = 0;
+  if (src < lay.world) {
+    if (slot < (long long)*reinterpret_cast<const uint32_t*>(mine + lay.cnt2_off(par, src))) {
+      const int4 r = *reinterpret_cast<const int4*>(mine + lay.rows2_off(par, 0) + (long long)sizeof(XRow2) * g);
+      c = r.x; s = r.y; e = r.z;
+    }
+    s_contig[g] = c;
+    s_start[g] = s;
+    s_end[g] = e;
+  }
+  bucket_count_one(bk, c, s, e, false, nullptr);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+static XLayout make_layout(const gci_ctx* ctx) {
+  XLayout l;
+  l.world = ctx->shard.world;
+  l.files = ctx->shard.max_files;
+  l.cap1 = ctx->shard.cap1;
+  l.cap2 = ctx->shard.cap2;
+  return l;
+}
+
+static XPeers make_peers(const gci_ctx* ctx) {
+  XPeers p;
+  for (int r = 0; r < GCI_MAX_RANKS; r++) p.area[r] = r < ctx->shard.world ? (char*)ctx->shard.peer[r] : nullptr;
+  return p;
+}
+
+// dispatch 1 .. consume 2 of one step; the BAM legs (win per global read, highq) and the PAF legs (home tables) have
+// been enqueued before.  Leaves the survivors in ctx->surv_* (shard.surv_slots slots) with their events counted.
+int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t flank_len) {
+  gci_ctx::Shard& sh = ctx->shard;
+  if (!sh.on || !sh.opened) return ctx->fail(GCI_E_ARG, "sharded read set: gci_shard_open / gci_shard_attach missing");
+  const XLayout lay = make_layout(ctx);
+  const XPeers peers = make_peers(ctx);
+  char* mine = (char*)sh.area.p;
+  if ((int64_t)ctx->n_reads > lay.cap1 * lay.world)
+    return ctx->fail(GCI_E_ARG, "sharded read set: %u reads, exchange sized for %lld", ctx->n_reads, lay.cap1 * lay.world);
+  int n_bam = 0;
+  for (size_t i = 0; i < ctx->n_files; i++) n_bam += ctx->files[i].kind == 0 ? 1 : 0;
+  if (n_bam > sh.max_files) return ctx->fail(GCI_E_ARG, "sharded read set: %d BAM files, exchange sized for %d", n_bam, sh.max_files);
+  uint32_t* send_cnt = sh.send_cnt.as<uint32_t>();
+  unsigned long long* d_err = ctx->d_err.as<unsigned long long>();
+  ctx->counted_track = -1;
+  ctx->stage_begin(GCI_ST_JOIN);
+  xchg_begin_kernel<<<1, 128, 0, ctx->stream>>>(mine, send_cnt, (sh.max_files + 1) * sh.world);
+  GCI_LAUNCH_CHECK(ctx);
+  // dispatch 1: BAM winners to the read homes
+  int f = 0;
+  for (size_t i = 0; i < ctx->n_files; i++) {
+    FileTable& ft = ctx->files[i];
+    if (ft.kind != 0) continue;
+    BamFile& b = ctx->bam[ft.src];
+    if (ctx->n_reads) {
+      dispatch1_kernel<<<(ctx->n_reads + 255) / 256, 256, 0, ctx->stream>>>(
+          lay, peers, sh.rank, f, ctx->n_reads, ft.win.as<long long>(), b.ref_id.as<int32_t>(), b.ref_start.as<int32_t>(),
+          b.ref_end.as<int32_t>(), b.qlen.as<int32_t>(), ctx->highq.as<uint8_t>(), send_cnt, d_err);
+      GCI_LAUNCH_CHECK(ctx);
+    }
+    f++;
+  }
+  xchg_signal_kernel<<<1, 32, 0, ctx->stream>>>(lay, peers, sh.rank, 0, n_bam, send_cnt);
+  GCI_LAUNCH_CHECK(ctx);
+  xchg_wait_kernel<<<1, 32, 0, ctx->stream>>>(lay, mine, 0, d_err);
+  GCI_LAUNCH_CHECK(ctx);
+  // home: merge the inbox rows per BAM file, then join all files of the home reads
+  HomeArgs ha;
+  memset(&ha, 0, sizeof ha);
+  ha.n_files = (int)ctx->n_files;
+  f = 0;
+  const size_t nh = std::max<uint32_t>(1, sh.n_home);
+  const XRow1* row0 = reinterpret_cast<const XRow1*>(mine + lay.rows1_base());
+  for (size_t i = 0; i < ctx->n_files; i++) {
+    FileTable& ft = ctx->files[i];
+    HomeFile& hf = ha.f[i];
+    if (ft.kind == 0) {
+      GCI_TRY(ctx->ensure(sh.hwin[f], 8 * nh));
+      GCI_CUDA_TRY(ctx, cudaMemsetAsync(sh.hwin[f].p, 0xff, 8 * nh, ctx->stream));
+      const long long rows = lay.cap1 * (long long)lay.world;
+      merge1_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(lay, mine, f, sh.hwin[f].as<long long>(),
+                                                                            sh.hq_home.as<uint8_t>());
+      GCI_LAUNCH_CHECK(ctx);
+      hf.win = sh.hwin[f].as<long long>();
+      hf.c = &row0->contig; hf.s = &row0->start; hf.e = &row0->end; hf.q = &row0->qlen;
+      hf.stride = (int)(sizeof(XRow1) / 4);
+      f++;
+    } else {
+      // a table indexed by home read: the PAF election over home-local ids (or a caller's table with such ids)
+      hf.win = ft.win.as<long long>();
+      hf.c = ft.ref_id.as<int32_t>(); hf.s = ft.start.as<int32_t>(); hf.e = ft.end.as<int32_t>(); hf.q = ft.qlen.as<int32_t>();
+      hf.stride = 1;
+    }
+  }
+  const size_t slots = (size_t)std::max<int64_t>(1, sh.surv_slots);
+  GCI_TRY(ctx->ensure(ctx->surv_contig, 4 * slots));
+  GCI_TRY(ctx->ensure(ctx->surv_start, 4 * slots));
+  GCI_TRY(ctx->ensure(ctx->surv_end, 4 * slots));
+  BucketArgs bk;
+  memset(&bk, 0, sizeof bk);
+  if (track >= 0) GCI_TRY(gci_depth_prepare(ctx, track, flank_len, &bk));
+  if (sh.n_home) {
+    home_join_kernel<<<(sh.n_home + 255) / 256, 256, 0, ctx->stream>>>(
+        lay, peers, sh.rank, ha, sh.n_home, sh.hq_home.as<uint8_t>(), op, sh.d_owner.as<int32_t>(), ctx->n_contigs,
+        send_cnt, d_err + 2, d_err);
+    GCI_LAUNCH_CHECK(ctx);
+  }
+  xchg_signal_kernel<<<1, 32, 0, ctx->stream>>>(lay, peers, sh.rank, 1, n_bam, send_cnt);
+  GCI_LAUNCH_CHECK(ctx);
+  xchg_wait_kernel<<<1, 32, 0, ctx->stream>>>(lay, mine, 1, d_err);
+  GCI_LAUNCH_CHECK(ctx);
+  // owner: the survivors that arrived, their depth events counted on the way
+  consume2_kernel<<<(unsigned)((sh.surv_slots + 255) / 256), 256, 0, ctx->stream>>>(
+      lay, mine, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(), bk);
+  GCI_LAUNCH_CHECK(ctx);
+  ctx->stage_end();
+  if (track >= 0) {
+    ctx->counted_track = track;
+    ctx->counted_flank = flank_len;
+  }
+  return GCI_OK;
+}
+
+void gci_shard_destroy_internal(gci_ctx* ctx) {
+  gci_ctx::Shard& sh = ctx->shard;
+  for (int r = 0; r < GCI_MAX_RANKS; r++) {
+    if (sh.peer[r] && sh.mapped[r]) cudaIpcCloseMemHandle(sh.peer[r]);
+    sh.peer[r] = nullptr;
+    sh.mapped[r] = false;
+  }
+  cudaGetLastError();
+  for (DevBuf* d : {&sh.d_owner, &sh.area, &sh.send_cnt, &sh.hq_home}) ctx->release(*d);
+  for (auto& d : sh.hwin) ctx->release(d);
+  sh.on = sh.opened = false;
+}
+
+extern "C" {
+
+// contig owners and this rank's place among `world` ranks; gate_selected[n_contigs] (NULL = the contigs given to
+// gci_set_contigs) = every contig selected by --chrs on ANY rank: the gates and the PAF election must see them all.
+// Call after gci_set_contigs (whose `selected` then means: selected AND owned by this rank).
+int gci_shard_config(gci_ctx* ctx, int32_t rank, int32_t world, const int32_t* contig_owner, const uint8_t* gate_selected) {
+  if (!ctx || world < 1 || world > GCI_MAX_RANKS || rank < 0 || rank >= world || !contig_owner) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->n_contigs <= 0) return ctx->fail(GCI_E_ARG, "gci_shard_config before gci_set_contigs");
+  ctx->epoch++;
+  gci_ctx::Shard& sh = ctx->shard;
+  for (int c = 0; c < ctx->n_contigs; c++) {
+    if (contig_owner[c] < 0 || contig_owner[c] >= world) return ctx->fail(GCI_E_ARG, "contig %d has owner %d", c, contig_owner[c]);
+    if (ctx->selected[c] && contig_owner[c] != rank)
+      return ctx->fail(GCI_E_ARG, "contig %d is selected here but owned by rank %d", c, contig_owner[c]);
+  }
+  sh.rank = rank;
+  sh.world = world;
+  sh.owner.assign(contig_owner, contig_owner + ctx->n_contigs);
+  GCI_TRY(gci_h2d(ctx, sh.d_owner, contig_owner, 4 * (size_t)ctx->n_contigs));
+  if (gate_selected) GCI_TRY(gci_h2d(ctx, ctx->d_gate_sel, gate_selected, (size_t)ctx->n_contigs));
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  sh.on = true;
+  sh.n_home = ctx->n_reads > (uint32_t)rank ? (ctx->n_reads - rank + world - 1) / world : 0;
+  return GCI_OK;
+}
+
+// this rank's exchange area for read sets of up to max_reads reads and max_bam_files BAM files per read type; `out`
+// (optional) receives its CUDA IPC handle for the other processes
+int gci_shard_alloc(gci_ctx* ctx, uint32_t max_reads, int32_t max_bam_files, gci_ipc_handle* out) {
+  if (!ctx || max_bam_files < 1 || max_bam_files > GCI_MAX_FILES) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  gci_ctx::Shard& sh = ctx->shard;
+  if (!sh.on) return ctx->fail(GCI_E_ARG, "gci_shard_alloc before gci_shard_config");
+  ctx->epoch++;
+  sh.opened = false;
+  sh.max_files = max_bam_files;
+  sh.cap1 = sh.cap2 = ((int64_t)max_reads + sh.world - 1) / sh.world + 1;
+  sh.surv_slots = sh.cap2 * sh.world;
+  const XLayout lay = make_layout(ctx);
+  if (2LL * lay.files * lay.world * lay.cap1 >= (1LL << 32)) return ctx->fail(GCI_E_ARG, "exchange area: too many rows");
+  sh.area_bytes = (size_t)lay.total();
+  GCI_TRY(ctx->ensure(sh.area, sh.area_bytes));
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(sh.area.p, 0, (size_t)lay.rows1_base(), ctx->stream));   // header: epoch, flags, counts
+  GCI_TRY(ctx->ensure(sh.send_cnt, 4 * (size_t)(sh.max_files + 1) * sh.world));
+  GCI_TRY(ctx->ensure(sh.hq_home, (size_t)sh.cap1 + 16));
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(gci_ipc_handle), "IPC handle does not fit");
+    memset(out, 0, sizeof *out);
+    cudaIpcMemHandle_t h;
+    GCI_CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, sh.area.p));
+    memcpy(out, &h, sizeof h);
+  }
+  return GCI_OK;
+}
+
+void* gci_shard_area(gci_ctx* ctx) { return ctx ? ctx->shard.area.p : nullptr; }
+
+// map the peers' areas: handles[r] = what rank r got from gci_shard_alloc (same max_reads / max_bam_files everywhere)
+int gci_shard_open(gci_ctx* ctx, const gci_ipc_handle* handles) {
+  if (!ctx || !handles) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  gci_ctx::Shard& sh = ctx->shard;
+  if (!sh.on || !sh.area.p) return ctx->fail(GCI_E_ARG, "gci_shard_open before gci_shard_alloc");
+  ctx->epoch++;
+  for (int r = 0; r < sh.world; r++) {
+    if (r == sh.rank) { sh.peer[r] = sh.area.p; sh.mapped[r] = false; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, &handles[r], sizeof h);
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return ctx->fail(GCI_E_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+    }
+    sh.peer[r] = p;
+    sh.mapped[r] = true;
+  }
+  sh.opened = true;
+  return GCI_OK;
+}
+
+// contexts of ONE process (several "ranks" on the GPUs this process can address; tests): areas[r] = gci_shard_area
+// of rank r's context
+int gci_shard_attach(gci_ctx* ctx, void* const* areas) {
+  if (!ctx || !areas) return GCI_E_ARG;
+  gci_ctx::Shard& sh = ctx->shard;
+  if (!sh.on || !sh.area.p) return ctx->fail(GCI_E_ARG, "gci_shard_attach before gci_shard_alloc");
+  ctx->epoch++;
+  for (int r = 0; r < sh.world; r++) {
+    if (!areas[r]) return ctx->fail(GCI_E_ARG, "gci_shard_attach: no area for rank %d", r);
+    sh.peer[r] = r == sh.rank ? sh.area.p : areas[r];
+    sh.mapped[r] = false;
+  }
+  sh.opened = true;
+  return GCI_OK;
+}
+
+}  // extern "C"

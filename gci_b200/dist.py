@@ -1,12 +1,11 @@
 """Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink/NVSwitch; gloo on CPU
 for tests).  Contigs shard across ranks; the only exchanges of the path are
 
-  * exchange_file_tables(): all-gather of the compact per-file winner tables before the cross-file
-    join, because the join is keyed by read, not by contig (multi-file read sets only);
+  * the read-set exchange of a sharded run (winners to the read homes, survivors to the contig owners): inside
+    libgci_cuda.so over NVLink peer memory (csrc/shard.cu, host side gci_b200/sharded.py) — not here;
   * genome_row(): all-reduce of (sum depth, sum length, curated-contig count) and all-gather of the
     curated lengths for the genome-level N50 / GCI row (GCI.py:572-587, :862-868).
 
-Message sizes are KB..MB: latency-bound, no custom kernel is warranted.
 """
 from __future__ import annotations
 
@@ -125,16 +124,6 @@ def assign_contigs(lengths, weights, world):
         owner[i] = r
         load[r] += (weights[i] if weights is not None else 0) + lengths[i]
     return owner
-
-
-def exchange_file_tables(tables):
-    """tables: per file, the tuple (read_id, contig, start, end, qlen, highq) of THIS rank's winners
-    (Context.fetch_file_table).  Returns the same per file with every rank's rows merged; a read that won on
-    two ranks (duplicate primary names on different contigs) keeps the row of the higher contig index, which is
-    the reference's fetch order (GCI.py:260-269); high-quality marks are OR-ed per read."""
-    from .sharded import merge_tables
-    gathered = [tuple(np.concatenate(allgather_varlen(np.ascontiguousarray(c))) for c in cols) for cols in tables]
-    return merge_tables([gathered])
 
 
 _ROW_CAP = 2048

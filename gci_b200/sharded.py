@@ -1,85 +1,74 @@
-"""Contig-sharded filter -> depth for multi-GPU runs.
+"""Host side of a read set sharded over several GPUs (libgci_cuda's shard.cu does the exchange).
 
-Each rank owns a set of contigs and receives only the BAM records of those contigs.  Gates and the
-last-record-wins dedup are local.  The cross-file join is keyed by READ (a read aligned to different
-contigs by two aligners must be dropped, GCI.py:296-297), so the per-file winner tables are exchanged
-before the join: every rank then evaluates the join for all reads and accumulates depth only on the
-contigs it owns.  PAF files are small (GCI.py:211-254 needs all lines of a read to elect its primary
-target), so every rank runs the PAF leg on the whole file.
+Contigs have an owner rank (LPT over their lengths, `dist.assign_contigs`), reads a home rank (read id % world).
+The host only DEALS the decoded records:
 
-Two phases so that the exchange can be NCCL (`dist.exchange_file_tables`) or, in tests, a plain merge:
+    shard_bam(table, plan)   records lying on the contigs this rank owns          (global read / contig ids)
+    shard_paf(table, plan)   lines of the reads this rank is home to, read ids divided by world (home-local ids)
 
-    tables = local_tables(ctx, ...)            # phase 1, per rank
-    merged = exchange(tables)                  # all ranks' rows per file
-    n_surv = join_and_depth(ctx, merged, ...)  # phase 2, per rank
+Everything else — PAF election, gates, the two all-to-all dispatches over NVLink peer memory (winners to the read
+homes, survivors to the contig owners), merge, join, depth, scan, score — runs inside `Context.pipeline`.
+Nothing here touches alignment data with numpy beyond those two selections.
 """
 from __future__ import annotations
 
+from dataclasses import dataclass
+
 import numpy as np
 
-from ._lib import Context, NO_FLAGS
+from .records import AlnTable, PafTable
+
+_PAF_COLS = ("read_id", "qlen", "qstart", "qend", "ref_id", "tstart", "tend", "nmatch", "alnlen", "mapq")
 
 
-def owned_mask(n_contigs, owner, rank, chrs_selected=None):
-    own = np.array([owner[c] == rank for c in range(n_contigs)], dtype=bool)
-    if chrs_selected is not None:
-        own &= np.asarray(chrs_selected, dtype=bool)
-    return own
+@dataclass
+class ShardPlan:
+    rank: int
+    world: int
+    owner: list                 # owner[contig] = rank
+    selected: np.ndarray        # bool[n_contigs]: contigs of the run (--chrs), on any rank
+
+    @property
+    def owned(self):
+        """contigs this rank stores depth for: selected AND owned"""
+        return self.selected & (np.asarray(self.owner) == self.rank)
 
 
-def local_tables(ctx: Context, lengths, name_rank, selected_all, owned, pafs, bams_local, n_reads, map_qual=30,
-                 mq_cutoff=50, iden_percent=0.9, clip_percent=0.1):
-    """Phase 1.  `bams_local`: this rank's records (contigs it owns) of every BAM file, in CLI order.
-    Returns one table per file in join order (PAFs first): (read_id, contig, start, end, qlen, highq)."""
-    # PAF election must see every selected contig; BAM gates only this rank's contigs
-    out = []
-    if pafs:
-        ctx.set_contigs(lengths, selected_all)
-        ctx.set_name_rank(name_rank)
-        ctx.reads_begin(n_reads)
-        for t in pafs:
-            ctx.upload_paf(t)
-        ctx.filter(map_qual, mq_cutoff, iden_percent, clip_percent, 0.0)
-        out += [ctx.fetch_file_table(i) for i in range(len(pafs))]
-    ctx.set_contigs(lengths, owned)
+def make_plan(rank, world, lengths, selected=None):
+    from .dist import assign_contigs
+    n = len(lengths)
+    sel = np.ones(n, bool) if selected is None else np.asarray(selected, bool)
+    # unselected contigs hold no depth: they weigh nothing, the selected ones are balanced by length
+    owner = assign_contigs([int(l) if s else 0 for l, s in zip(lengths, sel)], None, world)
+    return ShardPlan(rank, world, owner, sel)
+
+
+def shard_bam(tab: AlnTable, plan: ShardPlan) -> AlnTable:
+    own = np.asarray(plan.owner) == plan.rank
+    rid = tab.ref_id
+    keep = np.flatnonzero((rid >= 0) & (rid < len(own)) & own[np.clip(rid, 0, len(own) - 1)])
+    return tab.take(keep)
+
+
+def shard_paf(tab: PafTable, plan: ShardPlan) -> PafTable:
+    keep = np.flatnonzero(tab.read_id % np.uint32(plan.world) == plan.rank)
+    cols = {k: getattr(tab, k)[keep] for k in _PAF_COLS}
+    cols["read_id"] = cols["read_id"] // np.uint32(plan.world)
+    return PafTable(*[cols[k] for k in _PAF_COLS])
+
+
+def configure(ctx, plan: ShardPlan, lengths, name_rank, max_reads, max_bam_files=2):
+    """contig table, owners and this rank's exchange area -> its CUDA IPC handle (uint8[64]).  The caller gathers
+    every rank's handle and calls ctx.shard_open (processes) or ctx.shard_attach (contexts of one process)."""
+    ctx.set_contigs(lengths, plan.owned)
     ctx.set_name_rank(name_rank)
-    if bams_local:
-        ctx.reads_begin(n_reads)
-        for t in bams_local:
-            ctx.upload_bam(t)
-        ctx.filter(map_qual, mq_cutoff, iden_percent, clip_percent, 0.0)
-        out += [ctx.fetch_file_table(i) for i in range(len(bams_local))]
-    return out
+    ctx.shard_config(plan.rank, plan.world, plan.owner, plan.selected)
+    return ctx.shard_alloc(max_reads, max_bam_files)
 
 
-def merge_tables(per_rank_tables):
-    """Single-process stand-in for dist.exchange_file_tables: per file, concatenate the ranks' rows; a read
-    present on several ranks keeps the row of the highest contig (the reference's fetch order)."""
-    n_files = len(per_rank_tables[0])
-    out = []
-    for f in range(n_files):
-        cols = [np.concatenate([rt[f][k] for rt in per_rank_tables]) for k in range(6)]
-        r, c = cols[0], cols[1]
-        if len(r):
-            order = np.lexsort((c, r))
-            rs = r[order]
-            last = np.ones(len(r), bool)
-            last[:-1] = rs[1:] != rs[:-1]
-            # high-quality marks are per read: OR over the rows that are dropped too
-            hq = np.zeros(int(r.max()) + 1, np.uint8)
-            np.maximum.at(hq, r, cols[5])
-            keep = order[last]
-            cols = [x[keep] for x in cols]
-            cols[5] = hq[cols[0]]
-        out.append(tuple(cols))
-    return out
-
-
-def join_and_depth(ctx: Context, merged, n_reads, track=0, ovlp_percent=0.9, flank_len=15, lo=NO_FLAGS, hi=NO_FLAGS):
-    """Phase 2: join over the exchanged tables, depth on the contigs this context owns."""
-    ctx.reads_begin(n_reads)
-    for r, c, s, e, q, h in merged:
-        ctx.upload_table(r, c, s, e, q, h)
-    n_surv = ctx.filter(0, 0, 0.0, 1.0, ovlp_percent)     # tables carry no gates of their own
-    ctx.depth(track, flank_len, lo, hi)
-    return n_surv
+def open_over_process_group(ctx, plan: ShardPlan, handle):
+    """all-gather the IPC handles over torch.distributed and map the peers' areas"""
+    from . import dist as D
+    handles = np.zeros((plan.world, 64), np.int64)
+    handles[plan.rank] = handle
+    ctx.shard_open(D.allreduce(handles, "sum").astype(np.uint8))

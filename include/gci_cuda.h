@@ -227,6 +227,26 @@ int gci_pipeline_row(gci_ctx* ctx, int32_t track, int32_t map_qual, int32_t mq_c
                      double dist_percent, int64_t* n_survivors, int64_t* n_intervals, int64_t* n50, int64_t* n_ctg,
                      int64_t* depth_sums, int64_t sum_len, int64_t cap, int64_t* rows);
 
+/* ---- multi-GPU: read sets sharded over the ranks (the reference's analogue is the Pool fan-out and
+   dict merge of GCI.py:257-301) -------------------------------------------------------------------------------------
+   Contigs have an owner rank, reads a home rank (read id % world).  A rank uploads
+     - the BAM records lying on the contigs it owns (global read ids, global contig ids), and
+     - the PAF lines of the reads it is home to, with HOME-LOCAL read ids (read id / world),
+   and gci_pipeline / gci_pipeline_row then run: PAF election and BAM gates locally -> every per-file winner goes to
+   its read's home over NVLink peer memory -> merge + join at the home (GCI.py:268-301) -> every survivor goes to the
+   owner of its contig -> depth, scan and score on the owned contigs.  n_survivors is then the number of survivors
+   among this rank's home reads (the global count is the sum over the ranks).
+   Call order: gci_set_contigs(selected = selected AND owned) -> gci_shard_config -> gci_shard_alloc (once, sized for
+   the largest read set) -> exchange the handles, gci_shard_open -> per read type gci_reads_begin(global read count),
+   uploads, gci_pipeline. */
+int gci_shard_config(gci_ctx* ctx, int32_t rank, int32_t world, const int32_t* contig_owner /* [n_contigs] */,
+                     const uint8_t* gate_selected /* [n_contigs] or NULL: contigs selected on ANY rank */);
+int gci_shard_alloc(gci_ctx* ctx, uint32_t max_reads, int32_t max_bam_files, gci_ipc_handle* out /* or NULL */);
+int gci_shard_open(gci_ctx* ctx, const gci_ipc_handle* handles /* [world] */);
+/* contexts of one process (tests; several GPUs driven by one process): areas[r] = gci_shard_area of rank r's context */
+void* gci_shard_area(gci_ctx* ctx);
+int gci_shard_attach(gci_ctx* ctx, void* const* areas /* [world] */);
+
 #ifdef __cplusplus
 }
 #endif

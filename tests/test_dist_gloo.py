@@ -1,4 +1,5 @@
-"""world_size-2 gloo test of the multi-GPU host logic (contig assignment, table exchange, genome row)."""
+"""world_size-2 gloo test of the multi-GPU host logic (contig assignment, dealing a read set by contig owner / read
+home, genome row)."""
 import os
 import subprocess
 import sys
@@ -19,15 +20,19 @@ WORKER = textwrap.dedent("""
     lens = [np.array([10, 7, 3]), np.array([8, 8])][rank]
     mean, nctg, all_len = D.genome_row([300, 500][rank], [100, 100][rank], [3, 2][rank], lens)
     assert abs(mean - 4.0) < 1e-12 and nctg == 5 and sorted(all_len.tolist()) == [3, 7, 8, 8, 10]
-    # table exchange: read 5 won on both ranks -> the higher contig wins; read ids stay unique
-    if rank == 0:
-        t = (np.array([1, 5], np.uint32), np.array([0, 0], np.int32), np.array([10, 20], np.int32),
-             np.array([110, 120], np.int32), np.array([100, 100], np.int32), np.array([1, 0], np.uint8))
-    else:
-        t = (np.array([5, 9], np.uint32), np.array([1, 1], np.int32), np.array([30, 40], np.int32),
-             np.array([130, 140], np.int32), np.array([100, 100], np.int32), np.array([0, 1], np.uint8))
-    (r, c, s, e, q, h), = D.exchange_file_tables([t])
-    assert r.tolist() == [1, 5, 9] and c.tolist() == [0, 1, 1] and s.tolist() == [10, 30, 40], (r, c, s)
+    # dealing a read set: records by contig owner, PAF lines by read home with home-local ids
+    from gci_b200 import sharded, synth
+    lengths = [50_000, 30_000, 20_000]
+    w = synth.make_genome(lengths, ["a", "b", "c"], coverage=10, seed=3, read_mean=3000, read_min=500, read_max=8000)
+    plan = sharded.make_plan(rank, world, lengths)
+    assert sorted(set(plan.owner)) == [0, 1]
+    bam, paf = sharded.shard_bam(w.bam, plan), sharded.shard_paf(w.paf, plan)
+    own = np.asarray(plan.owner) == rank
+    assert own[bam.ref_id].all() and bam.n_records == int(own[w.bam.ref_id].sum())
+    mine = w.paf.read_id %% 2 == rank
+    assert paf.n_records == int(mine.sum()) and np.array_equal(paf.read_id, w.paf.read_id[mine] // 2)
+    counts = D.allreduce(np.array([bam.n_records, paf.n_records], np.int64))
+    assert counts.tolist() == [w.bam.n_records, w.paf.n_records]
     assert D.allreduce(np.array([rank + 1.5]), "max").tolist() == [2.5]
     print("rank", rank, "ok")
 """)

@@ -336,45 +336,6 @@ def test_gpu_gzip_whole_track_one_pass(ctx):
     assert ctx.depth_gzip(0, 0, header=headers[0]).tobytes() == blob[off[0]:off[1]].tobytes()
 
 
-@pytest.mark.parametrize("seed", range(3))
-def test_contig_sharded_two_ranks_equal_single_gpu(seed):
-    """multi-file read set split over two 'ranks' by contig (two contexts on one GPU): the exchanged-table
-    join gives the single-GPU depth on every contig"""
-    from gci_b200._lib import Context
-    from gci_b200 import sharded
-    lengths = [150_000, 90_000, 60_000, 40_000]
-    d = synth.make_reads(synth.SynthSpec(lengths, coverage=20, seed=900 + seed, read_mean=6000, read_min=1000,
-                                         read_max=15000))
-    b1 = synth.drop_reads(d.bam, 0.03, seed)
-    b2 = synth.second_aligner(d, seed=seed + 5)
-    pafs = [synth.aln_to_paf(synth.second_aligner(d, seed=seed + 9))] if seed != 1 else []
-    names = d.contigs.names
-    want_d, want_s = O.filter_depth(pafs, [b1, b2], names, lengths)
-    owner = [0, 1, 1, 0]
-    rank_of = np.array(owner)
-    ctxs = [Context(0), Context(0)]
-    try:
-        per_rank = []
-        for rank, ctx in enumerate(ctxs):
-            local = [t.take(np.flatnonzero((t.ref_id >= 0) & (rank_of[np.maximum(t.ref_id, 0)] == rank)))
-                     for t in (b1, b2)]
-            per_rank.append(sharded.local_tables(ctx, lengths, _name_rank(names), np.ones(4, bool),
-                                                 sharded.owned_mask(4, owner, rank), pafs, local, d.n_reads))
-        merged = sharded.merge_tables(per_rank)
-        total = 0
-        for rank, ctx in enumerate(ctxs):
-            n_surv = sharded.join_and_depth(ctx, merged, d.n_reads)
-            assert n_surv == len(want_s)             # every rank evaluates the join for all reads
-            for c in range(4):
-                if owner[c] == rank:
-                    assert np.array_equal(ctx.fetch_depth(0, c).astype(np.int64), want_d[c]), (rank, c)
-                    total += 1
-        assert total == 4
-    finally:
-        for c in ctxs:
-            c.close()
-
-
 def test_paf_election_known_cases(ctx):
     """PAF leg on the GPU: multi-block merge (touching blocks merge), longest target block with ties, equal scores
     decided by the contig NAME (not its index), query length of the first line, duplicates, two PAF files."""

@@ -1,0 +1,135 @@
+"""Read sets sharded over several ranks (csrc/shard.cu): contexts standing in for the ranks of a multi-GPU run — one
+host thread per rank, the exchange areas attached directly when the ranks share a process — must give, on the
+contigs each rank owns, exactly the depth / intervals / score terms of the C port on the whole read set.  With one
+visible GPU all ranks live on it (the peer stores become local stores, the protocol is the same); with several GPUs
+the ranks are spread over them, and tests/test_gpu_multi.py runs the real thing with one process per GPU."""
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import gci_oracle as O, c_oracle as CO
+from gci_b200 import sharded, synth
+
+pytestmark = pytest.mark.gpu
+
+GATES = dict(map_qual=30, mq_cutoff=50, iden_percent=0.9, clip_percent=0.1, ovlp_percent=0.9)
+
+
+def _run_ranks(world, fn):
+    """fn(rank) on one thread per rank; re-raises the first failure"""
+    errs = [None] * world
+    def wrap(r):
+        try:
+            fn(r)
+        except BaseException as e:                     # noqa: BLE001
+            errs[r] = e
+    ts = [threading.Thread(target=wrap, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for e in errs:
+        if e is not None:
+            raise e
+
+
+def _sharded_run(world, names, lengths, n_reads, pafs, bams, selected=None, steps=3, devices=None, op=0.9):
+    """-> per rank: dict(owned contigs, depth per owned contig, intervals, n50, nctg, sums, n_surv)"""
+    import torch
+    from gci_b200._lib import Context
+    n_dev = torch.cuda.device_count()
+    ctxs = [Context((devices or list(range(n_dev)))[r % n_dev] if n_dev else 0) for r in range(world)]
+    plans = [sharded.make_plan(r, world, lengths, selected) for r in range(world)]
+    rank_of = CO.name_rank(names)
+    out = [None] * world
+    try:
+        for r in range(world):
+            sharded.configure(ctxs[r], plans[r], lengths, rank_of, n_reads, max_bam_files=max(1, len(bams)))
+        areas = [c.shard_area() for c in ctxs]
+        for c in ctxs:
+            c.shard_attach(areas)
+
+        def one(r):
+            ctx, plan = ctxs[r], plans[r]
+            ctx.set_timing(False)                      # graph capture on the second step, replay on the third
+            ctx.reads_begin(n_reads)
+            for t in pafs:
+                ctx.upload_paf(sharded.shard_paf(t, plan))
+            for t in bams:
+                ctx.upload_bam(sharded.shard_bam(t, plan))
+            owned = np.flatnonzero(plan.owned)
+            for _ in range(steps):
+                n_surv, n_iv, n50, nctg, sums = ctx.pipeline(0, len(owned), flank_len=15, lo=-1, hi=0, dist_percent=0.005,
+                                                             **dict(GATES, ovlp_percent=op))
+            gs, ge, off = ctx.fetch_intervals(0, len(owned))
+            out[r] = dict(owned=owned, depth=[ctx.fetch_depth(0, int(c)) for c in owned], n_surv=n_surv,
+                          beds=[list(zip(gs[off[o]:off[o + 1]].tolist(), ge[off[o]:off[o + 1]].tolist()))
+                                for o in range(len(owned))],
+                          n50=n50, nctg=nctg, sums=sums, replays=ctx.graph_replays)
+
+        _run_ranks(world, one)
+    finally:
+        for c in ctxs:
+            c.close()
+    return out
+
+
+def _check(out, want_d, want_n, lengths, selected=None):
+    seen = []
+    assert sum(o["n_surv"] for o in out) == want_n
+    for o in out:
+        for k, c in enumerate(o["owned"].tolist()):
+            assert np.array_equal(o["depth"][k].astype(np.int64), want_d[c]), f"depth differs on contig {c}"
+            bed = CO.collapse(want_d[c], -1, 0, 15, 0)
+            assert o["beds"][k] == bed, f"intervals differ on contig {c}"
+            assert int(o["sums"][k]) == int(want_d[c].sum())
+            assert int(o["n50"][k]) == O.n50(O.complement_lengths(bed, int(lengths[c]), 15))
+            seen.append(c)
+    sel = range(len(lengths)) if selected is None else np.flatnonzero(selected).tolist()
+    assert sorted(seen) == list(sel)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_sharded_bam_plus_paf_equals_whole_read_set(world):
+    """configs[2] shape at 1/100 size: BAM + PAF, reads of the second aligner on other contigs (other owners),
+    split / alternative / tied PAF lines; three steps (eager, captured, replayed: both inbox parities)."""
+    lengths = [x // 100 for x in synth.CHM13_LENGTHS]
+    w = synth.make_genome(lengths, synth.CHM13_NAMES, coverage=25, seed=31 + world)
+    want_d, _, want_n = CO.hot_path([w.bam], lengths, w.n_reads, threads=8, pafs=[w.paf], names=w.contigs.names, **GATES)
+    out = _sharded_run(world, w.contigs.names, lengths, w.n_reads, [w.paf], [w.bam])
+    _check(out, want_d, want_n, lengths)
+    assert all(o["replays"] >= 2 for o in out)
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_sharded_three_files_with_duplicates_and_chrs(seed):
+    """PAF + two BAMs (delete-then-re-add in three-file joins), reads with primary records on two contigs of
+    DIFFERENT owners (the higher contig wins, GCI.py:268-270), --chrs leaving contigs out on every rank."""
+    lengths = [150_000, 90_000, 60_000, 40_000, 30_000]
+    d = synth.make_reads(synth.SynthSpec(lengths, coverage=20, seed=900 + seed, read_mean=6000, read_min=1000,
+                                         read_max=15000))
+    b1 = synth.drop_reads(d.bam, 0.03, seed)
+    b2 = synth.second_aligner(d, seed=seed + 5)
+    # duplicate primary names: a tenth of the reads of contig 0 also get a passing record on another contig
+    src = np.flatnonzero((b1.ref_id == 0) & (b1.flag & 0x904 == 0))[::10]
+    dup = b1.take(src)
+    dup.ref_id[:] = np.where(np.arange(len(src)) % 2 == 0, 3, 1)
+    dup.ref_start[:] = np.minimum(dup.ref_start, np.asarray(lengths)[dup.ref_id] - dup.ref_len() - 1).clip(0)
+    both = synth.concat_aln([b1, dup])
+    b1 = both.take(np.lexsort((both.ref_start, both.ref_id)))
+    paf = synth.aln_to_paf(synth.second_aligner(d, seed=seed + 9))
+    names = d.contigs.names
+    sel = np.array([True, True, seed == 0, True, True])
+    want_d, want_s = O.filter_depth([paf], [b1, b2], names, lengths, sel, ovlp_percent=0.8)
+    out = _sharded_run(2, names, lengths, d.n_reads, [paf], [b1, b2], selected=sel, op=0.8)
+    _check(out, want_d, len(want_s), lengths, sel)
+
+
+def test_sharded_single_bam_no_join():
+    """one file: the join is a pass-through (GCI.py:300-301), the exchange still moves every winner and survivor"""
+    lengths = [120_000, 80_000, 50_000]
+    d = synth.make_reads(synth.SynthSpec(lengths, coverage=15, seed=77, read_mean=5000, read_min=800, read_max=12000))
+    want_d, want_s = O.filter_depth([], [d.bam], d.contigs.names, lengths)
+    out = _sharded_run(3, d.contigs.names, lengths, d.n_reads, [], [d.bam])
+    _check(out, want_d, len(want_s), lengths)
