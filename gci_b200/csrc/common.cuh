@@ -336,19 +336,19 @@ struct BucketArgs {
   long long* sums;         // per-contig depth sums
 };
 
-// count the two events of one survivor (c < 0: none) into the tile table and add its slice length to the
-// contig's depth sum.  Block-collective (every thread of the CTA must call it, blockDim.x <= 1024): the depth sums
-// and the survivor count are reduced per warp, then per CTA in shared memory, so that a launch over millions of
-// reads sends one atomic per CTA to those few hot addresses instead of one per warp.
-// count != NULL: also adds the number of threads with `have` to *count.
-__device__ __forceinline__ void bucket_count_one(const BucketArgs& bk, int32_t c, int32_t s, int32_t e, bool have,
-                                                 unsigned long long* count) {
-  __shared__ long long s_cov[32];
-  __shared__ int32_t s_ctg[32];
-  __shared__ int s_have[32];
-  long long covered = 0;
-  if (bk.tile_ps) {
-    if (c >= 0) {
+// The two events of one survivor (c < 0: none) go to the tile table with one 64-bit atomic each; its slice length
+// goes to the contig's depth sum and `have` to the survivor count.  Those two land on a handful of hot addresses, so
+// they are accumulated per WARP in registers across the iterations of a grid-stride loop (consecutive reads sit on
+// the same contig) and flushed when the contig changes and at the end: a launch over millions of reads sends a few
+// thousand atomics to them instead of one per warp and iteration.  Warp-collective: every lane calls add / flush.
+struct WarpSums {
+  int32_t cur_c;
+  long long cur_sum;
+  int n_have;
+  __device__ __forceinline__ void init() { cur_c = -1; cur_sum = 0; n_have = 0; }
+  __device__ __forceinline__ void add(const BucketArgs& bk, int32_t c, int32_t s, int32_t e, bool have) {
+    long long covered = 0;
+    if (bk.tile_ps && c >= 0) {
       const Slice sl = survivor_slice(c, s, e, bk.fl, bk.len, bk.tile_off);
       if (sl.ok) {
         atomicAdd(&bk.tile_ps[sl.tile_a].x, EV_PLUS);
@@ -357,39 +357,32 @@ __device__ __forceinline__ void bucket_count_one(const BucketArgs& bk, int32_t c
       } else {
         c = -1;
       }
-    }
-  } else {
-    c = -1;
-  }
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, n_wp = (blockDim.x + 31) >> 5;
-  // sum of depth per contig = sum of slice lengths; aggregate per warp when the warp agrees on a contig
-  const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
-  int32_t c0 = -1;
-  long long t = 0;
-  if (act) {
-    const int leader = __ffs(act) - 1;
-    c0 = __shfl_sync(0xffffffffu, c, leader);
-    const bool uniform = __all_sync(0xffffffffu, c < 0 || c == c0);
-    if (uniform) {
-      t = warp_sum_ll(covered);
     } else {
-      if (c >= 0) atomicAdd((unsigned long long*)(bk.sums + c), (unsigned long long)covered);
-      c0 = -1;
+      c = -1;
+    }
+    n_have += __popc(__ballot_sync(0xffffffffu, have));
+    const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
+    if (act == 0) return;
+    const int32_t c0 = __shfl_sync(0xffffffffu, c, __ffs(act) - 1);
+    if (__all_sync(0xffffffffu, c < 0 || c == c0)) {
+      const long long t = warp_sum_ll(covered);
+      if (c0 != cur_c) {
+        flush_sum(bk);
+        cur_c = c0;
+      }
+      cur_sum += t;
+    } else if (c >= 0) {                      // a warp straddling two contigs: rare, straight to memory
+      atomicAdd((unsigned long long*)(bk.sums + c), (unsigned long long)covered);
     }
   }
-  const unsigned hv = __ballot_sync(0xffffffffu, have);
-  if (lane == 0) { s_cov[wp] = t; s_ctg[wp] = c0; s_have[wp] = __popc(hv); }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int n_have = 0;
-    for (int i = 0; i < n_wp; i++) {
-      n_have += s_have[i];
-      if (s_ctg[i] < 0) continue;
-      long long sum = s_cov[i];
-      for (int j = i + 1; j < n_wp; j++)
-        if (s_ctg[j] == s_ctg[i]) { sum += s_cov[j]; s_ctg[j] = -1; }
-      if (sum) atomicAdd((unsigned long long*)(bk.sums + s_ctg[i]), (unsigned long long)sum);
-    }
-    if (count && n_have) atomicAdd(count, (unsigned long long)n_have);
+  __device__ __forceinline__ void flush_sum(const BucketArgs& bk) {
+    if ((threadIdx.x & 31) == 0 && cur_c >= 0 && cur_sum)
+      atomicAdd((unsigned long long*)(bk.sums + cur_c), (unsigned long long)cur_sum);
+    cur_sum = 0;
   }
-}
+  __device__ __forceinline__ void flush(const BucketArgs& bk, unsigned long long* count) {
+    flush_sum(bk);
+    if ((threadIdx.x & 31) == 0 && count && n_have) atomicAdd(count, (unsigned long long)n_have);
+    n_have = 0;
+  }
+};

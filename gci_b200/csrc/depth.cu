@@ -17,11 +17,17 @@ int gci_scan_tile_pack(gci_ctx* ctx, ulonglong2* tile_ps, int64_t n);   // scan.
 // carried into it (high word: sum of all earlier nets; a contig's nets sum to zero, so the carry
 // restarts at 0 on every contig without any segmentation).
 
-__global__ void bucket_count_kernel(uint32_t n_reads, const int32_t* __restrict__ sc, const int32_t* __restrict__ ss,
-                                    const int32_t* __restrict__ se, BucketArgs bk) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in = r < n_reads;
-  bucket_count_one(bk, in ? sc[r] : -1, in ? ss[r] : 0, in ? se[r] : 0, false, nullptr);
+__global__ void __launch_bounds__(256)
+bucket_count_kernel(uint32_t n_reads, const int32_t* __restrict__ sc, const int32_t* __restrict__ ss,
+                    const int32_t* __restrict__ se, BucketArgs bk) {
+  WarpSums ws;
+  ws.init();
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n_reads; base += gridDim.x * blockDim.x) {
+    const uint32_t r = base + threadIdx.x;
+    const bool in = r < n_reads;
+    ws.add(bk, in ? sc[r] : -1, in ? ss[r] : 0, in ? se[r] : 0, false);
+  }
+  ws.flush(bk, nullptr);
 }
 
 __global__ void bucket_fill_kernel(uint32_t n_reads, const int32_t* __restrict__ sc, const int32_t* __restrict__ ss,
@@ -466,7 +472,7 @@ int gci_depth_enqueue(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo
     BucketArgs bk;
     GCI_TRY(gci_depth_prepare(ctx, track, flank_len, &bk));
     if (nr && nt) {
-      bucket_count_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(
+      bucket_count_kernel<<<(unsigned)std::min<int64_t>(((int64_t)nr + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
           nr, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(), bk);
       GCI_LAUNCH_CHECK(ctx);
     }

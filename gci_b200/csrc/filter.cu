@@ -151,6 +151,28 @@ struct GateArgs {
   unsigned long long* err;
 };
 
+// (double)a / (double)b <= lim and >= lim exactly as fp64 div.rn decides them (Python int / int is correctly rounded,
+// GCI.py:165), without paying for an fp64 division on almost every record: a single-precision quotient carries a
+// relative error below 2^-21 here (two conversions + one division, each within 2^-23), so unless it lies within
+// 2^-18 of the limit the comparison is already decided; only the few records on the boundary divide in fp64.
+// |a|, b < 2^40; b > 0.
+__device__ __forceinline__ bool ratio_le(long long a, long long b, double lim) {
+  const float q = __fdividef((float)a, (float)b);
+  const float l = (float)lim;
+  const float tol = fabsf(l) * 3.9e-6f + 1e-30f;
+  if (q < l - tol) return true;
+  if (q > l + tol) return false;
+  return (double)a / (double)b <= lim;
+}
+__device__ __forceinline__ bool ratio_ge(long long a, long long b, double lim) {
+  const float q = __fdividef((float)a, (float)b);
+  const float l = (float)lim;
+  const float tol = fabsf(l) * 3.9e-6f + 1e-30f;
+  if (q > l + tol) return true;
+  if (q < l - tol) return false;
+  return (double)a / (double)b >= lim;
+}
+
 __device__ __forceinline__ void gate_one(const GateArgs& g, int64_t r, uint32_t sMx, uint32_t sI, uint32_t sD,
                                          uint32_t sN, uint32_t sS) {
   // every column of the record is requested up front: behind the early returns below the loads would be issued
@@ -180,14 +202,14 @@ __device__ __forceinline__ void gate_one(const GateArgs& g, int64_t r, uint32_t 
     atomicMin(g.err + 1, (unsigned long long)r);
     return;
   }
-  if (!((double)S / (double)d1 <= g.cp)) return;                 // :165, fp64 div.rn like Python int/int
+  if (!ratio_le(S, d1, g.cp)) return;                            // :165, fp64 div.rn like Python int/int
   const long long d2 = Mx + I + D;
   if (d2 == 0) {
     atomicOr(g.err, 4ull);
     atomicMin(g.err + 1, (unsigned long long)r);
     return;
   }
-  if (!((double)(Mx - mm) / (double)d2 >= g.ip)) return;
+  if (!ratio_ge(Mx - mm, d2, g.ip)) return;
   if (q >= g.n_reads) return;
   // fetch order = contigs in header order, file order inside: the later record wins (:166, :269)
   atomicMax(g.win + q, ((long long)c << 32) | (long long)r);
@@ -596,65 +618,72 @@ struct JoinArgs {
   int n_files;
 };
 
-__global__ void join_kernel(JoinArgs a, uint32_t n_reads, const uint8_t* __restrict__ highq, double op,
-                            int32_t* __restrict__ s_contig, int32_t* __restrict__ s_start, int32_t* __restrict__ s_end,
-                            unsigned long long* __restrict__ count, unsigned long long* __restrict__ err,
-                            BucketArgs bk) {
-  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  bool have = false;
-  int32_t c = -1, s = 0, e = 0;
-  if (r < n_reads) {
-    const long long k0 = a.f[0].win[r];
-    if (a.n_files == 1) {                                         // :300-301
-      if (k0 >= 0) {
-        const uint32_t i = (uint32_t)(k0 & 0xffffffffll);
-        have = true;
-        c = a.f[0].ref_id[i]; s = a.f[0].start[i]; e = a.f[0].end[i];
-      }
-    } else {
-      bool comm = true;
-      for (int f = 0; f < a.n_files; f++) comm = comm && (a.f[f].win[r] >= 0);          // :274-277
-      const bool hq = highq[r] != 0;
-      if (k0 >= 0 && (hq || comm)) {                                                     // :279-280
-        const uint32_t i = (uint32_t)(k0 & 0xffffffffll);
-        have = true;
-        c = a.f[0].ref_id[i]; s = a.f[0].start[i]; e = a.f[0].end[i];
-      }
-      for (int f = 1; f < a.n_files; f++) {                                               // :281-299
-        const long long k = a.f[f].win[r];
-        if (k < 0) continue;
-        const uint32_t i = (uint32_t)(k & 0xffffffffll);
-        const int32_t cf = a.f[f].ref_id[i], sf = a.f[f].start[i], ef = a.f[f].end[i];
-        if (have) {
-          if (cf == c) {
-            const long long ov = (long long)min(ef, e) - (long long)max(sf, s);
-            const int32_t ql = a.f[f].qlen[i];
-            if (ql == 0) {                                                                // ZeroDivisionError :292
-              atomicOr(err, 8ull);
-              atomicMin(err + 1, (unsigned long long)r);
-              have = false;
-            } else if ((double)ov / (double)ql < op) {
-              have = false;
-            } else {
-              s = max(sf, s);
-              e = min(ef, e);
-            }
-          } else {
-            have = false;
-          }
-        } else if (hq) {
+// persistent grid: a warp walks 32 consecutive reads per round, so its depth-sum / survivor-count partials stay in
+// registers (WarpSums) until the contig changes
+__global__ void __launch_bounds__(256)
+join_kernel(JoinArgs a, uint32_t n_reads, const uint8_t* __restrict__ highq, double op,
+            int32_t* __restrict__ s_contig, int32_t* __restrict__ s_start, int32_t* __restrict__ s_end,
+            unsigned long long* __restrict__ count, unsigned long long* __restrict__ err, BucketArgs bk) {
+  WarpSums ws;
+  ws.init();
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n_reads; base += gridDim.x * blockDim.x) {
+    const uint32_t r = base + threadIdx.x;
+    bool have = false;
+    int32_t c = -1, s = 0, e = 0;
+    if (r < n_reads) {
+      const long long k0 = a.f[0].win[r];
+      if (a.n_files == 1) {                                         // :300-301
+        if (k0 >= 0) {
+          const uint32_t i = (uint32_t)(k0 & 0xffffffffll);
           have = true;
-          c = cf; s = sf; e = ef;
+          c = a.f[0].ref_id[i]; s = a.f[0].start[i]; e = a.f[0].end[i];
+        }
+      } else {
+        bool comm = true;
+        for (int f = 0; f < a.n_files; f++) comm = comm && (a.f[f].win[r] >= 0);          // :274-277
+        const bool hq = highq[r] != 0;
+        if (k0 >= 0 && (hq || comm)) {                                                     // :279-280
+          const uint32_t i = (uint32_t)(k0 & 0xffffffffll);
+          have = true;
+          c = a.f[0].ref_id[i]; s = a.f[0].start[i]; e = a.f[0].end[i];
+        }
+        for (int f = 1; f < a.n_files; f++) {                                               // :281-299
+          const long long k = a.f[f].win[r];
+          if (k < 0) continue;
+          const uint32_t i = (uint32_t)(k & 0xffffffffll);
+          const int32_t cf = a.f[f].ref_id[i], sf = a.f[f].start[i], ef = a.f[f].end[i];
+          if (have) {
+            if (cf == c) {
+              const long long ov = (long long)min(ef, e) - (long long)max(sf, s);
+              const int32_t ql = a.f[f].qlen[i];
+              if (ql == 0) {                                                                // ZeroDivisionError :292
+                atomicOr(err, 8ull);
+                atomicMin(err + 1, (unsigned long long)r);
+                have = false;
+              } else if ((double)ov / (double)ql < op) {
+                have = false;
+              } else {
+                s = max(sf, s);
+                e = min(ef, e);
+              }
+            } else {
+              have = false;
+            }
+          } else if (hq) {
+            have = true;
+            c = cf; s = sf; e = ef;
+          }
         }
       }
+      s_contig[r] = have ? c : -1;
+      s_start[r] = s;
+      s_end[r] = e;
     }
-    s_contig[r] = have ? c : -1;
-    s_start[r] = s;
-    s_end[r] = e;
+    // the survivor count, and for gci_pipeline the depth events of the survivor, are counted right here (no second
+    // pass over the survivors)
+    ws.add(bk, have ? c : -1, s, e, have);
   }
-  // the survivor count, and for gci_pipeline the depth events of the survivor, are counted right here (no second
-  // pass over the survivors); block-collective
-  bucket_count_one(bk, have ? c : -1, s, e, have, count);
+  ws.flush(bk, count);
 }
 
 // ================================================================================================
@@ -999,67 +1028,91 @@ __device__ void paf_elect_read(uint32_t r, int g, const Get& get, const int32_t*
 }
 
 // one thread per read: no kept line -> absent; ONE kept line (almost every read) -> that line is the result;
-// more -> the read goes to the list of paf_elect_multi_kernel, so no warp waits for a lane walking a group
-__global__ void paf_elect_kernel(uint32_t n_reads, PafSet ps, const int32_t* __restrict__ off,
-                                 const int32_t* __restrict__ idx, PafTableOut o, int32_t* __restrict__ multi,
-                                 unsigned int* __restrict__ n_multi, unsigned long long* __restrict__ err) {
+// more -> the read is left for paf_elect_multi_kernel (its slot of `multi` says so), so no warp waits for a lane
+// walking a group
+constexpr int PAF_ELECT_THREADS = 128;
+__global__ void __launch_bounds__(PAF_ELECT_THREADS)
+paf_elect_kernel(uint32_t n_reads, PafSet ps, const int32_t* __restrict__ off, const int32_t* __restrict__ idx,
+                 PafTableOut o, uint8_t* __restrict__ multi, unsigned long long* __restrict__ err) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  int g = 0;
-  int32_t a0 = 0;
-  if (r < n_reads) {
-    a0 = off[r];
-    g = off[r + 1] - a0;
+  if (r >= n_reads) return;
+  const int32_t a0 = off[r], g = off[r + 1] - a0;
+  multi[r] = g >= 2;
+  if (g == 0) o.win[r] = -1;
+  if (g != 1) return;
+  const int32_t line = idx[a0];
+  int k = 0;
+  while (k + 1 < ps.n && (int64_t)line >= ps.off[k + 1]) k++;
+  const int64_t i = (int64_t)line - ps.off[k];
+  const PafCols& p = ps.f[k];
+  const int32_t ql = p.qlen[i];
+  if (ql == 0) {                             // ZeroDivisionError :247
+    atomicOr(err, 32ull);
+    atomicMin(err + 1, (unsigned long long)r);
+    o.win[r] = -1;
+    return;
   }
-  if (r < n_reads && g == 0) o.win[r] = -1;
-  if (g == 1) {
-    const int32_t line = idx[a0];
-    int k = 0;
-    while (k + 1 < ps.n && (int64_t)line >= ps.off[k + 1]) k++;
-    const int64_t i = (int64_t)line - ps.off[k];
-    const PafCols& p = ps.f[k];
-    const int32_t ql = p.qlen[i];
-    if (ql == 0) {                           // ZeroDivisionError :247
-      atomicOr(err, 32ull);
-      atomicMin(err + 1, (unsigned long long)r);
-      o.win[r] = -1;
-    } else {
-      o.ref[r] = p.ref_id[i]; o.start[r] = p.tstart[i]; o.end[r] = p.tend[i]; o.qlen[r] = ql;
-      o.win[r] = (long long)r;
-    }
-  }
-  const unsigned many = __ballot_sync(0xffffffffu, g >= 2);
-  if (many) {
-    const int lane = threadIdx.x & 31;
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(n_multi, (unsigned)__popc(many));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (g >= 2) multi[base + __popc(many & ((1u << lane) - 1u))] = (int32_t)r;
-  }
+  o.ref[r] = p.ref_id[i]; o.start[r] = p.tstart[i]; o.end[r] = p.tend[i]; o.qlen[r] = ql;
+  o.win[r] = (long long)r;
 }
 
+// the reads with several kept lines: a warp scans 32 marks at a time and its lanes take the marked reads one each
+// (compacted inside the warp: no lane idles while its neighbour walks a group)
 constexpr int PAF_LOCAL = 8;                 // lines of one read kept in registers / local memory
 __global__ void __launch_bounds__(128)
-paf_elect_multi_kernel(PafSet ps, const int32_t* __restrict__ off, int32_t* __restrict__ idx,
-                       const int32_t* __restrict__ name_rank, PafTableOut o, const int32_t* __restrict__ multi,
-                       const unsigned int* __restrict__ n_multi, unsigned long long* __restrict__ err) {
-  const unsigned n = *n_multi;
-  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const uint32_t r = (uint32_t)multi[k];
-    const int32_t a0 = off[r], g = off[r + 1] - a0;
-    int32_t* seg = idx + a0;
-    for (int i = 1; i < g; i++) {            // insertion sort by line id = arrival order (file order, :237)
-      const int32_t e = seg[i];
-      int j = i - 1;
-      while (j >= 0 && seg[j] > e) { seg[j + 1] = seg[j]; j--; }
-      seg[j + 1] = e;
-    }
-    if (g <= PAF_LOCAL) {
-      PafLine L[PAF_LOCAL];
-      for (int j = 0; j < g; j++) L[j] = paf_line(ps, seg[j]);
-      paf_elect_read(r, g, [&L](int j) { return L[j]; }, name_rank, o, err);
+paf_elect_multi_kernel(uint32_t n_reads, PafSet ps, const int32_t* __restrict__ off, int32_t* __restrict__ idx,
+                       const int32_t* __restrict__ name_rank, PafTableOut o, const uint8_t* __restrict__ multi,
+                       unsigned long long* __restrict__ err) {
+  __shared__ uint32_t s_list[4][1024];
+  const int lane = threadIdx.x & 31;
+  const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+  const uint32_t chunk = 1024;               // reads per warp round: 32 marks per lane
+  for (uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * chunk; base < n_reads;
+       base += n_warps * chunk) {
+    // lane l looks at reads base + 32 l .. + 31 (32 bytes: two 16-byte loads when the range is complete)
+    uint32_t mask = 0;
+    const uint32_t r0 = base + lane * 32;
+    if (r0 + 32 <= n_reads && (r0 & 15u) == 0) {
+      const uint4 x = *reinterpret_cast<const uint4*>(multi + r0), y = *reinterpret_cast<const uint4*>(multi + r0 + 16);
+      const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) mask |= ((w[k] >> (8 * b)) & 1u) << (k * 4 + b);
     } else {
-      paf_elect_read(r, g, [&ps, seg](int j) { return paf_line(ps, seg[j]); }, name_rank, o, err);
+      for (int k = 0; k < 32; k++)
+        if (r0 + k < n_reads && multi[r0 + k]) mask |= 1u << k;
     }
+    // hand the marked reads out: the lanes list them in the warp's shared buffer, then take one each per round
+    const int cnt = __popc(mask);
+    const int incl = warp_incl_scan(cnt, lane);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t* list = s_list[threadIdx.x >> 5];
+    int pos = incl - cnt;
+    while (mask) {
+      list[pos++] = r0 + (__ffs(mask) - 1);
+      mask &= mask - 1;
+    }
+    __syncwarp();
+    for (int t = lane; t < total; t += 32) {
+      const uint32_t r = list[t];
+      const int32_t a0 = off[r], g = off[r + 1] - a0;
+      int32_t* seg = idx + a0;
+      for (int i = 1; i < g; i++) {          // insertion sort by line id = arrival order (file order, :237)
+        const int32_t e = seg[i];
+        int j = i - 1;
+        while (j >= 0 && seg[j] > e) { seg[j + 1] = seg[j]; j--; }
+        seg[j + 1] = e;
+      }
+      if (g <= PAF_LOCAL) {
+        PafLine L[PAF_LOCAL];
+        for (int j = 0; j < g; j++) L[j] = paf_line(ps, seg[j]);
+        paf_elect_read(r, g, [&L](int j) { return L[j]; }, name_rank, o, err);
+      } else {
+        paf_elect_read(r, g, [&ps, seg](int j) { return paf_line(ps, seg[j]); }, name_rank, o, err);
+      }
+    }
+    __syncwarp();                            // everybody is done with the list before the next round rewrites it
   }
 }
 
@@ -1130,15 +1183,13 @@ int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
       upto.n = k + 1;
       PafTableOut o{ft.ref_id.as<int32_t>(), ft.start.as<int32_t>(), ft.end.as<int32_t>(), ft.qlen.as<int32_t>(),
                     ft.win.as<long long>()};
-      int32_t* multi = multi_buf.as<int32_t>();
-      unsigned int* n_multi = reinterpret_cast<unsigned int*>(multi + nr);
-      GCI_CUDA_TRY(ctx, cudaMemsetAsync(n_multi, 0, 4, ctx->stream));
-      paf_elect_kernel<<<(n_reads + 127) / 128, 128, 0, ctx->stream>>>(
-          n_reads, upto, off.as<int32_t>(), idx.as<int32_t>(), o, multi, n_multi, ctx->d_err.as<unsigned long long>());
+      uint8_t* multi = multi_buf.as<uint8_t>();
+      paf_elect_kernel<<<(n_reads + PAF_ELECT_THREADS - 1) / PAF_ELECT_THREADS, PAF_ELECT_THREADS, 0, ctx->stream>>>(
+          n_reads, upto, off.as<int32_t>(), idx.as<int32_t>(), o, multi, ctx->d_err.as<unsigned long long>());
       GCI_LAUNCH_CHECK(ctx);
-      const unsigned mgrid = (unsigned)std::min<int64_t>((n_reads + 127) / 128, (int64_t)ctx->sm_count * 8);
+      const unsigned mgrid = (unsigned)std::min<int64_t>(((int64_t)n_reads + 4095) / 4096, (int64_t)ctx->sm_count * 8);
       paf_elect_multi_kernel<<<mgrid, 128, 0, ctx->stream>>>(
-          upto, off.as<int32_t>(), idx.as<int32_t>(), ctx->d_name_rank.as<int32_t>(), o, multi, n_multi,
+          n_reads, upto, off.as<int32_t>(), idx.as<int32_t>(), ctx->d_name_rank.as<int32_t>(), o, multi,
           ctx->d_err.as<unsigned long long>());
       GCI_LAUNCH_CHECK(ctx);
     }
@@ -1182,7 +1233,8 @@ int gci_run_join_counting(gci_ctx* ctx, double op, int32_t track, int32_t flank_
   unsigned long long* cnt = ctx->d_err.as<unsigned long long>() + 2;
   ctx->stage_begin(GCI_ST_JOIN);
   if (ctx->n_reads) {
-    join_kernel<<<(ctx->n_reads + 255) / 256, 256, 0, ctx->stream>>>(
+    const unsigned grid = (unsigned)std::min<int64_t>(((int64_t)ctx->n_reads + 255) / 256, (int64_t)ctx->sm_count * 8);
+    join_kernel<<<grid, 256, 0, ctx->stream>>>(
         a, ctx->n_reads, ctx->highq.as<uint8_t>(), op, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(),
         ctx->surv_end.as<int32_t>(), cnt, ctx->d_err.as<unsigned long long>(), bk);
     GCI_LAUNCH_CHECK(ctx);

@@ -248,21 +248,27 @@ home_join_kernel(XLayout lay, XPeers peers, int me, HomeArgs a, uint32_t n_home,
 __global__ void __launch_bounds__(256)
 consume2_kernel(XLayout lay, const char* __restrict__ mine, int32_t* __restrict__ s_contig, int32_t* __restrict__ s_start,
                 int32_t* __restrict__ s_end, BucketArgs bk) {
-  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;       // (source, slot)
-  const int src = (int)(g / lay.cap2);
-  const long long slot = g - (long long)src * lay.cap2;
   const int par = (int)(*reinterpret_cast<const unsigned long long*>(mine) & 1ull);
-  int32_t c = -1, s = 0, e = 0;
-  if (src < lay.world) {
-    if (slot < (long long)*reinterpret_cast<const uint32_t*>(mine + lay.cnt2_off(par, src))) {
-      const int4 r = *reinterpret_cast<const int4*>(mine + lay.rows2_off(par, 0) + (long long)sizeof(XRow2) * g);
-      c = r.x; s = r.y; e = r.z;
+  const long long n_slots = lay.cap2 * lay.world;
+  WarpSums ws;
+  ws.init();
+  for (long long base = blockIdx.x * (long long)blockDim.x; base < n_slots; base += gridDim.x * (long long)blockDim.x) {
+    const long long g = base + threadIdx.x;                                   // (source, slot)
+    int32_t c = -1, s = 0, e = 0;
+    if (g < n_slots) {
+      const int src = (int)(g / lay.cap2);
+      const long long slot = g - (long long)src * lay.cap2;
+      if (slot < (long long)*reinterpret_cast<const uint32_t*>(mine + lay.cnt2_off(par, src))) {
+        const int4 r = *reinterpret_cast<const int4*>(mine + lay.rows2_off(par, 0) + (long long)sizeof(XRow2) * g);
+        c = r.x; s = r.y; e = r.z;
+      }
+      s_contig[g] = c;
+      s_start[g] = s;
+      s_end[g] = e;
     }
-    s_contig[g] = c;
-    s_start[g] = s;
-    s_end[g] = e;
+    ws.add(bk, c, s, e, false);
   }
-  bucket_count_one(bk, c, s, e, false, nullptr);
+  ws.flush(bk, nullptr);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
@@ -364,7 +370,7 @@ int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t f
   xchg_wait_kernel<<<1, 32, 0, ctx->stream>>>(lay, mine, 1, d_err);
   GCI_LAUNCH_CHECK(ctx);
   // owner: the survivors that arrived, their depth events counted on the way
-  consume2_kernel<<<(unsigned)((sh.surv_slots + 255) / 256), 256, 0, ctx->stream>>>(
+  consume2_kernel<<<(unsigned)std::min<int64_t>((sh.surv_slots + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
       lay, mine, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(), bk);
   GCI_LAUNCH_CHECK(ctx);
   ctx->stage_end();
