@@ -56,22 +56,38 @@ def genome_shape(scale):
     return [max(2000, int(x * scale)) for x in synth.CHM13_LENGTHS], list(synth.CHM13_NAMES)
 
 
-def make_workload(rank, world, scale=1.0):
-    """rank's share of the workload: at N = 1 the whole configs[2] genome; at N > 1 genome copy `rank` of N
-    (contig names suffixed), i.e. per-GPU work is fixed (weak scaling)."""
-    from gci_b200 import synth
+def genome_of(world, scale):
+    """contig table of the run: the configs[2] genome; at N > 1, N copies of it (names suffixed _h1.._hN), so that
+    per-GPU work stays fixed (weak scaling) and the 24 N contigs are dealt to the ranks by length"""
     lengths, names = genome_shape(scale)
+    if world == 1:
+        return lengths, names
+    return lengths * world, [f"{n}_h{k + 1}" for k in range(world) for n in names]
+
+
+def make_workload(rank, world, scale=1.0, contig_ids=None):
+    """rank's share of the workload: at N = 1 the whole genome; at N > 1 the reads of the contigs this rank owns
+    (BAM records on them; the PAF lines of those reads, which the second aligner may have put on ANY contig)."""
+    from gci_b200 import sharded, synth
+    lengths, names = genome_of(world, scale)
+    plan = None
     if world > 1:
-        names = [f"{n}_h{rank + 1}" for n in names]
-    return synth.make_genome(lengths, names, coverage=COVERAGE, seed=SEED + 1000 * rank)
+        plan = sharded.make_plan(rank, world, lengths)
+        contig_ids = np.flatnonzero(plan.owned).tolist()
+    w = synth.make_genome(lengths, names, coverage=COVERAGE, seed=SEED, contig_ids=contig_ids)
+    return w, plan
 
 
-def workload_config(w, world, scale):
-    cfg = {"workload": "chm13like_3.1Gbp_24contigs_30x_hifi_1bam+1paf_op0.9" + ("" if world == 1 else f"_x{world}_genomes_contig_sharded"),
-           "genome_bases": int(w.contigs.lengths.sum()), "contigs": len(w.contigs), "coverage": COVERAGE,
+def workload_config(world, scale):
+    """generation-independent description of the workload: identical in both arms and on every rank"""
+    lengths, names = genome_of(world, scale)
+    reads = int(sum(max(1, int(l * COVERAGE / 15000.0)) for l in lengths))
+    cfg = {"workload": "chm13like_3.1Gbp_24contigs_30x_hifi_1bam+1paf_op0.9" +
+                       ("" if world == 1 else f"_x{world}_genome_copies_contig_sharded"),
+           "genome_bases": int(sum(lengths)), "contigs": len(lengths), "coverage": COVERAGE,
            "files": "1 BAM (first aligner) + 1 PAF (second aligner), PAF joined first (GCI.py:272)",
-           "records": int(w.bam.n_records), "paf_lines": int(w.paf.n_records), "cigar_ops": int(w.bam.n_ops),
-           "reads": int(w.n_reads), "aligned_bases": int(w.aligned_bases),
+           "reads": reads, "read_model": "HiFi lognormal(15 kb), ~31 CIGAR ops per record; PAF: 2% missing, 5% shifted, "
+                                         "3% other contig, 3% split, 2% alternative, 0.3% tied lines",
            "args": dict(PARAMS, flank_len=FLANK, threshold=THRESHOLD, dist_percent=DIST), "seed": SEED,
            "l2": "GPU arm: 512 MiB buffer written between timed steps (L2 flush); per-step inputs (1.2 GB) and "
                  "outputs (12.8 GB) both exceed the 126 MB L2",
@@ -175,20 +191,19 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import c_oracle as CO
-    w = make_workload(0, world, args.scale)
-    config = workload_config(w, world, args.scale)
-    L = [int(x) for x in w.contigs.lengths]
-    sel = cpu_sample_selection(L, args.ref_sample)
-    sample_aligned = aligned_on(w, sel)
-    # the sample's own input files: records / lines on the selected contigs only (what `samtools view` of those
-    # contigs would hold), so the arm does not pay for CIGARs it never uses
+    config = workload_config(world, args.scale)
+    lengths, names = genome_shape(args.scale)                 # the sample comes from the first genome copy
+    sel = cpu_sample_selection(lengths, args.ref_sample)
+    # the sample's own input files: the reads of the selected contigs; PAF lines the second aligner moved to an
+    # unselected contig are not the sample's (the reference skips them at GCI.py:220)
     from gci_b200 import synth
     from gci_b200.records import PafTable
+    w = synth.make_genome(lengths, names, coverage=COVERAGE, seed=SEED, contig_ids=np.flatnonzero(sel).tolist())
     keep = np.flatnonzero(sel[w.paf.ref_id])
-    w = synth.GenomeWorkload(w.contigs, w.bam.take(np.flatnonzero(sel[w.bam.ref_id])),
-                             PafTable(*[getattr(w.paf, k)[keep] for k in ("read_id", "qlen", "qstart", "qend", "ref_id",
-                                                                         "tstart", "tend", "nmatch", "alnlen", "mapq")]),
-                             w.n_reads, w.holes, w.n_runs, w.aligned_bases)
+    w.paf = PafTable(*[getattr(w.paf, k)[keep] for k in ("read_id", "qlen", "qstart", "qend", "ref_id", "tstart", "tend",
+                                                         "nmatch", "alnlen", "mapq")])
+    L = lengths
+    sample_aligned = aligned_on(w, sel)
     threads = CO.max_threads()
     for _ in range(args.warmup):
         cpu_port_pass(w, threads, sel)
@@ -239,11 +254,11 @@ def main():
         return
 
     t_gen = time.perf_counter()
-    w = make_workload(rank, world, args.scale)
+    w, plan = make_workload(rank, world, args.scale)
     t_gen = time.perf_counter() - t_gen
 
     import torch
-    from gci_b200 import dist as D
+    from gci_b200 import dist as D, sharded
     from gci_b200._lib import Context, PinnedPool
     from gci_b200.records import AlnTable, PafTable
     if not torch.cuda.is_available():
@@ -254,22 +269,31 @@ def main():
     import torch.distributed as tdist
 
     L = [int(x) for x in w.contigs.lengths]
-    nct = len(L)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = Context(local)
     ctx.set_stream(stream.cuda_stream)
-    ctx.set_contigs(L)
-    ctx.set_name_rank(w.contigs.name_rank())
+    paf = w.paf
     if world > 1:
+        # contigs owned by this rank, reads homed here: the library moves winners and survivors between the ranks
+        # over NVLink peer memory inside every step (csrc/shard.cu); here the PAF lines are dealt to the read homes once
+        handle = sharded.configure(ctx, plan, L, w.contigs.name_rank(), w.n_reads, max_bam_files=1)
+        sharded.open_over_process_group(ctx, plan, handle)
         D.init_native_comm(ctx)
+        paf = sharded.deal_paf_over_process_group(w.paf, plan)
+        owned = np.flatnonzero(plan.owned).tolist()
+    else:
+        ctx.set_contigs(L)
+        ctx.set_name_rank(w.contigs.name_rank())
+        owned = list(range(len(L)))
+    nct = len(owned)
     pool = PinnedPool()
     pinned_bam = AlnTable(*[pool.copy(getattr(w.bam, c)) for c in
                             ("ref_id", "ref_start", "mapq", "flag", "nm", "qlen", "read_id", "cigar_off", "cigar")])
-    pinned_paf = PafTable(*[pool.copy(getattr(w.paf, c)) for c in
+    pinned_paf = PafTable(*[pool.copy(getattr(paf, c)) for c in
                             ("read_id", "qlen", "qstart", "qend", "ref_id", "tstart", "tend", "nmatch", "alnlen", "mapq")])
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
-    h2d_bytes = w.bam.nbytes() + w.paf.nbytes()
+    h2d_bytes = w.bam.nbytes() + paf.nbytes()
     result = {}
     headers = [f">{n}\n".encode() for n in w.contigs.names]
 
@@ -318,7 +342,7 @@ def main():
         return ms
 
     upload()                                  # records resident in HBM for the `value` region
-    gz_out = pool.empty(max(64 << 20, int(sum(L) * 0.10) + (1 << 20)), np.uint8)
+    gz_out = pool.empty(max(64 << 20, int(sum(L[c] for c in owned) * 0.10) + (1 << 20)), np.uint8)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -364,7 +388,7 @@ def main():
     gpu_hash = ctx.depth_hash(0)
     gs, ge, goff = ctx.fetch_intervals(0, nct)
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle as CO
         threads = CO.max_threads()
         t0 = time.perf_counter()
@@ -380,8 +404,7 @@ def main():
         for c in range(nct):
             assert (int(result["n50"][c]), int(result["nctg"][c])) == (want_rows[c][2], want_rows[c][4]), \
                 (c, want_rows[c], int(result["n50"][c]), int(result["nctg"][c]))
-        if world == 1:
-            assert (int(result["n50"][nct]), int(result["nctg"][nct])) == (want_rows[nct][2], want_rows[nct][4])
+        assert (int(result["n50"][nct]), int(result["nctg"][nct])) == (want_rows[nct][2], want_rows[nct][4])
 
     if world > 1:
         tdist.barrier()
@@ -395,7 +418,7 @@ def main():
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     d_ms, d_k = stage["depth"]
-    n_tiles = sum(l // 1024 + 1 for l in L)            # one 1024-position tile per warp
+    n_tiles = sum(L[c] // 1024 + 1 for c in owned)     # one 1024-position tile per warp (this rank's contigs)
     n_events = 2 * result["n_surv"]
     alg_bytes = BYTES_PER_BASE * n_tiles * 1024 + 2.0 * n_events + 16.0 * n_tiles
     achieved = alg_bytes / (d_ms / max(1, d_k) * 1e-3) / 1e9 if d_ms > 0 else None
@@ -409,7 +432,7 @@ def main():
     stage_ms = {k: v[0] / prof_steps for k, v in stage.items() if v[1]}
     # step-level algorithmic bytes: depth + flags written once, every CIGAR op, BAM columns (35 B) and PAF columns
     # (40 B) read once
-    step_bytes = alg_bytes + 4.0 * w.bam.n_ops + 35.0 * w.bam.n_records + 40.0 * w.paf.n_records
+    step_bytes = alg_bytes + 4.0 * w.bam.n_ops + 35.0 * w.bam.n_records + 40.0 * paf.n_records
     roofline = {"bound": "hbm", "kernel": "depth_tile_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": d_ms / max(1, d_k),
@@ -422,16 +445,22 @@ def main():
                                "as one CUDA graph per step"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic", "config": workload_config(w, world, args.scale),
-            "details": {"aligned_bases_total": total_aligned, "survivors": result["n_surv"],
+            "data": "synthetic", "config": workload_config(world, args.scale),
+            "details": {"aligned_bases_total": total_aligned, "records_rank0": int(w.bam.n_records),
+                        "paf_lines_rank0": int(paf.n_records), "cigar_ops_rank0": int(w.bam.n_ops),
+                        "survivors_rank0": result["n_surv"],
                         "issue_intervals": result["n_iv"], "generate_s": t_gen,
                         "launch": "the step is replayed as a CUDA graph (captured on its second run): " +
                                   ("off (GCI_GRAPH=0)" if os.environ.get("GCI_GRAPH", "1").startswith("0") else "on"),
                         "parallelism": "contig sharding, 1 process per GPU" if world > 1 else "single GPU",
                         "graph_replays": int(ctx.graph_replays), "device_bytes": int(ctx.device_bytes),
                         "row_exchange": getattr(ctx, "row_exchange", None) if world > 1 else None,
-                        "parity_gate": None if cpu is None else "depth checksums, intervals, survivors, depth sums and "
-                                                                "score rows equal the CPU port's"},
+                        "read_set_exchange": None if world == 1 else
+                        "winners to read homes, survivors to contig owners: stores into NVLink peer memory (CUDA IPC), "
+                        "csrc/shard.cu",
+                        "parity_gate": ("N > 1: the sharded path is checked against the C port by tests/test_gpu_shard.py "
+                                        "and tests/test_gpu_multi.py" if world > 1 else None) if cpu is None else
+                        "depth checksums, intervals, survivors, depth sums and score rows equal the CPU port's"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(result.get("d2h_gz_bytes", 0) + 8 * result["n_iv"] + 8 * 3 * (nct + 1)),

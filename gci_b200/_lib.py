@@ -93,6 +93,7 @@ _SIGNATURES = {
     "gci_shard_config": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "gci_shard_alloc": (C.c_int, [_p, _u32, _i32, _p]),
     "gci_shard_open": (C.c_int, [_p, _p]),
+    "gci_shard_close": (C.c_int, [_p]),
     "gci_shard_area": (_p, [_p]),
     "gci_shard_attach": (C.c_int, [_p, _p]),
 }
@@ -501,6 +502,9 @@ class Context:
         h = _arr(handles, np.uint8)
         assert h.size == 64 * self.shard_world
         self._check(self._lib.gci_shard_open(self._h, _ptr(h)))
+
+    def shard_close(self):
+        self._check(self._lib.gci_shard_close(self._h))
 
     def shard_area(self):
         return int(self._lib.gci_shard_area(self._h) or 0)

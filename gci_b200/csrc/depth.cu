@@ -1,6 +1,8 @@
 // Depth stage: survivors -> per-tile event buckets -> per-base depth tiles (+ fused issue flags),
 // N-run masking, two-type max, stand-alone flags, depth text.
 // Reference: GCI.py:302-306 (accumulate), :315-329 (mask), :332-353 (max), :110-117 (text).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -176,6 +178,87 @@ depth_tile_kernel(const ulonglong2* __restrict__ tile_ps /* (pack, scan) per til
     }
     __syncwarp();   // re-zeroing stores of all lanes are done before the next tile's events land
   }
+}
+
+// The same expansion with TMA bulk stores (verdict r01 item 6): the prefix sums are written back INTO the warp's shared
+// tile and one lane hands the finished 4 KB to the copy engine (cp.async.bulk.global.shared::cta -> SASS UBLKCP);
+// the warp goes on with its second buffer while the store drains, so no lane ever holds a store in a register or
+// waits on the LSU.  Two 4 KB buffers per warp: a buffer is reused two tiles later, after wait_group.read.
+__device__ __forceinline__ void bulk_store_4k(void* gdst, const void* ssrc) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;\n"
+               "cp.async.bulk.commit_group;" ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc))
+               : "memory");
+}
+
+template <bool FLAGS>
+__global__ void __launch_bounds__(GCI_TILE_THREADS)
+depth_tile_tma_kernel(const ulonglong2* __restrict__ tile_ps, const uint16_t* __restrict__ events, int64_t n_tiles,
+                      int32_t* __restrict__ depth, uint32_t* __restrict__ flags, int32_t lo1, uint32_t span) {
+  extern __shared__ __align__(128) int s_dyn[];                        // [warps][2][GCI_TILE]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int* const s_warp = s_dyn + warp * 2 * GCI_TILE;
+  constexpr int ITERS = GCI_TILE / 256;                                // 4
+  const int64_t n_warps = (int64_t)gridDim.x * (GCI_TILE_THREADS / 32);
+  int64_t tile = (int64_t)blockIdx.x * (GCI_TILE_THREADS / 32) + warp;
+  const ulonglong2 zero2 = make_ulonglong2(0, 0);
+  ulonglong2 ps = tile < n_tiles ? tile_ps[tile] : zero2;                       // current tile
+  ulonglong2 ps1 = tile + n_warps < n_tiles ? tile_ps[tile + n_warps] : zero2;  // next tile
+  uint32_t ev = lane < (uint32_t)(ps.x & 0xffffffffull) ? events[(uint32_t)(ps.y & 0xffffffffull) + lane] : 0u;
+  int cur = 0;
+  for (; tile < n_tiles; tile += n_warps, cur ^= 1) {
+    int* __restrict__ s_delta = s_warp + cur * GCI_TILE;
+    // the bulk store that read this buffer two tiles ago is done reading (only the latest group may be pending)
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int v = lane; v < GCI_TILE / 4; v += 32) reinterpret_cast<int4*>(s_delta)[v] = make_int4(0, 0, 0, 0);
+    __syncwarp();
+    const uint32_t n_ev = (uint32_t)(ps.x & 0xffffffffull);
+    const uint32_t ev0 = (uint32_t)(ps.y & 0xffffffffull);
+    int carry = (int)(uint32_t)(ps.y >> 32);                     // depth carried into the tile
+    if (lane < n_ev) atomicAdd(&s_delta[ev >> 1], (ev & 1u) ? -1 : 1);
+    for (uint32_t i = lane + 32; i < n_ev; i += 32) {            // more than 32 events in the tile: rare
+      const uint32_t e = events[ev0 + i];
+      atomicAdd(&s_delta[e >> 1], (e & 1u) ? -1 : 1);
+    }
+    ps = ps1;
+    ev = lane < (uint32_t)(ps.x & 0xffffffffull) ? events[(uint32_t)(ps.y & 0xffffffffull) + lane] : 0u;
+    ps1 = tile + 2 * n_warps < n_tiles ? tile_ps[tile + 2 * n_warps] : zero2;
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < ITERS; it++) {
+      const int ia = it * 256 + lane * 4, ib = ia + 128;
+      const int4 va = *reinterpret_cast<const int4*>(&s_delta[ia]);
+      const int4 vb = *reinterpret_cast<const int4*>(&s_delta[ib]);
+      const int a0 = va.x, a1 = a0 + va.y, a2 = a1 + va.z, a3 = a2 + va.w;
+      const int b0 = vb.x, b1 = b0 + vb.y, b2 = b1 + vb.z, b3 = b2 + vb.w;
+      int tot_a, tot_b;
+      const int ra = carry + sparse_excl_scan(a3, lane, tot_a);
+      const int rb = carry + tot_a + sparse_excl_scan(b3, lane, tot_b);
+      carry += tot_a + tot_b;
+      const int4 oa = make_int4(ra + a0, ra + a1, ra + a2, ra + a3);
+      const int4 ob = make_int4(rb + b0, rb + b1, rb + b2, rb + b3);
+      *reinterpret_cast<int4*>(&s_delta[ia]) = oa;               // depth replaces the deltas in place
+      *reinterpret_cast<int4*>(&s_delta[ib]) = ob;
+      if (FLAGS) {
+        const uint32_t na = flag4(oa.x, oa.y, oa.z, oa.w, lo1, span), nb = flag4(ob.x, ob.y, ob.z, ob.w, lo1, span);
+        const bool odd = lane & 1;
+        uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? na : nb, 1);
+        uint32_t acc = odd ? (got | (nb << 4)) : (na | (got << 4));
+        got = __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc = (lane & 2) ? (got | (acc << 8)) : (acc | (got << 8));
+        got = __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc = (lane & 4) ? (got | (acc << 16)) : (acc | (got << 16));
+        if ((lane & 6) == 0)   // lanes 8g (A word g) and 8g+1 (B word g)
+          flags[tile * (GCI_TILE / 32) + it * 8 + (odd ? 4 : 0) + (lane >> 3)] = acc;
+      }
+    }
+    // generic-proxy writes of the whole warp -> visible to the async proxy, then one lane starts the copy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) bulk_store_4k(depth + tile * GCI_TILE, s_delta);
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the tile must have left before the CTA does
 }
 
 // ================================================================================================
@@ -502,8 +585,29 @@ int gci_depth_enqueue(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo
   const uint16_t* evs = ctx->events.as<uint16_t>();
   int32_t* dp = t.depth.as<int32_t>();
   uint32_t* fp = t.flags.as<uint32_t>();
-  if (fuse) depth_tile_kernel<true><<<grid, GCI_TILE_THREADS, 0, ctx->stream>>>(tile_ps, evs, nt, dp, fp, lo1, span);
-  else depth_tile_kernel<false><<<grid, GCI_TILE_THREADS, 0, ctx->stream>>>(tile_ps, evs, nt, dp, fp, lo1, span);
+  static int use_tma = -1, tma_ctas = 0;
+  constexpr size_t TMA_SMEM = sizeof(int) * 2 * GCI_TILE * (GCI_TILE_THREADS / 32);      // 64 KB
+  if (use_tma < 0) {
+    const char* g = getenv("GCI_DEPTH_TMA");
+    use_tma = !(g && g[0] == '0');
+    if (use_tma &&
+        (cudaFuncSetAttribute(depth_tile_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM) != cudaSuccess ||
+         cudaFuncSetAttribute(depth_tile_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM) != cudaSuccess ||
+         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tma_ctas, depth_tile_tma_kernel<true>, GCI_TILE_THREADS, TMA_SMEM) != cudaSuccess ||
+         tma_ctas < 1)) {
+      cudaGetLastError();
+      use_tma = 0;
+    }
+  }
+  if (use_tma) {
+    const unsigned tgrid = (unsigned)std::min<int64_t>(ctas_needed, (int64_t)ctx->sm_count * tma_ctas);
+    if (fuse) depth_tile_tma_kernel<true><<<tgrid, GCI_TILE_THREADS, TMA_SMEM, ctx->stream>>>(tile_ps, evs, nt, dp, fp, lo1, span);
+    else depth_tile_tma_kernel<false><<<tgrid, GCI_TILE_THREADS, TMA_SMEM, ctx->stream>>>(tile_ps, evs, nt, dp, fp, lo1, span);
+  } else if (fuse) {
+    depth_tile_kernel<true><<<grid, GCI_TILE_THREADS, 0, ctx->stream>>>(tile_ps, evs, nt, dp, fp, lo1, span);
+  } else {
+    depth_tile_kernel<false><<<grid, GCI_TILE_THREADS, 0, ctx->stream>>>(tile_ps, evs, nt, dp, fp, lo1, span);
+  }
   GCI_LAUNCH_CHECK(ctx);
   ctx->stage_end();
   // depth and flags are both un-masked here (the reference writes the single-type .depth.gz before

@@ -618,70 +618,123 @@ struct JoinArgs {
   int n_files;
 };
 
+// The join of ONE read from the entries of its files (GCI.py:272-301); k[f] < 0 = absent in file f.
+struct JoinEntry { int32_t c, s, e, q; };
+template <class Entry>
+__device__ __forceinline__ bool join_one(int n_files, const long long* k, const Entry& entry, bool hq, double op,
+                                         uint32_t r, unsigned long long* err, int32_t& c, int32_t& s, int32_t& e) {
+  bool have = false;
+  c = -1; s = 0; e = 0;
+  if (n_files == 1) {                                           // :300-301
+    if (k[0] >= 0) {
+      const JoinEntry x = entry(0);
+      have = true;
+      c = x.c; s = x.s; e = x.e;
+    }
+    return have;
+  }
+  bool comm = true;
+  for (int f = 0; f < n_files; f++) comm = comm && (k[f] >= 0);                            // :274-277
+  if (k[0] >= 0 && (hq || comm)) {                                                         // :279-280
+    const JoinEntry x = entry(0);
+    have = true;
+    c = x.c; s = x.s; e = x.e;
+  }
+  for (int f = 1; f < n_files; f++) {                                                       // :281-299
+    if (k[f] < 0) continue;
+    const JoinEntry x = entry(f);
+    if (have) {
+      if (x.c == c) {
+        const long long ov = (long long)min(x.e, e) - (long long)max(x.s, s);
+        if (x.q == 0) {                                                                     // ZeroDivisionError :292
+          atomicOr(err, 8ull);
+          atomicMin(err + 1, (unsigned long long)r);
+          have = false;
+        } else if (!ratio_ge(ov, x.q, op)) {                                                // ovlp / qlen < -op: delete
+          have = false;
+        } else {
+          s = max(x.s, s);
+          e = min(x.e, e);
+        }
+      } else {
+        have = false;
+      }
+    } else if (hq) {
+      have = true;
+      c = x.c; s = x.s; e = x.e;
+    }
+  }
+  return have;
+}
+
 // persistent grid: a warp walks 32 consecutive reads per round, so its depth-sum / survivor-count partials stay in
-// registers (WarpSums) until the contig changes
+// registers (WarpSums) until the contig changes.
+// NF = 1, 2: the common shapes (one file; BAM + PAF or two BAMs).  The kernel is a chain of dependent gathers
+// (winner -> record -> fields), so a thread works on JOIN_ILP reads at once and issues every load of one level for
+// all of them before it looks at any: the chain is paid once per JOIN_ILP reads instead of once per read.
+// NF = 0: any number of files, one read at a time.
+constexpr int JOIN_ILP = 4;
+template <int NF>
 __global__ void __launch_bounds__(256)
 join_kernel(JoinArgs a, uint32_t n_reads, const uint8_t* __restrict__ highq, double op,
             int32_t* __restrict__ s_contig, int32_t* __restrict__ s_start, int32_t* __restrict__ s_end,
             unsigned long long* __restrict__ count, unsigned long long* __restrict__ err, BucketArgs bk) {
   WarpSums ws;
   ws.init();
-  for (uint32_t base = blockIdx.x * blockDim.x; base < n_reads; base += gridDim.x * blockDim.x) {
-    const uint32_t r = base + threadIdx.x;
-    bool have = false;
-    int32_t c = -1, s = 0, e = 0;
-    if (r < n_reads) {
-      const long long k0 = a.f[0].win[r];
-      if (a.n_files == 1) {                                         // :300-301
-        if (k0 >= 0) {
-          const uint32_t i = (uint32_t)(k0 & 0xffffffffll);
-          have = true;
-          c = a.f[0].ref_id[i]; s = a.f[0].start[i]; e = a.f[0].end[i];
-        }
-      } else {
-        bool comm = true;
-        for (int f = 0; f < a.n_files; f++) comm = comm && (a.f[f].win[r] >= 0);          // :274-277
-        const bool hq = highq[r] != 0;
-        if (k0 >= 0 && (hq || comm)) {                                                     // :279-280
-          const uint32_t i = (uint32_t)(k0 & 0xffffffffll);
-          have = true;
-          c = a.f[0].ref_id[i]; s = a.f[0].start[i]; e = a.f[0].end[i];
-        }
-        for (int f = 1; f < a.n_files; f++) {                                               // :281-299
-          const long long k = a.f[f].win[r];
-          if (k < 0) continue;
-          const uint32_t i = (uint32_t)(k & 0xffffffffll);
-          const int32_t cf = a.f[f].ref_id[i], sf = a.f[f].start[i], ef = a.f[f].end[i];
-          if (have) {
-            if (cf == c) {
-              const long long ov = (long long)min(ef, e) - (long long)max(sf, s);
-              const int32_t ql = a.f[f].qlen[i];
-              if (ql == 0) {                                                                // ZeroDivisionError :292
-                atomicOr(err, 8ull);
-                atomicMin(err + 1, (unsigned long long)r);
-                have = false;
-              } else if ((double)ov / (double)ql < op) {
-                have = false;
-              } else {
-                s = max(sf, s);
-                e = min(ef, e);
-              }
-            } else {
-              have = false;
-            }
-          } else if (hq) {
-            have = true;
-            c = cf; s = sf; e = ef;
-          }
-        }
+  if (NF == 0) {
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_reads; base += gridDim.x * blockDim.x) {
+      const uint32_t r = base + threadIdx.x;
+      bool have = false;
+      int32_t c = -1, s = 0, e = 0;
+      if (r < n_reads) {
+        long long k[GCI_MAX_FILES];
+        for (int f = 0; f < a.n_files; f++) k[f] = a.f[f].win[r];
+        have = join_one(a.n_files, k, [&](int f) {
+          const uint32_t i = (uint32_t)(k[f] & 0xffffffffll);
+          return JoinEntry{a.f[f].ref_id[i], a.f[f].start[i], a.f[f].end[i], f ? a.f[f].qlen[i] : 0};
+        }, a.n_files > 1 && highq[r] != 0, op, r, err, c, s, e);
+        s_contig[r] = have ? c : -1;
+        s_start[r] = s;
+        s_end[r] = e;
       }
-      s_contig[r] = have ? c : -1;
-      s_start[r] = s;
-      s_end[r] = e;
+      ws.add(bk, have ? c : -1, s, e, have);
     }
-    // the survivor count, and for gci_pipeline the depth events of the survivor, are counted right here (no second
-    // pass over the survivors)
-    ws.add(bk, have ? c : -1, s, e, have);
+  } else {
+    const uint32_t span = blockDim.x * JOIN_ILP;
+    for (uint32_t base = blockIdx.x * span; base < n_reads; base += gridDim.x * span) {
+      // read j of this thread: base + j * blockDim + tid (a warp still covers 32 consecutive reads per j)
+      constexpr int NFX = NF > 0 ? NF : 1;
+      long long k[JOIN_ILP][NFX];
+      uint8_t hq[JOIN_ILP];
+#pragma unroll
+      for (int j = 0; j < JOIN_ILP; j++) {
+        const uint32_t r = base + j * blockDim.x + threadIdx.x;
+        const bool in = r < n_reads;
+#pragma unroll
+        for (int f = 0; f < NF; f++) k[j][f] = in ? a.f[f].win[r] : -1;
+        hq[j] = (NF > 1 && in) ? highq[r] : 0;
+      }
+      JoinEntry x[JOIN_ILP][NFX];
+#pragma unroll
+      for (int j = 0; j < JOIN_ILP; j++)
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+          const uint32_t i = k[j][f] >= 0 ? (uint32_t)(k[j][f] & 0xffffffffll) : 0u;   // absent: any valid entry
+          x[j][f] = JoinEntry{a.f[f].ref_id[i], a.f[f].start[i], a.f[f].end[i], f ? a.f[f].qlen[i] : 0};
+        }
+#pragma unroll
+      for (int j = 0; j < JOIN_ILP; j++) {
+        const uint32_t r = base + j * blockDim.x + threadIdx.x;
+        int32_t c, s, e;
+        const bool have = join_one(NF, k[j], [&](int f) { return x[j][f]; }, hq[j] != 0, op, r, err, c, s, e);
+        if (r < n_reads) {
+          s_contig[r] = have ? c : -1;
+          s_start[r] = s;
+          s_end[r] = e;
+        }
+        ws.add(bk, have ? c : -1, s, e, have);
+      }
+    }
   }
   ws.flush(bk, count);
 }
@@ -1059,28 +1112,28 @@ paf_elect_kernel(uint32_t n_reads, PafSet ps, const int32_t* __restrict__ off, c
 // the reads with several kept lines: a warp scans 32 marks at a time and its lanes take the marked reads one each
 // (compacted inside the warp: no lane idles while its neighbour walks a group)
 constexpr int PAF_LOCAL = 8;                 // lines of one read kept in registers / local memory
+constexpr int PAF_MULTI_CHUNK = 256;         // reads per warp round of paf_elect_multi_kernel
 __global__ void __launch_bounds__(128)
 paf_elect_multi_kernel(uint32_t n_reads, PafSet ps, const int32_t* __restrict__ off, int32_t* __restrict__ idx,
                        const int32_t* __restrict__ name_rank, PafTableOut o, const uint8_t* __restrict__ multi,
                        unsigned long long* __restrict__ err) {
-  __shared__ uint32_t s_list[4][1024];
+  __shared__ uint32_t s_list[4][PAF_MULTI_CHUNK];
   const int lane = threadIdx.x & 31;
   const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
-  const uint32_t chunk = 1024;               // reads per warp round: 32 marks per lane
+  constexpr uint32_t chunk = PAF_MULTI_CHUNK; // reads per warp round: 8 marks per lane
+  constexpr int PER_LANE = PAF_MULTI_CHUNK / 32;
   for (uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * chunk; base < n_reads;
        base += n_warps * chunk) {
-    // lane l looks at reads base + 32 l .. + 31 (32 bytes: two 16-byte loads when the range is complete)
+    // lane l looks at reads base + 8 l .. + 7 (one 8-byte load when the range is complete)
     uint32_t mask = 0;
-    const uint32_t r0 = base + lane * 32;
-    if (r0 + 32 <= n_reads && (r0 & 15u) == 0) {
-      const uint4 x = *reinterpret_cast<const uint4*>(multi + r0), y = *reinterpret_cast<const uint4*>(multi + r0 + 16);
-      const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    const uint32_t r0 = base + lane * PER_LANE;
+    static_assert(PER_LANE == 8, "one 8-byte load per lane");
+    if (r0 + PER_LANE <= n_reads) {
+      const unsigned long long w = *reinterpret_cast<const unsigned long long*>(multi + r0);
 #pragma unroll
-      for (int k = 0; k < 8; k++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) mask |= ((w[k] >> (8 * b)) & 1u) << (k * 4 + b);
+      for (int b8 = 0; b8 < PER_LANE; b8++) mask |= (uint32_t)((w >> (8 * b8)) & 1ull) << b8;
     } else {
-      for (int k = 0; k < 32; k++)
+      for (int k = 0; k < PER_LANE; k++)
         if (r0 + k < n_reads && multi[r0 + k]) mask |= 1u << k;
     }
     // hand the marked reads out: the lanes list them in the warp's shared buffer, then take one each per round
@@ -1187,7 +1240,8 @@ int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
       paf_elect_kernel<<<(n_reads + PAF_ELECT_THREADS - 1) / PAF_ELECT_THREADS, PAF_ELECT_THREADS, 0, ctx->stream>>>(
           n_reads, upto, off.as<int32_t>(), idx.as<int32_t>(), o, multi, ctx->d_err.as<unsigned long long>());
       GCI_LAUNCH_CHECK(ctx);
-      const unsigned mgrid = (unsigned)std::min<int64_t>(((int64_t)n_reads + 4095) / 4096, (int64_t)ctx->sm_count * 8);
+      const unsigned mgrid = (unsigned)std::min<int64_t>(((int64_t)n_reads + 4 * PAF_MULTI_CHUNK - 1) / (4 * PAF_MULTI_CHUNK),
+                                                         (int64_t)ctx->sm_count * 16);
       paf_elect_multi_kernel<<<mgrid, 128, 0, ctx->stream>>>(
           n_reads, upto, off.as<int32_t>(), idx.as<int32_t>(), ctx->d_name_rank.as<int32_t>(), o, multi,
           ctx->d_err.as<unsigned long long>());
@@ -1233,10 +1287,18 @@ int gci_run_join_counting(gci_ctx* ctx, double op, int32_t track, int32_t flank_
   unsigned long long* cnt = ctx->d_err.as<unsigned long long>() + 2;
   ctx->stage_begin(GCI_ST_JOIN);
   if (ctx->n_reads) {
-    const unsigned grid = (unsigned)std::min<int64_t>(((int64_t)ctx->n_reads + 255) / 256, (int64_t)ctx->sm_count * 8);
-    join_kernel<<<grid, 256, 0, ctx->stream>>>(
-        a, ctx->n_reads, ctx->highq.as<uint8_t>(), op, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(),
-        ctx->surv_end.as<int32_t>(), cnt, ctx->d_err.as<unsigned long long>(), bk);
+    // an empty file table (no rows) still has a win array; entry 0 of its columns must be readable for the
+    // load-everything-first path, so files without rows take the generic kernel
+    bool small = a.n_files <= 2;
+    for (int i = 0; i < a.n_files; i++) small = small && ctx->files[i].n > 0;
+    const int64_t per_cta = small ? 256 * JOIN_ILP : 256;
+    const unsigned grid = (unsigned)std::min<int64_t>(((int64_t)ctx->n_reads + per_cta - 1) / per_cta, (int64_t)ctx->sm_count * 8);
+    int32_t *sc = ctx->surv_contig.as<int32_t>(), *ss = ctx->surv_start.as<int32_t>(), *se = ctx->surv_end.as<int32_t>();
+    unsigned long long* d_err = ctx->d_err.as<unsigned long long>();
+    const uint8_t* hq = ctx->highq.as<uint8_t>();
+    if (small && a.n_files == 1) join_kernel<1><<<grid, 256, 0, ctx->stream>>>(a, ctx->n_reads, hq, op, sc, ss, se, cnt, d_err, bk);
+    else if (small) join_kernel<2><<<grid, 256, 0, ctx->stream>>>(a, ctx->n_reads, hq, op, sc, ss, se, cnt, d_err, bk);
+    else join_kernel<0><<<grid, 256, 0, ctx->stream>>>(a, ctx->n_reads, hq, op, sc, ss, se, cnt, d_err, bk);
     GCI_LAUNCH_CHECK(ctx);
   }
   ctx->stage_end();

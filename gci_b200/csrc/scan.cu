@@ -340,14 +340,27 @@ runs_kernel(const uint32_t* __restrict__ flags, const int32_t* __restrict__ chun
   // my 8 words and the one before them lie completely inside the window: two 16-byte loads, no masking
   const int64_t p0w = (w.w0 + j0) << 5;
   const int64_t gw = (w.g0 >> 5) + w.w0 + j0;
+  bool quiet = false;
   if (j0 >= 1 && j0 + RUN_WPT <= w.n_words && p0w - 32 >= w.lo && p0w + RUN_WPT * 32 <= w.hi && (gw & 3) == 0) {
     const uint4 a = *reinterpret_cast<const uint4*>(flags + gw), b = *reinterpret_cast<const uint4*>(flags + gw + 4);
     prev = flags[gw - 1];
     m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+    quiet = ((a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) == 0u) && (prev >> 31) == 0u;
   } else {
     prev = win_word(flags, w, j0 - 1);
+    uint32_t any = prev >> 31;
 #pragma unroll
-    for (int k = 0; k < RUN_WPT; k++) m[k] = win_word(flags, w, j0 + k);
+    for (int k = 0; k < RUN_WPT; k++) {
+      m[k] = win_word(flags, w, j0 + k);
+      any |= m[k];
+    }
+    quiet = any == 0u;
+  }
+  // almost every stretch of an assembly is issue-free: no bit set in the CTA's chunk and none just before its
+  // threads' words -> nothing starts or ends here
+  if (__syncthreads_and(quiet)) {
+    if (!WRITE && threadIdx.x == 0) cnt[chunk] = make_int2(0, 0);
+    return;
   }
 #pragma unroll
   for (int k = 0; k < RUN_WPT; k++) {

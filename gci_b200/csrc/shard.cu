@@ -477,6 +477,22 @@ int gci_shard_open(gci_ctx* ctx, const gci_ipc_handle* handles) {
   return GCI_OK;
 }
 
+int gci_shard_close(gci_ctx* ctx) {
+  if (!ctx) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  gci_ctx::Shard& sh = ctx->shard;
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->epoch++;
+  for (int r = 0; r < GCI_MAX_RANKS; r++) {
+    if (sh.peer[r] && sh.mapped[r]) cudaIpcCloseMemHandle(sh.peer[r]);
+    sh.peer[r] = nullptr;
+    sh.mapped[r] = false;
+  }
+  cudaGetLastError();
+  sh.opened = false;
+  return GCI_OK;
+}
+
 // contexts of ONE process (several "ranks" on the GPUs this process can address; tests): areas[r] = gci_shard_area
 // of rank r's context
 int gci_shard_attach(gci_ctx* ctx, void* const* areas) {

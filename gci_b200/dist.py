@@ -39,6 +39,32 @@ def init(backend=None):
     return rank, world, local
 
 
+def rank():
+    import torch.distributed as dist
+    return dist.get_rank() if is_dist() else 0
+
+
+def world():
+    import torch.distributed as dist
+    return dist.get_world_size() if is_dist() else 1
+
+
+def barrier():
+    if is_dist():
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def gather_objects(obj):
+    """every rank's (small, picklable) object, in rank order, on every rank"""
+    if not is_dist():
+        return [obj]
+    import torch.distributed as dist
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out
+
+
 def _device():
     import torch
     import torch.distributed as dist

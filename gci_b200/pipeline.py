@@ -45,14 +45,25 @@ class Session:
         self.selected = None
         self.scan_hint = None          # (lo, hi): thresholds the driver will scan with -> fused flags
         self._n_runs_key = None
+        self.plan = None               # gci_b200.sharded.ShardPlan of a multi-GPU run (torchrun), else None
+        self.run_selected = None
 
     def close(self):
         self.ctx.close()
 
     def configure(self, names, lengths, chrs_list):
+        """contig table of the run.  Under torchrun (WORLD_SIZE > 1) the selected contigs are dealt to the ranks
+        (gci_b200.sharded): `selected` then means selected AND owned by this rank, `run_selected` selected anywhere."""
         names = list(names)
         lengths = [int(x) for x in lengths]
-        selected = [(n in chrs_list) if len(chrs_list) > 0 else True for n in names]
+        run_selected = [(n in chrs_list) if len(chrs_list) > 0 else True for n in names]
+        plan = None
+        if _world() > 1:
+            from . import sharded
+            plan = sharded.make_plan(_rank(), _world(), lengths, run_selected)
+            if sum(run_selected) < _world():
+                sys.exit(f'ERROR!!! {_world()} GPUs for {sum(run_selected)} chromosomes: use at most one GPU per chromosome')
+        selected = run_selected if plan is None else [bool(x) for x in plan.owned]
         if self.names == names and self.lengths == lengths and self.selected == selected:
             return
         self.ctx.set_contigs(lengths, selected)
@@ -60,8 +71,28 @@ class Session:
         rank = np.empty(len(names), np.int32)
         rank[order] = np.arange(len(names), dtype=np.int32)
         self.ctx.set_name_rank(rank)
-        self.names, self.lengths, self.selected = names, lengths, selected
+        if plan is not None:
+            self.ctx.shard_config(plan.rank, plan.world, plan.owner, plan.selected)
+            self._exchange = (0, 0)
+        self.names, self.lengths, self.selected, self.run_selected, self.plan = names, lengths, selected, run_selected, plan
         self._n_runs_key = None
+
+    def ensure_exchange(self, n_reads, n_bam_files):
+        """(re)allocate the ranks' exchange areas when a read set needs more room; collective"""
+        have_reads, have_files = getattr(self, "_exchange", (0, 0))
+        if n_reads <= have_reads and n_bam_files <= have_files:
+            return
+        from . import sharded
+        want = (max(n_reads, have_reads), max(n_bam_files, have_files, 1))
+        self.ctx.shard_close()             # nobody may still map an area that is about to be reallocated
+        _dist().barrier()
+        handle = self.ctx.shard_alloc(want[0], want[1])
+        sharded.open_over_process_group(self.ctx, self.plan, handle)
+        self._exchange = want
+
+    def run_selected_names(self):
+        sel = getattr(self, "run_selected", None) or self.selected
+        return [n for n, s in zip(self.names, sel) if s]
 
     @property
     def index(self):
@@ -82,6 +113,39 @@ class Session:
                     c.append(idx[target]); s.append(seg[0]); e.append(seg[1])
         self.ctx.set_n_runs(c, s, e)
         self._n_runs_key = key
+
+
+def _world():
+    return int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def _rank():
+    return int(os.environ.get("RANK", "0"))
+
+
+def _dist():
+    """torch.distributed helpers of a multi-GPU run (one process per GPU under torchrun), initialised on first use"""
+    from . import dist as D
+    if _world() > 1 and not D.is_dist():
+        D.init()
+    return D
+
+
+def _by_rank_merge(local: dict, order):
+    """per-contig results of every rank -> one dict in `order` (every contig lives on exactly one rank)"""
+    merged = {}
+    for part in _dist().gather_objects(local):
+        merged.update(part)
+    return {k: merged[k] for k in order if k in merged}
+
+
+def _open_out(path, mode='w'):
+    """output files are written by rank 0 of a multi-GPU run; the other ranks compute the same text and drop it"""
+    return open(path if _rank() == 0 else os.devnull, mode)
+
+
+def _exists(path):
+    return _rank() == 0 and os.path.exists(path)
 
 
 _default_session = None
@@ -113,6 +177,10 @@ class DeviceDepths(Mapping):
 
     def fetch_i32(self, name):
         return self.session.ctx.fetch_depth(self.track, self.session.index[name])
+
+    def order_all(self):
+        """contigs of the run in output order (in a multi-GPU run the mapping itself only holds the owned ones)"""
+        return getattr(self, "_all_names", None) or list(self._names)
 
     def __iter__(self):
         return iter(self._names)
@@ -159,6 +227,19 @@ def write_depth(directory='.', prefix='GCI', depths={}, threads=1):
     session, ctx = depths.session, depths.session.ctx
     idx = session.index
     heads = {target: f'>{target}\n'.encode('utf-8') for target in depths.keys()}
+    if session.plan is not None:
+        # every rank compresses the contigs it owns; rank 0 writes the members in the reference's contig order
+        D = _dist()
+        blob, off = ctx.depth_gzip_track(depths.track, [heads.get(n, b'') for n in session.names])
+        parts = D.allgather_varlen(blob)
+        offs = D.gather_objects(off.tolist())
+        if _rank() == 0:
+            with open(f'{directory}/{prefix}.depth.gz', 'wb') as f:
+                for target in depths.order_all():
+                    c = idx[target]
+                    r = session.plan.owner[c]
+                    f.write(parts[r][offs[r][c]:offs[r][c + 1]].tobytes())
+        return
     with open(f'{directory}/{prefix}.depth.gz', 'wb') as f:
         if list(depths.keys()) == session.selected_names() and all(len(h) <= 4096 for h in heads.values()):
             blob, _ = ctx.depth_gzip_track(depths.track, [heads.get(n, b'') for n in session.names])
@@ -238,7 +319,7 @@ def filter(paf_files=[], bam_files=[], prefix='GCI', map_qual=30, mq_cutoff=50, 
            ovlp_percent=0.9, flank_len=15, directory='.', force=False, log_reads_type='', chrs_list=[], threads=1,
            session=None, write=True):
     """GCI.py:172-312.  Returns (depths, targets_length)."""
-    if os.path.exists(f'{directory}/{prefix}.depth.gz') and force == False:
+    if _exists(f'{directory}/{prefix}.depth.gz') and force == False:
         sys.exit(f'ERROR!!! The file "{directory}/{prefix}.depth.gz" exists\nPlease use "-f" or "--force" to rewrite')
     print(f'Filtering {log_reads_type} alignment files ...')
     session = session or default_session()
@@ -257,20 +338,37 @@ def filter(paf_files=[], bam_files=[], prefix='GCI', map_qual=30, mq_cutoff=50, 
     session.configure(names, lengths, chrs_list)
     if out_order is None:
         out_order = names
-    sel = dict(zip(names, session.selected))
+    sel = dict(zip(names, session.run_selected if session.plan is not None else session.selected))
     targets_length = {n: l for n, l in zip(out_order, (dict(zip(names, lengths))[x] for x in out_order)) if sel[n]}
     track = TRACK_NANO if log_reads_type == 'ONT' else TRACK_HIFI
 
-    ctx.reads_begin(n_reads)
-    for t in pafs:                       # files = paf_lines + samfile_dicts (GCI.py:272)
-        ctx.upload_paf(t)
-    for t in bams:
-        ctx.upload_bam(t)
-    ctx.filter(map_qual, mq_cutoff, iden_percent, clip_percent, ovlp_percent)
     lo, hi = session.scan_hint if session.scan_hint is not None else (NO_FLAGS, NO_FLAGS)
-    ctx.depth(track, flank_len, lo, hi)
-    depths = DeviceDepths(session, track)
-    depths._names = list(targets_length.keys())
+    if session.plan is None:
+        ctx.reads_begin(n_reads)
+        for t in pafs:                       # files = paf_lines + samfile_dicts (GCI.py:272)
+            ctx.upload_paf(t)
+        for t in bams:
+            ctx.upload_bam(t)
+        ctx.filter(map_qual, mq_cutoff, iden_percent, clip_percent, ovlp_percent)
+        ctx.depth(track, flank_len, lo, hi)
+        depths = DeviceDepths(session, track)
+        depths._names = list(targets_length.keys())
+    else:
+        # multi-GPU: this rank holds the records of its contigs and the PAF lines of its home reads; the library
+        # moves winners and survivors between the ranks inside the call (csrc/shard.cu)
+        from . import sharded
+        session.ensure_exchange(n_reads, len(bams))
+        ctx.reads_begin(n_reads)
+        for t in pafs:
+            ctx.upload_paf(sharded.shard_paf(t, session.plan))
+        for t in bams:
+            ctx.upload_bam(sharded.shard_bam(t, session.plan))
+        flo, fhi = (lo, hi) if lo != NO_FLAGS else (-1, 0)
+        ctx.pipeline(track, sum(session.selected), map_qual, mq_cutoff, iden_percent, clip_percent, ovlp_percent,
+                     flank_len, flo, fhi, 0.005)
+        depths = DeviceDepths(session, track)
+        depths._all_names = list(targets_length.keys())
+        depths._names = [n for n in depths._all_names if session.selected[session.index[n]]]
 
     print(f'Filtering {log_reads_type} alignment files done!!!')
     if write:
@@ -293,7 +391,7 @@ def merge_two_type_depth(hifi_depths={}, nano_depths={}, prefix='GCI_two_type', 
                          write=True):
     """GCI.py:332-353."""
     print('Merging HiFi and ONT depth file ...')
-    if os.path.exists(f'{directory}/{prefix}.depth.gz') and force == False:
+    if _exists(f'{directory}/{prefix}.depth.gz') and force == False:
         sys.exit(f'ERROR!!! The file "{directory}/{prefix}.depth.gz" exists\nPlease use "-f" or "--force" to rewrite')
     if not (isinstance(hifi_depths, DeviceDepths) and isinstance(nano_depths, DeviceDepths)
             and hifi_depths.session is nano_depths.session):
@@ -303,6 +401,7 @@ def merge_two_type_depth(hifi_depths={}, nano_depths={}, prefix='GCI_two_type', 
     session.ctx.merge_max(hifi_depths.track, nano_depths.track, TRACK_MERGED, lo, hi)
     merged = DeviceDepths(session, TRACK_MERGED)
     merged._names = list(hifi_depths.keys())
+    merged._all_names = getattr(hifi_depths, "_all_names", None)
     if write:
         write_depth(directory, prefix, merged, threads)
     print('Merging HiFi and ONT depth file done!!!\n\n')
@@ -331,7 +430,9 @@ def collapse_depth_range(depths={}, leftmost=-1, rightmost=0, flank_len=15, star
     for o, name in enumerate(owners):
         a, b = int(off[o]), int(off[o + 1])
         by_name[name] = list(zip(sl[a:b], el[a:b]))
-    for name in depths.keys():           # the depth mapping's own order (a permuted @SQ order keeps its file's)
+    if session.plan is not None:         # every rank scanned its contigs: the BED of the run, on every rank
+        by_name = _by_rank_merge(by_name, depths.order_all())
+    for name in depths.order_all():      # the depth mapping's own order (a permuted @SQ order keeps its file's)
         bed[name] = by_name[name]
     _scan_counter[0] += 1
     bed.session, bed.track, bed.scan_id = session, depths.track, _scan_counter[0]
@@ -342,12 +443,13 @@ def collapse_depth_range(depths={}, leftmost=-1, rightmost=0, flank_len=15, star
 def merge_depth(depths={}, prefix='GCI', threshold=0, flank_len=15, directory='.', force=False, log_reads_type=''):
     """GCI.py:393-419."""
     print(f'Getting {log_reads_type} issues bed file detected by GCI ...')
-    if os.path.exists(f'{directory}/{prefix}.{threshold}.depth.bed') and force == False:
+    if _exists(f'{directory}/{prefix}.{threshold}.depth.bed') and force == False:
         sys.exit(f'ERROR!!! The file "{directory}/{prefix}.{threshold}.depth.bed" exists\nPlease use "-f" or "--force" to rewrite')
     merged_depths_bed = collapse_depth_range(depths, -1, threshold, flank_len, 0)
-    with open(f'{directory}/{prefix}.{threshold}.depth.bed', 'w') as f:
-        for target, segments in merged_depths_bed.items():
-            f.write(''.join(f'{target}\t{s}\t{e}\n' for s, e in segments))
+    if _rank() == 0:
+        with open(f'{directory}/{prefix}.{threshold}.depth.bed', 'w') as f:
+            for target, segments in merged_depths_bed.items():
+                f.write(''.join(f'{target}\t{s}\t{e}\n' for s, e in segments))
     print(f'Getting {log_reads_type} issues bed file done!!!\n\n')
     return merged_depths_bed
 
@@ -381,6 +483,17 @@ def _terms_for_bed(bed, targets_length, dist_percent, flank_len, session):
     ctx = session.ctx
     owners = list(targets_length.keys())
     last = session.__dict__.get("_last_scan", {})
+    if session.plan is not None:
+        # multi-GPU: every rank scores the contigs it owns (the intervals of its last scan are still on its GPU);
+        # the genome row needs every curated length (GCI.py:572-587): they are few and travel as Python lists
+        mine = session.selected_names()
+        n_iv = last[bed.track][1]
+        n50, nctg, lens, off = ctx.score_terms(bed.track, len(mine), n_iv, dist_percent, flank_len)
+        local = {name: (int(n50[o]), int(nctg[o]), lens[off[o]:off[o + 1]].tolist()) for o, name in enumerate(mine)}
+        full = _by_rank_merge(local, owners)
+        all_len = [x for name in owners for x in full[name][2]]
+        return (np.array([full[name][0] for name in owners] + [compute_n50(all_len)], np.int64),
+                np.array([full[name][1] for name in owners] + [sum(full[name][1] for name in owners)], np.int64))
     if isinstance(bed, DeviceBed) and bed.track is not None and last.get(bed.track, (None,))[0] == bed.scan_id \
             and owners == session.selected_names():
         track, n_iv = bed.track, last[bed.track][1]
@@ -402,14 +515,14 @@ def compute_index(targets_length={}, prefix='GCI', directory='.', force=False, m
                   flank_len=15, dist_percent=0.005, regions_bed={}, depths_list=[], threshold=0, chrs_list=[],
                   session=None):
     """GCI.py:522-657."""
-    if os.path.exists(f'{directory}/{prefix}.gci') and force == False:
+    if _exists(f'{directory}/{prefix}.gci') and force == False:
         sys.exit(f'ERROR!!! The file "{directory}/{prefix}.gci" exists\nPlease use "-f" or "--force" to rewrite')
-    with open(f'{directory}/{prefix}.gci', 'w') as f:
+    with _open_out(f'{directory}/{prefix}.gci', 'w') as f:
         pass
     if len(regions_bed) > 0:
-        if os.path.exists(f'{directory}/{prefix}.regions.gci') and force == False:
+        if _exists(f'{directory}/{prefix}.regions.gci') and force == False:
             sys.exit(f'ERROR!!! The file "{directory}/{prefix}.regions.gci" exists\nPlease use "-f" or "--force" to rewrite')
-        with open(f'{directory}/{prefix}.regions.gci', 'w') as f:
+        with _open_out(f'{directory}/{prefix}.regions.gci', 'w') as f:
             f.write('Chromosome\tStart\tEnd\t' + '\t'.join(type_list) + '\n')
 
     print('Computing Theoretical minimum N50 and contigs number ...')
@@ -424,7 +537,7 @@ def compute_index(targets_length={}, prefix='GCI', directory='.', force=False, m
         print(f'Computing Curated N50 and contigs number for {type_list[i]} done!!!')
 
         print(f'Writing results to {directory}/{prefix}.gci ...')
-        with open(f'{directory}/{prefix}.gci', 'a') as f:
+        with _open_out(f'{directory}/{prefix}.gci', 'a') as f:
             f.write(f'{type_list[i]}:\n')
             f.write('Chromosome\tTheoretical maximum N50\tCurated N50\tTheoretical minimum contigs number\tCurated contigs number\tGCI score\n')
             for o, (target, length) in enumerate(targets_length.items()):
@@ -450,11 +563,27 @@ def compute_index(targets_length={}, prefix='GCI', directory='.', force=False, m
             depths = _adopt(depths, session)
             ses, ctx = depths.session, depths.session.ctx
             idx = ses.index
+            if ses.plan is not None:
+                # multi-GPU: every rank scans the regions lying on its contigs; All_regions needs all curated lengths
+                mine = [w for w, (t, _, _) in enumerate(windows) if ses.selected[idx[t]]]
+                local = {}
+                if mine:
+                    n_iv = ctx.scan_windows(depths.track, [idx[windows[w][0]] for w in mine], [windows[w][1] for w in mine],
+                                            [windows[w][2] for w in mine], -1, threshold)
+                    ses.__dict__.setdefault("_last_scan", {})[depths.track] = (None, n_iv)
+                    a50, actg, lens, off = ctx.score_terms(depths.track, len(mine), n_iv, dist_percent, 0)
+                    local = {w: (int(a50[k]), int(actg[k]), lens[off[k]:off[k + 1]].tolist()) for k, w in enumerate(mine)}
+                full = _by_rank_merge(local, range(len(windows)))
+                all_len = [x for w in range(len(windows)) for x in full[w][2]]
+                per_type.append((np.array([full[w][0] for w in range(len(windows))] + [compute_n50(all_len)], np.int64),
+                                 np.array([full[w][1] for w in range(len(windows))] +
+                                          [sum(full[w][1] for w in range(len(windows)))], np.int64)))
+                continue
             n_iv = ctx.scan_windows(depths.track, [idx[t] for t, _, _ in windows], [s for _, s, _ in windows],
                                     [e for _, _, e in windows], -1, threshold)
             ses.__dict__.setdefault("_last_scan", {})[depths.track] = (None, n_iv)
             per_type.append(ctx.score_terms(depths.track, len(windows), n_iv, dist_percent, 0)[:2])
-        with open(f'{directory}/{prefix}.regions.gci', 'a') as f:
+        with _open_out(f'{directory}/{prefix}.regions.gci', 'a') as f:
             for w, (target, start, end) in enumerate(windows):
                 gci = [_gci(int(n50[w]), end - start, int(nctg[w]), 1) for n50, nctg in per_type]
                 f.write(f'{target}\t{start}\t{end}\t' + '\t'.join(map(str, gci)) + '\n')
@@ -473,9 +602,9 @@ def get_Ns_ref(reference=None, prefix='GCI', directory='.', force=False, _parsed
     """GCI.py:18-46."""
     ids, Ns_bed = _parsed if _parsed is not None else _read_reference(reference)
     if len(Ns_bed) > 0:
-        if os.path.exists(f'{directory}/{prefix}.gaps.bed') and force == False:
+        if _exists(f'{directory}/{prefix}.gaps.bed') and force == False:
             sys.exit(f'ERROR!!! The file "{directory}/{prefix}.gaps.bed" exists\nPlease use "-f" or "--force" to rewrite')
-        with open(f'{directory}/{prefix}.gaps.bed', 'w') as f:
+        with _open_out(f'{directory}/{prefix}.gaps.bed', 'w') as f:
             for target, segments in Ns_bed.items():
                 for segment in segments:
                     f.write(f'{target}\t{segment[0]}\t{segment[1]}\n')

@@ -57,6 +57,20 @@ def shard_paf(tab: PafTable, plan: ShardPlan) -> PafTable:
     return PafTable(*[cols[k] for k in _PAF_COLS])
 
 
+def shard_paf_source(tab: PafTable, plan: ShardPlan, bam: AlnTable) -> PafTable:
+    """The PAF lines a rank 'decoded' in a run where every rank decodes a part of the PAF: here the lines of the reads
+    whose first BAM record lies on a contig this rank owns (any partition of the lines by read works; tests and the
+    bench use it so that `deal_paf_over_process_group` has real work to do)."""
+    own = np.asarray(plan.owner) == plan.rank
+    n = int(max(tab.read_id.max(initial=0), bam.read_id.max(initial=0))) + 1
+    first_contig = np.full(n, -1, np.int64)
+    rid = bam.read_id[::-1]
+    first_contig[rid] = bam.ref_id[::-1]                 # the FIRST record of every read wins
+    src = first_contig[tab.read_id]
+    keep = np.flatnonzero(np.where(src >= 0, own[np.clip(src, 0, len(own) - 1)], plan.rank == 0))
+    return PafTable(*[getattr(tab, k)[keep] for k in _PAF_COLS])
+
+
 def configure(ctx, plan: ShardPlan, lengths, name_rank, max_reads, max_bam_files=2):
     """contig table, owners and this rank's exchange area -> its CUDA IPC handle (uint8[64]).  The caller gathers
     every rank's handle and calls ctx.shard_open (processes) or ctx.shard_attach (contexts of one process)."""
@@ -72,3 +86,36 @@ def open_over_process_group(ctx, plan: ShardPlan, handle):
     handles = np.zeros((plan.world, 64), np.int64)
     handles[plan.rank] = handle
     ctx.shard_open(D.allreduce(handles, "sum").astype(np.uint8))
+
+
+def deal_paf_over_process_group(tab: PafTable, plan: ShardPlan) -> PafTable:
+    """Every rank holds the PAF lines it decoded / generated (any reads); returns the lines of the reads THIS rank
+    is home to (home-local ids), moved with one all-to-all.  Lines of one read keep their relative order as long as
+    they all come from one rank."""
+    from . import dist as D
+    if not D.is_dist() or plan.world == 1:
+        return shard_paf(tab, plan)
+    import torch
+    import torch.distributed as dist
+    world = plan.world
+    mat = np.stack([getattr(tab, k).astype(np.int64) for k in _PAF_COLS], axis=1)
+    dst = (tab.read_id % np.uint32(world)).astype(np.int64)
+    order = np.argsort(dst, kind="stable")
+    counts = np.bincount(dst, minlength=world).astype(np.int64)
+    if dist.get_backend() != "nccl":
+        parts = D.allgather_varlen(mat.reshape(-1))
+        allm = np.concatenate([p.reshape(-1, len(_PAF_COLS)) for p in parts])
+        mine = allm[allm[:, 0] % world == plan.rank]
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        send = torch.from_numpy(np.ascontiguousarray(mat[order])).to(dev)
+        c_in = torch.from_numpy(counts).to(dev)
+        c_out = torch.empty_like(c_in)
+        dist.all_to_all_single(c_out, c_in)
+        n_out = [int(x) for x in c_out.cpu().tolist()]
+        recv = torch.empty((sum(n_out), len(_PAF_COLS)), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(recv, send, output_split_sizes=n_out, input_split_sizes=[int(x) for x in counts])
+        mine = recv.cpu().numpy()
+    cols = {k: mine[:, i] for i, k in enumerate(_PAF_COLS)}
+    cols["read_id"] = cols["read_id"] // world
+    return PafTable(*[cols[k] for k in _PAF_COLS])

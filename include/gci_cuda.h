@@ -243,6 +243,8 @@ int gci_shard_config(gci_ctx* ctx, int32_t rank, int32_t world, const int32_t* c
                      const uint8_t* gate_selected /* [n_contigs] or NULL: contigs selected on ANY rank */);
 int gci_shard_alloc(gci_ctx* ctx, uint32_t max_reads, int32_t max_bam_files, gci_ipc_handle* out /* or NULL */);
 int gci_shard_open(gci_ctx* ctx, const gci_ipc_handle* handles /* [world] */);
+/* unmap the peers' areas (before any rank reallocates its own with gci_shard_alloc; the caller puts a barrier between) */
+int gci_shard_close(gci_ctx* ctx);
 /* contexts of one process (tests; several GPUs driven by one process): areas[r] = gci_shard_area of rank r's context */
 void* gci_shard_area(gci_ctx* ctx);
 int gci_shard_attach(gci_ctx* ctx, void* const* areas /* [world] */);
