@@ -49,6 +49,7 @@ FLANK, THRESHOLD, DIST = 15, 0, 0.005
 # algorithmic bytes of the dominant kernel (depth_tile_kernel<flags>), per genome base: 4 B int32 depth
 # written once + 1 bit of issue flag; per event 2 B read; per tile 16 B of tile tables
 BYTES_PER_BASE = 4.0 + 1.0 / 8.0
+ROW_CAP = 16384          # curated lengths per rank in the genome-row exchange (a 3.1 Gbp share holds ~4.5 k)
 
 
 def genome_shape(scale):
@@ -279,7 +280,7 @@ def main():
         # over NVLink peer memory inside every step (csrc/shard.cu); here the PAF lines are dealt to the read homes once
         handle = sharded.configure(ctx, plan, L, w.contigs.name_rank(), w.n_reads, max_bam_files=1)
         sharded.open_over_process_group(ctx, plan, handle)
-        D.init_native_comm(ctx)
+        D.init_native_comm(ctx, cap=ROW_CAP)
         paf = sharded.deal_paf_over_process_group(w.paf, plan)
         owned = np.flatnonzero(plan.owned).tolist()
     else:
@@ -300,7 +301,7 @@ def main():
     def core_step():
         kw = dict(flank_len=FLANK, lo=-1, hi=THRESHOLD, dist_percent=DIST, **PARAMS)
         if world > 1:
-            n_surv, n_iv, n50, nctg, sums, mean, all_ctg, all_len = ctx.pipeline_row(0, nct, sum(L), **kw)
+            n_surv, n_iv, n50, nctg, sums, mean, all_ctg, all_len = ctx.pipeline_row(0, nct, sum(L[c] for c in owned), cap=ROW_CAP, **kw)
             result["mean_depth"] = mean
         else:
             n_surv, n_iv, n50, nctg, sums = ctx.pipeline(0, nct, **kw)

@@ -201,9 +201,14 @@ depth_tile_tma_kernel(const ulonglong2* __restrict__ tile_ps, const uint16_t* __
   const int64_t n_warps = (int64_t)gridDim.x * (GCI_TILE_THREADS / 32);
   int64_t tile = (int64_t)blockIdx.x * (GCI_TILE_THREADS / 32) + warp;
   const ulonglong2 zero2 = make_ulonglong2(0, 0);
-  ulonglong2 ps = tile < n_tiles ? tile_ps[tile] : zero2;                       // current tile
-  ulonglong2 ps1 = tile + n_warps < n_tiles ? tile_ps[tile + n_warps] : zero2;  // next tile
-  uint32_t ev = lane < (uint32_t)(ps.x & 0xffffffffull) ? events[(uint32_t)(ps.y & 0xffffffffull) + lane] : 0u;
+  // software pipeline over the warp's tiles: a tile takes a warp a few hundred cycles, a DRAM round trip about a
+  // thousand, so the tile table entry is requested three tiles ahead and the tile's first 32 events two tiles ahead
+  auto table = [&](int64_t t) { return t < n_tiles ? tile_ps[t] : zero2; };
+  auto first_events = [&](const ulonglong2& p) {
+    return lane < (uint32_t)(p.x & 0xffffffffull) ? (uint32_t)events[(uint32_t)(p.y & 0xffffffffull) + lane] : 0u;
+  };
+  ulonglong2 ps = table(tile), ps1 = table(tile + n_warps), ps2 = table(tile + 2 * n_warps);
+  uint32_t ev = first_events(ps), ev1 = first_events(ps1);
   int cur = 0;
   for (; tile < n_tiles; tile += n_warps, cur ^= 1) {
     int* __restrict__ s_delta = s_warp + cur * GCI_TILE;
@@ -221,9 +226,9 @@ depth_tile_tma_kernel(const ulonglong2* __restrict__ tile_ps, const uint16_t* __
       const uint32_t e = events[ev0 + i];
       atomicAdd(&s_delta[e >> 1], (e & 1u) ? -1 : 1);
     }
-    ps = ps1;
-    ev = lane < (uint32_t)(ps.x & 0xffffffffull) ? events[(uint32_t)(ps.y & 0xffffffffull) + lane] : 0u;
-    ps1 = tile + 2 * n_warps < n_tiles ? tile_ps[tile + 2 * n_warps] : zero2;
+    ps = ps1; ps1 = ps2; ev = ev1;
+    ev1 = first_events(ps1);                                     // events of the tile after the next one
+    ps2 = table(tile + 3 * n_warps);
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < ITERS; it++) {

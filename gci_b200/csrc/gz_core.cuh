@@ -180,9 +180,13 @@ struct GzBitPut {
 };
 
 GZ_HD uint32_t gz_rev(uint32_t v, int bits) {         // Huffman codes go MSB first
+#if defined(__CUDA_ARCH__)
+  return __brev(v) >> (32 - bits);
+#else
   uint32_t r = 0;
   for (int i = 0; i < bits; i++) r |= ((v >> i) & 1u) << (bits - 1 - i);
   return r;
+#endif
 }
 
 template <typename Sink>

@@ -67,21 +67,31 @@ gz_mark_kernel(GzCall call, const int32_t* __restrict__ depth, uint32_t* __restr
   const int32_t* d = depth + s.g0 + p0;
   int carry = p0 > 0 ? d[-1] : 0;                                       // depth of the position before the round
   int count = 0;
+  // a tile inside the range (all but the first / last tile of a contig's range): a run starts where the value
+  // changes, plus at the tile's first position when a member or the range starts there
+  const bool inner = p0 >= s.first && p0 + GCI_TILE <= s.end;
+  const bool forced0 = p0 == s.first || (p0 & (GZ_MEMBER - 1)) == 0;
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     const int4 v = *reinterpret_cast<const int4*>(d + r * 128 + lane * 4);
     int prev = __shfl_up_sync(0xffffffffu, v.w, 1);
     if (lane == 0) prev = carry;
     carry = __shfl_sync(0xffffffffu, v.w, 31);
-    const int64_t p = p0 + r * 128 + lane * 4;
-    uint32_t nib = 0;
-    const int x[5] = {prev, v.x, v.y, v.z, v.w};
+    uint32_t nib;
+    if (inner) {
+      nib = (v.x != prev ? 1u : 0u) | (v.y != v.x ? 2u : 0u) | (v.z != v.y ? 4u : 0u) | (v.w != v.z ? 8u : 0u);
+      if (r == 0 && lane == 0 && forced0) nib |= 1u;
+    } else {
+      const int64_t p = p0 + r * 128 + lane * 4;
+      nib = 0;
+      const int x[5] = {prev, v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int64_t q = p + k;
-      const bool in = q >= s.first && q < s.end;
-      const bool start = q == s.first || (q & (GZ_MEMBER - 1)) == 0 || x[k + 1] != x[k];
-      nib |= (in && start ? 1u : 0u) << k;
+      for (int k = 0; k < 4; k++) {
+        const int64_t q = p + k;
+        const bool in = q >= s.first && q < s.end;
+        const bool start = q == s.first || (q & (GZ_MEMBER - 1)) == 0 || x[k + 1] != x[k];
+        nib |= (in && start ? 1u : 0u) << k;
+      }
     }
     uint32_t word = nib << ((lane & 7) * 4);
     word |= __shfl_xor_sync(0xffffffffu, word, 1);

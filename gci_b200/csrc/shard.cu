@@ -500,10 +500,21 @@ int gci_shard_attach(gci_ctx* ctx, void* const* areas) {
   gci_ctx::Shard& sh = ctx->shard;
   if (!sh.on || !sh.area.p) return ctx->fail(GCI_E_ARG, "gci_shard_attach before gci_shard_alloc");
   ctx->epoch++;
+  cudaSetDevice(ctx->device);
   for (int r = 0; r < sh.world; r++) {
     if (!areas[r]) return ctx->fail(GCI_E_ARG, "gci_shard_attach: no area for rank %d", r);
     sh.peer[r] = r == sh.rank ? sh.area.p : areas[r];
     sh.mapped[r] = false;
+    // an area on another GPU of this process: its pointer is valid here (UVA) once peer access is on
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, areas[r]) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device != ctx->device) {
+      const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return ctx->fail(GCI_E_CUDA, "no peer access from GPU %d to GPU %d: %s", ctx->device, at.device, cudaGetErrorString(e));
+      }
+    }
+    cudaGetLastError();
   }
   sh.opened = true;
   return GCI_OK;

@@ -41,7 +41,7 @@ WORKER = textwrap.dedent("""
     ctx.upload_bam(sharded.shard_bam(w.bam, plan))
     owned = np.flatnonzero(plan.owned)
     for _ in range(3):
-        out = ctx.pipeline_row(0, len(owned), sum(lengths), flank_len=15, lo=-1, hi=0, dist_percent=0.005, **GATES)
+        out = ctx.pipeline_row(0, len(owned), sum(lengths[c] for c in owned.tolist()), flank_len=15, lo=-1, hi=0, dist_percent=0.005, **GATES)
     n_surv = int(D.allreduce(np.array([out[0]], np.int64))[0])
     assert n_surv == want_n, (n_surv, want_n)
     gs, ge, off = ctx.fetch_intervals(0, len(owned))
