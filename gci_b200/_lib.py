@@ -17,7 +17,8 @@ INT32_MIN = -(2 ** 31)
 NO_FLAGS = INT32_MIN
 
 STAGES = {"h2d": 0, "cigar": 1, "gate": 2, "join": 3, "bucket": 4, "depth": 5, "flags": 6, "runs": 7,
-          "max": 8, "mask": 9, "d2h": 10, "paf": 11, "text": 12, "score": 13}
+          "max": 8, "mask": 9, "d2h": 10, "paf": 11, "text": 12, "score": 13, "xdispatch": 14, "xwait": 15,
+          "xconsume": 16}
 
 TRACK_HIFI, TRACK_NANO, TRACK_MERGED = 0, 1, 2
 

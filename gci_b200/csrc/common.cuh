@@ -334,7 +334,25 @@ struct BucketArgs {
   const int64_t* tile_off;
   ulonglong2* tile_ps;     // NULL: no counting
   long long* sums;         // per-contig depth sums
+  int32_t n_contigs;
 };
+
+// The contig table (length, first tile) is looked up once per survivor; from global memory that is two more DRAM
+// round trips at the end of an already long chain of dependent gathers.  Kernels that walk millions of survivors
+// keep it in shared memory when it fits (assemblies have tens to hundreds of contigs).  Block-collective.
+constexpr int GCI_SMEM_CONTIGS = 1024;
+struct ContigCache {
+  int64_t len[GCI_SMEM_CONTIGS];
+  int64_t tile_off[GCI_SMEM_CONTIGS + 1];
+};
+__device__ __forceinline__ void contig_cache_load(ContigCache& cc, BucketArgs& bk) {
+  if (!bk.tile_ps || bk.n_contigs > GCI_SMEM_CONTIGS) return;
+  for (int i = threadIdx.x; i < bk.n_contigs; i += blockDim.x) cc.len[i] = bk.len[i];
+  for (int i = threadIdx.x; i <= bk.n_contigs; i += blockDim.x) cc.tile_off[i] = bk.tile_off[i];
+  __syncthreads();
+  bk.len = cc.len;
+  bk.tile_off = cc.tile_off;
+}
 
 // The two events of one survivor (c < 0: none) go to the tile table with one 64-bit atomic each; its slice length
 // goes to the contig's depth sum and `have` to the survivor count.  Those two land on a handful of hot addresses, so
@@ -386,3 +404,76 @@ struct WarpSums {
     n_have = 0;
   }
 };
+
+// (double)a / (double)b <= lim and >= lim exactly as fp64 div.rn decides them (Python int / int is correctly rounded,
+// GCI.py:165), without paying for an fp64 division on almost every record: a single-precision quotient carries a
+// relative error below 2^-21 here (two conversions + one division, each within 2^-23), so unless it lies within
+// 2^-18 of the limit the comparison is already decided; only the few records on the boundary divide in fp64.
+// |a|, b < 2^40; b > 0.
+__device__ __forceinline__ bool ratio_le(long long a, long long b, double lim) {
+  const float q = __fdividef((float)a, (float)b);
+  const float l = (float)lim;
+  const float tol = fabsf(l) * 3.9e-6f + 1e-30f;
+  if (q < l - tol) return true;
+  if (q > l + tol) return false;
+  return (double)a / (double)b <= lim;
+}
+__device__ __forceinline__ bool ratio_ge(long long a, long long b, double lim) {
+  const float q = __fdividef((float)a, (float)b);
+  const float l = (float)lim;
+  const float tol = fabsf(l) * 3.9e-6f + 1e-30f;
+  if (q > l + tol) return true;
+  if (q < l - tol) return false;
+  return (double)a / (double)b >= lim;
+}
+
+
+// The join of ONE read from the entries of its files (GCI.py:272-301); k[f] < 0 = absent in file f.
+struct JoinEntry { int32_t c, s, e, q; };
+template <class Entry>
+__device__ __forceinline__ bool join_one(int n_files, const long long* k, const Entry& entry, bool hq, double op,
+                                         uint32_t r, unsigned long long* err, int32_t& c, int32_t& s, int32_t& e) {
+  bool have = false;
+  c = -1; s = 0; e = 0;
+  if (n_files == 1) {                                           // :300-301
+    if (k[0] >= 0) {
+      const JoinEntry x = entry(0);
+      have = true;
+      c = x.c; s = x.s; e = x.e;
+    }
+    return have;
+  }
+  bool comm = true;
+  for (int f = 0; f < n_files; f++) comm = comm && (k[f] >= 0);                            // :274-277
+  if (k[0] >= 0 && (hq || comm)) {                                                         // :279-280
+    const JoinEntry x = entry(0);
+    have = true;
+    c = x.c; s = x.s; e = x.e;
+  }
+  for (int f = 1; f < n_files; f++) {                                                       // :281-299
+    if (k[f] < 0) continue;
+    const JoinEntry x = entry(f);
+    if (have) {
+      if (x.c == c) {
+        const long long ov = (long long)min(x.e, e) - (long long)max(x.s, s);
+        if (x.q == 0) {                                                                     // ZeroDivisionError :292
+          atomicOr(err, 8ull);
+          atomicMin(err + 1, (unsigned long long)r);
+          have = false;
+        } else if (!ratio_ge(ov, x.q, op)) {                                                // ovlp / qlen < -op: delete
+          have = false;
+        } else {
+          s = max(x.s, s);
+          e = min(x.e, e);
+        }
+      } else {
+        have = false;
+      }
+    } else if (hq) {
+      have = true;
+      c = x.c; s = x.s; e = x.e;
+    }
+  }
+  return have;
+}
+

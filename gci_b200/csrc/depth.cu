@@ -22,6 +22,8 @@ int gci_scan_tile_pack(gci_ctx* ctx, ulonglong2* tile_ps, int64_t n);   // scan.
 __global__ void __launch_bounds__(256)
 bucket_count_kernel(uint32_t n_reads, const int32_t* __restrict__ sc, const int32_t* __restrict__ ss,
                     const int32_t* __restrict__ se, BucketArgs bk) {
+  __shared__ ContigCache cc;
+  contig_cache_load(cc, bk);
   WarpSums ws;
   ws.init();
   for (uint32_t base = blockIdx.x * blockDim.x; base < n_reads; base += gridDim.x * blockDim.x) {
@@ -36,7 +38,15 @@ __global__ void bucket_fill_kernel(uint32_t n_reads, const int32_t* __restrict__
                                    const int32_t* __restrict__ se, int32_t fl, const int64_t* __restrict__ len,
                                    const int64_t* __restrict__ tile_off,
                                    const ulonglong2* __restrict__ tile_ps, uint32_t* __restrict__ cursor,
-                                   uint16_t* __restrict__ events) {
+                                   uint16_t* __restrict__ events, int32_t n_contigs) {
+  __shared__ ContigCache cc;
+  if (n_contigs <= GCI_SMEM_CONTIGS) {
+    for (int i = threadIdx.x; i < n_contigs; i += blockDim.x) cc.len[i] = len[i];
+    for (int i = threadIdx.x; i <= n_contigs; i += blockDim.x) cc.tile_off[i] = tile_off[i];
+    __syncthreads();
+    len = cc.len;
+    tile_off = cc.tile_off;
+  }
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const Slice sl = survivor_slice(sc[r], ss[r], se[r], fl, len, tile_off);
@@ -541,6 +551,7 @@ int gci_depth_prepare(gci_ctx* ctx, int32_t track, int32_t flank_len, BucketArgs
   bk->tile_off = ctx->d_tile_off.as<int64_t>();
   bk->tile_ps = ctx->tile_cnt.as<ulonglong2>();
   bk->sums = t.sums.as<long long>();
+  bk->n_contigs = ctx->n_contigs;
   return GCI_OK;
 }
 
@@ -575,7 +586,8 @@ int gci_depth_enqueue(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo
   if (nr) {
     bucket_fill_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(
         nr, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(), flank_len,
-        ctx->d_len.as<int64_t>(), ctx->d_tile_off.as<int64_t>(), tile_ps, cursor, ctx->events.as<uint16_t>());
+        ctx->d_len.as<int64_t>(), ctx->d_tile_off.as<int64_t>(), tile_ps, cursor, ctx->events.as<uint16_t>(),
+        ctx->n_contigs);
     GCI_LAUNCH_CHECK(ctx);
   }
   ctx->stage_end();

@@ -151,28 +151,6 @@ struct GateArgs {
   unsigned long long* err;
 };
 
-// (double)a / (double)b <= lim and >= lim exactly as fp64 div.rn decides them (Python int / int is correctly rounded,
-// GCI.py:165), without paying for an fp64 division on almost every record: a single-precision quotient carries a
-// relative error below 2^-21 here (two conversions + one division, each within 2^-23), so unless it lies within
-// 2^-18 of the limit the comparison is already decided; only the few records on the boundary divide in fp64.
-// |a|, b < 2^40; b > 0.
-__device__ __forceinline__ bool ratio_le(long long a, long long b, double lim) {
-  const float q = __fdividef((float)a, (float)b);
-  const float l = (float)lim;
-  const float tol = fabsf(l) * 3.9e-6f + 1e-30f;
-  if (q < l - tol) return true;
-  if (q > l + tol) return false;
-  return (double)a / (double)b <= lim;
-}
-__device__ __forceinline__ bool ratio_ge(long long a, long long b, double lim) {
-  const float q = __fdividef((float)a, (float)b);
-  const float l = (float)lim;
-  const float tol = fabsf(l) * 3.9e-6f + 1e-30f;
-  if (q > l + tol) return true;
-  if (q < l - tol) return false;
-  return (double)a / (double)b >= lim;
-}
-
 __device__ __forceinline__ void gate_one(const GateArgs& g, int64_t r, uint32_t sMx, uint32_t sI, uint32_t sD,
                                          uint32_t sN, uint32_t sS) {
   // every column of the record is requested up front: behind the early returns below the loads would be issued
@@ -618,55 +596,6 @@ struct JoinArgs {
   int n_files;
 };
 
-// The join of ONE read from the entries of its files (GCI.py:272-301); k[f] < 0 = absent in file f.
-struct JoinEntry { int32_t c, s, e, q; };
-template <class Entry>
-__device__ __forceinline__ bool join_one(int n_files, const long long* k, const Entry& entry, bool hq, double op,
-                                         uint32_t r, unsigned long long* err, int32_t& c, int32_t& s, int32_t& e) {
-  bool have = false;
-  c = -1; s = 0; e = 0;
-  if (n_files == 1) {                                           // :300-301
-    if (k[0] >= 0) {
-      const JoinEntry x = entry(0);
-      have = true;
-      c = x.c; s = x.s; e = x.e;
-    }
-    return have;
-  }
-  bool comm = true;
-  for (int f = 0; f < n_files; f++) comm = comm && (k[f] >= 0);                            // :274-277
-  if (k[0] >= 0 && (hq || comm)) {                                                         // :279-280
-    const JoinEntry x = entry(0);
-    have = true;
-    c = x.c; s = x.s; e = x.e;
-  }
-  for (int f = 1; f < n_files; f++) {                                                       // :281-299
-    if (k[f] < 0) continue;
-    const JoinEntry x = entry(f);
-    if (have) {
-      if (x.c == c) {
-        const long long ov = (long long)min(x.e, e) - (long long)max(x.s, s);
-        if (x.q == 0) {                                                                     // ZeroDivisionError :292
-          atomicOr(err, 8ull);
-          atomicMin(err + 1, (unsigned long long)r);
-          have = false;
-        } else if (!ratio_ge(ov, x.q, op)) {                                                // ovlp / qlen < -op: delete
-          have = false;
-        } else {
-          s = max(x.s, s);
-          e = min(x.e, e);
-        }
-      } else {
-        have = false;
-      }
-    } else if (hq) {
-      have = true;
-      c = x.c; s = x.s; e = x.e;
-    }
-  }
-  return have;
-}
-
 // persistent grid: a warp walks 32 consecutive reads per round, so its depth-sum / survivor-count partials stay in
 // registers (WarpSums) until the contig changes.
 // NF = 1, 2: the common shapes (one file; BAM + PAF or two BAMs).  The kernel is a chain of dependent gathers
@@ -679,6 +608,8 @@ __global__ void __launch_bounds__(256)
 join_kernel(JoinArgs a, uint32_t n_reads, const uint8_t* __restrict__ highq, double op,
             int32_t* __restrict__ s_contig, int32_t* __restrict__ s_start, int32_t* __restrict__ s_end,
             unsigned long long* __restrict__ count, unsigned long long* __restrict__ err, BucketArgs bk) {
+  __shared__ ContigCache cc;
+  contig_cache_load(cc, bk);
   WarpSums ws;
   ws.init();
   if (NF == 0) {

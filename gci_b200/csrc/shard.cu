@@ -8,35 +8,34 @@
 //   owner of the contig      BAM gates + last-record-wins dedup on the records it holds
 //        |   dispatch 1      every per-file winner row (read, contig, start, end, qlen, high-quality mark) is stored
 //        v                   straight into the inbox of the read's home over NVLink peer memory
-//   home of the read         PAF election for its reads (the host deals PAF lines by read), merge of the inbox rows
-//        |                   (highest contig wins, GCI.py:268-270), the join of all files for its reads
+//   home of the read         PAF election for its reads (the host deals PAF lines by read), the join of all files for
+//        |                   its reads (of the rows several owners sent for one read the highest contig wins, :268-270)
 //        |   dispatch 2      every survivor (contig, start, end) is stored into the inbox of the contig's owner
 //        v
 //   owner of the contig      depth events -> depth tiles -> scan -> score, as on one GPU
 //
 // Both dispatches are all-to-all exchanges written as plain kernels over peer pointers (CUDA IPC between processes):
-// rows go to slots claimed from per-destination counters, then every rank publishes its counts and an epoch flag
-// in the peers' headers and waits for theirs.  Two receive areas alternate by epoch parity (a rank can be at most
-// one step ahead of a peer), the epoch lives in device memory, so the step replays inside a CUDA graph.
+// the row of a read goes to a fixed slot (source rank, home-local read id) and carries the step's epoch as its
+// validity tag, so nothing is counted, claimed or cleared; every rank then raises an epoch flag in the peers' headers
+// and waits for theirs.  Two receive areas alternate by epoch parity (a rank can be at most one step ahead of a
+// peer), the epoch lives in device memory, so the step replays inside a CUDA graph.
 #include <algorithm>
 
 #include "common.cuh"
 
-struct XRow1 { uint32_t read; int32_t contig, start, end, qlen; uint32_t hq; };   // 24 B: a file's winner for one read
-struct XRow2 { int32_t contig, start, end, pad; };                                // 16 B: a survivor
+struct XRow1 { uint32_t tag; int32_t contig, start, end, qlen; uint32_t hq; };   // 24 B: a file's winner for one read
+struct XRow2 { int32_t contig, start, end; uint32_t tag; };                       // 16 B: a survivor
+// Slots are DENSE: the row of home read h (= read id / world) sent by rank `src` lives at [src][h], so a sender needs
+// no slot counter and the receiver no merge pass; a row is valid when its tag equals the step's epoch (the areas are
+// never cleared: a stale row carries an older epoch).
 
 // geometry of one rank's exchange area (identical on every rank)
 struct XLayout {
   int world, files;
-  long long cap1, cap2;
-  // header, in 8-byte words: [epoch | flag[2 phases][2 parities][world] | err]
+  long long cap1, cap2;          // home reads per rank (rows per source)
+  // header, in 8-byte words: [epoch | flag[2 phases][2 parities][world]]
   __host__ __device__ long long flag_word(int phase, int par, int src) const { return 1 + ((phase * 2 + par) * world + src); }
-  __host__ __device__ long long err_word() const { return 1 + 4LL * world; }
-  // then counts (u32): cnt1[2 parities][files][world], cnt2[2 parities][world]
-  __host__ __device__ long long cnt_base() const { return (err_word() + 1) * 8; }
-  __host__ __device__ long long cnt1_off(int par, int f, int src) const { return cnt_base() + 4LL * ((par * files + f) * world + src); }
-  __host__ __device__ long long cnt2_off(int par, int src) const { return cnt_base() + 4LL * (2LL * files * world + par * world + src); }
-  __host__ __device__ long long rows1_base() const { return (cnt_base() + 4LL * (2LL * files * world + 2LL * world) + 255) & ~255LL; }
+  __host__ __device__ long long rows1_base() const { return ((1 + 4LL * world) * 8 + 255) & ~255LL; }
   __host__ __device__ long long rows1_off(int par, int f, int src) const {
     return rows1_base() + (long long)sizeof(XRow1) * cap1 * ((par * files + f) * (long long)world + src);
   }
@@ -50,72 +49,42 @@ struct XLayout {
 struct XPeers { char* area[GCI_MAX_RANKS]; };
 constexpr unsigned long long XCHG_TIMEOUT_NS = 8000000000ull;
 
-// ---- step begin: advance the epoch, clear the send cursors --------------------------------------------------
-__global__ void xchg_begin_kernel(char* mine, uint32_t* send_cnt, int n) {
+// ---- step begin: advance the epoch ---------------------------------------------------------------------------
+__global__ void xchg_begin_kernel(char* mine) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *reinterpret_cast<unsigned long long*>(mine) += 1;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) send_cnt[i] = 0;
-}
-
-// slot for one row per destination rank: rows of one CTA are counted in shared memory, one global atomic per
-// (CTA, destination) claims the range.  Block-collective.
-__device__ __forceinline__ uint32_t claim_slot(uint32_t* cursor /* [world] */, int dst, bool active, int world) {
-  __shared__ uint32_t s_cnt[GCI_MAX_RANKS], s_base[GCI_MAX_RANKS];
-  if (threadIdx.x < GCI_MAX_RANKS) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  uint32_t local = 0;
-  if (active) local = atomicAdd(&s_cnt[dst], 1u);
-  __syncthreads();
-  if ((int)threadIdx.x < world && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], s_cnt[threadIdx.x]);
-  __syncthreads();
-  const uint32_t slot = active ? s_base[dst] + local : 0u;
-  __syncthreads();                                   // the shared counters are reused by the next call
-  return slot;
 }
 
 // ---- dispatch 1: per-file winners to the home of their read --------------------------------------------------
+// thread per global read id: consecutive reads go to consecutive destinations, so the lanes of a warp that talk to
+// one destination write consecutive 24-byte rows there
 __global__ void __launch_bounds__(256)
 dispatch1_kernel(XLayout lay, XPeers peers, int me, int f, uint32_t n_reads, const long long* __restrict__ win,
                  const int32_t* __restrict__ ref_id, const int32_t* __restrict__ start, const int32_t* __restrict__ end,
-                 const int32_t* __restrict__ qlen, const uint8_t* __restrict__ highq, uint32_t* __restrict__ send_cnt,
-                 unsigned long long* __restrict__ err) {
+                 const int32_t* __restrict__ qlen, const uint8_t* __restrict__ highq) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_reads) return;
+  const long long k = win[q];
+  if (k < 0) return;
   const unsigned long long epoch = *reinterpret_cast<const unsigned long long*>(peers.area[me]);
   const int par = (int)(epoch & 1ull);
-  long long k = -1;
-  if (q < n_reads) k = win[q];
-  const bool act = k >= 0;
-  const int dst = (int)(q % (uint32_t)lay.world);
-  const uint32_t slot = claim_slot(send_cnt + f * lay.world, dst, act, lay.world);
-  if (!act) return;
   const uint32_t i = (uint32_t)(k & 0xffffffffll);
-  XRow1 row{q, ref_id[i], start[i], end[i], qlen[i], (uint32_t)highq[q]};
-  if ((long long)slot >= lay.cap1) {                 // cannot happen: a source sends at most one row per home read
-    atomicOr(err, 128ull);
-    return;
-  }
-  XRow1* dstp = reinterpret_cast<XRow1*>(peers.area[dst] + lay.rows1_off(par, f, me)) + slot;
+  const XRow1 row{(uint32_t)epoch, ref_id[i], start[i], end[i], qlen[i], (uint32_t)highq[q]};
+  const uint32_t w = (uint32_t)lay.world;
+  XRow1* dstp = reinterpret_cast<XRow1*>(peers.area[q % w] + lay.rows1_off(par, f, me)) + q / w;
   // 24 bytes as three 8-byte stores (rows are 8-byte aligned)
   const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&row);
   unsigned long long* d = reinterpret_cast<unsigned long long*>(dstp);
   d[0] = src[0]; d[1] = src[1]; d[2] = src[2];
 }
 
-// ---- publish the counts of one phase at every peer, then raise the flag ----------------------------------------
-__global__ void xchg_signal_kernel(XLayout lay, XPeers peers, int me, int phase, int n_files, const uint32_t* send_cnt) {
+// ---- raise this rank's flag of one phase at every peer ---------------------------------------------------------
+__global__ void xchg_signal_kernel(XLayout lay, XPeers peers, int me, int phase) {
   const int dst = threadIdx.x;
   if (dst >= lay.world) return;
   const unsigned long long epoch = *reinterpret_cast<const unsigned long long*>(peers.area[me]);
   const int par = (int)(epoch & 1ull);
-  __threadfence_system();
-  char* area = peers.area[dst];
-  if (phase == 0) {
-    for (int f = 0; f < n_files; f++)
-      *reinterpret_cast<volatile uint32_t*>(area + lay.cnt1_off(par, f, me)) = send_cnt[f * lay.world + dst];
-  } else {
-    *reinterpret_cast<volatile uint32_t*>(area + lay.cnt2_off(par, me)) = send_cnt[lay.files * lay.world + dst];
-  }
-  __threadfence_system();
-  *(reinterpret_cast<volatile unsigned long long*>(area) + lay.flag_word(phase, par, me)) = epoch;
+  __threadfence_system();                             // the rows of the kernels before this one are out
+  *(reinterpret_cast<volatile unsigned long long*>(peers.area[dst]) + lay.flag_word(phase, par, me)) = epoch;
 }
 
 // ---- wait until every source's flag of this phase shows the step's epoch ---------------------------------------
@@ -139,28 +108,11 @@ __global__ void xchg_wait_kernel(XLayout lay, char* mine, int phase, unsigned lo
   __threadfence_system();
 }
 
-// ---- home: merge the inbox rows of one file (highest contig wins, the reference's fetch order) ----------------
-__global__ void __launch_bounds__(256)
-merge1_kernel(XLayout lay, const char* __restrict__ mine, int f, long long* __restrict__ hwin, uint8_t* __restrict__ hq_home) {
-  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;       // (source, slot)
-  const int src = (int)(g / lay.cap1);
-  const long long slot = g - (long long)src * lay.cap1;
-  if (src >= lay.world) return;
-  const int par = (int)(*reinterpret_cast<const unsigned long long*>(mine) & 1ull);
-  if (slot >= (long long)*reinterpret_cast<const uint32_t*>(mine + lay.cnt1_off(par, f, src))) return;
-  // row index over the whole rows1 block (both parities, all files): what home_join_kernel dereferences
-  const long long G = (lay.rows1_off(par, f, 0) - lay.rows1_base()) / (long long)sizeof(XRow1) + g;
-  const XRow1 r = reinterpret_cast<const XRow1*>(mine + lay.rows1_base())[G];
-  const uint32_t h = r.read / (uint32_t)lay.world;
-  atomicMax(hwin + h, ((long long)r.contig << 32) | G);
-  if (r.hq) hq_home[h] = 1;
-}
-
-// ---- home: the join of all files for the reads homed here (GCI.py:272-301), survivors to their contig's owner ---
+// ---- home: the join of all files for the reads homed here (GCI.py:268-301), survivors to their contig's owner ---
 struct HomeFile {
-  const long long* win;       // [n_home]: entry of the home read (low 32 bits), < 0 = absent in this file
-  const int32_t *c, *s, *e, *q;   // fields of entry 0
-  int stride;                 // int32 words between entries (1: separate columns, 6: inbox rows)
+  int bam;                        // >= 0: inbox rows of BAM upload `bam` (index among the BAM files); < 0: a table
+  const long long* win;           // table: [n_home] entry of the home read, < 0 = absent
+  const int32_t *c, *s, *e, *q;   // table columns
 };
 struct HomeArgs {
   HomeFile f[GCI_MAX_FILES];
@@ -169,67 +121,51 @@ struct HomeArgs {
 
 __global__ void __launch_bounds__(256)
 home_join_kernel(XLayout lay, XPeers peers, int me, HomeArgs a, uint32_t n_home, const uint8_t* __restrict__ hq_home,
-                 double op, const int32_t* __restrict__ owner, int32_t n_contigs, uint32_t* __restrict__ send_cnt,
-                 unsigned long long* __restrict__ count, unsigned long long* __restrict__ err) {
+                 double op, const int32_t* __restrict__ owner, int32_t n_contigs, unsigned long long* __restrict__ count,
+                 unsigned long long* __restrict__ err) {
   const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-  const int par = (int)(*reinterpret_cast<const unsigned long long*>(peers.area[me]) & 1ull);
+  const char* mine = peers.area[me];
+  const unsigned long long epoch = *reinterpret_cast<const unsigned long long*>(mine);
+  const int par = (int)(epoch & 1ull);
+  const uint32_t tag = (uint32_t)epoch;
   bool have = false;
   int32_t c = -1, s = 0, e = 0;
-  auto entry = [&a](int f, long long k, int32_t& cf, int32_t& sf, int32_t& ef, int32_t& qf) {
-    const HomeFile& hf = a.f[f];
-    const long long i = (long long)(uint32_t)(k & 0xffffffffll) * hf.stride;
-    cf = hf.c[i]; sf = hf.s[i]; ef = hf.e[i]; qf = hf.q[i];
-  };
   if (h < n_home) {
-    const long long k0 = a.f[0].win[h];
-    int32_t cf, sf, ef, qf;
-    if (a.n_files == 1) {                                                 // :300-301
-      if (k0 >= 0) { entry(0, k0, cf, sf, ef, qf); have = true; c = cf; s = sf; e = ef; }
-    } else {
-      bool comm = true;
-      for (int f = 0; f < a.n_files; f++) comm = comm && (a.f[f].win[h] >= 0);           // :274-277
-      const bool hq = hq_home[h] != 0;
-      if (k0 >= 0 && (hq || comm)) {                                                     // :279-280
-        entry(0, k0, cf, sf, ef, qf);
-        have = true; c = cf; s = sf; e = ef;
-      }
-      for (int f = 1; f < a.n_files; f++) {                                               // :281-299
-        const long long k = a.f[f].win[h];
-        if (k < 0) continue;
-        entry(f, k, cf, sf, ef, qf);
-        if (have) {
-          if (cf == c) {
-            const long long ov = (long long)min(ef, e) - (long long)max(sf, s);
-            if (qf == 0) {                                                                // ZeroDivisionError :292
-              atomicOr(err, 8ull);
-              atomicMin(err + 1, (unsigned long long)h * lay.world + me);
-              have = false;
-            } else if ((double)ov / (double)qf < op) {
-              have = false;
-            } else {
-              s = max(sf, s);
-              e = min(ef, e);
-            }
-          } else {
-            have = false;
+    long long k[GCI_MAX_FILES];
+    JoinEntry x[GCI_MAX_FILES];
+    bool hq = hq_home[h] != 0;
+    for (int f = 0; f < a.n_files; f++) {
+      const HomeFile& hf = a.f[f];
+      k[f] = -1;
+      x[f] = JoinEntry{-1, 0, 0, 0};
+      if (hf.bam < 0) {
+        k[f] = hf.win[h];
+        if (k[f] >= 0) {
+          const uint32_t i = (uint32_t)(k[f] & 0xffffffffll);
+          x[f] = JoinEntry{hf.c[i], hf.s[i], hf.e[i], hf.q[i]};
+        }
+      } else {
+        // one candidate row per source rank; the highest contig wins (the reference's fetch order, GCI.py:260-269),
+        // the high-quality marks of every rank's records count (:167-168)
+        for (int src = 0; src < lay.world; src++) {
+          const XRow1* row = reinterpret_cast<const XRow1*>(mine + lay.rows1_off(par, hf.bam, src)) + h;
+          const uint2* w2 = reinterpret_cast<const uint2*>(row);               // rows are 8-byte aligned
+          const uint2 r0 = w2[0], r1 = w2[1], r2 = w2[2];                     // (tag, contig) (start, end) (qlen, hq)
+          if (r0.x != tag) continue;
+          hq = hq || r2.y != 0;
+          if ((int32_t)r0.y > x[f].c) {
+            x[f] = JoinEntry{(int32_t)r0.y, (int32_t)r1.x, (int32_t)r1.y, (int32_t)r2.x};
+            k[f] = src;
           }
-        } else if (hq) {
-          have = true;
-          c = cf; s = sf; e = ef;
         }
       }
     }
-  }
-  const bool send = have && c >= 0 && c < n_contigs;
-  const int dst = send ? owner[c] : 0;
-  const bool act = send && dst >= 0 && dst < lay.world;
-  const uint32_t slot = claim_slot(send_cnt + lay.files * lay.world, act ? dst : 0, act, lay.world);
-  if (act) {
-    if ((long long)slot < lay.cap2) {
-      XRow2* p = reinterpret_cast<XRow2*>(peers.area[dst] + lay.rows2_off(par, me)) + slot;
-      *reinterpret_cast<int4*>(p) = make_int4(c, s, e, 0);
-    } else {
-      atomicOr(err, 128ull);
+    have = join_one(a.n_files, k, [&x](int f) { return x[f]; }, a.n_files > 1 && hq, op, h * (uint32_t)lay.world + me,
+                    err, c, s, e);
+    if (have && c >= 0 && c < n_contigs) {
+      const int dst = owner[c];
+      XRow2* p = reinterpret_cast<XRow2*>(peers.area[dst] + lay.rows2_off(par, me)) + h;
+      *reinterpret_cast<int4*>(p) = make_int4(c, s, e, (int)tag);
     }
   }
   // survivors evaluated here (the global count is the sum over the ranks)
@@ -248,20 +184,20 @@ home_join_kernel(XLayout lay, XPeers peers, int me, HomeArgs a, uint32_t n_home,
 __global__ void __launch_bounds__(256)
 consume2_kernel(XLayout lay, const char* __restrict__ mine, int32_t* __restrict__ s_contig, int32_t* __restrict__ s_start,
                 int32_t* __restrict__ s_end, BucketArgs bk) {
-  const int par = (int)(*reinterpret_cast<const unsigned long long*>(mine) & 1ull);
+  __shared__ ContigCache cc;
+  contig_cache_load(cc, bk);
+  const unsigned long long epoch = *reinterpret_cast<const unsigned long long*>(mine);
+  const int par = (int)(epoch & 1ull);
+  const uint32_t tag = (uint32_t)epoch;
   const long long n_slots = lay.cap2 * lay.world;
   WarpSums ws;
   ws.init();
   for (long long base = blockIdx.x * (long long)blockDim.x; base < n_slots; base += gridDim.x * (long long)blockDim.x) {
-    const long long g = base + threadIdx.x;                                   // (source, slot)
+    const long long g = base + threadIdx.x;                                   // (source, home read)
     int32_t c = -1, s = 0, e = 0;
     if (g < n_slots) {
-      const int src = (int)(g / lay.cap2);
-      const long long slot = g - (long long)src * lay.cap2;
-      if (slot < (long long)*reinterpret_cast<const uint32_t*>(mine + lay.cnt2_off(par, src))) {
-        const int4 r = *reinterpret_cast<const int4*>(mine + lay.rows2_off(par, 0) + (long long)sizeof(XRow2) * g);
-        c = r.x; s = r.y; e = r.z;
-      }
+      const int4 r = *reinterpret_cast<const int4*>(mine + lay.rows2_off(par, 0) + (long long)sizeof(XRow2) * g);
+      if ((uint32_t)r.w == tag) { c = r.x; s = r.y; e = r.z; }
       s_contig[g] = c;
       s_start[g] = s;
       s_end[g] = e;
@@ -300,58 +236,43 @@ int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t f
   int n_bam = 0;
   for (size_t i = 0; i < ctx->n_files; i++) n_bam += ctx->files[i].kind == 0 ? 1 : 0;
   if (n_bam > sh.max_files) return ctx->fail(GCI_E_ARG, "sharded read set: %d BAM files, exchange sized for %d", n_bam, sh.max_files);
-  uint32_t* send_cnt = sh.send_cnt.as<uint32_t>();
   unsigned long long* d_err = ctx->d_err.as<unsigned long long>();
   ctx->counted_track = -1;
-  ctx->stage_begin(GCI_ST_JOIN);
-  xchg_begin_kernel<<<1, 128, 0, ctx->stream>>>(mine, send_cnt, (sh.max_files + 1) * sh.world);
+  ctx->stage_begin(GCI_ST_XDISPATCH);
+  xchg_begin_kernel<<<1, 32, 0, ctx->stream>>>(mine);
   GCI_LAUNCH_CHECK(ctx);
   // dispatch 1: BAM winners to the read homes
+  HomeArgs ha;
+  memset(&ha, 0, sizeof ha);
+  ha.n_files = (int)ctx->n_files;
   int f = 0;
   for (size_t i = 0; i < ctx->n_files; i++) {
     FileTable& ft = ctx->files[i];
-    if (ft.kind != 0) continue;
+    HomeFile& hf = ha.f[i];
+    if (ft.kind != 0) {
+      // a table indexed by home read: the PAF election over home-local ids (or a caller's table with such ids)
+      hf.bam = -1;
+      hf.win = ft.win.as<long long>();
+      hf.c = ft.ref_id.as<int32_t>(); hf.s = ft.start.as<int32_t>(); hf.e = ft.end.as<int32_t>(); hf.q = ft.qlen.as<int32_t>();
+      continue;
+    }
     BamFile& b = ctx->bam[ft.src];
     if (ctx->n_reads) {
       dispatch1_kernel<<<(ctx->n_reads + 255) / 256, 256, 0, ctx->stream>>>(
           lay, peers, sh.rank, f, ctx->n_reads, ft.win.as<long long>(), b.ref_id.as<int32_t>(), b.ref_start.as<int32_t>(),
-          b.ref_end.as<int32_t>(), b.qlen.as<int32_t>(), ctx->highq.as<uint8_t>(), send_cnt, d_err);
+          b.ref_end.as<int32_t>(), b.qlen.as<int32_t>(), ctx->highq.as<uint8_t>());
       GCI_LAUNCH_CHECK(ctx);
     }
-    f++;
+    hf.bam = f++;
   }
-  xchg_signal_kernel<<<1, 32, 0, ctx->stream>>>(lay, peers, sh.rank, 0, n_bam, send_cnt);
+  xchg_signal_kernel<<<1, 32, 0, ctx->stream>>>(lay, peers, sh.rank, 0);
   GCI_LAUNCH_CHECK(ctx);
+  ctx->stage_end();
+  ctx->stage_begin(GCI_ST_XWAIT);
   xchg_wait_kernel<<<1, 32, 0, ctx->stream>>>(lay, mine, 0, d_err);
   GCI_LAUNCH_CHECK(ctx);
-  // home: merge the inbox rows per BAM file, then join all files of the home reads
-  HomeArgs ha;
-  memset(&ha, 0, sizeof ha);
-  ha.n_files = (int)ctx->n_files;
-  f = 0;
-  const size_t nh = std::max<uint32_t>(1, sh.n_home);
-  const XRow1* row0 = reinterpret_cast<const XRow1*>(mine + lay.rows1_base());
-  for (size_t i = 0; i < ctx->n_files; i++) {
-    FileTable& ft = ctx->files[i];
-    HomeFile& hf = ha.f[i];
-    if (ft.kind == 0) {
-      GCI_TRY(ctx->ensure(sh.hwin[f], 8 * nh));
-      GCI_CUDA_TRY(ctx, cudaMemsetAsync(sh.hwin[f].p, 0xff, 8 * nh, ctx->stream));
-      const long long rows = lay.cap1 * (long long)lay.world;
-      merge1_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(lay, mine, f, sh.hwin[f].as<long long>(),
-                                                                            sh.hq_home.as<uint8_t>());
-      GCI_LAUNCH_CHECK(ctx);
-      hf.win = sh.hwin[f].as<long long>();
-      hf.c = &row0->contig; hf.s = &row0->start; hf.e = &row0->end; hf.q = &row0->qlen;
-      hf.stride = (int)(sizeof(XRow1) / 4);
-      f++;
-    } else {
-      // a table indexed by home read: the PAF election over home-local ids (or a caller's table with such ids)
-      hf.win = ft.win.as<long long>();
-      hf.c = ft.ref_id.as<int32_t>(); hf.s = ft.start.as<int32_t>(); hf.e = ft.end.as<int32_t>(); hf.q = ft.qlen.as<int32_t>();
-      hf.stride = 1;
-    }
-  }
+  ctx->stage_end();
+  // home: join all files of the home reads, survivors to the owners of their contigs
   const size_t slots = (size_t)std::max<int64_t>(1, sh.surv_slots);
   GCI_TRY(ctx->ensure(ctx->surv_contig, 4 * slots));
   GCI_TRY(ctx->ensure(ctx->surv_start, 4 * slots));
@@ -359,17 +280,22 @@ int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t f
   BucketArgs bk;
   memset(&bk, 0, sizeof bk);
   if (track >= 0) GCI_TRY(gci_depth_prepare(ctx, track, flank_len, &bk));
+  ctx->stage_begin(GCI_ST_JOIN);
   if (sh.n_home) {
     home_join_kernel<<<(sh.n_home + 255) / 256, 256, 0, ctx->stream>>>(
         lay, peers, sh.rank, ha, sh.n_home, sh.hq_home.as<uint8_t>(), op, sh.d_owner.as<int32_t>(), ctx->n_contigs,
-        send_cnt, d_err + 2, d_err);
+        d_err + 2, d_err);
     GCI_LAUNCH_CHECK(ctx);
   }
-  xchg_signal_kernel<<<1, 32, 0, ctx->stream>>>(lay, peers, sh.rank, 1, n_bam, send_cnt);
+  xchg_signal_kernel<<<1, 32, 0, ctx->stream>>>(lay, peers, sh.rank, 1);
   GCI_LAUNCH_CHECK(ctx);
+  ctx->stage_end();
+  ctx->stage_begin(GCI_ST_XWAIT);
   xchg_wait_kernel<<<1, 32, 0, ctx->stream>>>(lay, mine, 1, d_err);
   GCI_LAUNCH_CHECK(ctx);
+  ctx->stage_end();
   // owner: the survivors that arrived, their depth events counted on the way
+  ctx->stage_begin(GCI_ST_XCONSUME);
   consume2_kernel<<<(unsigned)std::min<int64_t>((sh.surv_slots + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
       lay, mine, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(), bk);
   GCI_LAUNCH_CHECK(ctx);
@@ -431,14 +357,13 @@ int gci_shard_alloc(gci_ctx* ctx, uint32_t max_reads, int32_t max_bam_files, gci
   ctx->epoch++;
   sh.opened = false;
   sh.max_files = max_bam_files;
-  sh.cap1 = sh.cap2 = ((int64_t)max_reads + sh.world - 1) / sh.world + 1;
+  sh.cap1 = sh.cap2 = ((int64_t)max_reads + sh.world - 1) / sh.world;
   sh.surv_slots = sh.cap2 * sh.world;
   const XLayout lay = make_layout(ctx);
-  if (2LL * lay.files * lay.world * lay.cap1 >= (1LL << 32)) return ctx->fail(GCI_E_ARG, "exchange area: too many rows");
   sh.area_bytes = (size_t)lay.total();
   GCI_TRY(ctx->ensure(sh.area, sh.area_bytes));
-  GCI_CUDA_TRY(ctx, cudaMemsetAsync(sh.area.p, 0, (size_t)lay.rows1_base(), ctx->stream));   // header: epoch, flags, counts
-  GCI_TRY(ctx->ensure(sh.send_cnt, 4 * (size_t)(sh.max_files + 1) * sh.world));
+  // epoch, flags AND rows: a row is valid when its tag equals the epoch, so recycled memory must not hold old rows
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(sh.area.p, 0, sh.area_bytes, ctx->stream));
   GCI_TRY(ctx->ensure(sh.hq_home, (size_t)sh.cap1 + 16));
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (out) {

@@ -645,7 +645,7 @@ def _prepare_directory(directory, prefix):
     if directory.endswith('/'):
         directory = '/'.join(directory.split('/')[:-1])
     if not os.path.exists(directory):
-        os.makedirs(directory)
+        os.makedirs(directory, exist_ok=True)      # (several ranks of a multi-GPU run may get here together)
     else:
         for mode, what in ((os.R_OK, 'read'), (os.W_OK, 'write')):
             if not os.access(directory, mode):

@@ -47,7 +47,9 @@ enum {
 enum {
   GCI_ST_H2D = 0, GCI_ST_CIGAR = 1, GCI_ST_GATE = 2, GCI_ST_JOIN = 3, GCI_ST_BUCKET = 4,
   GCI_ST_DEPTH = 5, GCI_ST_FLAGS = 6, GCI_ST_RUNS = 7, GCI_ST_MAX = 8, GCI_ST_MASK = 9,
-  GCI_ST_D2H = 10, GCI_ST_PAF = 11, GCI_ST_TEXT = 12, GCI_ST_SCORE = 13, GCI_ST_COUNT = 14
+  GCI_ST_D2H = 10, GCI_ST_PAF = 11, GCI_ST_TEXT = 12, GCI_ST_SCORE = 13,
+  /* read-set exchange of a sharded run (shard.cu): dispatch to the read homes, waiting for the peers, survivors in */
+  GCI_ST_XDISPATCH = 14, GCI_ST_XWAIT = 15, GCI_ST_XCONSUME = 16, GCI_ST_COUNT = 17
 };
 
 /* ---- context ------------------------------------------------------------------------ */
