@@ -325,14 +325,13 @@ __device__ __forceinline__ Slice survivor_slice(int32_t c, int32_t s, int32_t e,
   return r;
 }
 
-constexpr unsigned long long EV_PLUS = 1ull + (1ull << 32);            // count+1, net+1
-constexpr unsigned long long EV_MINUS = 1ull + 0xffffffff00000000ull;  // count+1, net-1
 
 struct BucketArgs {
   int32_t fl;
   const int64_t* len;
   const int64_t* tile_off;
-  ulonglong2* tile_ps;     // NULL: no counting
+  uint32_t* cnt_start;     // per tile: +1 events (reads starting in the tile); NULL: no counting
+  uint32_t* cnt_end;       // per tile: -1 events
   long long* sums;         // per-contig depth sums
   int32_t n_contigs;
 };
@@ -346,7 +345,7 @@ struct ContigCache {
   int64_t tile_off[GCI_SMEM_CONTIGS + 1];
 };
 __device__ __forceinline__ void contig_cache_load(ContigCache& cc, BucketArgs& bk) {
-  if (!bk.tile_ps || bk.n_contigs > GCI_SMEM_CONTIGS) return;
+  if (!bk.cnt_start || bk.n_contigs > GCI_SMEM_CONTIGS) return;
   for (int i = threadIdx.x; i < bk.n_contigs; i += blockDim.x) cc.len[i] = bk.len[i];
   for (int i = threadIdx.x; i <= bk.n_contigs; i += blockDim.x) cc.tile_off[i] = bk.tile_off[i];
   __syncthreads();
@@ -354,7 +353,7 @@ __device__ __forceinline__ void contig_cache_load(ContigCache& cc, BucketArgs& b
   bk.tile_off = cc.tile_off;
 }
 
-// The two events of one survivor (c < 0: none) go to the tile table with one 64-bit atomic each; its slice length
+// The two events of one survivor (c < 0: none) are counted per tile with one 32-bit atomic each; its slice length
 // goes to the contig's depth sum and `have` to the survivor count.  Those two land on a handful of hot addresses, so
 // they are accumulated per WARP in registers across the iterations of a grid-stride loop (consecutive reads sit on
 // the same contig) and flushed when the contig changes and at the end: a launch over millions of reads sends a few
@@ -366,11 +365,11 @@ struct WarpSums {
   __device__ __forceinline__ void init() { cur_c = -1; cur_sum = 0; n_have = 0; }
   __device__ __forceinline__ void add(const BucketArgs& bk, int32_t c, int32_t s, int32_t e, bool have) {
     long long covered = 0;
-    if (bk.tile_ps && c >= 0) {
+    if (bk.cnt_start && c >= 0) {
       const Slice sl = survivor_slice(c, s, e, bk.fl, bk.len, bk.tile_off);
       if (sl.ok) {
-        atomicAdd(&bk.tile_ps[sl.tile_a].x, EV_PLUS);
-        atomicAdd(&bk.tile_ps[sl.tile_b].x, EV_MINUS);
+        atomicAdd(&bk.cnt_start[sl.tile_a], 1u);       // one 32-bit RED per event into a dense array: several times
+        atomicAdd(&bk.cnt_end[sl.tile_b], 1u);         // the rate of a 64-bit RED into a 16-byte strided table
         covered = sl.b - sl.a;
       } else {
         c = -1;

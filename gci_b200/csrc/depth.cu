@@ -7,7 +7,8 @@
 
 #include "common.cuh"
 
-int gci_scan_tile_pack(gci_ctx* ctx, ulonglong2* tile_ps, int64_t n);   // scan.cu: .y = exclusive scan of .x
+int gci_scan_tile_pack(gci_ctx* ctx, const uint32_t* cnt_start, const uint32_t* cnt_end, ulonglong2* tile_ps,
+                       int64_t n);   // scan.cu: .x = (events, net) of the tile, .y = exclusive scan of .x
 
 // ================================================================================================
 // K5  event buckets
@@ -211,14 +212,14 @@ depth_tile_tma_kernel(const ulonglong2* __restrict__ tile_ps, const uint16_t* __
   const int64_t n_warps = (int64_t)gridDim.x * (GCI_TILE_THREADS / 32);
   int64_t tile = (int64_t)blockIdx.x * (GCI_TILE_THREADS / 32) + warp;
   const ulonglong2 zero2 = make_ulonglong2(0, 0);
-  // software pipeline over the warp's tiles: a tile takes a warp a few hundred cycles, a DRAM round trip about a
-  // thousand, so the tile table entry is requested three tiles ahead and the tile's first 32 events two tiles ahead
+  // software pipeline over the warp's tiles: the tile table entry is requested two tiles ahead, the tile's first 32
+  // events one tile ahead (a deeper pipeline measured slower: profiles/r02g)
   auto table = [&](int64_t t) { return t < n_tiles ? tile_ps[t] : zero2; };
   auto first_events = [&](const ulonglong2& p) {
     return lane < (uint32_t)(p.x & 0xffffffffull) ? (uint32_t)events[(uint32_t)(p.y & 0xffffffffull) + lane] : 0u;
   };
-  ulonglong2 ps = table(tile), ps1 = table(tile + n_warps), ps2 = table(tile + 2 * n_warps);
-  uint32_t ev = first_events(ps), ev1 = first_events(ps1);
+  ulonglong2 ps = table(tile), ps1 = table(tile + n_warps);
+  uint32_t ev = first_events(ps);
   int cur = 0;
   for (; tile < n_tiles; tile += n_warps, cur ^= 1) {
     int* __restrict__ s_delta = s_warp + cur * GCI_TILE;
@@ -236,9 +237,9 @@ depth_tile_tma_kernel(const ulonglong2* __restrict__ tile_ps, const uint16_t* __
       const uint32_t e = events[ev0 + i];
       atomicAdd(&s_delta[e >> 1], (e & 1u) ? -1 : 1);
     }
-    ps = ps1; ps1 = ps2; ev = ev1;
-    ev1 = first_events(ps1);                                     // events of the tile after the next one
-    ps2 = table(tile + 3 * n_warps);
+    ps = ps1;
+    ev = first_events(ps);                                       // events of the next tile
+    ps1 = table(tile + 2 * n_warps);
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < ITERS; it++) {
@@ -541,15 +542,18 @@ int gci_depth_prepare(gci_ctx* ctx, int32_t track, int32_t flank_len, BucketArgs
   memset(bk, 0, sizeof *bk);
   if (nt == 0) return GCI_OK;
   if (nt >= (int64_t(1) << 31)) return ctx->fail(GCI_E_ARG, "too many tiles");
-  // one scratch block zeroed with one memset: per tile (pack u64, scan u64) interleaved + fill cursor u32
-  GCI_TRY(ctx->ensure(ctx->tile_cnt, 20 * (size_t)nt));
+  // one scratch block: per tile the table entry (pack u64, scan u64: written by the tile scan), then three u32
+  // arrays zeroed with one memset: start events, end events, fill cursor
+  GCI_TRY(ctx->ensure(ctx->tile_cnt, 28 * (size_t)nt));
   GCI_TRY(ctx->ensure(ctx->events, 2 * 2 * (size_t)std::max<int64_t>(1, ctx->shard.on ? ctx->shard.surv_slots : (int64_t)ctx->n_reads)));
-  GCI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->tile_cnt.p, 0, 20 * (size_t)nt, ctx->stream));
+  uint32_t* counts = reinterpret_cast<uint32_t*>(ctx->tile_cnt.as<ulonglong2>() + nt);   // [start | end | cursor]
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, 12 * (size_t)nt, ctx->stream));
   GCI_CUDA_TRY(ctx, cudaMemsetAsync(t.sums.p, 0, sizeof(int64_t) * (size_t)ctx->n_contigs, ctx->stream));
   bk->fl = flank_len;
   bk->len = ctx->d_len.as<int64_t>();
   bk->tile_off = ctx->d_tile_off.as<int64_t>();
-  bk->tile_ps = ctx->tile_cnt.as<ulonglong2>();
+  bk->cnt_start = counts;
+  bk->cnt_end = counts + nt;
   bk->sums = t.sums.as<long long>();
   bk->n_contigs = ctx->n_contigs;
   return GCI_OK;
@@ -581,8 +585,9 @@ int gci_depth_enqueue(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo
     return GCI_OK;
   }
   ulonglong2* tile_ps = ctx->tile_cnt.as<ulonglong2>();
-  uint32_t* cursor = reinterpret_cast<uint32_t*>(tile_ps + nt);
-  GCI_TRY(gci_scan_tile_pack(ctx, tile_ps, nt));
+  uint32_t* counts = reinterpret_cast<uint32_t*>(tile_ps + nt);
+  uint32_t* cursor = counts + 2 * nt;
+  GCI_TRY(gci_scan_tile_pack(ctx, counts, counts + nt, tile_ps, nt));
   if (nr) {
     bucket_fill_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(
         nr, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(), flank_len,

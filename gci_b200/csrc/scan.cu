@@ -142,16 +142,25 @@ int gci_exclusive_scan_i32(gci_ctx* ctx, const int32_t* in, int32_t* out, int64_
   return exclusive_scan<int32_t, int32_t>(ctx, in, out, n, nullptr);
 }
 
-// tile table: .y = exclusive scan of .x over all tiles (packed (count, net) sums never carry between halves)
+// tile table from the per-tile event counts: .x = (events, net) packed = (starts + ends) | (starts - ends) << 32,
+// .y = exclusive scan of .x over all tiles (the two halves never carry into each other: a contig's nets sum to 0 and
+// the event total stays below 2^32)
+__device__ __forceinline__ unsigned long long tile_pack(const uint32_t* __restrict__ cs, const uint32_t* __restrict__ ce,
+                                                       int64_t i) {
+  const uint32_t s = cs[i], e = ce[i];
+  return (unsigned long long)(s + e) | ((unsigned long long)(uint32_t)(s - e) << 32);
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS)
-tile_reduce_kernel(const ulonglong2* __restrict__ ps, int64_t n, unsigned long long* __restrict__ block_sums) {
+tile_reduce_kernel(const uint32_t* __restrict__ cs, const uint32_t* __restrict__ ce, int64_t n,
+                   unsigned long long* __restrict__ block_sums) {
   __shared__ unsigned long long s_w[SCAN_THREADS / 32];
   const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK;
   unsigned long long v = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) {
     const int64_t i = base + k * SCAN_THREADS + threadIdx.x;
-    if (i < n) v += ps[i].x;
+    if (i < n) v += tile_pack(cs, ce, i);
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -167,7 +176,8 @@ tile_reduce_kernel(const ulonglong2* __restrict__ ps, int64_t n, unsigned long l
 // block b first sums the block totals before it (at most a few thousand values: 10 Gbp = 4 768 blocks), so
 // no separate scan of the block totals is needed between the reduce and the apply pass
 __global__ void __launch_bounds__(SCAN_THREADS)
-tile_apply_kernel(ulonglong2* __restrict__ ps, int64_t n, const unsigned long long* __restrict__ block_sums) {
+tile_apply_kernel(const uint32_t* __restrict__ cs, const uint32_t* __restrict__ ce, ulonglong2* __restrict__ ps,
+                  int64_t n, const unsigned long long* __restrict__ block_sums) {
   __shared__ unsigned long long s_w[SCAN_THREADS / 32];
   __shared__ unsigned long long s_b[SCAN_THREADS / 32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -182,7 +192,7 @@ tile_apply_kernel(ulonglong2* __restrict__ ps, int64_t n, const unsigned long lo
   unsigned long long item[SCAN_ITEMS], sum = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) {
-    item[k] = base + k < n ? ps[base + k].x : 0ull;
+    item[k] = base + k < n ? tile_pack(cs, ce, base + k) : 0ull;
     sum += item[k];
   }
   unsigned long long incl = sum;
@@ -200,24 +210,25 @@ tile_apply_kernel(ulonglong2* __restrict__ ps, int64_t n, const unsigned long lo
   unsigned long long run = woff + incl - sum;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) {
-    if (base + k < n) ps[base + k].y = run;
+    if (base + k < n) ps[base + k] = make_ulonglong2(item[k], run);
     run += item[k];
   }
 }
 
-int gci_scan_tile_pack(gci_ctx* ctx, ulonglong2* tile_ps, int64_t n) {
+int gci_scan_tile_pack(gci_ctx* ctx, const uint32_t* cnt_start, const uint32_t* cnt_end, ulonglong2* tile_ps, int64_t n) {
   if (n <= 0) return GCI_OK;
   const int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
   if (nb == 1) {
-    tile_apply_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(tile_ps, n, nullptr);
+    tile_apply_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(cnt_start, cnt_end, tile_ps, n, nullptr);
     GCI_LAUNCH_CHECK(ctx);
     return GCI_OK;
   }
   DevBuf& sums = ctx->scan_lvl[6];
   GCI_TRY(ctx->ensure(sums, 8 * (size_t)nb));
-  tile_reduce_kernel<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(tile_ps, n, sums.as<unsigned long long>());
+  tile_reduce_kernel<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(cnt_start, cnt_end, n, sums.as<unsigned long long>());
   GCI_LAUNCH_CHECK(ctx);
-  tile_apply_kernel<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(tile_ps, n, sums.as<unsigned long long>());
+  tile_apply_kernel<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(cnt_start, cnt_end, tile_ps, n,
+                                                                   sums.as<unsigned long long>());
   GCI_LAUNCH_CHECK(ctx);
   return GCI_OK;
 }

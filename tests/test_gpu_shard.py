@@ -1,8 +1,8 @@
 """Read sets sharded over several ranks (csrc/shard.cu): contexts standing in for the ranks of a multi-GPU run — one
 host thread per rank, the exchange areas attached directly when the ranks share a process — must give, on the
 contigs each rank owns, exactly the depth / intervals / score terms of the C port on the whole read set.  With one
-visible GPU all ranks live on it (the peer stores become local stores, the protocol is the same); with several GPUs
-the ranks are spread over them, and tests/test_gpu_multi.py runs the real thing with one process per GPU."""
+GPU all ranks live on it (the peer stores become local stores, the protocol is the same);
+tests/test_gpu_multi.py runs the real thing with one process per GPU."""
 import threading
 
 import numpy as np
@@ -36,10 +36,10 @@ def _run_ranks(world, fn):
 
 def _sharded_run(world, names, lengths, n_reads, pafs, bams, selected=None, steps=3, devices=None, op=0.9):
     """-> per rank: dict(owned contigs, depth per owned contig, intervals, n50, nctg, sums, n_surv)"""
-    import torch
     from gci_b200._lib import Context
-    n_dev = torch.cuda.device_count()
-    ctxs = [Context((devices or list(range(n_dev)))[r % n_dev] if n_dev else 0) for r in range(world)]
+    # all ranks on one GPU: the protocol (slots, epochs, flags, parities) is what this file checks; ranks on different
+    # GPUs are one PROCESS per GPU in production (CUDA IPC) and tests/test_gpu_multi.py runs exactly that
+    ctxs = [Context((devices or [0])[r % len(devices or [0])]) for r in range(world)]
     plans = [sharded.make_plan(r, world, lengths, selected) for r in range(world)]
     rank_of = CO.name_rank(names)
     out = [None] * world
