@@ -91,6 +91,7 @@ _SIGNATURES = {
     "gci_comm_p2p_disable": (C.c_int, [_p]),
     "gci_genome_row": (C.c_int, [_p, _i32, _f64, _i32, _i64, _i64, _p, _p, _p, _p]),
     "gci_score_terms_sums": (C.c_int, [_p, _i32, _f64, _i32, _p, _p, _i64, _p, _p, _p]),
+    "gci_sliding_window": (C.c_int, [_p, _i32, _i32, _i64, _i64, _i64, _i64, _p, _p, _p, _p, C.POINTER(_i64)]),
     "gci_shard_config": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "gci_shard_alloc": (C.c_int, [_p, _u32, _i32, _p]),
     "gci_shard_open": (C.c_int, [_p, _p]),
@@ -484,6 +485,19 @@ class Context:
 
     def comm_p2p_disable(self):
         self._check(self._lib.gci_comm_p2p_disable(self._h))
+
+    def sliding_window(self, track, contig, start, end, window_size):
+        """points of GCI.py:660-705 over depth[start:end]: -> (idx, num, den, kind) int64 x3 + uint8, position order"""
+        n = _i64()
+        self._check(self._lib.gci_sliding_window(self._h, track, contig, int(start), int(end), int(window_size), 0,
+                                                 None, None, None, None, C.byref(n)))
+        k = n.value
+        idx, num, den = (np.empty(k, np.int64) for _ in range(3))
+        kind = np.empty(k, np.uint8)
+        if k:
+            self._check(self._lib.gci_sliding_window(self._h, track, contig, int(start), int(end), int(window_size), k,
+                                                     _ptr(idx), _ptr(num), _ptr(den), _ptr(kind), C.byref(n)))
+        return idx, num, den, kind
 
     # ---- read sets sharded over ranks (contig owners, read homes) ----
     def shard_config(self, rank, world, contig_owner, gate_selected=None):

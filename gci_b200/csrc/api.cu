@@ -206,6 +206,8 @@ void gci_destroy(gci_ctx* ctx) {
   for (DevBuf* d : {&ctx->gz_tables, &ctx->gz_seg, &ctx->gz_hdr, &ctx->gz_bits, &ctx->gz_tile_cnt, &ctx->gz_tile_run,
                     &ctx->gz_run_pos, &ctx->gz_run_val, &ctx->gz_msize, &ctx->gz_moff, &ctx->gz_packed})
     ctx->release(*d);
+  ctx->release(ctx->sw_csum);
+  ctx->release(ctx->sw_out);
   for (auto& d : ctx->scan_lvl) ctx->release(d);
   for (auto& d : ctx->tmp) ctx->release(d);
   for (cudaEvent_t e : ctx->timer.pool) cudaEventDestroy(e);

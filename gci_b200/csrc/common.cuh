@@ -161,6 +161,7 @@ struct gci_ctx {
   bool gz_valid = false;
   unsigned long long gz_key = 0;
   int64_t gz_total = 0;
+  DevBuf sw_csum, sw_out;           // plot feed (gci_sliding_window): depth prefix sums of the region, packed points
   DevBuf gz_tables, gz_seg, gz_hdr, gz_bits, gz_tile_cnt, gz_tile_run, gz_run_pos, gz_run_val, gz_msize, gz_moff, gz_packed;
 
   // NCCL communicator of a multi-GPU run (comm.cu; resolved with dlopen)

@@ -969,3 +969,114 @@ int gci_score_terms_sums(gci_ctx* ctx, int32_t track, double dist_percent, int32
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// plot feed: sliding_window_average_depth (GCI.py:660-705) on the device
+// ================================================================================================
+// The reference walks one contig (or region) base by base: every zero-depth base is a point of its own and closes the
+// open window; non-zero bases fill windows of `window_size`; a window still open at a zero or at the end is averaged
+// over what it holds.  Here: the zero runs of the region come from the run extraction above (bit = depth == 0), the
+// region is then a sequence of SEGMENTS nz0 z0 nz1 z1 ... nz_last; a zero segment of length m emits m points, a
+// non-zero one floor(m / ws) full windows + one short window for the rest.  Points are (index, sum, count, kind);
+// the division, the clip at max_depth and the Mbp positions stay on the host (Python float semantics).
+struct SwArgs {
+  const int32_t* iv_start;   // zero runs [start, end) in contig coordinates, sorted
+  const int32_t* iv_end;
+  int64_t n_iv;
+  int64_t lo, hi;            // region [lo, hi) in contig coordinates
+  int64_t ws;
+};
+
+// segment k: even = non-zero stretch before zero run k/2 (or the tail), odd = zero run (k-1)/2
+__device__ __forceinline__ void sw_segment(const SwArgs& a, int64_t k, int64_t& s, int64_t& e) {
+  const int64_t j = k >> 1;
+  if (k & 1) { s = a.iv_start[j]; e = a.iv_end[j]; return; }
+  s = j == 0 ? a.lo : (int64_t)a.iv_end[j - 1];
+  e = j == a.n_iv ? a.hi : (int64_t)a.iv_start[j];
+}
+
+__global__ void sw_count_kernel(SwArgs a, int64_t n_seg, int32_t* __restrict__ cnt) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= n_seg) return;
+  int64_t s, e;
+  sw_segment(a, k, s, e);
+  const int64_t m = max((int64_t)0, e - s);
+  cnt[k] = (int32_t)((k & 1) ? m : m / a.ws + (m % a.ws ? 1 : 0));
+}
+
+__global__ void sw_emit_kernel(SwArgs a, int64_t n_seg, const int64_t* __restrict__ seg_off, int64_t n_points,
+                               const int64_t* __restrict__ csum /* exclusive prefix of depth over [lo, hi) */,
+                               int64_t* __restrict__ o_idx, int64_t* __restrict__ o_num, int64_t* __restrict__ o_den,
+                               uint8_t* __restrict__ o_kind) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= n_points) return;
+  const int64_t k = upper_bound_minus1<int64_t>(seg_off, n_seg, p);
+  // (segments without points share their offset with the next one: step to the last segment starting at or before p
+  // that really holds it)
+  int64_t s, e;
+  sw_segment(a, k, s, e);
+  const int64_t r = p - seg_off[k];
+  if (k & 1) {                                     // a zero base: a point of its own, value 0
+    o_idx[p] = s + r - a.lo; o_num[p] = 0; o_den[p] = 1; o_kind[p] = 2;
+    return;
+  }
+  const int64_t w0 = s + r * a.ws, w1 = min(e, w0 + a.ws);
+  o_idx[p] = w1 - 1 - a.lo;                        // reported at the window's last base
+  o_num[p] = csum[w1 - a.lo] - csum[w0 - a.lo];
+  o_den[p] = w1 - w0;
+  o_kind[p] = (w1 - w0 == a.ws) ? 0 : 1;
+}
+
+extern "C" int gci_sliding_window(gci_ctx* ctx, int32_t track, int32_t contig, int64_t start, int64_t end,
+                                  int64_t window_size, int64_t cap, int64_t* idx, int64_t* num, int64_t* den,
+                                  uint8_t* kind, int64_t* n_points) {
+  if (!ctx || track < 0 || track >= GCI_MAX_TRACKS || !n_points || window_size < 1) return GCI_E_ARG;
+  cudaSetDevice(ctx->device);
+  Track& t = ctx->track[track];
+  if (!t.allocated) return ctx->fail(GCI_E_ARG, "gci_sliding_window: track %d holds no depth", track);
+  if (contig < 0 || contig >= ctx->n_contigs || !ctx->selected[contig] || start < 0 || end < start || end > ctx->len[contig])
+    return ctx->fail(GCI_E_ARG, "gci_sliding_window: bad region");
+  *n_points = 0;
+  const int64_t n = end - start;
+  if (n == 0) return GCI_OK;
+  // zero runs of the region: depth == 0  <=>  -1 < depth <= 0 for the non-negative depths of a track
+  int64_t n_iv = 0;
+  const int64_t cs = start, ce = end;
+  GCI_TRY(gci_scan_windows(ctx, track, -1, 0, 1, &contig, &cs, &ce, &n_iv));
+  const int64_t n_seg = 2 * n_iv + 1;
+  DevBuf &cnt = ctx->tmp[6], &off = ctx->tmp[7], &csum = ctx->sw_csum, &out = ctx->sw_out;
+  GCI_TRY(ctx->ensure(cnt, 4 * (size_t)(n_seg + 1)));
+  GCI_TRY(ctx->ensure(off, 8 * (size_t)(n_seg + 2)));
+  GCI_TRY(ctx->ensure(csum, 8 * (size_t)(n + 1)));
+  SwArgs a{t.iv_start.as<int32_t>(), t.iv_end.as<int32_t>(), n_iv, start, end, window_size};
+  sw_count_kernel<<<(unsigned)((n_seg + 255) / 256), 256, 0, ctx->stream>>>(a, n_seg, cnt.as<int32_t>());
+  GCI_LAUNCH_CHECK(ctx);
+  GCI_CUDA_TRY(ctx, cudaMemsetAsync(cnt.as<int32_t>() + n_seg, 0, 4, ctx->stream));
+  GCI_TRY(gci_exclusive_scan_i64_from_i32(ctx, cnt.as<int32_t>(), off.as<int64_t>(), n_seg + 1, nullptr));
+  int64_t* h = (int64_t*)ctx->pinned(8);
+  if (!h) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
+  GCI_TRY(gci_d2h(ctx, h, off.as<int64_t>() + n_seg, 8));
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const int64_t P = *h;
+  *n_points = P;
+  if (!idx && !num && !den && !kind) return GCI_OK;
+  if (cap < P) return ctx->fail(GCI_E_ARG, "gci_sliding_window: %lld points, buffers hold %lld", (long long)P, (long long)cap);
+  if (P == 0) return GCI_OK;
+  const int32_t* d = t.depth.as<int32_t>() + ctx->pos_off[contig] + start;
+  GCI_TRY(gci_exclusive_scan_i64_from_i32(ctx, d, csum.as<int64_t>(), n, csum.as<int64_t>() + n));
+  GCI_TRY(ctx->ensure(out, 25 * (size_t)P));
+  int64_t* o_idx = out.as<int64_t>();
+  int64_t* o_num = o_idx + P;
+  int64_t* o_den = o_num + P;
+  uint8_t* o_kind = reinterpret_cast<uint8_t*>(o_den + P);
+  sw_emit_kernel<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(a, n_seg, off.as<int64_t>(), P, csum.as<int64_t>(),
+                                                                      o_idx, o_num, o_den, o_kind);
+  GCI_LAUNCH_CHECK(ctx);
+  if (idx) GCI_TRY(gci_d2h(ctx, idx, o_idx, 8 * (size_t)P));
+  if (num) GCI_TRY(gci_d2h(ctx, num, o_num, 8 * (size_t)P));
+  if (den) GCI_TRY(gci_d2h(ctx, den, o_den, 8 * (size_t)P));
+  if (kind) GCI_TRY(gci_d2h(ctx, kind, o_kind, (size_t)P));
+  GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return GCI_OK;
+}
+

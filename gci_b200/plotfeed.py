@@ -63,3 +63,21 @@ def sliding_window_average_depth(depths=[], window_size=50000, max_depth=None, s
     avg = (num / den).tolist()
     values = [0 if kd == 2 else (max_depth if a > max_depth else a) for kd, a in zip(kind.tolist(), avg)]
     return positions, np.array(values)
+
+
+def sliding_window_average_depth_gpu(ctx, track, contig, lo, hi, window_size=50000, max_depth=None, start=0, target=None):
+    """The same result for depth[lo:hi] of one contig of a GPU depth track (`Context.sliding_window`: zero runs from the
+    run extraction, window sums from a device prefix sum); only the points come back — the division, the clip and the
+    Mbp positions are finished here with the reference's Python types, so values and dtype are the reference's."""
+    n = int(hi) - int(lo)
+    if n < window_size:
+        print(f'Warning!!! The length ({n}) of plotting region ({target}:{start}-{start + n}) is '
+              f'less than the window size ({window_size}), and therefore the window size will be 1 bp', file=sys.stderr)
+        window_size = 1
+    if n <= 0:
+        return [], np.array([])
+    idx, num, den, kind = ctx.sliding_window(track, contig, lo, hi, window_size)
+    positions = ((idx + start) / 1e6).tolist()
+    avg = (num / den).tolist()
+    values = [0 if kd == 2 else (max_depth if a > max_depth else a) for kd, a in zip(kind.tolist(), avg)]
+    return positions, np.array(values)

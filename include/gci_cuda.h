@@ -179,6 +179,15 @@ int gci_fetch_intervals(gci_ctx* ctx, int32_t track, int64_t cap, int32_t* start
 int gci_load_intervals(gci_ctx* ctx, int32_t track, int64_t n_owners, const int32_t* contig,
                        const int64_t* owner_off, const int32_t* start, const int32_t* end);
 
+/* ---- plot feed: sliding_window_average_depth (GCI.py:660-705) over depth[start:end] of one contig ---------------
+   Points in position order: idx = base index inside the region the point is reported at, num / den = sum and number
+   of the bases averaged (the caller divides, clips at max_depth and converts to Mbp like GCI.py:679-704),
+   kind = 0 full window, 1 window cut short by a zero or the end, 2 a zero-depth base (a point of its own).
+   Pass NULL buffers to get the count.  A region shorter than window_size is the CALLER's case (GCI.py:674-676 sets
+   the window to 1).  Uses the track's scan state (like gci_scan_windows). */
+int gci_sliding_window(gci_ctx* ctx, int32_t track, int32_t contig, int64_t start, int64_t end, int64_t window_size,
+                       int64_t cap, int64_t* idx, int64_t* num, int64_t* den, uint8_t* kind, int64_t* n_points);
+
 /* ---- score terms (GCI.py:422-519) --------------------------------------------------------- */
 /* per owner (contig or window) of the last scan: curated N50 of the un-merged complement, number of
    curated contigs after the -dp merge, and the complement lengths themselves (for the genome row).
