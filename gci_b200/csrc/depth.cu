@@ -39,8 +39,11 @@ __global__ void bucket_fill_kernel(uint32_t n_reads, const int32_t* __restrict__
                                    const int32_t* __restrict__ se, int32_t fl, const int64_t* __restrict__ len,
                                    const int64_t* __restrict__ tile_off,
                                    const ulonglong2* __restrict__ tile_ps, uint32_t* __restrict__ cursor,
-                                   uint16_t* __restrict__ events, int32_t n_contigs) {
+                                   uint16_t* __restrict__ events, int32_t n_contigs,
+                                   const uint32_t* __restrict__ n_dev /* survivor count on the device, or NULL */) {
   __shared__ ContigCache cc;
+  const uint32_t limit = n_dev ? *n_dev : n_reads;
+  if (blockIdx.x * blockDim.x >= limit) return;            // (whole CTA: the grid is sized for the slot capacity)
   if (n_contigs <= GCI_SMEM_CONTIGS) {
     for (int i = threadIdx.x; i < n_contigs; i += blockDim.x) cc.len[i] = len[i];
     for (int i = threadIdx.x; i <= n_contigs; i += blockDim.x) cc.tile_off[i] = tile_off[i];
@@ -49,7 +52,7 @@ __global__ void bucket_fill_kernel(uint32_t n_reads, const int32_t* __restrict__
     tile_off = cc.tile_off;
   }
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_reads) return;
+  if (r >= limit) return;
   const Slice sl = survivor_slice(sc[r], ss[r], se[r], fl, len, tile_off);
   if (!sl.ok) return;
   {
@@ -592,7 +595,7 @@ int gci_depth_enqueue(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo
     bucket_fill_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(
         nr, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(), flank_len,
         ctx->d_len.as<int64_t>(), ctx->d_tile_off.as<int64_t>(), tile_ps, cursor, ctx->events.as<uint16_t>(),
-        ctx->n_contigs);
+        ctx->n_contigs, ctx->shard.on ? ctx->shard.send_cnt.as<uint32_t>() + GCI_MAX_RANKS : nullptr);
     GCI_LAUNCH_CHECK(ctx);
   }
   ctx->stage_end();

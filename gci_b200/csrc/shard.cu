@@ -24,18 +24,21 @@
 #include "common.cuh"
 
 struct XRow1 { uint32_t tag; int32_t contig, start, end, qlen; uint32_t hq; };   // 24 B: a file's winner for one read
-struct XRow2 { int32_t contig, start, end; uint32_t tag; };                       // 16 B: a survivor
-// Slots are DENSE: the row of home read h (= read id / world) sent by rank `src` lives at [src][h], so a sender needs
-// no slot counter and the receiver no merge pass; a row is valid when its tag equals the step's epoch (the areas are
-// never cleared: a stale row carries an older epoch).
+struct XRow2 { int32_t contig, start, end, pad; };                                // 16 B: a survivor
+// Winner slots are DENSE: the row of home read h (= read id / world) sent by rank `src` lives at [src][h], so a sender
+// needs no slot counter and the receiver no merge pass; a row is valid when its tag equals the step's epoch (the areas
+// are never cleared: a stale row carries an older epoch).  Survivor rows are COMPACT per (destination, source): the
+// owner of a contig must not scan world x home-reads slots to find the few that are his, so the home claims slots per
+// destination (one atomic per CTA and destination) and publishes the counts with its flag.
 
 // geometry of one rank's exchange area (identical on every rank)
 struct XLayout {
   int world, files;
   long long cap1, cap2;          // home reads per rank (rows per source)
-  // header, in 8-byte words: [epoch | flag[2 phases][2 parities][world]]
+  // header, in 8-byte words: [epoch | flag[2 phases][2 parities][world] | cnt2[2 parities][world]]
   __host__ __device__ long long flag_word(int phase, int par, int src) const { return 1 + ((phase * 2 + par) * world + src); }
-  __host__ __device__ long long rows1_base() const { return ((1 + 4LL * world) * 8 + 255) & ~255LL; }
+  __host__ __device__ long long cnt2_word(int par, int src) const { return 1 + 4LL * world + par * world + src; }
+  __host__ __device__ long long rows1_base() const { return ((1 + 6LL * world) * 8 + 255) & ~255LL; }
   __host__ __device__ long long rows1_off(int par, int f, int src) const {
     return rows1_base() + (long long)sizeof(XRow1) * cap1 * ((par * files + f) * (long long)world + src);
   }
@@ -50,8 +53,23 @@ struct XPeers { char* area[GCI_MAX_RANKS]; };
 constexpr unsigned long long XCHG_TIMEOUT_NS = 8000000000ull;
 
 // ---- step begin: advance the epoch ---------------------------------------------------------------------------
-__global__ void xchg_begin_kernel(char* mine) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) *reinterpret_cast<unsigned long long*>(mine) += 1;
+__global__ void xchg_begin_kernel(char* mine, uint32_t* send_cnt, int world) {
+  if (threadIdx.x == 0) *reinterpret_cast<unsigned long long*>(mine) += 1;
+  if ((int)threadIdx.x < world) send_cnt[threadIdx.x] = 0;
+}
+
+// slot for one row per destination rank: rows of one CTA are counted in shared memory, one global atomic per
+// (CTA, destination) claims the range.  Block-collective.
+__device__ __forceinline__ uint32_t claim_slot(uint32_t* cursor /* [world] */, int dst, bool active, int world) {
+  __shared__ uint32_t s_cnt[GCI_MAX_RANKS], s_base[GCI_MAX_RANKS];
+  if (threadIdx.x < GCI_MAX_RANKS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t local = 0;
+  if (active) local = atomicAdd(&s_cnt[dst], 1u);
+  __syncthreads();
+  if ((int)threadIdx.x < world && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], s_cnt[threadIdx.x]);
+  __syncthreads();
+  return active ? s_base[dst] + local : 0u;
 }
 
 // ---- dispatch 1: per-file winners to the home of their read --------------------------------------------------
@@ -78,13 +96,18 @@ dispatch1_kernel(XLayout lay, XPeers peers, int me, int f, uint32_t n_reads, con
 }
 
 // ---- raise this rank's flag of one phase at every peer ---------------------------------------------------------
-__global__ void xchg_signal_kernel(XLayout lay, XPeers peers, int me, int phase) {
+__global__ void xchg_signal_kernel(XLayout lay, XPeers peers, int me, int phase, const uint32_t* __restrict__ send_cnt) {
   const int dst = threadIdx.x;
   if (dst >= lay.world) return;
   const unsigned long long epoch = *reinterpret_cast<const unsigned long long*>(peers.area[me]);
   const int par = (int)(epoch & 1ull);
+  volatile unsigned long long* hdr = reinterpret_cast<volatile unsigned long long*>(peers.area[dst]);
   __threadfence_system();                             // the rows of the kernels before this one are out
-  *(reinterpret_cast<volatile unsigned long long*>(peers.area[dst]) + lay.flag_word(phase, par, me)) = epoch;
+  if (phase == 1) {
+    hdr[lay.cnt2_word(par, me)] = send_cnt[dst];      // survivors this rank sent to dst
+    __threadfence_system();
+  }
+  hdr[lay.flag_word(phase, par, me)] = epoch;
 }
 
 // ---- wait until every source's flag of this phase shows the step's epoch ---------------------------------------
@@ -121,8 +144,8 @@ struct HomeArgs {
 
 __global__ void __launch_bounds__(256)
 home_join_kernel(XLayout lay, XPeers peers, int me, HomeArgs a, uint32_t n_home, const uint8_t* __restrict__ hq_home,
-                 double op, const int32_t* __restrict__ owner, int32_t n_contigs, unsigned long long* __restrict__ count,
-                 unsigned long long* __restrict__ err) {
+                 double op, const int32_t* __restrict__ owner, int32_t n_contigs, uint32_t* __restrict__ send_cnt,
+                 unsigned long long* __restrict__ count, unsigned long long* __restrict__ err) {
   const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
   const char* mine = peers.area[me];
   const unsigned long long epoch = *reinterpret_cast<const unsigned long long*>(mine);
@@ -162,10 +185,18 @@ home_join_kernel(XLayout lay, XPeers peers, int me, HomeArgs a, uint32_t n_home,
     }
     have = join_one(a.n_files, k, [&x](int f) { return x[f]; }, a.n_files > 1 && hq, op, h * (uint32_t)lay.world + me,
                     err, c, s, e);
-    if (have && c >= 0 && c < n_contigs) {
-      const int dst = owner[c];
-      XRow2* p = reinterpret_cast<XRow2*>(peers.area[dst] + lay.rows2_off(par, me)) + h;
-      *reinterpret_cast<int4*>(p) = make_int4(c, s, e, (int)tag);
+  }
+  {
+    const bool send = have && c >= 0 && c < n_contigs;
+    const int dst = send ? owner[c] : 0;
+    const uint32_t slot = claim_slot(send_cnt, dst, send, lay.world);
+    if (send) {
+      if ((long long)slot < lay.cap2) {
+        XRow2* p = reinterpret_cast<XRow2*>(peers.area[dst] + lay.rows2_off(par, me)) + slot;
+        *reinterpret_cast<int4*>(p) = make_int4(c, s, e, 0);
+      } else {
+        atomicOr(err, 128ull);                        // cannot happen: a home sends at most one survivor per home read
+      }
     }
   }
   // survivors evaluated here (the global count is the sum over the ranks)
@@ -180,24 +211,36 @@ home_join_kernel(XLayout lay, XPeers peers, int me, HomeArgs a, uint32_t n_home,
   }
 }
 
-// ---- owner: survivors of the inbox into the survivor slots, depth events counted on the way ---------------------
+// ---- owner: the survivors every home sent, packed into the survivor arrays, depth events counted on the way -------
 __global__ void __launch_bounds__(256)
 consume2_kernel(XLayout lay, const char* __restrict__ mine, int32_t* __restrict__ s_contig, int32_t* __restrict__ s_start,
-                int32_t* __restrict__ s_end, BucketArgs bk) {
+                int32_t* __restrict__ s_end, uint32_t* __restrict__ n_surv_dev, BucketArgs bk) {
   __shared__ ContigCache cc;
+  __shared__ long long s_off[GCI_MAX_RANKS + 1];
   contig_cache_load(cc, bk);
-  const unsigned long long epoch = *reinterpret_cast<const unsigned long long*>(mine);
-  const int par = (int)(epoch & 1ull);
-  const uint32_t tag = (uint32_t)epoch;
-  const long long n_slots = lay.cap2 * lay.world;
+  const unsigned long long* hdr = reinterpret_cast<const unsigned long long*>(mine);
+  const int par = (int)(hdr[0] & 1ull);
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int r = 0; r < lay.world; r++) {
+      s_off[r] = t;
+      t += (long long)min((unsigned long long)lay.cap2, hdr[lay.cnt2_word(par, r)]);
+    }
+    s_off[lay.world] = t;
+    if (blockIdx.x == 0) *n_surv_dev = (uint32_t)t;
+  }
+  __syncthreads();
+  const long long total = s_off[lay.world];
   WarpSums ws;
   ws.init();
-  for (long long base = blockIdx.x * (long long)blockDim.x; base < n_slots; base += gridDim.x * (long long)blockDim.x) {
-    const long long g = base + threadIdx.x;                                   // (source, home read)
+  for (long long base = blockIdx.x * (long long)blockDim.x; base < total; base += gridDim.x * (long long)blockDim.x) {
+    const long long g = base + threadIdx.x;
     int32_t c = -1, s = 0, e = 0;
-    if (g < n_slots) {
-      const int4 r = *reinterpret_cast<const int4*>(mine + lay.rows2_off(par, 0) + (long long)sizeof(XRow2) * g);
-      if ((uint32_t)r.w == tag) { c = r.x; s = r.y; e = r.z; }
+    if (g < total) {
+      int src = 0;
+      while (src + 1 < lay.world && g >= s_off[src + 1]) src++;
+      const int4 r = *reinterpret_cast<const int4*>(mine + lay.rows2_off(par, src) + (long long)sizeof(XRow2) * (g - s_off[src]));
+      c = r.x; s = r.y; e = r.z;
       s_contig[g] = c;
       s_start[g] = s;
       s_end[g] = e;
@@ -239,7 +282,8 @@ int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t f
   unsigned long long* d_err = ctx->d_err.as<unsigned long long>();
   ctx->counted_track = -1;
   ctx->stage_begin(GCI_ST_XDISPATCH);
-  xchg_begin_kernel<<<1, 32, 0, ctx->stream>>>(mine);
+  uint32_t* send_cnt = sh.send_cnt.as<uint32_t>();
+  xchg_begin_kernel<<<1, 32, 0, ctx->stream>>>(mine, send_cnt, sh.world);
   GCI_LAUNCH_CHECK(ctx);
   // dispatch 1: BAM winners to the read homes
   HomeArgs ha;
@@ -265,7 +309,7 @@ int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t f
     }
     hf.bam = f++;
   }
-  xchg_signal_kernel<<<1, 32, 0, ctx->stream>>>(lay, peers, sh.rank, 0);
+  xchg_signal_kernel<<<1, 32, 0, ctx->stream>>>(lay, peers, sh.rank, 0, send_cnt);
   GCI_LAUNCH_CHECK(ctx);
   ctx->stage_end();
   ctx->stage_begin(GCI_ST_XWAIT);
@@ -284,10 +328,10 @@ int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t f
   if (sh.n_home) {
     home_join_kernel<<<(sh.n_home + 255) / 256, 256, 0, ctx->stream>>>(
         lay, peers, sh.rank, ha, sh.n_home, sh.hq_home.as<uint8_t>(), op, sh.d_owner.as<int32_t>(), ctx->n_contigs,
-        d_err + 2, d_err);
+        send_cnt, d_err + 2, d_err);
     GCI_LAUNCH_CHECK(ctx);
   }
-  xchg_signal_kernel<<<1, 32, 0, ctx->stream>>>(lay, peers, sh.rank, 1);
+  xchg_signal_kernel<<<1, 32, 0, ctx->stream>>>(lay, peers, sh.rank, 1, send_cnt);
   GCI_LAUNCH_CHECK(ctx);
   ctx->stage_end();
   ctx->stage_begin(GCI_ST_XWAIT);
@@ -297,7 +341,8 @@ int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t f
   // owner: the survivors that arrived, their depth events counted on the way
   ctx->stage_begin(GCI_ST_XCONSUME);
   consume2_kernel<<<(unsigned)std::min<int64_t>((sh.surv_slots + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
-      lay, mine, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(), bk);
+      lay, mine, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(),
+      send_cnt + GCI_MAX_RANKS, bk);
   GCI_LAUNCH_CHECK(ctx);
   ctx->stage_end();
   if (track >= 0) {
@@ -365,6 +410,7 @@ int gci_shard_alloc(gci_ctx* ctx, uint32_t max_reads, int32_t max_bam_files, gci
   // epoch, flags AND rows: a row is valid when its tag equals the epoch, so recycled memory must not hold old rows
   GCI_CUDA_TRY(ctx, cudaMemsetAsync(sh.area.p, 0, sh.area_bytes, ctx->stream));
   GCI_TRY(ctx->ensure(sh.hq_home, (size_t)sh.cap1 + 16));
+  GCI_TRY(ctx->ensure(sh.send_cnt, 4 * (GCI_MAX_RANKS + 4)));      // [world] send cursors | survivors received
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (out) {
     static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(gci_ipc_handle), "IPC handle does not fit");
