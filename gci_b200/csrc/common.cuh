@@ -354,6 +354,17 @@ __device__ __forceinline__ void contig_cache_load(ContigCache& cc, BucketArgs& b
   bk.tile_off = cc.tile_off;
 }
 
+// Work split of the persistent kernels: every CTA walks ONE contiguous range of the items, `step` items per round.
+// (A grid-stride loop makes every warp jump by grid x block items per round: each round touches a new page of every
+// array for every warp of the GPU — measured 3-4x slower on the 6 M-read walks of the join / survivor kernels,
+// profiles/r02j — and neighbouring rounds of a warp stop sharing a contig, which the per-warp partial sums rely on.)
+__device__ __forceinline__ void cta_range(long long total, long long step, long long& begin, long long& end) {
+  long long per = (total + gridDim.x - 1) / gridDim.x;
+  per = (per + step - 1) / step * step;
+  begin = min(total, (long long)blockIdx.x * per);
+  end = min(total, begin + per);
+}
+
 // The two events of one survivor (c < 0: none) are counted per tile with one 32-bit atomic each; its slice length
 // goes to the contig's depth sum and `have` to the survivor count.  Those two land on a handful of hot addresses, so
 // they are accumulated per WARP in registers across the iterations of a grid-stride loop (consecutive reads sit on

@@ -679,8 +679,10 @@ join_kernel(JoinArgs a, uint32_t n_reads, const uint8_t* __restrict__ highq, dou
   WarpSums ws;
   ws.init();
   if (NF == 0) {
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n_reads; base += gridDim.x * blockDim.x) {
-      const uint32_t r = base + threadIdx.x;
+    long long begin, end;
+    cta_range(n_reads, blockDim.x, begin, end);
+    for (long long base = begin; base < end; base += blockDim.x) {
+      const uint32_t r = (uint32_t)(base + threadIdx.x);
       bool have = false;
       int32_t c = -1, s = 0, e = 0;
       if (r < n_reads) {
@@ -698,14 +700,16 @@ join_kernel(JoinArgs a, uint32_t n_reads, const uint8_t* __restrict__ highq, dou
     }
   } else {
     const uint32_t span = blockDim.x * JOIN_ILP;
-    for (uint32_t base = blockIdx.x * span; base < n_reads; base += gridDim.x * span) {
+    long long begin, end;
+    cta_range(n_reads, span, begin, end);
+    for (long long base = begin; base < end; base += span) {
       // read j of this thread: base + j * blockDim + tid (a warp still covers 32 consecutive reads per j)
       constexpr int NFX = NF > 0 ? NF : 1;
       long long k[JOIN_ILP][NFX];
       uint8_t hq[JOIN_ILP];
 #pragma unroll
       for (int j = 0; j < JOIN_ILP; j++) {
-        const uint32_t r = base + j * blockDim.x + threadIdx.x;
+        const uint32_t r = (uint32_t)(base + j * blockDim.x + threadIdx.x);
         const bool in = r < n_reads;
 #pragma unroll
         for (int f = 0; f < NF; f++) k[j][f] = in ? a.f[f].win[r] : -1;
@@ -721,7 +725,7 @@ join_kernel(JoinArgs a, uint32_t n_reads, const uint8_t* __restrict__ highq, dou
         }
 #pragma unroll
       for (int j = 0; j < JOIN_ILP; j++) {
-        const uint32_t r = base + j * blockDim.x + threadIdx.x;
+        const uint32_t r = (uint32_t)(base + j * blockDim.x + threadIdx.x);
         int32_t c, s, e;
         const bool have = join_one(NF, k[j], [&](int f) { return x[j][f]; }, hq[j] != 0, op, r, err, c, s, e);
         if (r < n_reads) {
@@ -1136,8 +1140,12 @@ paf_elect_multi_kernel(uint32_t n_reads, PafSet ps, const int32_t* __restrict__ 
   const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
   constexpr uint32_t chunk = PAF_MULTI_CHUNK; // reads per warp round: 8 marks per lane
   constexpr int PER_LANE = PAF_MULTI_CHUNK / 32;
-  for (uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * chunk; base < n_reads;
-       base += n_warps * chunk) {
+  // every warp walks one contiguous range of reads, `chunk` reads per round
+  const uint32_t wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint32_t per_warp = ((n_reads + n_warps - 1) / n_warps + chunk - 1) / chunk * chunk;
+  const uint32_t w_begin = (uint32_t)min((unsigned long long)n_reads, (unsigned long long)wid * per_warp);
+  const uint32_t w_end = (uint32_t)min((unsigned long long)n_reads, (unsigned long long)w_begin + per_warp);
+  for (uint32_t base = w_begin; base < w_end; base += chunk) {
     // lane l looks at reads base + 8 l .. + 7 (one 8-byte load when the range is complete)
     uint32_t mask = 0;
     const uint32_t r0 = base + lane * PER_LANE;

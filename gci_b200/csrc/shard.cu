@@ -233,7 +233,9 @@ consume2_kernel(XLayout lay, const char* __restrict__ mine, int32_t* __restrict_
   const long long total = s_off[lay.world];
   WarpSums ws;
   ws.init();
-  for (long long base = blockIdx.x * (long long)blockDim.x; base < total; base += gridDim.x * (long long)blockDim.x) {
+  long long begin, end;
+  cta_range(total, blockDim.x, begin, end);
+  for (long long base = begin; base < end; base += blockDim.x) {
     const long long g = base + threadIdx.x;
     int32_t c = -1, s = 0, e = 0;
     if (g < total) {

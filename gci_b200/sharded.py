@@ -119,3 +119,47 @@ def deal_paf_over_process_group(tab: PafTable, plan: ShardPlan) -> PafTable:
     cols = {k: mine[:, i] for i, k in enumerate(_PAF_COLS)}
     cols["read_id"] = cols["read_id"] // world
     return PafTable(*[cols[k] for k in _PAF_COLS])
+
+
+def deal_bam_over_process_group(tab: AlnTable, plan: ShardPlan) -> AlnTable:
+    """Every rank holds BAM records of ANY contig (e.g. what it decoded from its part of a file, or what a second
+    aligner placed elsewhere); returns the records lying on the contigs THIS rank owns, coordinate sorted, moved with
+    two all-to-alls (record columns, CIGAR ops).  Records on contigs without an owner here are dropped."""
+    from . import dist as D
+    if not D.is_dist() or plan.world == 1:
+        return shard_bam(tab, plan)
+    import torch
+    import torch.distributed as dist
+    world = plan.world
+    owner = np.asarray(plan.owner, np.int64)
+    rid = tab.ref_id.astype(np.int64)
+    ok = (rid >= 0) & (rid < len(owner))
+    dst = np.where(ok, owner[np.clip(rid, 0, len(owner) - 1)], -1)
+    keep = np.flatnonzero(dst >= 0)
+    order = keep[np.argsort(dst[keep], kind="stable")]
+    t = tab.take(order)
+    n_ops = np.diff(t.cigar_off.astype(np.int64))
+    mat = np.stack([t.ref_id.astype(np.int64), t.ref_start.astype(np.int64), t.mapq.astype(np.int64),
+                    t.flag.astype(np.int64), t.nm.astype(np.int64), t.qlen.astype(np.int64),
+                    t.read_id.astype(np.int64), n_ops], axis=1)
+    d_sorted = dst[order]
+    rec_counts = np.bincount(d_sorted, minlength=world).astype(np.int64)
+    op_counts = np.bincount(d_sorted, weights=n_ops, minlength=world).astype(np.int64)
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def a2a(data, counts, width):
+        c_in = torch.from_numpy(counts).to(dev)
+        c_out = torch.empty_like(c_in)
+        dist.all_to_all_single(c_out, c_in)
+        n_out = [int(x) for x in c_out.cpu().tolist()]
+        send = torch.from_numpy(np.ascontiguousarray(data)).to(dev)
+        shape = (sum(n_out), width) if width else (sum(n_out),)
+        recv = torch.empty(shape, dtype=send.dtype, device=dev)
+        dist.all_to_all_single(recv, send, output_split_sizes=n_out, input_split_sizes=[int(x) for x in counts])
+        return recv.cpu().numpy()
+
+    rec = a2a(mat, rec_counts, mat.shape[1])
+    ops = a2a(t.cigar.astype(np.int64), op_counts, 0).astype(np.uint32)
+    off = np.concatenate([[0], np.cumsum(rec[:, 7])]).astype(np.uint64)
+    got = AlnTable(rec[:, 0], rec[:, 1], rec[:, 2], rec[:, 3], rec[:, 4], rec[:, 5], rec[:, 6], off, ops)
+    return got.take(np.lexsort((got.ref_start, got.ref_id)))

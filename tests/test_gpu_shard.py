@@ -93,8 +93,10 @@ def _check(out, want_d, want_n, lengths, selected=None):
 def test_three_ranks_in_a_fresh_process():
     """Three ranks as contexts of ONE process share the process's hardware launch queues: a rank's waiting kernel can
     sit in front of another rank's kernels in the same queue (a false dependency that one process per GPU — the real
-    deployment — cannot have).  With more queues than streams the in-process stand-in is reliable, so this case runs
-    in a fresh interpreter with CUDA_DEVICE_MAX_CONNECTIONS=32."""
+    deployment — cannot have); and a kernel that is launched for the first time is loaded lazily, which has to wait for
+    the context to go idle — it never does while another rank's waiting kernel spins.  With more queues than streams
+    and eager module loading the in-process stand-in is reliable, so this case runs in a fresh interpreter with
+    CUDA_DEVICE_MAX_CONNECTIONS=32 and CUDA_MODULE_LOADING=EAGER."""
     import os
     import subprocess
     import sys
@@ -102,7 +104,7 @@ def test_three_ranks_in_a_fresh_process():
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_shard as t; "
             "t.test_sharded_bam_plus_paf_equals_whole_read_set(3); print('three ranks ok')") % (root, os.path.join(root, "tests"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
-                       env=dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32"))
+                       env=dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", CUDA_MODULE_LOADING="EAGER"))
     assert r.returncode == 0 and "three ranks ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
