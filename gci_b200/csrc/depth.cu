@@ -99,6 +99,30 @@ __device__ __forceinline__ uint32_t flag4(int a, int b, int c, int d, int lo1, u
          ((uint32_t)(c - lo1) < span ? 4u : 0u) | ((uint32_t)(d - lo1) < span ? 8u : 0u);
 }
 
+// Issue-flag words of one round (256 positions): lane l holds the depths of positions [4l, 4l+4) (oa) and
+// [128+4l, 128+4l+4) (ob).  Almost every round of an assembly holds no issue at all, so the warp first asks whether
+// ANY of its 256 values is inside (lo, hi] — an unsigned minimum per lane and one vote — and only builds the bit
+// masks (two flag4 + a 3-shuffle butterfly) for the rounds that need them.
+__device__ __forceinline__ void emit_flags(uint32_t* __restrict__ flags, int64_t tile, int it, int lane, const int4& oa,
+                                           const int4& ob, int32_t lo1, uint32_t span) {
+  const uint32_t m = min(min(min((uint32_t)(oa.x - lo1), (uint32_t)(oa.y - lo1)), min((uint32_t)(oa.z - lo1), (uint32_t)(oa.w - lo1))),
+                         min(min((uint32_t)(ob.x - lo1), (uint32_t)(ob.y - lo1)), min((uint32_t)(ob.z - lo1), (uint32_t)(ob.w - lo1))));
+  const bool odd = lane & 1;
+  uint32_t acc = 0;
+  if (__any_sync(0xffffffffu, m < span)) {
+    // butterfly: even lanes collect the A-half words, odd lanes the B-half words (3 shuffles for 8 words)
+    const uint32_t na = flag4(oa.x, oa.y, oa.z, oa.w, lo1, span), nb = flag4(ob.x, ob.y, ob.z, ob.w, lo1, span);
+    uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? na : nb, 1);
+    acc = odd ? (got | (nb << 4)) : (na | (got << 4));
+    got = __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc = (lane & 2) ? (got | (acc << 8)) : (acc | (got << 8));
+    got = __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc = (lane & 4) ? (got | (acc << 16)) : (acc | (got << 16));
+  }
+  if ((lane & 6) == 0)   // lanes 8g (A word g) and 8g+1 (B word g)
+    flags[tile * (GCI_TILE / 32) + it * 8 + (odd ? 4 : 0) + (lane >> 3)] = acc;
+}
+
 // exclusive prefix over lanes of a mostly-zero per-lane value: one shuffle per non-zero lane instead of
 // the 5 dependent shuffles of a full warp scan (falls back to the scan when more than 4 lanes are set)
 __device__ __forceinline__ int sparse_excl_scan(int v, int lane, int& total) {
@@ -178,19 +202,7 @@ depth_tile_kernel(const ulonglong2* __restrict__ tile_ps /* (pack, scan) per til
       const int4 ob = make_int4(rb + b0, rb + b1, rb + b2, rb + b3);
       *reinterpret_cast<int4*>(out + ia) = oa;
       *reinterpret_cast<int4*>(out + ib) = ob;
-      if (FLAGS) {
-        // butterfly: even lanes collect the A-half words, odd lanes the B-half words (3 shuffles for 8 words)
-        const uint32_t na = flag4(oa.x, oa.y, oa.z, oa.w, lo1, span), nb = flag4(ob.x, ob.y, ob.z, ob.w, lo1, span);
-        const bool odd = lane & 1;
-        uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? na : nb, 1);
-        uint32_t acc = odd ? (got | (nb << 4)) : (na | (got << 4));
-        got = __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc = (lane & 2) ? (got | (acc << 8)) : (acc | (got << 8));
-        got = __shfl_xor_sync(0xffffffffu, acc, 4);
-        acc = (lane & 4) ? (got | (acc << 16)) : (acc | (got << 16));
-        if ((lane & 6) == 0)   // lanes 8g (A word g) and 8g+1 (B word g)
-          flags[tile * (GCI_TILE / 32) + it * 8 + (odd ? 4 : 0) + (lane >> 3)] = acc;
-      }
+      if (FLAGS) emit_flags(flags, tile, it, lane, oa, ob, lo1, span);
     }
     __syncwarp();   // re-zeroing stores of all lanes are done before the next tile's events land
   }
@@ -206,96 +218,67 @@ __device__ __forceinline__ void bulk_store_4k(void* gdst, const void* ssrc) {
                : "memory");
 }
 
-constexpr int DT_STAGE = 512;        // events of one 32-tile group kept in the warp's shared staging buffer
-constexpr size_t DT_SMEM = (sizeof(int) * 2 * GCI_TILE + sizeof(uint16_t) * DT_STAGE) * (GCI_TILE_THREADS / 32);   // 72 KB
-
-// Every warp owns ONE CONTIGUOUS range of tiles and walks it in groups of 32: the group's 32 table entries are one
-// coalesced 512-byte load (requested one group ahead) and — the events being bucketed in tile order — the group's
-// events are one contiguous stretch of the event array, staged in shared memory with coalesced loads.  Inside a group
-// the warp issues no global load at all: the kernel's reads are a few large requests per 128 KB of output instead of
-// two small dependent ones per 4 KB, which is what a stream of writes this dense tolerates
-// (tools/probe/store_probe.cu: the same store pattern without any read runs at 6.4 TB/s, with the per-tile reads at 5.7).
 template <bool FLAGS>
 __global__ void __launch_bounds__(GCI_TILE_THREADS)
 depth_tile_tma_kernel(const ulonglong2* __restrict__ tile_ps, const uint16_t* __restrict__ events, int64_t n_tiles,
                       int32_t* __restrict__ depth, uint32_t* __restrict__ flags, int32_t lo1, uint32_t span) {
-  extern __shared__ __align__(128) int s_dyn[];                        // [warps][2][GCI_TILE] | [warps][DT_STAGE] u16
+  extern __shared__ __align__(128) int s_dyn[];                        // [warps][2][GCI_TILE]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* const s_warp = s_dyn + warp * 2 * GCI_TILE;
-  uint16_t* const s_ev = reinterpret_cast<uint16_t*>(s_dyn + (GCI_TILE_THREADS / 32) * 2 * GCI_TILE) + warp * DT_STAGE;
   constexpr int ITERS = GCI_TILE / 256;                                // 4
   const int64_t n_warps = (int64_t)gridDim.x * (GCI_TILE_THREADS / 32);
-  const int64_t per = (n_tiles + n_warps - 1) / n_warps;
-  const int64_t t_begin = min(n_tiles, ((int64_t)blockIdx.x * (GCI_TILE_THREADS / 32) + warp) * per);
-  const int64_t t_end = min(n_tiles, t_begin + per);
+  int64_t tile = (int64_t)blockIdx.x * (GCI_TILE_THREADS / 32) + warp;
   const ulonglong2 zero2 = make_ulonglong2(0, 0);
-  auto entry = [&](int64_t g0) { return g0 + lane < t_end ? tile_ps[g0 + lane] : zero2; };
-  ulonglong2 ps_next = entry(t_begin);
+  // software pipeline over the warp's tiles: the tile table entry is requested two tiles ahead, the tile's first 32
+  // events one tile ahead (a deeper pipeline measured slower: profiles/r02g)
+  auto table = [&](int64_t t) { return t < n_tiles ? tile_ps[t] : zero2; };
+  auto first_events = [&](const ulonglong2& p) {
+    return lane < (uint32_t)(p.x & 0xffffffffull) ? (uint32_t)events[(uint32_t)(p.y & 0xffffffffull) + lane] : 0u;
+  };
+  ulonglong2 ps = table(tile), ps1 = table(tile + n_warps);
+  uint32_t ev = first_events(ps);
   int cur = 0;
-  for (int64_t g0 = t_begin; g0 < t_end; g0 += 32) {
-    const ulonglong2 ps = ps_next;                               // lane j: entry of tile g0 + j
-    ps_next = entry(g0 + 32);
-    const int n_in = (int)min((int64_t)32, t_end - g0);
-    const uint32_t my_cnt = (uint32_t)(ps.x & 0xffffffffull), my_off = (uint32_t)(ps.y & 0xffffffffull);
-    const int my_carry = (int)(uint32_t)(ps.y >> 32);
-    const uint32_t ev_begin = __shfl_sync(0xffffffffu, my_off, 0);
-    const uint32_t ev_end = __shfl_sync(0xffffffffu, my_off + my_cnt, n_in - 1);
-    const uint32_t n_group = ev_end - ev_begin;
-    const bool staged = n_group <= (uint32_t)DT_STAGE;
-    __syncwarp();                                                // the previous group is done with the staging buffer
-    if (staged)
-      for (uint32_t i = lane; i < n_group; i += 32) s_ev[i] = events[ev_begin + i];
+  for (; tile < n_tiles; tile += n_warps, cur ^= 1) {
+    int* __restrict__ s_delta = s_warp + cur * GCI_TILE;
+    // the bulk store that read this buffer two tiles ago is done reading (only the latest group may be pending)
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
     __syncwarp();
-    for (int t = 0; t < n_in; t++, cur ^= 1) {
-      const int64_t tile = g0 + t;
-      const uint32_t n_ev = __shfl_sync(0xffffffffu, my_cnt, t);
-      const uint32_t e0 = __shfl_sync(0xffffffffu, my_off, t) - ev_begin;
-      int carry = __shfl_sync(0xffffffffu, my_carry, t);         // depth carried into the tile
-      int* __restrict__ s_delta = s_warp + cur * GCI_TILE;
-      // the bulk store that read this buffer two tiles ago is done reading (only the latest group may be pending)
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      __syncwarp();
 #pragma unroll
-      for (int v = lane; v < GCI_TILE / 4; v += 32) reinterpret_cast<int4*>(s_delta)[v] = make_int4(0, 0, 0, 0);
-      __syncwarp();
-      for (uint32_t i = lane; i < n_ev; i += 32) {
-        const uint32_t e = staged ? (uint32_t)s_ev[e0 + i] : (uint32_t)events[ev_begin + e0 + i];
-        atomicAdd(&s_delta[e >> 1], (e & 1u) ? -1 : 1);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int it = 0; it < ITERS; it++) {
-        const int ia = it * 256 + lane * 4, ib = ia + 128;
-        const int4 va = *reinterpret_cast<const int4*>(&s_delta[ia]);
-        const int4 vb = *reinterpret_cast<const int4*>(&s_delta[ib]);
-        const int a0 = va.x, a1 = a0 + va.y, a2 = a1 + va.z, a3 = a2 + va.w;
-        const int b0 = vb.x, b1 = b0 + vb.y, b2 = b1 + vb.z, b3 = b2 + vb.w;
-        int tot_a, tot_b;
-        const int ra = carry + sparse_excl_scan(a3, lane, tot_a);
-        const int rb = carry + tot_a + sparse_excl_scan(b3, lane, tot_b);
-        carry += tot_a + tot_b;
-        const int4 oa = make_int4(ra + a0, ra + a1, ra + a2, ra + a3);
-        const int4 ob = make_int4(rb + b0, rb + b1, rb + b2, rb + b3);
-        *reinterpret_cast<int4*>(&s_delta[ia]) = oa;               // depth replaces the deltas in place
-        *reinterpret_cast<int4*>(&s_delta[ib]) = ob;
-        if (FLAGS) {
-          const uint32_t na = flag4(oa.x, oa.y, oa.z, oa.w, lo1, span), nb = flag4(ob.x, ob.y, ob.z, ob.w, lo1, span);
-          const bool odd = lane & 1;
-          uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? na : nb, 1);
-          uint32_t acc = odd ? (got | (nb << 4)) : (na | (got << 4));
-          got = __shfl_xor_sync(0xffffffffu, acc, 2);
-          acc = (lane & 2) ? (got | (acc << 8)) : (acc | (got << 8));
-          got = __shfl_xor_sync(0xffffffffu, acc, 4);
-          acc = (lane & 4) ? (got | (acc << 16)) : (acc | (got << 16));
-          if ((lane & 6) == 0)   // lanes 8g (A word g) and 8g+1 (B word g)
-            flags[tile * (GCI_TILE / 32) + it * 8 + (odd ? 4 : 0) + (lane >> 3)] = acc;
-        }
-      }
-      // generic-proxy writes of the whole warp -> visible to the async proxy, then one lane starts the copy
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) bulk_store_4k(depth + tile * GCI_TILE, s_delta);
+    for (int v = lane; v < GCI_TILE / 4; v += 32) reinterpret_cast<int4*>(s_delta)[v] = make_int4(0, 0, 0, 0);
+    __syncwarp();
+    const uint32_t n_ev = (uint32_t)(ps.x & 0xffffffffull);
+    const uint32_t ev0 = (uint32_t)(ps.y & 0xffffffffull);
+    int carry = (int)(uint32_t)(ps.y >> 32);                     // depth carried into the tile
+    if (lane < n_ev) atomicAdd(&s_delta[ev >> 1], (ev & 1u) ? -1 : 1);
+    for (uint32_t i = lane + 32; i < n_ev; i += 32) {            // more than 32 events in the tile: rare
+      const uint32_t e = events[ev0 + i];
+      atomicAdd(&s_delta[e >> 1], (e & 1u) ? -1 : 1);
     }
+    ps = ps1;
+    ev = first_events(ps);                                       // events of the next tile
+    ps1 = table(tile + 2 * n_warps);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < ITERS; it++) {
+      const int ia = it * 256 + lane * 4, ib = ia + 128;
+      const int4 va = *reinterpret_cast<const int4*>(&s_delta[ia]);
+      const int4 vb = *reinterpret_cast<const int4*>(&s_delta[ib]);
+      const int a0 = va.x, a1 = a0 + va.y, a2 = a1 + va.z, a3 = a2 + va.w;
+      const int b0 = vb.x, b1 = b0 + vb.y, b2 = b1 + vb.z, b3 = b2 + vb.w;
+      int tot_a, tot_b;
+      const int ra = carry + sparse_excl_scan(a3, lane, tot_a);
+      const int rb = carry + tot_a + sparse_excl_scan(b3, lane, tot_b);
+      carry += tot_a + tot_b;
+      const int4 oa = make_int4(ra + a0, ra + a1, ra + a2, ra + a3);
+      const int4 ob = make_int4(rb + b0, rb + b1, rb + b2, rb + b3);
+      *reinterpret_cast<int4*>(&s_delta[ia]) = oa;               // depth replaces the deltas in place
+      *reinterpret_cast<int4*>(&s_delta[ib]) = ob;
+      if (FLAGS) emit_flags(flags, tile, it, lane, oa, ob, lo1, span);
+    }
+    // generic-proxy writes of the whole warp -> visible to the async proxy, then one lane starts the copy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) bulk_store_4k(depth + tile * GCI_TILE, s_delta);
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the tile must have left before the CTA does
 }
@@ -631,7 +614,7 @@ int gci_depth_enqueue(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo
   int32_t* dp = t.depth.as<int32_t>();
   uint32_t* fp = t.flags.as<uint32_t>();
   static int use_tma = -1, tma_ctas = 0;
-  constexpr size_t TMA_SMEM = DT_SMEM;
+  constexpr size_t TMA_SMEM = sizeof(int) * 2 * GCI_TILE * (GCI_TILE_THREADS / 32);      // 64 KB
   if (use_tma < 0) {
     const char* g = getenv("GCI_DEPTH_TMA");
     use_tma = !(g && g[0] == '0');

@@ -73,20 +73,24 @@ __device__ __forceinline__ uint32_t claim_slot(uint32_t* cursor /* [world] */, i
 }
 
 // ---- dispatch 1: per-file winners to the home of their read --------------------------------------------------
-// thread per global read id: consecutive reads go to consecutive destinations, so the lanes of a warp that talk to
-// one destination write consecutive 24-byte rows there
+// thread per LOCAL record (the work scales with what this rank holds, not with the global read count): the record
+// that won its read (win[read] names it) sends the row.  Records are coordinate sorted and read ids follow first
+// appearance, so consecutive records carry nearby ids and the lanes that talk to one destination write neighbouring
+// 24-byte rows there.
 __global__ void __launch_bounds__(256)
-dispatch1_kernel(XLayout lay, XPeers peers, int me, int f, uint32_t n_reads, const long long* __restrict__ win,
+dispatch1_kernel(XLayout lay, XPeers peers, int me, int f, int64_t n_rec, uint32_t n_reads,
+                 const uint32_t* __restrict__ read_id, const long long* __restrict__ win,
                  const int32_t* __restrict__ ref_id, const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                  const int32_t* __restrict__ qlen, const uint8_t* __restrict__ highq) {
-  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n_rec) return;
+  const uint32_t q = read_id[r];
   if (q >= n_reads) return;
   const long long k = win[q];
-  if (k < 0) return;
+  if (k < 0 || (int64_t)(k & 0xffffffffll) != r) return;
   const unsigned long long epoch = *reinterpret_cast<const unsigned long long*>(peers.area[me]);
   const int par = (int)(epoch & 1ull);
-  const uint32_t i = (uint32_t)(k & 0xffffffffll);
-  const XRow1 row{(uint32_t)epoch, ref_id[i], start[i], end[i], qlen[i], (uint32_t)highq[q]};
+  const XRow1 row{(uint32_t)epoch, ref_id[r], start[r], end[r], qlen[r], (uint32_t)highq[q]};
   const uint32_t w = (uint32_t)lay.world;
   XRow1* dstp = reinterpret_cast<XRow1*>(peers.area[q % w] + lay.rows1_off(par, f, me)) + q / w;
   // 24 bytes as three 8-byte stores (rows are 8-byte aligned)
@@ -303,10 +307,11 @@ int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t f
       continue;
     }
     BamFile& b = ctx->bam[ft.src];
-    if (ctx->n_reads) {
-      dispatch1_kernel<<<(ctx->n_reads + 255) / 256, 256, 0, ctx->stream>>>(
-          lay, peers, sh.rank, f, ctx->n_reads, ft.win.as<long long>(), b.ref_id.as<int32_t>(), b.ref_start.as<int32_t>(),
-          b.ref_end.as<int32_t>(), b.qlen.as<int32_t>(), ctx->highq.as<uint8_t>());
+    if (b.n) {
+      dispatch1_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, ctx->stream>>>(
+          lay, peers, sh.rank, f, b.n, ctx->n_reads, b.read_id.as<uint32_t>(), ft.win.as<long long>(),
+          b.ref_id.as<int32_t>(), b.ref_start.as<int32_t>(), b.ref_end.as<int32_t>(), b.qlen.as<int32_t>(),
+          ctx->highq.as<uint8_t>());
       GCI_LAUNCH_CHECK(ctx);
     }
     hf.bam = f++;
