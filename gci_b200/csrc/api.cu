@@ -193,7 +193,7 @@ void gci_destroy(gci_ctx* ctx) {
   for (auto& b : ctx->bam) free_bam(ctx, b);
   for (auto& f : ctx->files) free_table(ctx, f);
   for (auto& p : ctx->paf)
-    for (DevBuf* d : {&p.read_id, &p.qlen, &p.qstart, &p.qend, &p.ref_id, &p.tstart, &p.tend, &p.nmatch, &p.alnlen, &p.mapq})
+    for (DevBuf* d : {&p.read_id, &p.qlen, &p.qstart, &p.qend, &p.ref_id, &p.tstart, &p.tend, &p.nmatch, &p.alnlen, &p.mapq, &p.rows})
       ctx->release(*d);
   ctx->release(ctx->paf_keep);
   ctx->release(ctx->d_name_rank);
@@ -458,6 +458,7 @@ int gci_upload_paf(gci_ctx* ctx, int64_t n, const uint32_t* read_id, const int32
   GCI_TRY(gci_h2d(ctx, p.alnlen, alnlen, 4 * n));
   GCI_TRY(gci_h2d(ctx, p.mapq, mapq, 4 * n));
   ctx->stage_end();
+  GCI_TRY(gci_pack_paf_rows(ctx, p));   // a property of the file, built once (filter.cu)
   if (ctx->n_files == ctx->files.size()) ctx->files.emplace_back();
   FileTable& f = ctx->files[ctx->n_files++];
   f.kind = 1;   // a table, rebuilt from the PAF lines by every gci_filter (the gates are filter arguments)

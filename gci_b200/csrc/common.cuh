@@ -64,6 +64,8 @@ struct BamFile {
 struct PafFile {
   int64_t n = 0;
   DevBuf read_id, qlen, qstart, qend, ref_id, tstart, tend, nmatch, alnlen, mapq;
+  DevBuf rows;   // int4[n][2], packed at upload: (ref, qlen, qstart, qend) (tstart, tend, nmatch, alnlen) — the election
+                 // gathers whole lines, and a line is then ONE 32-byte sector instead of eight
 };
 
 // one file after its per-file leg: at most one entry per read
@@ -236,6 +238,7 @@ int gci_exclusive_scan_i32(gci_ctx* ctx, const int32_t* in, int32_t* out, int64_
 
 // stage entry points
 int gci_index_bam(gci_ctx* ctx, BamFile& b);
+int gci_pack_paf_rows(gci_ctx* ctx, PafFile& p);
 void gci_index_bam_finish(gci_ctx* ctx, BamFile& b);
 int gci_run_bam_leg(gci_ctx* ctx, int file_idx, int bam_idx, int32_t mq, int32_t mq_cutoff, double ip, double cp);
 int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip);

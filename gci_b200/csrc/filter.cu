@@ -956,6 +956,7 @@ struct PafCols {
 };
 struct PafSet {
   PafCols f[GCI_MAX_FILES];
+  const int4* rows[GCI_MAX_FILES];    // packed lines of every file (PafFile::rows)
   int64_t off[GCI_MAX_FILES + 1];     // first global line id of every file
   int n;
 };
@@ -964,12 +965,30 @@ struct PafLine { int32_t ref, qlen, q0, q1, t0, t1; double ident; };
 __device__ __forceinline__ PafLine paf_line(const PafSet& ps, int32_t g) {
   int k = 0;
   while (k + 1 < ps.n && (int64_t)g >= ps.off[k + 1]) k++;
-  const int64_t i = (int64_t)g - ps.off[k];
-  const PafCols& p = ps.f[k];
+  const int4* row = ps.rows[k] + 2 * ((int64_t)g - ps.off[k]);
+  const int4 a = row[0], b = row[1];                                   // one 32-byte sector
   PafLine l;
-  l.ref = p.ref_id[i]; l.qlen = p.qlen[i]; l.q0 = p.qstart[i]; l.q1 = p.qend[i]; l.t0 = p.tstart[i]; l.t1 = p.tend[i];
-  l.ident = (double)p.nmatch[i] / (double)p.alnlen[i];                 // :231 (kept lines have alnlen != 0)
+  l.ref = a.x; l.qlen = a.y; l.q0 = a.z; l.q1 = a.w; l.t0 = b.x; l.t1 = b.y;
+  l.ident = (double)b.z / (double)b.w;                                 // :231 (kept lines have alnlen != 0)
   return l;
+}
+
+__global__ void paf_pack_rows_kernel(int64_t n, PafCols p, int4* __restrict__ rows) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rows[2 * i] = make_int4(p.ref_id[i], p.qlen[i], p.qstart[i], p.qend[i]);
+  rows[2 * i + 1] = make_int4(p.tstart[i], p.tend[i], p.nmatch[i], p.alnlen[i]);
+}
+
+int gci_pack_paf_rows(gci_ctx* ctx, PafFile& pf) {
+  GCI_TRY(ctx->ensure(pf.rows, 32 * (size_t)std::max<int64_t>(1, pf.n)));
+  if (pf.n == 0) return GCI_OK;
+  const PafCols pc{pf.read_id.as<uint32_t>(), pf.qlen.as<int32_t>(), pf.qstart.as<int32_t>(), pf.qend.as<int32_t>(),
+                   pf.ref_id.as<int32_t>(), pf.tstart.as<int32_t>(), pf.tend.as<int32_t>(), pf.nmatch.as<int32_t>(),
+                   pf.alnlen.as<int32_t>(), pf.mapq.as<int32_t>()};
+  paf_pack_rows_kernel<<<(unsigned)((pf.n + 255) / 256), 256, 0, ctx->stream>>>(pf.n, pc, pf.rows.as<int4>());
+  GCI_LAUNCH_CHECK(ctx);
+  return GCI_OK;
 }
 
 __global__ void paf_mark_kernel(int64_t n, PafCols p, int64_t line0, const uint8_t* __restrict__ selected,
@@ -1114,16 +1133,15 @@ paf_elect_kernel(uint32_t n_reads, PafSet ps, const int32_t* __restrict__ off, c
   const int32_t line = idx[a0];
   int k = 0;
   while (k + 1 < ps.n && (int64_t)line >= ps.off[k + 1]) k++;
-  const int64_t i = (int64_t)line - ps.off[k];
-  const PafCols& p = ps.f[k];
-  const int32_t ql = p.qlen[i];
-  if (ql == 0) {                             // ZeroDivisionError :247
+  const int4* row = ps.rows[k] + 2 * ((int64_t)line - ps.off[k]);
+  const int4 a = row[0], b = row[1];         // (ref, qlen, q0, q1) (t0, t1, nmatch, alnlen): one sector
+  if (a.y == 0) {                            // ZeroDivisionError :247
     atomicOr(err, 32ull);
     atomicMin(err + 1, (unsigned long long)r);
     o.win[r] = -1;
     return;
   }
-  o.ref[r] = p.ref_id[i]; o.start[r] = p.tstart[i]; o.end[r] = p.tend[i]; o.qlen[r] = ql;
+  o.ref[r] = a.x; o.start[r] = b.x; o.end[r] = b.y; o.qlen[r] = a.y;
   o.win[r] = (long long)r;
 }
 
@@ -1208,6 +1226,7 @@ int gci_run_paf_legs(gci_ctx* ctx, int32_t mq, int32_t mq_cutoff, double ip) {
     ps.f[k] = PafCols{pf.read_id.as<uint32_t>(), pf.qlen.as<int32_t>(), pf.qstart.as<int32_t>(), pf.qend.as<int32_t>(),
                       pf.ref_id.as<int32_t>(), pf.tstart.as<int32_t>(), pf.tend.as<int32_t>(), pf.nmatch.as<int32_t>(),
                       pf.alnlen.as<int32_t>(), pf.mapq.as<int32_t>()};
+    ps.rows[k] = pf.rows.as<int4>();
     ps.off[k + 1] = ps.off[k] + pf.n;
     file_of.push_back((int)fi);
   }

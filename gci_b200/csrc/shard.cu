@@ -237,21 +237,32 @@ consume2_kernel(XLayout lay, const char* __restrict__ mine, int32_t* __restrict_
   const long long total = s_off[lay.world];
   WarpSums ws;
   ws.init();
+  // four rows per thread and round, all requested before any is used (the walk is a chain row -> slice -> events)
+  constexpr int ILP = 4;
   long long begin, end;
-  cta_range(total, blockDim.x, begin, end);
-  for (long long base = begin; base < end; base += blockDim.x) {
-    const long long g = base + threadIdx.x;
-    int32_t c = -1, s = 0, e = 0;
-    if (g < total) {
-      int src = 0;
-      while (src + 1 < lay.world && g >= s_off[src + 1]) src++;
-      const int4 r = *reinterpret_cast<const int4*>(mine + lay.rows2_off(par, src) + (long long)sizeof(XRow2) * (g - s_off[src]));
-      c = r.x; s = r.y; e = r.z;
-      s_contig[g] = c;
-      s_start[g] = s;
-      s_end[g] = e;
+  cta_range(total, (long long)blockDim.x * ILP, begin, end);
+  for (long long base = begin; base < end; base += (long long)blockDim.x * ILP) {
+    int4 row[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; j++) {
+      const long long g = base + j * (long long)blockDim.x + threadIdx.x;
+      row[j] = make_int4(-1, 0, 0, 0);
+      if (g < total) {
+        int src = 0;
+        while (src + 1 < lay.world && g >= s_off[src + 1]) src++;
+        row[j] = *reinterpret_cast<const int4*>(mine + lay.rows2_off(par, src) + (long long)sizeof(XRow2) * (g - s_off[src]));
+      }
     }
-    ws.add(bk, c, s, e, false);
+#pragma unroll
+    for (int j = 0; j < ILP; j++) {
+      const long long g = base + j * (long long)blockDim.x + threadIdx.x;
+      if (g < total) {
+        s_contig[g] = row[j].x;
+        s_start[g] = row[j].y;
+        s_end[g] = row[j].z;
+      }
+      ws.add(bk, row[j].x, row[j].y, row[j].z, false);
+    }
   }
   ws.flush(bk, nullptr);
 }
