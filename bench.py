@@ -287,7 +287,8 @@ def main():
         # profiling aid: the sharded path with ONE rank (every row is exchanged with itself), so that ncu — which must
         # not wrap a multi-rank command — can see dispatch1 / home_join / consume2 at full size
         plan = sharded.make_plan(0, 1, L)
-        sharded.configure(ctx, plan, L, w.contigs.name_rank(), w.n_reads, max_bam_files=1)
+        sharded.configure(ctx, plan, L, w.contigs.name_rank(), w.n_reads, max_bam_files=1,
+                          ipc=os.environ.get("GCI_BENCH_SHARD1") != "noipc")
         ctx.shard_attach([ctx.shard_area()])
         paf = sharded.shard_paf(w.paf, plan)
         owned = list(range(len(L)))

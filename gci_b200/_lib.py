@@ -507,10 +507,10 @@ class Context:
         self._check(self._lib.gci_shard_config(self._h, int(rank), int(world), _ptr(owner), _ptr(gs)))
         self.shard_rank, self.shard_world = int(rank), int(world)
 
-    def shard_alloc(self, max_reads, max_bam_files=2):
-        """-> 64-byte CUDA IPC handle of this rank's exchange area"""
+    def shard_alloc(self, max_reads, max_bam_files=2, ipc=True):
+        """-> 64-byte CUDA IPC handle of this rank's exchange area (ipc=False: no handle, for contexts of one process)"""
         h = np.zeros(64, np.uint8)
-        self._check(self._lib.gci_shard_alloc(self._h, int(max_reads), int(max_bam_files), _ptr(h)))
+        self._check(self._lib.gci_shard_alloc(self._h, int(max_reads), int(max_bam_files), _ptr(h) if ipc else None))
         return h
 
     def shard_open(self, handles):

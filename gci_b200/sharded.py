@@ -71,13 +71,13 @@ def shard_paf_source(tab: PafTable, plan: ShardPlan, bam: AlnTable) -> PafTable:
     return PafTable(*[getattr(tab, k)[keep] for k in _PAF_COLS])
 
 
-def configure(ctx, plan: ShardPlan, lengths, name_rank, max_reads, max_bam_files=2):
+def configure(ctx, plan: ShardPlan, lengths, name_rank, max_reads, max_bam_files=2, ipc=True):
     """contig table, owners and this rank's exchange area -> its CUDA IPC handle (uint8[64]).  The caller gathers
     every rank's handle and calls ctx.shard_open (processes) or ctx.shard_attach (contexts of one process)."""
     ctx.set_contigs(lengths, plan.owned)
     ctx.set_name_rank(name_rank)
     ctx.shard_config(plan.rank, plan.world, plan.owner, plan.selected)
-    return ctx.shard_alloc(max_reads, max_bam_files)
+    return ctx.shard_alloc(max_reads, max_bam_files, ipc)
 
 
 def open_over_process_group(ctx, plan: ShardPlan, handle):
