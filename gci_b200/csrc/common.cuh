@@ -20,7 +20,7 @@
 constexpr int GCI_TILE = 1024;            // positions per depth tile = per warp (4 KB of int32)
 constexpr int GCI_TILE_THREADS = 256;     // 8 warps = 8 independent tiles in flight per CTA
 constexpr int GCI_CHUNK = 8192;           // positions per CTA in the streaming kernels (max / flags / sum)
-constexpr int GCI_RUN_CHUNK_WORDS = 8192; // flag words (of 32 positions) per run-extraction chunk: one CTA of 1024 threads
+constexpr int GCI_RUN_CHUNK_WORDS = 2048; // flag words (of 32 positions) per run-extraction chunk
 constexpr int GCI_MAX_RANKS = 16;         // GPUs of one NVLink domain taking part in the peer-memory row exchange
 
 #define GCI_CUDA_TRY(ctx, expr)                                                              \
