@@ -216,12 +216,16 @@ home_join_kernel(XLayout lay, XPeers peers, int me, HomeArgs a, uint32_t n_home,
 }
 
 // ---- owner: the survivors every home sent, packed into the survivor arrays, depth events counted on the way -------
+// One thread per received row, the grid sized for the slot capacity (CTAs behind the received count leave at once).
+// (A persistent form of this kernel — contiguous CTA ranges, four rows per thread, per-warp register sums — measured
+// 0.38-0.48 ms for 4.6 M rows with its memory-instruction queue throttled 80 cycles per issue, profiles/r02j; the plain
+// form below has the shape of bucket_fill_kernel, which moves the same rows in 0.07 ms.)
 __global__ void __launch_bounds__(256)
 consume2_kernel(XLayout lay, const char* __restrict__ mine, int32_t* __restrict__ s_contig, int32_t* __restrict__ s_start,
                 int32_t* __restrict__ s_end, uint32_t* __restrict__ n_surv_dev, BucketArgs bk) {
-  __shared__ ContigCache cc;
   __shared__ long long s_off[GCI_MAX_RANKS + 1];
-  contig_cache_load(cc, bk);
+  __shared__ long long s_cov[8];
+  __shared__ int32_t s_ctg[8];
   const unsigned long long* hdr = reinterpret_cast<const unsigned long long*>(mine);
   const int par = (int)(hdr[0] & 1ull);
   if (threadIdx.x == 0) {
@@ -235,36 +239,50 @@ consume2_kernel(XLayout lay, const char* __restrict__ mine, int32_t* __restrict_
   }
   __syncthreads();
   const long long total = s_off[lay.world];
-  WarpSums ws;
-  ws.init();
-  // four rows per thread and round, all requested before any is used (the walk is a chain row -> slice -> events)
-  constexpr int ILP = 4;
-  long long begin, end;
-  cta_range(total, (long long)blockDim.x * ILP, begin, end);
-  for (long long base = begin; base < end; base += (long long)blockDim.x * ILP) {
-    int4 row[ILP];
-#pragma unroll
-    for (int j = 0; j < ILP; j++) {
-      const long long g = base + j * (long long)blockDim.x + threadIdx.x;
-      row[j] = make_int4(-1, 0, 0, 0);
-      if (g < total) {
-        int src = 0;
-        while (src + 1 < lay.world && g >= s_off[src + 1]) src++;
-        row[j] = *reinterpret_cast<const int4*>(mine + lay.rows2_off(par, src) + (long long)sizeof(XRow2) * (g - s_off[src]));
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < ILP; j++) {
-      const long long g = base + j * (long long)blockDim.x + threadIdx.x;
-      if (g < total) {
-        s_contig[g] = row[j].x;
-        s_start[g] = row[j].y;
-        s_end[g] = row[j].z;
-      }
-      ws.add(bk, row[j].x, row[j].y, row[j].z, false);
+  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (blockIdx.x * (long long)blockDim.x >= total) return;                    // whole CTA
+  int32_t c = -1;
+  long long covered = 0;
+  if (g < total) {
+    int src = 0;
+    while (src + 1 < lay.world && g >= s_off[src + 1]) src++;
+    const int4 r = *reinterpret_cast<const int4*>(mine + lay.rows2_off(par, src) + (long long)sizeof(XRow2) * (g - s_off[src]));
+    s_contig[g] = r.x;
+    s_start[g] = r.y;
+    s_end[g] = r.z;
+    const Slice sl = survivor_slice(r.x, r.y, r.z, bk.fl, bk.len, bk.tile_off);
+    if (sl.ok) {
+      atomicAdd(&bk.cnt_start[sl.tile_a], 1u);
+      atomicAdd(&bk.cnt_end[sl.tile_b], 1u);
+      covered = sl.b - sl.a;
+      c = r.x;
     }
   }
-  ws.flush(bk, nullptr);
+  // depth sum per contig = sum of the slice lengths: per warp when the warp agrees on a contig, then per CTA
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
+  int32_t c0 = -1;
+  long long t = 0;
+  if (act) {
+    c0 = __shfl_sync(0xffffffffu, c, __ffs(act) - 1);
+    if (__all_sync(0xffffffffu, c < 0 || c == c0)) {
+      t = warp_sum_ll(covered);
+    } else {
+      if (c >= 0) atomicAdd((unsigned long long*)(bk.sums + c), (unsigned long long)covered);
+      c0 = -1;
+    }
+  }
+  if (lane == 0) { s_cov[wp] = t; s_ctg[wp] = c0; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; i++) {
+      if (s_ctg[i] < 0) continue;
+      long long sum = s_cov[i];
+      for (int j = i + 1; j < 8; j++)
+        if (s_ctg[j] == s_ctg[i]) { sum += s_cov[j]; s_ctg[j] = -1; }
+      if (sum) atomicAdd((unsigned long long*)(bk.sums + s_ctg[i]), (unsigned long long)sum);
+    }
+  }
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
@@ -358,7 +376,7 @@ int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t f
   ctx->stage_end();
   // owner: the survivors that arrived, their depth events counted on the way
   ctx->stage_begin(GCI_ST_XCONSUME);
-  consume2_kernel<<<(unsigned)std::min<int64_t>((sh.surv_slots + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
+  consume2_kernel<<<(unsigned)((sh.surv_slots + 255) / 256), 256, 0, ctx->stream>>>(
       lay, mine, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(),
       send_cnt + GCI_MAX_RANKS, bk);
   GCI_LAUNCH_CHECK(ctx);
