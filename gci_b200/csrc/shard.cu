@@ -357,9 +357,6 @@ int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t f
   GCI_TRY(ctx->ensure(ctx->surv_contig, 4 * slots));
   GCI_TRY(ctx->ensure(ctx->surv_start, 4 * slots));
   GCI_TRY(ctx->ensure(ctx->surv_end, 4 * slots));
-  BucketArgs bk;
-  memset(&bk, 0, sizeof bk);
-  if (track >= 0) GCI_TRY(gci_depth_prepare(ctx, track, flank_len, &bk));
   ctx->stage_begin(GCI_ST_JOIN);
   if (sh.n_home) {
     home_join_kernel<<<(sh.n_home + 255) / 256, 256, 0, ctx->stream>>>(
@@ -374,7 +371,11 @@ int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t f
   xchg_wait_kernel<<<1, 32, 0, ctx->stream>>>(lay, mine, 1, d_err);
   GCI_LAUNCH_CHECK(ctx);
   ctx->stage_end();
-  // owner: the survivors that arrived, their depth events counted on the way
+  // owner: the survivors that arrived, their depth events counted on the way (the count arrays are zeroed right
+  // here, so that they are still in L2 when the REDs arrive)
+  BucketArgs bk;
+  memset(&bk, 0, sizeof bk);
+  if (track >= 0) GCI_TRY(gci_depth_prepare(ctx, track, flank_len, &bk));
   ctx->stage_begin(GCI_ST_XCONSUME);
   consume2_kernel<<<(unsigned)((sh.surv_slots + 255) / 256), 256, 0, ctx->stream>>>(
       lay, mine, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(),
