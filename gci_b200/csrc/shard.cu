@@ -216,16 +216,21 @@ home_join_kernel(XLayout lay, XPeers peers, int me, HomeArgs a, uint32_t n_home,
 }
 
 // ---- owner: the survivors every home sent, packed into the survivor arrays, depth events counted on the way -------
-// One thread per received row, the grid sized for the slot capacity (CTAs behind the received count leave at once).
-// (A persistent form of this kernel — contiguous CTA ranges, four rows per thread, per-warp register sums — measured
-// 0.38-0.48 ms for 4.6 M rows with its memory-instruction queue throttled 80 cycles per issue, profiles/r02j; the plain
-// form below has the shape of bucket_fill_kernel, which moves the same rows in 0.07 ms.)
+// Rows arrive in the homes' read order, i.e. scattered over the contigs: the per-contig depth sums are therefore kept
+// per CTA in a small shared-memory table (contig & 63, claimed by compare-and-swap; a clash goes straight to memory)
+// and flushed once at the end.  (Sending the slice length of every row of a warp that straddles contigs to
+// bk.sums[contig] — 24 hot addresses — was 0.25 ms of this kernel's 0.30 ms for 4.6 M rows: a skip-the-sums ablation
+// ran in 0.046 ms, profiles/r02t.)  Contiguous row range per CTA, at most CONSUME_ROWS_PER_CTA rows so the 16-bit
+// halves of the slice lengths add up in 32-bit shared atomics.
+constexpr int CONSUME_SLOTS = 64;
+constexpr long long CONSUME_ROWS_PER_CTA = 32768;
+
 __global__ void __launch_bounds__(256)
 consume2_kernel(XLayout lay, const char* __restrict__ mine, int32_t* __restrict__ s_contig, int32_t* __restrict__ s_start,
                 int32_t* __restrict__ s_end, uint32_t* __restrict__ n_surv_dev, BucketArgs bk) {
   __shared__ long long s_off[GCI_MAX_RANKS + 1];
-  __shared__ long long s_cov[8];
-  __shared__ int32_t s_ctg[8];
+  __shared__ int32_t s_key[CONSUME_SLOTS];
+  __shared__ uint32_t s_lo[CONSUME_SLOTS], s_hi[CONSUME_SLOTS];
   const unsigned long long* hdr = reinterpret_cast<const unsigned long long*>(mine);
   const int par = (int)(hdr[0] & 1ull);
   if (threadIdx.x == 0) {
@@ -237,51 +242,61 @@ consume2_kernel(XLayout lay, const char* __restrict__ mine, int32_t* __restrict_
     s_off[lay.world] = t;
     if (blockIdx.x == 0) *n_surv_dev = (uint32_t)t;
   }
+  if (threadIdx.x < CONSUME_SLOTS) { s_key[threadIdx.x] = -1; s_lo[threadIdx.x] = 0; s_hi[threadIdx.x] = 0; }
   __syncthreads();
-  const long long total = s_off[lay.world];
-  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (blockIdx.x * (long long)blockDim.x >= total) return;                    // whole CTA
-  int32_t c = -1;
-  long long covered = 0;
-  if (g < total) {
-    int src = 0;
-    while (src + 1 < lay.world && g >= s_off[src + 1]) src++;
-    const int4 r = *reinterpret_cast<const int4*>(mine + lay.rows2_off(par, src) + (long long)sizeof(XRow2) * (g - s_off[src]));
-    s_contig[g] = r.x;
-    s_start[g] = r.y;
-    s_end[g] = r.z;
-    const Slice sl = survivor_slice(r.x, r.y, r.z, bk.fl, bk.len, bk.tile_off);
-    if (sl.ok) {
-      atomicAdd(&bk.cnt_start[sl.tile_a], 1u);
-      atomicAdd(&bk.cnt_end[sl.tile_b], 1u);
-      covered = sl.b - sl.a;
-      c = r.x;
+  long long begin, end;
+  cta_range(s_off[lay.world], blockDim.x, begin, end);
+  if (begin >= end) return;                                                   // whole CTA
+  int src = 0;
+  for (long long base = begin; base < end; base += blockDim.x) {
+    const long long g = base + threadIdx.x;
+    int32_t c = -1;
+    uint32_t covered = 0;
+    if (g < end) {
+      while (src + 1 < lay.world && g >= s_off[src + 1]) src++;
+      const int4 r = *reinterpret_cast<const int4*>(mine + lay.rows2_off(par, src) + (long long)sizeof(XRow2) * (g - s_off[src]));
+      s_contig[g] = r.x;
+      s_start[g] = r.y;
+      s_end[g] = r.z;
+      const Slice sl = survivor_slice(r.x, r.y, r.z, bk.fl, bk.len, bk.tile_off);
+      if (sl.ok) {
+        atomicAdd(&bk.cnt_start[sl.tile_a], 1u);
+        atomicAdd(&bk.cnt_end[sl.tile_b], 1u);
+        covered = (uint32_t)(sl.b - sl.a);
+        c = r.x;
+      }
     }
-  }
-  // depth sum per contig = sum of the slice lengths: per warp when the warp agrees on a contig, then per CTA
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
-  int32_t c0 = -1;
-  long long t = 0;
-  if (act) {
-    c0 = __shfl_sync(0xffffffffu, c, __ffs(act) - 1);
+    // slice length -> the CTA's table: one lane for a warp that agrees on the contig, every lane otherwise
+    const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
+    if (act == 0) continue;
+    const int32_t c0 = __shfl_sync(0xffffffffu, c, __ffs(act) - 1);
+    uint32_t lo = covered & 0xffffu, hi = covered >> 16;
+    bool add = c >= 0;
     if (__all_sync(0xffffffffu, c < 0 || c == c0)) {
-      t = warp_sum_ll(covered);
-    } else {
-      if (c >= 0) atomicAdd((unsigned long long*)(bk.sums + c), (unsigned long long)covered);
-      c0 = -1;
+      lo = __reduce_add_sync(0xffffffffu, lo);
+      hi = __reduce_add_sync(0xffffffffu, hi);
+      add = (threadIdx.x & 31) == 0;
+      c = c0;
+    }
+    if (add) {
+      const int slot = c & (CONSUME_SLOTS - 1);
+      int32_t k = s_key[slot];
+      if (k == -1) {
+        const int32_t old = atomicCAS(&s_key[slot], -1, c);
+        k = old == -1 ? c : old;
+      }
+      if (k == c) {
+        atomicAdd(&s_lo[slot], lo);
+        atomicAdd(&s_hi[slot], hi);
+      } else {
+        atomicAdd((unsigned long long*)(bk.sums + c), (unsigned long long)lo + ((unsigned long long)hi << 16));
+      }
     }
   }
-  if (lane == 0) { s_cov[wp] = t; s_ctg[wp] = c0; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 8; i++) {
-      if (s_ctg[i] < 0) continue;
-      long long sum = s_cov[i];
-      for (int j = i + 1; j < 8; j++)
-        if (s_ctg[j] == s_ctg[i]) { sum += s_cov[j]; s_ctg[j] = -1; }
-      if (sum) atomicAdd((unsigned long long*)(bk.sums + s_ctg[i]), (unsigned long long)sum);
-    }
+  if (threadIdx.x < CONSUME_SLOTS && s_key[threadIdx.x] >= 0) {
+    const unsigned long long sum = (unsigned long long)s_lo[threadIdx.x] + ((unsigned long long)s_hi[threadIdx.x] << 16);
+    if (sum) atomicAdd((unsigned long long*)(bk.sums + s_key[threadIdx.x]), sum);
   }
 }
 
@@ -377,9 +392,15 @@ int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t f
   memset(&bk, 0, sizeof bk);
   if (track >= 0) GCI_TRY(gci_depth_prepare(ctx, track, flank_len, &bk));
   ctx->stage_begin(GCI_ST_XCONSUME);
-  consume2_kernel<<<(unsigned)((sh.surv_slots + 255) / 256), 256, 0, ctx->stream>>>(
-      lay, mine, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(),
-      send_cnt + GCI_MAX_RANKS, bk);
+  {
+    // one CTA per SM x 8 unless the slot capacity asks for more to keep a CTA's range within CONSUME_ROWS_PER_CTA
+    const long long by_block = (sh.surv_slots + 255) / 256;
+    const long long by_cap = (sh.surv_slots + CONSUME_ROWS_PER_CTA - 1) / CONSUME_ROWS_PER_CTA;
+    const long long grid = std::max<long long>(1, std::max(by_cap, std::min<long long>(by_block, (long long)ctx->sm_count * 8)));
+    consume2_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(
+        lay, mine, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(),
+        send_cnt + GCI_MAX_RANKS, bk);
+  }
   GCI_LAUNCH_CHECK(ctx);
   ctx->stage_end();
   if (track >= 0) {
