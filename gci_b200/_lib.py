@@ -92,6 +92,7 @@ _SIGNATURES = {
     "gci_genome_row": (C.c_int, [_p, _i32, _f64, _i32, _i64, _i64, _p, _p, _p, _p]),
     "gci_score_terms_sums": (C.c_int, [_p, _i32, _f64, _i32, _p, _p, _i64, _p, _p, _p]),
     "gci_sliding_window": (C.c_int, [_p, _i32, _i32, _i64, _i64, _i64, _i64, _p, _p, _p, _p, C.POINTER(_i64)]),
+    "gci_shard_home": (C.c_int, [_u32, _i32, C.POINTER(_i32), C.POINTER(_u32)]),
     "gci_shard_config": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "gci_shard_alloc": (C.c_int, [_p, _u32, _i32, _p]),
     "gci_shard_open": (C.c_int, [_p, _p]),

@@ -381,7 +381,7 @@ int gci_reads_begin(gci_ctx* ctx, uint32_t n_reads) {
   ctx->n_reads = n_reads;
   if (ctx->shard.on) {
     gci_ctx::Shard& sh = ctx->shard;
-    sh.n_home = n_reads > (uint32_t)sh.rank ? (n_reads - sh.rank + sh.world - 1) / sh.world : 0;
+    sh.n_home = home_count(n_reads, (uint32_t)sh.rank, (uint32_t)sh.world);
     if (sh.area.p && (int64_t)sh.n_home > sh.cap1)
       return ctx->fail(GCI_E_ARG, "gci_reads_begin: %u reads exceed the exchange area (gci_shard_alloc)", n_reads);
   }

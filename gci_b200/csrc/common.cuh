@@ -175,11 +175,11 @@ struct gci_ctx {
   int64_t p2p_row_cap = 0;            // int64 words per row the area was sized for
   bool p2p_ok = false;                // all peers mapped: gci_enqueue_genome_row pushes instead of calling NCCL
 
-  // read-set sharding over several GPUs (shard.cu): contigs have an owner rank, reads a home rank (id % world)
+  // read-set sharding over several GPUs (shard.cu): contigs have an owner rank, reads a home rank (home_rank())
   struct Shard {
     bool on = false;
     int rank = 0, world = 1, max_files = 0;
-    uint32_t n_home = 0;              // reads this rank is home to: ids rank, rank + world, ...
+    uint32_t n_home = 0;              // reads this rank is home to (home_count())
     int64_t cap1 = 0, cap2 = 0;       // rows per (file, source rank) / per source rank in the inboxes
     int64_t surv_slots = 0;           // survivor slots behind surv_contig / surv_start / surv_end (world * cap2)
     std::vector<int32_t> owner;       // host copy of the contig owners
@@ -355,6 +355,26 @@ __device__ __forceinline__ void contig_cache_load(ContigCache& cc, BucketArgs& b
   __syncthreads();
   bk.len = cc.len;
   bk.tile_off = cc.tile_off;
+}
+
+// Home rank of a read (shard.cu): block-cyclic over the ranks in blocks of GCI_HOME_BLOCK ids.  Consecutive records
+// of a coordinate-sorted file carry neighbouring read ids, so the lanes of a warp send their rows to ONE home, into
+// adjacent slots: the stores leave over NVLink as a few hundred contiguous bytes instead of 24-byte pieces to every
+// peer in turn (id % world measured 0.68 ms per step for the dispatch at 8 GPUs against 0.14 ms of local stores).
+#define GCI_HOME_BLOCK 64u
+__host__ __device__ __forceinline__ uint32_t home_rank(uint32_t q, uint32_t world) { return (q / GCI_HOME_BLOCK) % world; }
+__host__ __device__ __forceinline__ uint32_t home_local(uint32_t q, uint32_t world) {
+  return q / (GCI_HOME_BLOCK * world) * GCI_HOME_BLOCK + q % GCI_HOME_BLOCK;
+}
+__host__ __device__ __forceinline__ uint32_t home_global(uint32_t h, uint32_t rank, uint32_t world) {
+  return (h / GCI_HOME_BLOCK * world + rank) * GCI_HOME_BLOCK + h % GCI_HOME_BLOCK;
+}
+// how many of the ids 0 .. n_reads-1 are homed at `rank` (their local ids are 0 .. count-1)
+__host__ __device__ __forceinline__ uint32_t home_count(uint32_t n_reads, uint32_t rank, uint32_t world) {
+  const uint32_t cyc = GCI_HOME_BLOCK * world, full = n_reads / cyc, rest = n_reads % cyc;
+  const uint32_t lo = rank * GCI_HOME_BLOCK;
+  const uint32_t tail = rest > lo ? (rest - lo < GCI_HOME_BLOCK ? rest - lo : GCI_HOME_BLOCK) : 0u;
+  return full * GCI_HOME_BLOCK + tail;
 }
 
 // Work split of the persistent kernels: every CTA walks ONE contiguous range of the items, `step` items per round.

@@ -45,7 +45,11 @@ __global__ void bucket_fill_kernel(uint32_t n_reads, const int32_t* __restrict__
                                    const uint32_t* __restrict__ n_dev /* survivor count on the device, or NULL */) {
   __shared__ ContigCache cc;
   const uint32_t limit = n_dev ? *n_dev : n_reads;
-  if (blockIdx.x * blockDim.x >= limit) return;            // (whole CTA: the grid is sized for the slot capacity)
+  // contiguous survivor range per CTA: the grid is bounded (a sharded read set sizes n_reads for the slot capacity,
+  // world x the survivors that arrive), CTAs behind the count leave at once
+  long long begin, end;
+  cta_range(limit, blockDim.x, begin, end);
+  if (begin >= end) return;
   if (n_contigs <= GCI_SMEM_CONTIGS) {
     for (int i = threadIdx.x; i < n_contigs; i += blockDim.x) cc.len[i] = len[i];
     for (int i = threadIdx.x; i <= n_contigs; i += blockDim.x) cc.tile_off[i] = tile_off[i];
@@ -53,19 +57,21 @@ __global__ void bucket_fill_kernel(uint32_t n_reads, const int32_t* __restrict__
     len = cc.len;
     tile_off = cc.tile_off;
   }
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= limit) return;
-  const Slice sl = survivor_slice(sc[r], ss[r], se[r], fl, len, tile_off);
-  if (!sl.ok) return;
-  {
-    const uint32_t base = (uint32_t)(tile_ps[sl.tile_a].y & 0xffffffffull);
-    const uint32_t k = atomicAdd(cursor + sl.tile_a, 1u);
-    events[base + k] = (uint16_t)(((uint32_t)(sl.a % GCI_TILE) << 1) | 0u);
-  }
-  {
-    const uint32_t base = (uint32_t)(tile_ps[sl.tile_b].y & 0xffffffffull);
-    const uint32_t k = atomicAdd(cursor + sl.tile_b, 1u);
-    events[base + k] = (uint16_t)(((uint32_t)(sl.b % GCI_TILE) << 1) | 1u);
+  for (long long at = begin; at < end; at += blockDim.x) {
+    const long long r = at + threadIdx.x;
+    if (r >= end) break;
+    const Slice sl = survivor_slice(sc[r], ss[r], se[r], fl, len, tile_off);
+    if (!sl.ok) continue;
+    {
+      const uint32_t base = (uint32_t)(tile_ps[sl.tile_a].y & 0xffffffffull);
+      const uint32_t k = atomicAdd(cursor + sl.tile_a, 1u);
+      events[base + k] = (uint16_t)(((uint32_t)(sl.a % GCI_TILE) << 1) | 0u);
+    }
+    {
+      const uint32_t base = (uint32_t)(tile_ps[sl.tile_b].y & 0xffffffffull);
+      const uint32_t k = atomicAdd(cursor + sl.tile_b, 1u);
+      events[base + k] = (uint16_t)(((uint32_t)(sl.b % GCI_TILE) << 1) | 1u);
+    }
   }
 }
 
@@ -615,7 +621,7 @@ int gci_depth_enqueue(gci_ctx* ctx, int32_t track, int32_t flank_len, int32_t lo
   uint32_t* cursor = counts + 2 * nt;
   GCI_TRY(gci_scan_tile_pack(ctx, counts, counts + nt, tile_ps, nt));
   if (nr) {
-    bucket_fill_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(
+    bucket_fill_kernel<<<(unsigned)std::min<int64_t>(((int64_t)nr + 255) / 256, (int64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
         nr, ctx->surv_contig.as<int32_t>(), ctx->surv_start.as<int32_t>(), ctx->surv_end.as<int32_t>(), flank_len,
         ctx->d_len.as<int64_t>(), ctx->d_tile_off.as<int64_t>(), tile_ps, cursor, ctx->events.as<uint16_t>(),
         ctx->n_contigs, ctx->shard.on ? ctx->shard.send_cnt.as<uint32_t>() + GCI_MAX_RANKS : nullptr);

@@ -3,7 +3,7 @@
 //
 // Contigs are owned by ranks (depth, scan and score are per contig), but the cross-file join (GCI.py:272-301) is
 // keyed by READ: a read's records may sit on contigs of different owners.  Instead of gathering every table on every
-// rank, every read has a HOME rank (read id % world) and the step moves each piece of data exactly once:
+// rank, every read has a HOME rank (block-cyclic in the read id, home_rank()) and the step moves each piece of data exactly once:
 //
 //   owner of the contig      BAM gates + last-record-wins dedup on the records it holds
 //        |   dispatch 1      every per-file winner row (read, contig, start, end, qlen, high-quality mark) is stored
@@ -25,7 +25,7 @@
 
 struct XRow1 { uint32_t tag; int32_t contig, start, end, qlen; uint32_t hq; };   // 24 B: a file's winner for one read
 struct XRow2 { int32_t contig, start, end, pad; };                                // 16 B: a survivor
-// Winner slots are DENSE: the row of home read h (= read id / world) sent by rank `src` lives at [src][h], so a sender
+// Winner slots are DENSE: the row of home read h (= home_local(read id)) sent by rank `src` lives at [src][h], so a sender
 // needs no slot counter and the receiver no merge pass; a row is valid when its tag equals the step's epoch (the areas
 // are never cleared: a stale row carries an older epoch).  Survivor rows are COMPACT per (destination, source): the
 // owner of a contig must not scan world x home-reads slots to find the few that are his, so the home claims slots per
@@ -46,7 +46,14 @@ struct XLayout {
   __host__ __device__ long long rows2_off(int par, int src) const {
     return rows2_base() + (long long)sizeof(XRow2) * cap2 * (par * (long long)world + src);
   }
-  __host__ __device__ long long total() const { return rows2_off(2, 0); }
+  // validity tags of the winner rows again, on their own ([par][file][src][cap1] u32): the home looks at world tags per
+  // read and file but only one or two rows carry the step's epoch, so it reads 4 bytes per source instead of a
+  // 32-byte sector of every source's row array
+  __host__ __device__ long long tags1_base() const { return (rows2_off(2, 0) + 255) & ~255LL; }
+  __host__ __device__ long long tags1_off(int par, int f, int src) const {
+    return tags1_base() + 4LL * ((cap1 + 63) & ~63LL) * ((par * files + f) * (long long)world + src);
+  }
+  __host__ __device__ long long total() const { return tags1_off(2, 0, 0); }
 };
 
 struct XPeers { char* area[GCI_MAX_RANKS]; };
@@ -92,11 +99,14 @@ dispatch1_kernel(XLayout lay, XPeers peers, int me, int f, int64_t n_rec, uint32
   const int par = (int)(epoch & 1ull);
   const XRow1 row{(uint32_t)epoch, ref_id[r], start[r], end[r], qlen[r], (uint32_t)highq[q]};
   const uint32_t w = (uint32_t)lay.world;
-  XRow1* dstp = reinterpret_cast<XRow1*>(peers.area[q % w] + lay.rows1_off(par, f, me)) + q / w;
+  char* dst_area = peers.area[home_rank(q, w)];
+  const uint32_t hl = home_local(q, w);
+  XRow1* dstp = reinterpret_cast<XRow1*>(dst_area + lay.rows1_off(par, f, me)) + hl;
   // 24 bytes as three 8-byte stores (rows are 8-byte aligned)
   const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&row);
   unsigned long long* d = reinterpret_cast<unsigned long long*>(dstp);
   d[0] = src[0]; d[1] = src[1]; d[2] = src[2];
+  reinterpret_cast<uint32_t*>(dst_area + lay.tags1_off(par, f, me))[hl] = (uint32_t)epoch;
 }
 
 // ---- raise this rank's flag of one phase at every peer ---------------------------------------------------------
@@ -175,10 +185,11 @@ home_join_kernel(XLayout lay, XPeers peers, int me, HomeArgs a, uint32_t n_home,
         // one candidate row per source rank; the highest contig wins (the reference's fetch order, GCI.py:260-269),
         // the high-quality marks of every rank's records count (:167-168)
         for (int src = 0; src < lay.world; src++) {
+          if (reinterpret_cast<const uint32_t*>(mine + lay.tags1_off(par, hf.bam, src))[h] != tag) continue;
           const XRow1* row = reinterpret_cast<const XRow1*>(mine + lay.rows1_off(par, hf.bam, src)) + h;
           const uint2* w2 = reinterpret_cast<const uint2*>(row);               // rows are 8-byte aligned
           const uint2 r0 = w2[0], r1 = w2[1], r2 = w2[2];                     // (tag, contig) (start, end) (qlen, hq)
-          if (r0.x != tag) continue;
+          if (r0.x != tag) continue;                                           // (cannot differ from the tag array)
           hq = hq || r2.y != 0;
           if ((int32_t)r0.y > x[f].c) {
             x[f] = JoinEntry{(int32_t)r0.y, (int32_t)r1.x, (int32_t)r1.y, (int32_t)r2.x};
@@ -187,7 +198,7 @@ home_join_kernel(XLayout lay, XPeers peers, int me, HomeArgs a, uint32_t n_home,
         }
       }
     }
-    have = join_one(a.n_files, k, [&x](int f) { return x[f]; }, a.n_files > 1 && hq, op, h * (uint32_t)lay.world + me,
+    have = join_one(a.n_files, k, [&x](int f) { return x[f]; }, a.n_files > 1 && hq, op, home_global(h, (uint32_t)me, (uint32_t)lay.world),
                     err, c, s, e);
   }
   {
@@ -425,6 +436,13 @@ void gci_shard_destroy_internal(gci_ctx* ctx) {
 
 extern "C" {
 
+int gci_shard_home(uint32_t read_id, int32_t world, int32_t* rank, uint32_t* local) {
+  if (world < 1 || world > GCI_MAX_RANKS) return GCI_E_ARG;
+  if (rank) *rank = (int32_t)home_rank(read_id, (uint32_t)world);
+  if (local) *local = home_local(read_id, (uint32_t)world);
+  return GCI_OK;
+}
+
 // contig owners and this rank's place among `world` ranks; gate_selected[n_contigs] (NULL = the contigs given to
 // gci_set_contigs) = every contig selected by --chrs on ANY rank: the gates and the PAF election must see them all.
 // Call after gci_set_contigs (whose `selected` then means: selected AND owned by this rank).
@@ -446,7 +464,7 @@ int gci_shard_config(gci_ctx* ctx, int32_t rank, int32_t world, const int32_t* c
   if (gate_selected) GCI_TRY(gci_h2d(ctx, ctx->d_gate_sel, gate_selected, (size_t)ctx->n_contigs));
   GCI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   sh.on = true;
-  sh.n_home = ctx->n_reads > (uint32_t)rank ? (ctx->n_reads - rank + world - 1) / world : 0;
+  sh.n_home = home_count(ctx->n_reads, (uint32_t)rank, (uint32_t)world);
   return GCI_OK;
 }
 
@@ -460,7 +478,7 @@ int gci_shard_alloc(gci_ctx* ctx, uint32_t max_reads, int32_t max_bam_files, gci
   ctx->epoch++;
   sh.opened = false;
   sh.max_files = max_bam_files;
-  sh.cap1 = sh.cap2 = ((int64_t)max_reads + sh.world - 1) / sh.world;
+  sh.cap1 = sh.cap2 = (int64_t)home_count(max_reads, 0, (uint32_t)sh.world);     // rank 0 is home to the most
   sh.surv_slots = sh.cap2 * sh.world;
   const XLayout lay = make_layout(ctx);
   sh.area_bytes = (size_t)lay.total();

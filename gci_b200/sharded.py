@@ -1,10 +1,10 @@
 """Host side of a read set sharded over several GPUs (libgci_cuda's shard.cu does the exchange).
 
-Contigs have an owner rank (LPT over their lengths, `dist.assign_contigs`), reads a home rank (read id % world).
+Contigs have an owner rank (LPT over their lengths, `dist.assign_contigs`), reads a home rank (block-cyclic in the read id, `home_rank`).
 The host only DEALS the decoded records:
 
     shard_bam(table, plan)   records lying on the contigs this rank owns          (global read / contig ids)
-    shard_paf(table, plan)   lines of the reads this rank is home to, read ids divided by world (home-local ids)
+    shard_paf(table, plan)   lines of the reads this rank is home to, read ids turned into home-local ids (`home_local`)
 
 Everything else — PAF election, gates, the two all-to-all dispatches over NVLink peer memory (winners to the read
 homes, survivors to the contig owners), merge, join, depth, scan, score — runs inside `Context.pipeline`.
@@ -19,6 +19,20 @@ import numpy as np
 from .records import AlnTable, PafTable
 
 _PAF_COLS = ("read_id", "qlen", "qstart", "qend", "ref_id", "tstart", "tend", "nmatch", "alnlen", "mapq")
+
+
+HOME_BLOCK = 64      # csrc/common.cuh GCI_HOME_BLOCK: reads are dealt to their home ranks in blocks of this many ids
+
+
+def home_rank(read_id, world):
+    """home rank of every read id (csrc/common.cuh home_rank)"""
+    return (np.asarray(read_id).astype(np.int64) // HOME_BLOCK) % int(world)
+
+
+def home_local(read_id, world):
+    """index of every read id among the reads of its home (csrc/common.cuh home_local)"""
+    q = np.asarray(read_id).astype(np.int64)
+    return q // (HOME_BLOCK * int(world)) * HOME_BLOCK + q % HOME_BLOCK
 
 
 @dataclass
@@ -51,9 +65,9 @@ def shard_bam(tab: AlnTable, plan: ShardPlan) -> AlnTable:
 
 
 def shard_paf(tab: PafTable, plan: ShardPlan) -> PafTable:
-    keep = np.flatnonzero(tab.read_id % np.uint32(plan.world) == plan.rank)
+    keep = np.flatnonzero(home_rank(tab.read_id, plan.world) == plan.rank)
     cols = {k: getattr(tab, k)[keep] for k in _PAF_COLS}
-    cols["read_id"] = cols["read_id"] // np.uint32(plan.world)
+    cols["read_id"] = home_local(cols["read_id"], plan.world).astype(np.uint32)
     return PafTable(*[cols[k] for k in _PAF_COLS])
 
 
@@ -99,13 +113,13 @@ def deal_paf_over_process_group(tab: PafTable, plan: ShardPlan) -> PafTable:
     import torch.distributed as dist
     world = plan.world
     mat = np.stack([getattr(tab, k).astype(np.int64) for k in _PAF_COLS], axis=1)
-    dst = (tab.read_id % np.uint32(world)).astype(np.int64)
+    dst = home_rank(tab.read_id, world)
     order = np.argsort(dst, kind="stable")
     counts = np.bincount(dst, minlength=world).astype(np.int64)
     if dist.get_backend() != "nccl":
         parts = D.allgather_varlen(mat.reshape(-1))
         allm = np.concatenate([p.reshape(-1, len(_PAF_COLS)) for p in parts])
-        mine = allm[allm[:, 0] % world == plan.rank]
+        mine = allm[home_rank(allm[:, 0], world) == plan.rank]
     else:
         dev = torch.device("cuda", torch.cuda.current_device())
         send = torch.from_numpy(np.ascontiguousarray(mat[order])).to(dev)
@@ -117,7 +131,7 @@ def deal_paf_over_process_group(tab: PafTable, plan: ShardPlan) -> PafTable:
         dist.all_to_all_single(recv, send, output_split_sizes=n_out, input_split_sizes=[int(x) for x in counts])
         mine = recv.cpu().numpy()
     cols = {k: mine[:, i] for i, k in enumerate(_PAF_COLS)}
-    cols["read_id"] = cols["read_id"] // world
+    cols["read_id"] = home_local(cols["read_id"], world)
     return PafTable(*[cols[k] for k in _PAF_COLS])
 
 

@@ -240,9 +240,10 @@ int gci_pipeline_row(gci_ctx* ctx, int32_t track, int32_t map_qual, int32_t mq_c
 
 /* ---- multi-GPU: read sets sharded over the ranks (the reference's analogue is the Pool fan-out and
    dict merge of GCI.py:257-301) -------------------------------------------------------------------------------------
-   Contigs have an owner rank, reads a home rank (read id % world).  A rank uploads
+   Contigs have an owner rank, reads a home rank: block-cyclic in the read id (gci_shard_home: blocks of 64 ids go
+   round the ranks, so neighbouring ids share a home and their rows leave as one contiguous NVLink write).  A rank uploads
      - the BAM records lying on the contigs it owns (global read ids, global contig ids), and
-     - the PAF lines of the reads it is home to, with HOME-LOCAL read ids (read id / world),
+     - the PAF lines of the reads it is home to, with HOME-LOCAL read ids (gci_shard_home's `local`),
    and gci_pipeline / gci_pipeline_row then run: PAF election and BAM gates locally -> every per-file winner goes to
    its read's home over NVLink peer memory -> merge + join at the home (GCI.py:268-301) -> every survivor goes to the
    owner of its contig -> depth, scan and score on the owned contigs.  n_survivors is then the number of survivors
@@ -250,6 +251,9 @@ int gci_pipeline_row(gci_ctx* ctx, int32_t track, int32_t map_qual, int32_t mq_c
    Call order: gci_set_contigs(selected = selected AND owned) -> gci_shard_config -> gci_shard_alloc (once, sized for
    the largest read set) -> exchange the handles, gci_shard_open -> per read type gci_reads_begin(global read count),
    uploads, gci_pipeline. */
+/* home rank and home-local id of a read among `world` ranks; returns how many of the ids 0 .. read_id-1 share that
+   home (== *local).  Host arithmetic only (no context, no GPU): what the caller deals PAF lines by. */
+int gci_shard_home(uint32_t read_id, int32_t world, int32_t* rank, uint32_t* local);
 int gci_shard_config(gci_ctx* ctx, int32_t rank, int32_t world, const int32_t* contig_owner /* [n_contigs] */,
                      const uint8_t* gate_selected /* [n_contigs] or NULL: contigs selected on ANY rank */);
 int gci_shard_alloc(gci_ctx* ctx, uint32_t max_reads, int32_t max_bam_files, gci_ipc_handle* out /* or NULL */);

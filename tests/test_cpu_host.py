@@ -32,6 +32,26 @@ def test_library_exports_every_header_symbol():
     assert lib.gci_version() >= 100
 
 
+def test_home_mapping_host_matches_library():
+    """the PAF dealing on the host (sharded.home_rank / home_local) and the kernels (gci_shard_home: the same inline
+    functions the dispatch kernel uses) agree, and the home-local ids of every rank are 0 .. count-1 without holes"""
+    import ctypes as C
+    from gci_b200 import sharded
+    lib = _ensure_built().load_library()
+    ids = np.concatenate([np.arange(0, 3000), np.arange(2**31 - 200, 2**31 + 200), [2**32 - 1]]).astype(np.uint32)
+    for world in (1, 2, 3, 8):
+        hr, hl = sharded.home_rank(ids, world), sharded.home_local(ids, world)
+        for q, r_want, l_want in zip(ids.tolist(), hr.tolist(), hl.tolist()):
+            r, l = C.c_int32(-1), C.c_uint32(0)
+            assert lib.gci_shard_home(q, world, C.byref(r), C.byref(l)) == 0
+            assert (r.value, l.value) == (r_want, l_want), (q, world)
+        n = 1000
+        for rank in range(world):
+            loc = np.sort(hl[:n][hr[:n] == rank])
+            assert np.array_equal(loc, np.arange(len(loc))), (world, rank)
+    assert lib.gci_shard_home(1, 0, None, None) != 0
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

@@ -29,8 +29,9 @@ WORKER = textwrap.dedent("""
     bam, paf = sharded.shard_bam(w.bam, plan), sharded.shard_paf(w.paf, plan)
     own = np.asarray(plan.owner) == rank
     assert own[bam.ref_id].all() and bam.n_records == int(own[w.bam.ref_id].sum())
-    mine = w.paf.read_id %% 2 == rank
-    assert paf.n_records == int(mine.sum()) and np.array_equal(paf.read_id, w.paf.read_id[mine] // 2)
+    mine = sharded.home_rank(w.paf.read_id, 2) == rank
+    assert 0 < int(mine.sum()) < w.paf.n_records
+    assert paf.n_records == int(mine.sum()) and np.array_equal(paf.read_id, sharded.home_local(w.paf.read_id[mine], 2))
     counts = D.allreduce(np.array([bam.n_records, paf.n_records], np.int64))
     assert counts.tolist() == [w.bam.n_records, w.paf.n_records]
     assert D.allreduce(np.array([rank + 1.5]), "max").tolist() == [2.5]
