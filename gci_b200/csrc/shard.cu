@@ -23,11 +23,14 @@
 
 #include "common.cuh"
 
-struct XRow1 { uint32_t tag; int32_t contig, start, end, qlen; uint32_t hq; };   // 24 B: a file's winner for one read
+// 16 B: a file's winner for one read; the high-quality mark of the read rides in bit 31 of the query length.  One
+// 16-byte store per lane: a warp whose reads share a home writes 512 contiguous bytes there.
+struct XRow1 { int32_t contig, start, end; uint32_t qlen_hq; };
+static_assert(sizeof(XRow1) == 16, "winner rows are stored and loaded as int4");
 struct XRow2 { int32_t contig, start, end, pad; };                                // 16 B: a survivor
 // Winner slots are DENSE: the row of home read h (= home_local(read id)) sent by rank `src` lives at [src][h], so a sender
-// needs no slot counter and the receiver no merge pass; a row is valid when its tag equals the step's epoch (the areas
-// are never cleared: a stale row carries an older epoch).  Survivor rows are COMPACT per (destination, source): the
+// needs no slot counter and the receiver no merge pass; a row is valid when its tag (tags1, an array of its own) equals
+// the step's epoch (the areas are never cleared: a stale row carries an older epoch).  Survivor rows are COMPACT per (destination, source): the
 // owner of a contig must not scan world x home-reads slots to find the few that are his, so the home claims slots per
 // destination (one atomic per CTA and destination) and publishes the counts with its flag.
 
@@ -83,7 +86,7 @@ __device__ __forceinline__ uint32_t claim_slot(uint32_t* cursor /* [world] */, i
 // thread per LOCAL record (the work scales with what this rank holds, not with the global read count): the record
 // that won its read (win[read] names it) sends the row.  Records are coordinate sorted and read ids follow first
 // appearance, so consecutive records carry nearby ids and the lanes that talk to one destination write neighbouring
-// 24-byte rows there.
+// 16-byte rows there.
 __global__ void __launch_bounds__(256)
 dispatch1_kernel(XLayout lay, XPeers peers, int me, int f, int64_t n_rec, uint32_t n_reads,
                  const uint32_t* __restrict__ read_id, const long long* __restrict__ win,
@@ -97,15 +100,11 @@ dispatch1_kernel(XLayout lay, XPeers peers, int me, int f, int64_t n_rec, uint32
   if (k < 0 || (int64_t)(k & 0xffffffffll) != r) return;
   const unsigned long long epoch = *reinterpret_cast<const unsigned long long*>(peers.area[me]);
   const int par = (int)(epoch & 1ull);
-  const XRow1 row{(uint32_t)epoch, ref_id[r], start[r], end[r], qlen[r], (uint32_t)highq[q]};
   const uint32_t w = (uint32_t)lay.world;
   char* dst_area = peers.area[home_rank(q, w)];
   const uint32_t hl = home_local(q, w);
-  XRow1* dstp = reinterpret_cast<XRow1*>(dst_area + lay.rows1_off(par, f, me)) + hl;
-  // 24 bytes as three 8-byte stores (rows are 8-byte aligned)
-  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&row);
-  unsigned long long* d = reinterpret_cast<unsigned long long*>(dstp);
-  d[0] = src[0]; d[1] = src[1]; d[2] = src[2];
+  reinterpret_cast<int4*>(dst_area + lay.rows1_off(par, f, me))[hl] =
+      make_int4(ref_id[r], start[r], end[r], (int)((uint32_t)qlen[r] | (highq[q] ? 0x80000000u : 0u)));
   reinterpret_cast<uint32_t*>(dst_area + lay.tags1_off(par, f, me))[hl] = (uint32_t)epoch;
 }
 
@@ -184,15 +183,19 @@ home_join_kernel(XLayout lay, XPeers peers, int me, HomeArgs a, uint32_t n_home,
       } else {
         // one candidate row per source rank; the highest contig wins (the reference's fetch order, GCI.py:260-269),
         // the high-quality marks of every rank's records count (:167-168)
-        for (int src = 0; src < lay.world; src++) {
-          if (reinterpret_cast<const uint32_t*>(mine + lay.tags1_off(par, hf.bam, src))[h] != tag) continue;
-          const XRow1* row = reinterpret_cast<const XRow1*>(mine + lay.rows1_off(par, hf.bam, src)) + h;
-          const uint2* w2 = reinterpret_cast<const uint2*>(row);               // rows are 8-byte aligned
-          const uint2 r0 = w2[0], r1 = w2[1], r2 = w2[2];                     // (tag, contig) (start, end) (qlen, hq)
-          if (r0.x != tag) continue;                                           // (cannot differ from the tag array)
-          hq = hq || r2.y != 0;
-          if ((int32_t)r0.y > x[f].c) {
-            x[f] = JoinEntry{(int32_t)r0.y, (int32_t)r1.x, (int32_t)r1.y, (int32_t)r2.x};
+        // the tags of every source first (independent loads), then the rows of the one or two that sent
+        uint32_t sent = 0;
+#pragma unroll
+        for (int src = 0; src < GCI_MAX_RANKS; src++)
+          if (src < lay.world && reinterpret_cast<const uint32_t*>(mine + lay.tags1_off(par, hf.bam, src))[h] == tag)
+            sent |= 1u << src;
+        while (sent) {
+          const int src = __ffs(sent) - 1;
+          sent &= sent - 1;
+          const int4 r = reinterpret_cast<const int4*>(mine + lay.rows1_off(par, hf.bam, src))[h];
+          hq = hq || ((uint32_t)r.w >> 31) != 0;
+          if (r.x > x[f].c) {
+            x[f] = JoinEntry{r.x, r.y, r.z, (int32_t)((uint32_t)r.w & 0x7fffffffu)};
             k[f] = src;
           }
         }
