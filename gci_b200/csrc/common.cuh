@@ -251,6 +251,7 @@ int gci_compute_flags(gci_ctx* ctx, int track, int32_t lo, int32_t hi);
 int gci_launch_score_kernels(gci_ctx* ctx, Track& t, double dist_percent, int32_t flank_len, int64_t* n_owners,
                              int64_t* n_slots, bool pending);   // scan.cu: result stays in ctx->tmp[1], no sync
 int gci_enqueue_genome_row(gci_ctx* ctx, Track& t, int64_t no, int64_t sum_len, int64_t cap, int64_t* h_rows);   // comm.cu
+int gci_shard_dispatch_enqueue(gci_ctx* ctx);                                                              // shard.cu
 int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t flank_len);           // shard.cu
 void gci_shard_destroy_internal(gci_ctx* ctx);                                                      // shard.cu
 int gci_scan_enqueue(gci_ctx* ctx, int32_t track, int32_t lo, int32_t hi, int32_t flank_len, int64_t* pin);

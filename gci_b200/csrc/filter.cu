@@ -1592,12 +1592,18 @@ static std::vector<char> pipeline_signature(gci_ctx* ctx, const PipeArgs& a) {
 
 static int pipeline_enqueue(gci_ctx* ctx, const PipeArgs& a, PipeOut* out) {
   GCI_TRY(reset_err(ctx));
-  GCI_TRY(gci_run_paf_legs(ctx, a.map_qual, a.mq_cutoff, a.ip));
+  // sharded read set: the BAM winners leave for their homes first, the PAF legs (home-local) run while they travel
+  if (!ctx->shard.on) GCI_TRY(gci_run_paf_legs(ctx, a.map_qual, a.mq_cutoff, a.ip));
   for (size_t i = 0; i < ctx->n_files; i++)
     if (ctx->files[i].kind == 0)
       GCI_TRY(gci_run_bam_leg(ctx, (int)i, ctx->files[i].src, a.map_qual, a.mq_cutoff, a.ip, a.cp));
-  if (ctx->shard.on) GCI_TRY(gci_shard_exchange_enqueue(ctx, a.op, a.track, a.flank_len));   // join at the read homes
-  else GCI_TRY(gci_run_join_counting(ctx, a.op, a.track, a.flank_len));
+  if (ctx->shard.on) {
+    GCI_TRY(gci_shard_dispatch_enqueue(ctx));
+    GCI_TRY(gci_run_paf_legs(ctx, a.map_qual, a.mq_cutoff, a.ip));
+    GCI_TRY(gci_shard_exchange_enqueue(ctx, a.op, a.track, a.flank_len));   // join at the read homes
+  } else {
+    GCI_TRY(gci_run_join_counting(ctx, a.op, a.track, a.flank_len));
+  }
   ctx->filtered = true;
   GCI_TRY(gci_depth_enqueue(ctx, a.track, a.flank_len, a.lo, a.hi));
   Track& t = ctx->track[a.track];

@@ -330,26 +330,72 @@ static XPeers make_peers(const gci_ctx* ctx) {
   return p;
 }
 
-// dispatch 1 .. consume 2 of one step; the BAM legs (win per global read, highq) and the PAF legs (home tables) have
-// been enqueued before.  Leaves the survivors in ctx->surv_* (shard.surv_slots slots) with their events counted.
-int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t flank_len) {
+struct XStep {
+  XLayout lay;
+  XPeers peers;
+  char* mine;
+  uint32_t* send_cnt;
+  unsigned long long* d_err;
+};
+
+static int step_args(gci_ctx* ctx, XStep* x) {
   gci_ctx::Shard& sh = ctx->shard;
   if (!sh.on || !sh.opened) return ctx->fail(GCI_E_ARG, "sharded read set: gci_shard_open / gci_shard_attach missing");
-  const XLayout lay = make_layout(ctx);
-  const XPeers peers = make_peers(ctx);
-  char* mine = (char*)sh.area.p;
-  if ((int64_t)ctx->n_reads > lay.cap1 * lay.world)
-    return ctx->fail(GCI_E_ARG, "sharded read set: %u reads, exchange sized for %lld", ctx->n_reads, lay.cap1 * lay.world);
+  x->lay = make_layout(ctx);
+  x->peers = make_peers(ctx);
+  x->mine = (char*)sh.area.p;
+  if ((int64_t)ctx->n_reads > x->lay.cap1 * x->lay.world)
+    return ctx->fail(GCI_E_ARG, "sharded read set: %u reads, exchange sized for %lld", ctx->n_reads, x->lay.cap1 * x->lay.world);
   int n_bam = 0;
   for (size_t i = 0; i < ctx->n_files; i++) n_bam += ctx->files[i].kind == 0 ? 1 : 0;
   if (n_bam > sh.max_files) return ctx->fail(GCI_E_ARG, "sharded read set: %d BAM files, exchange sized for %d", n_bam, sh.max_files);
-  unsigned long long* d_err = ctx->d_err.as<unsigned long long>();
-  ctx->counted_track = -1;
+  x->d_err = ctx->d_err.as<unsigned long long>();
+  x->send_cnt = sh.send_cnt.as<uint32_t>();
+  return GCI_OK;
+}
+
+// Dispatch 1 of one step: needs the BAM legs only (win per global read, highq), so the pipeline enqueues it right
+// after them and runs the PAF legs (home-local work) while the rows travel and the slower peers catch up.
+int gci_shard_dispatch_enqueue(gci_ctx* ctx) {
+  gci_ctx::Shard& sh = ctx->shard;
+  XStep x;
+  GCI_TRY(step_args(ctx, &x));
+  const XLayout& lay = x.lay;
   ctx->stage_begin(GCI_ST_XDISPATCH);
-  uint32_t* send_cnt = sh.send_cnt.as<uint32_t>();
-  xchg_begin_kernel<<<1, 32, 0, ctx->stream>>>(mine, send_cnt, sh.world);
+  xchg_begin_kernel<<<1, 32, 0, ctx->stream>>>(x.mine, x.send_cnt, sh.world);
   GCI_LAUNCH_CHECK(ctx);
-  // dispatch 1: BAM winners to the read homes
+  int f = 0;
+  for (size_t i = 0; i < ctx->n_files; i++) {
+    FileTable& ft = ctx->files[i];
+    if (ft.kind != 0) continue;
+    BamFile& b = ctx->bam[ft.src];
+    if (b.n) {
+      dispatch1_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, ctx->stream>>>(
+          lay, x.peers, sh.rank, f, b.n, ctx->n_reads, b.read_id.as<uint32_t>(), ft.win.as<long long>(),
+          b.ref_id.as<int32_t>(), b.ref_start.as<int32_t>(), b.ref_end.as<int32_t>(), b.qlen.as<int32_t>(),
+          ctx->highq.as<uint8_t>());
+      GCI_LAUNCH_CHECK(ctx);
+    }
+    f++;
+  }
+  xchg_signal_kernel<<<1, 32, 0, ctx->stream>>>(lay, x.peers, sh.rank, 0, x.send_cnt);
+  GCI_LAUNCH_CHECK(ctx);
+  ctx->stage_end();
+  return GCI_OK;
+}
+
+// The rest of the step, after gci_shard_dispatch_enqueue and the PAF legs (home tables): wait for the winners, join at
+// the homes, dispatch 2, consume.  Leaves the survivors in ctx->surv_* (shard.surv_slots slots), events counted.
+int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t flank_len) {
+  gci_ctx::Shard& sh = ctx->shard;
+  XStep x;
+  GCI_TRY(step_args(ctx, &x));
+  const XLayout& lay = x.lay;
+  const XPeers& peers = x.peers;
+  char* mine = x.mine;
+  uint32_t* send_cnt = x.send_cnt;
+  unsigned long long* d_err = x.d_err;
+  ctx->counted_track = -1;
   HomeArgs ha;
   memset(&ha, 0, sizeof ha);
   ha.n_files = (int)ctx->n_files;
@@ -364,19 +410,8 @@ int gci_shard_exchange_enqueue(gci_ctx* ctx, double op, int32_t track, int32_t f
       hf.c = ft.ref_id.as<int32_t>(); hf.s = ft.start.as<int32_t>(); hf.e = ft.end.as<int32_t>(); hf.q = ft.qlen.as<int32_t>();
       continue;
     }
-    BamFile& b = ctx->bam[ft.src];
-    if (b.n) {
-      dispatch1_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, ctx->stream>>>(
-          lay, peers, sh.rank, f, b.n, ctx->n_reads, b.read_id.as<uint32_t>(), ft.win.as<long long>(),
-          b.ref_id.as<int32_t>(), b.ref_start.as<int32_t>(), b.ref_end.as<int32_t>(), b.qlen.as<int32_t>(),
-          ctx->highq.as<uint8_t>());
-      GCI_LAUNCH_CHECK(ctx);
-    }
     hf.bam = f++;
   }
-  xchg_signal_kernel<<<1, 32, 0, ctx->stream>>>(lay, peers, sh.rank, 0, send_cnt);
-  GCI_LAUNCH_CHECK(ctx);
-  ctx->stage_end();
   ctx->stage_begin(GCI_ST_XWAIT);
   xchg_wait_kernel<<<1, 32, 0, ctx->stream>>>(lay, mine, 0, d_err);
   GCI_LAUNCH_CHECK(ctx);
