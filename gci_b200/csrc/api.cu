@@ -201,7 +201,7 @@ void gci_destroy(gci_ctx* ctx) {
   for (DevBuf* d : {&ctx->d_len, &ctx->d_selected, &ctx->d_tile_off, &ctx->d_owner_of, &ctx->d_nr_contig, &ctx->d_nr_start,
                     &ctx->d_nr_end, &ctx->highq, &ctx->highq_base, &ctx->surv_contig, &ctx->surv_start, &ctx->surv_end,
                     &ctx->tile_cnt, &ctx->events,
-                    &ctx->scan_tmp, &ctx->scan_tmp2, &ctx->misc, &ctx->d_err, &ctx->chunk_cnt, &ctx->chunk_off})
+                    &ctx->scan_tmp, &ctx->scan_tmp2, &ctx->misc, &ctx->d_err, &ctx->chunk_cnt, &ctx->chunk_off, &ctx->run_stage})
     ctx->release(*d);
   for (DevBuf* d : {&ctx->gz_tables, &ctx->gz_seg, &ctx->gz_hdr, &ctx->gz_bits, &ctx->gz_tile_cnt, &ctx->gz_tile_run,
                     &ctx->gz_run_pos, &ctx->gz_run_val, &ctx->gz_msize, &ctx->gz_moff, &ctx->gz_packed})

@@ -153,7 +153,7 @@ struct gci_ctx {
 
   // depth scratch
   DevBuf tile_cnt, events, scan_tmp, scan_tmp2, misc, d_err;
-  DevBuf chunk_cnt, chunk_off;
+  DevBuf chunk_cnt, chunk_off, run_stage;
   DevBuf scan_lvl[8];               // block sums / offsets of the recursive scan, two per level
   DevBuf tmp[10];                   // small per-call scratch (score terms, fetches)
   Track track[GCI_MAX_TRACKS];

@@ -324,28 +324,46 @@ __device__ __forceinline__ uint32_t win_word(const uint32_t* __restrict__ flags,
 
 constexpr int RUN_THREADS = 256;   // (CTAs of 1024 threads over 262 144 positions measured 0.38 instead of 0.21 ms, r02o)
 constexpr int RUN_WPT = GCI_RUN_CHUNK_WORDS / RUN_THREADS;   // words per thread (8)
+// Run starts / ends a chunk may leave in its staging slots during the COUNT pass.  The positions are known there
+// already, only their place in the interval arrays is not: staging them spares the second walk over the flag words
+// of every chunk that has a run border (17 M warp instructions, 62 us for configs[2] under ncu, profiles/r02ac).
+constexpr int RUN_STAGE = 16;
 
 // chunk -> owner through a host-built table (the chunk layout only depends on the contig table / regions):
 // one load instead of a binary search, and the contig's first flag word comes with the layout, so a CTA sees
 // two dependent global loads before its flag words instead of eight.
-// WRITE pass: chunks without a run start or end (almost all of them) leave after reading their counts.
+// One chunk by one CTA (block-collective; every return is taken by the whole CTA).  !WRITE: count, and stage the
+// positions of a chunk with few of them.  WRITE: a chunk with more than RUN_STAGE starts or ends, straight to the
+// interval arrays at the offsets the scan produced.
+struct RunArgs {
+  const uint32_t* flags;
+  const int32_t* chunk_owner;
+  const int64_t *chunk_off, *w_lo, *w_hi, *lay_w0, *lay_g0;
+  int2* cnt;
+  const longlong2* off;
+  int32_t *iv_start, *iv_end;
+  int64_t cap;
+  int32_t* stage;                 // [n_chunks][2][RUN_STAGE]
+  int64_t n_chunks;
+};
+
 template <bool WRITE>
-__global__ void __launch_bounds__(RUN_THREADS)
-runs_kernel(const uint32_t* __restrict__ flags, const int32_t* __restrict__ chunk_owner,
-            const int64_t* __restrict__ chunk_off, const int64_t* __restrict__ w_lo, const int64_t* __restrict__ w_hi,
-            const int64_t* __restrict__ lay_w0, const int64_t* __restrict__ lay_g0, int2* __restrict__ cnt,
-            const longlong2* __restrict__ off, int32_t* __restrict__ iv_start, int32_t* __restrict__ iv_end,
-            int64_t cap) {
+__device__ __forceinline__ void runs_chunk(const RunArgs& a, const int64_t chunk) {
+  const uint32_t* __restrict__ flags = a.flags;
+  const int32_t* __restrict__ chunk_owner = a.chunk_owner;
+  const int64_t* __restrict__ chunk_off = a.chunk_off;
+  const int64_t *__restrict__ w_lo = a.w_lo, *__restrict__ w_hi = a.w_hi, *__restrict__ lay_w0 = a.lay_w0,
+                *__restrict__ lay_g0 = a.lay_g0;
+  int2* __restrict__ cnt = a.cnt;
+  const longlong2* __restrict__ off = a.off;
+  int32_t *__restrict__ iv_start = a.iv_start, *__restrict__ iv_end = a.iv_end;
+  int64_t cap = a.cap;
+  int32_t* __restrict__ stage = a.stage;
   __shared__ int s_ws[RUN_THREADS / 32], s_we[RUN_THREADS / 32];
-  const int64_t chunk = blockIdx.x;
-  if (WRITE) {
-    const int2 c = cnt[chunk];
-    if (c.x == 0 && c.y == 0) return;
-  }
   const int64_t o = chunk_owner[chunk];
   const RunWin w = load_win(o, w_lo, w_hi, lay_w0, lay_g0);
   const int64_t j0 = (chunk - chunk_off[o]) * GCI_RUN_CHUNK_WORDS + (int64_t)threadIdx.x * RUN_WPT;
-  uint32_t st[RUN_WPT], en[RUN_WPT], m[RUN_WPT];
+  uint32_t m[RUN_WPT];
   int ns = 0, ne = 0;
   uint32_t prev;
   // my 8 words and the one before them lie completely inside the window: two 16-byte loads, no masking
@@ -373,16 +391,22 @@ runs_kernel(const uint32_t* __restrict__ flags, const int32_t* __restrict__ chun
     if (!WRITE && threadIdx.x == 0) cnt[chunk] = make_int2(0, 0);
     return;
   }
+  // run starts / ends of word k (recomputed where they are written: the masks of eight words cost 16 registers, and
+  // the count pass lives on eight resident CTAs per SM)
+  auto borders = [&](int k, uint32_t& st, uint32_t& en) {
+    const uint32_t before = k ? m[k - 1] : prev;
+    const uint32_t sh = (m[k] << 1) | (before >> 31);
+    st = m[k] & ~sh;
+    en = ~m[k] & sh;
+    // an end can only be reported on a word that exists in the layout (positions <= hi)
+    if (j0 + k >= w.n_words) en = 0u;
+  };
 #pragma unroll
   for (int k = 0; k < RUN_WPT; k++) {
-    const uint32_t sh = (m[k] << 1) | (prev >> 31);
-    st[k] = m[k] & ~sh;
-    en[k] = ~m[k] & sh;
-    // an end can only be reported on a word that exists in the layout (positions <= hi)
-    if (j0 + k >= w.n_words) en[k] = 0u;
-    ns += __popc(st[k]);
-    ne += __popc(en[k]);
-    prev = m[k];
+    uint32_t st, en;
+    borders(k, st, en);
+    ns += __popc(st);
+    ne += __popc(en);
   }
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const int is = warp_incl_scan(ns, lane), ie = warp_incl_scan(ne, lane);
@@ -395,56 +419,109 @@ runs_kernel(const uint32_t* __restrict__ flags, const int32_t* __restrict__ chun
   }
   if (!WRITE) {
     if (threadIdx.x == 0) cnt[chunk] = make_int2(ts, te);
-    return;
+    if (ts > RUN_STAGE || te > RUN_STAGE) return;           // the write pass walks this chunk again
   }
-  if (ts == 0 && te == 0) return;
-  const longlong2 base = off[chunk];
+  // count pass: the chunk's few positions go to its staging slots (runs_unstage_kernel moves them once the offsets
+  // are known); write pass (a chunk with more than RUN_STAGE of either kind): straight to the interval arrays
+  int32_t* out_s = WRITE ? iv_start : stage + chunk * (2 * RUN_STAGE);
+  int32_t* out_e = WRITE ? iv_end : stage + chunk * (2 * RUN_STAGE) + RUN_STAGE;
+  if (!WRITE) cap = RUN_STAGE;
+  longlong2 base = make_longlong2(0, 0);
+  if (WRITE) base = off[chunk];
   int64_t ps = base.x + bs + is - ns;
   int64_t pe = base.y + be + ie - ne;
 #pragma unroll
   for (int k = 0; k < RUN_WPT; k++) {
     const int64_t p0 = (w.w0 + j0 + k) << 5;
-    uint32_t m = st[k];
-    while (m) {
-      const int b = __ffs(m) - 1;
-      m &= m - 1;
-      if (ps < cap) iv_start[ps] = (int32_t)(p0 + b);
+    uint32_t st, en;
+    borders(k, st, en);
+    while (st) {
+      const int b = __ffs(st) - 1;
+      st &= st - 1;
+      if (ps < cap) out_s[ps] = (int32_t)(p0 + b);
       ps++;
     }
-    m = en[k];
-    while (m) {
-      const int b = __ffs(m) - 1;
-      m &= m - 1;
-      if (pe < cap) iv_end[pe] = (int32_t)(p0 + b);
+    while (en) {
+      const int b = __ffs(en) - 1;
+      en &= en - 1;
+      if (pe < cap) out_e[pe] = (int32_t)(p0 + b);
       pe++;
     }
   }
 }
 
+// count pass: one CTA per chunk
+__global__ void __launch_bounds__(RUN_THREADS, 8)   // 32 registers: eight CTAs per SM keep enough flag loads in flight
+runs_count_kernel(RunArgs a) { runs_chunk<false>(a, blockIdx.x); }
+
+// write pass for the chunks the count pass could not stage (normally none): a bounded grid looks at 32 counts per
+// CTA and round, and walks the few chunks that need it (a CTA per chunk was 28 us of launches for nothing)
+__global__ void __launch_bounds__(RUN_THREADS)
+runs_write_kernel(RunArgs a) {
+  __shared__ int s_list[32];
+  __shared__ int s_n;
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < a.n_chunks; base += (int64_t)gridDim.x * 32) {
+    if (threadIdx.x < 32) {
+      const int64_t chunk = base + threadIdx.x;
+      bool need = false;
+      if (chunk < a.n_chunks) {
+        const int2 c = a.cnt[chunk];
+        need = c.x > RUN_STAGE || c.y > RUN_STAGE;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, need);
+      if (need) s_list[__popc(m & ((1u << threadIdx.x) - 1u))] = (int)threadIdx.x;
+      if (threadIdx.x == 0) s_n = __popc(m);
+    }
+    __syncthreads();
+    const int n = s_n;
+    for (int i = 0; i < n; i++) {
+      runs_chunk<true>(a, base + s_list[i]);
+      __syncthreads();                                      // the chunk's shared scratch is free again
+    }
+    __syncthreads();                                        // s_list / s_n are rewritten in the next round
+  }
+}
+
+// staged positions -> interval arrays, one thread per chunk (almost every chunk has nothing)
+__global__ void __launch_bounds__(256)
+runs_unstage_kernel(const int2* __restrict__ cnt, const longlong2* __restrict__ off, int64_t n_chunks,
+                    const int32_t* __restrict__ stage, int32_t* __restrict__ iv_start, int32_t* __restrict__ iv_end,
+                    int64_t cap) {
+  const int64_t chunk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (chunk >= n_chunks) return;
+  const int2 c = cnt[chunk];
+  if ((c.x | c.y) == 0 || c.x > RUN_STAGE || c.y > RUN_STAGE) return;
+  const longlong2 base = off[chunk];
+  const int32_t* sp = stage + chunk * (2 * RUN_STAGE);
+  for (int j = 0; j < c.x; j++)
+    if (base.x + j < cap) iv_start[base.x + j] = sp[j];
+  for (int j = 0; j < c.y; j++)
+    if (base.y + j < cap) iv_end[base.y + j] = sp[RUN_STAGE + j];
+}
+
 // one block: exclusive scan of the (starts, ends) chunk counts, totals, and the per-owner interval offsets.
-// Every thread owns a contiguous strip of chunks: strip sums -> one block-wide scan of the 1024 strip totals ->
-// strip-serial write (two passes over an L2-resident array instead of one block barrier per 1024 chunks).
+// Every WARP owns a contiguous strip of chunks and walks it 32 chunks at a time with coalesced loads: strip sums ->
+// the 32 strip totals through shared memory -> second walk with a warp scan per 32 chunks, the next 32 counts
+// already requested.  (A strip per THREAD made every load of a warp touch 32 different lines, one after the other:
+// 55 us for 47 578 chunks under ncu, profiles/r02ac, with the rest of the GPU idle.)
 __global__ void __launch_bounds__(1024)
 runs_scan_kernel(const int2* __restrict__ cnt, int64_t n_chunks, longlong2* __restrict__ off, int64_t n_owners,
                  const int64_t* __restrict__ chunk_off, int64_t* __restrict__ owner_off /* [n_owners+1 | total_s | total_e] */) {
   __shared__ long long s_ws[32], s_we[32];
   __shared__ long long s_ts, s_te;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t strip = (n_chunks + 1023) / 1024;
-  const int64_t i0 = min(n_chunks, (int64_t)threadIdx.x * strip), i1 = min(n_chunks, i0 + strip);
+  const int64_t strip = (((n_chunks + 31) / 32) + 31) & ~int64_t(31);
+  const int64_t i0 = min(n_chunks, (int64_t)w * strip), i1 = min(n_chunks, i0 + strip);
   long long ss = 0, se = 0;
-  for (int64_t i = i0; i < i1; i++) {
+#pragma unroll 4
+  for (int64_t i = i0 + lane; i < i1; i += 32) {
     const int2 v = cnt[i];
     ss += v.x;
     se += v.y;
   }
-  long long is = ss, ie = se;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const long long a = __shfl_up_sync(0xffffffffu, is, d), b = __shfl_up_sync(0xffffffffu, ie, d);
-    if (lane >= d) { is += a; ie += b; }
-  }
-  if (lane == 31) { s_ws[w] = is; s_we[w] = ie; }
+  ss = warp_sum_ll(ss);
+  se = warp_sum_ll(se);
+  if (lane == 0) { s_ws[w] = ss; s_we[w] = se; }
   __syncthreads();
   long long os = 0, oe = 0, ts = 0, te = 0;
   for (int j = 0; j < 32; j++) {
@@ -452,12 +529,15 @@ runs_scan_kernel(const int2* __restrict__ cnt, int64_t n_chunks, longlong2* __re
     if (j < w) { os += a; oe += b; }
     ts += a; te += b;
   }
-  long long rs = os + is - ss, re = oe + ie - se;          // exclusive prefix of my strip
-  for (int64_t i = i0; i < i1; i++) {
-    const int2 v = cnt[i];
-    off[i] = make_longlong2(rs, re);
-    rs += v.x;
-    re += v.y;
+  // a chunk holds at most 2^15 runs: the scan of 32 chunks fits 32 bits
+  int2 v = (i0 + lane < i1) ? cnt[i0 + lane] : make_int2(0, 0);
+  for (int64_t base = i0; base < i1; base += 32) {
+    const int2 nxt = (base + 32 + lane < i1) ? cnt[base + 32 + lane] : make_int2(0, 0);
+    const int xs = warp_incl_scan(v.x, lane), xe = warp_incl_scan(v.y, lane);
+    if (base + lane < i1) off[base + lane] = make_longlong2(os + xs - v.x, oe + xe - v.y);
+    os += __shfl_sync(0xffffffffu, xs, 31);
+    oe += __shfl_sync(0xffffffffu, xe, 31);
+    v = nxt;
   }
   if (threadIdx.x == 0) { s_ts = ts; s_te = te; }
   __syncthreads();                                          // off[] of the whole block is written (same block reads it)
@@ -516,6 +596,8 @@ static int extract_runs(gci_ctx* ctx, Track& t, const std::vector<int64_t>& lay_
   const int32_t* d_chunk_owner = reinterpret_cast<const int32_t*>(d_chunk_off + lay_head);
   GCI_TRY(ctx->ensure(ctx->chunk_cnt, sizeof(int2) * (size_t)n_chunks));
   GCI_TRY(ctx->ensure(ctx->scan_tmp, sizeof(longlong2) * (size_t)n_chunks));
+  GCI_TRY(ctx->ensure(ctx->run_stage, sizeof(int32_t) * 2 * RUN_STAGE * (size_t)n_chunks));
+  int32_t* stage = ctx->run_stage.as<int32_t>();
   int2* cnt = ctx->chunk_cnt.as<int2>();
   longlong2* off = ctx->scan_tmp.as<longlong2>();
   if (t.iv_cap < 4096) {
@@ -523,27 +605,45 @@ static int extract_runs(gci_ctx* ctx, Track& t, const std::vector<int64_t>& lay_
     GCI_TRY(ctx->ensure(t.iv_end, sizeof(int32_t) * 4096));
     t.iv_cap = 4096;
   }
-  runs_kernel<false><<<(unsigned)n_chunks, RUN_THREADS, 0, ctx->stream>>>(
-      t.flags.as<uint32_t>(), d_chunk_owner, d_chunk_off, t.win_lo.as<int64_t>(), t.win_hi.as<int64_t>(), d_w0, d_g0,
-      cnt, nullptr, nullptr, nullptr, 0);
+  RunArgs ra;
+  ra.flags = t.flags.as<uint32_t>();
+  ra.chunk_owner = d_chunk_owner;
+  ra.chunk_off = d_chunk_off;
+  ra.w_lo = t.win_lo.as<int64_t>();
+  ra.w_hi = t.win_hi.as<int64_t>();
+  ra.lay_w0 = d_w0;
+  ra.lay_g0 = d_g0;
+  ra.cnt = cnt;
+  ra.off = off;
+  ra.iv_start = nullptr;
+  ra.iv_end = nullptr;
+  ra.cap = 0;
+  ra.stage = stage;
+  ra.n_chunks = n_chunks;
+  runs_count_kernel<<<(unsigned)n_chunks, RUN_THREADS, 0, ctx->stream>>>(ra);
   GCI_LAUNCH_CHECK(ctx);
   runs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, n_chunks, off, n_owners, d_chunk_off, t.owner_off.as<int64_t>());
   GCI_LAUNCH_CHECK(ctx);
-  if (defer_pin) {
-    runs_kernel<true><<<(unsigned)n_chunks, RUN_THREADS, 0, ctx->stream>>>(
-        t.flags.as<uint32_t>(), d_chunk_owner, d_chunk_off, t.win_lo.as<int64_t>(), t.win_hi.as<int64_t>(), d_w0, d_g0,
-        cnt, off, t.iv_start.as<int32_t>(), t.iv_end.as<int32_t>(), t.iv_cap);
+  auto emit = [&]() -> int {
+    runs_unstage_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, ctx->stream>>>(
+        cnt, off, n_chunks, stage, t.iv_start.as<int32_t>(), t.iv_end.as<int32_t>(), t.iv_cap);
     GCI_LAUNCH_CHECK(ctx);
+    ra.iv_start = t.iv_start.as<int32_t>();
+    ra.iv_end = t.iv_end.as<int32_t>();
+    ra.cap = t.iv_cap;
+    runs_write_kernel<<<(unsigned)std::min<int64_t>((n_chunks + 31) / 32, (int64_t)ctx->sm_count * 8), RUN_THREADS, 0, ctx->stream>>>(ra);
+    GCI_LAUNCH_CHECK(ctx);
+    return GCI_OK;
+  };
+  if (defer_pin) {
+    GCI_TRY(emit());
     GCI_TRY(gci_d2h(ctx, defer_pin, t.owner_off.p, sizeof(int64_t) * (size_t)(n_owners + 3)));
     return GCI_OK;
   }
   int64_t* h = (int64_t*)ctx->pinned(sizeof(int64_t) * (size_t)(n_owners + 3));
   if (!h) return ctx->fail(GCI_E_NOMEM, "pinned scratch allocation failed");
   for (int attempt = 0; attempt < 2; attempt++) {
-    runs_kernel<true><<<(unsigned)n_chunks, RUN_THREADS, 0, ctx->stream>>>(
-        t.flags.as<uint32_t>(), d_chunk_owner, d_chunk_off, t.win_lo.as<int64_t>(), t.win_hi.as<int64_t>(), d_w0, d_g0,
-        cnt, off, t.iv_start.as<int32_t>(), t.iv_end.as<int32_t>(), t.iv_cap);
-    GCI_LAUNCH_CHECK(ctx);
+    GCI_TRY(emit());
     if (attempt == 0) {
       GCI_TRY(gci_d2h(ctx, h, t.owner_off.p, sizeof(int64_t) * (size_t)(n_owners + 3)));
     }
