@@ -231,6 +231,33 @@ def test_regions_windows(ctx):
             assert int(nctg[k]) == len(O.complement_lengths(merged, e - s, s, s, e))
 
 
+def test_scan_staged_and_walked_chunks(ctx):
+    """run extraction: a 65 536-position chunk with at most 16 run starts / ends stages them while counting, one with
+    more is walked a second time (csrc/scan.cu RUN_STAGE): both kinds side by side, a run across a chunk border, a run
+    that starts on the last position of a chunk, flanks 0 and 15, thresholds 0 and 3"""
+    L = 4 * 65536 + 1234
+    d = np.full(L, 9, np.int32)
+    for k in range(16):                                   # chunk 0: exactly 16 runs -> staged
+        d[1000 + 300 * k:1000 + 300 * k + 7] = 0
+    for k in range(17):                                   # chunk 1: 17 runs -> walked
+        d[65536 + 500 + 200 * k:65536 + 500 + 200 * k + 3] = 2
+    d[2 * 65536 - 40:2 * 65536 + 90] = 0                  # across the border of chunks 1 and 2
+    d[3 * 65536 - 1:3 * 65536 + 5] = 1                    # starts on the last position of chunk 2
+    d[L - 20:] = 0                                        # reaches the end of the contig
+    ctx.set_contigs([L, 70_000])
+    ctx.load_depth(0, 0, d)
+    e = np.full(70_000, 5, np.int32)
+    e[::2] = 0                                            # 35 000 runs in two chunks
+    ctx.load_depth(0, 1, e)
+    for fl in (0, 15):
+        for hi in (0, 3):
+            ctx.scan(0, -1, hi, fl)
+            gs, ge, off = ctx.fetch_intervals(0, 2)
+            for i, dep in enumerate((d, e)):
+                got = list(zip(gs[off[i]:off[i + 1]].tolist(), ge[off[i]:off[i + 1]].tolist()))
+                assert got == O.collapse_depth_range(dep.astype(np.int64), -1, hi, fl, 0), (fl, hi, i)
+
+
 def test_full_size_chr19_properties(ctx):
     """BASELINE config 2 size (58 Mbp, 30x): size-independent properties instead of the slow oracle"""
     L = 58_000_000
