@@ -443,7 +443,8 @@ def main():
     # step-level algorithmic bytes: depth + flags written once, every CIGAR op, BAM columns (35 B) and PAF columns
     # (40 B) read once
     step_bytes = alg_bytes + 4.0 * w.bam.n_ops + 35.0 * w.bam.n_records + 40.0 * paf.n_records
-    roofline = {"bound": "hbm", "kernel": "depth_tile_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    depth_kernel = "depth_tile_kernel<true>" if os.environ.get("GCI_DEPTH_TMA", "1")[:1] == "0" else "depth_tile_tma_kernel<true>"
+    roofline = {"bound": "hbm", "kernel": depth_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": d_ms / max(1, d_k),
                 "kernel_share_of_step": (d_ms / max(1, d_k)) / step_ms,
