@@ -424,7 +424,9 @@ struct gci_paf {
 };
 
 static inline bool parse_int(std::string_view s, long long& v) {
-  // Python int(): optional surrounding whitespace was already stripped by split; optional sign
+  // Python int(): surrounding blanks are accepted (a tab-split field may keep them), optional sign, '_' between digits
+  while (!s.empty() && (s.front() == ' ' || s.front() == '\r' || s.front() == '\f' || s.front() == '\v')) s.remove_prefix(1);
+  while (!s.empty() && (s.back() == ' ' || s.back() == '\r' || s.back() == '\f' || s.back() == '\v')) s.remove_suffix(1);
   if (s.empty()) return false;
   size_t i = 0;
   bool neg = false;
@@ -435,6 +437,7 @@ static inline bool parse_int(std::string_view s, long long& v) {
     if (s[i] == '_') continue;
     if (s[i] < '0' || s[i] > '9') return false;
     x = x * 10 + (s[i] - '0');
+    if (x > (1ll << 40)) return false;            // far outside any column: no overflow of x itself
   }
   v = neg ? -x : x;
   return true;
@@ -507,6 +510,9 @@ int gci_paf_open(const char* path, gci_interner* it, int32_t n_contigs, const ch
         bool ok = true;
         for (int k = 0; want[k] >= 0; k++) ok = ok && parse_int(col[want[k]], v[want[k]]);
         if (!ok) { pt.bad_line = pt.lines; pt.bad_what = "invalid integer"; break; }
+        // the device columns are int32: a value outside that range is reported, not truncated
+        for (int k = 0; want[k] >= 0; k++) ok = ok && v[want[k]] >= INT32_MIN && v[want[k]] <= INT32_MAX;
+        if (!ok) { pt.bad_line = pt.lines; pt.bad_what = "integer outside the int32 range of the device columns"; break; }
         pt.names.push_back(col[0]);
         pt.hashes.push_back(name_hash(col[0].data(), col[0].size()));
         auto c = cidx.find(col[5]);

@@ -287,6 +287,27 @@ def _remap_paf_by_name(t, names, base_names):
     return PafTable(t.read_id, t.qlen, t.qstart, t.qend, lut[rid], t.tstart, t.tend, t.nmatch, t.alnlen, t.mapq)
 
 
+def _prune_for_gates(t, selected, map_qual):
+    """Records the gates drop before they look at anything else never need to reach the GPU: unmapped / secondary /
+    supplementary records and records below `-mq` (GCI.py:153-156: skipped before the NM tag is read, so they cannot
+    raise either) and records on contigs that are never fetched (`--chrs`, :151, :202-207).  Their CIGARs are most of
+    what a BAM with many supplementary alignments uploads.  A table that keeps more than 90 % of its records is
+    passed on as it is (the copy would cost more than it saves)."""
+    n = t.n_records
+    if n == 0:
+        return t
+    sel = np.asarray(selected, bool)
+    rid = np.asarray(t.ref_id, np.int64)
+    ok = (rid >= 0) & (rid < len(sel))
+    ok &= sel[np.clip(rid, 0, len(sel) - 1)]
+    ok &= (np.asarray(t.flag, np.int64) & (0x4 | 0x100 | 0x800)) == 0
+    ok &= np.asarray(t.mapq, np.int64) >= int(map_qual)
+    kept = int(ok.sum())
+    if kept > 0.9 * n:
+        return t
+    return t.take(np.flatnonzero(ok))
+
+
 def _load_inputs(paf_files, bam_files, threads=1):
     """Decode / collect the files of one read type.  Returns (names, lengths, paf tables, bam tables, n_reads).
     Contig names and lengths are the first BAM's (GCI.py:201); every later BAM is remapped onto them by name."""
@@ -342,6 +363,8 @@ def filter(paf_files=[], bam_files=[], prefix='GCI', map_qual=30, mq_cutoff=50, 
     targets_length = {n: l for n, l in zip(out_order, (dict(zip(names, lengths))[x] for x in out_order)) if sel[n]}
     track = TRACK_NANO if log_reads_type == 'ONT' else TRACK_HIFI
 
+    gate_sel = session.run_selected if session.plan is not None else session.selected
+    bams = [_prune_for_gates(t, gate_sel, map_qual) for t in bams]
     lo, hi = session.scan_hint if session.scan_hint is not None else (NO_FLAGS, NO_FLAGS)
     if session.plan is None:
         ctx.reads_begin(n_reads)

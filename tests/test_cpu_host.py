@@ -151,6 +151,17 @@ def test_paf_parallel_chunks(tmp_path, monkeypatch):
         monkeypatch.setenv("GCI_IO_THREADS", threads)
         with pytest.raises(ValueError, match="PAF line 25001: invalid integer"):
             gio.read_paf(p, ["chr1", "chr2"], gio.NameTable(native=True))
+    # Python's int() accepts blanks around a field; a value outside int32 is reported, not truncated
+    ok = lines[:50]
+    ok[7] = ok[7].replace("\t20000\t", "\t 20000 \t", 1)
+    open(p, "w").write("\n".join(ok) + "\n")
+    want = gio.read_paf_py(p, {"chr1": 0, "chr2": 1})
+    got = gio.read_paf(p, ["chr1", "chr2"], gio.NameTable(native=True))
+    assert np.array_equal(got.qlen, want.qlen) and int(got.qlen[7]) == 20000
+    ok[9] = ok[9].replace("\t20000\t", "\t3000000000\t", 1)
+    open(p, "w").write("\n".join(ok) + "\n")
+    with pytest.raises(ValueError, match="PAF line 10: integer outside the int32 range"):
+        gio.read_paf(p, ["chr1", "chr2"], gio.NameTable(native=True))
 
 
 def test_bam_long_cigar_cg_tag(tmp_path):
@@ -337,3 +348,30 @@ def test_later_bam_with_permuted_sq_order_is_remapped_by_name():
     assert bams[0].ref_id.tolist() == [0, 1]
     assert bams[1].ref_id.tolist() == [1, 0, -1, -1]
     assert bams[1].ref_start.tolist() == [5, 7, 1, 0]
+
+
+def test_records_the_gates_drop_first_are_pruned_before_upload():
+    """unmapped / secondary / supplementary / below -mq / never-fetched-contig records are dropped on the
+    host (GCI.py:151-156 skips them before it reads anything else); their CIGARs go with them; a table that keeps
+    almost everything is passed on untouched"""
+    from gci_b200 import pipeline as P
+    rows = []
+    for i in range(40):
+        flag = [0, 16, 0x100, 0x800, 4, 0x900][i % 6]
+        rows.append(dict(ref_id=[0, 1, 2, -1][i % 4], ref_start=i, mapq=[60, 10][i % 2 if i % 5 == 0 else 0], flag=flag,
+                         nm=None if i % 7 == 0 else 1, qlen=10 + i, read_id=i, cigar=f"{5 + i}M{1 + i % 3}I2S"))
+    t = AlnTable.from_rows(rows)
+    sel = [True, False, True]
+    got = P._prune_for_gates(t, sel, 30)
+    want = [i for i, r in enumerate(rows) if r["ref_id"] in (0, 2) and not (r["flag"] & 0x904) and r["mapq"] >= 30]
+    assert 0 < len(want) < 36 and got.read_id.tolist() == want
+    for k, i in enumerate(want):
+        a, b = int(t.cigar_off[i]), int(t.cigar_off[i + 1])
+        c, d = int(got.cigar_off[k]), int(got.cigar_off[k + 1])
+        assert np.array_equal(got.cigar[c:d], t.cigar[a:b])
+        assert int(got.nm[k]) == int(t.nm[i]) and int(got.qlen[k]) == rows[i]["qlen"]
+    clean = AlnTable.from_rows([dict(ref_id=0, ref_start=i, mapq=60, flag=0, nm=0, qlen=10, read_id=i, cigar="10M")
+                                for i in range(20)])
+    assert P._prune_for_gates(clean, [True], 30) is clean
+    empty = clean.take(np.zeros(0, np.int64))
+    assert P._prune_for_gates(empty, [True], 30).n_records == 0
