@@ -170,15 +170,18 @@ def aligned_on(w, sel):
     return b + p
 
 
-def cpu_port_pass(w, threads, selected=None, with_hash=False):
+def cpu_port_pass(w, threads, selected=None, with_hash=False, with_write=True):
     """One pass of the oracle's C port over the workload (test infrastructure used as the timed baseline): PAF
-    election, BAM gates + dedup, join, int64 depth `+=`, the per-base collapse loop, score rows."""
+    election, BAM gates + dedup, join, int64 depth `+=`, `write_depth` (GCI.py:99-143: text + gzip level 9, `threads`
+    members per contig, kept in memory — what the GPU arm's e2e returns as `.depth.gz` bytes), the per-base collapse
+    loop, score rows."""
     from oracle import c_oracle as CO
     from oracle import gci_oracle as O
     L = [int(x) for x in w.contigs.lengths]
     beds, hashes, sums, n_surv, t_chk = CO.hot_path_summary([w.bam], L, w.n_reads, selected=selected, flank_len=FLANK,
                                                      threshold=THRESHOLD, threads=threads, pafs=[w.paf],
-                                                     names=w.contigs.names, with_hash=with_hash, **PARAMS)
+                                                     names=w.contigs.names, with_hash=with_hash,
+                                                     with_write=with_write, **PARAMS)
     keep = [i for i in range(len(L)) if selected is None or selected[i]]
     rows = O.score_rows([w.contigs.names[i] for i in keep], [L[i] for i in keep], [beds[i] for i in keep], FLANK, DIST)
     return dict(n_surv=n_surv, beds=beds, hashes=hashes, sums=sums, rows=rows, t_chk=t_chk)
@@ -215,7 +218,8 @@ def run_reference(args, rank, world):
     val = sample_aligned * args.steps / dt / 1e9
     sample = (f"per step: the {int(sel.sum())} shortest contigs ({sum(l for l, s in zip(L, sel) if s)} bases, "
               f"{sample_aligned} aligned bases of both files) of the workload as a --chrs run (oracle/gci_oracle.c: "
-              "PAF election, gates, dedup, join, int64 depth +=, per-base collapse loop, score rows)")
+              "PAF election, gates, dedup, join, int64 depth +=, write_depth text + gzip level 9 in memory, per-base "
+              "collapse loop, score rows)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
@@ -485,7 +489,8 @@ def main():
     if cpu is not None:
         line["cpu_baseline"] = {"value": w.aligned_bases / cpu_dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "1 pass over the full workload (oracle/gci_oracle.c, pthreads: PAF election, "
-                                          "gates, dedup, join, int64 depth +=, per-base collapse loop, score rows), "
+                                          "gates, dedup, join, int64 depth +=, write_depth text + gzip level 9 in "
+                                          "memory, per-base collapse loop, score rows), "
                                           f"{cpu_dt:.1f} s"}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
     pool.close()

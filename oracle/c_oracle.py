@@ -29,6 +29,7 @@ def lib():
         _lib.orc_collapse.restype = C.c_int64
         _lib.orc_max_threads.restype = C.c_int
         _lib.orc_depth_hash.restype = C.c_uint64
+        _lib.orc_write_depth.restype = C.c_int64
     return _lib
 
 
@@ -141,6 +142,25 @@ def depth_hash(depth_arr, threads=1):
     return int(lib().orc_depth_hash(_ptr(d), C.c_int64(len(d)), C.c_int(threads)))
 
 
+def write_depth(depth_arr, name, threads=1, level=9, workers=None, fetch=False):
+    """write_depth of one contig (GCI.py:99-143): `threads` gzip members (level 9 like gzip.open) of ">name" + one
+    decimal per line, formatted and deflated on `workers` host threads.  -> number of bytes, or the bytes (fetch)."""
+    d = np.ascontiguousarray(depth_arr, dtype=np.int64)
+    workers = int(workers or threads)
+    nm = str(name).encode()
+    n = int(lib().orc_write_depth(_ptr(d), C.c_int64(len(d)), C.c_char_p(nm), int(threads), int(level), workers, None,
+                                  C.c_int64(0)))
+    if n < 0:
+        raise RuntimeError("orc_write_depth failed")
+    if not fetch:
+        return n
+    out = np.zeros(max(1, n), np.uint8)
+    m = int(lib().orc_write_depth(_ptr(d), C.c_int64(len(d)), C.c_char_p(nm), int(threads), int(level), workers,
+                                  _ptr(out), C.c_int64(n)))
+    assert m == n
+    return out[:n].tobytes()
+
+
 def name_rank(names):
     order = sorted(range(len(names)), key=lambda i: names[i])
     rank = np.empty(len(names), np.int32)
@@ -181,9 +201,11 @@ def hot_path(bams, lengths, n_reads, selected=None, map_qual=30, mq_cutoff=50, i
 
 
 def hot_path_summary(bams, lengths, n_reads, selected=None, flank_len=15, threshold=0, threads=1, pafs=(), names=None,
-                     with_hash=True, **gates):
+                     with_hash=True, with_write=False, **gates):
     """The same path with one contig's depth array alive at a time (a 3.1 Gbp genome is 25 GB of int64 otherwise):
-    -> (beds, depth checksums (orc_depth_hash) or None, depth sums, n_survivors, seconds spent on the checksums)"""
+    -> (beds, depth checksums (orc_depth_hash) or None, depth sums, n_survivors, seconds spent on the checksums).
+    with_write: every contig's depth also goes through write_depth (GCI.py:99-143, `threads` members per contig,
+    level 9, in memory); the byte count is left in hot_path_summary.gz_bytes."""
     import time
     if selected is None:
         selected = np.ones(len(lengths), bool)
@@ -191,6 +213,7 @@ def hot_path_summary(bams, lengths, n_reads, selected=None, flank_len=15, thresh
     order = np.argsort(sc, kind="stable")
     bounds = np.searchsorted(sc[order], np.arange(len(lengths) + 1))
     beds, hashes, sums, t_hash = [], [], [], 0.0
+    gz_bytes = 0
     for c, L in enumerate(lengths):
         if not selected[c]:
             beds.append([]); hashes.append(0); sums.append(0)
@@ -198,8 +221,11 @@ def hot_path_summary(bams, lengths, n_reads, selected=None, flank_len=15, thresh
         idx = order[bounds[c]:bounds[c + 1]]
         d = depth(np.zeros(len(idx), np.int32), ss[idx], se[idx], [int(L)], flank_len, threads)[0]
         beds.append(collapse(d, -1, threshold, flank_len, 0))
+        if with_write:
+            gz_bytes += write_depth(d, names[c] if names is not None else f"contig{c}", threads, 9, threads)
         t0 = time.perf_counter()
         hashes.append(depth_hash(d, threads) if with_hash else 0)
         sums.append(int(d.sum()))
         t_hash += time.perf_counter() - t0
+    hot_path_summary.gz_bytes = gz_bytes
     return beds, (hashes if with_hash else None), sums, int((sc >= 0).sum()), t_hash

@@ -16,7 +16,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
 #include <unistd.h>
+#include <zlib.h>
 
 /* minimal fork-join: run fn(tid, nt, arg) on nt threads (libgomp is not in the image) */
 typedef void (*par_fn)(int tid, int nt, void* arg);
@@ -407,6 +409,91 @@ uint64_t orc_depth_hash(const int64_t* depth, int64_t n, int threads) {
   uint64_t h = 0;
   for (int t = 0; t < threads; t++) h += a.part[t];
   return h;
+}
+
+/* write_depth, GCI.py:99-143: per contig `threads` parts of stp = 1 + (len - 1) / threads positions, each part its own
+   gzip file written with gzip.open(..., 'wb') (compresslevel 9): ">name\n" in part 0, then one decimal per line; the
+   parts are concatenated in order.  Here every part is formatted and deflated (zlib, level 9, gzip wrapper) by one of
+   `workers` threads into memory; nothing touches the disk.  out == NULL: only the sizes are produced (the timed
+   baseline); otherwise the members are copied to out in file order.  Returns the total number of bytes, -1 on error. */
+typedef struct {
+  const int64_t* d; int64_t n, stp; int parts; const char* name; int level;
+  unsigned char** buf; int64_t* len; int err;
+} wd_args;
+static int wd_one(const wd_args* a, int part) {
+  const int64_t lft = (int64_t)part * a->stp, rgh = lft + a->stp < a->n ? lft + a->stp : a->n;
+  z_stream z;
+  memset(&z, 0, sizeof z);
+  if (deflateInit2(&z, a->level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return -1;
+  size_t cap = (size_t)(rgh - lft) / 8 + 4096, used = 0;
+  unsigned char* out = (unsigned char*)malloc(cap);
+  char text[1 << 16];
+  size_t fill = 0;
+  int rc = 0;
+  if (part == 0) fill = (size_t)snprintf(text, sizeof text, ">%s\n", a->name);
+  for (int64_t i = lft; i <= rgh && rc == 0; i++) {
+    if (i < rgh) {                                  /* f'{depth}\n' */
+      long long v = (long long)a->d[i];
+      char tmp[24];
+      int k = 0, neg = v < 0;
+      unsigned long long u = neg ? 0ull - (unsigned long long)v : (unsigned long long)v;
+      do { tmp[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+      if (neg) text[fill++] = '-';
+      while (k) text[fill++] = tmp[--k];
+      text[fill++] = '\n';
+    }
+    if (fill + 32 > sizeof text || i == rgh) {
+      z.next_in = (unsigned char*)text;
+      z.avail_in = (uInt)fill;
+      const int flush = i == rgh ? Z_FINISH : Z_NO_FLUSH;
+      for (;;) {
+        if (cap - used < 4096) {
+          cap *= 2;
+          unsigned char* grown = (unsigned char*)realloc(out, cap);
+          if (!grown) { rc = -1; break; }
+          out = grown;
+        }
+        z.next_out = out + used;
+        z.avail_out = (uInt)(cap - used > 0x40000000u ? 0x40000000u : cap - used);
+        const uInt before = z.avail_out;
+        const int r = deflate(&z, flush);
+        used += before - z.avail_out;
+        if (r == Z_STREAM_ERROR) { rc = -1; break; }
+        if (flush == Z_FINISH ? r == Z_STREAM_END : z.avail_in == 0) break;
+      }
+      fill = 0;
+    }
+  }
+  deflateEnd(&z);
+  a->buf[part] = out;
+  a->len[part] = (int64_t)used;
+  return rc;
+}
+static void wd_part(int tid, int nt, void* p) {
+  wd_args* a = (wd_args*)p;
+  for (int part = tid; part < a->parts; part += nt)
+    if (wd_one(a, part) != 0) a->err = 1;
+}
+int64_t orc_write_depth(const int64_t* depth, int64_t n, const char* name, int threads, int level, int workers,
+                        unsigned char* out, int64_t out_cap) {
+  if (n <= 0 || threads < 1) return 0;
+  wd_args a;
+  memset(&a, 0, sizeof a);
+  a.d = depth; a.n = n; a.name = name; a.level = level;
+  a.stp = 1 + (n - 1) / threads;
+  a.parts = (int)((n + a.stp - 1) / a.stp);
+  a.buf = (unsigned char**)calloc((size_t)a.parts, sizeof *a.buf);
+  a.len = (int64_t*)calloc((size_t)a.parts, sizeof *a.len);
+  run_parallel(wd_part, &a, workers < a.parts ? workers : a.parts);
+  int64_t total = 0;
+  for (int k = 0; k < a.parts; k++) {
+    if (out && !a.err && total + a.len[k] <= out_cap) memcpy(out + total, a.buf[k], (size_t)a.len[k]);
+    total += a.len[k];
+    free(a.buf[k]);
+  }
+  free(a.buf);
+  free(a.len);
+  return a.err ? -1 : total;
 }
 
 int orc_max_threads(void) {

@@ -74,3 +74,27 @@ def test_c_depth_hash_is_position_sensitive():
         v = ((v ^ (v >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
         return v ^ (v >> 31)
     assert CO.depth_hash(d[:50]) == sum((int(v) + 1) * sm(i) for i, v in enumerate(d[:50])) % 2**64
+
+
+def test_write_depth_port_matches_reference_text_and_member_layout():
+    """orc_write_depth (GCI.py:99-143): `threads` gzip members per contig, ">name" only in the first, one decimal per
+    line; the concatenation inflates to the text the reference writes"""
+    import gzip
+    import zlib
+    rng = np.random.default_rng(7)
+    d = np.repeat(rng.integers(0, 60, 300), rng.integers(1, 900, 300)).astype(np.int64)
+    d[3], d[77], d[-1] = -4, 2**40, 0
+    want = ">chr1 some text\n" + "".join(f"{int(v)}\n" for v in d.tolist())
+    for threads in (1, 4, 7):
+        blob = CO.write_depth(d, "chr1 some text", threads, fetch=True)
+        assert gzip.decompress(blob).decode() == want
+        assert CO.write_depth(d, "chr1 some text", threads) == len(blob)
+        members, rest = 0, blob
+        while rest:
+            o = zlib.decompressobj(31)
+            o.decompress(rest)
+            rest = o.unused_data
+            members += 1
+        stp = 1 + (len(d) - 1) // threads
+        assert members == (len(d) + stp - 1) // stp
+    assert CO.write_depth(np.zeros(0, np.int64), "empty", 4) == 0
