@@ -159,6 +159,23 @@ def deal_bam_over_process_group(tab: AlnTable, plan: ShardPlan) -> AlnTable:
     d_sorted = dst[order]
     rec_counts = np.bincount(d_sorted, minlength=world).astype(np.int64)
     op_counts = np.bincount(d_sorted, weights=n_ops, minlength=world).astype(np.int64)
+    if dist.get_backend() != "nccl":
+        # CPU process groups (tests): every rank gathers everything and keeps what lies on its contigs
+        recs = D.allgather_varlen(mat.reshape(-1))
+        opss = D.allgather_varlen(t.cigar.astype(np.int64))
+        dsts = D.allgather_varlen(d_sorted)
+        rec_parts, op_parts = [], []
+        for r_flat, o_flat, d_of in zip(recs, opss, dsts):
+            r_mat = r_flat.reshape(-1, mat.shape[1])
+            mine = d_of == plan.rank
+            o_off = np.concatenate([[0], np.cumsum(r_mat[:, 7])])
+            rec_parts.append(r_mat[mine])
+            op_parts.extend(o_flat[o_off[i]:o_off[i + 1]] for i in np.flatnonzero(mine))
+        rec = np.concatenate(rec_parts) if rec_parts else np.zeros((0, mat.shape[1]), np.int64)
+        ops = (np.concatenate(op_parts) if op_parts else np.zeros(0, np.int64)).astype(np.uint32)
+        off = np.concatenate([[0], np.cumsum(rec[:, 7])]).astype(np.uint64)
+        got = AlnTable(rec[:, 0], rec[:, 1], rec[:, 2], rec[:, 3], rec[:, 4], rec[:, 5], rec[:, 6], off, ops)
+        return got.take(np.lexsort((got.ref_start, got.ref_id)))
     dev = torch.device("cuda", torch.cuda.current_device())
 
     def a2a(data, counts, width):

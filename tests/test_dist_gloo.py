@@ -35,6 +35,21 @@ WORKER = textwrap.dedent("""
     counts = D.allreduce(np.array([bam.n_records, paf.n_records], np.int64))
     assert counts.tolist() == [w.bam.n_records, w.paf.n_records]
     assert D.allreduce(np.array([rank + 1.5]), "max").tolist() == [2.5]
+    # every rank 'decoded' a part of the files: PAF lines move to the read homes, BAM records to the contig owners
+    cols = ("read_id", "qlen", "qstart", "qend", "ref_id", "tstart", "tend", "nmatch", "alnlen", "mapq")
+    rows = lambda t: sorted(zip(*[np.asarray(getattr(t, c)).astype(np.int64).tolist() for c in cols]))
+    src = sharded.shard_paf_source(w.paf, plan, w.bam)
+    assert 0 < src.n_records < w.paf.n_records
+    assert rows(sharded.deal_paf_over_process_group(src, plan)) == rows(paf)
+    part = w.bam.take(np.arange(rank, w.bam.n_records, 2))             # every other record, any contig
+    dealt = sharded.deal_bam_over_process_group(part, plan)
+    def recs(t):
+        off = t.cigar_off.astype(np.int64)
+        return sorted((int(t.ref_id[i]), int(t.ref_start[i]), int(t.read_id[i]), int(t.mapq[i]), int(t.flag[i]),
+                       int(t.nm[i]), int(t.qlen[i]), t.cigar[off[i]:off[i + 1]].tobytes()) for i in range(t.n_records))
+    assert recs(dealt) == recs(bam)
+    key = dealt.ref_id.astype(np.int64) * 2**32 + dealt.ref_start.astype(np.int64)
+    assert np.all(np.diff(key) >= 0)                                   # coordinate sorted, as the CIGAR kernels expect
     print("rank", rank, "ok")
 """)
 
