@@ -3,21 +3,23 @@
 //
 // Contigs are owned by ranks (depth, scan and score are per contig), but the cross-file join (GCI.py:272-301) is
 // keyed by READ: a read's records may sit on contigs of different owners.  Instead of gathering every table on every
-// rank, every read has a HOME rank (block-cyclic in the read id, home_rank()) and the step moves each piece of data exactly once:
+// rank, every read has a HOME rank (block-cyclic in the read id, home_rank()) and the step moves each piece of data
+// exactly once:
 //
 //   owner of the contig      BAM gates + last-record-wins dedup on the records it holds
-//        |   dispatch 1      every per-file winner row (read, contig, start, end, qlen, high-quality mark) is stored
+//        |   dispatch 1      every per-file winner row (contig, start, end, qlen, high-quality mark) is stored
 //        v                   straight into the inbox of the read's home over NVLink peer memory
-//   home of the read         PAF election for its reads (the host deals PAF lines by read), the join of all files for
-//        |                   its reads (of the rows several owners sent for one read the highest contig wins, :268-270)
+//   home of the read         PAF election for its reads (the host deals PAF lines by read) while the rows travel, then
+//        |                   the join of all files for its reads (of the rows several owners sent for one read the
+//        |                   highest contig wins, :268-270)
 //        |   dispatch 2      every survivor (contig, start, end) is stored into the inbox of the contig's owner
 //        v
 //   owner of the contig      depth events -> depth tiles -> scan -> score, as on one GPU
 //
 // Both dispatches are all-to-all exchanges written as plain kernels over peer pointers (CUDA IPC between processes):
-// the row of a read goes to a fixed slot (source rank, home-local read id) and carries the step's epoch as its
-// validity tag, so nothing is counted, claimed or cleared; every rank then raises an epoch flag in the peers' headers
-// and waits for theirs.  Two receive areas alternate by epoch parity (a rank can be at most one step ahead of a
+// the row of a read goes to a fixed slot (source rank, home-local read id) and the step's epoch, stored beside it,
+// is its validity tag, so nothing is counted, claimed or cleared; every rank then raises an epoch flag in the peers'
+// headers and waits for theirs.  Two receive areas alternate by epoch parity (a rank can be at most one step ahead of a
 // peer), the epoch lives in device memory, so the step replays inside a CUDA graph.
 #include <algorithm>
 
@@ -28,11 +30,12 @@
 struct XRow1 { int32_t contig, start, end; uint32_t qlen_hq; };
 static_assert(sizeof(XRow1) == 16, "winner rows are stored and loaded as int4");
 struct XRow2 { int32_t contig, start, end, pad; };                                // 16 B: a survivor
-// Winner slots are DENSE: the row of home read h (= home_local(read id)) sent by rank `src` lives at [src][h], so a sender
-// needs no slot counter and the receiver no merge pass; a row is valid when its tag (tags1, an array of its own) equals
-// the step's epoch (the areas are never cleared: a stale row carries an older epoch).  Survivor rows are COMPACT per (destination, source): the
-// owner of a contig must not scan world x home-reads slots to find the few that are his, so the home claims slots per
-// destination (one atomic per CTA and destination) and publishes the counts with its flag.
+// Winner slots are DENSE: the row of home read h (= home_local(read id)) sent by rank `src` lives at [src][h], so a
+// sender needs no slot counter and the receiver no merge pass; a row is valid when its tag (tags1, an array of its
+// own) equals the step's epoch (the areas are never cleared: a stale row carries an older epoch).  Survivor rows are
+// COMPACT per (destination, source): the owner of a contig must not scan world x home-reads slots to find the few
+// that are his, so the home claims slots per destination (one atomic per CTA and destination) and publishes the
+// counts with its flag.
 
 // geometry of one rank's exchange area (identical on every rank)
 struct XLayout {
